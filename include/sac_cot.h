@@ -1,0 +1,183 @@
+/*
+ * sac_cot.h — C ABI of the SAC-COT registration hot path.
+ *
+ * Boundary provenance. The reference repository (ytuhzq/SAC-COT) ships no code and no
+ * FFI surface: /root/reference/README.md:1-2 is the whole repo.  The boundary declared
+ * here is therefore the one BASELINE.json `north_star` dictates —
+ *     sac_cot_register(src, dst, N, params, &R, &t, &inliers)
+ * — fleshed out as SURVEY.md §8b describes.  Every entry point below "replaces" the
+ * (absent) reference interface README.md:2 promises ("method code for the paper").
+ *
+ * The same header is implemented twice:
+ *   - sac_cot_b200/lib/libsaccot.so    the B200 product (hand-written sm_100a CUDA, no CPU path)
+ *   - oracle/libsaccot_oracle.so       the from-paper CPU oracle (test infrastructure only)
+ * so one ctypes harness drives both and parity tests read identically for both.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross the ABI; every function returns a status
+ *     (0 = OK, <0 = invalid argument / unsupported, >0 = CUDA runtime failure).
+ *   - points are fp32, row-major N x 3 (x,y,z); correspondence n is (src[n], dst[n]).
+ *   - R is row-major 3x3 with dst ~= R*src + t.
+ *   - the caller owns every in/out buffer; nothing is retained after return.
+ *   - a ctx is single-threaded (one caller at a time); distinct ctxs are independent.
+ *   - "no valid triangle" (graph has no 3-clique among the selected edges) is a *result*:
+ *     status 0, R = I, t = 0, inliers = 0.
+ */
+#ifndef SAC_COT_H_
+#define SAC_COT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SAC_COT_API
+#else
+#define SAC_COT_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------ limits */
+#define SAC_COT_MAX_N            65535   /* node ids and per-edge counts are packed in 16 bit */
+#define SAC_COT_MAX_EDGES        4096    /* K_e  */
+#define SAC_COT_MAX_APEX         8       /* m    */
+#define SAC_COT_MAX_HYPOTHESES   32768   /* K_e*m; hypothesis ids are packed in 16 bit      */
+
+/* ------------------------------------------------------------------ status */
+enum {
+  SAC_COT_OK             = 0,
+  SAC_COT_E_NULL         = -1,  /* a required pointer is NULL                              */
+  SAC_COT_E_SIZE         = -2,  /* N < 3, N > SAC_COT_MAX_N, B < 0                         */
+  SAC_COT_E_PARAMS       = -3,  /* struct_size mismatch or a field out of range            */
+  SAC_COT_E_NODEVICE     = -4,  /* GPU library only: no usable CUDA device / ext. missing  */
+  SAC_COT_E_UNSUPPORTED  = -5,  /* entry point not provided by this implementation         */
+  SAC_COT_E_WHICH        = -6,  /* debug_get: unknown selector or pair index               */
+  SAC_COT_E_CAPACITY     = -7,  /* debug_get: caller buffer too small (written = needed)   */
+  SAC_COT_E_NOMEM        = -8   /* workspace could not be allocated                        */
+  /* > 0 : cudaError_t of the failing CUDA call (GPU library only)                          */
+};
+
+/* ------------------------------------------------------------------ params */
+enum { SAC_COT_SCORE_INLIER_COUNT = 0, SAC_COT_SCORE_TRUNCATED_RESIDUAL = 1 };
+
+typedef struct sac_cot_params {
+  uint32_t struct_size;    /* = sizeof(sac_cot_params); ABI version check                    */
+  float    tau_compat;     /* tau_c : |len_src - len_dst| < tau_c  => compatible  (S1)        */
+  float    tau_inlier;     /* tau_in: |R s + t - d|^2 < tau_in^2   => inlier      (S5)        */
+  int32_t  num_edges;      /* K_e   : top-ranked edges used as triangle bases     (S3)        */
+  int32_t  apex_per_edge;  /* m     : apexes per edge; K = K_e*m hypotheses       (S3)        */
+  int32_t  score_mode;     /* SAC_COT_SCORE_*                                     (S5)        */
+  int32_t  refit;          /* 1: fp64 Kabsch over the winner's inliers (S7); 0: return winner */
+  int32_t  reserved;       /* must be 0                                                       */
+} sac_cot_params;
+
+/* Fills *p with the defaults (tau 0.1/0.1, K_e 1024, m 4, inlier count, refit on). */
+SAC_COT_API int sac_cot_params_default(sac_cot_params* p);
+
+/* ------------------------------------------------------------------ one pair */
+/* Uses a lazily created process-global ctx (GPU library: device 0, its own stream). */
+SAC_COT_API int sac_cot_register(const float* src, const float* dst, int32_t N,
+                                 const sac_cot_params* params,
+                                 float R[9], float t[3], int32_t* inliers);
+
+/* ------------------------------------------------------------------ contexts */
+typedef struct sac_cot_ctx sac_cot_ctx;
+
+/* device: CUDA ordinal (ignored by the oracle).  stream: a cudaStream_t on that device on
+ * which every kernel and copy of this ctx is enqueued, or NULL for a private stream.
+ * Passing the caller's stream lets the caller bracket the work with its own events. */
+SAC_COT_API int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream);
+SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
+
+/* Tunables/inspection by name; unknown names return SAC_COT_E_WHICH.
+ *   set: "keep_debug" (0/1: retain per-pair intermediates for sac_cot_debug_get; forces
+ *        chunk = whole batch), "chunk_pairs" (pairs per kernel wave, 0 = auto),
+ *        "triangle_path" (0 = POPC bitset, 1 = tensor-core dense; GPU only)
+ *   get: "launches" (kernels launched since ctx creation), "workspace_bytes",
+ *        "device", "sm_count", "retries" (workspace-growth re-runs)                       */
+SAC_COT_API int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value);
+SAC_COT_API int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value);
+
+/* ------------------------------------------------------------------ batches */
+/* B independent pairs, host pointer arrays (SURVEY.md §8b signature).  Outputs: R[B*9],
+ * t[B*3], inliers[B] (host). */
+SAC_COT_API int sac_cot_register_batch(sac_cot_ctx* ctx,
+                                       const float* const* src, const float* const* dst,
+                                       const int32_t* N, int32_t B,
+                                       const sac_cot_params* params,
+                                       float* R, float* t, int32_t* inliers);
+
+/* B independent pairs packed back to back: pair b owns points [offsets[b], offsets[b+1])
+ * of src/dst (each total x 3 floats).  `offsets` (B+1 entries) is always a host array.
+ * location = SAC_COT_LOC_HOST: src/dst/R/t/inliers are host buffers (pinned or pageable);
+ * the H2D and D2H copies are part of the call.
+ * location = SAC_COT_LOC_DEVICE (GPU library only): they are device buffers on the ctx
+ * device; the call only enqueues work on the ctx stream and returns without
+ * synchronising (status reflects enqueue errors; results are ready when the stream is). */
+enum { SAC_COT_LOC_HOST = 0, SAC_COT_LOC_DEVICE = 1 };
+SAC_COT_API int sac_cot_register_packed(sac_cot_ctx* ctx,
+                                        const float* src, const float* dst,
+                                        const int64_t* offsets, int32_t B,
+                                        const sac_cot_params* params,
+                                        float* R, float* t, int32_t* inliers,
+                                        int32_t location);
+
+/* ------------------------------------------------------------------ one large pair, sharded */
+/* A single pair whose triangle-count work units and hypothesis ranges are split over
+ * `world` ranks (one process per GPU).  The library never communicates: the host layer
+ * above it performs exactly two exchanges between the three phases:
+ *
+ *   phase 1  graph (full, local) + triangle counts for this rank's work units
+ *            -> t_partial[N] (u64, sum of T_ij over this rank's edges incident to node i;
+ *               summed over ranks it equals 2*t_i)
+ *            -> cand[K_e] (u64 edge keys, this rank's top-K_e, descending, 0-padded)
+ *   exchange #1: all-gather t_partial and cand over ranks
+ *   phase 2  merge (sum of t_partial; top-K_e of the gathered candidates), apexes, Kabsch,
+ *            score this rank's hypothesis range -> best_key (u64, 0 = none)
+ *   exchange #2: all-reduce(max) of best_key
+ *   phase 3  inlier mask + refit of the global winner (every rank computes the same result)
+ *
+ * All buffers are host arrays; t_all is world x N, cand_all is world x K_e.            */
+SAC_COT_API int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
+                                       int32_t N, const sac_cot_params* params,
+                                       int32_t rank, int32_t world,
+                                       uint64_t* t_partial, uint64_t* cand);
+SAC_COT_API int sac_cot_sharded_phase2(sac_cot_ctx* ctx, const uint64_t* t_all,
+                                       const uint64_t* cand_all, uint64_t* best_key);
+SAC_COT_API int sac_cot_sharded_phase3(sac_cot_ctx* ctx, uint64_t best_key_global,
+                                       float R[9], float t[3], int32_t* inliers);
+
+/* ------------------------------------------------------------------ parity/debug access */
+/* Intermediates of pair `pair` of the most recent call on ctx (requires keep_debug = 1).
+ * Copies into `out` (host) and reports the byte count in *written.                      */
+enum {
+  SAC_COT_DBG_ADJ        = 0, /* u32[N][stride_words]: bit j&31 of word j>>5 of row i = A_ij;
+                                 stride_words = ceil(N/128)*4; pad bits 0                    */
+  SAC_COT_DBG_T_NODE     = 1, /* u32[N]  t_i  = #triangles through node i                    */
+  SAC_COT_DBG_NUM_EDGES  = 2, /* u64     E    = #undirected edges                            */
+  SAC_COT_DBG_EDGE_KEYS  = 3, /* u64[E]  all edge keys, ORDER UNSPECIFIED (sort to compare)   */
+  SAC_COT_DBG_TOP_EDGES  = 4, /* u64[K_e'] selected edge keys, descending; K_e'=min(K_e,E)   */
+  SAC_COT_DBG_TRIANGLES  = 5, /* i32[K][3] (i,j,k) per hypothesis id, -1,-1,-1 if invalid    */
+  SAC_COT_DBG_HYP_RT     = 6, /* f32[K][12] R (9, row-major) then t (3); zeros if invalid    */
+  SAC_COT_DBG_HYP_SCORE  = 7, /* u64[K]  packed selection key per hypothesis (0 = invalid)   */
+  SAC_COT_DBG_BEST_KEY   = 8, /* u64     max of HYP_SCORE                                    */
+  SAC_COT_DBG_MASK       = 9, /* u32[ceil(N/32)] inlier bits of the winning hypothesis       */
+  SAC_COT_DBG_HIST       = 10 /* u32[4096] histogram of (T_ij >> 4) over all edges           */
+};
+SAC_COT_API int sac_cot_debug_get(sac_cot_ctx* ctx, int32_t pair, int32_t which,
+                                  void* out, size_t cap, size_t* written);
+
+/* Edge key layout (u64):  T_ij << 32 | (0xFFFF - i) << 16 | (0xFFFF - j),  i < j.
+ *   larger key = better edge: more triangles first, then smaller i, then smaller j.
+ * Hypothesis key layout (u64):  score << 16 | (0xFFFF - h).
+ *   mode 0: score = inlier_count + 1;  mode 1: score = N*2^20 - sum_fixed + 1;  0 = invalid. */
+
+SAC_COT_API const char* sac_cot_strerror(int status);
+SAC_COT_API const char* sac_cot_version(void); /* "sac-cot-b200 <ver> (cuda sm_100a)" / "... (oracle)" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAC_COT_H_ */
