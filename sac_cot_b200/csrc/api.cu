@@ -1,0 +1,747 @@
+// api.cu — host library behind the C ABI of include/sac_cot.h: contexts, workspace planning,
+// the chunked kernel pipeline, key-pool growth/retry, the three sharded phases and the parity
+// getter.  CUDA only: there is no CPU path; without a usable device every entry point fails
+// with SAC_COT_E_NODEVICE or the cudaError_t.
+//
+// The reference ships no host layer to follow (/root/reference/README.md:1-2 is the repo); the
+// contract implemented here is SURVEY.md §8b.
+#include "../../include/sac_cot.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+using namespace saccot;
+
+namespace {
+
+#define CU_TRY(expr)                                    \
+  do {                                                  \
+    const cudaError_t e__ = (expr);                     \
+    if (e__ != cudaSuccess) return static_cast<int>(e__); \
+  } while (0)
+
+#define KL_TRY(expr)                 \
+  do {                               \
+    const int n__ = (expr);          \
+    if (n__ < 0) return -n__;        \
+    ctx->launches += n__;            \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Sub-buffers of the arena for one chunk of pairs.
+struct Layout {
+  int pairs = 0;
+  int max_n = 0, max_npad = 0, max_nblk = 0, max_stride = 0;
+  size_t sum_n = 0, sum_npad = 0;
+  int Ke = 0, m = 0, K = 0;
+  // zero region (one memset): state | chunk | hist | t2
+  PairDev* state = nullptr;
+  ChunkDev* chunk = nullptr;
+  uint32_t* hist = nullptr;
+  unsigned long long* t2 = nullptr;
+  size_t zero_bytes = 0;
+  // the rest
+  PairDesc* desc = nullptr;
+  float* in_src = nullptr;
+  float* in_dst = nullptr;
+  float* soa = nullptr;
+  uint32_t* adj = nullptr;
+  unsigned long long* sel = nullptr;
+  unsigned long long* tie = nullptr;
+  unsigned long long* top = nullptr;
+  int32_t* tri = nullptr;
+  float* rt = nullptr;
+  unsigned long long* hyp_key = nullptr;
+  uint32_t* mask = nullptr;
+  float* outR = nullptr;
+  float* outT = nullptr;
+  int32_t* outInl = nullptr;
+  unsigned long long* best_override = nullptr;
+  size_t total_bytes = 0;
+  unsigned long long key_guess = 0;  // initial key-pool demand estimate
+};
+
+unsigned long long key_guess_for(int N) {
+  const unsigned long long P = static_cast<unsigned long long>(N) * (N - 1) / 2;
+  unsigned long long g = P / 8;  // 12.5 % edge density; grows on demand
+  if (g < 4096) g = 4096;
+  return g < P ? g : P;
+}
+
+size_t pair_bytes_estimate(int N, int K, int Ke) {
+  const size_t npad = align_up(static_cast<size_t>(N), 128);
+  return npad * (npad / 32) * 4 + key_guess_for(N) * 8 + npad * (6 * 4 + 8 + 24) + static_cast<size_t>(K) * (12 + 48 + 8) +
+         static_cast<size_t>(Ke) * 16 + static_cast<size_t>(kTieCap) * 8 + kHistBins * 4 + 4096;
+}
+
+}  // namespace
+
+struct sac_cot_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  bool keep_debug = false;
+  int chunk_pairs = 0;
+  int64_t launches = 0;
+  int64_t retries = 0;
+  int deferred_status = 0;  // device-location calls: status discovered after the fact
+
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  unsigned long long* keys = nullptr;
+  unsigned long long key_cap = 0;
+  ChunkDev* h_chunk = nullptr;  // pinned read-back of the chunk header
+  cudaEvent_t chunk_event = nullptr;
+  bool chunk_event_pending = false;
+
+  // description of what is resident in the workspace (for debug_get / sharded phases)
+  Layout lay;
+  std::vector<PairDesc> descs;
+  sac_cot_params prm{};
+  bool ws_valid = false;
+  // sharded call in flight
+  int sh_rank = 0, sh_world = 1, sh_N = 0;
+  bool sh_valid = false;
+
+  // host staging for the pointer-array batch entry point
+  std::vector<float> stage_src, stage_dst;
+};
+
+namespace {
+
+int check_params(const sac_cot_params* p) {
+  if (!p) return SAC_COT_E_NULL;
+  if (p->struct_size != sizeof(sac_cot_params)) return SAC_COT_E_PARAMS;
+  if (!(p->tau_compat > 0.0f) || !(p->tau_inlier > 0.0f)) return SAC_COT_E_PARAMS;
+  if (p->num_edges < 1 || p->num_edges > SAC_COT_MAX_EDGES) return SAC_COT_E_PARAMS;
+  if (p->apex_per_edge < 1 || p->apex_per_edge > SAC_COT_MAX_APEX) return SAC_COT_E_PARAMS;
+  if (p->num_edges * p->apex_per_edge > SAC_COT_MAX_HYPOTHESES) return SAC_COT_E_PARAMS;
+  if (p->score_mode != 0 && p->score_mode != 1) return SAC_COT_E_PARAMS;
+  if (p->refit != 0 && p->refit != 1) return SAC_COT_E_PARAMS;
+  if (p->reserved != 0) return SAC_COT_E_PARAMS;
+  return SAC_COT_OK;
+}
+
+// Builds the descriptors and the arena layout for pairs with the given sizes.
+void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_input_copy, std::vector<PairDesc>& descs,
+          Layout& L) {
+  L = Layout();
+  L.pairs = pairs;
+  L.Ke = prm.num_edges;
+  L.m = prm.apex_per_edge;
+  L.K = L.Ke * L.m;
+  descs.resize(pairs);
+  size_t pt = 0, soa = 0, adj = 0, node = 0, mask = 0;
+  for (int b = 0; b < pairs; ++b) {
+    PairDesc& d = descs[b];
+    d.N = Ns[b];
+    d.Npad = static_cast<int32_t>(align_up(static_cast<size_t>(Ns[b]), 128));
+    d.stride = d.Npad / 32;
+    d.nblk = d.Npad / 128;
+    d.pt_off = static_cast<int64_t>(pt);
+    d.soa_off = static_cast<int64_t>(soa);
+    d.adj_off = static_cast<int64_t>(adj);
+    d.node_off = static_cast<int64_t>(node);
+    d.mask_off = static_cast<int64_t>(mask);
+    pt += d.N;
+    soa += static_cast<size_t>(6) * d.Npad;
+    adj += static_cast<size_t>(d.Npad) * d.stride;
+    node += d.Npad;
+    mask += d.Npad / 32;
+    L.max_n = std::max(L.max_n, d.N);
+    L.max_npad = std::max(L.max_npad, d.Npad);
+    L.max_nblk = std::max(L.max_nblk, d.nblk);
+    L.max_stride = std::max(L.max_stride, d.stride);
+    L.key_guess += key_guess_for(d.N);
+  }
+  L.sum_n = pt;
+  L.sum_npad = node;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  // zero region first
+  const size_t o_state = take(sizeof(PairDev) * pairs);
+  const size_t o_chunk = take(sizeof(ChunkDev));
+  const size_t o_hist = take(sizeof(uint32_t) * kHistBins * pairs);
+  const size_t o_t2 = take(sizeof(unsigned long long) * node);
+  L.zero_bytes = off;
+  const size_t o_desc = take(sizeof(PairDesc) * pairs);
+  const size_t o_insrc = need_input_copy ? take(sizeof(float) * 3 * pt) : 0;
+  const size_t o_indst = need_input_copy ? take(sizeof(float) * 3 * pt) : 0;
+  const size_t o_soa = take(sizeof(float) * soa);
+  const size_t o_adj = take(sizeof(uint32_t) * adj);
+  const size_t o_sel = take(sizeof(unsigned long long) * L.Ke * pairs);
+  const size_t o_tie = take(sizeof(unsigned long long) * kTieCap * pairs);
+  const size_t o_top = take(sizeof(unsigned long long) * L.Ke * pairs);
+  const size_t o_tri = take(sizeof(int32_t) * 3 * L.K * pairs);
+  const size_t o_rt = take(sizeof(float) * 12 * L.K * pairs);
+  const size_t o_hk = take(sizeof(unsigned long long) * L.K * pairs);
+  const size_t o_mask = take(sizeof(uint32_t) * mask);
+  const size_t o_R = take(sizeof(float) * 9 * pairs);
+  const size_t o_T = take(sizeof(float) * 3 * pairs);
+  const size_t o_inl = take(sizeof(int32_t) * pairs);
+  const size_t o_bo = take(sizeof(unsigned long long));
+  L.total_bytes = off;
+  // stash offsets as pointers relative to nullptr; bind() adds the arena base
+  L.state = reinterpret_cast<PairDev*>(o_state);
+  L.chunk = reinterpret_cast<ChunkDev*>(o_chunk);
+  L.hist = reinterpret_cast<uint32_t*>(o_hist);
+  L.t2 = reinterpret_cast<unsigned long long*>(o_t2);
+  L.desc = reinterpret_cast<PairDesc*>(o_desc);
+  L.in_src = need_input_copy ? reinterpret_cast<float*>(o_insrc) : nullptr;
+  L.in_dst = need_input_copy ? reinterpret_cast<float*>(o_indst) : nullptr;
+  L.soa = reinterpret_cast<float*>(o_soa);
+  L.adj = reinterpret_cast<uint32_t*>(o_adj);
+  L.sel = reinterpret_cast<unsigned long long*>(o_sel);
+  L.tie = reinterpret_cast<unsigned long long*>(o_tie);
+  L.top = reinterpret_cast<unsigned long long*>(o_top);
+  L.tri = reinterpret_cast<int32_t*>(o_tri);
+  L.rt = reinterpret_cast<float*>(o_rt);
+  L.hyp_key = reinterpret_cast<unsigned long long*>(o_hk);
+  L.mask = reinterpret_cast<uint32_t*>(o_mask);
+  L.outR = reinterpret_cast<float*>(o_R);
+  L.outT = reinterpret_cast<float*>(o_T);
+  L.outInl = reinterpret_cast<int32_t*>(o_inl);
+  L.best_override = reinterpret_cast<unsigned long long*>(o_bo);
+}
+
+template <typename T>
+inline T* rebase(T* rel, unsigned char* base, bool present = true) {
+  return present ? reinterpret_cast<T*>(base + reinterpret_cast<size_t>(rel)) : nullptr;
+}
+
+void bind(Layout& L, unsigned char* base, bool has_input) {
+  L.state = rebase(L.state, base);
+  L.chunk = rebase(L.chunk, base);
+  L.hist = rebase(L.hist, base);
+  L.t2 = rebase(L.t2, base);
+  L.desc = rebase(L.desc, base);
+  L.in_src = rebase(L.in_src, base, has_input);
+  L.in_dst = rebase(L.in_dst, base, has_input);
+  L.soa = rebase(L.soa, base);
+  L.adj = rebase(L.adj, base);
+  L.sel = rebase(L.sel, base);
+  L.tie = rebase(L.tie, base);
+  L.top = rebase(L.top, base);
+  L.tri = rebase(L.tri, base);
+  L.rt = rebase(L.rt, base);
+  L.hyp_key = rebase(L.hyp_key, base);
+  L.mask = rebase(L.mask, base);
+  L.outR = rebase(L.outR, base);
+  L.outT = rebase(L.outT, base);
+  L.outInl = rebase(L.outInl, base);
+  L.best_override = rebase(L.best_override, base);
+}
+
+int ensure_arena(sac_cot_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->arena_bytes) return 0;
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->arena) CU_TRY(cudaFree(ctx->arena));
+  ctx->arena = nullptr;
+  ctx->arena_bytes = 0;
+  const size_t want = align_up(bytes + bytes / 8, 1 << 20);
+  cudaError_t e = cudaMalloc(&ctx->arena, want);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    e = cudaMalloc(&ctx->arena, bytes);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return SAC_COT_E_NOMEM;
+    }
+    ctx->arena_bytes = bytes;
+  } else {
+    ctx->arena_bytes = want;
+  }
+  ctx->ws_valid = false;
+  ctx->sh_valid = false;
+  return 0;
+}
+
+int ensure_keys(sac_cot_ctx* ctx, unsigned long long cap) {
+  if (cap <= ctx->key_cap) return 0;
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->keys) CU_TRY(cudaFree(ctx->keys));
+  ctx->keys = nullptr;
+  ctx->key_cap = 0;
+  if (cudaMalloc(&ctx->keys, cap * sizeof(unsigned long long)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return SAC_COT_E_NOMEM;
+  }
+  ctx->key_cap = cap;
+  return 0;
+}
+
+// Resolves the status of an earlier device-location call (key-pool overflow is only known
+// once its chunk header has been copied back).
+int resolve_pending(sac_cot_ctx* ctx) {
+  if (!ctx->chunk_event_pending) return 0;
+  CU_TRY(cudaEventSynchronize(ctx->chunk_event));
+  ctx->chunk_event_pending = false;
+  if (ctx->h_chunk->overflow) {
+    ctx->deferred_status = SAC_COT_E_NOMEM;
+    const unsigned long long want = ctx->h_chunk->total_edges + ctx->h_chunk->total_edges / 8 + 1024;
+    ++ctx->retries;
+    const int rc = ensure_keys(ctx, want);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// Enqueues the whole pipeline for the pairs described by ctx->descs / ctx->lay.
+//   d_src/d_dst : device AoS inputs for this chunk (pt_off relative to them)
+//   dR/dT/dInl  : device outputs for this chunk
+int enqueue_pipeline(sac_cot_ctx* ctx, const float* d_src, const float* d_dst, float* dR, float* dT, int32_t* dInl,
+                     int rank, int world, bool stop_after_edges) {
+  Layout& L = ctx->lay;
+  const sac_cot_params& prm = ctx->prm;
+  LaunchCtx lc{ctx->stream, ctx->sm_count};
+  CU_TRY(cudaMemsetAsync(L.state, 0, L.zero_bytes, ctx->stream));
+  KL_TRY(launch_pack_soa(lc, L.desc, L.pairs, L.max_npad, d_src, d_dst, L.soa));
+  KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.state, prm.tau_compat));
+  KL_TRY(launch_key_scan(lc, L.pairs, L.state, L.chunk, ctx->key_cap));
+  KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ctx->keys, L.hist,
+                          L.t2, rank, world));
+  KL_TRY(launch_select_edges(lc, L.pairs, L.state, L.chunk, ctx->keys, L.hist, L.sel, L.tie, L.top, L.Ke));
+  if (stop_after_edges) return 0;
+  const float tau2 = prm.tau_inlier * prm.tau_inlier;
+  KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
+  KL_TRY(launch_kabsch(lc, L.desc, L.pairs, L.soa, L.tri, L.rt, L.K));
+  KL_TRY(launch_score(lc, L.desc, L.pairs, L.max_n, L.soa, L.tri, L.rt, L.hyp_key, L.state, tau2, L.K, 0, L.K,
+                      prm.score_mode));
+  KL_TRY(launch_finalize(lc, L.desc, L.pairs, L.soa, L.rt, L.state, nullptr, L.mask, dR, dT, dInl, tau2, L.K,
+                         prm.refit));
+  return 0;
+}
+
+// One chunk, host or device location.  offsets are absolute (whole call); [b0,b1) is the chunk.
+int run_chunk(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_t* offsets, int b0, int b1,
+              const sac_cot_params& prm, float* R, float* t, int32_t* inliers, int location) {
+  const int pairs = b1 - b0;
+  std::vector<int32_t> Ns(pairs);
+  for (int b = 0; b < pairs; ++b) Ns[b] = static_cast<int32_t>(offsets[b0 + b + 1] - offsets[b0 + b]);
+  const bool host = location == SAC_COT_LOC_HOST;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    plan(Ns.data(), pairs, prm, host, ctx->descs, ctx->lay);
+    if (int rc = ensure_arena(ctx, ctx->lay.total_bytes)) return rc;
+    if (int rc = ensure_keys(ctx, ctx->lay.key_guess)) return rc;
+    bind(ctx->lay, ctx->arena, host);
+    ctx->prm = prm;
+    ctx->ws_valid = false;
+    ctx->sh_valid = false;
+    Layout& L = ctx->lay;
+    CU_TRY(cudaMemcpyAsync(L.desc, ctx->descs.data(), sizeof(PairDesc) * pairs, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t p0 = offsets[b0];
+    const float* d_src;
+    const float* d_dst;
+    float *dR, *dT;
+    int32_t* dInl;
+    if (host) {
+      CU_TRY(cudaMemcpyAsync(L.in_src, src + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ctx->stream));
+      CU_TRY(cudaMemcpyAsync(L.in_dst, dst + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ctx->stream));
+      d_src = L.in_src; d_dst = L.in_dst;
+      dR = L.outR; dT = L.outT; dInl = L.outInl;
+    } else {
+      d_src = src + 3 * p0; d_dst = dst + 3 * p0;
+      dR = R + 9 * static_cast<size_t>(b0); dT = t + 3 * static_cast<size_t>(b0); dInl = inliers + b0;
+    }
+    if (int rc = enqueue_pipeline(ctx, d_src, d_dst, dR, dT, dInl, 0, 1, false)) return rc;
+    CU_TRY(cudaMemcpyAsync(ctx->h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!host) {
+      CU_TRY(cudaEventRecord(ctx->chunk_event, ctx->stream));
+      ctx->chunk_event_pending = true;
+      ctx->ws_valid = true;
+      return 0;  // enqueue only; overflow (if any) surfaces through resolve_pending()
+    }
+    CU_TRY(cudaMemcpyAsync(R + 9 * static_cast<size_t>(b0), L.outR, sizeof(float) * 9 * pairs, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CU_TRY(cudaMemcpyAsync(t + 3 * static_cast<size_t>(b0), L.outT, sizeof(float) * 3 * pairs, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CU_TRY(cudaMemcpyAsync(inliers + b0, L.outInl, sizeof(int32_t) * pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->h_chunk->overflow) {
+      ctx->ws_valid = true;
+      return 0;
+    }
+    // key pool too small for this chunk's edge count: grow to the measured demand and re-run
+    ++ctx->retries;
+    const unsigned long long want = ctx->h_chunk->total_edges + ctx->h_chunk->total_edges / 16 + 1024;
+    if (int rc = ensure_keys(ctx, want)) return rc;
+    // ensure_keys(key_guess) in the next attempt is a no-op because key_cap only grows
+  }
+  return SAC_COT_E_NOMEM;
+}
+
+int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_t* offsets, int32_t B,
+               const sac_cot_params* params, float* R, float* t, int32_t* inliers, int32_t location) {
+  if (!ctx || !offsets) return SAC_COT_E_NULL;
+  if (location != SAC_COT_LOC_HOST && location != SAC_COT_LOC_DEVICE) return SAC_COT_E_UNSUPPORTED;
+  if (B < 0) return SAC_COT_E_SIZE;
+  if (int rc = check_params(params)) return rc;
+  if (B > 0 && (!src || !dst || !R || !t || !inliers)) return SAC_COT_E_NULL;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = offsets[b + 1] - offsets[b];
+    if (n < 3 || n > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
+  }
+  if (B == 0) return SAC_COT_OK;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (int rc = resolve_pending(ctx)) return rc;
+  // chunking: bounded workspace per wave of kernels (keep_debug keeps the whole batch resident)
+  const int K = params->num_edges * params->apex_per_edge;
+  int chunk = B;
+  if (!ctx->keep_debug) {
+    if (ctx->chunk_pairs > 0) {
+      chunk = std::min(B, ctx->chunk_pairs);
+    } else {
+      size_t total = 0;
+      for (int b = 0; b < B; ++b)
+        total += pair_bytes_estimate(static_cast<int>(offsets[b + 1] - offsets[b]), K, params->num_edges);
+      const size_t budget = static_cast<size_t>(3) << 30;
+      const int nchunks = static_cast<int>((total + budget - 1) / budget);
+      chunk = (B + nchunks - 1) / std::max(1, nchunks);
+    }
+  }
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int b1 = std::min(B, b0 + chunk);
+    if (int rc = run_chunk(ctx, src, dst, offsets, b0, b1, *params, R, t, inliers, location)) return rc;
+  }
+  return SAC_COT_OK;
+}
+
+std::mutex g_mutex;
+sac_cot_ctx* g_ctx = nullptr;
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int sac_cot_params_default(sac_cot_params* p) {
+  if (!p) return SAC_COT_E_NULL;
+  p->struct_size = sizeof(sac_cot_params);
+  p->tau_compat = 0.1f;
+  p->tau_inlier = 0.1f;
+  p->num_edges = 1024;
+  p->apex_per_edge = 4;
+  p->score_mode = SAC_COT_SCORE_INLIER_COUNT;
+  p->refit = 1;
+  p->reserved = 0;
+  return SAC_COT_OK;
+}
+
+int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
+  if (!out) return SAC_COT_E_NULL;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    (void)cudaGetLastError();
+    return SAC_COT_E_NODEVICE;
+  }
+  if (device < 0 || device >= count) return SAC_COT_E_NODEVICE;
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return SAC_COT_E_NODEVICE;  // built for sm_100a only
+  sac_cot_ctx* ctx = new (std::nothrow) sac_cot_ctx();
+  if (!ctx) return SAC_COT_E_NOMEM;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (stream) {
+    ctx->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return static_cast<int>(e); }
+    ctx->own_stream = true;
+  }
+  cudaError_t e = cudaMallocHost(&ctx->h_chunk, sizeof(ChunkDev));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->chunk_event, cudaEventDisableTiming);
+  if (e != cudaSuccess) { sac_cot_ctx_destroy(ctx); return static_cast<int>(e); }
+  std::memset(ctx->h_chunk, 0, sizeof(ChunkDev));
+  const int rc = triangles_configure();
+  if (rc < 0) { sac_cot_ctx_destroy(ctx); return -rc; }
+  *out = ctx;
+  return SAC_COT_OK;
+}
+
+int sac_cot_ctx_destroy(sac_cot_ctx* ctx) {
+  if (!ctx) return SAC_COT_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->keys) cudaFree(ctx->keys);
+  if (ctx->h_chunk) cudaFreeHost(ctx->h_chunk);
+  if (ctx->chunk_event) cudaEventDestroy(ctx->chunk_event);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SAC_COT_OK;
+}
+
+int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return SAC_COT_E_NULL;
+  if (!std::strcmp(name, "keep_debug")) { ctx->keep_debug = value != 0; return SAC_COT_OK; }
+  if (!std::strcmp(name, "chunk_pairs")) {
+    if (value < 0) return SAC_COT_E_SIZE;
+    ctx->chunk_pairs = static_cast<int>(std::min<int64_t>(value, 65535));
+    return SAC_COT_OK;
+  }
+  if (!std::strcmp(name, "triangle_path")) return value == 0 ? SAC_COT_OK : SAC_COT_E_UNSUPPORTED;
+  return SAC_COT_E_WHICH;
+}
+
+int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
+  if (!ctx || !name || !value) return SAC_COT_E_NULL;
+  if (!std::strcmp(name, "launches")) { *value = ctx->launches; return SAC_COT_OK; }
+  if (!std::strcmp(name, "workspace_bytes")) {
+    *value = static_cast<int64_t>(ctx->arena_bytes + ctx->key_cap * sizeof(unsigned long long));
+    return SAC_COT_OK;
+  }
+  if (!std::strcmp(name, "retries")) { *value = ctx->retries; return SAC_COT_OK; }
+  if (!std::strcmp(name, "device")) { *value = ctx->device; return SAC_COT_OK; }
+  if (!std::strcmp(name, "sm_count")) { *value = ctx->sm_count; return SAC_COT_OK; }
+  if (!std::strcmp(name, "threads")) { *value = 0; return SAC_COT_OK; }
+  if (!std::strcmp(name, "last_status")) {
+    // status of the most recent device-location call; synchronises with it
+    cudaSetDevice(ctx->device);
+    const int rc = resolve_pending(ctx);
+    *value = rc ? rc : ctx->deferred_status;
+    ctx->deferred_status = 0;
+    return SAC_COT_OK;
+  }
+  return SAC_COT_E_WHICH;
+}
+
+int sac_cot_register_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_t* offsets, int32_t B,
+                            const sac_cot_params* params, float* R, float* t, int32_t* inliers, int32_t location) {
+  try {
+    return run_packed(ctx, src, dst, offsets, B, params, R, t, inliers, location);
+  } catch (const std::bad_alloc&) {
+    return SAC_COT_E_NOMEM;
+  }
+}
+
+int sac_cot_register_batch(sac_cot_ctx* ctx, const float* const* src, const float* const* dst, const int32_t* N,
+                           int32_t B, const sac_cot_params* params, float* R, float* t, int32_t* inliers) {
+  if (!ctx) return SAC_COT_E_NULL;
+  if (B < 0) return SAC_COT_E_SIZE;
+  if (int rc = check_params(params)) return rc;
+  if (B > 0 && (!src || !dst || !N || !R || !t || !inliers)) return SAC_COT_E_NULL;
+  try {
+    std::vector<int64_t> offsets(static_cast<size_t>(B) + 1, 0);
+    for (int b = 0; b < B; ++b) {
+      if (!src[b] || !dst[b]) return SAC_COT_E_NULL;
+      if (N[b] < 3 || N[b] > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
+      offsets[b + 1] = offsets[b] + N[b];
+    }
+    ctx->stage_src.resize(static_cast<size_t>(offsets[B]) * 3);
+    ctx->stage_dst.resize(static_cast<size_t>(offsets[B]) * 3);
+    for (int b = 0; b < B; ++b) {
+      std::memcpy(&ctx->stage_src[static_cast<size_t>(offsets[b]) * 3], src[b], sizeof(float) * 3 * N[b]);
+      std::memcpy(&ctx->stage_dst[static_cast<size_t>(offsets[b]) * 3], dst[b], sizeof(float) * 3 * N[b]);
+    }
+    return run_packed(ctx, ctx->stage_src.data(), ctx->stage_dst.data(), offsets.data(), B, params, R, t, inliers,
+                      SAC_COT_LOC_HOST);
+  } catch (const std::bad_alloc&) {
+    return SAC_COT_E_NOMEM;
+  }
+}
+
+int sac_cot_register(const float* src, const float* dst, int32_t N, const sac_cot_params* params, float R[9],
+                     float t[3], int32_t* inliers) {
+  if (!src || !dst || !R || !t || !inliers) return SAC_COT_E_NULL;
+  if (N < 3 || N > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
+  if (int rc = check_params(params)) return rc;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (!g_ctx) {
+    const int rc = sac_cot_ctx_create(&g_ctx, 0, nullptr);
+    if (rc) return rc;
+  }
+  const int64_t offsets[2] = {0, N};
+  return sac_cot_register_packed(g_ctx, src, dst, offsets, 1, params, R, t, inliers, SAC_COT_LOC_HOST);
+}
+
+// ---- sharded single pair ------------------------------------------------------------------
+int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst, int32_t N,
+                           const sac_cot_params* params, int32_t rank, int32_t world, uint64_t* t_partial,
+                           uint64_t* cand) {
+  if (!ctx || !src || !dst || !t_partial || !cand) return SAC_COT_E_NULL;
+  if (N < 3 || N > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
+  if (world < 1 || rank < 0 || rank >= world) return SAC_COT_E_SIZE;
+  if (int rc = check_params(params)) return rc;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (int rc = resolve_pending(ctx)) return rc;
+  ctx->sh_valid = false;
+  try {
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      plan(&N, 1, *params, true, ctx->descs, ctx->lay);
+      if (int rc = ensure_arena(ctx, ctx->lay.total_bytes)) return rc;
+      // a rank evaluates ~1/world of the edges; the scan checks the full E against the pool,
+      // so size for the whole pair (N = 50000 at 7.6 % density: 0.75 GB)
+      if (int rc = ensure_keys(ctx, ctx->lay.key_guess)) return rc;
+      bind(ctx->lay, ctx->arena, true);
+      ctx->prm = *params;
+      ctx->ws_valid = false;
+      Layout& L = ctx->lay;
+      CU_TRY(cudaMemcpyAsync(L.desc, ctx->descs.data(), sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
+      CU_TRY(cudaMemcpyAsync(L.in_src, src, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
+      CU_TRY(cudaMemcpyAsync(L.in_dst, dst, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
+      if (int rc = enqueue_pipeline(ctx, L.in_src, L.in_dst, nullptr, nullptr, nullptr, rank, world, true)) return rc;
+      CU_TRY(cudaMemcpyAsync(ctx->h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(cudaMemcpyAsync(t_partial, L.t2, sizeof(uint64_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(cudaMemcpyAsync(cand, L.top, sizeof(uint64_t) * params->num_edges, cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(cudaStreamSynchronize(ctx->stream));
+      if (!ctx->h_chunk->overflow) {
+        ctx->sh_rank = rank;
+        ctx->sh_world = world;
+        ctx->sh_N = N;
+        ctx->sh_valid = true;
+        return SAC_COT_OK;
+      }
+      ++ctx->retries;
+      if (int rc = ensure_keys(ctx, ctx->h_chunk->total_edges + ctx->h_chunk->total_edges / 16 + 1024)) return rc;
+    }
+  } catch (const std::bad_alloc&) {
+    return SAC_COT_E_NOMEM;
+  }
+  return SAC_COT_E_NOMEM;
+}
+
+int sac_cot_sharded_phase2(sac_cot_ctx* ctx, const uint64_t* t_all, const uint64_t* cand_all, uint64_t* best_key) {
+  if (!ctx || !t_all || !cand_all || !best_key) return SAC_COT_E_NULL;
+  if (!ctx->sh_valid) return SAC_COT_E_SIZE;
+  CU_TRY(cudaSetDevice(ctx->device));
+  try {
+    Layout& L = ctx->lay;
+    const int N = ctx->sh_N, world = ctx->sh_world, Ke = L.Ke;
+    // exchange #1 results: node sums add up over ranks; candidates merge to the global top-K_e
+    std::vector<unsigned long long> t2(static_cast<size_t>(ctx->descs[0].Npad), 0ull);
+    for (int g = 0; g < world; ++g)
+      for (int i = 0; i < N; ++i) t2[i] += t_all[static_cast<size_t>(g) * N + i];
+    std::vector<unsigned long long> all;
+    all.reserve(static_cast<size_t>(world) * Ke);
+    for (size_t k = 0; k < static_cast<size_t>(world) * Ke; ++k)
+      if (cand_all[k]) all.push_back(cand_all[k]);
+    std::sort(all.begin(), all.end(), [](unsigned long long a, unsigned long long b) { return a > b; });
+    all.resize(static_cast<size_t>(Ke), 0ull);
+    CU_TRY(cudaMemcpyAsync(L.t2, t2.data(), sizeof(unsigned long long) * t2.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(L.top, all.data(), sizeof(unsigned long long) * Ke, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemsetAsync(&L.state[0].best_key, 0, sizeof(unsigned long long), ctx->stream));
+    CU_TRY(cudaMemsetAsync(L.hyp_key, 0, sizeof(unsigned long long) * L.K, ctx->stream));
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    const float tau2 = ctx->prm.tau_inlier * ctx->prm.tau_inlier;
+    KL_TRY(launch_select_apex(lc, L.desc, 1, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
+    KL_TRY(launch_kabsch(lc, L.desc, 1, L.soa, L.tri, L.rt, L.K));
+    const int per = (L.K + world - 1) / world;
+    const int h0 = std::min(L.K, ctx->sh_rank * per), h1 = std::min(L.K, h0 + per);
+    KL_TRY(launch_score(lc, L.desc, 1, L.max_n, L.soa, L.tri, L.rt, L.hyp_key, L.state, tau2, L.K, h0, h1,
+                        ctx->prm.score_mode));
+    unsigned long long best = 0;
+    CU_TRY(cudaMemcpyAsync(&best, &L.state[0].best_key, sizeof(best), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    *best_key = best;
+  } catch (const std::bad_alloc&) {
+    return SAC_COT_E_NOMEM;
+  }
+  return SAC_COT_OK;
+}
+
+int sac_cot_sharded_phase3(sac_cot_ctx* ctx, uint64_t best_key_global, float R[9], float t[3], int32_t* inliers) {
+  if (!ctx || !R || !t || !inliers) return SAC_COT_E_NULL;
+  if (!ctx->sh_valid) return SAC_COT_E_SIZE;
+  CU_TRY(cudaSetDevice(ctx->device));
+  Layout& L = ctx->lay;
+  const unsigned long long key = best_key_global;
+  CU_TRY(cudaMemcpyAsync(L.best_override, &key, sizeof(key), cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(&L.state[0].best_key, &key, sizeof(key), cudaMemcpyHostToDevice, ctx->stream));
+  LaunchCtx lc{ctx->stream, ctx->sm_count};
+  const float tau2 = ctx->prm.tau_inlier * ctx->prm.tau_inlier;
+  KL_TRY(launch_finalize(lc, L.desc, 1, L.soa, L.rt, L.state, L.best_override, L.mask, L.outR, L.outT, L.outInl, tau2,
+                         L.K, ctx->prm.refit));
+  CU_TRY(cudaMemcpyAsync(R, L.outR, sizeof(float) * 9, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(t, L.outT, sizeof(float) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(inliers, L.outInl, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->ws_valid = true;  // the single pair is fully resident: debug_get(pair = 0 or -1) works
+  return SAC_COT_OK;
+}
+
+// ---- parity getter ------------------------------------------------------------------------
+int sac_cot_debug_get(sac_cot_ctx* ctx, int32_t pair, int32_t which, void* out, size_t cap, size_t* written) {
+  if (!ctx || !written) return SAC_COT_E_NULL;
+  if (pair == -1) pair = 0;
+  if (!(ctx->ws_valid || ctx->sh_valid) || pair < 0 || pair >= ctx->lay.pairs) return SAC_COT_E_WHICH;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (int rc = resolve_pending(ctx)) return rc;
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  const Layout& L = ctx->lay;
+  const PairDesc& d = ctx->descs[pair];
+  PairDev st;
+  CU_TRY(cudaMemcpy(&st, L.state + pair, sizeof(st), cudaMemcpyDeviceToHost));
+  const void* dsrc = nullptr;
+  size_t bytes = 0;
+  uint64_t scalar = 0;
+  std::vector<uint32_t> tmp32;
+  switch (which) {
+    case SAC_COT_DBG_ADJ: dsrc = L.adj + d.adj_off; bytes = static_cast<size_t>(d.N) * d.stride * 4; break;
+    case SAC_COT_DBG_T_NODE: bytes = static_cast<size_t>(d.N) * 4; break;
+    case SAC_COT_DBG_NUM_EDGES: scalar = st.num_edges; bytes = 8; break;
+    case SAC_COT_DBG_EDGE_KEYS: dsrc = ctx->keys + st.key_base; bytes = static_cast<size_t>(st.key_count) * 8; break;
+    case SAC_COT_DBG_TOP_EDGES: dsrc = L.top + static_cast<size_t>(pair) * L.Ke; bytes = static_cast<size_t>(st.n_sel) * 8; break;
+    case SAC_COT_DBG_TRIANGLES: dsrc = L.tri + static_cast<size_t>(pair) * L.K * 3; bytes = static_cast<size_t>(L.K) * 12; break;
+    case SAC_COT_DBG_HYP_RT: dsrc = L.rt + static_cast<size_t>(pair) * L.K * 12; bytes = static_cast<size_t>(L.K) * 48; break;
+    case SAC_COT_DBG_HYP_SCORE: dsrc = L.hyp_key + static_cast<size_t>(pair) * L.K; bytes = static_cast<size_t>(L.K) * 8; break;
+    case SAC_COT_DBG_BEST_KEY: scalar = st.best_key; bytes = 8; break;
+    case SAC_COT_DBG_MASK: dsrc = L.mask + d.mask_off; bytes = static_cast<size_t>((d.N + 31) / 32) * 4; break;
+    case SAC_COT_DBG_HIST: dsrc = L.hist + static_cast<size_t>(pair) * kHistBins; bytes = kHistBins * 4; break;
+    default: return SAC_COT_E_WHICH;
+  }
+  *written = bytes;
+  if (bytes > cap) return SAC_COT_E_CAPACITY;
+  if (bytes && !out) return SAC_COT_E_NULL;
+  if (!bytes) return SAC_COT_OK;
+  if (which == SAC_COT_DBG_NUM_EDGES || which == SAC_COT_DBG_BEST_KEY) {
+    std::memcpy(out, &scalar, 8);
+    return SAC_COT_OK;
+  }
+  if (which == SAC_COT_DBG_T_NODE) {
+    try {
+      std::vector<unsigned long long> t2(static_cast<size_t>(d.N));
+      CU_TRY(cudaMemcpy(t2.data(), L.t2 + d.node_off, sizeof(unsigned long long) * d.N, cudaMemcpyDeviceToHost));
+      uint32_t* o = static_cast<uint32_t*>(out);
+      for (int i = 0; i < d.N; ++i) o[i] = static_cast<uint32_t>(t2[i] / 2);
+    } catch (const std::bad_alloc&) {
+      return SAC_COT_E_NOMEM;
+    }
+    return SAC_COT_OK;
+  }
+  CU_TRY(cudaMemcpy(out, dsrc, bytes, cudaMemcpyDeviceToHost));
+  return SAC_COT_OK;
+}
+
+const char* sac_cot_strerror(int status) {
+  switch (status) {
+    case SAC_COT_OK: return "ok";
+    case SAC_COT_E_NULL: return "null pointer argument";
+    case SAC_COT_E_SIZE: return "size out of range (3 <= N <= 65535, B >= 0) or call out of sequence";
+    case SAC_COT_E_PARAMS: return "invalid sac_cot_params";
+    case SAC_COT_E_NODEVICE: return "no usable sm_100 CUDA device";
+    case SAC_COT_E_UNSUPPORTED: return "not supported by this implementation";
+    case SAC_COT_E_WHICH: return "unknown selector / index, or nothing resident";
+    case SAC_COT_E_CAPACITY: return "output buffer too small";
+    case SAC_COT_E_NOMEM: return "out of device memory / workspace overflow";
+    default: return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown status";
+  }
+}
+
+const char* sac_cot_version(void) { return "sac-cot-b200 0.1 (cuda sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// common.cuh — shared declarations of the sm_100a SAC-COT kernels and their host launchers.
+//
+// Stage ids (S1..S7) refer to SURVEY.md §8a; the reference repository holds no code to cite
+// (/root/reference/README.md:1-2), so the normative text is BASELINE.json `north_star`.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace saccot {
+
+// ------------------------------------------------------------------------------------------
+// Per-pair descriptors.  PairDesc is built on the host and read-only on the device; PairDev
+// is device state zeroed at the start of every run.
+// ------------------------------------------------------------------------------------------
+struct PairDesc {
+  int32_t N;         // correspondences
+  int32_t Npad;      // N rounded up to a multiple of 128
+  int32_t stride;    // 32-bit words per adjacency row = Npad / 32 (multiple of 4 => 16 B rows)
+  int32_t nblk;      // Npad / 128
+  int64_t pt_off;    // first point of this pair in the packed AoS inputs
+  int64_t soa_off;   // first float of this pair's 6 x Npad SoA block (sx,sy,sz,dx,dy,dz)
+  int64_t adj_off;   // first u32 word of this pair's Npad x stride adjacency block
+  int64_t node_off;  // first entry of this pair in per-node arrays (t2), sum of Npad
+  int64_t mask_off;  // first u32 word of this pair's inlier mask (Npad/32 words)
+};
+
+struct PairDev {
+  unsigned long long num_edges;  // E, counted by the graph kernel
+  unsigned long long key_base;   // offset of this pair's edge keys in the key pool (scan)
+  unsigned long long key_count;  // append cursor of the triangle kernel (ends == evaluated edges)
+  unsigned long long best_key;   // max hypothesis key
+  uint32_t sel_count;            // keys appended to the selected list so far
+  uint32_t tie_count;            // keys appended to the tie list so far
+  uint32_t dstar;                // threshold digit (T >> 4) of the top-K_e selection
+  uint32_t n_above;              // #keys with digit > dstar
+  uint32_t n_tie;                // #keys with digit == dstar
+  uint32_t tie_inplace;          // 1: tie bucket too large for the tie list, scan keys in place
+  uint32_t n_sel;                // number of selected edges = min(K_e, evaluated edges)
+  uint32_t pad_;
+};
+
+struct ChunkDev {
+  unsigned long long total_edges;  // sum of E over the chunk (key pool demand)
+  uint32_t overflow;               // 1: key pool too small; downstream kernels do nothing
+  uint32_t pad_;
+};
+
+constexpr int kMaxEdges = 4096;     // == SAC_COT_MAX_EDGES
+constexpr int kMaxApex = 8;         // == SAC_COT_MAX_APEX
+constexpr int kHistBins = 4096;     // histogram of T >> 4
+constexpr int kTieCap = 16384;      // tie-list entries per pair
+constexpr int kTriJ = 128;          // J-block rows staged per triangle work unit
+constexpr int kTriI = 256;          // rows of i per triangle work unit
+constexpr int kTriThreads = 512;
+constexpr int kTriMaxR = 11;        // max words per lane per row chunk (352 words)
+constexpr int kTriChunkR = 8;       // words per lane per chunk when rows do not fit (256 words)
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk asynchronous copy (TMA, 1-D form; SASS UBLKCP).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other > v ? other : v;
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host launchers (one per kernel file).  Every launcher returns the number of kernels it
+// enqueued on `stream` (for the ctx "launches" counter) or a negative cudaError_t.
+// ------------------------------------------------------------------------------------------
+struct LaunchCtx {
+  cudaStream_t stream;
+  int sm_count;
+};
+
+// kernels_graph.cu — S0 repack + S1 compatibility graph
+int launch_pack_soa(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const float* d_src,
+                    const float* d_dst, float* d_soa);
+int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, const float* d_soa,
+                 uint32_t* d_adj, PairDev* d_state, float tau);
+int launch_key_scan(const LaunchCtx& lc, int pairs, PairDev* d_state, ChunkDev* d_chunk, unsigned long long key_cap);
+
+// kernels_triangles.cu — S2 triangle counts (POPC bitset path)
+int launch_triangles(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, int max_stride,
+                     const uint32_t* d_adj, PairDev* d_state, const ChunkDev* d_chunk, unsigned long long* d_keys,
+                     uint32_t* d_hist, unsigned long long* d_t2, int rank, int world);
+int triangles_configure();  // opt-in dynamic shared memory; call once per device
+
+// kernels_select.cu — S3 edge ranking + apex selection
+int launch_select_edges(const LaunchCtx& lc, int pairs, PairDev* d_state, const ChunkDev* d_chunk,
+                        const unsigned long long* d_keys, const uint32_t* d_hist, unsigned long long* d_sel,
+                        unsigned long long* d_tie, unsigned long long* d_top, int Ke);
+int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const uint32_t* d_adj,
+                       const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m);
+
+// kernels_hypo.cu — S4 Kabsch, S5/S6 scoring + argmax, S7 refit
+int launch_kabsch(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const float* d_soa, const int32_t* d_tri,
+                  float* d_rt, int K);
+int launch_score(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_n, const float* d_soa,
+                 const int32_t* d_tri, const float* d_rt, unsigned long long* d_hyp_key, PairDev* d_state, float tau2,
+                 int K, int h_begin, int h_end, int mode);
+int launch_finalize(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const float* d_soa, const float* d_rt,
+                    const PairDev* d_state, const unsigned long long* d_best_override, uint32_t* d_mask, float* d_R,
+                    float* d_t, int32_t* d_inl, float tau2, int K, int refit);
+
+}  // namespace saccot

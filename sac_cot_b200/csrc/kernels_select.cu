@@ -1,0 +1,297 @@
+// kernels_select.cu — S3, guided selection of the top-ranked compatibility triangles
+// (SURVEY.md §8a row S3).
+//
+//  (1) edges ordered by key = T<<32 | (0xFFFF-i)<<16 | (0xFFFF-j) descending, i.e. (T desc, i asc,
+//      j asc); the first K_e are kept.  Exact top-K_e without sorting E keys:
+//        a. the triangle kernel left a 4096-bin histogram of the top digit T>>4;
+//        b. select_scatter finds the threshold digit d* (largest d with #{digit >= d} >= K_e),
+//           appends every key with digit > d* to the selected list and every key with digit == d*
+//           to a tie list (or flags an in-place scan if that bucket exceeds the tie list);
+//        c. select_final (one CTA per pair) radix-selects, over the remaining 36 key bits, the
+//           exact key threshold among the ties (keys are unique, so the r-th largest is unique),
+//           appends the ties >= threshold, and bitonic-sorts the <= 4096 selected keys.
+//      The result does not depend on the (atomic, unordered) placement of keys in any list.
+//  (2) select_apex: one warp per selected edge (i,j) enumerates k in N(i) ∩ N(j) and keeps the
+//      m best by (t_k desc, k asc); hypothesis id h = r*m + q.
+#include "common.cuh"
+
+namespace saccot {
+
+constexpr int kSelThreads = 256;
+
+__device__ __forceinline__ unsigned int key_digit(unsigned long long key) {
+  return static_cast<unsigned int>(key >> 36);  // T >> 4 (T < 65536 => digit < 4096)
+}
+
+// Threshold digit from the pair's histogram.  All threads of a 256-thread CTA call this.
+// Thread t owns bins [4095-16t-15, 4095-16t] (descending order => thread 0 owns the top bins).
+__device__ void find_threshold_digit(const uint32_t* __restrict__ histp, unsigned int Ke, unsigned int* s_scan,
+                                     unsigned int* s_out /* [3]: dstar, n_above, n_tie */) {
+  const int t = threadIdx.x;
+  unsigned int bins[16];
+  unsigned int mine = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    bins[k] = histp[kHistBins - 1 - (16 * t + k)];  // descending digits
+    mine += bins[k];
+  }
+  s_scan[t] = mine;
+  __syncthreads();
+  for (int o = 1; o < kSelThreads; o <<= 1) {
+    const unsigned int add = t >= o ? s_scan[t - o] : 0u;
+    __syncthreads();
+    s_scan[t] += add;
+    __syncthreads();
+  }
+  const unsigned int incl = s_scan[t];
+  const unsigned int excl = incl - mine;
+  const unsigned int total = s_scan[kSelThreads - 1];
+  if (total < Ke) {
+    // fewer edges than K_e: everything is selected; treat digit 0 as the tie bucket
+    if (t == kSelThreads - 1) {
+      s_out[0] = 0;
+      s_out[1] = total - bins[15];
+      s_out[2] = bins[15];
+    }
+  } else if (excl < Ke && incl >= Ke) {
+    unsigned int cum = excl;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (cum < Ke && cum + bins[k] >= Ke) {
+        s_out[0] = static_cast<unsigned int>(kHistBins - 1 - (16 * t + k));
+        s_out[1] = cum;
+        s_out[2] = bins[k];
+      }
+      cum += bins[k];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_scatter_kernel(
+    PairDev* __restrict__ state, const ChunkDev* __restrict__ chunk, const unsigned long long* __restrict__ keys,
+    const uint32_t* __restrict__ hist, unsigned long long* __restrict__ sel, unsigned long long* __restrict__ tie,
+    int Ke) {
+  if (chunk->overflow) return;
+  const int pair = blockIdx.y;
+  __shared__ unsigned int s_scan[kSelThreads];
+  __shared__ unsigned int s_out[3];
+  find_threshold_digit(hist + static_cast<size_t>(pair) * kHistBins, static_cast<unsigned int>(Ke), s_scan, s_out);
+  const unsigned int dstar = s_out[0], n_above = s_out[1], n_tie = s_out[2];
+  const bool inplace = n_tie > static_cast<unsigned int>(kTieCap);
+  PairDev* st = state + pair;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->dstar = dstar;
+    st->n_above = n_above;
+    st->n_tie = n_tie;
+    st->tie_inplace = inplace ? 1u : 0u;
+  }
+  const unsigned long long E = st->key_count;
+  const unsigned long long* kp = keys + st->key_base;
+  unsigned long long* selp = sel + static_cast<size_t>(pair) * Ke;
+  unsigned long long* tiep = tie + static_cast<size_t>(pair) * kTieCap;
+  for (unsigned long long idx = static_cast<unsigned long long>(blockIdx.x) * kSelThreads + threadIdx.x; idx < E;
+       idx += static_cast<unsigned long long>(gridDim.x) * kSelThreads) {
+    const unsigned long long key = kp[idx];
+    const unsigned int dg = key_digit(key);
+    if (dg > dstar) {
+      const unsigned int pos = atomicAdd(&st->sel_count, 1u);
+      selp[pos] = key;  // pos < n_above < K_e by construction
+    } else if (dg == dstar && !inplace) {
+      const unsigned int pos = atomicAdd(&st->tie_count, 1u);
+      tiep[pos] = key;  // pos < n_tie <= kTieCap
+    }
+  }
+}
+
+// One CTA (1024 threads) per pair.
+__global__ void __launch_bounds__(1024) select_final_kernel(
+    PairDev* __restrict__ state, const ChunkDev* __restrict__ chunk, const unsigned long long* __restrict__ keys,
+    unsigned long long* __restrict__ sel, const unsigned long long* __restrict__ tie,
+    unsigned long long* __restrict__ top, int Ke) {
+  const int pair = blockIdx.x;
+  unsigned long long* topp = top + static_cast<size_t>(pair) * Ke;
+  if (chunk->overflow) return;
+  PairDev* st = state + pair;
+  __shared__ unsigned long long sbuf[kMaxEdges];
+  __shared__ unsigned int h256[256];
+  __shared__ unsigned long long s_pref;
+  __shared__ unsigned int s_need;
+
+  const int t = threadIdx.x;
+  const unsigned int dstar = st->dstar, n_above = st->n_above, n_tie = st->n_tie;
+  const bool inplace = st->tie_inplace != 0;
+  const unsigned long long* srcp = inplace ? keys + st->key_base : tie + static_cast<size_t>(pair) * kTieCap;
+  const unsigned long long n_src = inplace ? st->key_count : static_cast<unsigned long long>(n_tie);
+  unsigned int need = static_cast<unsigned int>(Ke) - n_above;  // n_above < K_e
+  if (need > n_tie) need = n_tie;
+  unsigned long long* selp = sel + static_cast<size_t>(pair) * Ke;
+
+  unsigned long long theta = static_cast<unsigned long long>(dstar) << 36;  // take every tie by default
+  if (need < n_tie) {
+    // radix select of the `need`-th largest key among {key : digit == dstar} over bits [35:0]
+    if (t == 0) {
+      s_pref = static_cast<unsigned long long>(dstar) << 36;
+      s_need = need;
+    }
+    __syncthreads();
+    int known = 36;  // bits [63:known] of the threshold are fixed in s_pref
+    while (known > 0) {
+      const int width = known >= 8 ? 8 : known;
+      const int shift = known - width;
+      if (t < 256) h256[t] = 0;
+      __syncthreads();
+      const unsigned long long pref = s_pref;
+      for (unsigned long long idx = t; idx < n_src; idx += 1024) {
+        const unsigned long long key = srcp[idx];
+        if ((key >> known) == (pref >> known)) atomicAdd(&h256[(key >> shift) & ((1u << width) - 1u)], 1u);
+      }
+      __syncthreads();
+      if (t == 0) {
+        unsigned int remaining = s_need, cum = 0;
+        int dsel = 0;
+        for (int dgt = (1 << width) - 1; dgt >= 0; --dgt) {
+          if (cum + h256[dgt] >= remaining) {
+            dsel = dgt;
+            break;
+          }
+          cum += h256[dgt];
+        }
+        s_need = remaining - cum;  // still needed inside the chosen bucket (>= 1)
+        s_pref = pref | (static_cast<unsigned long long>(dsel) << shift);
+      }
+      __syncthreads();
+      known = shift;
+    }
+    theta = s_pref;  // exact key of the `need`-th largest tie
+  }
+  // append the ties at or above the threshold
+  if (need > 0) {
+    for (unsigned long long idx = t; idx < n_src; idx += 1024) {
+      const unsigned long long key = srcp[idx];
+      if (key_digit(key) == dstar && key >= theta) {
+        const unsigned int pos = atomicAdd(&st->sel_count, 1u);
+        if (pos < static_cast<unsigned int>(Ke)) selp[pos] = key;
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned int n_sel = n_above + need;
+  // bitonic sort (descending) of the selected keys, zero padded to a power of two >= Ke
+  int P = 1;
+  while (P < Ke) P <<= 1;
+  for (int k = t; k < P; k += 1024) sbuf[k] = static_cast<unsigned int>(k) < n_sel ? selp[k] : 0ull;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int strd = size >> 1; strd > 0; strd >>= 1) {
+      for (int k = t; k < P; k += 1024) {
+        const int partner = k ^ strd;
+        if (partner > k) {
+          const bool desc = (k & size) == 0;
+          const unsigned long long a = sbuf[k], b = sbuf[partner];
+          if (desc ? (a < b) : (a > b)) {
+            sbuf[k] = b;
+            sbuf[partner] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int k = t; k < Ke; k += 1024) topp[k] = sbuf[k];
+  if (t == 0) st->n_sel = n_sel;
+}
+
+int launch_select_edges(const LaunchCtx& lc, int pairs, PairDev* d_state, const ChunkDev* d_chunk,
+                        const unsigned long long* d_keys, const uint32_t* d_hist, unsigned long long* d_sel,
+                        unsigned long long* d_tie, unsigned long long* d_top, int Ke) {
+  int gx = (4 * lc.sm_count + pairs - 1) / pairs;
+  if (gx < 16) gx = 16;
+  if (gx > 4 * lc.sm_count) gx = 4 * lc.sm_count;
+  select_scatter_kernel<<<dim3(gx, pairs), kSelThreads, 0, lc.stream>>>(d_state, d_chunk, d_keys, d_hist, d_sel,
+                                                                        d_tie, Ke);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  select_final_kernel<<<pairs, 1024, 0, lc.stream>>>(d_state, d_chunk, d_keys, d_sel, d_tie, d_top, Ke);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 2 : -static_cast<int>(e);
+}
+
+// ------------------------------------------------------------------------------------------
+// Apex selection: one warp per selected edge.
+// ------------------------------------------------------------------------------------------
+constexpr int kApexMax = 8;
+
+__global__ void __launch_bounds__(128) select_apex_kernel(const PairDesc* __restrict__ descs,
+                                                          const uint32_t* __restrict__ adj,
+                                                          const unsigned long long* __restrict__ t2,
+                                                          const unsigned long long* __restrict__ top,
+                                                          int32_t* __restrict__ tri, int Ke, int m) {
+  const int pair = blockIdx.y;
+  const PairDesc d = descs[pair];
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= Ke) return;
+  int32_t* out = tri + (static_cast<size_t>(pair) * Ke + r) * m * 3;
+  const unsigned long long ekey = top[static_cast<size_t>(pair) * Ke + r];
+  if (ekey == 0) {  // fewer than K_e edges: slot unused
+    for (int k = lane; k < m * 3; k += 32) out[k] = -1;
+    return;
+  }
+  const int i = static_cast<int>(0xFFFFu - static_cast<unsigned int>((ekey >> 16) & 0xFFFFu));
+  const int j = static_cast<int>(0xFFFFu - static_cast<unsigned int>(ekey & 0xFFFFu));
+  const uint32_t* ri = adj + d.adj_off + static_cast<size_t>(i) * d.stride;
+  const uint32_t* rj = adj + d.adj_off + static_cast<size_t>(j) * d.stride;
+  const unsigned long long* t2p = t2 + d.node_off;
+
+  // per-lane best-m candidates, sorted descending; candidate key = t_k << 32 | (0xFFFFFFFF - k)
+  unsigned long long best[kApexMax];
+#pragma unroll
+  for (int q = 0; q < kApexMax; ++q) best[q] = 0ull;
+  for (int w = lane; w < d.stride; w += 32) {
+    uint32_t bits = ri[w] & rj[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const unsigned int k = static_cast<unsigned int>(w * 32 + b);
+      unsigned long long c = ((t2p[k] >> 1) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - k);
+      // insertion into the sorted register array (fully unrolled compare-exchange chain)
+#pragma unroll
+      for (int q = 0; q < kApexMax; ++q) {
+        if (c > best[q]) {
+          const unsigned long long tmp = best[q];
+          best[q] = c;
+          c = tmp;
+        }
+      }
+    }
+  }
+  // warp merge: m rounds of "global max, owner pops"
+  for (int q = 0; q < m; ++q) {
+    const unsigned long long mine = best[0];
+    const unsigned long long wmax = warp_max_u64(mine);
+    if (wmax == 0ull) {
+      if (lane == 0) { out[q * 3 + 0] = -1; out[q * 3 + 1] = -1; out[q * 3 + 2] = -1; }
+      continue;
+    }
+    // candidate keys are unique (distinct k), so exactly one lane owns the maximum
+    if (mine == wmax) {
+      out[q * 3 + 0] = i;
+      out[q * 3 + 1] = j;
+      out[q * 3 + 2] = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned int>(wmax & 0xFFFFFFFFull));
+#pragma unroll
+      for (int s = 0; s < kApexMax - 1; ++s) best[s] = best[s + 1];
+      best[kApexMax - 1] = 0ull;
+    }
+  }
+}
+
+int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const uint32_t* d_adj,
+                       const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m) {
+  dim3 grid((Ke + 3) / 4, pairs);
+  select_apex_kernel<<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+}  // namespace saccot

@@ -1,0 +1,279 @@
+"""GPU parity: the CUDA path through the C ABI against the from-paper oracle on the same seeded
+inputs.  Bit-exact for the compatibility graph, triangle counts, edge ranking, triangles,
+per-hypothesis (R,t) bits, per-hypothesis scores, the winning id and its inlier mask; the fp64
+refit within 1e-5 rad / 1e-5 units (BASELINE.json north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from sac_cot_b200 import _abi, synth
+from sac_cot_b200.api import Registrar, SacCotError
+
+pytestmark = pytest.mark.gpu
+
+EXACT = [("adj", _abi.DBG_ADJ), ("num_edges", _abi.DBG_NUM_EDGES), ("hist", _abi.DBG_HIST),
+         ("t_node", _abi.DBG_T_NODE), ("top_edges", _abi.DBG_TOP_EDGES), ("triangles", _abi.DBG_TRIANGLES),
+         ("hyp_rt", _abi.DBG_HYP_RT), ("hyp_score", _abi.DBG_HYP_SCORE), ("best_key", _abi.DBG_BEST_KEY),
+         ("mask", _abi.DBG_MASK)]
+TOL_ANG = 1e-5   # rad
+TOL_T = 1e-5     # translation units
+
+
+def set_params(reg, **kw):
+    for k, v in kw.items():
+        setattr(reg.params, k, v)
+
+
+def compare_stages(gpu, oracle, pair_idx=0, stages=EXACT):
+    bad = []
+    for name, which in stages:
+        a, b = gpu.debug(pair_idx, which), oracle.debug(pair_idx, which)
+        if a.shape != b.shape:
+            bad.append(f"{name}: shape {a.shape} vs {b.shape}")
+        elif not (a.view(np.uint8) == b.view(np.uint8)).all():
+            n = int((a.view(np.uint8) != b.view(np.uint8)).sum())
+            bad.append(f"{name}: {n} differing bytes of {a.nbytes}")
+    a = np.sort(gpu.debug(pair_idx, _abi.DBG_EDGE_KEYS))
+    b = np.sort(oracle.debug(pair_idx, _abi.DBG_EDGE_KEYS))
+    if a.shape != b.shape or not (a == b).all():
+        bad.append("edge_keys (sorted) differ")
+    assert not bad, "; ".join(bad)
+
+
+def compare_pose(Rg, tg, ig, Ro, to, io):
+    assert ig == io
+    ang, dt = synth.pose_error(Rg, tg, np.asarray(Ro, np.float64), np.asarray(to, np.float64))
+    assert ang < TOL_ANG and dt < TOL_T, (ang, dt)
+
+
+def run_both(gpu, oracle, p, **kw):
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier, **kw)
+    out_g = gpu.register(p.src, p.dst)
+    out_o = oracle.register(p.src, p.dst)
+    compare_stages(gpu, oracle)
+    compare_pose(*out_g, *out_o)
+    return out_g
+
+
+@pytest.mark.parametrize("N", [3, 4, 31, 32, 33, 100, 127, 128, 129, 255, 256, 257, 300, 1000, 1025])
+def test_stage_parity_small_and_ragged_sizes(gpu, oracle, N):
+    p = synth.make_pair(N, 0.3, 7000 + N)
+    run_both(gpu, oracle, p, num_edges=64, apex_per_edge=4)
+
+
+@pytest.mark.parametrize("Ke,m", [(1, 1), (5, 8), (1024, 4), (4096, 8)])
+def test_stage_parity_selection_sizes(gpu, oracle, Ke, m):
+    p = synth.make_pair(700, 0.1, 7100 + Ke)
+    run_both(gpu, oracle, p, num_edges=Ke, apex_per_edge=m)
+
+
+def test_cfg1_single_pair_n1000(gpu, oracle):
+    p = synth.make_config_pair("cfg1_single_n1000", 0)
+    R, t, inl = run_both(gpu, oracle, p)
+    ang, dt = synth.pose_error(R, t, p.R_gt, p.t_gt)
+    assert ang < np.deg2rad(1.0) and dt < 0.02
+
+
+@pytest.mark.parametrize("cfg,b", [("cfg2_3dmatch_256x5000", 0), ("cfg2_3dmatch_256x5000", 1),
+                                   ("cfg3_3dlomatch_256x5000", 0), ("cfg3_3dlomatch_256x5000", 1)])
+def test_n5000_pairs_full_stage_parity(gpu, oracle, cfg, b):
+    p = synth.make_config_pair(cfg, b)
+    R, t, inl = run_both(gpu, oracle, p)
+    ang, dt = synth.pose_error(R, t, p.R_gt, p.t_gt)
+    assert ang < np.deg2rad(2.0) and dt < 0.05
+    assert inl >= len(p.inlier_idx)
+
+
+def test_kitti_scale_pair_n10000(gpu, oracle):
+    p = synth.make_config_pair("cfg4_kitti_128x10000", 0)
+    run_both(gpu, oracle, p)
+
+
+def test_chunked_row_path_n13000(gpu, oracle):
+    # stride 408 words > 352: the triangle kernel runs its 256-word chunk / accumulate mode
+    p = synth.make_pair(13000, 0.03, 7300)
+    run_both(gpu, oracle, p)
+
+
+def test_truncated_residual_mode(gpu, oracle):
+    p = synth.make_pair(1500, 0.08, 7400)
+    run_both(gpu, oracle, p, score_mode=1, num_edges=256)
+
+
+def test_refit_off_returns_winner_bits(gpu, oracle):
+    p = synth.make_pair(900, 0.1, 7500)
+    for r in (gpu, oracle):
+        set_params(r, refit=0)
+    Rg, tg, ig = gpu.register(p.src, p.dst)
+    Ro, to, io = oracle.register(p.src, p.dst)
+    np.testing.assert_array_equal(Rg, Ro)
+    np.testing.assert_array_equal(tg, to)
+    assert ig == io
+
+
+def test_complete_graph_and_exact_pose(gpu, oracle):
+    # noise-free all-inlier input: complete graph, every T equal -> the tie bucket holds all E keys
+    # (in-place radix select path), pose exact
+    N = 400
+    p = synth.make_pair(N, 1.0, 7600)
+    dst = (p.src.astype(np.float64) @ p.R_gt.T + p.t_gt).astype(np.float32)
+    for r in (gpu, oracle):
+        set_params(r, num_edges=512, apex_per_edge=4)
+    out_g = gpu.register(p.src, dst)
+    out_o = oracle.register(p.src, dst)
+    compare_stages(gpu, oracle)
+    compare_pose(*out_g, *out_o)
+    assert out_g[2] == N
+    assert int(gpu.debug(0, _abi.DBG_NUM_EDGES)[0]) == N * (N - 1) // 2
+
+
+def test_empty_graph_is_a_result(gpu, oracle):
+    rng = np.random.default_rng(0)
+    src = (rng.random((64, 3)) * 100).astype(np.float32)
+    dst = (rng.random((64, 3)) * 100).astype(np.float32)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=1e-5)
+    out_g = gpu.register(src, dst)
+    out_o = oracle.register(src, dst)
+    compare_stages(gpu, oracle)
+    np.testing.assert_array_equal(out_g[0], out_o[0])
+    np.testing.assert_array_equal(out_g[1], out_o[1])
+    assert out_g[2] == out_o[2]
+
+
+def test_fewer_edges_than_requested(gpu, oracle):
+    # tiny graph: E < K_e, triangles missing for most slots
+    p = synth.make_pair(12, 0.5, 7700)
+    run_both(gpu, oracle, p, num_edges=256, apex_per_edge=8)
+
+
+def test_batch_with_ragged_sizes_matches_oracle(gpu, oracle):
+    sizes = (300, 1000, 129, 2048, 64, 777)
+    pairs = [synth.make_pair(n, 0.1, 7800 + k) for k, n in enumerate(sizes)]
+    rg = gpu.register_batch([p.src for p in pairs], [p.dst for p in pairs])
+    ro = oracle.register_batch([p.src for p in pairs], [p.dst for p in pairs])
+    for b in range(len(pairs)):
+        compare_stages(gpu, oracle, b)
+        compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
+    # pointer-array entry point and chunked execution give the same bits
+    rp = gpu.register_pointer_batch([p.src for p in pairs], [p.dst for p in pairs])
+    np.testing.assert_array_equal(rp.R, rg.R)
+    np.testing.assert_array_equal(rp.t, rg.t)
+    np.testing.assert_array_equal(rp.inliers, rg.inliers)
+    gpu.set("keep_debug", 0)
+    gpu.set("chunk_pairs", 2)
+    rc = gpu.register_batch([p.src for p in pairs], [p.dst for p in pairs])
+    np.testing.assert_array_equal(rc.R, rg.R)
+    np.testing.assert_array_equal(rc.t, rg.t)
+    np.testing.assert_array_equal(rc.inliers, rg.inliers)
+
+
+def test_key_pool_growth_retry(gpu_lib, oracle):
+    # a dense graph (large tau) exceeds the 12.5 % initial key-pool guess: the library must grow
+    # the pool and re-run transparently
+    p = synth.make_pair(1200, 0.2, 7900)
+    with Registrar(lib=gpu_lib, tau_compat=1.5, tau_inlier=0.1) as g:
+        g.set("keep_debug", 1)
+        set_params(oracle, tau_compat=1.5, tau_inlier=0.1)
+        out_g = g.register(p.src, p.dst)
+        out_o = oracle.register(p.src, p.dst)
+        assert g.get("retries") >= 1
+        compare_stages(g, oracle)
+        compare_pose(*out_g, *out_o)
+
+
+def test_device_resident_entry_point(gpu_lib, oracle):
+    import torch
+    pairs = [synth.make_pair(1000, 0.1, 8000 + k) for k in range(5)]
+    src = np.concatenate([p.src for p in pairs])
+    dst = np.concatenate([p.dst for p in pairs])
+    offsets = np.arange(6, dtype=np.int64) * 1000
+    dev = torch.device("cuda", 0)
+    d_src, d_dst = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
+    d_R = torch.empty((5, 3, 3), dtype=torch.float32, device=dev)
+    d_t = torch.empty((5, 3), dtype=torch.float32, device=dev)
+    d_i = torch.empty(5, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    with Registrar(lib=gpu_lib, device=0, stream=stream.cuda_stream) as g:
+        g.register_packed_ptr(d_src.data_ptr(), d_dst.data_ptr(), offsets, d_R.data_ptr(), d_t.data_ptr(),
+                              d_i.data_ptr(), _abi.LOC_DEVICE)
+        stream.synchronize()
+        assert g.get("last_status") == 0
+        assert g.get("launches") == 10
+    ro = oracle.register_batch([p.src for p in pairs], [p.dst for p in pairs])
+    for b in range(5):
+        compare_pose(d_R[b].cpu().numpy(), d_t[b].cpu().numpy(), int(d_i[b]), ro.R[b], ro.t[b], ro.inliers[b])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_phases_match_unsharded_and_oracle(gpu_lib, oracle_lib, world):
+    # ranks emulated one after the other on the single GPU (no kernel waits on another)
+    N = 6000
+    p = synth.make_pair(N, 0.05, 8100)
+    with Registrar(lib=gpu_lib) as one:
+        R1, t1, i1 = one.register(p.src, p.dst)
+    ranks = [Registrar(lib=gpu_lib) for _ in range(world)]
+    oranks = [Registrar(lib=oracle_lib) for _ in range(world)]
+    try:
+        ph = [r.sharded_phase1(p.src, p.dst, g, world) for g, r in enumerate(ranks)]
+        oph = [r.sharded_phase1(p.src, p.dst, g, world) for g, r in enumerate(oranks)]
+        for g in range(world):
+            np.testing.assert_array_equal(ph[g][0], oph[g][0])   # partial node sums, bit-exact per rank
+            np.testing.assert_array_equal(ph[g][1], oph[g][1])   # local top-K_e candidates
+        t_all = np.stack([x[0] for x in ph])
+        c_all = np.stack([x[1] for x in ph])
+        keys = [r.sharded_phase2(t_all, c_all) for r in ranks]
+        okeys = [r.sharded_phase2(t_all, c_all) for r in oranks]
+        assert keys == okeys
+        best = max(keys)
+        for r in ranks:
+            R, t, inl = r.sharded_phase3(best)
+            np.testing.assert_array_equal(R, R1)   # identical to the unsharded GPU result, bit for bit
+            np.testing.assert_array_equal(t, t1)
+            assert inl == i1
+    finally:
+        for r in ranks + oranks:
+            r.close()
+
+
+def test_argument_checking_matches_oracle(gpu_lib, oracle_lib):
+    src = np.zeros((10, 3), np.float32)
+    R = np.zeros(9, np.float32)
+    t = np.zeros(3, np.float32)
+    inl = C.c_int32()
+    f = _abi.fptr
+    for lib in (gpu_lib, oracle_lib):
+        p = _abi.default_params(lib)
+        assert lib.sac_cot_register(None, f(src), 10, C.byref(p), f(R), f(t), C.byref(inl)) == _abi.E_NULL
+        assert lib.sac_cot_register(f(src), f(src), 2, C.byref(p), f(R), f(t), C.byref(inl)) == _abi.E_SIZE
+        assert lib.sac_cot_register(f(src), f(src), 70000, C.byref(p), f(R), f(t), C.byref(inl)) == _abi.E_SIZE
+        for field, bad in [("struct_size", 4), ("tau_compat", 0.0), ("num_edges", 0), ("num_edges", 5000),
+                           ("apex_per_edge", 9), ("score_mode", 2), ("refit", 2), ("reserved", 1)]:
+            q = _abi.default_params(lib, **{field: bad})
+            assert lib.sac_cot_register(f(src), f(src), 10, C.byref(q), f(R), f(t), C.byref(inl)) == _abi.E_PARAMS
+    with Registrar(lib=gpu_lib) as g:
+        with pytest.raises(SacCotError):
+            g.set("no_such_knob", 1)
+        with pytest.raises(SacCotError):
+            g.debug(0, _abi.DBG_ADJ)  # nothing resident yet
+
+
+def test_module_level_register_uses_cuda(gpu_lib):
+    import sac_cot_b200
+    p = synth.make_pair(800, 0.1, 8200)
+    R, t, inl = sac_cot_b200.register(p.src, p.dst)
+    ang, dt = synth.pose_error(R, t, p.R_gt, p.t_gt)
+    assert ang < np.deg2rad(1.0) and dt < 0.02 and inl >= 75
+
+
+def test_run_to_run_determinism(gpu):
+    p = synth.make_pair(3000, 0.05, 8300)
+    outs = []
+    for _ in range(3):
+        R, t, inl = gpu.register(p.src, p.dst)
+        outs.append((R.copy(), t.copy(), inl, gpu.debug(0, _abi.DBG_TOP_EDGES), gpu.debug(0, _abi.DBG_HYP_SCORE)))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            np.testing.assert_array_equal(a, b)
