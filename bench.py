@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — registrations/sec of the SAC-COT hot path on BASELINE.json configs[1]
+(3DMatch-scale synthetic batch: 256 pairs x N=5000 correspondences, 5 % inliers, tau_c = 0.1 m).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the whole hot path (graph -> triangle counts -> COT selection ->
+3-point Kabsch -> K x N scoring + argmax -> fp64 refit) over one batch of 256 synthetic pairs
+per GPU.  Pairs are independent, so multi-GPU = one process per GPU (torchrun), each with its own
+batch, no data-path collective (weak scaling).
+
+  value : whole-job registrations/s with the inputs already resident in HBM
+          (sac_cot_register_packed, SAC_COT_LOC_DEVICE, on torch's current stream), timed with
+          CUDA events per step, L2 flushed between steps, max over ranks.
+  e2e   : the same metric through the host-buffer C-ABI call (pinned host inputs, H2D and D2H
+          inside the timed region).
+  roofline     : the dominant kernel (triangle counting), timed live with CUDA events inside
+                 the library during the timed steps.
+  cpu_baseline : the from-paper oracle on this box's host cores, rank 0, N = 1 only.
+
+--impl reference times the oracle (OpenMP build, all host threads) on a bounded sample of the
+same workload: the upstream repository ships no code (/root/reference/README.md:1-2), so the
+from-paper CPU oracle is the only "reference implementation" there is.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from sac_cot_b200 import _abi, synth  # noqa: E402
+from sac_cot_b200.api import Registrar, load_library  # noqa: E402
+
+WORKLOAD = "cfg2_3dmatch_256x5000"
+METRIC = "registrations/sec at N=5000 corr, 5% inliers"
+UNIT = "registrations/s"
+STAGES = ("pack", "graph", "scan", "triangles", "select", "apex", "kabsch", "score", "finalize")
+
+
+def make_batch(pairs, rank):
+    cfg = synth.CONFIGS[WORKLOAD]
+    ps = [synth.make_config_pair(WORKLOAD, b, seed_shift=rank * cfg["pairs"]) for b in range(pairs)]
+    src = np.ascontiguousarray(np.concatenate([p.src for p in ps]))
+    dst = np.ascontiguousarray(np.concatenate([p.dst for p in ps]))
+    offsets = np.arange(pairs + 1, dtype=np.int64) * cfg["N"]
+    return ps, src, dst, offsets
+
+
+def load_oracle(omp):
+    name = "libsaccot_oracle_omp.so" if omp else "libsaccot_oracle.so"
+    path = os.path.join(ROOT, "oracle", name)
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), name], check=True, stdout=subprocess.DEVNULL)
+    return _abi.bind(ctypes.CDLL(path))
+
+
+def time_oracle(lib, ps, cfg):
+    """Seconds per pair of the oracle over the given pairs."""
+    with Registrar(lib=lib, tau_compat=cfg["tau"], tau_inlier=cfg["tau"]) as reg:
+        t0 = time.perf_counter()
+        res = reg.register_batch([p.src for p in ps], [p.dst for p in ps])
+        dt = time.perf_counter() - t0
+        threads = reg.get("threads")
+    return dt / len(ps), threads, res
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+                power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            # "under load" = samples at or above the median power draw
+            pm = statistics.median(power)
+            load = [s for s, p in zip(sm, power) if p >= pm] or sm
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(smax), power_w_max=max(power),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the from-paper oracle (all host threads) on a bounded sample per step."""
+    if rank != 0:
+        return
+    cfg = synth.CONFIGS[WORKLOAD]
+    lib = load_oracle(omp=True)
+    sample = 32
+    ps, _, _, _ = make_batch(sample, 0)
+    for _ in range(args.warmup):
+        time_oracle(lib, ps[:8], cfg)
+    t0 = time.perf_counter()
+    threads = 1
+    for _ in range(args.steps):
+        _, threads, _ = time_oracle(lib, ps, cfg)
+    dt = time.perf_counter() - t0
+    value = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: N={cfg['N']}, 5% inliers, tau_c={cfg['tau']} (BASELINE.json configs[1])",
+                   "step": f"bounded sample of {sample} of the 256 pairs per step", "K_e": 1024, "apex_per_edge": 4},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(threads), "kind": "port",
+                         "sample": f"{sample} pairs/step x {args.steps} steps, from-paper oracle, OpenMP build "
+                                   "(upstream repo has no code to run)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU per step (default: the config's 256)")
+    ap.add_argument("--chunk-pairs", type=int, default=0, help="library knob chunk_pairs (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — sac_cot_b200 has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.CONFIGS[WORKLOAD]
+    pairs = args.pairs or cfg["pairs"]
+    N = cfg["N"]
+    ps, src, dst, offsets = make_batch(pairs, rank)
+
+    lib = load_library()
+    stream = torch.cuda.Stream(dev)  # every kernel/copy of the library and every timing event lives on this stream
+    torch.cuda.set_stream(stream)
+    reg = Registrar(lib=lib, device=local_rank, stream=stream.cuda_stream, tau_compat=cfg["tau"],
+                    tau_inlier=cfg["tau"])
+    if args.chunk_pairs:
+        reg.set("chunk_pairs", args.chunk_pairs)
+    K = reg.params.num_edges * reg.params.apex_per_edge
+
+    # device-resident inputs / outputs
+    d_src = torch.from_numpy(src).to(dev)
+    d_dst = torch.from_numpy(dst).to(dev)
+    d_R = torch.empty((pairs, 3, 3), dtype=torch.float32, device=dev)
+    d_t = torch.empty((pairs, 3), dtype=torch.float32, device=dev)
+    d_i = torch.empty(pairs, dtype=torch.int32, device=dev)
+    # pinned host inputs / outputs for the end-to-end leg
+    h_src = torch.from_numpy(src).pin_memory()
+    h_dst = torch.from_numpy(dst).pin_memory()
+    h_R = torch.empty((pairs, 3, 3), dtype=torch.float32).pin_memory()
+    h_t = torch.empty((pairs, 3), dtype=torch.float32).pin_memory()
+    h_i = torch.empty(pairs, dtype=torch.int32).pin_memory()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device():
+        reg.register_packed_ptr(d_src.data_ptr(), d_dst.data_ptr(), offsets, d_R.data_ptr(), d_t.data_ptr(),
+                                d_i.data_ptr(), _abi.LOC_DEVICE)
+
+    def step_host():
+        reg.register_packed_ptr(h_src.data_ptr(), h_dst.data_ptr(), offsets, h_R.data_ptr(), h_t.data_ptr(),
+                                h_i.data_ptr(), _abi.LOC_HOST)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up (also grows the workspace / key pool to steady state) ----
+    for _ in range(args.warmup):
+        step_device()
+        torch.cuda.synchronize(dev)
+        status = reg.get("last_status")
+        if status != 0:  # key pool grew: this step's results are void, the next one is clean
+            continue
+    step_device()
+    torch.cuda.synchronize(dev)
+    assert reg.get("last_status") == 0, "workspace did not reach steady state during warm-up"
+    # sanity: the device-resident results recover the ground-truth poses
+    R_chk, t_chk = d_R.cpu().numpy(), d_t.cpu().numpy()
+    ok = 0
+    for b in range(pairs):
+        ang, dt_ = synth.pose_error(R_chk[b], t_chk[b], ps[b].R_gt, ps[b].t_gt)
+        ok += ang < np.deg2rad(5.0) and dt_ < 0.15
+    recall = ok / pairs
+
+    # ---- timed region 1: device-resident (value) ----
+    reg.set("stage_timing", 1)
+    launches0 = reg.get("launches")
+    sampler = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # evict L2 between steps (not timed)
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+    barrier()
+    wall_dev = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    assert reg.get("last_status") == 0
+    launches = reg.get("launches") - launches0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    stage_us = {s: reg.get(f"stage_us_{s}") for s in STAGES}
+    stage_calls = {s: reg.get(f"stage_calls_{s}") for s in STAGES}
+    reg.set("stage_timing", 0)
+    total_ms = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * pairs * args.steps / (total_ms * 1e-3)
+
+    # ---- timed region 2: end to end through the host-buffer C-ABI call (e2e) ----
+    step_host()  # warm the host path (arena regrows once: it now also holds the input copy)
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()  # H2D (pinned) -> pipeline -> D2H -> stream sync, all inside the call
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * pairs * args.steps / float(e2e_s.item())
+    # host-path results equal the device-resident ones
+    same = bool((h_R.numpy() == R_chk).all() and (h_t.numpy() == t_chk).all())
+
+    # ---- roofline of the dominant kernel (triangle counting), from the live stage timers ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak_gbs, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    reg.set("keep_debug", 1)
+    small = min(pairs, 8)
+    reg.register_packed(src[: small * N], dst[: small * N], offsets[: small + 1])
+    E_mean = float(np.mean([int(reg.debug(b, _abi.DBG_NUM_EDGES)[0]) for b in range(small)]))
+    reg.set("keep_debug", 0)
+    npad = (N + 127) // 128 * 128
+    stride = npad // 32
+    # algorithmic bytes per pair of S2: read A once, write one 8-byte key per edge,
+    # read-modify-write the per-node sums and the histogram once
+    tri_bytes_pair = npad * stride * 4 + E_mean * 8 + npad * 8 * 2 + 4096 * 4 * 2
+    tri_calls = max(1, stage_calls["triangles"])
+    tri_us = stage_us["triangles"] / tri_calls                 # average launch duration
+    pairs_per_launch = pairs * args.steps / tri_calls
+    achieved_gbs = tri_bytes_pair * pairs_per_launch / (tri_us * 1e-6) / 1e9
+    wordops = E_mean * stride * pairs_per_launch               # AND+POPC on 32-bit words
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    popc_peak = 16 * 148 * sm_mhz * 1e6                        # nominal 16 POPC/clk/SM
+    roofline = {
+        "kernel": "triangles_kernel<5> (S2, POPC bitset)", "bound": "hbm", "achieved": achieved_gbs,
+        "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "launch_us": tri_us, "pairs_per_launch": pairs_per_launch, "algorithmic_bytes_per_pair": tri_bytes_pair,
+        "note": "S2 is bound by POPC/ALU issue, not HBM (arithmetic intensity ~ 40 word-ops/B): the HBM "
+                "fraction is small by construction; the issue-side figure is in `issue`",
+        "issue": {"wordops_per_s": wordops / (tri_us * 1e-6), "nominal_popc_peak_per_s": popc_peak,
+                  "frac": wordops / (tri_us * 1e-6) / popc_peak, "edges_per_pair": E_mean, "words_per_row": stride},
+        "stage_share": {s: stage_us[s] / max(1, sum(stage_us.values())) for s in STAGES},
+        "stage_us_per_step": {s: stage_us[s] / args.steps for s in STAGES},
+    }
+
+    # ---- CPU baseline: the from-paper oracle on this box's host cores (rank 0, N = 1 only) ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n1, nall = min(pairs, 24), min(pairs, 64)
+        s1, _, res1 = time_oracle(load_oracle(omp=False), ps[:n1], cfg)
+        sall, threads, _ = time_oracle(load_oracle(omp=True), ps[:nall], cfg)
+        agree = bool((res1.inliers == d_i.cpu().numpy()[:n1]).all())
+        cpu_baseline = {
+            "value": 1.0 / s1, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first {n1} of the {pairs} pairs, from-paper C++ oracle, 1 thread ({s1:.3f} s/pair); "
+                      "the upstream repo has no code to run",
+            "all_cores": {"value": 1.0 / sall, "cores": int(threads), "sample": f"first {nall} pairs, OpenMP build"},
+            "host_cpus": os.cpu_count(), "inlier_counts_match_gpu": agree,
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{WORKLOAD}: {pairs} pairs/GPU x N={N}, 5% inliers, tau_c={cfg['tau']} "
+                            "(BASELINE.json configs[1])",
+                "pairs_per_gpu": pairs, "N": N, "K_e": int(reg.params.num_edges),
+                "apex_per_edge": int(reg.params.apex_per_edge), "hypotheses_per_pair": K,
+                "parallelism": f"{world} x independent batches, no collective",
+                "l2": "512 MB flush write between timed steps; per-step workspace (~3 GB) also exceeds the 126 MB L2",
+            },
+            "hypotheses_per_sec": value * K,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(src.nbytes + dst.nbytes),
+                    "d2h_bytes_per_step": int(pairs * (36 + 12 + 4)), "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "recall_vs_ground_truth": recall, "ms_steps": ms_steps, "wall_s_device_region": wall_dev,
+            "workspace_bytes": reg.get("workspace_bytes"), "retries": reg.get("retries"),
+        }
+        print(json.dumps(line))
+    reg.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

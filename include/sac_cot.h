@@ -86,17 +86,24 @@ SAC_COT_API int sac_cot_register(const float* src, const float* dst, int32_t N,
 typedef struct sac_cot_ctx sac_cot_ctx;
 
 /* device: CUDA ordinal (ignored by the oracle).  stream: a cudaStream_t on that device on
- * which every kernel and copy of this ctx is enqueued, or NULL for a private stream.
- * Passing the caller's stream lets the caller bracket the work with its own events. */
+ * which every kernel and copy of this ctx is enqueued, or NULL for a private non-blocking
+ * stream.  Passing the caller's stream lets the caller bracket the work with its own events;
+ * to name the legacy default stream (handle 0, e.g. torch's default stream) pass
+ * cudaStreamLegacy ((void*)0x1), since NULL means "private". */
 SAC_COT_API int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream);
 SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
 
 /* Tunables/inspection by name; unknown names return SAC_COT_E_WHICH.
  *   set: "keep_debug" (0/1: retain per-pair intermediates for sac_cot_debug_get; forces
  *        chunk = whole batch), "chunk_pairs" (pairs per kernel wave, 0 = auto),
- *        "triangle_path" (0 = POPC bitset, 1 = tensor-core dense; GPU only)
+ *        "triangle_path" (0 = POPC bitset, 1 = tensor-core dense; GPU only),
+ *        "stage_timing" (0/1: bracket every pipeline stage with CUDA events on the ctx
+ *        stream; setting it also clears the accumulated times; GPU only)
  *   get: "launches" (kernels launched since ctx creation), "workspace_bytes",
- *        "device", "sm_count", "retries" (workspace-growth re-runs)                       */
+ *        "device", "sm_count", "retries" (workspace-growth re-runs),
+ *        "last_status" (deferred status of the latest SAC_COT_LOC_DEVICE call; synchronises),
+ *        "stage_us_<s>" / "stage_calls_<s>" with <s> in pack, graph, scan, triangles, select,
+ *        apex, kabsch, score, finalize: accumulated device microseconds / launches      */
 SAC_COT_API int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value);
 SAC_COT_API int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value);
 

@@ -69,7 +69,9 @@ class Registrar:
     def __init__(self, lib: C.CDLL | None = None, device: int = 0, stream: int | None = None, **params):
         self.lib = lib if lib is not None else load_library()
         self._ctx = C.c_void_p()
-        rc = self.lib.sac_cot_ctx_create(C.byref(self._ctx), int(device), C.c_void_p(stream or 0))
+        # stream: None -> private stream; 0 (torch's legacy default stream) -> cudaStreamLegacy handle 0x1
+        handle = 0 if stream is None else (1 if int(stream) == 0 else int(stream))
+        rc = self.lib.sac_cot_ctx_create(C.byref(self._ctx), int(device), C.c_void_p(handle))
         if rc != _abi.OK:
             self._ctx = C.c_void_p()
             raise SacCotError(rc, "sac_cot_ctx_create", self.lib)

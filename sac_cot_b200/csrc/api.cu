@@ -39,12 +39,15 @@ struct Layout {
   int max_n = 0, max_npad = 0, max_nblk = 0, max_stride = 0;
   size_t sum_n = 0, sum_npad = 0;
   int Ke = 0, m = 0, K = 0;
-  // zero region (one memset): state | chunk | hist | t2
+  // zero region (one memset): state | chunk | hist | t2 | ucount
   PairDev* state = nullptr;
   ChunkDev* chunk = nullptr;
   uint32_t* hist = nullptr;
   unsigned long long* t2 = nullptr;
+  uint32_t* ucount = nullptr;  // edges per triangle work unit, [pairs][unit_pitch]
   size_t zero_bytes = 0;
+  uint32_t* ubase = nullptr;   // key offset per unit inside the pair's key slice
+  int unit_pitch = 0;
   // the rest
   PairDesc* desc = nullptr;
   float* in_src = nullptr;
@@ -79,6 +82,48 @@ size_t pair_bytes_estimate(int N, int K, int Ke) {
          static_cast<size_t>(Ke) * 16 + static_cast<size_t>(kTieCap) * 8 + kHistBins * 4 + 4096;
 }
 
+// Optional per-stage timing with CUDA events on the ctx stream ("stage_timing" knob).
+enum Stage { ST_PACK = 0, ST_GRAPH, ST_SCAN, ST_TRIANGLES, ST_SELECT, ST_APEX, ST_KABSCH, ST_SCORE, ST_FINALIZE, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"pack", "graph", "scan", "triangles", "select", "apex", "kabsch", "score", "finalize"};
+
+struct StageTimer {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int stage; cudaEvent_t a, b; };
+  std::vector<Rec> pending;
+  double acc_ms[ST_COUNT] = {0};
+  int64_t calls[ST_COUNT] = {0};
+
+  cudaEvent_t next() {
+    if (used == pool.size()) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void resolve() {
+    for (const Rec& r : pending) {
+      float ms = 0.0f;
+      if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+        acc_ms[r.stage] += ms;
+        ++calls[r.stage];
+      }
+    }
+    pending.clear();
+    used = 0;
+  }
+  void reset() {
+    resolve();
+    for (int k = 0; k < ST_COUNT; ++k) { acc_ms[k] = 0; calls[k] = 0; }
+  }
+  void destroy() {
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pool.clear();
+  }
+};
+
 }  // namespace
 
 struct sac_cot_ctx {
@@ -96,9 +141,10 @@ struct sac_cot_ctx {
   size_t arena_bytes = 0;
   unsigned long long* keys = nullptr;
   unsigned long long key_cap = 0;
-  ChunkDev* h_chunk = nullptr;  // pinned read-back of the chunk header
-  cudaEvent_t chunk_event = nullptr;
-  bool chunk_event_pending = false;
+  ChunkDev* h_chunk = nullptr;    // pinned read-back of the chunk header (host-location calls)
+  StickyDev* d_sticky = nullptr;  // device: overflow record that survives across calls
+  StickyDev* h_sticky = nullptr;  // pinned mirror, refreshed asynchronously after device-location calls
+  uint32_t seen_overflows = 0;
 
   // description of what is resident in the workspace (for debug_get / sharded phases)
   Layout lay;
@@ -111,6 +157,7 @@ struct sac_cot_ctx {
 
   // host staging for the pointer-array batch entry point
   std::vector<float> stage_src, stage_dst;
+  StageTimer timer;
 };
 
 namespace {
@@ -173,7 +220,10 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_chunk = take(sizeof(ChunkDev));
   const size_t o_hist = take(sizeof(uint32_t) * kHistBins * pairs);
   const size_t o_t2 = take(sizeof(unsigned long long) * node);
+  L.unit_pitch = static_cast<int>(unit_count(static_cast<unsigned int>(L.max_nblk)));
+  const size_t o_ucount = take(sizeof(uint32_t) * L.unit_pitch * pairs);
   L.zero_bytes = off;
+  const size_t o_ubase = take(sizeof(uint32_t) * L.unit_pitch * pairs);
   const size_t o_desc = take(sizeof(PairDesc) * pairs);
   const size_t o_insrc = need_input_copy ? take(sizeof(float) * 3 * pt) : 0;
   const size_t o_indst = need_input_copy ? take(sizeof(float) * 3 * pt) : 0;
@@ -196,6 +246,8 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.chunk = reinterpret_cast<ChunkDev*>(o_chunk);
   L.hist = reinterpret_cast<uint32_t*>(o_hist);
   L.t2 = reinterpret_cast<unsigned long long*>(o_t2);
+  L.ucount = reinterpret_cast<uint32_t*>(o_ucount);
+  L.ubase = reinterpret_cast<uint32_t*>(o_ubase);
   L.desc = reinterpret_cast<PairDesc*>(o_desc);
   L.in_src = need_input_copy ? reinterpret_cast<float*>(o_insrc) : nullptr;
   L.in_dst = need_input_copy ? reinterpret_cast<float*>(o_indst) : nullptr;
@@ -224,6 +276,8 @@ void bind(Layout& L, unsigned char* base, bool has_input) {
   L.chunk = rebase(L.chunk, base);
   L.hist = rebase(L.hist, base);
   L.t2 = rebase(L.t2, base);
+  L.ucount = rebase(L.ucount, base);
+  L.ubase = rebase(L.ubase, base);
   L.desc = rebase(L.desc, base);
   L.in_src = rebase(L.in_src, base, has_input);
   L.in_dst = rebase(L.in_dst, base, has_input);
@@ -280,18 +334,20 @@ int ensure_keys(sac_cot_ctx* ctx, unsigned long long cap) {
   return 0;
 }
 
-// Resolves the status of an earlier device-location call (key-pool overflow is only known
-// once its chunk header has been copied back).
-int resolve_pending(sac_cot_ctx* ctx) {
-  if (!ctx->chunk_event_pending) return 0;
-  CU_TRY(cudaEventSynchronize(ctx->chunk_event));
-  ctx->chunk_event_pending = false;
-  if (ctx->h_chunk->overflow) {
+// Picks up key-pool overflows of earlier device-location calls from the pinned mirror of the
+// sticky record.  block = false never waits: it sees whatever has been copied back so far (the
+// record only grows, so a stale view is merely late).  On a new overflow the pool is grown to
+// the recorded demand, so the caller's next call succeeds; the overflowed call's outputs are
+// void and "last_status" reports SAC_COT_E_NOMEM for it.
+int resolve_pending(sac_cot_ctx* ctx, bool block) {
+  if (block) CU_TRY(cudaStreamSynchronize(ctx->stream));
+  const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&ctx->h_sticky->overflow_count);
+  if (count != ctx->seen_overflows) {
+    ctx->seen_overflows = count;
     ctx->deferred_status = SAC_COT_E_NOMEM;
-    const unsigned long long want = ctx->h_chunk->total_edges + ctx->h_chunk->total_edges / 8 + 1024;
+    const unsigned long long demand = *reinterpret_cast<volatile unsigned long long*>(&ctx->h_sticky->max_total_edges);
     ++ctx->retries;
-    const int rc = ensure_keys(ctx, want);
-    if (rc) return rc;
+    if (int rc = ensure_keys(ctx, demand + demand / 8 + 1024)) return rc;
   }
   return 0;
 }
@@ -304,21 +360,43 @@ int enqueue_pipeline(sac_cot_ctx* ctx, const float* d_src, const float* d_dst, f
   Layout& L = ctx->lay;
   const sac_cot_params& prm = ctx->prm;
   LaunchCtx lc{ctx->stream, ctx->sm_count};
+  StageTimer& tm = ctx->timer;
+  if (tm.enabled && tm.pending.size() > 8192) tm.resolve();
+  cudaEvent_t ev_prev = nullptr;
+  auto mark = [&](int stage) {  // closes `stage`: records an event and pairs it with the previous one
+    if (!tm.enabled) return;
+    cudaEvent_t e = tm.next();
+    if (!e) return;
+    cudaEventRecord(e, ctx->stream);
+    if (stage >= 0 && ev_prev) tm.pending.push_back({stage, ev_prev, e});
+    ev_prev = e;
+  };
   CU_TRY(cudaMemsetAsync(L.state, 0, L.zero_bytes, ctx->stream));
+  mark(-1);
   KL_TRY(launch_pack_soa(lc, L.desc, L.pairs, L.max_npad, d_src, d_dst, L.soa));
-  KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.state, prm.tau_compat));
-  KL_TRY(launch_key_scan(lc, L.pairs, L.state, L.chunk, ctx->key_cap));
-  KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ctx->keys, L.hist,
-                          L.t2, rank, world));
+  mark(ST_PACK);
+  KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.ucount, L.unit_pitch, prm.tau_compat));
+  mark(ST_GRAPH);
+  KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world));
+  KL_TRY(launch_key_scan(lc, L.pairs, L.state, L.chunk, ctx->d_sticky, ctx->key_cap));
+  mark(ST_SCAN);
+  KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ctx->keys, L.ubase,
+                          L.unit_pitch, L.hist, L.t2, rank, world));
+  mark(ST_TRIANGLES);
   KL_TRY(launch_select_edges(lc, L.pairs, L.state, L.chunk, ctx->keys, L.hist, L.sel, L.tie, L.top, L.Ke));
+  mark(ST_SELECT);
   if (stop_after_edges) return 0;
   const float tau2 = prm.tau_inlier * prm.tau_inlier;
   KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
+  mark(ST_APEX);
   KL_TRY(launch_kabsch(lc, L.desc, L.pairs, L.soa, L.tri, L.rt, L.K));
+  mark(ST_KABSCH);
   KL_TRY(launch_score(lc, L.desc, L.pairs, L.max_n, L.soa, L.tri, L.rt, L.hyp_key, L.state, tau2, L.K, 0, L.K,
                       prm.score_mode));
+  mark(ST_SCORE);
   KL_TRY(launch_finalize(lc, L.desc, L.pairs, L.soa, L.rt, L.state, nullptr, L.mask, dR, dT, dInl, tau2, L.K,
                          prm.refit));
+  mark(ST_FINALIZE);
   return 0;
 }
 
@@ -354,13 +432,12 @@ int run_chunk(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_
       dR = R + 9 * static_cast<size_t>(b0); dT = t + 3 * static_cast<size_t>(b0); dInl = inliers + b0;
     }
     if (int rc = enqueue_pipeline(ctx, d_src, d_dst, dR, dT, dInl, 0, 1, false)) return rc;
-    CU_TRY(cudaMemcpyAsync(ctx->h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ctx->stream));
     if (!host) {
-      CU_TRY(cudaEventRecord(ctx->chunk_event, ctx->stream));
-      ctx->chunk_event_pending = true;
+      CU_TRY(cudaMemcpyAsync(ctx->h_sticky, ctx->d_sticky, sizeof(StickyDev), cudaMemcpyDeviceToHost, ctx->stream));
       ctx->ws_valid = true;
-      return 0;  // enqueue only; overflow (if any) surfaces through resolve_pending()
+      return 0;  // enqueue only; an overflow (if any) surfaces through resolve_pending()
     }
+    CU_TRY(cudaMemcpyAsync(ctx->h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaMemcpyAsync(R + 9 * static_cast<size_t>(b0), L.outR, sizeof(float) * 9 * pairs, cudaMemcpyDeviceToHost,
                            ctx->stream));
     CU_TRY(cudaMemcpyAsync(t + 3 * static_cast<size_t>(b0), L.outT, sizeof(float) * 3 * pairs, cudaMemcpyDeviceToHost,
@@ -393,7 +470,7 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
   }
   if (B == 0) return SAC_COT_OK;
   CU_TRY(cudaSetDevice(ctx->device));
-  if (int rc = resolve_pending(ctx)) return rc;
+  if (int rc = resolve_pending(ctx, false)) return rc;
   // chunking: bounded workspace per wave of kernels (keep_debug keeps the whole batch resident)
   const int K = params->num_edges * params->apex_per_edge;
   int chunk = B;
@@ -457,16 +534,19 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (stream) {
-    ctx->stream = static_cast<cudaStream_t>(stream);
+    ctx->stream = static_cast<cudaStream_t>(stream);  // cudaStreamLegacy / cudaStreamPerThread handles work too
   } else {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return static_cast<int>(e); }
     ctx->own_stream = true;
   }
   cudaError_t e = cudaMallocHost(&ctx->h_chunk, sizeof(ChunkDev));
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->chunk_event, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_sticky, sizeof(StickyDev));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_sticky, sizeof(StickyDev));
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_sticky, 0, sizeof(StickyDev));
   if (e != cudaSuccess) { sac_cot_ctx_destroy(ctx); return static_cast<int>(e); }
   std::memset(ctx->h_chunk, 0, sizeof(ChunkDev));
+  std::memset(ctx->h_sticky, 0, sizeof(StickyDev));
   const int rc = triangles_configure();
   if (rc < 0) { sac_cot_ctx_destroy(ctx); return -rc; }
   *out = ctx;
@@ -480,7 +560,9 @@ int sac_cot_ctx_destroy(sac_cot_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->keys) cudaFree(ctx->keys);
   if (ctx->h_chunk) cudaFreeHost(ctx->h_chunk);
-  if (ctx->chunk_event) cudaEventDestroy(ctx->chunk_event);
+  if (ctx->h_sticky) cudaFreeHost(ctx->h_sticky);
+  if (ctx->d_sticky) cudaFree(ctx->d_sticky);
+  ctx->timer.destroy();
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SAC_COT_OK;
@@ -495,6 +577,12 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     return SAC_COT_OK;
   }
   if (!std::strcmp(name, "triangle_path")) return value == 0 ? SAC_COT_OK : SAC_COT_E_UNSUPPORTED;
+  if (!std::strcmp(name, "stage_timing")) {
+    cudaSetDevice(ctx->device);
+    ctx->timer.reset();
+    ctx->timer.enabled = value != 0;
+    return SAC_COT_OK;
+  }
   return SAC_COT_E_WHICH;
 }
 
@@ -509,10 +597,22 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
   if (!std::strcmp(name, "device")) { *value = ctx->device; return SAC_COT_OK; }
   if (!std::strcmp(name, "sm_count")) { *value = ctx->sm_count; return SAC_COT_OK; }
   if (!std::strcmp(name, "threads")) { *value = 0; return SAC_COT_OK; }
+  if (!std::strncmp(name, "stage_us_", 9) || !std::strncmp(name, "stage_calls_", 12)) {
+    const bool us = name[6] == 'u';
+    const char* stage = name + (us ? 9 : 12);
+    for (int k = 0; k < ST_COUNT; ++k)
+      if (!std::strcmp(stage, kStageNames[k])) {
+        cudaSetDevice(ctx->device);
+        ctx->timer.resolve();
+        *value = us ? static_cast<int64_t>(ctx->timer.acc_ms[k] * 1000.0 + 0.5) : ctx->timer.calls[k];
+        return SAC_COT_OK;
+      }
+    return SAC_COT_E_WHICH;
+  }
   if (!std::strcmp(name, "last_status")) {
     // status of the most recent device-location call; synchronises with it
     cudaSetDevice(ctx->device);
-    const int rc = resolve_pending(ctx);
+    const int rc = resolve_pending(ctx, true);
     *value = rc ? rc : ctx->deferred_status;
     ctx->deferred_status = 0;
     return SAC_COT_OK;
@@ -578,7 +678,7 @@ int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
   if (world < 1 || rank < 0 || rank >= world) return SAC_COT_E_SIZE;
   if (int rc = check_params(params)) return rc;
   CU_TRY(cudaSetDevice(ctx->device));
-  if (int rc = resolve_pending(ctx)) return rc;
+  if (int rc = resolve_pending(ctx, false)) return rc;
   ctx->sh_valid = false;
   try {
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -680,8 +780,7 @@ int sac_cot_debug_get(sac_cot_ctx* ctx, int32_t pair, int32_t which, void* out, 
   if (pair == -1) pair = 0;
   if (!(ctx->ws_valid || ctx->sh_valid) || pair < 0 || pair >= ctx->lay.pairs) return SAC_COT_E_WHICH;
   CU_TRY(cudaSetDevice(ctx->device));
-  if (int rc = resolve_pending(ctx)) return rc;
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  if (int rc = resolve_pending(ctx, true)) return rc;
   const Layout& L = ctx->lay;
   const PairDesc& d = ctx->descs[pair];
   PairDev st;

@@ -26,9 +26,9 @@ struct PairDesc {
 };
 
 struct PairDev {
-  unsigned long long num_edges;  // E, counted by the graph kernel
+  unsigned long long num_edges;  // evaluated edges (all of E unless sharded), from the unit scan
   unsigned long long key_base;   // offset of this pair's edge keys in the key pool (scan)
-  unsigned long long key_count;  // append cursor of the triangle kernel (ends == evaluated edges)
+  unsigned long long key_count;  // keys in this pair's slice of the pool (== num_edges)
   unsigned long long best_key;   // max hypothesis key
   uint32_t sel_count;            // keys appended to the selected list so far
   uint32_t tie_count;            // keys appended to the tie list so far
@@ -46,11 +46,19 @@ struct ChunkDev {
   uint32_t pad_;
 };
 
+// Survives across calls (never zeroed by the pipeline): lets device-location calls report a
+// key-pool overflow without a host synchronisation.
+struct StickyDev {
+  unsigned long long max_total_edges;  // largest chunk demand seen in an overflowing chunk
+  uint32_t overflow_count;             // number of chunks that overflowed so far
+  uint32_t pad_;
+};
+
 constexpr int kMaxEdges = 4096;     // == SAC_COT_MAX_EDGES
 constexpr int kMaxApex = 8;         // == SAC_COT_MAX_APEX
 constexpr int kHistBins = 4096;     // histogram of T >> 4
 constexpr int kTieCap = 16384;      // tie-list entries per pair
-constexpr int kTriJ = 128;          // J-block rows staged per triangle work unit
+constexpr int kTriJ = 128;          // columns per triangle work unit (unit = 128 columns x 256 rows)
 constexpr int kTriI = 256;          // rows of i per triangle work unit
 constexpr int kTriThreads = 512;
 constexpr int kTriMaxR = 11;        // max words per lane per row chunk (352 words)
@@ -106,6 +114,15 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 // Host launchers (one per kernel file).  Every launcher returns the number of kernels it
 // enqueued on `stream` (for the ctx "launches" counter) or a negative cudaError_t.
 // ------------------------------------------------------------------------------------------
+// Triangle work units: unit (jb, ic) = columns [128 jb, 128 jb + 128) x rows [256 ic, 256 ic + 256)
+// with ic <= jb/2 (only i < j matters).  unit id = unit_offset(jb) + ic; the oracle uses the same
+// numbering to assign edges to ranks in sharded mode (unit id % world).
+__host__ __device__ inline unsigned int unit_offset(unsigned int jb) {
+  const unsigned int h = jb >> 1;  // sum_{b<jb} (b/2+1) = h(h+1) for jb=2h, (h+1)^2 for jb=2h+1
+  return (jb & 1u) ? (h + 1) * (h + 1) : h * (h + 1);
+}
+__host__ __device__ inline unsigned int unit_count(unsigned int nblk) { return unit_offset(nblk); }
+
 struct LaunchCtx {
   cudaStream_t stream;
   int sm_count;
@@ -115,13 +132,17 @@ struct LaunchCtx {
 int launch_pack_soa(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const float* d_src,
                     const float* d_dst, float* d_soa);
 int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, const float* d_soa,
-                 uint32_t* d_adj, PairDev* d_state, float tau);
-int launch_key_scan(const LaunchCtx& lc, int pairs, PairDev* d_state, ChunkDev* d_chunk, unsigned long long key_cap);
+                 uint32_t* d_adj, uint32_t* d_ucount, int unit_pitch, float tau);
+int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state,
+                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world);
+int launch_key_scan(const LaunchCtx& lc, int pairs, PairDev* d_state, ChunkDev* d_chunk, StickyDev* d_sticky,
+                    unsigned long long key_cap);
 
 // kernels_triangles.cu — S2 triangle counts (POPC bitset path)
 int launch_triangles(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, int max_stride,
                      const uint32_t* d_adj, PairDev* d_state, const ChunkDev* d_chunk, unsigned long long* d_keys,
-                     uint32_t* d_hist, unsigned long long* d_t2, int rank, int world);
+                     const uint32_t* d_ubase, int unit_pitch, uint32_t* d_hist, unsigned long long* d_t2, int rank,
+                     int world);
 int triangles_configure();  // opt-in dynamic shared memory; call once per device
 
 // kernels_select.cu — S3 edge ranking + apex selection

@@ -73,7 +73,7 @@ __device__ __forceinline__ bool compat_pred(float sxi, float syi, float szi, flo
 
 __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__ descs,
                                                     const float* __restrict__ soa, uint32_t* __restrict__ adj,
-                                                    PairDev* __restrict__ state, float tau) {
+                                                    uint32_t* __restrict__ ucount, int unit_pitch, float tau) {
   const PairDesc d = descs[blockIdx.y];
   const int ntiles = d.nblk * (d.nblk + 1) / 2;
   const int tile = blockIdx.x;
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
   __shared__ __align__(128) float cs[6][128];
   __shared__ __align__(16) uint32_t tsm[128][4];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ unsigned int wcnt[4];
 
   const int r = threadIdx.x;
   const int lane = r & 31, warp = r >> 5;
@@ -163,15 +164,83 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
     *reinterpret_cast<uint4*>(adjp + static_cast<size_t>(J0 + r) * d.stride + I0 / 32) = tw;
   }
 
-  // edge total of the pair (upper triangle only)
+  // edges (i<j) of this tile, added to the count of its triangle work unit (J, I/2): the unit
+  // scan turns these into exact key-pool offsets, so the triangle kernel needs no reservation
   cnt = __reduce_add_sync(0xffffffffu, cnt);
-  if (lane == 0 && cnt) atomicAdd(&state[blockIdx.y].num_edges, static_cast<unsigned long long>(cnt));
+  if (lane == 0) wcnt[warp] = cnt;
+  __syncthreads();
+  if (r == 0) {
+    const unsigned int total = wcnt[0] + wcnt[1] + wcnt[2] + wcnt[3];
+    if (total)
+      atomicAdd(&ucount[static_cast<size_t>(blockIdx.y) * unit_pitch + unit_offset(static_cast<unsigned int>(J)) + (I >> 1)],
+                total);
+  }
 }
 
 int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, const float* d_soa,
-                 uint32_t* d_adj, PairDev* d_state, float tau) {
+                 uint32_t* d_adj, uint32_t* d_ucount, int unit_pitch, float tau) {
   dim3 grid(max_nblk * (max_nblk + 1) / 2, pairs);
-  graph_kernel<<<grid, 128, 0, lc.stream>>>(d_desc, d_soa, d_adj, d_state, tau);
+  graph_kernel<<<grid, 128, 0, lc.stream>>>(d_desc, d_soa, d_adj, d_ucount, unit_pitch, tau);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+// ------------------------------------------------------------------------------------------
+// Per pair: exclusive scan of the unit edge counts over the units this rank owns (all of them
+// unless sharded) -> ubase[unit] = offset of the unit's keys inside the pair's key slice, and
+// the pair's evaluated-edge total.  One CTA per pair.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) unit_scan_kernel(const PairDesc* __restrict__ descs,
+                                                         PairDev* __restrict__ state,
+                                                         const uint32_t* __restrict__ ucount,
+                                                         uint32_t* __restrict__ ubase, int unit_pitch, int rank,
+                                                         int world) {
+  const int pair = blockIdx.x;
+  const unsigned int U = unit_count(static_cast<unsigned int>(descs[pair].nblk));
+  const uint32_t* cnt = ucount + static_cast<size_t>(pair) * unit_pitch;
+  uint32_t* out = ubase + static_cast<size_t>(pair) * unit_pitch;
+  __shared__ unsigned int wsum[32];
+  __shared__ unsigned long long carry;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) carry = 0;
+  __syncthreads();
+  for (unsigned int u0 = 0; u0 < U; u0 += 1024) {
+    const unsigned int u = u0 + t;
+    const bool owned = u < U && (world <= 1 || (u % static_cast<unsigned int>(world)) == static_cast<unsigned int>(rank));
+    const unsigned int v = owned ? cnt[u] : 0u;
+    unsigned int incl = v;  // warp inclusive scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned int w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int n = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += n;
+      }
+      wsum[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned long long base = carry + (warp ? wsum[warp - 1] : 0u);
+    if (u < U) out[u] = static_cast<uint32_t>(base + incl - v);
+    __syncthreads();
+    if (t == 1023) carry = base + incl;
+    __syncthreads();
+  }
+  if (t == 0) {
+    state[pair].num_edges = carry;
+    state[pair].key_count = carry;
+  }
+}
+
+int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state,
+                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world) {
+  unit_scan_kernel<<<pairs, 1024, 0, lc.stream>>>(d_desc, d_state, d_ucount, d_ubase, unit_pitch, rank, world);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }
@@ -182,7 +251,8 @@ int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max
 // and the host grows the pool and re-runs the chunk.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) key_scan_kernel(int pairs, PairDev* __restrict__ state,
-                                                        ChunkDev* __restrict__ chunk, unsigned long long key_cap) {
+                                                        ChunkDev* __restrict__ chunk, StickyDev* __restrict__ sticky,
+                                                        unsigned long long key_cap) {
   __shared__ unsigned long long part[1024];
   __shared__ unsigned long long carry;
   const int t = threadIdx.x;
@@ -207,11 +277,16 @@ __global__ void __launch_bounds__(1024) key_scan_kernel(int pairs, PairDev* __re
   if (t == 0) {
     chunk->total_edges = carry;
     chunk->overflow = carry > key_cap ? 1u : 0u;
+    if (carry > key_cap) {
+      atomicMax(&sticky->max_total_edges, carry);
+      atomicAdd(&sticky->overflow_count, 1u);
+    }
   }
 }
 
-int launch_key_scan(const LaunchCtx& lc, int pairs, PairDev* d_state, ChunkDev* d_chunk, unsigned long long key_cap) {
-  key_scan_kernel<<<1, 1024, 0, lc.stream>>>(pairs, d_state, d_chunk, key_cap);
+int launch_key_scan(const LaunchCtx& lc, int pairs, PairDev* d_state, ChunkDev* d_chunk, StickyDev* d_sticky,
+                    unsigned long long key_cap) {
+  key_scan_kernel<<<1, 1024, 0, lc.stream>>>(pairs, d_state, d_chunk, d_sticky, key_cap);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }
