@@ -150,7 +150,6 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
   const int jrows = min(JB, d.Npad - J0);                          // staged rows (128 or 256)
 
   constexpr int PITCH = 32 * R;
-  constexpr int NWARP = THREADS / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw);                 // [JB][PITCH]
   uint32_t* hist_s = rows + JB * PITCH;                                   // [4096]
@@ -185,8 +184,12 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
   const int row_end = min(d.N, J0 + jrows - 1);  // rows i >= row_end have no neighbour j > i in the block
 
   // ---- software pipeline: the next row visit is fetched while the current one is processed ----
+  // Edge bits travel one byte per lane: lane l holds the bits of columns J0+8l .. J0+8l+7
+  // (JB = 256 -> 32 bytes, JB = 128 -> lanes 0..15).
+  const uint32_t unit0 = unit_offset(jb0), unit1 = NB == 2 ? unit_offset(jb0 + 1) : 0u;
+  const bool sub1 = NB == 2 && jrows > 128;  // second 128-column sub-block exists
   int i_next;
-  EdgeBits<NB> eb_next;
+  uint32_t byte_next = 0;
   LaneWords<R> ri_next;
   uint32_t ub_next[NB];
   auto fetch = [&]() {
@@ -195,11 +198,10 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
     i_next = __shfl_sync(0xffffffffu, rr, 0);
     if (i_next < row_end) {
       const uint32_t* rowp = adjp + static_cast<size_t>(i_next) * stride;
-      eb_next.load(rowp + J0 / 32, jrows / 128);
+      byte_next = lane < jrows / 8 ? reinterpret_cast<const uint8_t*>(rowp + J0 / 32)[lane] : 0u;
       ri_next.load_global(rowp, lane, stride);
-#pragma unroll
-      for (int s = 0; s < NB; ++s)
-        ub_next[s] = s < jrows / 128 ? ubp[unit_offset(jb0 + s) + (static_cast<unsigned int>(i_next) >> 8)] : 0u;
+      ub_next[0] = ubp[unit0 + (static_cast<unsigned int>(i_next) >> 8)];
+      if (NB == 2) ub_next[NB - 1] = sub1 ? ubp[unit1 + (static_cast<unsigned int>(i_next) >> 8)] : 0u;
     }
   };
   fetch();
@@ -207,36 +209,53 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
 
   while (i_next < row_end) {
     const int i = i_next;
-    EdgeBits<NB> eb = eb_next;
+    uint32_t bits = byte_next;
     const LaneWords<R> ri = ri_next;
     uint32_t ub[NB];
 #pragma unroll
     for (int s = 0; s < NB; ++s) ub[s] = ub_next[s];
     fetch();
 
-    eb.restrict_to(i, J0, jb0, rank, world);
-    int ns[NB], n = 0;
+    if (i >= J0) {  // diagonal region: keep only columns j > i
+      const int li = i - J0;
+      if (8 * lane + 7 <= li) bits = 0u;
+      else if (8 * lane <= li) bits &= (0xFFu << ((li & 7) + 1)) & 0xFFu;
+    }
+    if (world > 1) {  // sharded: keep only the sub-blocks whose unit this rank owns
+      const uint32_t unit = ((NB == 2 && lane >= 16) ? unit1 : unit0) + (static_cast<unsigned int>(i) >> 8);
+      if ((unit % static_cast<unsigned int>(world)) != static_cast<unsigned int>(rank)) bits = 0u;
+    }
+    // ordinal of each lane's first edge: inclusive warp scan of the per-byte counts
+    const int cnt = __popc(bits);
+    int incl = cnt;
 #pragma unroll
-    for (int s = 0; s < NB; ++s) { ns[s] = eb.count(s); n += ns[s]; }
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int n = __shfl_sync(0xffffffffu, incl, 31);
     if (n == 0) continue;
+    const int n0 = NB == 2 ? __shfl_sync(0xffffffffu, incl, 15) : n;  // edges in the first sub-block
 
     // sub-range of each unit's key region for this row visit (lane 0 asks the unit cursors)
     uint32_t pos[NB];
-#pragma unroll
-    for (int s = 0; s < NB; ++s) {
-      uint32_t off = 0;
-      if (lane == 0 && ns[s]) off = atomicAdd(&cur[s * 256 + (i >> 8)], static_cast<uint32_t>(ns[s]));
-      pos[s] = ub[s] + off;  // valid in lane 0; broadcast below
+    {
+      uint32_t off0 = 0, off1 = 0;
+      if (lane == 0) {
+        if (n0) off0 = atomicAdd(&cur[i >> 8], static_cast<uint32_t>(n0));
+        if (NB == 2 && n > n0) off1 = atomicAdd(&cur[256 + (i >> 8)], static_cast<uint32_t>(n - n0));
+      }
+      pos[0] = ub[0] + off0;
+      if (NB == 2) pos[NB - 1] = ub[NB - 1] + off1;
     }
     // edge columns in ascending order -> elist
     __syncwarp();  // the previous row's elist has been consumed by every lane
     {
-      const uint32_t lt = (1u << lane) - 1u;
-      int before = 0;
-#pragma unroll
-      for (int k = 0; k < 4 * NB; ++k) {
-        if ((eb.w[k] >> lane) & 1u) elist[before + __popc(eb.w[k] & lt)] = static_cast<uint8_t>(k * 32 + lane);
-        before += __popc(eb.w[k]);
+      int o = incl - cnt;
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        elist[o++] = static_cast<uint8_t>(8 * lane + b);
       }
     }
     __syncwarp();
@@ -245,24 +264,25 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
 
     const unsigned long long ikey = static_cast<unsigned long long>(0xFFFFu - static_cast<unsigned int>(i)) << 16;
     const unsigned int jkey0 = 0xFFFFu - static_cast<unsigned int>(J0);  // (0xFFFF - j) = jkey0 - jl
-    unsigned int myT = 0, myJ = 0, tsum = 0;
-    auto flush = [&](int q0, int cnt) {  // bookkeeping for up to 32 edges, one per lane
-      if (lane < cnt) {
+    unsigned int myT = 0, tsum = 0;
+    auto flush = [&](int q0, int cntq) {  // bookkeeping for up to 32 edges, one per lane
+      if (lane < cntq) {
         const int q = q0 + lane;
+        const unsigned int myJ = elist[q];
         uint32_t at = pos[0] + static_cast<uint32_t>(q);
-        if (NB == 2 && q >= ns[0]) at = pos[NB - 1] + static_cast<uint32_t>(q - ns[0]);
+        if (NB == 2 && q >= n0) at = pos[NB - 1] + static_cast<uint32_t>(q - n0);
         keyp[at] = (static_cast<unsigned long long>(myT) << 32) | ikey | static_cast<unsigned long long>(jkey0 - myJ);
         atomicAdd(&hist_s[myT >> 4], 1u);
         atomicAdd(&tJ[myJ], myT);
         tsum += myT;
       }
     };
-#pragma unroll 2
+#pragma unroll 4
     for (int q = 0; q < n; ++q) {
       const int jl = elist[q];
       const int s = ri.and_popc(rows + jl * PITCH, lane);
       const unsigned int T = static_cast<unsigned int>(__reduce_add_sync(0xffffffffu, s));
-      if (lane == (q & 31)) { myT = T; myJ = static_cast<unsigned int>(jl); }
+      if (lane == (q & 31)) myT = T;
       if ((q & 31) == 31) flush(q - 31, 32);
     }
     if (n & 31) flush(n & ~31, n & 31);
