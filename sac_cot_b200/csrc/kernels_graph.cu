@@ -2,10 +2,11 @@
 // compatibility graph), plus the tiny per-chunk key-pool scan.
 //
 // S1 arithmetic contract (bit-exact against the oracle): every fp32 operation is an
-// individually rounded IEEE op issued through __f*_rn intrinsics, which the compiler never
-// contracts into FMAs (equivalent to -fmad=false on this kernel), in the order
+// individually rounded IEEE op (explicit .rn PTX / __f*_rn intrinsics, never contracted into
+// FMAs: equivalent to -fmad=false on this kernel), in the order
 //   a=sx_i-sx_j; b=..; c=..; s2=(a*a+b*b)+c*c; ls=sqrt(s2); (same for dst -> ld);
-//   A_ij = |ls-ld| < tau_c.
+//   A_ij = |ls-ld| < tau_c
+// where the final decision is taken by an exact sqrt-free filter with a literal fallback (below).
 // Only tiles on or above the diagonal are evaluated; the mirrored tile is emitted from the
 // same predicate bits (negating a,b,c leaves the squares unchanged, so the mirrored entry is
 // bit-identical to evaluating it directly).
@@ -50,30 +51,85 @@ int launch_pack_soa(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int 
 // ------------------------------------------------------------------------------------------
 // S1: one CTA per 128 x 128 tile (I <= J) of one pair.  Thread r owns row I0+r: its point lives
 // in registers, the 128 column points are staged in shared memory by six 512-byte bulk copies
-// (TMA, completion on an mbarrier) and read as warp-wide broadcasts.  Each thread builds the
-// four 32-bit words of its row with one predicate per pair and stores them as one 128-bit
-// word; the mirrored tile is produced with warp ballots, staged through shared memory, and
-// stored the same way.
+// (TMA, completion on an mbarrier) and read as warp-wide broadcasts, two columns per load.
+// Each thread builds the four 32-bit words of its row and stores them as one 128-bit word; the
+// mirrored tile is produced by a shuffle-based 32x32 bit transpose per warp, staged through
+// shared memory and stored the same way.
+//
+// Exact decision without square roots.  The specified predicate is
+//     P(x, y) = | RN(RN(sqrt x) - RN(sqrt y)) | < tau          x = s2, y = d2 (fp32, as above)
+// Evaluating it literally costs two sqrt.rn expansions (~20 instructions).  Instead the kernel
+// computes, in fp32 (u = 2^-24, every op individually rounded),
+//     S = x + y;  U = S - tau2f;  Q = U*U - 4*(x*y);  Theta = (S*S) * 2^-19
+// with tau2f = RN(tau*tau).  In real arithmetic  Q* = ((a-b)^2 - tau^2)((a+b)^2 - tau^2), a = sqrt x,
+// b = sqrt y, so for (a+b) > 2 tau its sign is the sign of |a-b| - tau.  Error analysis (DESIGN.md
+// "S1 exact filter"): if S > lo = max(4 tau2f, 2^-50) then |Q - Q*| <= 7.6u (x+y)^2, and whenever
+// the literal predicate could disagree with sign(|a-b| - tau) (rounding of the two square roots
+// and of their difference, at most 2.1u (a+b) in total) one has |Q*| <= 8.5u (x+y)^2.  Hence
+//     |Q| > Theta  (Theta >= 31.9u (x+y)^2)   ==>   P(x, y) == (Q < 0)          exactly.
+// Everything else — the ~1e-4 fraction of pairs inside the band, tiny/huge/NaN inputs, tau so
+// large that lo overflows — takes the literal sqrt.rn evaluation.  The result is bit-identical to
+// the oracle's for every input; tests/test_gpu_parity.py has adversarial near-threshold sets.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool compat_pred(float sxi, float syi, float szi, float dxi, float dyi, float dzi,
-                                            float sxj, float syj, float szj, float dxj, float dyj, float dzj,
-                                            float tau) {
-  const float a = __fsub_rn(sxi, sxj);
-  const float b = __fsub_rn(syi, syj);
-  const float c = __fsub_rn(szi, szj);
-  const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
-  const float ls = __fsqrt_rn(s2);
-  const float u = __fsub_rn(dxi, dxj);
-  const float v = __fsub_rn(dyi, dyj);
-  const float w = __fsub_rn(dzi, dzj);
-  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)), __fmul_rn(w, w));
-  const float ld = __fsqrt_rn(d2);
-  return fabsf(__fsub_rn(ls, ld)) < tau;
+typedef unsigned long long f32x2;  // two packed fp32 lanes (sm_100 FADD2 / FMUL2 / FFMA2)
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// (a*a + b*b) + c*c per packed lane with individually rounded operations
+__device__ __forceinline__ f32x2 sum_sq(f32x2 a, f32x2 b, f32x2 c) {
+  float aa0, aa1, bb0, bb1, cc0, cc1;
+  unpack2(mul2(a, a), aa0, aa1);
+  unpack2(mul2(b, b), bb0, bb1);
+  unpack2(mul2(c, c), cc0, cc1);
+  return pack2(__fadd_rn(__fadd_rn(aa0, bb0), cc0), __fadd_rn(__fadd_rn(aa1, bb1), cc1));
+}
+
+// literal evaluation of the specified predicate from the squared lengths
+__device__ __noinline__ bool compat_literal(float x, float y, float tau) {
+  return fabsf(__fsub_rn(__fsqrt_rn(x), __fsqrt_rn(y))) < tau;
+}
+
+// out[lane] bit r = in[r] bit lane, for the 32 lanes of a warp
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+    x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+  }
+  return x;
 }
 
 __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__ descs,
                                                     const float* __restrict__ soa, uint32_t* __restrict__ adj,
-                                                    uint32_t* __restrict__ ucount, int unit_pitch, float tau) {
+                                                    uint32_t* __restrict__ ucount, int unit_pitch, float tau,
+                                                    float tau2f, float lo) {
   const PairDesc d = descs[blockIdx.y];
   const int ntiles = d.nblk * (d.nblk + 1) / 2;
   const int tile = blockIdx.x;
@@ -104,25 +160,54 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
 #pragma unroll
     for (int c = 0; c < 6; ++c) bulk_g2s(&cs[c][0], base + static_cast<size_t>(c) * d.Npad + J0, 128 * sizeof(float), &bar);
   }
-  // own row point (coalesced), overlapped with the bulk copies
-  const float sxi = base[0 * static_cast<size_t>(d.Npad) + I0 + r];
-  const float syi = base[1 * static_cast<size_t>(d.Npad) + I0 + r];
-  const float szi = base[2 * static_cast<size_t>(d.Npad) + I0 + r];
-  const float dxi = base[3 * static_cast<size_t>(d.Npad) + I0 + r];
-  const float dyi = base[4 * static_cast<size_t>(d.Npad) + I0 + r];
-  const float dzi = base[5 * static_cast<size_t>(d.Npad) + I0 + r];
+  // own row point (coalesced), overlapped with the bulk copies; duplicated into both packed lanes
+  f32x2 ri[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const float v = base[static_cast<size_t>(c) * d.Npad + I0 + r];
+    ri[c] = pack2(v, v);
+  }
+  const f32x2 ntau2 = pack2(-tau2f, -tau2f);
+  const f32x2 m4 = pack2(-4.0f, -4.0f);
+  const f32x2 kth = pack2(1.9073486328125e-06f, 1.9073486328125e-06f);  // 2^-19
   mbar_wait(&bar, 0);
 
   uint32_t words[4];
 #pragma unroll
   for (int cw = 0; cw < 4; ++cw) {
     uint32_t wbits = 0;
-#pragma unroll 8
-    for (int b = 0; b < 32; ++b) {
+#pragma unroll 4
+    for (int b = 0; b < 32; b += 2) {
       const int c = cw * 32 + b;
-      const bool p = compat_pred(sxi, syi, szi, dxi, dyi, dzi, cs[0][c], cs[1][c], cs[2][c], cs[3][c], cs[4][c],
-                                 cs[5][c], tau);
-      wbits |= (p ? 1u : 0u) << b;
+      f32x2 cj[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cj[k] = *reinterpret_cast<const f32x2*>(&cs[k][c]);
+      // squared lengths, op order of the specification:  (a*a + b*b) + c*c.  Differences and
+      // squares are packed; the two additions are scalar add.rn.f32, which ptxas never contracts
+      // (it does fuse mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would break the rounding spec).
+      const f32x2 x = sum_sq(sub2(ri[0], cj[0]), sub2(ri[1], cj[1]), sub2(ri[2], cj[2]));
+      const f32x2 y = sum_sq(sub2(ri[3], cj[3]), sub2(ri[4], cj[4]), sub2(ri[5], cj[5]));
+      // exact filter
+      const f32x2 S = add2(x, y);
+      const f32x2 U = add2(S, ntau2);
+      const f32x2 Q = fma2(mul2(x, y), m4, mul2(U, U));
+      const f32x2 T = mul2(mul2(S, S), kth);
+      float q0, q1, t0, t1, s0, s1;
+      unpack2(Q, q0, q1);
+      unpack2(T, t0, t1);
+      unpack2(S, s0, s1);
+      bool p0 = q0 < 0.0f, p1 = q1 < 0.0f;
+      const bool sure0 = fabsf(q0) > t0 && s0 > lo;
+      const bool sure1 = fabsf(q1) > t1 && s1 > lo;
+      if (!(sure0 && sure1)) {  // rare: inside the rounding band, or out-of-range magnitudes / NaN
+        float x0, x1, y0, y1;
+        unpack2(x, x0, x1);
+        unpack2(y, y0, y1);
+        if (!sure0) p0 = compat_literal(x0, y0, tau);
+        if (!sure1) p1 = compat_literal(x1, y1, tau);
+      }
+      wbits |= (p0 ? 1u : 0u) << b;
+      wbits |= (p1 ? 1u : 0u) << (b + 1);
     }
     words[cw] = wbits;
   }
@@ -150,15 +235,7 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
   if (I != J) {
     // mirrored tile: word for row J0+c, column word I0/32+warp, bit lane = A[I0+32*warp+lane][J0+c]
 #pragma unroll
-    for (int cw = 0; cw < 4; ++cw) {
-      uint32_t mine = 0;
-#pragma unroll
-      for (int b = 0; b < 32; ++b) {
-        const uint32_t v = __ballot_sync(0xffffffffu, (words[cw] >> b) & 1u);
-        if (lane == b) mine = v;
-      }
-      tsm[cw * 32 + lane][warp] = mine;
-    }
+    for (int cw = 0; cw < 4; ++cw) tsm[cw * 32 + lane][warp] = transpose32(words[cw], lane);
     __syncthreads();
     const uint4 tw = *reinterpret_cast<const uint4*>(&tsm[r][0]);
     *reinterpret_cast<uint4*>(adjp + static_cast<size_t>(J0 + r) * d.stride + I0 / 32) = tw;
@@ -180,7 +257,10 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
 int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, const float* d_soa,
                  uint32_t* d_adj, uint32_t* d_ucount, int unit_pitch, float tau) {
   dim3 grid(max_nblk * (max_nblk + 1) / 2, pairs);
-  graph_kernel<<<grid, 128, 0, lc.stream>>>(d_desc, d_soa, d_adj, d_ucount, unit_pitch, tau);
+  const float tau2f = tau * tau;  // one fp32 multiply
+  float lo = 4.0f * tau2f;        // exact scaling (or +inf: then every pair takes the literal path)
+  if (!(lo >= 8.8817841970012523e-16f)) lo = 8.8817841970012523e-16f;  // 2^-50; also replaces NaN
+  graph_kernel<<<grid, 128, 0, lc.stream>>>(d_desc, d_soa, d_adj, d_ucount, unit_pitch, tau, tau2f, lo);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }

@@ -220,8 +220,7 @@ int launch_select_edges(const LaunchCtx& lc, int pairs, PairDev* d_state, const 
 // ------------------------------------------------------------------------------------------
 // Apex selection: one warp per selected edge.
 // ------------------------------------------------------------------------------------------
-constexpr int kApexMax = 8;
-
+template <int M>
 __global__ void __launch_bounds__(128) select_apex_kernel(const PairDesc* __restrict__ descs,
                                                           const uint32_t* __restrict__ adj,
                                                           const unsigned long long* __restrict__ t2,
@@ -244,10 +243,10 @@ __global__ void __launch_bounds__(128) select_apex_kernel(const PairDesc* __rest
   const uint32_t* rj = adj + d.adj_off + static_cast<size_t>(j) * d.stride;
   const unsigned long long* t2p = t2 + d.node_off;
 
-  // per-lane best-m candidates, sorted descending; candidate key = t_k << 32 | (0xFFFFFFFF - k)
-  unsigned long long best[kApexMax];
+  // per-lane best-M candidates, sorted descending; candidate key = t_k << 32 | (0xFFFFFFFF - k)
+  unsigned long long best[M];
 #pragma unroll
-  for (int q = 0; q < kApexMax; ++q) best[q] = 0ull;
+  for (int q = 0; q < M; ++q) best[q] = 0ull;
   for (int w = lane; w < d.stride; w += 32) {
     uint32_t bits = ri[w] & rj[w];
     while (bits) {
@@ -255,13 +254,14 @@ __global__ void __launch_bounds__(128) select_apex_kernel(const PairDesc* __rest
       bits &= bits - 1;
       const unsigned int k = static_cast<unsigned int>(w * 32 + b);
       unsigned long long c = ((t2p[k] >> 1) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - k);
-      // insertion into the sorted register array (fully unrolled compare-exchange chain)
+      if (c > best[M - 1]) {  // most candidates fail this test once the array has warmed up
 #pragma unroll
-      for (int q = 0; q < kApexMax; ++q) {
-        if (c > best[q]) {
-          const unsigned long long tmp = best[q];
-          best[q] = c;
-          c = tmp;
+        for (int q = 0; q < M; ++q) {
+          if (c > best[q]) {
+            const unsigned long long tmp = best[q];
+            best[q] = c;
+            c = tmp;
+          }
         }
       }
     }
@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(128) select_apex_kernel(const PairDesc* __rest
       out[q * 3 + 1] = j;
       out[q * 3 + 2] = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned int>(wmax & 0xFFFFFFFFull));
 #pragma unroll
-      for (int s = 0; s < kApexMax - 1; ++s) best[s] = best[s + 1];
-      best[kApexMax - 1] = 0ull;
+      for (int s = 0; s < M - 1; ++s) best[s] = best[s + 1];
+      best[M - 1] = 0ull;
     }
   }
 }
@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(128) select_apex_kernel(const PairDesc* __rest
 int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const uint32_t* d_adj,
                        const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m) {
   dim3 grid((Ke + 3) / 4, pairs);
-  select_apex_kernel<<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+  if (m <= 1) select_apex_kernel<1><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+  else if (m <= 2) select_apex_kernel<2><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+  else if (m <= 4) select_apex_kernel<4><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+  else select_apex_kernel<8><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }

@@ -277,3 +277,60 @@ def test_run_to_run_determinism(gpu):
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             np.testing.assert_array_equal(a, b)
+
+
+# ---- adversarial inputs for the graph kernel's exact sqrt-free filter ------------------------
+def _adj_parity(gpu, oracle, src, dst, tau):
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=tau, tau_inlier=tau, num_edges=16, apex_per_edge=2)
+    gpu.register(src, dst)
+    oracle.register(src, dst)
+    compare_stages(gpu, oracle, stages=[("adj", _abi.DBG_ADJ), ("num_edges", _abi.DBG_NUM_EDGES),
+                                        ("t_node", _abi.DBG_T_NODE)])
+    return int(gpu.debug(0, _abi.DBG_NUM_EDGES)[0])
+
+
+def test_graph_near_threshold_scaled_cloud(gpu, oracle):
+    # dst = rotated (1+eps) * src: |ld - ls| = eps * ls, so every pair with ls ~ tau/eps sits on the
+    # decision boundary; thousands of pairs land inside the filter's rounding band
+    rng = np.random.default_rng(5)
+    N = 1500
+    src = (rng.random((N, 3)) * 4 - 2).astype(np.float32)
+    p = synth.make_pair(8, 0.5, 1)  # only for a rotation
+    for eps in (1.0 / 64, 0.03, 0.1):
+        dst = ((1 + eps) * src.astype(np.float64) @ p.R_gt.T).astype(np.float32)
+        tau = float(np.float32(eps * 2.0))
+        E = _adj_parity(gpu, oracle, src, dst, tau)
+        assert 0 < E < N * (N - 1) // 2
+
+
+def test_graph_exact_ties_on_a_lattice(gpu, oracle):
+    # collinear integer lattice, dst stretched by 1 + 2^-6: ld - ls = |i-j| * 2^-6 exactly, so with
+    # tau = k * 2^-6 every pair at lattice distance k is an exact tie (strict '<' => no edge)
+    N = 700
+    n = np.arange(N, dtype=np.float64)
+    src = np.stack([n, np.zeros(N), np.zeros(N)], 1).astype(np.float32)
+    dst = np.stack([n * (1 + 2.0 ** -6), np.zeros(N), np.zeros(N)], 1).astype(np.float32)
+    for k in (1, 7, 64):
+        E = _adj_parity(gpu, oracle, src, dst, float(k * 2.0 ** -6))
+        A = np.abs(n[:, None] - n[None, :])
+        assert E == int(((A < k) & (A > 0)).sum()) // 2
+
+
+@pytest.mark.parametrize("scale", [1e-18, 1e-9, 1e-3, 1e6, 1e15])
+def test_graph_extreme_magnitudes_and_duplicates(gpu, oracle, scale):
+    rng = np.random.default_rng(9)
+    N = 300
+    src = (rng.random((N, 3)) * scale).astype(np.float32)
+    dst = (rng.random((N, 3)) * scale).astype(np.float32)
+    src[10:20] = src[0]          # duplicated points: zero lengths
+    dst[15:40] = dst[1]
+    dst[50:60] = 0.0
+    _adj_parity(gpu, oracle, src, dst, float(np.float32(0.3 * scale)))
+    _adj_parity(gpu, oracle, src, dst, float(np.float32(1e-3 * scale)))
+
+
+def test_graph_huge_threshold_takes_literal_path(gpu, oracle):
+    p = synth.make_pair(257, 0.2, 77)
+    E = _adj_parity(gpu, oracle, p.src, p.dst, 1e30)   # 4*tau^2 overflows: every pair decided literally
+    assert E == 257 * 256 // 2
