@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU per step (default: the config's 256)")
     ap.add_argument("--chunk-pairs", type=int, default=0, help="library knob chunk_pairs (0 = auto)")
+    ap.add_argument("--lanes", type=int, default=0, help="library knob lanes (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -202,6 +203,8 @@ def main():
                     tau_inlier=cfg["tau"])
     if args.chunk_pairs:
         reg.set("chunk_pairs", args.chunk_pairs)
+    if args.lanes:
+        reg.set("lanes", args.lanes)
     K = reg.params.num_edges * reg.params.apex_per_edge
 
     # device-resident inputs / outputs

@@ -95,7 +95,8 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
 
 /* Tunables/inspection by name; unknown names return SAC_COT_E_WHICH.
  *   set: "keep_debug" (0/1: retain per-pair intermediates for sac_cot_debug_get; forces
- *        chunk = whole batch), "chunk_pairs" (pairs per kernel wave, 0 = auto),
+ *        chunk = whole batch), "chunk_pairs" (pairs per kernel wave, 0 = auto), "lanes" (1..4
+ *        internal streams the chunks of a batch are dealt to, default 2; GPU only),
  *        "triangle_path" (0 = POPC bitset, 1 = tensor-core dense; GPU only),
  *        "stage_timing" (0/1: bracket every pipeline stage with CUDA events on the ctx
  *        stream; setting it also clears the accumulated times; GPU only)

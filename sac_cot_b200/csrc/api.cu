@@ -126,32 +126,44 @@ struct StageTimer {
 
 }  // namespace
 
-struct sac_cot_ctx {
-  int device = 0;
+// A lane = one internal stream with its own workspace.  Chunks of a batch are dealt to the lanes
+// round-robin, so the tail of one chunk's kernels (and, in host mode, its H2D / D2H copies)
+// overlaps the next chunk's work.  Lane streams fork from / join into the ctx stream with events,
+// so a caller bracketing the call with events on the ctx stream still times everything.
+struct Lane {
   cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  int sm_count = 0;
-  bool keep_debug = false;
-  int chunk_pairs = 0;
-  int64_t launches = 0;
-  int64_t retries = 0;
-  int deferred_status = 0;  // device-location calls: status discovered after the fact
-
+  cudaEvent_t done = nullptr;
   unsigned char* arena = nullptr;
   size_t arena_bytes = 0;
   unsigned long long* keys = nullptr;
   unsigned long long key_cap = 0;
-  ChunkDev* h_chunk = nullptr;    // pinned read-back of the chunk header (host-location calls)
-  StickyDev* d_sticky = nullptr;  // device: overflow record that survives across calls
-  StickyDev* h_sticky = nullptr;  // pinned mirror, refreshed asynchronously after device-location calls
+  Layout lay;                     // layout of the chunk most recently enqueued on this lane
+  std::vector<PairDesc> descs;
+};
+constexpr int kMaxLanes = 4;
+
+struct sac_cot_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;  // the caller-visible stream
+  bool own_stream = false;
+  int sm_count = 0;
+  bool keep_debug = false;
+  int chunk_pairs = 0;
+  int n_lanes = 2;
+  int64_t launches = 0;
+  int64_t retries = 0;
+  int deferred_status = 0;  // device-location calls: status discovered after the fact
+
+  Lane lanes[kMaxLanes];
+  cudaEvent_t fork_event = nullptr;
+  std::vector<ChunkDev*> h_chunks;  // pinned read-backs of the chunk headers (host-location calls)
+  StickyDev* d_sticky = nullptr;    // device: overflow record that survives across calls
+  StickyDev* h_sticky = nullptr;    // pinned mirror, refreshed asynchronously after device-location calls
   uint32_t seen_overflows = 0;
 
-  // description of what is resident in the workspace (for debug_get / sharded phases)
-  Layout lay;
-  std::vector<PairDesc> descs;
+  // what is resident in lane 0's workspace (debug_get / sharded phases)
   sac_cot_params prm{};
   bool ws_valid = false;
-  // sharded call in flight
   int sh_rank = 0, sh_world = 1, sh_N = 0;
   bool sh_valid = false;
 
@@ -296,70 +308,81 @@ void bind(Layout& L, unsigned char* base, bool has_input) {
   L.best_override = rebase(L.best_override, base);
 }
 
-int ensure_arena(sac_cot_ctx* ctx, size_t bytes) {
-  if (bytes <= ctx->arena_bytes) return 0;
+int sync_all(sac_cot_ctx* ctx) {
+  for (int l = 0; l < kMaxLanes; ++l)
+    if (ctx->lanes[l].stream) CU_TRY(cudaStreamSynchronize(ctx->lanes[l].stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
-  if (ctx->arena) CU_TRY(cudaFree(ctx->arena));
-  ctx->arena = nullptr;
-  ctx->arena_bytes = 0;
+  return 0;
+}
+
+int ensure_arena(sac_cot_ctx* ctx, Lane& ln, size_t bytes) {
+  if (bytes <= ln.arena_bytes) return 0;
+  if (int rc = sync_all(ctx)) return rc;
+  if (ln.arena) CU_TRY(cudaFree(ln.arena));
+  ln.arena = nullptr;
+  ln.arena_bytes = 0;
   const size_t want = align_up(bytes + bytes / 8, 1 << 20);
-  cudaError_t e = cudaMalloc(&ctx->arena, want);
+  cudaError_t e = cudaMalloc(&ln.arena, want);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
-    e = cudaMalloc(&ctx->arena, bytes);
+    e = cudaMalloc(&ln.arena, bytes);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       return SAC_COT_E_NOMEM;
     }
-    ctx->arena_bytes = bytes;
+    ln.arena_bytes = bytes;
   } else {
-    ctx->arena_bytes = want;
+    ln.arena_bytes = want;
   }
-  ctx->ws_valid = false;
-  ctx->sh_valid = false;
+  if (&ln == &ctx->lanes[0]) {
+    ctx->ws_valid = false;
+    ctx->sh_valid = false;
+  }
   return 0;
 }
 
-int ensure_keys(sac_cot_ctx* ctx, unsigned long long cap) {
-  if (cap <= ctx->key_cap) return 0;
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
-  if (ctx->keys) CU_TRY(cudaFree(ctx->keys));
-  ctx->keys = nullptr;
-  ctx->key_cap = 0;
-  if (cudaMalloc(&ctx->keys, cap * sizeof(unsigned long long)) != cudaSuccess) {
+int ensure_keys(sac_cot_ctx* ctx, Lane& ln, unsigned long long cap) {
+  if (cap <= ln.key_cap) return 0;
+  if (int rc = sync_all(ctx)) return rc;
+  if (ln.keys) CU_TRY(cudaFree(ln.keys));
+  ln.keys = nullptr;
+  ln.key_cap = 0;
+  if (cudaMalloc(&ln.keys, cap * sizeof(unsigned long long)) != cudaSuccess) {
     (void)cudaGetLastError();
     return SAC_COT_E_NOMEM;
   }
-  ctx->key_cap = cap;
+  ln.key_cap = cap;
   return 0;
 }
 
 // Picks up key-pool overflows of earlier device-location calls from the pinned mirror of the
 // sticky record.  block = false never waits: it sees whatever has been copied back so far (the
-// record only grows, so a stale view is merely late).  On a new overflow the pool is grown to
-// the recorded demand, so the caller's next call succeeds; the overflowed call's outputs are
-// void and "last_status" reports SAC_COT_E_NOMEM for it.
+// record only grows, so a stale view is merely late).  On a new overflow every lane's pool is
+// grown to the recorded demand, so the caller's next call succeeds; the overflowed call's outputs
+// are void and "last_status" reports SAC_COT_E_NOMEM for it.
 int resolve_pending(sac_cot_ctx* ctx, bool block) {
-  if (block) CU_TRY(cudaStreamSynchronize(ctx->stream));
+  if (block)
+    if (int rc = sync_all(ctx)) return rc;
   const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&ctx->h_sticky->overflow_count);
   if (count != ctx->seen_overflows) {
     ctx->seen_overflows = count;
     ctx->deferred_status = SAC_COT_E_NOMEM;
     const unsigned long long demand = *reinterpret_cast<volatile unsigned long long*>(&ctx->h_sticky->max_total_edges);
     ++ctx->retries;
-    if (int rc = ensure_keys(ctx, demand + demand / 8 + 1024)) return rc;
+    for (int l = 0; l < ctx->n_lanes; ++l)
+      if (int rc = ensure_keys(ctx, ctx->lanes[l], demand + demand / 8 + 1024)) return rc;
   }
   return 0;
 }
 
-// Enqueues the whole pipeline for the pairs described by ctx->descs / ctx->lay.
+// Enqueues the whole pipeline on lane `ln` for the pairs described by ln.descs / ln.lay.
 //   d_src/d_dst : device AoS inputs for this chunk (pt_off relative to them)
 //   dR/dT/dInl  : device outputs for this chunk
-int enqueue_pipeline(sac_cot_ctx* ctx, const float* d_src, const float* d_dst, float* dR, float* dT, int32_t* dInl,
-                     int rank, int world, bool stop_after_edges) {
-  Layout& L = ctx->lay;
+int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float* d_dst, float* dR, float* dT,
+                     int32_t* dInl, int rank, int world, bool stop_after_edges) {
+  Layout& L = ln.lay;
   const sac_cot_params& prm = ctx->prm;
-  LaunchCtx lc{ctx->stream, ctx->sm_count};
+  LaunchCtx lc{ln.stream, ctx->sm_count};
   StageTimer& tm = ctx->timer;
   if (tm.enabled && tm.pending.size() > 8192) tm.resolve();
   cudaEvent_t ev_prev = nullptr;
@@ -367,23 +390,23 @@ int enqueue_pipeline(sac_cot_ctx* ctx, const float* d_src, const float* d_dst, f
     if (!tm.enabled) return;
     cudaEvent_t e = tm.next();
     if (!e) return;
-    cudaEventRecord(e, ctx->stream);
+    cudaEventRecord(e, ln.stream);
     if (stage >= 0 && ev_prev) tm.pending.push_back({stage, ev_prev, e});
     ev_prev = e;
   };
-  CU_TRY(cudaMemsetAsync(L.state, 0, L.zero_bytes, ctx->stream));
+  CU_TRY(cudaMemsetAsync(L.state, 0, L.zero_bytes, ln.stream));
   mark(-1);
   KL_TRY(launch_pack_soa(lc, L.desc, L.pairs, L.max_npad, d_src, d_dst, L.soa));
   mark(ST_PACK);
   KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.ucount, L.unit_pitch, prm.tau_compat));
   mark(ST_GRAPH);
   KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world));
-  KL_TRY(launch_key_scan(lc, L.pairs, L.state, L.chunk, ctx->d_sticky, ctx->key_cap));
+  KL_TRY(launch_key_scan(lc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap));
   mark(ST_SCAN);
-  KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ctx->keys, L.ubase,
+  KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ln.keys, L.ubase,
                           L.unit_pitch, L.hist, L.t2, rank, world));
   mark(ST_TRIANGLES);
-  KL_TRY(launch_select_edges(lc, L.pairs, L.state, L.chunk, ctx->keys, L.hist, L.sel, L.tie, L.top, L.Ke));
+  KL_TRY(launch_select_edges(lc, L.pairs, L.state, L.chunk, ln.keys, L.hist, L.sel, L.tie, L.top, L.Ke));
   mark(ST_SELECT);
   if (stop_after_edges) return 0;
   const float tau2 = prm.tau_inlier * prm.tau_inlier;
@@ -400,61 +423,60 @@ int enqueue_pipeline(sac_cot_ctx* ctx, const float* d_src, const float* d_dst, f
   return 0;
 }
 
-// One chunk, host or device location.  offsets are absolute (whole call); [b0,b1) is the chunk.
-int run_chunk(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_t* offsets, int b0, int b1,
-              const sac_cot_params& prm, float* R, float* t, int32_t* inliers, int location) {
+// lane streams start after everything already enqueued on the ctx stream ...
+int fork_lanes(sac_cot_ctx* ctx, int n) {
+  CU_TRY(cudaEventRecord(ctx->fork_event, ctx->stream));
+  for (int l = 0; l < n; ++l) CU_TRY(cudaStreamWaitEvent(ctx->lanes[l].stream, ctx->fork_event, 0));
+  return 0;
+}
+// ... and the ctx stream continues after everything enqueued on the lanes
+int join_lanes(sac_cot_ctx* ctx, int n) {
+  for (int l = 0; l < n; ++l) {
+    CU_TRY(cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].stream));
+    CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
+  }
+  return 0;
+}
+
+// Enqueues one chunk [b0,b1) on a lane.  offsets are absolute (whole call).
+int enqueue_chunk(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst, const int64_t* offsets, int b0,
+                  int b1, const sac_cot_params& prm, float* R, float* t, int32_t* inliers, bool host,
+                  ChunkDev* h_chunk) {
   const int pairs = b1 - b0;
   std::vector<int32_t> Ns(pairs);
   for (int b = 0; b < pairs; ++b) Ns[b] = static_cast<int32_t>(offsets[b0 + b + 1] - offsets[b0 + b]);
-  const bool host = location == SAC_COT_LOC_HOST;
-  for (int attempt = 0; attempt < 3; ++attempt) {
-    plan(Ns.data(), pairs, prm, host, ctx->descs, ctx->lay);
-    if (int rc = ensure_arena(ctx, ctx->lay.total_bytes)) return rc;
-    if (int rc = ensure_keys(ctx, ctx->lay.key_guess)) return rc;
-    bind(ctx->lay, ctx->arena, host);
-    ctx->prm = prm;
-    ctx->ws_valid = false;
-    ctx->sh_valid = false;
-    Layout& L = ctx->lay;
-    CU_TRY(cudaMemcpyAsync(L.desc, ctx->descs.data(), sizeof(PairDesc) * pairs, cudaMemcpyHostToDevice, ctx->stream));
-    const int64_t p0 = offsets[b0];
-    const float* d_src;
-    const float* d_dst;
-    float *dR, *dT;
-    int32_t* dInl;
-    if (host) {
-      CU_TRY(cudaMemcpyAsync(L.in_src, src + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ctx->stream));
-      CU_TRY(cudaMemcpyAsync(L.in_dst, dst + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ctx->stream));
-      d_src = L.in_src; d_dst = L.in_dst;
-      dR = L.outR; dT = L.outT; dInl = L.outInl;
-    } else {
-      d_src = src + 3 * p0; d_dst = dst + 3 * p0;
-      dR = R + 9 * static_cast<size_t>(b0); dT = t + 3 * static_cast<size_t>(b0); dInl = inliers + b0;
-    }
-    if (int rc = enqueue_pipeline(ctx, d_src, d_dst, dR, dT, dInl, 0, 1, false)) return rc;
-    if (!host) {
-      CU_TRY(cudaMemcpyAsync(ctx->h_sticky, ctx->d_sticky, sizeof(StickyDev), cudaMemcpyDeviceToHost, ctx->stream));
-      ctx->ws_valid = true;
-      return 0;  // enqueue only; an overflow (if any) surfaces through resolve_pending()
-    }
-    CU_TRY(cudaMemcpyAsync(ctx->h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ctx->stream));
+  plan(Ns.data(), pairs, prm, host, ln.descs, ln.lay);
+  if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
+  if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
+  bind(ln.lay, ln.arena, host);
+  Layout& L = ln.lay;
+  CU_TRY(cudaMemcpyAsync(L.desc, ln.descs.data(), sizeof(PairDesc) * pairs, cudaMemcpyHostToDevice, ln.stream));
+  const int64_t p0 = offsets[b0];
+  if (host) {
+    CU_TRY(cudaMemcpyAsync(L.in_src, src + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ln.stream));
+    CU_TRY(cudaMemcpyAsync(L.in_dst, dst + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ln.stream));
+    if (int rc = enqueue_pipeline(ctx, ln, L.in_src, L.in_dst, L.outR, L.outT, L.outInl, 0, 1, false)) return rc;
+    CU_TRY(cudaMemcpyAsync(h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ln.stream));
     CU_TRY(cudaMemcpyAsync(R + 9 * static_cast<size_t>(b0), L.outR, sizeof(float) * 9 * pairs, cudaMemcpyDeviceToHost,
-                           ctx->stream));
+                           ln.stream));
     CU_TRY(cudaMemcpyAsync(t + 3 * static_cast<size_t>(b0), L.outT, sizeof(float) * 3 * pairs, cudaMemcpyDeviceToHost,
-                           ctx->stream));
-    CU_TRY(cudaMemcpyAsync(inliers + b0, L.outInl, sizeof(int32_t) * pairs, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    if (!ctx->h_chunk->overflow) {
-      ctx->ws_valid = true;
-      return 0;
-    }
-    // key pool too small for this chunk's edge count: grow to the measured demand and re-run
-    ++ctx->retries;
-    const unsigned long long want = ctx->h_chunk->total_edges + ctx->h_chunk->total_edges / 16 + 1024;
-    if (int rc = ensure_keys(ctx, want)) return rc;
-    // ensure_keys(key_guess) in the next attempt is a no-op because key_cap only grows
+                           ln.stream));
+    CU_TRY(cudaMemcpyAsync(inliers + b0, L.outInl, sizeof(int32_t) * pairs, cudaMemcpyDeviceToHost, ln.stream));
+  } else {
+    if (int rc = enqueue_pipeline(ctx, ln, src + 3 * p0, dst + 3 * p0, R + 9 * static_cast<size_t>(b0),
+                                  t + 3 * static_cast<size_t>(b0), inliers + b0, 0, 1, false))
+      return rc;
   }
-  return SAC_COT_E_NOMEM;
+  return 0;
+}
+
+int ensure_chunk_headers(sac_cot_ctx* ctx, size_t n) {
+  while (ctx->h_chunks.size() < n) {
+    ChunkDev* h = nullptr;
+    CU_TRY(cudaMallocHost(&h, sizeof(ChunkDev)));
+    ctx->h_chunks.push_back(h);
+  }
+  return 0;
 }
 
 int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_t* offsets, int32_t B,
@@ -471,9 +493,12 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
   if (B == 0) return SAC_COT_OK;
   CU_TRY(cudaSetDevice(ctx->device));
   if (int rc = resolve_pending(ctx, false)) return rc;
-  // chunking: bounded workspace per wave of kernels (keep_debug keeps the whole batch resident)
+  const bool host = location == SAC_COT_LOC_HOST;
+  // chunking: bounded workspace per wave of kernels (keep_debug keeps the whole batch resident on
+  // lane 0); chunks are dealt round-robin to the lanes
   const int K = params->num_edges * params->apex_per_edge;
   int chunk = B;
+  int lanes = ctx->keep_debug ? 1 : ctx->n_lanes;
   if (!ctx->keep_debug) {
     if (ctx->chunk_pairs > 0) {
       chunk = std::min(B, ctx->chunk_pairs);
@@ -481,15 +506,58 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
       size_t total = 0;
       for (int b = 0; b < B; ++b)
         total += pair_bytes_estimate(static_cast<int>(offsets[b + 1] - offsets[b]), K, params->num_edges);
-      const size_t budget = static_cast<size_t>(3) << 30;
-      const int nchunks = static_cast<int>((total + budget - 1) / budget);
+      const size_t budget = static_cast<size_t>(3) << 29;  // ~1.5 GB of workspace per chunk
+      int nchunks = static_cast<int>((total + budget - 1) / budget);
+      if (nchunks < lanes && B >= 2 * lanes) nchunks = lanes;  // give every lane something to overlap
       chunk = (B + nchunks - 1) / std::max(1, nchunks);
     }
   }
-  for (int b0 = 0; b0 < B; b0 += chunk) {
-    const int b1 = std::min(B, b0 + chunk);
-    if (int rc = run_chunk(ctx, src, dst, offsets, b0, b1, *params, R, t, inliers, location)) return rc;
+  const int nchunks = (B + chunk - 1) / chunk;
+  lanes = std::min(lanes, nchunks);
+  ctx->prm = *params;
+  ctx->ws_valid = false;
+  ctx->sh_valid = false;
+  if (host)
+    if (int rc = ensure_chunk_headers(ctx, static_cast<size_t>(nchunks))) return rc;
+
+  std::vector<int> todo(nchunks);
+  for (int c = 0; c < nchunks; ++c) todo[c] = c;
+  for (int attempt = 0; attempt < 3 && !todo.empty(); ++attempt) {
+    if (int rc = fork_lanes(ctx, lanes)) return rc;
+    for (size_t k = 0; k < todo.size(); ++k) {
+      const int c = todo[k];
+      const int b0 = c * chunk, b1 = std::min(B, b0 + chunk);
+      Lane& ln = ctx->lanes[k % lanes];
+      if (int rc = enqueue_chunk(ctx, ln, src, dst, offsets, b0, b1, *params, R, t, inliers, host,
+                                 host ? ctx->h_chunks[c] : nullptr))
+        return rc;
+    }
+    if (int rc = join_lanes(ctx, lanes)) return rc;
+    if (!host) {
+      // enqueue only; an overflow (if any) surfaces through resolve_pending()
+      CU_TRY(cudaMemcpyAsync(ctx->h_sticky, ctx->d_sticky, sizeof(StickyDev), cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->ws_valid = nchunks == 1;
+      return SAC_COT_OK;
+    }
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    // chunks whose edge count exceeded the lane's key pool: grow every lane to the measured demand
+    // and re-run just those chunks
+    std::vector<int> again;
+    unsigned long long want = 0;
+    for (int c : todo)
+      if (ctx->h_chunks[c]->overflow) {
+        again.push_back(c);
+        want = std::max(want, ctx->h_chunks[c]->total_edges + ctx->h_chunks[c]->total_edges / 16 + 1024);
+      }
+    if (!again.empty()) {
+      ++ctx->retries;
+      for (int l = 0; l < lanes; ++l)
+        if (int rc = ensure_keys(ctx, ctx->lanes[l], want)) return rc;
+    }
+    todo.swap(again);
   }
+  if (!todo.empty()) return SAC_COT_E_NOMEM;
+  ctx->ws_valid = nchunks == 1;
   return SAC_COT_OK;
 }
 
@@ -540,12 +608,15 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
     if (e != cudaSuccess) { delete ctx; return static_cast<int>(e); }
     ctx->own_stream = true;
   }
-  cudaError_t e = cudaMallocHost(&ctx->h_chunk, sizeof(ChunkDev));
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_sticky, sizeof(StickyDev));
+  cudaError_t e = cudaMallocHost(&ctx->h_sticky, sizeof(StickyDev));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_sticky, sizeof(StickyDev));
   if (e == cudaSuccess) e = cudaMemset(ctx->d_sticky, 0, sizeof(StickyDev));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming);
+  for (int l = 0; l < kMaxLanes && e == cudaSuccess; ++l) {
+    e = cudaStreamCreateWithFlags(&ctx->lanes[l].stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].done, cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) { sac_cot_ctx_destroy(ctx); return static_cast<int>(e); }
-  std::memset(ctx->h_chunk, 0, sizeof(ChunkDev));
   std::memset(ctx->h_sticky, 0, sizeof(StickyDev));
   const int rc = triangles_configure();
   if (rc < 0) { sac_cot_ctx_destroy(ctx); return -rc; }
@@ -556,10 +627,16 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
 int sac_cot_ctx_destroy(sac_cot_ctx* ctx) {
   if (!ctx) return SAC_COT_OK;
   cudaSetDevice(ctx->device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  if (ctx->arena) cudaFree(ctx->arena);
-  if (ctx->keys) cudaFree(ctx->keys);
-  if (ctx->h_chunk) cudaFreeHost(ctx->h_chunk);
+  (void)sync_all(ctx);
+  for (int l = 0; l < kMaxLanes; ++l) {
+    Lane& ln = ctx->lanes[l];
+    if (ln.arena) cudaFree(ln.arena);
+    if (ln.keys) cudaFree(ln.keys);
+    if (ln.done) cudaEventDestroy(ln.done);
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+  }
+  for (ChunkDev* h : ctx->h_chunks) cudaFreeHost(h);
+  if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   if (ctx->h_sticky) cudaFreeHost(ctx->h_sticky);
   if (ctx->d_sticky) cudaFree(ctx->d_sticky);
   ctx->timer.destroy();
@@ -576,6 +653,11 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     ctx->chunk_pairs = static_cast<int>(std::min<int64_t>(value, 65535));
     return SAC_COT_OK;
   }
+  if (!std::strcmp(name, "lanes")) {
+    if (value < 1 || value > kMaxLanes) return SAC_COT_E_SIZE;
+    ctx->n_lanes = static_cast<int>(value);
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "triangle_path")) return value == 0 ? SAC_COT_OK : SAC_COT_E_UNSUPPORTED;
   if (!std::strcmp(name, "stage_timing")) {
     cudaSetDevice(ctx->device);
@@ -590,12 +672,16 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
   if (!ctx || !name || !value) return SAC_COT_E_NULL;
   if (!std::strcmp(name, "launches")) { *value = ctx->launches; return SAC_COT_OK; }
   if (!std::strcmp(name, "workspace_bytes")) {
-    *value = static_cast<int64_t>(ctx->arena_bytes + ctx->key_cap * sizeof(unsigned long long));
+    int64_t total = 0;
+    for (int l = 0; l < kMaxLanes; ++l)
+      total += static_cast<int64_t>(ctx->lanes[l].arena_bytes + ctx->lanes[l].key_cap * sizeof(unsigned long long));
+    *value = total;
     return SAC_COT_OK;
   }
   if (!std::strcmp(name, "retries")) { *value = ctx->retries; return SAC_COT_OK; }
   if (!std::strcmp(name, "device")) { *value = ctx->device; return SAC_COT_OK; }
   if (!std::strcmp(name, "sm_count")) { *value = ctx->sm_count; return SAC_COT_OK; }
+  if (!std::strcmp(name, "lanes")) { *value = ctx->n_lanes; return SAC_COT_OK; }
   if (!std::strcmp(name, "threads")) { *value = 0; return SAC_COT_OK; }
   if (!std::strncmp(name, "stage_us_", 9) || !std::strncmp(name, "stage_calls_", 12)) {
     const bool us = name[6] == 'u';
@@ -680,26 +766,30 @@ int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
   CU_TRY(cudaSetDevice(ctx->device));
   if (int rc = resolve_pending(ctx, false)) return rc;
   ctx->sh_valid = false;
+  ctx->ws_valid = false;
+  Lane& ln = ctx->lanes[0];
   try {
+    if (int rc = ensure_chunk_headers(ctx, 1)) return rc;
+    ChunkDev* h_chunk = ctx->h_chunks[0];
     for (int attempt = 0; attempt < 3; ++attempt) {
-      plan(&N, 1, *params, true, ctx->descs, ctx->lay);
-      if (int rc = ensure_arena(ctx, ctx->lay.total_bytes)) return rc;
-      // a rank evaluates ~1/world of the edges; the scan checks the full E against the pool,
-      // so size for the whole pair (N = 50000 at 7.6 % density: 0.75 GB)
-      if (int rc = ensure_keys(ctx, ctx->lay.key_guess)) return rc;
-      bind(ctx->lay, ctx->arena, true);
+      plan(&N, 1, *params, true, ln.descs, ln.lay);
+      if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
+      // a rank evaluates ~1/world of the edges: the unit scan counts only the owned units, so the
+      // pool demand is ~E/world; the initial guess covers a whole pair at 12.5 % density
+      if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
+      bind(ln.lay, ln.arena, true);
       ctx->prm = *params;
-      ctx->ws_valid = false;
-      Layout& L = ctx->lay;
-      CU_TRY(cudaMemcpyAsync(L.desc, ctx->descs.data(), sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
-      CU_TRY(cudaMemcpyAsync(L.in_src, src, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
-      CU_TRY(cudaMemcpyAsync(L.in_dst, dst, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
-      if (int rc = enqueue_pipeline(ctx, L.in_src, L.in_dst, nullptr, nullptr, nullptr, rank, world, true)) return rc;
-      CU_TRY(cudaMemcpyAsync(ctx->h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ctx->stream));
-      CU_TRY(cudaMemcpyAsync(t_partial, L.t2, sizeof(uint64_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
-      CU_TRY(cudaMemcpyAsync(cand, L.top, sizeof(uint64_t) * params->num_edges, cudaMemcpyDeviceToHost, ctx->stream));
-      CU_TRY(cudaStreamSynchronize(ctx->stream));
-      if (!ctx->h_chunk->overflow) {
+      Layout& L = ln.lay;
+      if (int rc = fork_lanes(ctx, 1)) return rc;
+      CU_TRY(cudaMemcpyAsync(L.desc, ln.descs.data(), sizeof(PairDesc), cudaMemcpyHostToDevice, ln.stream));
+      CU_TRY(cudaMemcpyAsync(L.in_src, src, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ln.stream));
+      CU_TRY(cudaMemcpyAsync(L.in_dst, dst, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ln.stream));
+      if (int rc = enqueue_pipeline(ctx, ln, L.in_src, L.in_dst, nullptr, nullptr, nullptr, rank, world, true)) return rc;
+      CU_TRY(cudaMemcpyAsync(h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ln.stream));
+      CU_TRY(cudaMemcpyAsync(t_partial, L.t2, sizeof(uint64_t) * N, cudaMemcpyDeviceToHost, ln.stream));
+      CU_TRY(cudaMemcpyAsync(cand, L.top, sizeof(uint64_t) * params->num_edges, cudaMemcpyDeviceToHost, ln.stream));
+      CU_TRY(cudaStreamSynchronize(ln.stream));
+      if (!h_chunk->overflow) {
         ctx->sh_rank = rank;
         ctx->sh_world = world;
         ctx->sh_N = N;
@@ -707,7 +797,7 @@ int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
         return SAC_COT_OK;
       }
       ++ctx->retries;
-      if (int rc = ensure_keys(ctx, ctx->h_chunk->total_edges + ctx->h_chunk->total_edges / 16 + 1024)) return rc;
+      if (int rc = ensure_keys(ctx, ln, h_chunk->total_edges + h_chunk->total_edges / 16 + 1024)) return rc;
     }
   } catch (const std::bad_alloc&) {
     return SAC_COT_E_NOMEM;
@@ -719,11 +809,12 @@ int sac_cot_sharded_phase2(sac_cot_ctx* ctx, const uint64_t* t_all, const uint64
   if (!ctx || !t_all || !cand_all || !best_key) return SAC_COT_E_NULL;
   if (!ctx->sh_valid) return SAC_COT_E_SIZE;
   CU_TRY(cudaSetDevice(ctx->device));
+  Lane& ln = ctx->lanes[0];
   try {
-    Layout& L = ctx->lay;
+    Layout& L = ln.lay;
     const int N = ctx->sh_N, world = ctx->sh_world, Ke = L.Ke;
     // exchange #1 results: node sums add up over ranks; candidates merge to the global top-K_e
-    std::vector<unsigned long long> t2(static_cast<size_t>(ctx->descs[0].Npad), 0ull);
+    std::vector<unsigned long long> t2(static_cast<size_t>(ln.descs[0].Npad), 0ull);
     for (int g = 0; g < world; ++g)
       for (int i = 0; i < N; ++i) t2[i] += t_all[static_cast<size_t>(g) * N + i];
     std::vector<unsigned long long> all;
@@ -732,11 +823,11 @@ int sac_cot_sharded_phase2(sac_cot_ctx* ctx, const uint64_t* t_all, const uint64
       if (cand_all[k]) all.push_back(cand_all[k]);
     std::sort(all.begin(), all.end(), [](unsigned long long a, unsigned long long b) { return a > b; });
     all.resize(static_cast<size_t>(Ke), 0ull);
-    CU_TRY(cudaMemcpyAsync(L.t2, t2.data(), sizeof(unsigned long long) * t2.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(L.top, all.data(), sizeof(unsigned long long) * Ke, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(cudaMemsetAsync(&L.state[0].best_key, 0, sizeof(unsigned long long), ctx->stream));
-    CU_TRY(cudaMemsetAsync(L.hyp_key, 0, sizeof(unsigned long long) * L.K, ctx->stream));
-    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    CU_TRY(cudaMemcpyAsync(L.t2, t2.data(), sizeof(unsigned long long) * t2.size(), cudaMemcpyHostToDevice, ln.stream));
+    CU_TRY(cudaMemcpyAsync(L.top, all.data(), sizeof(unsigned long long) * Ke, cudaMemcpyHostToDevice, ln.stream));
+    CU_TRY(cudaMemsetAsync(&L.state[0].best_key, 0, sizeof(unsigned long long), ln.stream));
+    CU_TRY(cudaMemsetAsync(L.hyp_key, 0, sizeof(unsigned long long) * L.K, ln.stream));
+    LaunchCtx lc{ln.stream, ctx->sm_count};
     const float tau2 = ctx->prm.tau_inlier * ctx->prm.tau_inlier;
     KL_TRY(launch_select_apex(lc, L.desc, 1, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
     KL_TRY(launch_kabsch(lc, L.desc, 1, L.soa, L.tri, L.rt, L.K));
@@ -745,8 +836,8 @@ int sac_cot_sharded_phase2(sac_cot_ctx* ctx, const uint64_t* t_all, const uint64
     KL_TRY(launch_score(lc, L.desc, 1, L.max_n, L.soa, L.tri, L.rt, L.hyp_key, L.state, tau2, L.K, h0, h1,
                         ctx->prm.score_mode));
     unsigned long long best = 0;
-    CU_TRY(cudaMemcpyAsync(&best, &L.state[0].best_key, sizeof(best), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaMemcpyAsync(&best, &L.state[0].best_key, sizeof(best), cudaMemcpyDeviceToHost, ln.stream));
+    CU_TRY(cudaStreamSynchronize(ln.stream));
     *best_key = best;
   } catch (const std::bad_alloc&) {
     return SAC_COT_E_NOMEM;
@@ -758,18 +849,19 @@ int sac_cot_sharded_phase3(sac_cot_ctx* ctx, uint64_t best_key_global, float R[9
   if (!ctx || !R || !t || !inliers) return SAC_COT_E_NULL;
   if (!ctx->sh_valid) return SAC_COT_E_SIZE;
   CU_TRY(cudaSetDevice(ctx->device));
-  Layout& L = ctx->lay;
+  Lane& ln = ctx->lanes[0];
+  Layout& L = ln.lay;
   const unsigned long long key = best_key_global;
-  CU_TRY(cudaMemcpyAsync(L.best_override, &key, sizeof(key), cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(cudaMemcpyAsync(&L.state[0].best_key, &key, sizeof(key), cudaMemcpyHostToDevice, ctx->stream));
-  LaunchCtx lc{ctx->stream, ctx->sm_count};
+  CU_TRY(cudaMemcpyAsync(L.best_override, &key, sizeof(key), cudaMemcpyHostToDevice, ln.stream));
+  CU_TRY(cudaMemcpyAsync(&L.state[0].best_key, &key, sizeof(key), cudaMemcpyHostToDevice, ln.stream));
+  LaunchCtx lc{ln.stream, ctx->sm_count};
   const float tau2 = ctx->prm.tau_inlier * ctx->prm.tau_inlier;
   KL_TRY(launch_finalize(lc, L.desc, 1, L.soa, L.rt, L.state, L.best_override, L.mask, L.outR, L.outT, L.outInl, tau2,
                          L.K, ctx->prm.refit));
-  CU_TRY(cudaMemcpyAsync(R, L.outR, sizeof(float) * 9, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(cudaMemcpyAsync(t, L.outT, sizeof(float) * 3, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(cudaMemcpyAsync(inliers, L.outInl, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaMemcpyAsync(R, L.outR, sizeof(float) * 9, cudaMemcpyDeviceToHost, ln.stream));
+  CU_TRY(cudaMemcpyAsync(t, L.outT, sizeof(float) * 3, cudaMemcpyDeviceToHost, ln.stream));
+  CU_TRY(cudaMemcpyAsync(inliers, L.outInl, sizeof(int32_t), cudaMemcpyDeviceToHost, ln.stream));
+  CU_TRY(cudaStreamSynchronize(ln.stream));
   ctx->ws_valid = true;  // the single pair is fully resident: debug_get(pair = 0 or -1) works
   return SAC_COT_OK;
 }
@@ -778,11 +870,12 @@ int sac_cot_sharded_phase3(sac_cot_ctx* ctx, uint64_t best_key_global, float R[9
 int sac_cot_debug_get(sac_cot_ctx* ctx, int32_t pair, int32_t which, void* out, size_t cap, size_t* written) {
   if (!ctx || !written) return SAC_COT_E_NULL;
   if (pair == -1) pair = 0;
-  if (!(ctx->ws_valid || ctx->sh_valid) || pair < 0 || pair >= ctx->lay.pairs) return SAC_COT_E_WHICH;
+  Lane& ln = ctx->lanes[0];
+  if (!(ctx->ws_valid || ctx->sh_valid) || pair < 0 || pair >= ln.lay.pairs) return SAC_COT_E_WHICH;
   CU_TRY(cudaSetDevice(ctx->device));
   if (int rc = resolve_pending(ctx, true)) return rc;
-  const Layout& L = ctx->lay;
-  const PairDesc& d = ctx->descs[pair];
+  const Layout& L = ln.lay;
+  const PairDesc& d = ln.descs[pair];
   PairDev st;
   CU_TRY(cudaMemcpy(&st, L.state + pair, sizeof(st), cudaMemcpyDeviceToHost));
   const void* dsrc = nullptr;
@@ -793,7 +886,7 @@ int sac_cot_debug_get(sac_cot_ctx* ctx, int32_t pair, int32_t which, void* out, 
     case SAC_COT_DBG_ADJ: dsrc = L.adj + d.adj_off; bytes = static_cast<size_t>(d.N) * d.stride * 4; break;
     case SAC_COT_DBG_T_NODE: bytes = static_cast<size_t>(d.N) * 4; break;
     case SAC_COT_DBG_NUM_EDGES: scalar = st.num_edges; bytes = 8; break;
-    case SAC_COT_DBG_EDGE_KEYS: dsrc = ctx->keys + st.key_base; bytes = static_cast<size_t>(st.key_count) * 8; break;
+    case SAC_COT_DBG_EDGE_KEYS: dsrc = ln.keys + st.key_base; bytes = static_cast<size_t>(st.key_count) * 8; break;
     case SAC_COT_DBG_TOP_EDGES: dsrc = L.top + static_cast<size_t>(pair) * L.Ke; bytes = static_cast<size_t>(st.n_sel) * 8; break;
     case SAC_COT_DBG_TRIANGLES: dsrc = L.tri + static_cast<size_t>(pair) * L.K * 3; bytes = static_cast<size_t>(L.K) * 12; break;
     case SAC_COT_DBG_HYP_RT: dsrc = L.rt + static_cast<size_t>(pair) * L.K * 12; bytes = static_cast<size_t>(L.K) * 48; break;

@@ -201,15 +201,16 @@ int launch_kabsch(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const 
 }
 
 // ------------------------------------------------------------------------------------------
-// S5/S6: each thread scores two hypotheses (held in registers) against all N correspondences,
-// which the CTA stages through shared memory in 256-point slabs laid out as two float4 per
-// point so the inner loop issues two broadcast LDS.128 per point for 2 x 16 FP32 instructions.
+// S5/S6: each thread scores two hypotheses (held in registers, duplicated into packed lanes)
+// against all N correspondences, which the CTA stages through shared memory in 256-point slabs
+// laid out as three float4 per PAIR of correspondences, so the inner loop issues three broadcast
+// LDS.128 per two points for 2 x 15 packed FP32 instructions (FFMA2/FADD2/FMUL2).
 // The packed selection key  score<<16 | (0xFFFF-h)  is max-reduced per warp, per block, and
 // with one 64-bit atomicMax per block into the pair's best key (ties -> lowest h).
 // ------------------------------------------------------------------------------------------
 constexpr int kScoreThreads = 128;
 constexpr int kScoreHyp = 2;     // hypotheses per thread
-constexpr int kScoreSlab = 256;  // points per shared-memory slab
+constexpr int kScoreSlab = 256;  // points per shared-memory slab (even)
 
 __device__ __forceinline__ float residual2(const float (&rt)[12], const float4 a, const float4 b) {
   // a = (sx, sy, sz, dx), b = (dy, dz, -, -)
@@ -220,6 +221,44 @@ __device__ __forceinline__ float residual2(const float (&rt)[12], const float4 a
   return FFMA(ez, ez, FFMA(ey, ey, FMUL(ex, ex)));
 }
 
+// Packed fp32x2 arithmetic (sm_100 FFMA2/FADD2/FMUL2): two correspondences per instruction.  Each
+// lane of a packed op is an individually rounded IEEE operation, so the results are bit-identical
+// to the scalar chain above; every multiply-add here is a specified fma (nothing for ptxas to
+// contract).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// squared residuals of two correspondences under one hypothesis (rt2[k] = {rt[k], rt[k]})
+__device__ __forceinline__ f32x2 residual2_x2(const f32x2 (&rt2)[12], f32x2 px, f32x2 py, f32x2 pz, f32x2 qx, f32x2 qy,
+                                              f32x2 qz) {
+  const f32x2 xp = fma2(rt2[0], px, fma2(rt2[1], py, fma2(rt2[2], pz, rt2[9])));
+  const f32x2 yp = fma2(rt2[3], px, fma2(rt2[4], py, fma2(rt2[5], pz, rt2[10])));
+  const f32x2 zp = fma2(rt2[6], px, fma2(rt2[7], py, fma2(rt2[8], pz, rt2[11])));
+  const f32x2 ex = sub2(xp, qx), ey = sub2(yp, qy), ez = sub2(zp, qz);
+  return fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(
     const PairDesc* __restrict__ descs, const float* __restrict__ soa, const int32_t* __restrict__ tri,
@@ -227,20 +266,24 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
     float tau2, int K, int h_begin, int h_end) {
   const int pair = blockIdx.y;
   const PairDesc d = descs[pair];
-  __shared__ float4 slab[kScoreSlab][2];
+  // slab[p] holds correspondences 2p and 2p+1:  {sx0,sx1,sy0,sy1} {sz0,sz1,dx0,dx1} {dy0,dy1,dz0,dz1}
+  __shared__ float4 slab[kScoreSlab / 2][3];
   __shared__ unsigned long long wbest[kScoreThreads / 32];
 
   const int tid = threadIdx.x;
   int hid[kScoreHyp];
   bool valid[kScoreHyp];
-  float rt[kScoreHyp][12];
+  f32x2 rt2[kScoreHyp][12];
 #pragma unroll
   for (int u = 0; u < kScoreHyp; ++u) {
     hid[u] = h_begin + blockIdx.x * (kScoreThreads * kScoreHyp) + u * kScoreThreads + tid;
     valid[u] = hid[u] < h_end && tri[(static_cast<size_t>(pair) * K + (hid[u] < K ? hid[u] : 0)) * 3] >= 0;
     const float* src_rt = rt_all + (static_cast<size_t>(pair) * K + (hid[u] < K ? hid[u] : 0)) * 12;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) rt[u][k] = valid[u] ? src_rt[k] : 0.0f;
+    for (int k = 0; k < 12; ++k) {
+      const float v = valid[u] ? src_rt[k] : 0.0f;
+      rt2[u][k] = pk(v, v);
+    }
   }
   unsigned int cnt[kScoreHyp];
   unsigned long long fsum[kScoreHyp];
@@ -249,28 +292,44 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
 
   const float* base = soa + d.soa_off;
   const size_t np = static_cast<size_t>(d.Npad);
+  const float nan = __int_as_float(0x7fc00000);
   for (int n0 = 0; n0 < d.N; n0 += kScoreSlab) {
     const int nn = min(kScoreSlab, d.N - n0);
+    const int npairs = (nn + 1) / 2;
     __syncthreads();  // previous slab fully consumed
-    for (int k = tid; k < nn; k += kScoreThreads) {
-      const int n = n0 + k;
-      slab[k][0] = make_float4(base[n], base[np + n], base[2 * np + n], base[3 * np + n]);
-      slab[k][1] = make_float4(base[4 * np + n], base[5 * np + n], 0.0f, 0.0f);
+    for (int k = tid; k < npairs; k += kScoreThreads) {
+      const int n = n0 + 2 * k;
+      // the SoA arrays are padded to Npad (even) with NaN, so n+1 is always readable; a NaN
+      // correspondence never counts as an inlier, and mode 1 masks it explicitly below
+      const float2 sx = *reinterpret_cast<const float2*>(base + n), sy = *reinterpret_cast<const float2*>(base + np + n),
+                   sz = *reinterpret_cast<const float2*>(base + 2 * np + n);
+      float2 dx = *reinterpret_cast<const float2*>(base + 3 * np + n), dy = *reinterpret_cast<const float2*>(base + 4 * np + n),
+             dz = *reinterpret_cast<const float2*>(base + 5 * np + n);
+      if (n + 1 >= d.N) { dx.y = nan; dy.y = nan; dz.y = nan; }
+      slab[k][0] = make_float4(sx.x, sx.y, sy.x, sy.y);
+      slab[k][1] = make_float4(sz.x, sz.y, dx.x, dx.y);
+      slab[k][2] = make_float4(dy.x, dy.y, dz.x, dz.y);
     }
     __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < nn; ++k) {
-      const float4 a = slab[k][0];
-      const float4 b = slab[k][1];
+#pragma unroll 2
+    for (int k = 0; k < npairs; ++k) {
+      const float4 a = slab[k][0], b = slab[k][1], c = slab[k][2];
+      const f32x2 px = pk(a.x, a.y), py = pk(a.z, a.w), pz = pk(b.x, b.y);
+      const f32x2 qx = pk(b.z, b.w), qy = pk(c.x, c.y), qz = pk(c.z, c.w);
+      const bool second = n0 + 2 * k + 1 < d.N;
 #pragma unroll
       for (int u = 0; u < kScoreHyp; ++u) {
-        const float r2 = residual2(rt[u], a, b);
+        float r0, r1;
+        unpk(residual2_x2(rt2[u], px, py, pz, qx, qy, qz), r0, r1);
         if (MODE == 0) {
-          cnt[u] += r2 < tau2 ? 1u : 0u;
+          cnt[u] += (r0 < tau2 ? 1u : 0u) + (r1 < tau2 ? 1u : 0u);  // NaN pad -> false
         } else {
-          const float mm = r2 < tau2 ? r2 : tau2;  // NaN -> tau2
-          const float qn = FDIV(mm, tau2);
-          fsum[u] += static_cast<unsigned int>(FMUL(qn, 1048576.0f));
+          const float m0 = r0 < tau2 ? r0 : tau2;  // NaN -> tau2
+          fsum[u] += static_cast<unsigned int>(FMUL(FDIV(m0, tau2), 1048576.0f));
+          if (second) {
+            const float m1 = r1 < tau2 ? r1 : tau2;
+            fsum[u] += static_cast<unsigned int>(FMUL(FDIV(m1, tau2), 1048576.0f));
+          }
         }
       }
     }
