@@ -210,9 +210,9 @@ class Registrar:
         dev = torch.device("cuda", self.get("device")) if dist.get_backend(group) == "nccl" else torch.device("cpu")
         # u64 payloads travel as int64 bit patterns (same width; all-gather is a pure copy)
         payload = torch.from_numpy(np.concatenate([t_partial, cand]).view(np.int64)).to(dev)
-        gathered = torch.empty((world, payload.numel()), dtype=torch.int64, device=dev)
+        gathered = torch.empty(world * payload.numel(), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(gathered, payload, group=group)                      # exchange #1
-        g = gathered.cpu().numpy().view(np.uint64)
+        g = gathered.cpu().numpy().view(np.uint64).reshape(world, -1)
         N = t_partial.shape[0]
         best = self.sharded_phase2(g[:, :N], g[:, N:])
         # keys are < 2^63 (score < 2^47), so signed max == unsigned max
