@@ -23,7 +23,7 @@ from sac_cot_b200.api import Registrar  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=50000)
+    ap.add_argument("--points", type=int, default=50000)
     ap.add_argument("--ratio", type=float, default=0.05)
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
@@ -36,7 +36,7 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    p = synth.make_pair(args.n, args.ratio, 7000)
+    p = synth.make_pair(args.points, args.ratio, 7000)
     reg = Registrar(device=local)
     times = []
     for _ in range(args.reps):
@@ -61,7 +61,7 @@ def main():
     ang, dtr = synth.pose_error(R, t, p.R_gt, p.t_gt)
     if rank == 0:
         print(json.dumps({
-            "workload": f"single pair N={args.n}, {args.ratio:.0%} inliers, sharded over {world} GPUs",
+            "workload": f"single pair N={args.points}, {args.ratio:.0%} inliers, sharded over {world} GPUs",
             "world": world, "sharded_s": times, "sharded_best_s": min(times), "unsharded_1gpu_s": t_single,
             "all_ranks_bit_identical_to_unsharded": bool(flag.item()), "inliers": int(inl),
             "rot_err_deg": float(np.degrees(ang)), "trans_err": dtr,
