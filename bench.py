@@ -165,6 +165,7 @@ def run_reference(args, rank, world, emit):
 
 
 def main():
+    global WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -178,7 +179,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    global WORKLOAD
     WORKLOAD = args.workload
 
     rank = int(os.environ.get("RANK", "0"))
