@@ -271,7 +271,6 @@ def main():
     recall = ok / pairs
 
     # ---- timed region 1: device-resident (value) ----
-    reg.set("stage_timing", 1)
     launches0 = reg.get("launches")
     sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -289,14 +288,31 @@ def main():
     assert reg.get("last_status") == 0
     launches = reg.get("launches") - launches0
     ms_steps = [a.elapsed_time(b) for a, b in ev]
-    stage_us = {s: reg.get(f"stage_us_{s}") for s in STAGES}
-    stage_calls = {s: reg.get(f"stage_calls_{s}") for s in STAGES}
-    reg.set("stage_timing", 0)
     total_ms = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = world * pairs * args.steps / (total_ms * 1e-3)
+
+    # ---- per-kernel pass: the same K steps on ONE lane (no chunk overlap), every stage bracketed by
+    # CUDA events on the stream it runs on.  With the default two lanes the stages of different
+    # chunks overlap, so their event spans measure contention, not kernel time. ----
+    lanes_default = reg.get("lanes")
+    reg.set("lanes", 1)
+    step_device()
+    torch.cuda.synchronize(dev)
+    reg.set("stage_timing", 1)
+    ev1 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev1[0].record(stream)
+    for k in range(args.steps):
+        step_device()
+    ev1[1].record(stream)
+    torch.cuda.synchronize(dev)
+    serial_ms_per_step = ev1[0].elapsed_time(ev1[1]) / args.steps
+    stage_us = {s: reg.get(f"stage_us_{s}") for s in STAGES}
+    stage_calls = {s: reg.get(f"stage_calls_{s}") for s in STAGES}
+    reg.set("stage_timing", 0)
+    reg.set("lanes", lanes_default)
 
     # ---- timed region 2: end to end through the host-buffer C-ABI call (e2e) ----
     step_host()  # warm the host path (arena regrows once: it now also holds the input copy)
@@ -346,6 +362,8 @@ def main():
                   "frac": wordops / (tri_us * 1e-6) / popc_peak, "edges_per_pair": E_mean, "words_per_row": stride},
         "stage_share": {s: stage_us[s] / max(1, sum(stage_us.values())) for s in STAGES},
         "stage_us_per_step": {s: stage_us[s] / args.steps for s in STAGES},
+        "timing": f"CUDA events around every stage over {args.steps} steps on one lane "
+                  f"({serial_ms_per_step:.2f} ms/step without chunk overlap; the headline uses {lanes_default} lanes)",
     }
 
     # ---- CPU baseline: the from-paper oracle on this box's host cores (rank 0, N = 1 only) ----

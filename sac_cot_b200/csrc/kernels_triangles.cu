@@ -78,6 +78,25 @@ struct LaneWords {
       w[4 * A + b] = idx < wc ? row[idx] : 0u;
     }
   }
+  // same as and_popc, addressing the staged row by 32-bit shared-window addresses: `a128` =
+  // row address + 16*lane (128-bit rounds), `a32` = row address + 4*(128*A + lane) (32-bit rounds)
+  __device__ __forceinline__ int and_popc_saddr(uint32_t a128, uint32_t a32) const {
+    uint32_t x[R];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      uint32_t v0, v1, v2, v3;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(a128 + 512u * a));
+      x[4 * a + 0] = w[4 * a + 0] & v0; x[4 * a + 1] = w[4 * a + 1] & v1;
+      x[4 * a + 2] = w[4 * a + 2] & v2; x[4 * a + 3] = w[4 * a + 3] & v3;
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      uint32_t v;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a32 + 128u * b));
+      x[4 * A + b] = w[4 * A + b] & v;
+    }
+    return PopcSum<R>::run(x);
+  }
   __device__ __forceinline__ int and_popc(const uint32_t* __restrict__ srow, int lane) const {
     uint32_t x[R];
 #pragma unroll
@@ -157,10 +176,10 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
   uint32_t* cur = tJ + JB;                                                // [NB][256] unit cursors
   uint64_t* bar = reinterpret_cast<uint64_t*>(cur + NB * 256);            // mbarrier
   int* next_row = reinterpret_cast<int*>(bar + 1);                        // dynamic row cursor
-  uint8_t* elist_all = reinterpret_cast<uint8_t*>(bar + 2);               // [NWARP][JB]
+  uint16_t* elist_all = reinterpret_cast<uint16_t*>(bar + 2);             // [NWARP][JB]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint8_t* elist = elist_all + warp * JB;
+  uint16_t* elist = elist_all + warp * JB;
   for (int k = tid; k < kHistBins; k += THREADS) hist_s[k] = 0;
   for (int k = tid; k < JB + NB * 256; k += THREADS) tJ[k] = 0;  // tJ and cur are contiguous
   if (tid == 0) {
@@ -206,6 +225,8 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
   };
   fetch();
   mbar_wait(bar, 0);
+  const uint32_t sa128 = smem_u32(rows) + 16u * lane;
+  const uint32_t sa32 = smem_u32(rows) + 4u * (128u * LaneWords<R>::A + lane);
 
   while (i_next < row_end) {
     const int i = i_next;
@@ -248,14 +269,14 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
       pos[0] = ub[0] + off0;
       if (NB == 2) pos[NB - 1] = ub[NB - 1] + off1;
     }
-    // edge columns in ascending order -> elist
+    // edge columns in ascending order -> elist (one u16 per edge: the local column jl)
     __syncwarp();  // the previous row's elist has been consumed by every lane
     {
       int o = incl - cnt;
       while (bits) {
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
-        elist[o++] = static_cast<uint8_t>(8 * lane + b);
+        elist[o++] = static_cast<uint16_t>(8 * lane + b);
       }
     }
     __syncwarp();
@@ -264,11 +285,23 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
 
     const unsigned long long ikey = static_cast<unsigned long long>(0xFFFFu - static_cast<unsigned int>(i)) << 16;
     const unsigned int jkey0 = 0xFFFFu - static_cast<unsigned int>(J0);  // (0xFFFF - j) = jkey0 - jl
-    unsigned int myT = 0, tsum = 0;
-    auto flush = [&](int q0, int cntq) {  // bookkeeping for up to 32 edges, one per lane
+    unsigned int tsum = 0;
+    // edges in groups of 32: lane k of the group keeps T of the group's k-th edge, then all lanes
+    // do the bookkeeping (key store, histogram, J-side node sum) for their edge at once
+    for (int q0 = 0; q0 < n; q0 += 32) {
+      const int cntq = min(32, n - q0);
+      unsigned int myT = 0;
+      const uint16_t* el = elist + q0;
+#pragma unroll 4
+      for (int k = 0; k < cntq; ++k) {
+        const uint32_t roff = static_cast<uint32_t>(el[k]) * (PITCH * 4u);
+        const int s = ri.and_popc_saddr(roff + sa128, roff + sa32);
+        const unsigned int T = static_cast<unsigned int>(__reduce_add_sync(0xffffffffu, s));
+        if (lane == k) myT = T;
+      }
       if (lane < cntq) {
         const int q = q0 + lane;
-        const unsigned int myJ = elist[q];
+        const unsigned int myJ = el[lane];
         uint32_t at = pos[0] + static_cast<uint32_t>(q);
         if (NB == 2 && q >= n0) at = pos[NB - 1] + static_cast<uint32_t>(q - n0);
         keyp[at] = (static_cast<unsigned long long>(myT) << 32) | ikey | static_cast<unsigned long long>(jkey0 - myJ);
@@ -276,16 +309,7 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
         atomicAdd(&tJ[myJ], myT);
         tsum += myT;
       }
-    };
-#pragma unroll 4
-    for (int q = 0; q < n; ++q) {
-      const int jl = elist[q];
-      const int s = ri.and_popc(rows + jl * PITCH, lane);
-      const unsigned int T = static_cast<unsigned int>(__reduce_add_sync(0xffffffffu, s));
-      if (lane == (q & 31)) myT = T;
-      if ((q & 31) == 31) flush(q - 31, 32);
     }
-    if (n & 31) flush(n & ~31, n & 31);
     tsum = __reduce_add_sync(0xffffffffu, tsum);
     if (lane == 0) atomicAdd(&t2[d.node_off + i], static_cast<unsigned long long>(tsum));
   }
@@ -469,7 +493,7 @@ __global__ void __launch_bounds__(kTriThreads) triangles_chunked_kernel(
 // ------------------------------------------------------------------------------------------
 static size_t block_smem_bytes(int R, int JB, int threads) {
   return static_cast<size_t>(JB) * 32 * R * 4 + kHistBins * 4 + JB * 4 + (JB / 128) * 256 * 4 + 16 +
-         static_cast<size_t>(threads / 32) * JB;
+         static_cast<size_t>(threads / 32) * JB * 2;
 }
 static size_t chunked_smem_bytes(int R) {
   return static_cast<size_t>(kTriJ) * 32 * R * 4 + kHistBins * 4 + kTriJ * 4 + 16 + (kTriThreads / 32) * kTriJ +
