@@ -110,9 +110,21 @@ __device__ __forceinline__ f32x2 sum_sq(f32x2 a, f32x2 b, f32x2 c) {
   return pack2(__fadd_rn(__fadd_rn(aa0, bb0), cc0), __fadd_rn(__fadd_rn(aa1, bb1), cc1));
 }
 
-// literal evaluation of the specified predicate from the squared lengths
-__device__ __noinline__ bool compat_literal(float x, float y, float tau) {
-  return fabsf(__fsub_rn(__fsqrt_rn(x), __fsqrt_rn(y))) < tau;
+// Literal evaluation of the specified predicate for the four columns c..c+3 of the staged tile:
+// the rare fallback of the filter.  Out of line and self-contained (recomputes the squared lengths
+// with the same individually rounded operations) so that it costs the hot loop nothing but a flag.
+__device__ __noinline__ uint32_t compat_literal4(const float (*cs)[128], int c, float sxi, float syi, float szi,
+                                                 float dxi, float dyi, float dzi, float tau) {
+  uint32_t bits = 0;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const float a = __fsub_rn(sxi, cs[0][c + k]), b = __fsub_rn(syi, cs[1][c + k]), cc = __fsub_rn(szi, cs[2][c + k]);
+    const float x = __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(cc, cc));
+    const float e = __fsub_rn(dxi, cs[3][c + k]), f = __fsub_rn(dyi, cs[4][c + k]), g = __fsub_rn(dzi, cs[5][c + k]);
+    const float y = __fadd_rn(__fadd_rn(__fmul_rn(e, e), __fmul_rn(f, f)), __fmul_rn(g, g));
+    if (fabsf(__fsub_rn(__fsqrt_rn(x), __fsqrt_rn(y))) < tau) bits |= 1u << k;
+  }
+  return bits;
 }
 
 // out[lane] bit r = in[r] bit lane, for the 32 lanes of a warp
@@ -160,13 +172,13 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
 #pragma unroll
     for (int c = 0; c < 6; ++c) bulk_g2s(&cs[c][0], base + static_cast<size_t>(c) * d.Npad + J0, 128 * sizeof(float), &bar);
   }
-  // own row point (coalesced), overlapped with the bulk copies; duplicated into both packed lanes
+  // own row point (coalesced), overlapped with the bulk copies
+  float rv[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) rv[c] = base[static_cast<size_t>(c) * d.Npad + I0 + r];
   f32x2 ri[6];
 #pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    const float v = base[static_cast<size_t>(c) * d.Npad + I0 + r];
-    ri[c] = pack2(v, v);
-  }
+  for (int c = 0; c < 6; ++c) ri[c] = pack2(rv[c], rv[c]);  // SASS uses the scalar-broadcast operand form
   const f32x2 ntau2 = pack2(-tau2f, -tau2f);
   const f32x2 m4 = pack2(-4.0f, -4.0f);
   const f32x2 kth = pack2(1.9073486328125e-06f, 1.9073486328125e-06f);  // 2^-19
@@ -176,38 +188,40 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
 #pragma unroll
   for (int cw = 0; cw < 4; ++cw) {
     uint32_t wbits = 0;
-#pragma unroll 4
-    for (int b = 0; b < 32; b += 2) {
+#pragma unroll 2
+    for (int b = 0; b < 32; b += 4) {
       const int c = cw * 32 + b;
-      f32x2 cj[6];
+      float4 cj[6];  // four staged columns per 128-bit broadcast load
 #pragma unroll
-      for (int k = 0; k < 6; ++k) cj[k] = *reinterpret_cast<const f32x2*>(&cs[k][c]);
-      // squared lengths, op order of the specification:  (a*a + b*b) + c*c.  Differences and
-      // squares are packed; the two additions are scalar add.rn.f32, which ptxas never contracts
-      // (it does fuse mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would break the rounding spec).
-      const f32x2 x = sum_sq(sub2(ri[0], cj[0]), sub2(ri[1], cj[1]), sub2(ri[2], cj[2]));
-      const f32x2 y = sum_sq(sub2(ri[3], cj[3]), sub2(ri[4], cj[4]), sub2(ri[5], cj[5]));
-      // exact filter
-      const f32x2 S = add2(x, y);
-      const f32x2 U = add2(S, ntau2);
-      const f32x2 Q = fma2(mul2(x, y), m4, mul2(U, U));
-      const f32x2 T = mul2(mul2(S, S), kth);
-      float q0, q1, t0, t1, s0, s1;
-      unpack2(Q, q0, q1);
-      unpack2(T, t0, t1);
-      unpack2(S, s0, s1);
-      bool p0 = q0 < 0.0f, p1 = q1 < 0.0f;
-      const bool sure0 = fabsf(q0) > t0 && s0 > lo;
-      const bool sure1 = fabsf(q1) > t1 && s1 > lo;
-      if (!(sure0 && sure1)) {  // rare: inside the rounding band, or out-of-range magnitudes / NaN
-        float x0, x1, y0, y1;
-        unpack2(x, x0, x1);
-        unpack2(y, y0, y1);
-        if (!sure0) p0 = compat_literal(x0, y0, tau);
-        if (!sure1) p1 = compat_literal(x1, y1, tau);
+      for (int k = 0; k < 6; ++k) cj[k] = *reinterpret_cast<const float4*>(&cs[k][c]);
+      bool sure = true;
+      uint32_t nib = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // two packed column pairs
+        f32x2 col[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) col[k] = h == 0 ? pack2(cj[k].x, cj[k].y) : pack2(cj[k].z, cj[k].w);
+        // squared lengths, op order of the specification:  (a*a + b*b) + c*c.  Differences and
+        // squares are packed; the two additions are scalar add.rn.f32, which ptxas never contracts
+        // (it does fuse mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would break the rounding spec).
+        const f32x2 x = sum_sq(sub2(ri[0], col[0]), sub2(ri[1], col[1]), sub2(ri[2], col[2]));
+        const f32x2 y = sum_sq(sub2(ri[3], col[3]), sub2(ri[4], col[4]), sub2(ri[5], col[5]));
+        // exact filter: trust sign(Q) iff |Q| > Theta and S > lo
+        const f32x2 S = add2(x, y);
+        const f32x2 U = add2(S, ntau2);
+        const f32x2 Q = fma2(mul2(x, y), m4, mul2(U, U));
+        const f32x2 T = mul2(mul2(S, S), kth);
+        float q0, q1, t0, t1, s0, s1;
+        unpack2(Q, q0, q1);
+        unpack2(T, t0, t1);
+        unpack2(S, s0, s1);
+        sure = sure && fabsf(q0) > t0 && s0 > lo && fabsf(q1) > t1 && s1 > lo;
+        nib |= (__float_as_uint(q0) >> 31) << (2 * h);      // bit = (Q < 0) when sure
+        nib |= (__float_as_uint(q1) >> 31) << (2 * h + 1);
       }
-      wbits |= (p0 ? 1u : 0u) << b;
-      wbits |= (p1 ? 1u : 0u) << (b + 1);
+      if (!sure)  // rare: inside the rounding band, out-of-range magnitudes, or NaN (pad columns)
+        nib = compat_literal4(cs, c, rv[0], rv[1], rv[2], rv[3], rv[4], rv[5], tau);
+      wbits |= nib << b;
     }
     words[cw] = wbits;
   }
