@@ -175,7 +175,6 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
   uint32_t* tJ = hist_s + kHistBins;                                      // [JB]
   uint32_t* cur = tJ + JB;                                                // [NB][256] unit cursors
   uint64_t* bar = reinterpret_cast<uint64_t*>(cur + NB * 256);            // mbarrier
-  int* next_row = reinterpret_cast<int*>(bar + 1);                        // dynamic row cursor
   uint16_t* elist_all = reinterpret_cast<uint16_t*>(bar + 2);             // [NWARP][JB]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -183,7 +182,6 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
   for (int k = tid; k < kHistBins; k += THREADS) hist_s[k] = 0;
   for (int k = tid; k < JB + NB * 256; k += THREADS) tJ[k] = 0;  // tJ and cur are contiguous
   if (tid == 0) {
-    *next_row = 0;
     mbar_init(bar, 1);
     mbar_fence_init();
   }
@@ -202,41 +200,51 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
   const uint32_t* ubp = ubase + static_cast<size_t>(pair) * unit_pitch;
   const int row_end = min(d.N, J0 + jrows - 1);  // rows i >= row_end have no neighbour j > i in the block
 
-  // ---- software pipeline: the next row visit is fetched while the current one is processed ----
+  // ---- row visits: warp w takes rows w, w+NWARP, ... (edge counts per row vary little, so a static
+  // interleave balances well and costs no atomics); the next visit's data is prefetched into a
+  // second register set while the current one is processed (two copies of the body, no moves) ----
   // Edge bits travel one byte per lane: lane l holds the bits of columns J0+8l .. J0+8l+7
   // (JB = 256 -> 32 bytes, JB = 128 -> lanes 0..15).
+  constexpr int NWARP = THREADS / 32;
   const uint32_t unit0 = unit_offset(jb0), unit1 = NB == 2 ? unit_offset(jb0 + 1) : 0u;
   const bool sub1 = NB == 2 && jrows > 128;  // second 128-column sub-block exists
-  int i_next;
-  uint32_t byte_next = 0;
-  LaneWords<R> ri_next;
-  uint32_t ub_next[NB];
-  auto fetch = [&]() {
-    int rr = 0;
-    if (lane == 0) rr = atomicAdd(next_row, 1);
-    i_next = __shfl_sync(0xffffffffu, rr, 0);
-    if (i_next < row_end) {
-      const uint32_t* rowp = adjp + static_cast<size_t>(i_next) * stride;
-      byte_next = lane < jrows / 8 ? reinterpret_cast<const uint8_t*>(rowp + J0 / 32)[lane] : 0u;
-      ri_next.load_global(rowp, lane, stride);
-      ub_next[0] = ubp[unit0 + (static_cast<unsigned int>(i_next) >> 8)];
-      if (NB == 2) ub_next[NB - 1] = sub1 ? ubp[unit1 + (static_cast<unsigned int>(i_next) >> 8)] : 0u;
-    }
+  // per-lane base pointers (row 0) and validity, loop invariant
+  const uint8_t* pbyte = reinterpret_cast<const uint8_t*>(adjp + J0 / 32) + lane;
+  const bool has_byte = lane < jrows / 8;
+  const uint32_t* pw128 = adjp + 4 * lane;
+  const uint32_t* pw32 = adjp + 128 * LaneWords<R>::A + lane;
+  bool ok128[LaneWords<R>::A > 0 ? LaneWords<R>::A : 1], ok32[LaneWords<R>::B > 0 ? LaneWords<R>::B : 1];
+#pragma unroll
+  for (int a = 0; a < LaneWords<R>::A; ++a) ok128[a] = 128 * a + 4 * lane < stride;
+#pragma unroll
+  for (int b = 0; b < LaneWords<R>::B; ++b) ok32[b] = 128 * LaneWords<R>::A + 32 * b + lane < stride;
+
+  struct Visit {
+    uint32_t byte;
+    LaneWords<R> ri;
+    uint32_t ub[NB];
   };
-  fetch();
-  mbar_wait(bar, 0);
+  auto fetch = [&](int i, Visit& v) {
+    if (i >= row_end) return;
+    const size_t off = static_cast<size_t>(i) * stride;  // words
+    v.byte = has_byte ? pbyte[off * 4] : 0u;
+#pragma unroll
+    for (int a = 0; a < LaneWords<R>::A; ++a) {
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      if (ok128[a]) q = *reinterpret_cast<const uint4*>(pw128 + off + 128 * a);
+      v.ri.w[4 * a + 0] = q.x; v.ri.w[4 * a + 1] = q.y; v.ri.w[4 * a + 2] = q.z; v.ri.w[4 * a + 3] = q.w;
+    }
+#pragma unroll
+    for (int b = 0; b < LaneWords<R>::B; ++b) v.ri.w[4 * LaneWords<R>::A + b] = ok32[b] ? pw32[off + 32 * b] : 0u;
+    v.ub[0] = ubp[unit0 + (static_cast<unsigned int>(i) >> 8)];
+    if (NB == 2) v.ub[NB - 1] = sub1 ? ubp[unit1 + (static_cast<unsigned int>(i) >> 8)] : 0u;
+  };
   const uint32_t sa128 = smem_u32(rows) + 16u * lane;
   const uint32_t sa32 = smem_u32(rows) + 4u * (128u * LaneWords<R>::A + lane);
+  const unsigned int jkey0 = 0xFFFFu - static_cast<unsigned int>(J0);  // (0xFFFF - j) = jkey0 - jl
 
-  while (i_next < row_end) {
-    const int i = i_next;
-    uint32_t bits = byte_next;
-    const LaneWords<R> ri = ri_next;
-    uint32_t ub[NB];
-#pragma unroll
-    for (int s = 0; s < NB; ++s) ub[s] = ub_next[s];
-    fetch();
-
+  auto process = [&](int i, const Visit& v) {
+    uint32_t bits = v.byte;
     if (i >= J0) {  // diagonal region: keep only columns j > i
       const int li = i - J0;
       if (8 * lane + 7 <= li) bits = 0u;
@@ -251,11 +259,11 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
     }
     const int n = __shfl_sync(0xffffffffu, incl, 31);
-    if (n == 0) continue;
+    if (n == 0) return;
     const int n0 = NB == 2 ? __shfl_sync(0xffffffffu, incl, 15) : n;  // edges in the first sub-block
 
     // sub-range of each unit's key region for this row visit (lane 0 asks the unit cursors)
@@ -266,8 +274,8 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
         if (n0) off0 = atomicAdd(&cur[i >> 8], static_cast<uint32_t>(n0));
         if (NB == 2 && n > n0) off1 = atomicAdd(&cur[256 + (i >> 8)], static_cast<uint32_t>(n - n0));
       }
-      pos[0] = ub[0] + off0;
-      if (NB == 2) pos[NB - 1] = ub[NB - 1] + off1;
+      pos[0] = v.ub[0] + off0;
+      if (NB == 2) pos[NB - 1] = v.ub[NB - 1] + off1;
     }
     // edge columns in ascending order -> elist (one u16 per edge: the local column jl)
     __syncwarp();  // the previous row's elist has been consumed by every lane
@@ -284,7 +292,6 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
     for (int s = 0; s < NB; ++s) pos[s] = __shfl_sync(0xffffffffu, pos[s], 0);
 
     const unsigned long long ikey = static_cast<unsigned long long>(0xFFFFu - static_cast<unsigned int>(i)) << 16;
-    const unsigned int jkey0 = 0xFFFFu - static_cast<unsigned int>(J0);  // (0xFFFF - j) = jkey0 - jl
     unsigned int tsum = 0;
     // edges in groups of 32: lane k of the group keeps T of the group's k-th edge, then all lanes
     // do the bookkeeping (key store, histogram, J-side node sum) for their edge at once
@@ -295,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
 #pragma unroll 4
       for (int k = 0; k < cntq; ++k) {
         const uint32_t roff = static_cast<uint32_t>(el[k]) * (PITCH * 4u);
-        const int s = ri.and_popc_saddr(roff + sa128, roff + sa32);
+        const int s = v.ri.and_popc_saddr(roff + sa128, roff + sa32);
         const unsigned int T = static_cast<unsigned int>(__reduce_add_sync(0xffffffffu, s));
         if (lane == k) myT = T;
       }
@@ -312,6 +319,20 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
     }
     tsum = __reduce_add_sync(0xffffffffu, tsum);
     if (lane == 0) atomicAdd(&t2[d.node_off + i], static_cast<unsigned long long>(tsum));
+  };
+
+  Visit va, vb;
+  int i = warp;
+  fetch(i, va);
+  mbar_wait(bar, 0);
+  while (i < row_end) {
+    fetch(i + NWARP, vb);
+    process(i, va);
+    i += NWARP;
+    if (i >= row_end) break;
+    fetch(i + NWARP, va);
+    process(i, vb);
+    i += NWARP;
   }
   __syncthreads();
 
