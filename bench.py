@@ -352,9 +352,17 @@ def main():
     wordops = E_mean * stride * pairs_per_launch               # AND+POPC on 32-bit words
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     popc_peak = 16 * 148 * sm_mhz * 1e6                        # nominal 16 POPC/clk/SM
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture, scaled per launch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and WORKLOAD == "cfg2_3dmatch_256x5000":
+        tj = json.load(open(tpath))["triangles_block_kernel"]
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pairs_in_launch"] * pairs_per_launch
     roofline = {
-        "kernel": "triangles_kernel<5> (S2, POPC bitset)", "bound": "hbm", "achieved": achieved_gbs,
-        "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "kernel": "triangles_block_kernel<5,256,1024> (S2, POPC bitset)", "bound": "hbm", "achieved": achieved_gbs,
+        "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs, "traffic": traffic,
+        "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/ncu_traffic.json)",
+        "algorithmic_bytes_per_launch": tri_bytes_pair * pairs_per_launch, "peak_source": peak_src,
         "launch_us": tri_us, "pairs_per_launch": pairs_per_launch, "algorithmic_bytes_per_pair": tri_bytes_pair,
         "note": "S2 is bound by POPC/ALU issue, not HBM (arithmetic intensity ~ 40 word-ops/B): the HBM "
                 "fraction is small by construction; the issue-side figure is in `issue`",

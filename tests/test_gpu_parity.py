@@ -334,3 +334,24 @@ def test_graph_huge_threshold_takes_literal_path(gpu, oracle):
     p = synth.make_pair(257, 0.2, 77)
     E = _adj_parity(gpu, oracle, p.src, p.dst, 1e30)   # 4*tau^2 overflows: every pair decided literally
     assert E == 257 * 256 // 2
+
+
+def test_cfg5_single_pair_n50000_full_stage_parity(gpu_lib, oracle_omp_lib):
+    # BASELINE.json configs[4]: 2.5e9-entry compatibility matrix, 9.4e7 edges, chunked-row triangle
+    # kernel.  The OpenMP build of the oracle (thread-count independent by construction) keeps the
+    # CPU side to a few seconds per core-minute.
+    p = synth.make_config_pair("cfg5_single_n50000", 0)
+    with Registrar(lib=gpu_lib) as g, Registrar(lib=oracle_omp_lib) as o:
+        for r in (g, o):
+            r.set("keep_debug", 1)
+            set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
+        out_g = g.register(p.src, p.dst)
+        out_o = o.register(p.src, p.dst)
+        compare_stages(g, o, stages=[s for s in EXACT if s[0] != "adj"])
+        # adjacency: 313 MB per side; compare through a checksum of 64-bit words plus the counts above
+        ag = g.debug(0, _abi.DBG_ADJ).view(np.uint64)
+        ao = o.debug(0, _abi.DBG_ADJ).view(np.uint64)
+        assert ag.shape == ao.shape and bool((ag == ao).all())
+        compare_pose(*out_g, *out_o)
+        ang, dt = synth.pose_error(out_g[0], out_g[1], p.R_gt, p.t_gt)
+        assert ang < np.deg2rad(1.0) and dt < 0.02
