@@ -512,6 +512,10 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
       chunk = (B + nchunks - 1) / std::max(1, nchunks);
     }
   }
+  if (chunk > 32768) {  // pairs index blockIdx.y (<= 65535)
+    if (ctx->keep_debug) return SAC_COT_E_SIZE;
+    chunk = 32768;
+  }
   const int nchunks = (B + chunk - 1) / chunk;
   lanes = std::min(lanes, nchunks);
   ctx->prm = *params;

@@ -355,3 +355,26 @@ def test_cfg5_single_pair_n50000_full_stage_parity(gpu_lib, oracle_omp_lib):
         compare_pose(*out_g, *out_o)
         ang, dt = synth.pose_error(out_g[0], out_g[1], p.R_gt, p.t_gt)
         assert ang < np.deg2rad(1.0) and dt < 0.02
+
+
+def test_many_tiny_pairs_and_repeated_calls_on_one_ctx(gpu_lib, oracle_lib):
+    # thousands of tiny pairs (several chunks over two lanes), then a larger call on the same ctx
+    # (workspace regrowth), then the tiny batch again: results never depend on call history
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(3, 40, size=3000)
+    pairs = [synth.make_pair(int(n), 0.5, 9000 + k) for k, n in enumerate(sizes)]
+    S, D = [p.src for p in pairs], [p.dst for p in pairs]
+    with Registrar(lib=gpu_lib, num_edges=32, apex_per_edge=2) as g, \
+            Registrar(lib=oracle_lib, num_edges=32, apex_per_edge=2) as o:
+        g.set("chunk_pairs", 700)
+        r1 = g.register_batch(S, D)
+        ro = o.register_batch(S, D)
+        np.testing.assert_array_equal(r1.inliers, ro.inliers)
+        for b in range(0, 3000, 97):
+            compare_pose(r1.R[b], r1.t[b], r1.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
+        big = synth.make_pair(4000, 0.05, 9999)
+        g.register(big.src, big.dst)
+        r2 = g.register_batch(S, D)
+        np.testing.assert_array_equal(r1.R, r2.R)
+        np.testing.assert_array_equal(r1.t, r2.t)
+        np.testing.assert_array_equal(r1.inliers, r2.inliers)
