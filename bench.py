@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU per step (default: the config's 256)")
     ap.add_argument("--chunk-pairs", type=int, default=0, help="library knob chunk_pairs (0 = auto)")
     ap.add_argument("--lanes", type=int, default=0, help="library knob lanes (0 = library default)")
+    ap.add_argument("--triangle-path", type=int, default=-1, help="library knob triangle_path (0 POPC, 1 tensor core)")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(synth.CONFIGS),
                     help="synthetic config (default: the headline config, BASELINE.json configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,6 +224,8 @@ def main():
         reg.set("chunk_pairs", args.chunk_pairs)
     if args.lanes:
         reg.set("lanes", args.lanes)
+    if args.triangle_path >= 0:
+        reg.set("triangle_path", args.triangle_path)
     K = reg.params.num_edges * reg.params.apex_per_edge
 
     # device-resident inputs / outputs

@@ -45,6 +45,7 @@ struct Layout {
   uint32_t* hist = nullptr;
   unsigned long long* t2 = nullptr;
   uint32_t* ucount = nullptr;  // edges per triangle work unit, [pairs][unit_pitch]
+  uint32_t* ucursor = nullptr; // per-unit key cursors (tensor-core triangle path only)
   size_t zero_bytes = 0;
   uint32_t* ubase = nullptr;   // key offset per unit inside the pair's key slice
   int unit_pitch = 0;
@@ -150,6 +151,7 @@ struct sac_cot_ctx {
   bool keep_debug = false;
   int chunk_pairs = 0;
   int n_lanes = 2;
+  int tri_path = 0;  // 0 = POPC bitset kernels, 1 = tensor-core (tcgen05 mxf4) kernel
   int64_t launches = 0;
   int64_t retries = 0;
   int deferred_status = 0;  // device-location calls: status discovered after the fact
@@ -234,6 +236,7 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_t2 = take(sizeof(unsigned long long) * node);
   L.unit_pitch = static_cast<int>(unit_count(static_cast<unsigned int>(L.max_nblk)));
   const size_t o_ucount = take(sizeof(uint32_t) * L.unit_pitch * pairs);
+  const size_t o_ucursor = take(sizeof(uint32_t) * L.unit_pitch * pairs);
   L.zero_bytes = off;
   const size_t o_ubase = take(sizeof(uint32_t) * L.unit_pitch * pairs);
   const size_t o_desc = take(sizeof(PairDesc) * pairs);
@@ -259,6 +262,7 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.hist = reinterpret_cast<uint32_t*>(o_hist);
   L.t2 = reinterpret_cast<unsigned long long*>(o_t2);
   L.ucount = reinterpret_cast<uint32_t*>(o_ucount);
+  L.ucursor = reinterpret_cast<uint32_t*>(o_ucursor);
   L.ubase = reinterpret_cast<uint32_t*>(o_ubase);
   L.desc = reinterpret_cast<PairDesc*>(o_desc);
   L.in_src = need_input_copy ? reinterpret_cast<float*>(o_insrc) : nullptr;
@@ -289,6 +293,7 @@ void bind(Layout& L, unsigned char* base, bool has_input) {
   L.hist = rebase(L.hist, base);
   L.t2 = rebase(L.t2, base);
   L.ucount = rebase(L.ucount, base);
+  L.ucursor = rebase(L.ucursor, base);
   L.ubase = rebase(L.ubase, base);
   L.desc = rebase(L.desc, base);
   L.in_src = rebase(L.in_src, base, has_input);
@@ -403,8 +408,12 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world));
   KL_TRY(launch_key_scan(lc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap));
   mark(ST_SCAN);
-  KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ln.keys, L.ubase,
-                          L.unit_pitch, L.hist, L.t2, rank, world));
+  if (ctx->tri_path == 1)
+    KL_TRY(launch_triangles_mma(lc, L.desc, L.pairs, L.max_npad, L.adj, L.state, L.chunk, ln.keys, L.ubase, L.ucursor,
+                                L.unit_pitch, L.hist, L.t2, rank, world));
+  else
+    KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ln.keys, L.ubase,
+                            L.unit_pitch, L.hist, L.t2, rank, world));
   mark(ST_TRIANGLES);
   KL_TRY(launch_select_edges(lc, L.pairs, L.state, L.chunk, ln.keys, L.hist, L.sel, L.tie, L.top, L.Ke));
   mark(ST_SELECT);
@@ -622,7 +631,8 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
   }
   if (e != cudaSuccess) { sac_cot_ctx_destroy(ctx); return static_cast<int>(e); }
   std::memset(ctx->h_sticky, 0, sizeof(StickyDev));
-  const int rc = triangles_configure();
+  int rc = triangles_configure();
+  if (rc >= 0) rc = triangles_mma_configure();
   if (rc < 0) { sac_cot_ctx_destroy(ctx); return -rc; }
   *out = ctx;
   return SAC_COT_OK;
@@ -662,7 +672,11 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     ctx->n_lanes = static_cast<int>(value);
     return SAC_COT_OK;
   }
-  if (!std::strcmp(name, "triangle_path")) return value == 0 ? SAC_COT_OK : SAC_COT_E_UNSUPPORTED;
+  if (!std::strcmp(name, "triangle_path")) {
+    if (value != 0 && value != 1) return SAC_COT_E_UNSUPPORTED;
+    ctx->tri_path = static_cast<int>(value);
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "stage_timing")) {
     cudaSetDevice(ctx->device);
     ctx->timer.reset();
@@ -686,6 +700,7 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
   if (!std::strcmp(name, "device")) { *value = ctx->device; return SAC_COT_OK; }
   if (!std::strcmp(name, "sm_count")) { *value = ctx->sm_count; return SAC_COT_OK; }
   if (!std::strcmp(name, "lanes")) { *value = ctx->n_lanes; return SAC_COT_OK; }
+  if (!std::strcmp(name, "triangle_path")) { *value = ctx->tri_path; return SAC_COT_OK; }
   if (!std::strcmp(name, "threads")) { *value = 0; return SAC_COT_OK; }
   if (!std::strncmp(name, "stage_us_", 9) || !std::strncmp(name, "stage_calls_", 12)) {
     const bool us = name[6] == 'u';

@@ -145,6 +145,13 @@ int launch_triangles(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
                      int world);
 int triangles_configure();  // opt-in dynamic shared memory; call once per device
 
+// kernels_triangles_mma.cu — S2 triangle counts on the tensor cores (tcgen05 kind::mxf4, TMEM)
+int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
+                         PairDev* d_state, const ChunkDev* d_chunk, unsigned long long* d_keys, const uint32_t* d_ubase,
+                         uint32_t* d_ucursor, int unit_pitch, uint32_t* d_hist, unsigned long long* d_t2, int rank,
+                         int world);
+int triangles_mma_configure();
+
 // kernels_select.cu — S3 edge ranking + apex selection
 int launch_select_edges(const LaunchCtx& lc, int pairs, PairDev* d_state, const ChunkDev* d_chunk,
                         const unsigned long long* d_keys, const uint32_t* d_hist, unsigned long long* d_sel,

@@ -378,3 +378,33 @@ def test_many_tiny_pairs_and_repeated_calls_on_one_ctx(gpu_lib, oracle_lib):
         np.testing.assert_array_equal(r1.R, r2.R)
         np.testing.assert_array_equal(r1.t, r2.t)
         np.testing.assert_array_equal(r1.inliers, r2.inliers)
+
+
+# ---- tensor-core triangle path (tcgen05 kind::mxf4, TMEM accumulators) ---------------------------
+@pytest.mark.parametrize("N,ratio", [(64, 0.3), (129, 0.3), (500, 0.2), (1000, 0.1), (2048, 0.1), (5000, 0.05)])
+def test_tensor_core_triangle_path_matches_oracle(gpu, oracle, N, ratio):
+    gpu.set("triangle_path", 1)
+    assert gpu.get("triangle_path") == 1
+    p = synth.make_pair(N, ratio, 8800 + N)
+    run_both(gpu, oracle, p, num_edges=256, apex_per_edge=4)
+
+
+def test_tensor_core_path_batch_and_complete_graph(gpu, oracle):
+    gpu.set("triangle_path", 1)
+    # complete graph: every T equals N-2 (exact integers out of the fp32 accumulators)
+    N = 300
+    p = synth.make_pair(N, 1.0, 8900)
+    dst = (p.src.astype(np.float64) @ p.R_gt.T + p.t_gt).astype(np.float32)
+    for r in (gpu, oracle):
+        set_params(r, num_edges=128, apex_per_edge=4)
+    out_g = gpu.register(p.src, dst)
+    out_o = oracle.register(p.src, dst)
+    compare_stages(gpu, oracle)
+    compare_pose(*out_g, *out_o)
+    # ragged batch
+    pairs = [synth.make_pair(n, 0.1, 8950 + k) for k, n in enumerate((300, 1000, 129, 2048, 64, 777))]
+    rg = gpu.register_batch([q.src for q in pairs], [q.dst for q in pairs])
+    ro = oracle.register_batch([q.src for q in pairs], [q.dst for q in pairs])
+    for b in range(len(pairs)):
+        compare_stages(gpu, oracle, b)
+        compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
