@@ -98,6 +98,9 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *        chunk = whole batch), "chunk_pairs" (pairs per kernel wave, 0 = auto), "lanes" (1..4
  *        internal streams the chunks of a batch are dealt to, default 2; GPU only),
  *        "triangle_path" (0 = POPC bitset, 1 = tensor-core dense; GPU only),
+ *        "triangle_prune" (tensor-core path, default 1: keep only edge keys whose count reaches
+ *        a per-pair threshold proven to lie at or below the K_e-th largest count; results are
+ *        unchanged, SAC_COT_DBG_EDGE_KEYS / _HIST then cover the kept edges only; GPU only),
  *        "stage_timing" (0/1: bracket every pipeline stage with CUDA events on the ctx
  *        stream; setting it also clears the accumulated times; GPU only)
  *   get: "launches" (kernels launched since ctx creation), "workspace_bytes",

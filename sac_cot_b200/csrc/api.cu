@@ -45,7 +45,6 @@ struct Layout {
   uint32_t* hist = nullptr;
   unsigned long long* t2 = nullptr;
   uint32_t* ucount = nullptr;  // edges per triangle work unit, [pairs][unit_pitch]
-  uint32_t* ucursor = nullptr; // per-unit key cursors (tensor-core triangle path only)
   size_t zero_bytes = 0;
   uint32_t* ubase = nullptr;   // key offset per unit inside the pair's key slice
   int unit_pitch = 0;
@@ -55,6 +54,9 @@ struct Layout {
   float* in_dst = nullptr;
   float* soa = nullptr;
   uint32_t* adj = nullptr;
+  uint32_t* panel = nullptr;   // K-panel copy of the adjacency (tensor-core triangle path only)
+  uint32_t* theta = nullptr;   // per-pair pruning threshold (tensor-core triangle path only)
+  int total_tiles = 0;         // tensor-core path: tiles of the whole chunk
   unsigned long long* sel = nullptr;
   unsigned long long* tie = nullptr;
   unsigned long long* top = nullptr;
@@ -77,9 +79,9 @@ unsigned long long key_guess_for(int N) {
   return g < P ? g : P;
 }
 
-size_t pair_bytes_estimate(int N, int K, int Ke) {
+size_t pair_bytes_estimate(int N, int K, int Ke, bool tensor_path) {
   const size_t npad = align_up(static_cast<size_t>(N), 128);
-  return npad * (npad / 32) * 4 + key_guess_for(N) * 8 + npad * (6 * 4 + 8 + 24) + static_cast<size_t>(K) * (12 + 48 + 8) +
+  return npad * (npad / 32) * 4 * (tensor_path ? 2 : 1) + key_guess_for(N) * 8 + npad * (6 * 4 + 8 + 24) + static_cast<size_t>(K) * (12 + 48 + 8) +
          static_cast<size_t>(Ke) * 16 + static_cast<size_t>(kTieCap) * 8 + kHistBins * 4 + 4096;
 }
 
@@ -151,7 +153,8 @@ struct sac_cot_ctx {
   bool keep_debug = false;
   int chunk_pairs = 0;
   int n_lanes = 2;
-  int tri_path = 0;  // 0 = POPC bitset kernels, 1 = tensor-core (tcgen05 mxf4) kernel
+  int tri_path = 0;   // 0 = POPC bitset kernels, 1 = tensor-core (tcgen05 mxf4) kernel
+  int tri_prune = 1;  // tensor-core path: drop edges below the per-pair threshold (exact for the selection)
   int64_t launches = 0;
   int64_t retries = 0;
   int deferred_status = 0;  // device-location calls: status discovered after the fact
@@ -190,15 +193,16 @@ int check_params(const sac_cot_params* p) {
 }
 
 // Builds the descriptors and the arena layout for pairs with the given sizes.
-void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_input_copy, std::vector<PairDesc>& descs,
-          Layout& L) {
+void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_input_copy, bool tensor_path,
+          std::vector<PairDesc>& descs, Layout& L) {
   L = Layout();
   L.pairs = pairs;
   L.Ke = prm.num_edges;
   L.m = prm.apex_per_edge;
   L.K = L.Ke * L.m;
   descs.resize(pairs);
-  size_t pt = 0, soa = 0, adj = 0, node = 0, mask = 0;
+  size_t pt = 0, soa = 0, adj = 0, node = 0, mask = 0, panel = 0;
+  int tiles = 0;
   for (int b = 0; b < pairs; ++b) {
     PairDesc& d = descs[b];
     d.N = Ns[b];
@@ -210,6 +214,13 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
     d.adj_off = static_cast<int64_t>(adj);
     d.node_off = static_cast<int64_t>(node);
     d.mask_off = static_cast<int64_t>(mask);
+    d.panel_off = static_cast<int64_t>(panel);
+    d.npanel = (d.Npad + 255) / 256;
+    d.tile_base = tiles;
+    if (tensor_path) {
+      panel += static_cast<size_t>(d.npanel) * d.Npad * 8;
+      tiles += mma_tiles_of_pair(d.N);
+    }
     pt += d.N;
     soa += static_cast<size_t>(6) * d.Npad;
     adj += static_cast<size_t>(d.Npad) * d.stride;
@@ -223,6 +234,7 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   }
   L.sum_n = pt;
   L.sum_npad = node;
+  L.total_tiles = tiles;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -236,7 +248,6 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_t2 = take(sizeof(unsigned long long) * node);
   L.unit_pitch = static_cast<int>(unit_count(static_cast<unsigned int>(L.max_nblk)));
   const size_t o_ucount = take(sizeof(uint32_t) * L.unit_pitch * pairs);
-  const size_t o_ucursor = take(sizeof(uint32_t) * L.unit_pitch * pairs);
   L.zero_bytes = off;
   const size_t o_ubase = take(sizeof(uint32_t) * L.unit_pitch * pairs);
   const size_t o_desc = take(sizeof(PairDesc) * pairs);
@@ -244,6 +255,8 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_indst = need_input_copy ? take(sizeof(float) * 3 * pt) : 0;
   const size_t o_soa = take(sizeof(float) * soa);
   const size_t o_adj = take(sizeof(uint32_t) * adj);
+  const size_t o_panel = tensor_path ? take(sizeof(uint32_t) * panel) : 0;
+  const size_t o_theta = tensor_path ? take(sizeof(uint32_t) * pairs) : 0;
   const size_t o_sel = take(sizeof(unsigned long long) * L.Ke * pairs);
   const size_t o_tie = take(sizeof(unsigned long long) * kTieCap * pairs);
   const size_t o_top = take(sizeof(unsigned long long) * L.Ke * pairs);
@@ -262,13 +275,14 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.hist = reinterpret_cast<uint32_t*>(o_hist);
   L.t2 = reinterpret_cast<unsigned long long*>(o_t2);
   L.ucount = reinterpret_cast<uint32_t*>(o_ucount);
-  L.ucursor = reinterpret_cast<uint32_t*>(o_ucursor);
   L.ubase = reinterpret_cast<uint32_t*>(o_ubase);
   L.desc = reinterpret_cast<PairDesc*>(o_desc);
   L.in_src = need_input_copy ? reinterpret_cast<float*>(o_insrc) : nullptr;
   L.in_dst = need_input_copy ? reinterpret_cast<float*>(o_indst) : nullptr;
   L.soa = reinterpret_cast<float*>(o_soa);
   L.adj = reinterpret_cast<uint32_t*>(o_adj);
+  L.panel = tensor_path ? reinterpret_cast<uint32_t*>(o_panel) : nullptr;
+  L.theta = tensor_path ? reinterpret_cast<uint32_t*>(o_theta) : nullptr;
   L.sel = reinterpret_cast<unsigned long long*>(o_sel);
   L.tie = reinterpret_cast<unsigned long long*>(o_tie);
   L.top = reinterpret_cast<unsigned long long*>(o_top);
@@ -287,19 +301,20 @@ inline T* rebase(T* rel, unsigned char* base, bool present = true) {
   return present ? reinterpret_cast<T*>(base + reinterpret_cast<size_t>(rel)) : nullptr;
 }
 
-void bind(Layout& L, unsigned char* base, bool has_input) {
+void bind(Layout& L, unsigned char* base, bool has_input, bool tensor_path) {
   L.state = rebase(L.state, base);
   L.chunk = rebase(L.chunk, base);
   L.hist = rebase(L.hist, base);
   L.t2 = rebase(L.t2, base);
   L.ucount = rebase(L.ucount, base);
-  L.ucursor = rebase(L.ucursor, base);
   L.ubase = rebase(L.ubase, base);
   L.desc = rebase(L.desc, base);
   L.in_src = rebase(L.in_src, base, has_input);
   L.in_dst = rebase(L.in_dst, base, has_input);
   L.soa = rebase(L.soa, base);
   L.adj = rebase(L.adj, base);
+  L.panel = rebase(L.panel, base, tensor_path);
+  L.theta = rebase(L.theta, base, tensor_path);
   L.sel = rebase(L.sel, base);
   L.tie = rebase(L.tie, base);
   L.top = rebase(L.top, base);
@@ -403,14 +418,15 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   mark(-1);
   KL_TRY(launch_pack_soa(lc, L.desc, L.pairs, L.max_npad, d_src, d_dst, L.soa));
   mark(ST_PACK);
-  KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.ucount, L.unit_pitch, prm.tau_compat));
+  const bool tensor = L.panel != nullptr;  // decided when the chunk was planned
+  KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.panel, L.ucount, L.unit_pitch, prm.tau_compat));
   mark(ST_GRAPH);
-  KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world));
+  KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world, tensor ? 1 : 0));
   KL_TRY(launch_key_scan(lc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap));
   mark(ST_SCAN);
-  if (ctx->tri_path == 1)
-    KL_TRY(launch_triangles_mma(lc, L.desc, L.pairs, L.max_npad, L.adj, L.state, L.chunk, ln.keys, L.ubase, L.ucursor,
-                                L.unit_pitch, L.hist, L.t2, rank, world));
+  if (tensor)
+    KL_TRY(launch_triangles_mma(lc, L.desc, L.pairs, L.total_tiles, L.max_npad, L.adj, L.panel, L.state, L.chunk, ln.keys,
+                                L.theta, L.hist, L.t2, L.Ke, ctx->tri_prune));
   else
     KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ln.keys, L.ubase,
                             L.unit_pitch, L.hist, L.t2, rank, world));
@@ -454,10 +470,11 @@ int enqueue_chunk(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst
   const int pairs = b1 - b0;
   std::vector<int32_t> Ns(pairs);
   for (int b = 0; b < pairs; ++b) Ns[b] = static_cast<int32_t>(offsets[b0 + b + 1] - offsets[b0 + b]);
-  plan(Ns.data(), pairs, prm, host, ln.descs, ln.lay);
+  const bool tensor = ctx->tri_path == 1;
+  plan(Ns.data(), pairs, prm, host, tensor, ln.descs, ln.lay);
   if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
   if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
-  bind(ln.lay, ln.arena, host);
+  bind(ln.lay, ln.arena, host, tensor);
   Layout& L = ln.lay;
   CU_TRY(cudaMemcpyAsync(L.desc, ln.descs.data(), sizeof(PairDesc) * pairs, cudaMemcpyHostToDevice, ln.stream));
   const int64_t p0 = offsets[b0];
@@ -514,7 +531,7 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
     } else {
       size_t total = 0;
       for (int b = 0; b < B; ++b)
-        total += pair_bytes_estimate(static_cast<int>(offsets[b + 1] - offsets[b]), K, params->num_edges);
+        total += pair_bytes_estimate(static_cast<int>(offsets[b + 1] - offsets[b]), K, params->num_edges, ctx->tri_path == 1);
       const size_t budget = static_cast<size_t>(3) << 30;  // ~3 GB of workspace per chunk (larger chunks measured faster)
       int nchunks = static_cast<int>((total + budget - 1) / budget);
       if (nchunks < lanes && B >= 2 * lanes) nchunks = lanes;  // give every lane something to overlap
@@ -677,6 +694,10 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     ctx->tri_path = static_cast<int>(value);
     return SAC_COT_OK;
   }
+  if (!std::strcmp(name, "triangle_prune")) {
+    ctx->tri_prune = value != 0;
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "stage_timing")) {
     cudaSetDevice(ctx->device);
     ctx->timer.reset();
@@ -701,6 +722,7 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
   if (!std::strcmp(name, "sm_count")) { *value = ctx->sm_count; return SAC_COT_OK; }
   if (!std::strcmp(name, "lanes")) { *value = ctx->n_lanes; return SAC_COT_OK; }
   if (!std::strcmp(name, "triangle_path")) { *value = ctx->tri_path; return SAC_COT_OK; }
+  if (!std::strcmp(name, "triangle_prune")) { *value = ctx->tri_prune; return SAC_COT_OK; }
   if (!std::strcmp(name, "threads")) { *value = 0; return SAC_COT_OK; }
   if (!std::strncmp(name, "stage_us_", 9) || !std::strncmp(name, "stage_calls_", 12)) {
     const bool us = name[6] == 'u';
@@ -791,12 +813,12 @@ int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
     if (int rc = ensure_chunk_headers(ctx, 1)) return rc;
     ChunkDev* h_chunk = ctx->h_chunks[0];
     for (int attempt = 0; attempt < 3; ++attempt) {
-      plan(&N, 1, *params, true, ln.descs, ln.lay);
+      plan(&N, 1, *params, true, false, ln.descs, ln.lay);  // sharded phases use the POPC kernels
       if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
       // a rank evaluates ~1/world of the edges: the unit scan counts only the owned units, so the
       // pool demand is ~E/world; the initial guess covers a whole pair at 12.5 % density
       if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
-      bind(ln.lay, ln.arena, true);
+      bind(ln.lay, ln.arena, true, false);
       ctx->prm = *params;
       Layout& L = ln.lay;
       if (int rc = fork_lanes(ctx, 1)) return rc;

@@ -23,6 +23,9 @@ struct PairDesc {
   int64_t adj_off;   // first u32 word of this pair's Npad x stride adjacency block
   int64_t node_off;  // first entry of this pair in per-node arrays (t2), sum of Npad
   int64_t mask_off;  // first u32 word of this pair's inlier mask (Npad/32 words)
+  int64_t panel_off; // first u32 word of this pair's K-panel copy of the adjacency (tensor-core path)
+  int32_t npanel;    // 256-column panels = ceil(Npad / 256); panel p holds [Npad rows][8 words]
+  int32_t tile_base; // first tile index of this pair in the chunk's tile list (tensor-core path)
 };
 
 struct PairDev {
@@ -132,9 +135,10 @@ struct LaunchCtx {
 int launch_pack_soa(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const float* d_src,
                     const float* d_dst, float* d_soa);
 int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, const float* d_soa,
-                 uint32_t* d_adj, uint32_t* d_ucount, int unit_pitch, float tau);
+                 uint32_t* d_adj, uint32_t* d_panel, uint32_t* d_ucount, int unit_pitch, float tau);
 int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state,
-                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world);
+                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world,
+                     int keys_appended);
 int launch_key_scan(const LaunchCtx& lc, int pairs, PairDev* d_state, ChunkDev* d_chunk, StickyDev* d_sticky,
                     unsigned long long key_cap);
 
@@ -146,10 +150,24 @@ int launch_triangles(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
 int triangles_configure();  // opt-in dynamic shared memory; call once per device
 
 // kernels_triangles_mma.cu — S2 triangle counts on the tensor cores (tcgen05 kind::mxf4, TMEM)
-int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
-                         PairDev* d_state, const ChunkDev* d_chunk, unsigned long long* d_keys, const uint32_t* d_ubase,
-                         uint32_t* d_ucursor, int unit_pitch, uint32_t* d_hist, unsigned long long* d_t2, int rank,
-                         int world);
+constexpr int kMmaTileM = 128;      // rows of i per tile (one TMEM accumulator, M = 128)
+constexpr int kMmaTileN = 240;      // columns of j per tile (UMMA N = 240; two accumulators = 480 TMEM columns)
+// tiles of one pair: J-blocks jq = 0 .. ceil(N/240)-1, each with the row blocks that hold some i < j
+__host__ __device__ inline int mma_tiles_of_jblock(int N, int jq) {
+  const int nI = (N + kMmaTileM - 1) / kMmaTileM;
+  const int c = (kMmaTileN * jq + kMmaTileN - 2) / kMmaTileM + 1;
+  return c < nI ? c : nI;
+}
+__host__ __device__ inline int mma_tiles_of_pair(int N) {
+  const int nJ = (N + kMmaTileN - 1) / kMmaTileN;
+  int t = 0;
+  for (int jq = 0; jq < nJ; ++jq) t += mma_tiles_of_jblock(N, jq);
+  return t;
+}
+int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int total_tiles, int max_npad,
+                         const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
+                         unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
+                         int Ke, int prune);
 int triangles_mma_configure();
 
 // kernels_select.cu — S3 edge ranking + apex selection

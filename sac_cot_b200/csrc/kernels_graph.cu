@@ -140,7 +140,8 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 
 __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__ descs,
                                                     const float* __restrict__ soa, uint32_t* __restrict__ adj,
-                                                    uint32_t* __restrict__ ucount, int unit_pitch, float tau,
+                                                    uint32_t* __restrict__ panel, uint32_t* __restrict__ ucount,
+                                                    int unit_pitch, float tau,
                                                     float tau2f, float lo) {
   const PairDesc d = descs[blockIdx.y];
   const int ntiles = d.nblk * (d.nblk + 1) / 2;
@@ -245,6 +246,14 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
   }
   *reinterpret_cast<uint4*>(adjp + static_cast<size_t>(I0 + r) * d.stride + J0 / 32) =
       make_uint4(words[0], words[1], words[2], words[3]);
+  // K-panel copy for the tensor-core triangle kernel: panel p = 256 columns, [Npad rows][8 words], so a
+  // block of rows of one panel is contiguous (one bulk copy per operand block and K stage)
+  uint32_t* pp = panel != nullptr ? panel + d.panel_off : nullptr;
+  if (pp != nullptr) {
+    uint32_t* prow = pp + (static_cast<size_t>(J >> 1) * d.Npad + I0 + r) * 8;
+    *reinterpret_cast<uint4*>(prow + (J & 1) * 4) = make_uint4(words[0], words[1], words[2], words[3]);
+    if (J == d.nblk - 1 && (J & 1) == 0) *reinterpret_cast<uint4*>(prow + 4) = make_uint4(0u, 0u, 0u, 0u);  // half panel
+  }
 
   if (I != J) {
     // mirrored tile: word for row J0+c, column word I0/32+warp, bit lane = A[I0+32*warp+lane][J0+c]
@@ -253,6 +262,7 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
     __syncthreads();
     const uint4 tw = *reinterpret_cast<const uint4*>(&tsm[r][0]);
     *reinterpret_cast<uint4*>(adjp + static_cast<size_t>(J0 + r) * d.stride + I0 / 32) = tw;
+    if (pp != nullptr) *reinterpret_cast<uint4*>(pp + (static_cast<size_t>(I >> 1) * d.Npad + J0 + r) * 8 + (I & 1) * 4) = tw;
   }
 
   // edges (i<j) of this tile, added to the count of its triangle work unit (J, I/2): the unit
@@ -269,12 +279,12 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
 }
 
 int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, const float* d_soa,
-                 uint32_t* d_adj, uint32_t* d_ucount, int unit_pitch, float tau) {
+                 uint32_t* d_adj, uint32_t* d_panel, uint32_t* d_ucount, int unit_pitch, float tau) {
   dim3 grid(max_nblk * (max_nblk + 1) / 2, pairs);
   const float tau2f = tau * tau;  // one fp32 multiply
   float lo = 4.0f * tau2f;        // exact scaling (or +inf: then every pair takes the literal path)
   if (!(lo >= 8.8817841970012523e-16f)) lo = 8.8817841970012523e-16f;  // 2^-50; also replaces NaN
-  graph_kernel<<<grid, 128, 0, lc.stream>>>(d_desc, d_soa, d_adj, d_ucount, unit_pitch, tau, tau2f, lo);
+  graph_kernel<<<grid, 128, 0, lc.stream>>>(d_desc, d_soa, d_adj, d_panel, d_ucount, unit_pitch, tau, tau2f, lo);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }
@@ -288,7 +298,7 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const PairDesc* __restr
                                                          PairDev* __restrict__ state,
                                                          const uint32_t* __restrict__ ucount,
                                                          uint32_t* __restrict__ ubase, int unit_pitch, int rank,
-                                                         int world) {
+                                                         int world, int keys_appended) {
   const int pair = blockIdx.x;
   const unsigned int U = unit_count(static_cast<unsigned int>(descs[pair].nblk));
   const uint32_t* cnt = ucount + static_cast<size_t>(pair) * unit_pitch;
@@ -328,13 +338,17 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const PairDesc* __restr
   }
   if (t == 0) {
     state[pair].num_edges = carry;
-    state[pair].key_count = carry;
+    // POPC path: every edge gets a key at an exact offset.  Tensor-core path: the kernel appends the
+    // keys that pass its pruning threshold and counts them here.
+    state[pair].key_count = keys_appended ? 0ull : carry;
   }
 }
 
 int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state,
-                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world) {
-  unit_scan_kernel<<<pairs, 1024, 0, lc.stream>>>(d_desc, d_state, d_ucount, d_ubase, unit_pitch, rank, world);
+                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world,
+                     int keys_appended) {
+  unit_scan_kernel<<<pairs, 1024, 0, lc.stream>>>(d_desc, d_state, d_ucount, d_ubase, unit_pitch, rank, world,
+                                                  keys_appended);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }

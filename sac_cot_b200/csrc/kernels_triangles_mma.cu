@@ -1,105 +1,190 @@
 // kernels_triangles_mma.cu — S2 on the tensor cores (K2b of SURVEY.md §2b): the dense contraction
-// T = (A·Aᵀ) ∘ A with tcgen05.mma, accumulators in TMEM.  Integer-exact: operands are 0/1.
+// T = (A·Aᵀ) ∘ A with tcgen05.mma, accumulators in TMEM.  Integer-exact: operands are 0/1 products.
 //
-// north_star names int8 tiles; the probe in profiles/microbench/umma_probe.cu measured one SM at
-// 7.9 k MAC/clk for kind::i8 and 15.6 k MAC/clk for kind::mxf4.block_scale, so the kernel uses
-// the 4-bit path: bit b becomes the e2m1 nibble 0b0010 (1.0) or 0, every UE8M0 scale factor is
-// 0x7F (1.0) — one TMEM region filled once and shared by all MMAs — and the fp32 accumulator holds
-// exact integers (counts < 2^24).
+// north_star names int8 tiles; profiles/microbench/umma_probe.cu measured one SM at 7.9 k MAC/clk for
+// kind::i8 and 15.6 k MAC/clk for kind::mxf4.block_scale, so the kernel uses the 4-bit path.
 //
-// Feeding the tensor core is the problem, not the MMA: pre-expanded operands would need > 400 MB
-// of L2->SMEM traffic per pair (L2-bound, slower than the POPC kernel), so the 1-bit adjacency rows
-// are expanded ON CHIP: producer warps read 32-bit words of the rows (L2), spread them to 16 bytes of
-// nibbles with a byte-permute LUT, and write them straight into the no-swizzle K-major canonical
-// layout the UMMA descriptors describe (core matrix = 8 rows x 16 B).
+// Operands are produced ON CHIP from the 1-bit adjacency (pre-expanded operands would need > 400 MB of
+// L2->SMEM traffic per pair).  The contraction index may be permuted freely as long as both operands use
+// the same permutation, so a 32-bit adjacency word w is turned into four words of eight e2m1 nibbles with
+//     w & 0x22222222  (nibble 0b0010 = 1.0)      w & 0x11111111  (nibble 0b0001 = 0.5)
+//     (w>>2) & 0x22222222                         (w>>2) & 0x11111111
+// and the 0.5 blocks carry the UE8M0 block scale 2.0 on BOTH operands: every product is exactly 0 or 1.
+// That is 5 ALU instructions per 32 adjacency bits (profiles/microbench/umma_contend.cu checks the result
+// against popcounts and shows the MMA pipe at 99.6 % with the shared-memory stores running flat out).
 //
-// One CTA per work item = (J-block of 224 columns, 256 rows = two 128-row A blocks).  TMEM: two
-// 128 x 224 fp32 accumulators (448 columns) + the scale-factor region (64 columns).  Warp roles:
-//   warps 0-3   epilogue: while the MMAs run they read the edge bits A[i][J-block], reserve key
-//               ranges (one warp-aggregated atomic per 32-column chunk) and then, when the
-//               accumulators are complete, tcgen05.ld them, keep T_ij where A_ij = 1 and j > i,
-//               emit keys / histogram / node sums exactly like the POPC kernel
-//   warp  4     MMA issuer (one lane): per stage 2 A-blocks x 4 k-steps of M=128, N=224, K=64
-//   warps 5-15  producers: expansion of 480 rows x 256 K-elements per stage, 3-stage ring
+// Kernel structure (persistent, one CTA per SM, 512 threads):
+//   tile        = 128 rows (i) x 240 columns (j), full K; only tiles that hold some i < j are visited
+//   warp  4     MMA issuer: per K stage (256 columns) 4 x tcgen05.mma M=128 N=240 K=64, two TMEM
+//               accumulators (2 x 240 columns) so that the epilogue of tile n overlaps the MMAs of n+1
+//   warp  5     bulk-copy (TMA) issuer: per stage the 128 + 240 raw rows of the K-panel copy of A
+//               (32 bytes per row, contiguous per operand block) into a 4-deep raw ring
+//   warps 6-15  expansion: raw ring -> 3-deep ring of canonical (no-swizzle, K-major) operand stages
+//   warps 0-3   epilogue: tcgen05.ld 16 columns at a time; mask with the edge bits (j > i), row sums
+//               (t2_i), column sums by a shuffle butterfly (t2_j), and edges whose T reaches the pair's
+//               pruning threshold are appended (key, histogram) through a per-warp staging buffer
+//
+// Pruning threshold (tri_theta_kernel): exact T of the edges among the ~128 highest-degree nodes; if at
+// least K_e of them exist, theta = the K_e-th largest of those counts.  Then at least K_e edges of the
+// graph have T >= theta, so no edge below theta can be among the top K_e: dropping them changes nothing
+// downstream (selection is exact), but removes ~98 % of the key traffic.  theta = 0 keeps every edge.
 #include "common.cuh"
 
 #include <algorithm>
 
 namespace saccot {
 
-constexpr int kMmaThreads = 512;
-constexpr int kMmaJ = 224;                 // columns per item (7 words)
-constexpr int kMmaI = 256;                 // rows per item (two A blocks of 128)
-constexpr int kMmaStageK = 256;            // K elements per stage (8 words, 128 bytes of nibbles per row)
-constexpr int kMmaStages = 3;
-constexpr int kMmaRows = kMmaI + kMmaJ;    // 480 rows expanded per stage
-constexpr int kMmaLBO = 128;               // next 16-byte K chunk (core matrices contiguous along K)
-constexpr int kMmaSBO = (kMmaStageK / 2 / 16) * 128;  // next 8-row group: 8 core matrices = 1024 B
-constexpr int kMmaStageBytes = (kMmaRows / 8) * kMmaSBO;  // 60 groups x 1024 B = 61440
-constexpr int kMmaProducerWarps = 11;
-constexpr uint32_t kSfCol = 448;           // scale-factor region: TMEM columns [448, 512)
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kStageK = 256;                          // K elements (adjacency columns) per stage
+constexpr int kStages = 3;                            // expanded operand stages
+constexpr int kRawStages = 4;                         // raw (bit) stages
+constexpr int kRows = kMmaTileM + kMmaTileN;          // 368 rows expanded per stage
+constexpr int kLBO = 128;                             // next 16-byte K chunk (core matrices contiguous along K)
+constexpr int kSBO = (kStageK / 2 / 16) * 128;        // next 8-row group: 8 core matrices = 1024 B
+constexpr int kStageBytes = (kRows / 8) * kSBO;       // 47104
+constexpr int kRawBytes = kRows * 32;                 // 11776
+constexpr int kRawABytes = kMmaTileM * 32;            // 4096
+constexpr int kProducerWarps = 10;
+constexpr int kTasks = kRows / 16;                    // 23 warp tasks (16 rows x 2 quads) per stage
+constexpr int kMaxT = (kTasks + kProducerWarps - 1) / kProducerWarps;  // 3
+constexpr int kKeyBuf = 640;                          // staged keys per epilogue warp (flush above 128)
+constexpr uint32_t kSfCol = 480;                      // scale factors: TMEM columns [480, 512)
+constexpr uint32_t kSfWord = 0x807F807Fu;             // UE8M0 per K block of 32: {1.0, 2.0, 1.0, 2.0}
+
+// shared-memory carve-up (dynamic)
+constexpr int kOffRaw = kStages * kStageBytes;                    // 141312
+constexpr int kOffHist = kOffRaw + kRawStages * kRawBytes;        // +47104
+constexpr int kOffKeys = kOffHist + kHistBins * 4;                // +16384
+constexpr int kOffBars = kOffKeys + 4 * kKeyBuf * 8;              // +20480
+constexpr int kNumBars = 2 * kStages + 2 * kRawStages + 4;
+constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((kMmaLBO >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((kMmaSBO >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>((kLBO >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((kSBO >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;  // descriptor version (Blackwell); SWIZZLE_NONE, base offset 0
   return d;
 }
 
-// 16 adjacency bits -> 16 e2m1 nibbles (two 32-bit words): spread the 2-bit groups into nibbles,
-// then a 4-entry byte LUT {00,01,10,11} -> {0x00,0x02,0x20,0x22} through PRMT.
-__device__ __forceinline__ void expand16(uint32_t x16, uint32_t& w0, uint32_t& w1) {
-  uint32_t t = __byte_perm(x16, 0u, 0x4140);          // byte0 -> byte0, byte1 -> byte2
-  t = (t | (t << 4)) & 0x0F0F0F0Fu;
-  t = (t | (t << 2)) & 0x33333333u;                   // nibble k = bits 2k, 2k+1
-  const uint32_t lut = 0x22200200u;
-  w0 = __byte_perm(lut, 0u, t & 0xFFFFu);
-  w1 = __byte_perm(lut, 0u, t >> 16);
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kMmaThreads, 1) triangles_mma_kernel(
-    const PairDesc* __restrict__ descs, const uint32_t* __restrict__ adj, const PairDev* __restrict__ state,
-    const ChunkDev* __restrict__ chunk, unsigned long long* __restrict__ keys, const uint32_t* __restrict__ ubase,
-    uint32_t* __restrict__ ucursor, int unit_pitch, uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2,
-    int rank, int world) {
-  if (chunk->overflow) return;
-  const int pair = blockIdx.y;
-  const PairDesc d = descs[pair];
-  // item -> (J, ip): J-block jq covers columns [224 jq, 224 jq + 224); row pairs ip = 0 .. last(jq)
-  // with last(jq) = (224 jq + 222) / 256 clipped to the rows that exist
-  const int nJ = (d.Npad + kMmaJ - 1) / kMmaJ;
-  const int nIp = (d.Npad + kMmaI - 1) / kMmaI;
-  int item = blockIdx.x, jq = nJ - 1, ip = -1;
-  for (; jq >= 0; --jq) {  // largest J-blocks (most row pairs) first
-    const int cnt = min(nIp, (kMmaJ * jq + kMmaJ - 2) / kMmaI + 1);
-    if (item < cnt) { ip = item; break; }
-    item -= cnt;
-  }
-  if (ip < 0) return;
-  const int J0 = jq * kMmaJ, I0 = ip * kMmaI;
-  const int stride = d.stride;
-  const int nstages = (stride + 7) / 8;
+// 128 adjacency bits of one row -> four 16-byte K chunks (see the header comment)
+__device__ __forceinline__ void expand_quad(const uint4 w, unsigned char* dst) {
+  const uint32_t m2 = 0x22222222u, m1 = 0x11111111u;
+  const uint32_t sx = w.x >> 2, sy = w.y >> 2, sz = w.z >> 2, sw = w.w >> 2;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(w.x & m2, w.y & m2, w.z & m2, w.w & m2);
+  *reinterpret_cast<uint4*>(dst + kLBO) = make_uint4(w.x & m1, w.y & m1, w.z & m1, w.w & m1);
+  *reinterpret_cast<uint4*>(dst + 2 * kLBO) = make_uint4(sx & m2, sy & m2, sz & m2, sw & m2);
+  *reinterpret_cast<uint4*>(dst + 3 * kLBO) = make_uint4(sx & m1, sy & m1, sz & m1, sw & m1);
+}
 
+// tile index -> (pair, I0, J0); `pair` is a cursor that only moves forward
+__device__ __forceinline__ void decode_tile(int t, const PairDesc* __restrict__ descs, int pairs, int& pair, PairDesc& d,
+                                            int& I0, int& J0) {
+  bool moved = pair < 0;
+  if (pair < 0) pair = 0;
+  while (pair + 1 < pairs && t >= descs[pair + 1].tile_base) {
+    ++pair;
+    moved = true;
+  }
+  if (moved) d = descs[pair];
+  int u = t - d.tile_base, jq = 0;
+  for (;; ++jq) {
+    const int cnt = mma_tiles_of_jblock(d.N, jq);
+    if (u < cnt) break;
+    u -= cnt;
+  }
+  I0 = u * kMmaTileM;
+  J0 = jq * kMmaTileN;
+}
+
+#define SACCOT_TMEM_LD16(v, taddr)                                                                                   \
+  asm volatile(                                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),  \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                      \
+      : "r"(taddr))
+
+// sum over the 32 lanes (rows) of 16 per-lane values (columns): afterwards lane L holds column (L>>1)&15
+__device__ __forceinline__ float colsum16(float (&m)[16], int lane) {
+  {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float send = hi ? m[k] : m[k + 8], keep = hi ? m[k + 8] : m[k];
+      m[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = (lane & 8) != 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float send = hi ? m[k] : m[k + 4], keep = hi ? m[k + 4] : m[k];
+      m[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = (lane & 4) != 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float send = hi ? m[k] : m[k + 2], keep = hi ? m[k + 2] : m[k];
+      m[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool hi = (lane & 2) != 0;
+    const float send = hi ? m[0] : m[1], keep = hi ? m[1] : m[0];
+    m[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return m[0] + __shfl_xor_sync(0xffffffffu, m[0], 1);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
+    const PairDesc* __restrict__ descs, int pairs, int total_tiles, const uint32_t* __restrict__ adj,
+    const uint32_t* __restrict__ panel, PairDev* __restrict__ state, const ChunkDev* __restrict__ chunk,
+    unsigned long long* __restrict__ keys, const uint32_t* __restrict__ theta, uint32_t* __restrict__ hist,
+    unsigned long long* __restrict__ t2) {
+  if (chunk->overflow) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* stage_base = smem_raw;                                           // [3][61440]
-  uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem_raw + kMmaStages * kMmaStageBytes);  // [4096]
-  uint32_t* tJ = hist_s + kHistBins;                                              // [224]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tJ + kMmaJ);                       // full[3], empty[3], acc
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kMmaStages;
-  uint64_t* acc_full = bars + 2 * kMmaStages;
+  unsigned char* stage_base = smem_raw;
+  unsigned char* raw_base = smem_raw + kOffRaw;
+  uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem_raw + kOffHist);
+  unsigned long long* kbuf = reinterpret_cast<unsigned long long*>(smem_raw + kOffKeys);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kOffBars);
+  uint64_t* full = bars;                                 // [kStages]   producers -> MMA
+  uint64_t* empty = full + kStages;                      // [kStages]   MMA commit -> producers
+  uint64_t* raw_full = empty + kStages;                  // [kRawStages] bulk copies -> producers
+  uint64_t* raw_empty = raw_full + kRawStages;           // [kRawStages] producers -> bulk-copy issuer
+  uint64_t* tmem_full = raw_empty + kRawStages;          // [2] MMA commit -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;                  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int k = tid; k < kHistBins + kMmaJ; k += kMmaThreads) hist_s[k] = 0;  // hist and tJ are contiguous
+  for (int k = tid; k < kHistBins; k += kThreads) hist_s[k] = 0;
   if (tid == 0) {
-    for (int s = 0; s < kMmaStages; ++s) {
-      mbar_init(&full[s], kMmaProducerWarps);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], kProducerWarps);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < kRawStages; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&raw_empty[s], kProducerWarps);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 4);
+    }
     mbar_fence_init();
   }
   if (warp == 4) {
@@ -110,241 +195,401 @@ __global__ void __launch_bounds__(kMmaThreads, 1) triangles_mma_kernel(
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = *tmem_slot;
-  const uint32_t* adjp = adj + d.adj_off;
 
   if (warp < 4) {
-    // ============================ epilogue warps ============================
-    // scale factors: every byte 0x7F (UE8M0 1.0) in columns [448, 512) of this warp's 32 lanes
-    {
-      const uint32_t v = 0x7F7F7F7Fu;
+    // ================================== epilogue warps ==================================
+    {  // scale factors: every 32-bit word of columns [480, 512) = {1.0, 2.0, 1.0, 2.0}
       const uint32_t taddr = tmem + ((32u * warp) << 16) + kSfCol;
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
-                taddr + 32u * h),
-            "r"(v)
-            : "memory");
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
+              taddr),
+          "r"(kSfWord)
+          : "memory");
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;");
     }
-    // named barrier 1: the four epilogue warps + the MMA warp (160 threads): SF region is ready
-    asm volatile("bar.sync 1, 160;" ::: "memory");
+    asm volatile("bar.sync 1, 160;" ::: "memory");  // epilogue warps + MMA warp: scale factors are in place
 
-    // ---- while the MMAs run: edge bits, counts and key positions of this thread's rows ----
-    const int m = 32 * warp + lane;  // row inside an A block
-    uint32_t ebits[2][7];
-    uint32_t epos[2][7];
-    const uint32_t* ubp = ubase + static_cast<size_t>(pair) * unit_pitch;
-    uint32_t* ucp = ucursor + static_cast<size_t>(pair) * unit_pitch;
-    const unsigned int ic = static_cast<unsigned int>(ip);  // rows [256 ip, 256 ip + 256) => i >> 8 == ip
+    unsigned long long* kb = kbuf + warp * kKeyBuf;
+    uint32_t fill = 0;          // staged keys of this warp (warp-uniform)
+    int pair = -1, cur_pair = -1;
+    PairDesc d;
+    unsigned long long* keyp = nullptr;
+    unsigned long long* kcount = nullptr;
+    int thbits = 0;
+    auto flush_keys = [&]() {
+      __syncwarp();
+      if (fill) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(kcount, static_cast<unsigned long long>(fill));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t k = lane; k < fill; k += 32) keyp[base + k] = kb[k];
+        fill = 0;
+      }
+      __syncwarp();
+    };
+    auto flush_pair = [&]() {  // all four epilogue warps
+      flush_keys();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      uint32_t* histp = hist + static_cast<size_t>(cur_pair) * kHistBins;
+      for (int k = tid; k < kHistBins; k += 128) {
+        const uint32_t v = hist_s[k];
+        if (v) {
+          atomicAdd(&histp[k], v);
+          hist_s[k] = 0;
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
+
+    int n = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n) {
+      int I0, J0;
+      decode_tile(t, descs, pairs, pair, d, I0, J0);
+      if (pair != cur_pair) {
+        if (cur_pair >= 0) flush_pair();
+        cur_pair = pair;
+        keyp = keys + state[pair].key_base;
+        kcount = &state[pair].key_count;
+        thbits = __float_as_int(static_cast<float>(theta[pair]));
+      }
+      // ---- edge bits of this thread's row inside the tile's 240 columns (window aligned to J0) ----
+      const int i = I0 + 32 * warp + lane;
+      uint32_t win[9];
+      {
+        const uint32_t* rowp = adj + d.adj_off + static_cast<size_t>(i) * d.stride;
+        const int w0 = J0 >> 5;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int i = I0 + 128 * a + m;
+        for (int k = 0; k < 9; ++k) win[k] = (w0 + k < d.stride) ? rowp[w0 + k] : 0u;
+        if (J0 & 16) {
 #pragma unroll
-      for (int c = 0; c < 7; ++c) {
-        const int jc = J0 + 32 * c;  // first column of the chunk
-        uint32_t bits = 0;
-        if (i < d.N && jc < d.Npad) bits = adjp[static_cast<size_t>(i) * stride + (jc >> 5)];
-        // keep j > i
-        if (i >= jc + 31) bits = 0;
-        else if (i >= jc) bits &= 0xFFFFFFFEu << (i - jc);
-        const unsigned int unit = unit_offset(static_cast<unsigned int>(jc) >> 7) + ic;
-        if (world > 1 && (unit % static_cast<unsigned int>(world)) != static_cast<unsigned int>(rank)) bits = 0;
-        ebits[a][c] = bits;
-        // warp-aggregated reservation inside the unit's key region
-        const int n = __popc(bits);
-        int incl = n;
+          for (int k = 0; k < 8; ++k) win[k] = __funnelshift_r(win[k], win[k + 1], 16);
+        }
+        win[7] &= 0xFFFFu;  // columns 240..255 of the window belong to the next J-block
+        const int dd = i - J0;  // keep j > i: clear window bits 0..dd
+        if (dd >= 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int lo = 32 * k;
+            if (dd >= lo + 31) win[k] = 0u;
+            else if (dd >= lo) win[k] &= 0xFFFFFFFEu << (dd - lo);
+          }
+        }
+      }
+      const unsigned long long ikey = static_cast<unsigned long long>(0xFFFFu - static_cast<unsigned int>(i)) << 16;
+
+      // ---- accumulators of tile n ----
+      const int buf = n & 1;
+      mbar_wait(&tmem_full[buf], static_cast<uint32_t>((n >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t tbase = tmem + ((32u * warp) << 16) + static_cast<uint32_t>(kMmaTileN * buf);
+      float rowsum = 0.0f;
+      uint32_t v[2][16];
+      SACCOT_TMEM_LD16(v[0], tbase);
+#pragma unroll
+      for (int c = 0; c < kMmaTileN / 16; ++c) {
+        uint32_t(&vc)[16] = v[c & 1];
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c + 1 < kMmaTileN / 16) SACCOT_TMEM_LD16(v[(c + 1) & 1], tbase + 16u * (c + 1));
+        const uint32_t bits16 = (win[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+        if (fill > 128u) flush_keys();
+        // candidates: edge and T >= theta (positive floats compare like integers)
+        uint32_t lt = 0;
+#pragma unroll
+        for (int k = 15; k >= 0; --k) lt = __funnelshift_l(static_cast<uint32_t>(static_cast<int>(vc[k]) - thbits), lt, 1);
+        const uint32_t cand = ~lt & bits16;
+        const int nc = __popc(cand);
+        int incl = nc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int u = __shfl_up_sync(0xffffffffu, incl, o);
           if (lane >= o) incl += u;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t base = 0;
-        if (total > 0) {
-          if (lane == 31) base = ubp[unit] + atomicAdd(&ucp[unit], static_cast<uint32_t>(total));
-          base = __shfl_sync(0xffffffffu, base, 31);
-        }
-        epos[a][c] = base + static_cast<uint32_t>(incl - n);
-      }
-    }
-
-    // ---- accumulators complete ----
-    mbar_wait(acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    unsigned long long* keyp = keys + state[pair].key_base;
+        if (total) {
+          uint32_t pos = fill + static_cast<uint32_t>(incl - nc);
+          const unsigned int jkey = 0xFFFFu - static_cast<unsigned int>(J0 + 16 * c);
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int i = I0 + 128 * a + m;
-      const unsigned long long ikey = static_cast<unsigned long long>(0xFFFFu - static_cast<unsigned int>(i)) << 16;
-      unsigned int tsum = 0;
-#pragma unroll
-      for (int c = 0; c < 7; ++c) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem + ((32u * warp) << 16) + static_cast<uint32_t>(kMmaJ * a + 32 * c);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const uint32_t bits = ebits[a][c];
-        if (bits) {
-          uint32_t at = epos[a][c];
-          const unsigned int jkey = 0xFFFFu - static_cast<unsigned int>(J0 + 32 * c);
-#pragma unroll
-          for (int b = 0; b < 32; ++b) {
-            if ((bits >> b) & 1u) {
-              const unsigned int T = static_cast<unsigned int>(__uint_as_float(v[b]));  // exact integer in fp32
-              keyp[at++] = (static_cast<unsigned long long>(T) << 32) | ikey | static_cast<unsigned long long>(jkey - b);
+          for (int k = 0; k < 16; ++k) {
+            if (cand & (1u << k)) {
+              const unsigned int T = __float2uint_rn(__uint_as_float(vc[k]));  // exact integer in fp32
+              kb[pos++] = (static_cast<unsigned long long>(T) << 32) | ikey | static_cast<unsigned long long>(jkey - k);
               atomicAdd(&hist_s[T >> 4], 1u);
-              atomicAdd(&tJ[32 * c + b], T);
-              tsum += T;
             }
           }
+          fill += static_cast<uint32_t>(total);
         }
+        // masked counts: row sum (t2_i) and column sums (t2_j)
+        float m[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          m[k] = (bits16 & (1u << k)) ? __uint_as_float(vc[k]) : 0.0f;
+          rowsum += m[k];
+        }
+        const float cs = colsum16(m, lane);
+        if (!(lane & 1) && cs > 0.0f)
+          atomicAdd(&t2[d.node_off + J0 + 16 * c + ((lane >> 1) & 15)], static_cast<unsigned long long>(cs));
       }
-      if (tsum) atomicAdd(&t2[d.node_off + i], static_cast<unsigned long long>(tsum));
+      // accumulator buffer is free again
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (rowsum > 0.0f) atomicAdd(&t2[d.node_off + i], static_cast<unsigned long long>(rowsum));
     }
-    asm volatile("tcgen05.fence::before_thread_sync;");
+    if (cur_pair >= 0) flush_pair();
   } else if (warp == 4) {
-    // ============================ MMA issuer ============================
-    asm volatile("bar.sync 1, 160;" ::: "memory");  // scale-factor region written
+    // ================================== MMA issuer ==================================
+    asm volatile("bar.sync 1, 160;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;");
-    // instruction descriptor: block-scaled, A/B = E2M1 (1), UE8M0 scales, N = 224, M = 128, K-major both
-    const uint32_t idesc = (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kMmaJ >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+    // instruction descriptor: block-scaled, A/B = E2M1, UE8M0 scales, N = 240, M = 128, K-major both
+    const uint32_t idesc = (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kMmaTileN >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
     const uint32_t sbase = smem_u32(stage_base);
-    for (int it = 0; it < nstages; ++it) {
-      const int s = it % kMmaStages;
-      mbar_wait(&full[s], static_cast<uint32_t>((it / kMmaStages) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      if (lane == 0) {
-        const uint32_t st = sbase + s * kMmaStageBytes;
-        const uint32_t bA0 = st, bA1 = st + 16 * kMmaSBO, bB = st + 32 * kMmaSBO;
+    int pair = -1, n = 0;
+    uint32_t g = 0;
+    PairDesc d;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n) {
+      int I0, J0;
+      decode_tile(t, descs, pairs, pair, d, I0, J0);
+      const int buf = n & 1;
+      if (n >= 2) {
+        mbar_wait(&tmem_empty[buf], static_cast<uint32_t>(((n >> 1) - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;");
+      }
+      for (int it = 0; it < d.npanel; ++it, ++g) {
+        const uint32_t s = g % kStages;
+        mbar_wait(&full[s], (g / kStages) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        if (lane == 0) {
+          const uint32_t bA = sbase + s * kStageBytes, bB = bA + (kMmaTileM / 8) * kSBO;
 #pragma unroll
-        for (int ks = 0; ks < kMmaStageK / 64; ++ks) {
-          const uint64_t db = umma_desc(bB + ks * 2 * kMmaLBO);
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const uint64_t da = umma_desc((a == 0 ? bA0 : bA1) + ks * 2 * kMmaLBO);
+          for (int ks = 0; ks < kStageK / 64; ++ks) {
+            const uint64_t da = umma_desc(bA + ks * 2 * kLBO), db = umma_desc(bB + ks * 2 * kLBO);
             const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
             asm volatile(
                 "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                 "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(
-                    tmem + static_cast<uint32_t>(kMmaJ * a)),
-                "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 32u)
+                    tmem + static_cast<uint32_t>(kMmaTileN * buf)),
+                "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 16u)
                 : "memory");
           }
+          umma_commit(&empty[s]);                           // stage reusable once these MMAs have read it
+          if (it == d.npanel - 1) umma_commit(&tmem_full[buf]);  // accumulator complete
         }
-        // the stage may be overwritten once these MMAs have read it
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
-        if (it == nstages - 1)
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(acc_full)) : "memory");
+        __syncwarp();
       }
-      __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-  } else {
-    // ============================ producers ============================
-    // Task = (row r of the 480, word j of the 8 in the stage): 32 bits -> 16 bytes of nibbles, one
-    // 128-bit store into the canonical layout.  A warp covers 8 rows x 4 words per step: its lanes
-    // write 512 contiguous bytes (conflict free) and read 16 contiguous bytes per row.
-    const int pw = warp - 5;               // 0..10
-    const int r8 = lane & 7, j4 = lane >> 3;
-    constexpr int kGroups = (kMmaRows / 8) * 2;  // 120 (row group, word half) pairs per stage
-    constexpr int kMaxT = (kGroups + kMmaProducerWarps - 1) / kMmaProducerWarps;  // 11
-    const uint32_t* rowp[kMaxT];
-    uint32_t soff[kMaxT];
-    int jword[kMaxT];
-#pragma unroll
-    for (int t = 0; t < kMaxT; ++t) {
-      const int g = pw + kMmaProducerWarps * t;
-      rowp[t] = nullptr;
-      soff[t] = 0;
-      jword[t] = 0;
-      if (g < kGroups) {
-        const int rg = g >> 1, jh = g & 1;
-        const int r = 8 * rg + r8;
-        const int grow = r < kMmaI ? I0 + r : J0 + (r - kMmaI);   // global adjacency row
-        jword[t] = 4 * jh + j4;
-        soff[t] = static_cast<uint32_t>(rg * kMmaSBO + jword[t] * kMmaLBO + r8 * 16);
-        if (grow < d.Npad) rowp[t] = adjp + static_cast<size_t>(grow) * stride;
-      }
-    }
-    uint32_t cur[kMaxT];
-    auto load_stage = [&](int it, uint32_t (&w)[kMaxT]) {
-#pragma unroll
-      for (int t = 0; t < kMaxT; ++t) {
-        const int widx = it * 8 + jword[t];
-        w[t] = (rowp[t] != nullptr && widx < stride) ? rowp[t][widx] : 0u;
-      }
-    };
-    load_stage(0, cur);
-    for (int it = 0; it < nstages; ++it) {
-      const int s = it % kMmaStages;
-      uint32_t nxt[kMaxT];
-      if (it + 1 < nstages) load_stage(it + 1, nxt);
-      if (it >= kMmaStages) mbar_wait(&empty[s], static_cast<uint32_t>(((it / kMmaStages) - 1) & 1));
-      unsigned char* st = stage_base + s * kMmaStageBytes;
-#pragma unroll
-      for (int t = 0; t < kMaxT; ++t) {
-        if (pw + kMmaProducerWarps * t < kGroups) {
-          uint4 o;
-          expand16(cur[t] & 0xFFFFu, o.x, o.y);
-          expand16(cur[t] >> 16, o.z, o.w);
-          *reinterpret_cast<uint4*>(st + soff[t]) = o;
+  } else if (warp == 5) {
+    // ================================== bulk-copy issuer ==================================
+    if (lane == 0) {
+      int pair = -1;
+      uint32_t g = 0;
+      PairDesc d;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int I0, J0;
+        decode_tile(t, descs, pairs, pair, d, I0, J0);
+        const uint32_t rowsB = static_cast<uint32_t>(min(kMmaTileN, d.Npad - J0));
+        const uint32_t* pp = panel + d.panel_off;
+        for (int it = 0; it < d.npanel; ++it, ++g) {
+          const uint32_t rs = g % kRawStages;
+          if (g >= kRawStages) mbar_wait(&raw_empty[rs], ((g / kRawStages) - 1) & 1u);
+          unsigned char* dst = raw_base + rs * kRawBytes;
+          const uint32_t* src = pp + static_cast<size_t>(it) * d.Npad * 8;
+          mbar_arrive_expect_tx(&raw_full[rs], kRawABytes + rowsB * 32u);
+          bulk_g2s(dst, src + static_cast<size_t>(I0) * 8, kRawABytes, &raw_full[rs]);
+          bulk_g2s(dst + kRawABytes, src + static_cast<size_t>(J0) * 8, rowsB * 32u, &raw_full[rs]);
         }
       }
-      // generic-proxy writes -> visible to the tensor core (async proxy), then one arrival per warp
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
-      if (it + 1 < nstages) {
+    }
+  } else {
+    // ================================== expansion warps ==================================
+    const int pw = warp - 6;
+    const int r8 = lane & 7, rg2 = (lane >> 3) & 1, q = lane >> 4;
+    uint32_t rawoff[kMaxT], dstoff[kMaxT];
+    int brow[kMaxT];  // row inside the B block (or -1 for A rows / unused slots)
 #pragma unroll
-        for (int t = 0; t < kMaxT; ++t) cur[t] = nxt[t];
+    for (int k = 0; k < kMaxT; ++k) {
+      const int task = pw + kProducerWarps * k;
+      const int r = 16 * task + 8 * rg2 + r8;
+      rawoff[k] = static_cast<uint32_t>(r * 32 + q * 16);
+      dstoff[k] = static_cast<uint32_t>((2 * task + rg2) * kSBO + 4 * q * kLBO + r8 * 16);
+      brow[k] = (task < kTasks && r >= kMmaTileM) ? r - kMmaTileM : -1;
+    }
+    int pair = -1;
+    uint32_t g = 0;
+    PairDesc d;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int I0, J0;
+      decode_tile(t, descs, pairs, pair, d, I0, J0);
+      bool valid[kMaxT];
+#pragma unroll
+      for (int k = 0; k < kMaxT; ++k) valid[k] = (pw + kProducerWarps * k < kTasks) && (brow[k] < 0 || J0 + brow[k] < d.Npad);
+      for (int it = 0; it < d.npanel; ++it, ++g) {
+        const uint32_t rs = g % kRawStages, s = g % kStages;
+        mbar_wait(&raw_full[rs], (g / kRawStages) & 1u);
+        const unsigned char* raw = raw_base + rs * kRawBytes;
+        uint4 w[kMaxT];
+#pragma unroll
+        for (int k = 0; k < kMaxT; ++k)
+          w[k] = valid[k] ? *reinterpret_cast<const uint4*>(raw + rawoff[k]) : make_uint4(0u, 0u, 0u, 0u);
+        if (g >= kStages) mbar_wait(&empty[s], ((g / kStages) - 1) & 1u);
+        unsigned char* st = stage_base + s * kStageBytes;
+#pragma unroll
+        for (int k = 0; k < kMaxT; ++k)
+          if (pw + kProducerWarps * k < kTasks) expand_quad(w[k], st + dstoff[k]);
+        // generic-proxy writes -> visible to the tensor core (async proxy), then one arrival per warp
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&full[s]);
+          mbar_arrive(&raw_empty[rs]);
+        }
       }
     }
   }
 
+  asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
-  // flush the item's histogram and J-side node sums
-  uint32_t* histp = hist + static_cast<size_t>(pair) * kHistBins;
-  for (int k = tid; k < kHistBins; k += kMmaThreads) {
-    const uint32_t v = hist_s[k];
-    if (v) atomicAdd(&histp[k], v);
-  }
-  for (int k = tid; k < kMmaJ; k += kMmaThreads) {
-    const uint32_t v = tJ[k];
-    if (v && J0 + k < d.Npad) atomicAdd(&t2[d.node_off + J0 + k], static_cast<unsigned long long>(v));
-  }
 }
 
-static size_t mma_smem_bytes() { return static_cast<size_t>(kMmaStages) * kMmaStageBytes + kHistBins * 4 + kMmaJ * 4 + 8 * 8 + 16; }
+// ------------------------------------------------------------------------------------------
+// Pruning threshold per pair (see the header comment).  One CTA of 1024 threads per pair.
+// ------------------------------------------------------------------------------------------
+constexpr int kThetaNodes = 128;
+constexpr int kThetaSamples = kThetaNodes * (kThetaNodes - 1) / 2;  // 8128
+
+__global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restrict__ descs,
+                                                         const uint32_t* __restrict__ adj,
+                                                         uint32_t* __restrict__ theta, int Ke, int prune) {
+  const int pair = blockIdx.x;
+  if (!prune) {
+    if (threadIdx.x == 0) theta[pair] = 0u;
+    return;
+  }
+  const PairDesc d = descs[pair];
+  extern __shared__ __align__(16) unsigned char th_smem[];
+  unsigned short* deg = reinterpret_cast<unsigned short*>(th_smem);  // [Npad] proxy degrees (first 1024 columns)
+  __shared__ unsigned short ts[kThetaSamples];
+  __shared__ int nodes[kThetaNodes];
+  __shared__ int s_cnt, s_nsel, s_nts;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t* adjp = adj + d.adj_off;
+  const int S = d.N < kThetaNodes ? d.N : kThetaNodes;
+
+  // 1. proxy degree: popcount of the first min(stride, 32) words of every row
+  for (int i0 = warp * 4; i0 < d.Npad; i0 += 128) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k;
+      w[k] = (i < d.N && lane < d.stride) ? adjp[static_cast<size_t>(i) * d.stride + lane] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = __reduce_add_sync(0xffffffffu, __popc(w[k]));
+      if (lane == 0 && i0 + k < d.Npad) deg[i0 + k] = static_cast<unsigned short>(c);
+    }
+  }
+  if (t == 0) s_nts = 0;
+  __syncthreads();
+
+  // block-wide count of a per-element predicate over n entries
+  auto block_count = [&](auto pred, int n) {
+    if (t == 0) s_cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int k = t; k < n; k += 1024) c += pred(k) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    const int r = s_cnt;
+    __syncthreads();
+    return r;
+  };
+
+  // 2. largest degree threshold that still leaves >= S nodes
+  int lo = 0, hi = 1025;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (block_count([&](int k) { return deg[k] >= mid; }, d.N) >= S) lo = mid;
+    else hi = mid;
+  }
+  const int thr = lo;
+  const int n_above = block_count([&](int k) { return deg[k] > thr; }, d.N);
+
+  // 3. the S sample nodes in index order: every node above the threshold, then ties until S are taken
+  if (warp == 0) {
+    int nsel = 0, quota = S - n_above;
+    for (int i0 = 0; i0 < d.N && nsel < S; i0 += 32) {
+      const int i = i0 + lane;
+      const int dg = i < d.N ? deg[i] : -1;
+      const bool tie = dg == thr;
+      const unsigned tmask = __ballot_sync(0xffffffffu, tie);
+      const int tie_rank = __popc(tmask & ((1u << lane) - 1u));
+      const bool take = dg > thr || (tie && tie_rank < quota);
+      const unsigned smask = __ballot_sync(0xffffffffu, take);
+      if (take) nodes[nsel + __popc(smask & ((1u << lane) - 1u))] = i;
+      nsel += __popc(smask);
+      quota -= min(quota, __popc(tmask));
+    }
+    if (lane == 0) s_nsel = nsel;
+  }
+  __syncthreads();
+  const int nsel = s_nsel;
+
+  // 4. exact T of every edge among the sample nodes (one warp per candidate pair)
+  for (int x = 0; x + 1 < nsel; ++x) {
+    const int a = nodes[x];
+    const uint32_t* ra = adjp + static_cast<size_t>(a) * d.stride;
+    for (int y = x + 1 + warp; y < nsel; y += 32) {
+      const int b = nodes[y];
+      if (!((ra[b >> 5] >> (b & 31)) & 1u)) continue;
+      const uint32_t* rb = adjp + static_cast<size_t>(b) * d.stride;
+      int c = 0;
+      for (int wd = lane; wd < d.stride; wd += 32) c += __popc(ra[wd] & rb[wd]);
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) ts[atomicAdd(&s_nts, 1)] = static_cast<unsigned short>(c);
+    }
+  }
+  __syncthreads();
+  const int nts = s_nts;
+
+  // 5. theta = K_e-th largest sample count (0 if the sample holds fewer than K_e edges)
+  uint32_t th = 0;
+  if (nts >= Ke) {
+    int l2 = 0, h2 = 65536;
+    while (h2 - l2 > 1) {
+      const int mid = (l2 + h2) >> 1;
+      if (block_count([&](int k) { return ts[k] >= mid; }, nts) >= Ke) l2 = mid;
+      else h2 = mid;
+    }
+    th = static_cast<uint32_t>(l2);
+  }
+  if (t == 0) theta[pair] = th;
+}
 
 int triangles_mma_configure() {
-  const cudaError_t e = cudaFuncSetAttribute(triangles_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(mma_smem_bytes()));
+  cudaError_t e = cudaFuncSetAttribute(triangles_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tri_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 * 2);
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
-int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
-                         PairDev* d_state, const ChunkDev* d_chunk, unsigned long long* d_keys, const uint32_t* d_ubase,
-                         uint32_t* d_ucursor, int unit_pitch, uint32_t* d_hist, unsigned long long* d_t2, int rank,
-                         int world) {
-  const int nJ = (max_npad + kMmaJ - 1) / kMmaJ, nIp = (max_npad + kMmaI - 1) / kMmaI;
-  int items = 0;
-  for (int jq = 0; jq < nJ; ++jq) items += std::min(nIp, (kMmaJ * jq + kMmaJ - 2) / kMmaI + 1);
-  dim3 grid(items, pairs);
-  triangles_mma_kernel<<<grid, kMmaThreads, mma_smem_bytes(), lc.stream>>>(d_desc, d_adj, d_state, d_chunk, d_keys, d_ubase,
-                                                                          d_ucursor, unit_pitch, d_hist, d_t2, rank, world);
-  const cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int total_tiles, int max_npad,
+                         const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
+                         unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
+                         int Ke, int prune) {
+  tri_theta_kernel<<<pairs, 1024, static_cast<size_t>(max_npad) * 2, lc.stream>>>(d_desc, d_adj, d_theta, Ke, prune);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  const int grid = std::min(total_tiles, lc.sm_count);
+  if (grid > 0)
+    triangles_mma_kernel<<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, pairs, total_tiles, d_adj, d_panel, d_state,
+                                                                   d_chunk, d_keys, d_theta, d_hist, d_t2);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 2 : -static_cast<int>(e);
 }
 
 }  // namespace saccot

@@ -25,7 +25,7 @@ def set_params(reg, **kw):
         setattr(reg.params, k, v)
 
 
-def compare_stages(gpu, oracle, pair_idx=0, stages=EXACT):
+def compare_stages(gpu, oracle, pair_idx=0, stages=EXACT, edge_keys=True):
     bad = []
     for name, which in stages:
         a, b = gpu.debug(pair_idx, which), oracle.debug(pair_idx, which)
@@ -34,10 +34,11 @@ def compare_stages(gpu, oracle, pair_idx=0, stages=EXACT):
         elif not (a.view(np.uint8) == b.view(np.uint8)).all():
             n = int((a.view(np.uint8) != b.view(np.uint8)).sum())
             bad.append(f"{name}: {n} differing bytes of {a.nbytes}")
-    a = np.sort(gpu.debug(pair_idx, _abi.DBG_EDGE_KEYS))
-    b = np.sort(oracle.debug(pair_idx, _abi.DBG_EDGE_KEYS))
-    if a.shape != b.shape or not (a == b).all():
-        bad.append("edge_keys (sorted) differ")
+    if edge_keys:
+        a = np.sort(gpu.debug(pair_idx, _abi.DBG_EDGE_KEYS))
+        b = np.sort(oracle.debug(pair_idx, _abi.DBG_EDGE_KEYS))
+        if a.shape != b.shape or not (a == b).all():
+            bad.append("edge_keys (sorted) differ")
     assert not bad, "; ".join(bad)
 
 
@@ -381,16 +382,79 @@ def test_many_tiny_pairs_and_repeated_calls_on_one_ctx(gpu_lib, oracle_lib):
 
 
 # ---- tensor-core triangle path (tcgen05 kind::mxf4, TMEM accumulators) ---------------------------
-@pytest.mark.parametrize("N,ratio", [(64, 0.3), (129, 0.3), (500, 0.2), (1000, 0.1), (2048, 0.1), (5000, 0.05)])
-def test_tensor_core_triangle_path_matches_oracle(gpu, oracle, N, ratio):
+PRUNED = [st for st in EXACT if st[0] != "hist"]
+
+
+def compare_pruned(gpu, oracle, pair_idx=0):
+    """With pruning the kernel keeps only edges whose T reaches a per-pair threshold that provably lies at
+    or below the K_e-th largest T: every stage downstream is identical, the key list is a subset that
+    contains every edge at or above the K_e-th key, and the histogram is exact above that key's digit."""
+    compare_stages(gpu, oracle, pair_idx, stages=PRUNED, edge_keys=False)
+    kg = np.sort(gpu.debug(pair_idx, _abi.DBG_EDGE_KEYS))
+    ko = np.sort(oracle.debug(pair_idx, _abi.DBG_EDGE_KEYS))
+    assert len(np.unique(kg)) == len(kg) and np.isin(kg, ko).all(), "pruned keys are not a subset of the oracle's"
+    top = oracle.debug(pair_idx, _abi.DBG_TOP_EDGES)
+    if len(top):
+        t_min = int(top[-1] >> np.uint64(32))
+        need = ko[(ko >> np.uint64(32)) >= np.uint64(t_min)]
+        assert np.isin(need, kg).all(), "an edge at or above the K_e-th count was pruned"
+        hg, ho = gpu.debug(pair_idx, _abi.DBG_HIST), oracle.debug(pair_idx, _abi.DBG_HIST)
+        d = t_min >> 4
+        assert (hg[d + 1:] == ho[d + 1:]).all(), "histogram differs above the threshold digit"
+        assert int((need >> np.uint64(36) == np.uint64(d)).sum()) <= hg[d] <= ho[d]
+    if len(ko) and len(kg) < len(ko):
+        assert len(kg) >= min(len(ko), len(top))
+
+
+@pytest.mark.parametrize("prune", [0, 1])
+@pytest.mark.parametrize("N,ratio", [(3, 1.0), (64, 0.3), (129, 0.3), (241, 0.2), (500, 0.2), (1000, 0.1), (2048, 0.1),
+                                     (5000, 0.05)])
+def test_tensor_core_triangle_path_matches_oracle(gpu, oracle, N, ratio, prune):
     gpu.set("triangle_path", 1)
-    assert gpu.get("triangle_path") == 1
+    gpu.set("triangle_prune", prune)
+    assert gpu.get("triangle_path") == 1 and gpu.get("triangle_prune") == prune
     p = synth.make_pair(N, ratio, 8800 + N)
-    run_both(gpu, oracle, p, num_edges=256, apex_per_edge=4)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier, num_edges=256, apex_per_edge=4)
+    out_g = gpu.register(p.src, p.dst)
+    out_o = oracle.register(p.src, p.dst)
+    if prune:
+        compare_pruned(gpu, oracle)
+    else:
+        compare_stages(gpu, oracle)
+    compare_pose(*out_g, *out_o)
 
 
-def test_tensor_core_path_batch_and_complete_graph(gpu, oracle):
+def test_tensor_core_path_prunes_most_edges_at_headline_scale(gpu, oracle):
     gpu.set("triangle_path", 1)
+    p = synth.make_config_pair("cfg2_3dmatch_256x5000", 3)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
+    out_g = gpu.register(p.src, p.dst)
+    out_o = oracle.register(p.src, p.dst)
+    compare_pruned(gpu, oracle)
+    compare_pose(*out_g, *out_o)
+    kept = len(gpu.debug(0, _abi.DBG_EDGE_KEYS))
+    E = int(gpu.debug(0, _abi.DBG_NUM_EDGES)[0])
+    assert kept >= 1024 and kept < E // 4, (kept, E)
+
+
+def test_tensor_core_path_no_inliers_keeps_selection_exact(gpu, oracle):
+    # no clique: the sample of high-degree nodes holds few edges, the threshold falls back towards 0
+    gpu.set("triangle_path", 1)
+    p = synth.make_pair(3000, 0.0, 8870)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier, num_edges=1024, apex_per_edge=2)
+    gpu.register(p.src, p.dst)
+    oracle.register(p.src, p.dst)
+    compare_pruned(gpu, oracle)
+
+
+@pytest.mark.parametrize("prune", [0, 1])
+def test_tensor_core_path_batch_and_complete_graph(gpu, oracle, prune):
+    gpu.set("triangle_path", 1)
+    gpu.set("triangle_prune", prune)
+    check = compare_pruned if prune else compare_stages
     # complete graph: every T equals N-2 (exact integers out of the fp32 accumulators)
     N = 300
     p = synth.make_pair(N, 1.0, 8900)
@@ -399,12 +463,12 @@ def test_tensor_core_path_batch_and_complete_graph(gpu, oracle):
         set_params(r, num_edges=128, apex_per_edge=4)
     out_g = gpu.register(p.src, dst)
     out_o = oracle.register(p.src, dst)
-    compare_stages(gpu, oracle)
+    check(gpu, oracle)
     compare_pose(*out_g, *out_o)
     # ragged batch
     pairs = [synth.make_pair(n, 0.1, 8950 + k) for k, n in enumerate((300, 1000, 129, 2048, 64, 777))]
     rg = gpu.register_batch([q.src for q in pairs], [q.dst for q in pairs])
     ro = oracle.register_batch([q.src for q in pairs], [q.dst for q in pairs])
     for b in range(len(pairs)):
-        compare_stages(gpu, oracle, b)
+        check(gpu, oracle, b)
         compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
