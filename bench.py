@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--chunk-pairs", type=int, default=0, help="library knob chunk_pairs (0 = auto)")
     ap.add_argument("--lanes", type=int, default=0, help="library knob lanes (0 = library default)")
     ap.add_argument("--triangle-path", type=int, default=-1, help="library knob triangle_path (0 POPC, 1 tensor core)")
+    ap.add_argument("--triangle-dbg", type=int, default=0, help="experiments only (library knob triangle_dbg)")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(synth.CONFIGS),
                     help="synthetic config (default: the headline config, BASELINE.json configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -226,6 +227,8 @@ def main():
         reg.set("lanes", args.lanes)
     if args.triangle_path >= 0:
         reg.set("triangle_path", args.triangle_path)
+    if args.triangle_dbg:
+        reg.set("triangle_dbg", args.triangle_dbg)
     K = reg.params.num_edges * reg.params.apex_per_edge
 
     # device-resident inputs / outputs

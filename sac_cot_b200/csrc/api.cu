@@ -154,6 +154,7 @@ struct sac_cot_ctx {
   int chunk_pairs = 0;
   int n_lanes = 2;
   int tri_path = 0;   // 0 = POPC bitset kernels, 1 = tensor-core (tcgen05 mxf4) kernel
+  int tri_dbg = 0;    // experiments only (bit 0: skip the tensor-core kernel's epilogue work; results are void)
   int tri_prune = 1;  // tensor-core path: drop edges below the per-pair threshold (exact for the selection)
   int64_t launches = 0;
   int64_t retries = 0;
@@ -426,7 +427,7 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   mark(ST_SCAN);
   if (tensor)
     KL_TRY(launch_triangles_mma(lc, L.desc, L.pairs, L.total_tiles, L.max_npad, L.adj, L.panel, L.state, L.chunk, ln.keys,
-                                L.theta, L.hist, L.t2, L.Ke, ctx->tri_prune));
+                                L.theta, L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg));
   else
     KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ln.keys, L.ubase,
                             L.unit_pitch, L.hist, L.t2, rank, world));
@@ -696,6 +697,10 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
   }
   if (!std::strcmp(name, "triangle_prune")) {
     ctx->tri_prune = value != 0;
+    return SAC_COT_OK;
+  }
+  if (!std::strcmp(name, "triangle_dbg")) {
+    ctx->tri_dbg = static_cast<int>(value);
     return SAC_COT_OK;
   }
   if (!std::strcmp(name, "stage_timing")) {

@@ -167,7 +167,7 @@ __host__ __device__ inline int mma_tiles_of_pair(int N) {
 int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int total_tiles, int max_npad,
                          const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
                          unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
-                         int Ke, int prune);
+                         int Ke, int prune, int dbg);
 int triangles_mma_configure();
 
 // kernels_select.cu — S3 edge ranking + apex selection

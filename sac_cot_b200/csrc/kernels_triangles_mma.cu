@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
     const PairDesc* __restrict__ descs, int pairs, int total_tiles, const uint32_t* __restrict__ adj,
     const uint32_t* __restrict__ panel, PairDev* __restrict__ state, const ChunkDev* __restrict__ chunk,
     unsigned long long* __restrict__ keys, const uint32_t* __restrict__ theta, uint32_t* __restrict__ hist,
-    unsigned long long* __restrict__ t2) {
+    unsigned long long* __restrict__ t2, int dbg) {
   if (chunk->overflow) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stage_base = smem_raw;
@@ -285,9 +285,10 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
       const uint32_t tbase = tmem + ((32u * warp) << 16) + static_cast<uint32_t>(kMmaTileN * buf);
       float rowsum = 0.0f;
       uint32_t v[2][16];
-      SACCOT_TMEM_LD16(v[0], tbase);
+      if (!(dbg & 1)) SACCOT_TMEM_LD16(v[0], tbase);
 #pragma unroll
       for (int c = 0; c < kMmaTileN / 16; ++c) {
+        if (dbg & 1) break;  // experiment: main loop without the epilogue work
         uint32_t(&vc)[16] = v[c & 1];
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (c + 1 < kMmaTileN / 16) SACCOT_TMEM_LD16(v[(c + 1) & 1], tbase + 16u * (c + 1));
@@ -363,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
           const uint32_t bA = sbase + s * kStageBytes, bB = bA + (kMmaTileM / 8) * kSBO;
 #pragma unroll
           for (int ks = 0; ks < kStageK / 64; ++ks) {
+            if (dbg & 8) break;
             const uint64_t da = umma_desc(bA + ks * 2 * kLBO), db = umma_desc(bB + ks * 2 * kLBO);
             const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
             asm volatile(
@@ -436,9 +438,9 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
         unsigned char* st = stage_base + s * kStageBytes;
 #pragma unroll
         for (int k = 0; k < kMaxT; ++k)
-          if (pw + kProducerWarps * k < kTasks) expand_quad(w[k], st + dstoff[k]);
+          if (pw + kProducerWarps * k < kTasks && !(dbg & 4)) expand_quad(w[k], st + dstoff[k]);
         // generic-proxy writes -> visible to the tensor core (async proxy), then one arrival per warp
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (!(dbg & 2)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&full[s]);
@@ -455,14 +457,21 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
-// Pruning threshold per pair (see the header comment).  One CTA of 1024 threads per pair.
+// Pruning threshold per pair (see the header comment).  One CTA of 1024 threads per pair; every phase is
+// arranged so that its global loads are independent (the kernel is latency-, not throughput-bound).
 // ------------------------------------------------------------------------------------------
 constexpr int kThetaNodes = 128;
 constexpr int kThetaSamples = kThetaNodes * (kThetaNodes - 1) / 2;  // 8128
+constexpr int kThetaChunkW = 192;                                   // adjacency words per staged row chunk
+
+static size_t theta_smem_bytes(int max_npad) {
+  const int cw = std::min(max_npad / 32, kThetaChunkW);
+  return static_cast<size_t>(max_npad) + static_cast<size_t>(kThetaNodes) * cw * 4 + kThetaSamples * 6 + 16;
+}
 
 __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restrict__ descs,
                                                          const uint32_t* __restrict__ adj,
-                                                         uint32_t* __restrict__ theta, int Ke, int prune) {
+                                                         uint32_t* __restrict__ theta, int Ke, int prune, int max_npad) {
   const int pair = blockIdx.x;
   if (!prune) {
     if (threadIdx.x == 0) theta[pair] = 0u;
@@ -470,26 +479,30 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
   }
   const PairDesc d = descs[pair];
   extern __shared__ __align__(16) unsigned char th_smem[];
-  unsigned short* deg = reinterpret_cast<unsigned short*>(th_smem);  // [Npad] proxy degrees (first 1024 columns)
-  __shared__ unsigned short ts[kThetaSamples];
+  const int cw_max = min(max_npad / 32, kThetaChunkW);
+  uint32_t* rows_s = reinterpret_cast<uint32_t*>(th_smem);                         // [128][cw]
+  uint32_t* cand = rows_s + static_cast<size_t>(kThetaNodes) * cw_max;             // [8128] x << 16 | y
+  unsigned short* ts = reinterpret_cast<unsigned short*>(cand + kThetaSamples);   // [8128] exact T (<= 65535)
+  unsigned char* deg = reinterpret_cast<unsigned char*>(ts + kThetaSamples);      // [Npad] proxy degrees, saturated
   __shared__ int nodes[kThetaNodes];
   __shared__ int s_cnt, s_nsel, s_nts;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const uint32_t* adjp = adj + d.adj_off;
   const int S = d.N < kThetaNodes ? d.N : kThetaNodes;
 
-  // 1. proxy degree: popcount of the first min(stride, 32) words of every row
-  for (int i0 = warp * 4; i0 < d.Npad; i0 += 128) {
-    uint32_t w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k;
-      w[k] = (i < d.N && lane < d.stride) ? adjp[static_cast<size_t>(i) * d.stride + lane] : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = __reduce_add_sync(0xffffffffu, __popc(w[k]));
-      if (lane == 0 && i0 + k < d.Npad) deg[i0 + k] = static_cast<unsigned short>(c);
+  // 1. proxy degree: popcount of the first min(stride, 16) words (512 columns) of every row
+  {
+    const int nq = min(d.stride, 16) / 4;  // stride is a multiple of 4
+    for (int i = t; i < d.Npad; i += 1024) {
+      int c = 0;
+      if (i < d.N) {
+        const uint4* rp = reinterpret_cast<const uint4*>(adjp + static_cast<size_t>(i) * d.stride);
+        for (int k = 0; k < nq; ++k) {
+          const uint4 w = rp[k];
+          c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+        }
+      }
+      deg[i] = static_cast<unsigned char>(min(c, 255));
     }
   }
   if (t == 0) s_nts = 0;
@@ -510,7 +523,7 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
   };
 
   // 2. largest degree threshold that still leaves >= S nodes
-  int lo = 0, hi = 1025;
+  int lo = 0, hi = 256;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (block_count([&](int k) { return deg[k] >= mid; }, d.N) >= S) lo = mid;
@@ -539,22 +552,40 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
   __syncthreads();
   const int nsel = s_nsel;
 
-  // 4. exact T of every edge among the sample nodes (one warp per candidate pair)
-  for (int x = 0; x + 1 < nsel; ++x) {
-    const int a = nodes[x];
-    const uint32_t* ra = adjp + static_cast<size_t>(a) * d.stride;
-    for (int y = x + 1 + warp; y < nsel; y += 32) {
-      const int b = nodes[y];
-      if (!((ra[b >> 5] >> (b & 31)) & 1u)) continue;
-      const uint32_t* rb = adjp + static_cast<size_t>(b) * d.stride;
-      int c = 0;
-      for (int wd = lane; wd < d.stride; wd += 32) c += __popc(ra[wd] & rb[wd]);
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0) ts[atomicAdd(&s_nts, 1)] = static_cast<unsigned short>(c);
+  // 4a. edges among the sample nodes
+  for (int idx = t; idx < nsel * nsel; idx += 1024) {
+    const int x = idx / nsel, y = idx - x * nsel;
+    if (x < y) {
+      const int a = nodes[x], b = nodes[y];
+      if ((adjp[static_cast<size_t>(a) * d.stride + (b >> 5)] >> (b & 31)) & 1u) {
+        const int pos = atomicAdd(&s_nts, 1);
+        cand[pos] = (static_cast<uint32_t>(x) << 16) | static_cast<uint32_t>(y);
+        ts[pos] = 0;
+      }
     }
   }
   __syncthreads();
   const int nts = s_nts;
+
+  // 4b. exact T of those edges: the sample rows are staged chunk by chunk, one warp per edge
+  for (int c0 = 0; c0 < d.stride; c0 += cw_max) {
+    const int cw = min(cw_max, d.stride - c0);
+    for (int r = warp; r < nsel; r += 32) {
+      const uint32_t* rp = adjp + static_cast<size_t>(nodes[r]) * d.stride + c0;
+      for (int w = lane; w < cw; w += 32) rows_s[r * cw_max + w] = rp[w];
+    }
+    __syncthreads();
+    for (int e = warp; e < nts; e += 32) {
+      const uint32_t xy = cand[e];
+      const uint32_t* ra = rows_s + (xy >> 16) * cw_max;
+      const uint32_t* rb = rows_s + (xy & 0xFFFFu) * cw_max;
+      int c = 0;
+      for (int w = lane; w < cw; w += 32) c += __popc(ra[w] & rb[w]);
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) ts[e] = static_cast<unsigned short>(ts[e] + c);
+    }
+    __syncthreads();
+  }
 
   // 5. theta = K_e-th largest sample count (0 if the sample holds fewer than K_e edges)
   uint32_t th = 0;
@@ -573,21 +604,22 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
 int triangles_mma_configure() {
   cudaError_t e = cudaFuncSetAttribute(triangles_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tri_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 * 2);
+    e = cudaFuncSetAttribute(tri_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(theta_smem_bytes(65536)));
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
 int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int total_tiles, int max_npad,
                          const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
                          unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
-                         int Ke, int prune) {
-  tri_theta_kernel<<<pairs, 1024, static_cast<size_t>(max_npad) * 2, lc.stream>>>(d_desc, d_adj, d_theta, Ke, prune);
+                         int Ke, int prune, int dbg) {
+  tri_theta_kernel<<<pairs, 1024, theta_smem_bytes(max_npad), lc.stream>>>(d_desc, d_adj, d_theta, Ke, prune, max_npad);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -static_cast<int>(e);
   const int grid = std::min(total_tiles, lc.sm_count);
   if (grid > 0)
     triangles_mma_kernel<<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, pairs, total_tiles, d_adj, d_panel, d_state,
-                                                                   d_chunk, d_keys, d_theta, d_hist, d_t2);
+                                                                   d_chunk, d_keys, d_theta, d_hist, d_t2, dbg);
   e = cudaGetLastError();
   return e == cudaSuccess ? 2 : -static_cast<int>(e);
 }
