@@ -150,7 +150,7 @@ int launch_triangles(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
 int triangles_configure();  // opt-in dynamic shared memory; call once per device
 
 // kernels_triangles_mma.cu — S2 triangle counts on the tensor cores (tcgen05 kind::mxf4, TMEM)
-constexpr int kMmaTileM = 128;      // rows of i per tile (one TMEM accumulator, M = 128)
+constexpr int kMmaTileM = 256;      // rows of i per tile: a CTA pair (cta_group::2), 128 rows = TMEM lanes per CTA
 constexpr int kMmaTileN = 240;      // columns of j per tile (UMMA N = 240; two accumulators = 480 TMEM columns)
 // tiles of one pair: J-blocks jq = 0 .. ceil(N/240)-1, each with the row blocks that hold some i < j
 __host__ __device__ inline int mma_tiles_of_jblock(int N, int jq) {

@@ -31,35 +31,44 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdio>
 
 namespace saccot {
 
 namespace {
 
 constexpr int kThreads = 512;
+constexpr int kCtaM = 128;                            // rows of the pair tile owned by one CTA (one TMEM lane each)
+constexpr int kCtaNB = kMmaTileN / 2;                 // 120 rows of the B operand staged by one CTA
 constexpr int kStageK = 256;                          // K elements (adjacency columns) per stage
-constexpr int kStages = 3;                            // expanded operand stages
-constexpr int kRawStages = 4;                         // raw (bit) stages
-constexpr int kRows = kMmaTileM + kMmaTileN;          // 368 rows expanded per stage
+constexpr int kStages = 4;                            // expanded operand stages
+constexpr int kRawStages = 8;                         // raw (bit) stages
+constexpr int kRows = kCtaM + kCtaNB;                 // 248 rows expanded per stage and CTA
+constexpr int kGroups = kRows / 8;                    // 31 groups of 8 rows
 constexpr int kLBO = 128;                             // next 16-byte K chunk (core matrices contiguous along K)
 constexpr int kSBO = (kStageK / 2 / 16) * 128;        // next 8-row group: 8 core matrices = 1024 B
-constexpr int kStageBytes = (kRows / 8) * kSBO;       // 47104
-constexpr int kRawBytes = kRows * 32;                 // 11776
-constexpr int kRawABytes = kMmaTileM * 32;            // 4096
-constexpr int kProducerWarps = 10;
-constexpr int kTasks = kRows / 16;                    // 23 warp tasks (16 rows x 2 quads) per stage
-constexpr int kMaxT = (kTasks + kProducerWarps - 1) / kProducerWarps;  // 3
+constexpr int kStageBytes = kGroups * kSBO;           // 31744
+constexpr int kRawBytes = kRows * 32;                 // 7936
+constexpr int kRawABytes = kCtaM * 32;                // 4096
+constexpr int kProducerWarps = 8;                     // warps 6..13 (14 and 15 idle)
+constexpr int kGroupsP = kProducerWarps / 2;          // producer groups of two warps; group = stage % kGroupsP
+// A group must meet every phase of the barriers it waits on in order (mbarrier waits only know the phase
+// parity: a waiter two phases early passes at once).  With the group count dividing both ring sizes, a
+// group always returns to the same slots.
+static_assert(kStages % kGroupsP == 0 && kRawStages % kGroupsP == 0, "producer groups must divide the ring sizes");
+constexpr int kTasksPerWarp = 8;                      // 16 warp tasks (16 rows x 2 quads) per stage, the last one half
 constexpr int kKeyBuf = 640;                          // staged keys per epilogue warp (flush above 128)
 constexpr uint32_t kSfCol = 480;                      // scale factors: TMEM columns [480, 512)
 constexpr uint32_t kSfWord = 0x807F807Fu;             // UE8M0 per K block of 32: {1.0, 2.0, 1.0, 2.0}
 
 // shared-memory carve-up (dynamic)
-constexpr int kOffRaw = kStages * kStageBytes;                    // 141312
-constexpr int kOffHist = kOffRaw + kRawStages * kRawBytes;        // +47104
+constexpr int kOffRaw = kStages * kStageBytes;                    // 126976
+constexpr int kOffHist = kOffRaw + kRawStages * kRawBytes;        // +63488
 constexpr int kOffKeys = kOffHist + kHistBins * 4;                // +16384
 constexpr int kOffBars = kOffKeys + 4 * kKeyBuf * 8;              // +20480
 constexpr int kNumBars = 2 * kStages + 2 * kRawStages + 4;
-constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16;
+constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 32;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -73,8 +82,53 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// Barrier wait with a watchdog: a protocol bug must end the kernel with an error, not hang the GPU.
+// Default (CTA-scope) semantics also for barriers that peer-CTA threads arrive on, as in CUTLASS's
+// ClusterBarrier: cluster-scope release/acquire compiles to MEMBAR.ALL.GPU / CCTL.IVALL per arrival
+// (measured: 3x slower main loop); what the tensor cores read was made visible by the writers'
+// fence.proxy.async before their arrival.
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag, uint32_t info) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (int spins = 0;; ++spins) {
+    uint32_t done;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins == 0) {
+      t0 = clock64();
+    } else {
+      const long long dt = clock64() - t0;
+      if (dt > 1000000000LL && (spins & 0x40000000) == 0) {  // report once, give the other roles time to report too
+        if ((threadIdx.x & 31) == 0)
+          printf("sac_cot: barrier timeout, cta %d warp %d tag %d parity %u info %u\n", blockIdx.x, threadIdx.x >> 5, tag,
+                 parity, info);
+        spins |= 0x40000000;
+      }
+      if (dt > 3000000000LL) __trap();
+    }
+  }
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// completion of every tcgen05 operation issued so far -> one arrival on `bar` in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // 128 adjacency bits of one row -> four 16-byte K chunks (see the header comment)
@@ -150,7 +204,21 @@ __device__ __forceinline__ float colsum16(float (&m)[16], int lane) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
+// PROF: experiments only — lane 0 of one warp per role accumulates the cycles it spends waiting on each
+// barrier and CTAs 0/1 print them (dbg bit 6).
+#define SACCOT_TIMED_WAIT(acc, call)       \
+  do {                                     \
+    if (PROF) {                            \
+      const long long t0__ = clock64();    \
+      call;                                \
+      acc += clock64() - t0__;             \
+    } else {                               \
+      call;                                \
+    }                                      \
+  } while (0)
+
+template <bool PROF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangles_mma_kernel(
     const PairDesc* __restrict__ descs, int pairs, int total_tiles, const uint32_t* __restrict__ adj,
     const uint32_t* __restrict__ panel, PairDev* __restrict__ state, const ChunkDev* __restrict__ chunk,
     unsigned long long* __restrict__ keys, const uint32_t* __restrict__ theta, uint32_t* __restrict__ hist,
@@ -162,69 +230,78 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
   uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem_raw + kOffHist);
   unsigned long long* kbuf = reinterpret_cast<unsigned long long*>(smem_raw + kOffKeys);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kOffBars);
-  uint64_t* full = bars;                                 // [kStages]   producers -> MMA
-  uint64_t* empty = full + kStages;                      // [kStages]   MMA commit -> producers
+  uint64_t* full = bars;                                 // [kStages]   producers of both CTAs -> MMA (leader's copy)
+  uint64_t* empty = full + kStages;                      // [kStages]   MMA commit (multicast) -> producers
   uint64_t* raw_full = empty + kStages;                  // [kRawStages] bulk copies -> producers
   uint64_t* raw_empty = raw_full + kRawStages;           // [kRawStages] producers -> bulk-copy issuer
-  uint64_t* tmem_full = raw_empty + kRawStages;          // [2] MMA commit -> epilogue
-  uint64_t* tmem_empty = tmem_full + 2;                  // [2] epilogue -> MMA
+  uint64_t* tmem_full = raw_empty + kRawStages;          // [2] MMA commit (multicast) -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;                  // [2] epilogue warps of both CTAs -> MMA (leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  uint32_t* fill_s = tmem_slot + 1;                      // [4] staged-key counters of the epilogue warps
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;  // cluster = CTA pair = one 256 x 240 tile at a time
+
   for (int k = tid; k < kHistBins; k += kThreads) hist_s[k] = 0;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], kProducerWarps);
+      mbar_init(&full[s], 4);  // two warps of the stage's group in each CTA
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < kRawStages; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], kProducerWarps);
+      mbar_init(&raw_empty[s], 2);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);
+      mbar_init(&tmem_empty[b], 8);
     }
     mbar_fence_init();
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = *tmem_slot;
+  if (warp < 4) {  // scale factors: every 32-bit word of columns [480, 512) = {1.0, 2.0, 1.0, 2.0}
+    const uint32_t taddr = tmem + ((32u * warp) << 16) + kSfCol;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
+            taddr),
+        "r"(kSfWord)
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  // barriers initialised, TMEM allocated and scale factors written in BOTH CTAs before anyone proceeds
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;");
 
   if (warp < 4) {
     // ================================== epilogue warps ==================================
-    {  // scale factors: every 32-bit word of columns [480, 512) = {1.0, 2.0, 1.0, 2.0}
-      const uint32_t taddr = tmem + ((32u * warp) << 16) + kSfCol;
-      asm volatile(
-          "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
-              taddr),
-          "r"(kSfWord)
-          : "memory");
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;");
-    }
-    asm volatile("bar.sync 1, 160;" ::: "memory");  // epilogue warps + MMA warp: scale factors are in place
-
     unsigned long long* kb = kbuf + warp * kKeyBuf;
-    uint32_t fill = 0;          // staged keys of this warp (warp-uniform)
-    int pair = -1, cur_pair = -1;
-    PairDesc d;
+    uint32_t* fill_p = fill_s + warp;  // staged keys of this warp
+    if (lane == 0) *fill_p = 0u;
+    __syncwarp();
+    int cur_pair = -1, cur_bins = 0;
     unsigned long long* keyp = nullptr;
     unsigned long long* kcount = nullptr;
-    int thbits = 0;
+    float thf = 0.0f;
     auto flush_keys = [&]() {
       __syncwarp();
+      const uint32_t fill = *fill_p;
       if (fill) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(kcount, static_cast<unsigned long long>(fill));
         base = __shfl_sync(0xffffffffu, base, 0);
         for (uint32_t k = lane; k < fill; k += 32) keyp[base + k] = kb[k];
-        fill = 0;
+        __syncwarp();
+        if (lane == 0) *fill_p = 0u;
       }
       __syncwarp();
     };
@@ -232,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
       flush_keys();
       asm volatile("bar.sync 2, 128;" ::: "memory");
       uint32_t* histp = hist + static_cast<size_t>(cur_pair) * kHistBins;
-      for (int k = tid; k < kHistBins; k += 128) {
+      for (int k = tid; k < cur_bins; k += 128) {  // T <= N - 2: higher bins are empty
         const uint32_t v = hist_s[k];
         if (v) {
           atomicAdd(&histp[k], v);
@@ -241,32 +318,51 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
     };
+    // raw edge-bit window of this thread's row for a tile: 9 words starting at the word that holds column J0
+    auto load_window = [&](const PairDesc& pd, int I0, int J0, uint32_t (&w)[9]) {
+      const int i = I0 + kCtaM * static_cast<int>(rank) + 32 * warp + lane;
+      const uint32_t* rowp = adj + pd.adj_off + static_cast<size_t>(i) * pd.stride;
+      const int w0 = J0 >> 5;
+      const bool row_ok = i < pd.Npad;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w[k] = (row_ok && w0 + k < pd.stride) ? rowp[w0 + k] : 0u;
+    };
 
-    int n = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n) {
-      int I0, J0;
+    int n = 0, pair = -1;
+    PairDesc d;
+    long long w_tfull = 0, t_begin = PROF ? clock64() : 0;
+    int t = cid, I0 = 0, J0 = 0;
+    uint32_t wraw[9];
+    if (t < total_tiles) {
       decode_tile(t, descs, pairs, pair, d, I0, J0);
+      load_window(d, I0, J0, wraw);
+    }
+    for (; t < total_tiles; ++n) {
+      // ---- this tile ----
+      const int tI0 = I0, tJ0 = J0;
+      const long long node_off = d.node_off;
       if (pair != cur_pair) {
         if (cur_pair >= 0) flush_pair();
         cur_pair = pair;
+        cur_bins = min(kHistBins, (d.N >> 4) + 1);
         keyp = keys + state[pair].key_base;
         kcount = &state[pair].key_count;
-        thbits = __float_as_int(static_cast<float>(theta[pair]));
+        thf = static_cast<float>(theta[pair]);
       }
-      // ---- edge bits of this thread's row inside the tile's 240 columns (window aligned to J0) ----
-      const int i = I0 + 32 * warp + lane;
-      uint32_t win[9];
+      uint32_t win[8];
       {
-        const uint32_t* rowp = adj + d.adj_off + static_cast<size_t>(i) * d.stride;
-        const int w0 = J0 >> 5;
+        if (tJ0 & 16) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) win[k] = (w0 + k < d.stride) ? rowp[w0 + k] : 0u;
-        if (J0 & 16) {
+          for (int k = 0; k < 8; ++k) win[k] = __funnelshift_r(wraw[k], wraw[k + 1], 16);
+        } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) win[k] = __funnelshift_r(win[k], win[k + 1], 16);
+          for (int k = 0; k < 8; ++k) win[k] = wraw[k];
         }
         win[7] &= 0xFFFFu;  // columns 240..255 of the window belong to the next J-block
-        const int dd = i - J0;  // keep j > i: clear window bits 0..dd
+      }
+      const int i = tI0 + kCtaM * static_cast<int>(rank) + 32 * warp + lane;
+      {
+        const int dd = i - tJ0;  // keep j > i: clear window bits 0..dd
         if (dd >= 0) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -276,14 +372,20 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
           }
         }
       }
+      // ---- next tile: decode it and start loading its window now (hidden behind this tile's work) ----
+      t += ncl;
+      if (t < total_tiles) {
+        decode_tile(t, descs, pairs, pair, d, I0, J0);
+        load_window(d, I0, J0, wraw);
+      }
       const unsigned long long ikey = static_cast<unsigned long long>(0xFFFFu - static_cast<unsigned int>(i)) << 16;
 
       // ---- accumulators of tile n ----
       const int buf = n & 1;
-      mbar_wait(&tmem_full[buf], static_cast<uint32_t>((n >> 1) & 1));
+      SACCOT_TIMED_WAIT(w_tfull, mbar_wait_wd(&tmem_full[buf], static_cast<uint32_t>((n >> 1) & 1), 1, n));
       asm volatile("tcgen05.fence::after_thread_sync;");
       const uint32_t tbase = tmem + ((32u * warp) << 16) + static_cast<uint32_t>(kMmaTileN * buf);
-      float rowsum = 0.0f;
+      float rs0 = 0.0f, rs1 = 0.0f, rs2 = 0.0f, rs3 = 0.0f;
       uint32_t v[2][16];
       if (!(dbg & 1)) SACCOT_TMEM_LD16(v[0], tbase);
 #pragma unroll
@@ -293,92 +395,92 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (c + 1 < kMmaTileN / 16) SACCOT_TMEM_LD16(v[(c + 1) & 1], tbase + 16u * (c + 1));
         const uint32_t bits16 = (win[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
-        if (fill > 128u) flush_keys();
-        // candidates: edge and T >= theta (positive floats compare like integers)
-        uint32_t lt = 0;
+        // masked counts (0 where there is no edge j > i)
+        float m[16];
 #pragma unroll
-        for (int k = 15; k >= 0; --k) lt = __funnelshift_l(static_cast<uint32_t>(static_cast<int>(vc[k]) - thbits), lt, 1);
-        const uint32_t cand = ~lt & bits16;
-        const int nc = __popc(cand);
-        int incl = nc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int u = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += u;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-          uint32_t pos = fill + static_cast<uint32_t>(incl - nc);
-          const unsigned int jkey = 0xFFFFu - static_cast<unsigned int>(J0 + 16 * c);
+        for (int k = 0; k < 16; ++k) m[k] = (bits16 & (1u << k)) ? __uint_as_float(vc[k]) : 0.0f;
+        rs0 += (m[0] + m[4]) + (m[8] + m[12]);
+        rs1 += (m[1] + m[5]) + (m[9] + m[13]);
+        rs2 += (m[2] + m[6]) + (m[10] + m[14]);
+        rs3 += (m[3] + m[7]) + (m[11] + m[15]);
+        const float vmax = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+        const float vmax2 =
+            fmaxf(fmaxf(fmaxf(m[8], m[9]), fmaxf(m[10], m[11])), fmaxf(fmaxf(m[12], m[13]), fmaxf(m[14], m[15])));
+        // rare (with a tight theta): some edge of these 32 x 16 entries reaches the pruning threshold
+        if (__any_sync(0xffffffffu, fmaxf(vmax, vmax2) >= thf)) {
+          const unsigned int jkey = 0xFFFFu - static_cast<unsigned int>(tJ0 + 16 * c);
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            if (cand & (1u << k)) {
+            if ((bits16 & (1u << k)) && __uint_as_float(vc[k]) >= thf) {
               const unsigned int T = __float2uint_rn(__uint_as_float(vc[k]));  // exact integer in fp32
-              kb[pos++] = (static_cast<unsigned long long>(T) << 32) | ikey | static_cast<unsigned long long>(jkey - k);
+              const uint32_t pos = atomicAdd(fill_p, 1u);
+              kb[pos] = (static_cast<unsigned long long>(T) << 32) | ikey | static_cast<unsigned long long>(jkey - k);
               atomicAdd(&hist_s[T >> 4], 1u);
             }
           }
-          fill += static_cast<uint32_t>(total);
+          __syncwarp();
+          if (*fill_p > 128u) flush_keys();
         }
-        // masked counts: row sum (t2_i) and column sums (t2_j)
-        float m[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          m[k] = (bits16 & (1u << k)) ? __uint_as_float(vc[k]) : 0.0f;
-          rowsum += m[k];
-        }
+        // column sums (t2_j)
         const float cs = colsum16(m, lane);
         if (!(lane & 1) && cs > 0.0f)
-          atomicAdd(&t2[d.node_off + J0 + 16 * c + ((lane >> 1) & 15)], static_cast<unsigned long long>(cs));
+          atomicAdd(&t2[node_off + tJ0 + 16 * c + ((lane >> 1) & 15)], static_cast<unsigned long long>(cs));
       }
-      // accumulator buffer is free again
+      // accumulator buffer is free again (the MMA issuer lives in the leader CTA)
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-      if (rowsum > 0.0f) atomicAdd(&t2[d.node_off + i], static_cast<unsigned long long>(rowsum));
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0u);
+      const float rowsum = (rs0 + rs1) + (rs2 + rs3);
+      if (rowsum > 0.0f) atomicAdd(&t2[node_off + i], static_cast<unsigned long long>(rowsum));
     }
     if (cur_pair >= 0) flush_pair();
+    if (PROF && blockIdx.x < 2 && tid == 0)
+      printf("cta %d epilogue: tiles %d total %lld wait_tmem_full %lld\n", blockIdx.x, n, clock64() - t_begin, w_tfull);
   } else if (warp == 4) {
-    // ================================== MMA issuer ==================================
-    asm volatile("bar.sync 1, 160;" ::: "memory");
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    // instruction descriptor: block-scaled, A/B = E2M1, UE8M0 scales, N = 240, M = 128, K-major both
-    const uint32_t idesc = (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kMmaTileN >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
-    const uint32_t sbase = smem_u32(stage_base);
-    int pair = -1, n = 0;
-    uint32_t g = 0;
-    PairDesc d;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n) {
-      int I0, J0;
-      decode_tile(t, descs, pairs, pair, d, I0, J0);
-      const int buf = n & 1;
-      if (n >= 2) {
-        mbar_wait(&tmem_empty[buf], static_cast<uint32_t>(((n >> 1) - 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;");
-      }
-      for (int it = 0; it < d.npanel; ++it, ++g) {
-        const uint32_t s = g % kStages;
-        mbar_wait(&full[s], (g / kStages) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        if (lane == 0) {
-          const uint32_t bA = sbase + s * kStageBytes, bB = bA + (kMmaTileM / 8) * kSBO;
-#pragma unroll
-          for (int ks = 0; ks < kStageK / 64; ++ks) {
-            if (dbg & 8) break;
-            const uint64_t da = umma_desc(bA + ks * 2 * kLBO), db = umma_desc(bB + ks * 2 * kLBO);
-            const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-            asm volatile(
-                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(
-                    tmem + static_cast<uint32_t>(kMmaTileN * buf)),
-                "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 16u)
-                : "memory");
-          }
-          umma_commit(&empty[s]);                           // stage reusable once these MMAs have read it
-          if (it == d.npanel - 1) umma_commit(&tmem_full[buf]);  // accumulator complete
+    // ================================== MMA issuer (leader CTA only) ==================================
+    if (rank == 0) {
+      // instruction descriptor: block-scaled, A/B = E2M1, UE8M0 scales, N = 240, M = 256 (2 x 128), K-major both
+      const uint32_t idesc = (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kMmaTileN >> 3) << 17) | (1u << 23) | ((256u >> 4) << 24);
+      const uint32_t sbase = smem_u32(stage_base);
+      int pair = -1, n = 0;
+      uint32_t g = 0;
+      PairDesc d;
+      long long w_full = 0, w_tempty = 0, t_begin = PROF ? clock64() : 0;
+      for (int t = cid; t < total_tiles; t += ncl, ++n) {
+        int I0, J0;
+        decode_tile(t, descs, pairs, pair, d, I0, J0);
+        const int buf = n & 1;
+        if (n >= 2) {
+          SACCOT_TIMED_WAIT(w_tempty, mbar_wait_wd(&tmem_empty[buf], static_cast<uint32_t>(((n >> 1) - 1) & 1), 2, n));
+          asm volatile("tcgen05.fence::after_thread_sync;");
         }
-        __syncwarp();
+        for (int it = 0; it < d.npanel; ++it, ++g) {
+          const uint32_t s = g % kStages;
+          SACCOT_TIMED_WAIT(w_full, mbar_wait_wd(&full[s], (g / kStages) & 1u, 3, g));
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          if (lane == 0) {
+            const uint32_t bA = sbase + s * kStageBytes, bB = bA + (kCtaM / 8) * kSBO;
+#pragma unroll
+            for (int ks = 0; ks < kStageK / 64; ++ks) {
+              if (dbg & 8) break;
+              const uint64_t da = umma_desc(bA + ks * 2 * kLBO), db = umma_desc(bB + ks * 2 * kLBO);
+              const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+              asm volatile(
+                  "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                  "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(
+                      tmem + static_cast<uint32_t>(kMmaTileN * buf)),
+                  "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 16u)
+                  : "memory");
+            }
+            umma_commit_pair(&empty[s]);                              // stage reusable in both CTAs
+            if (it == d.npanel - 1) umma_commit_pair(&tmem_full[buf]);  // accumulators complete in both CTAs
+          }
+          __syncwarp();
+        }
       }
+      if (PROF && blockIdx.x < 2 && lane == 0)
+        printf("cta %d mma: stages %u total %lld wait_full %lld wait_tmem_empty %lld\n", blockIdx.x, g, clock64() - t_begin,
+               w_full, w_tempty);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
   } else if (warp == 5) {
@@ -387,73 +489,87 @@ __global__ void __launch_bounds__(kThreads, 1) triangles_mma_kernel(
       int pair = -1;
       uint32_t g = 0;
       PairDesc d;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      long long w_rempty = 0, t_begin = PROF ? clock64() : 0;
+      for (int t = cid; t < total_tiles; t += ncl) {
         int I0, J0;
         decode_tile(t, descs, pairs, pair, d, I0, J0);
-        const uint32_t rowsB = static_cast<uint32_t>(min(kMmaTileN, d.Npad - J0));
+        const int a0 = I0 + kCtaM * static_cast<int>(rank), b0 = J0 + kCtaNB * static_cast<int>(rank);
+        const uint32_t bytesA = a0 < d.Npad ? kRawABytes : 0u;  // Npad is a multiple of 128
+        uint32_t bytesB = static_cast<uint32_t>(max(0, min(kCtaNB, d.Npad - b0))) * 32u;
+        if (dbg & 16) bytesB = 0;                 // experiments: no B copy / a 16-byte B copy
+        if ((dbg & 32) && bytesB) bytesB = 16;
         const uint32_t* pp = panel + d.panel_off;
         for (int it = 0; it < d.npanel; ++it, ++g) {
           const uint32_t rs = g % kRawStages;
-          if (g >= kRawStages) mbar_wait(&raw_empty[rs], ((g / kRawStages) - 1) & 1u);
+          if (g >= kRawStages) SACCOT_TIMED_WAIT(w_rempty, mbar_wait_wd(&raw_empty[rs], ((g / kRawStages) - 1) & 1u, 4, g));
           unsigned char* dst = raw_base + rs * kRawBytes;
           const uint32_t* src = pp + static_cast<size_t>(it) * d.Npad * 8;
-          mbar_arrive_expect_tx(&raw_full[rs], kRawABytes + rowsB * 32u);
-          bulk_g2s(dst, src + static_cast<size_t>(I0) * 8, kRawABytes, &raw_full[rs]);
-          bulk_g2s(dst + kRawABytes, src + static_cast<size_t>(J0) * 8, rowsB * 32u, &raw_full[rs]);
+          mbar_arrive_expect_tx(&raw_full[rs], bytesA + bytesB);
+          if (bytesA) bulk_g2s(dst, src + static_cast<size_t>(a0) * 8, bytesA, &raw_full[rs]);
+          if (bytesB) bulk_g2s(dst + kRawABytes, src + static_cast<size_t>(b0) * 8, bytesB, &raw_full[rs]);
         }
       }
+      if (PROF && blockIdx.x < 2)
+        printf("cta %d bulk-copy issuer: stages %u total %lld wait_raw_empty %lld\n", blockIdx.x, g, clock64() - t_begin, w_rempty);
     }
-  } else {
+  } else if (warp < 6 + kProducerWarps) {
     // ================================== expansion warps ==================================
+    // Stage g is expanded by group g % kGroupsP (two warps, eight 16-row tasks each): the fixed cost of a
+    // stage hand-over (two barrier waits, proxy fence, two arrivals; ~350 cycles measured) is paid once
+    // per kGroupsP stages by every warp instead of once per stage.
     const int pw = warp - 6;
+    const int grp = pw >> 1, half = pw & 1;
     const int r8 = lane & 7, rg2 = (lane >> 3) & 1, q = lane >> 4;
-    uint32_t rawoff[kMaxT], dstoff[kMaxT];
-    int brow[kMaxT];  // row inside the B block (or -1 for A rows / unused slots)
-#pragma unroll
-    for (int k = 0; k < kMaxT; ++k) {
-      const int task = pw + kProducerWarps * k;
-      const int r = 16 * task + 8 * rg2 + r8;
-      rawoff[k] = static_cast<uint32_t>(r * 32 + q * 16);
-      dstoff[k] = static_cast<uint32_t>((2 * task + rg2) * kSBO + 4 * q * kLBO + r8 * 16);
-      brow[k] = (task < kTasks && r >= kMmaTileM) ? r - kMmaTileM : -1;
-    }
-    int pair = -1;
     uint32_t g = 0;
+    int pair = -1;
     PairDesc d;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    long long w_rfull = 0, w_empty = 0, t_begin = PROF ? clock64() : 0;
+    for (int t = cid; t < total_tiles; t += ncl) {
       int I0, J0;
       decode_tile(t, descs, pairs, pair, d, I0, J0);
-      bool valid[kMaxT];
-#pragma unroll
-      for (int k = 0; k < kMaxT; ++k) valid[k] = (pw + kProducerWarps * k < kTasks) && (brow[k] < 0 || J0 + brow[k] < d.Npad);
+      const int a0 = I0 + kCtaM * static_cast<int>(rank), b0 = J0 + kCtaNB * static_cast<int>(rank);
+      // rows past the end of the pair were not copied: they expand to zeros
+      const int rowsA = a0 < d.Npad ? kCtaM : 0, rowsB = max(0, min(kCtaNB, d.Npad - b0));
       for (int it = 0; it < d.npanel; ++it, ++g) {
+        if (static_cast<int>(g % kGroupsP) != grp) continue;
         const uint32_t rs = g % kRawStages, s = g % kStages;
-        mbar_wait(&raw_full[rs], (g / kRawStages) & 1u);
+        SACCOT_TIMED_WAIT(w_rfull, mbar_wait_wd(&raw_full[rs], (g / kRawStages) & 1u, 5, g));
         const unsigned char* raw = raw_base + rs * kRawBytes;
-        uint4 w[kMaxT];
+        uint4 w[kTasksPerWarp];
 #pragma unroll
-        for (int k = 0; k < kMaxT; ++k)
-          w[k] = valid[k] ? *reinterpret_cast<const uint4*>(raw + rawoff[k]) : make_uint4(0u, 0u, 0u, 0u);
-        if (g >= kStages) mbar_wait(&empty[s], ((g / kStages) - 1) & 1u);
+        for (int k = 0; k < kTasksPerWarp; ++k) {
+          const int gr = 2 * (half + 2 * k) + rg2;  // 8-row group of this lane
+          const int r = 8 * gr + r8;
+          const bool ok = gr < kGroups && (r < kCtaM ? r < rowsA : r - kCtaM < rowsB);
+          w[k] = ok ? *reinterpret_cast<const uint4*>(raw + r * 32 + q * 16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (g >= kStages) SACCOT_TIMED_WAIT(w_empty, mbar_wait_wd(&empty[s], ((g / kStages) - 1) & 1u, 6, g));
         unsigned char* st = stage_base + s * kStageBytes;
 #pragma unroll
-        for (int k = 0; k < kMaxT; ++k)
-          if (pw + kProducerWarps * k < kTasks && !(dbg & 4)) expand_quad(w[k], st + dstoff[k]);
-        // generic-proxy writes -> visible to the tensor core (async proxy), then one arrival per warp
+        for (int k = 0; k < kTasksPerWarp; ++k) {
+          const int gr = 2 * (half + 2 * k) + rg2;
+          if (gr < kGroups && !(dbg & 4)) expand_quad(w[k], st + gr * kSBO + 4 * q * kLBO + r8 * 16);
+        }
+        // generic-proxy writes -> visible to the tensor cores (async proxy), then one arrival per warp on the
+        // leader's barrier: its MMAs read this CTA's stage too
         if (!(dbg & 2)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&full[s]);
+          mbar_arrive_cluster(&full[s], 0u);
           mbar_arrive(&raw_empty[rs]);
         }
       }
     }
+    if (PROF && blockIdx.x < 2 && lane == 0 && (pw == 0 || pw == kProducerWarps - 1))
+      printf("cta %d producer %d: stages %u total %lld wait_raw_full %lld wait_empty %lld\n", blockIdx.x, pw, g,
+             clock64() - t_begin, w_rfull, w_empty);
   }
 
+  // no CTA of the pair may exit (or free its TMEM) while the other can still touch its memory
   asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
+  cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;");
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -602,7 +718,9 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
 }
 
 int triangles_mma_configure() {
-  cudaError_t e = cudaFuncSetAttribute(triangles_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(triangles_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(triangles_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tri_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(theta_smem_bytes(65536)));
@@ -616,10 +734,15 @@ int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs,
   tri_theta_kernel<<<pairs, 1024, theta_smem_bytes(max_npad), lc.stream>>>(d_desc, d_adj, d_theta, Ke, prune, max_npad);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -static_cast<int>(e);
-  const int grid = std::min(total_tiles, lc.sm_count);
-  if (grid > 0)
-    triangles_mma_kernel<<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, pairs, total_tiles, d_adj, d_panel, d_state,
-                                                                   d_chunk, d_keys, d_theta, d_hist, d_t2, dbg);
+  const int grid = 2 * std::min(total_tiles, lc.sm_count / 2);  // CTA pairs
+  if (grid > 0) {
+    if (dbg & 64)
+      triangles_mma_kernel<true><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, pairs, total_tiles, d_adj, d_panel,
+                                                                           d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, dbg);
+    else
+      triangles_mma_kernel<false><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, pairs, total_tiles, d_adj, d_panel,
+                                                                            d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, dbg);
+  }
   e = cudaGetLastError();
   return e == cudaSuccess ? 2 : -static_cast<int>(e);
 }
