@@ -43,7 +43,7 @@ from sac_cot_b200.api import Registrar, load_library  # noqa: E402
 WORKLOAD = "cfg2_3dmatch_256x5000"   # BASELINE.json configs[1]; --workload selects another config for study
 METRIC = "registrations/sec at N=5000 corr, 5% inliers"
 UNIT = "registrations/s"
-STAGES = ("pack", "graph", "scan", "triangles", "select", "apex", "kabsch", "score", "finalize")
+STAGES = ("pack", "graph", "scan", "theta", "triangles", "select", "apex", "kabsch", "score", "finalize")
 
 
 def ratio_label(cfg):
@@ -174,7 +174,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU per step (default: the config's 256)")
     ap.add_argument("--chunk-pairs", type=int, default=0, help="library knob chunk_pairs (0 = auto)")
     ap.add_argument("--lanes", type=int, default=0, help="library knob lanes (0 = library default)")
-    ap.add_argument("--triangle-path", type=int, default=-1, help="library knob triangle_path (0 POPC, 1 tensor core)")
+    ap.add_argument("--triangle-path", type=int, default=-1,
+                    help="library knob triangle_path (0 POPC, 1 tensor core, 2 by edge density = library default)")
     ap.add_argument("--triangle-dbg", type=int, default=0, help="experiments only (library knob triangle_dbg)")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(synth.CONFIGS),
                     help="synthetic config (default: the headline config, BASELINE.json configs[1])")
@@ -337,48 +338,84 @@ def main():
 
     # ---- roofline of the dominant kernel (triangle counting), from the live stage timers ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak_gbs, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    path_used = reg.get("triangle_path_used")  # which S2 kernels the timed steps ran
     reg.set("keep_debug", 1)
     small = min(pairs, 8)
+    reg.set("triangle_path", 0)  # every edge key is kept on this path: exact edge count per pair
     reg.register_packed(src[: small * N], dst[: small * N], offsets[: small + 1])
     E_mean = float(np.mean([int(reg.debug(b, _abi.DBG_NUM_EDGES)[0]) for b in range(small)]))
     reg.set("keep_debug", 0)
     npad = (N + 127) // 128 * 128
     stride = npad // 32
-    # algorithmic bytes per pair of S2: read A once, write one 8-byte key per edge,
-    # read-modify-write the per-node sums and the histogram once
-    tri_bytes_pair = npad * stride * 4 + E_mean * 8 + npad * 8 * 2 + 4096 * 4 * 2
     tri_calls = max(1, stage_calls["triangles"])
-    tri_us = stage_us["triangles"] / tri_calls                 # average launch duration
+    tri_us = stage_us["triangles"] / tri_calls                 # average launch duration (CUDA events, live)
     pairs_per_launch = pairs * args.steps / tri_calls
-    achieved_gbs = tri_bytes_pair * pairs_per_launch / (tri_us * 1e-6) / 1e9
-    wordops = E_mean * stride * pairs_per_launch               # AND+POPC on 32-bit words
     sm_mhz = clocks.get("sm_mhz") or 1965.0
-    popc_peak = 16 * 148 * sm_mhz * 1e6                        # nominal 16 POPC/clk/SM
-    # DRAM traffic of the same kernel from the committed `ncu --set full` capture, scaled per launch
-    traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath) and WORKLOAD == "cfg2_3dmatch_256x5000":
-        tj = json.load(open(tpath))["triangles_block_kernel"]
-        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pairs_in_launch"] * pairs_per_launch
-    roofline = {
-        "kernel": "triangles_block_kernel<5,256,1024> (S2, POPC bitset)", "bound": "hbm", "achieved": achieved_gbs,
-        "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs, "traffic": traffic,
-        "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/ncu_traffic.json)",
-        "algorithmic_bytes_per_launch": tri_bytes_pair * pairs_per_launch, "peak_source": peak_src,
-        "launch_us": tri_us, "pairs_per_launch": pairs_per_launch, "algorithmic_bytes_per_pair": tri_bytes_pair,
-        "note": "S2 is bound by POPC/ALU issue, not HBM (arithmetic intensity ~ 40 word-ops/B): the HBM "
-                "fraction is small by construction; the issue-side figure is in `issue`",
-        "issue": {"wordops_per_s": wordops / (tri_us * 1e-6), "nominal_popc_peak_per_s": popc_peak,
-                  "frac": wordops / (tri_us * 1e-6) / popc_peak, "edges_per_pair": E_mean, "words_per_row": stride},
+    tj_all = json.load(open(tpath)) if os.path.exists(tpath) and WORKLOAD == "cfg2_3dmatch_256x5000" else {}
+    common = {
+        "launch_us": tri_us, "pairs_per_launch": pairs_per_launch,
         "stage_share": {s: stage_us[s] / max(1, sum(stage_us.values())) for s in STAGES},
         "stage_us_per_step": {s: stage_us[s] / args.steps for s in STAGES},
         "timing": f"CUDA events around every stage over {args.steps} steps on one lane "
                   f"({serial_ms_per_step:.2f} ms/step without chunk overlap; the headline uses {lanes_default} lanes)",
     }
+    if path_used == 1:
+        # S2 on the tensor cores: T = (A A^T) o A, upper triangle only (symmetry credited): N(N-1)/2 node pairs
+        # x N MACs x 2 flop
+        flop_pair = float(N) * (N - 1) * N
+        tiles_pair = sum(min((N + 255) // 256, (240 * jq + 238) // 256 + 1) for jq in range((N + 239) // 240))
+        kpad = (npad + 511) // 512 * 512
+        exec_flop_pair = tiles_pair * 256.0 * 240.0 * kpad * 2.0
+        achieved = flop_pair * pairs_per_launch / (tri_us * 1e-6) / 1e12
+        peak = peaks.get("bf16_tflops_sustained") or 2250.0
+        peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: dense bf16 cuBLAS inside a long step)"
+                    if peaks else "fallback (B200_PROFILING.md nominal dense bf16)")
+        fp4_peak = 16328.0 * 148 * sm_mhz * 1e6 * 2 / 1e12   # measured: profiles/umma_contend_r01.txt, MAC/clk/SM
+        traffic = None
+        if "triangles_mma_kernel" in tj_all:
+            tj = tj_all["triangles_mma_kernel"]
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pairs_in_launch"] * pairs_per_launch
+        roofline = {
+            "kernel": "triangles_mma_kernel (S2, tcgen05 kind::mxf4 cta_group::2, operands expanded on chip)",
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": traffic,
+            "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/ncu_traffic.json)",
+            "algorithmic_flop_per_pair": flop_pair, "executed_flop_per_pair": exec_flop_pair,
+            "algorithmic_flop_per_launch": flop_pair * pairs_per_launch, "peak_source": peak_src,
+            "note": "the kernel runs 4-bit (e2m1) MMAs, whose hardware rate is 4x the bf16 rate the contract's peak "
+                    "refers to, so frac can exceed 1; `fp4` relates the same algorithmic flops to the mxf4 MMA rate "
+                    "measured on this GPU with the same operand layout (profiles/umma_contend_r01.txt)",
+            "fp4": {"peak": fp4_peak, "frac": achieved / fp4_peak,
+                    "executed_frac": exec_flop_pair * pairs_per_launch / (tri_us * 1e-6) / 1e12 / fp4_peak},
+            "edges_per_pair": E_mean, **common,
+        }
+    else:
+        peak_gbs = peaks.get("hbm_gbs") or 6650.0
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)"
+        # algorithmic bytes per pair of S2: read A once, write one 8-byte key per edge,
+        # read-modify-write the per-node sums and the histogram once
+        tri_bytes_pair = npad * stride * 4 + E_mean * 8 + npad * 8 * 2 + 4096 * 4 * 2
+        achieved_gbs = tri_bytes_pair * pairs_per_launch / (tri_us * 1e-6) / 1e9
+        wordops = E_mean * stride * pairs_per_launch               # AND+POPC on 32-bit words
+        popc_peak = 16 * 148 * sm_mhz * 1e6                        # nominal 16 POPC/clk/SM
+        traffic = None
+        if "triangles_block_kernel" in tj_all:
+            tj = tj_all["triangles_block_kernel"]
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pairs_in_launch"] * pairs_per_launch
+        roofline = {
+            "kernel": "triangles_block_kernel (S2, POPC bitset)", "bound": "hbm", "achieved": achieved_gbs,
+            "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs, "traffic": traffic,
+            "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/ncu_traffic.json)",
+            "algorithmic_bytes_per_launch": tri_bytes_pair * pairs_per_launch, "peak_source": peak_src,
+            "algorithmic_bytes_per_pair": tri_bytes_pair,
+            "note": "S2 is bound by POPC/ALU issue, not HBM (arithmetic intensity ~ 40 word-ops/B): the HBM "
+                    "fraction is small by construction; the issue-side figure is in `issue`",
+            "issue": {"wordops_per_s": wordops / (tri_us * 1e-6), "nominal_popc_peak_per_s": popc_peak,
+                      "frac": wordops / (tri_us * 1e-6) / popc_peak, "edges_per_pair": E_mean, "words_per_row": stride},
+            **common,
+        }
 
     # ---- CPU baseline: the from-paper oracle on this box's host cores (rank 0, N = 1 only) ----
     cpu_baseline = None
@@ -406,6 +443,7 @@ def main():
                 "pairs_per_gpu": pairs, "N": N, "K_e": int(reg.params.num_edges),
                 "apex_per_edge": int(reg.params.apex_per_edge), "hypotheses_per_pair": K,
                 "parallelism": f"{world} x independent batches, no collective",
+                "triangle_path": "tensor cores (tcgen05 mxf4)" if path_used == 1 else "POPC bitset",
                 "l2": "512 MB flush write between timed steps; per-step workspace (~3 GB) also exceeds the 126 MB L2",
             },
             "hypotheses_per_sec": value * K,

@@ -97,13 +97,15 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *   set: "keep_debug" (0/1: retain per-pair intermediates for sac_cot_debug_get; forces
  *        chunk = whole batch), "chunk_pairs" (pairs per kernel wave, 0 = auto), "lanes" (1..4
  *        internal streams the chunks of a batch are dealt to, default 2; GPU only),
- *        "triangle_path" (0 = POPC bitset, 1 = tensor-core dense; GPU only),
+ *        "triangle_path" (0 = POPC bitset kernels, 1 = tensor-core dense kernel, 2 = chosen per chunk
+ *        from the measured edge density (default); GPU only),
  *        "triangle_prune" (tensor-core path, default 1: keep only edge keys whose count reaches
  *        a per-pair threshold proven to lie at or below the K_e-th largest count; results are
  *        unchanged, SAC_COT_DBG_EDGE_KEYS / _HIST then cover the kept edges only; GPU only),
  *        "stage_timing" (0/1: bracket every pipeline stage with CUDA events on the ctx
  *        stream; setting it also clears the accumulated times; GPU only)
- *   get: "launches" (kernels launched since ctx creation), "workspace_bytes",
+ *   get: "triangle_path_used" (0/1: which S2 kernels the latest chunk ran; synchronises; GPU only),
+ *        "launches" (kernels launched since ctx creation), "workspace_bytes",
  *        "device", "sm_count", "retries" (workspace-growth re-runs),
  *        "last_status" (deferred status of the latest SAC_COT_LOC_DEVICE call; synchronises),
  *        "stage_us_<s>" / "stage_calls_<s>" with <s> in pack, graph, scan, triangles, select,

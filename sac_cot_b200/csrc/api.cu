@@ -56,6 +56,7 @@ struct Layout {
   uint32_t* adj = nullptr;
   uint32_t* panel = nullptr;   // K-panel copy of the adjacency (tensor-core triangle path only)
   uint32_t* theta = nullptr;   // per-pair pruning threshold (tensor-core triangle path only)
+  uint2* tile_tab = nullptr;   // tensor-core path: (pair, row block << 16 | column block) per tile
   int total_tiles = 0;         // tensor-core path: tiles of the whole chunk
   unsigned long long* sel = nullptr;
   unsigned long long* tie = nullptr;
@@ -86,8 +87,8 @@ size_t pair_bytes_estimate(int N, int K, int Ke, bool tensor_path) {
 }
 
 // Optional per-stage timing with CUDA events on the ctx stream ("stage_timing" knob).
-enum Stage { ST_PACK = 0, ST_GRAPH, ST_SCAN, ST_TRIANGLES, ST_SELECT, ST_APEX, ST_KABSCH, ST_SCORE, ST_FINALIZE, ST_COUNT };
-const char* const kStageNames[ST_COUNT] = {"pack", "graph", "scan", "triangles", "select", "apex", "kabsch", "score", "finalize"};
+enum Stage { ST_PACK = 0, ST_GRAPH, ST_SCAN, ST_THETA, ST_TRIANGLES, ST_SELECT, ST_APEX, ST_KABSCH, ST_SCORE, ST_FINALIZE, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"pack", "graph", "scan", "theta", "triangles", "select", "apex", "kabsch", "score", "finalize"};
 
 struct StageTimer {
   bool enabled = false;
@@ -142,6 +143,7 @@ struct Lane {
   unsigned long long key_cap = 0;
   Layout lay;                     // layout of the chunk most recently enqueued on this lane
   std::vector<PairDesc> descs;
+  std::vector<uint2> tile_tab;    // host copy of the tensor-core path's tile list
 };
 constexpr int kMaxLanes = 4;
 
@@ -153,7 +155,7 @@ struct sac_cot_ctx {
   bool keep_debug = false;
   int chunk_pairs = 0;
   int n_lanes = 2;
-  int tri_path = 0;   // 0 = POPC bitset kernels, 1 = tensor-core (tcgen05 mxf4) kernel
+  int tri_path = 2;   // 0 = POPC bitset kernels, 1 = tensor-core (tcgen05 mxf4) kernel, 2 = by edge density per chunk
   int tri_dbg = 0;    // experiments only (bit 0: skip the tensor-core kernel's epilogue work; results are void)
   int tri_prune = 1;  // tensor-core path: drop edges below the per-pair threshold (exact for the selection)
   int64_t launches = 0;
@@ -195,7 +197,7 @@ int check_params(const sac_cot_params* p) {
 
 // Builds the descriptors and the arena layout for pairs with the given sizes.
 void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_input_copy, bool tensor_path,
-          std::vector<PairDesc>& descs, Layout& L) {
+          std::vector<PairDesc>& descs, std::vector<uint2>& tile_tab, Layout& L) {
   L = Layout();
   L.pairs = pairs;
   L.Ke = prm.num_edges;
@@ -204,6 +206,7 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   descs.resize(pairs);
   size_t pt = 0, soa = 0, adj = 0, node = 0, mask = 0, panel = 0;
   int tiles = 0;
+  tile_tab.clear();
   for (int b = 0; b < pairs; ++b) {
     PairDesc& d = descs[b];
     d.N = Ns[b];
@@ -220,7 +223,11 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
     d.tile_base = tiles;
     if (tensor_path) {
       panel += static_cast<size_t>(d.npanel) * d.Npad * 8;
-      tiles += mma_tiles_of_pair(d.N);
+      const int nJ = (d.N + kMmaTileN - 1) / kMmaTileN;
+      for (int jq = 0; jq < nJ; ++jq)
+        for (int ib = 0, c = mma_tiles_of_jblock(d.N, jq); ib < c; ++ib)
+          tile_tab.push_back(make_uint2(static_cast<unsigned>(b), (static_cast<unsigned>(ib) << 16) | static_cast<unsigned>(jq)));
+      tiles = static_cast<int>(tile_tab.size());
     }
     pt += d.N;
     soa += static_cast<size_t>(6) * d.Npad;
@@ -258,6 +265,7 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_adj = take(sizeof(uint32_t) * adj);
   const size_t o_panel = tensor_path ? take(sizeof(uint32_t) * panel) : 0;
   const size_t o_theta = tensor_path ? take(sizeof(uint32_t) * pairs) : 0;
+  const size_t o_tiles = tensor_path ? take(sizeof(uint2) * std::max(1, tiles)) : 0;
   const size_t o_sel = take(sizeof(unsigned long long) * L.Ke * pairs);
   const size_t o_tie = take(sizeof(unsigned long long) * kTieCap * pairs);
   const size_t o_top = take(sizeof(unsigned long long) * L.Ke * pairs);
@@ -284,6 +292,7 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.adj = reinterpret_cast<uint32_t*>(o_adj);
   L.panel = tensor_path ? reinterpret_cast<uint32_t*>(o_panel) : nullptr;
   L.theta = tensor_path ? reinterpret_cast<uint32_t*>(o_theta) : nullptr;
+  L.tile_tab = tensor_path ? reinterpret_cast<uint2*>(o_tiles) : nullptr;
   L.sel = reinterpret_cast<unsigned long long*>(o_sel);
   L.tie = reinterpret_cast<unsigned long long*>(o_tie);
   L.top = reinterpret_cast<unsigned long long*>(o_top);
@@ -316,6 +325,7 @@ void bind(Layout& L, unsigned char* base, bool has_input, bool tensor_path) {
   L.adj = rebase(L.adj, base);
   L.panel = rebase(L.panel, base, tensor_path);
   L.theta = rebase(L.theta, base, tensor_path);
+  L.tile_tab = rebase(L.tile_tab, base, tensor_path);
   L.sel = rebase(L.sel, base);
   L.tie = rebase(L.tie, base);
   L.top = rebase(L.top, base);
@@ -419,16 +429,21 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   mark(-1);
   KL_TRY(launch_pack_soa(lc, L.desc, L.pairs, L.max_npad, d_src, d_dst, L.soa));
   mark(ST_PACK);
-  const bool tensor = L.panel != nullptr;  // decided when the chunk was planned
+  // planned with the tensor-core buffers: mode 1 (forced) or 2 (the key scan decides from the edge density);
+  // both triangle kernels are then enqueued and the one not chosen returns at once
+  const int tri_mode = L.panel != nullptr ? ctx->tri_path : 0;
   KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.panel, L.ucount, L.unit_pitch, prm.tau_compat));
   mark(ST_GRAPH);
-  KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world, tensor ? 1 : 0));
-  KL_TRY(launch_key_scan(lc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap));
+  KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world));
+  KL_TRY(launch_key_scan(lc, L.desc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap, tri_mode));
   mark(ST_SCAN);
-  if (tensor)
-    KL_TRY(launch_triangles_mma(lc, L.desc, L.pairs, L.total_tiles, L.max_npad, L.adj, L.panel, L.state, L.chunk, ln.keys,
-                                L.theta, L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg));
-  else
+  if (tri_mode != 0) {
+    KL_TRY(launch_tri_theta(lc, L.desc, L.pairs, L.max_npad, L.adj, L.chunk, L.theta, L.Ke, ctx->tri_prune));
+    mark(ST_THETA);
+    KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, L.adj, L.panel, L.state, L.chunk, ln.keys, L.theta,
+                                L.hist, L.t2, ctx->tri_dbg));
+  }
+  if (tri_mode != 1)
     KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ln.keys, L.ubase,
                             L.unit_pitch, L.hist, L.t2, rank, world));
   mark(ST_TRIANGLES);
@@ -471,13 +486,15 @@ int enqueue_chunk(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst
   const int pairs = b1 - b0;
   std::vector<int32_t> Ns(pairs);
   for (int b = 0; b < pairs; ++b) Ns[b] = static_cast<int32_t>(offsets[b0 + b + 1] - offsets[b0 + b]);
-  const bool tensor = ctx->tri_path == 1;
-  plan(Ns.data(), pairs, prm, host, tensor, ln.descs, ln.lay);
+  const bool tensor = ctx->tri_path != 0;
+  plan(Ns.data(), pairs, prm, host, tensor, ln.descs, ln.tile_tab, ln.lay);
   if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
   if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
   bind(ln.lay, ln.arena, host, tensor);
   Layout& L = ln.lay;
   CU_TRY(cudaMemcpyAsync(L.desc, ln.descs.data(), sizeof(PairDesc) * pairs, cudaMemcpyHostToDevice, ln.stream));
+  if (tensor && !ln.tile_tab.empty())
+    CU_TRY(cudaMemcpyAsync(L.tile_tab, ln.tile_tab.data(), sizeof(uint2) * ln.tile_tab.size(), cudaMemcpyHostToDevice, ln.stream));
   const int64_t p0 = offsets[b0];
   if (host) {
     CU_TRY(cudaMemcpyAsync(L.in_src, src + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ln.stream));
@@ -532,7 +549,7 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
     } else {
       size_t total = 0;
       for (int b = 0; b < B; ++b)
-        total += pair_bytes_estimate(static_cast<int>(offsets[b + 1] - offsets[b]), K, params->num_edges, ctx->tri_path == 1);
+        total += pair_bytes_estimate(static_cast<int>(offsets[b + 1] - offsets[b]), K, params->num_edges, ctx->tri_path != 0);
       const size_t budget = static_cast<size_t>(3) << 30;  // ~3 GB of workspace per chunk (larger chunks measured faster)
       int nchunks = static_cast<int>((total + budget - 1) / budget);
       if (nchunks < lanes && B >= 2 * lanes) nchunks = lanes;  // give every lane something to overlap
@@ -691,7 +708,7 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     return SAC_COT_OK;
   }
   if (!std::strcmp(name, "triangle_path")) {
-    if (value != 0 && value != 1) return SAC_COT_E_UNSUPPORTED;
+    if (value < 0 || value > 2) return SAC_COT_E_UNSUPPORTED;
     ctx->tri_path = static_cast<int>(value);
     return SAC_COT_OK;
   }
@@ -728,6 +745,17 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
   if (!std::strcmp(name, "lanes")) { *value = ctx->n_lanes; return SAC_COT_OK; }
   if (!std::strcmp(name, "triangle_path")) { *value = ctx->tri_path; return SAC_COT_OK; }
   if (!std::strcmp(name, "triangle_prune")) { *value = ctx->tri_prune; return SAC_COT_OK; }
+  if (!std::strcmp(name, "triangle_path_used")) {
+    // which S2 kernels the most recent chunk on lane 0 ran (0 = POPC, 1 = tensor core); synchronises
+    Lane& ln = ctx->lanes[0];
+    if (!ln.arena || !ln.lay.chunk || ln.lay.pairs == 0) return SAC_COT_E_WHICH;
+    cudaSetDevice(ctx->device);
+    if (int rc = sync_all(ctx)) return rc;
+    ChunkDev c;
+    CU_TRY(cudaMemcpy(&c, ln.lay.chunk, sizeof(c), cudaMemcpyDeviceToHost));
+    *value = c.use_tensor;
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "threads")) { *value = 0; return SAC_COT_OK; }
   if (!std::strncmp(name, "stage_us_", 9) || !std::strncmp(name, "stage_calls_", 12)) {
     const bool us = name[6] == 'u';
@@ -818,7 +846,7 @@ int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
     if (int rc = ensure_chunk_headers(ctx, 1)) return rc;
     ChunkDev* h_chunk = ctx->h_chunks[0];
     for (int attempt = 0; attempt < 3; ++attempt) {
-      plan(&N, 1, *params, true, false, ln.descs, ln.lay);  // sharded phases use the POPC kernels
+      plan(&N, 1, *params, true, false, ln.descs, ln.tile_tab, ln.lay);  // sharded phases use the POPC kernels
       if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
       // a rank evaluates ~1/world of the edges: the unit scan counts only the owned units, so the
       // pool demand is ~E/world; the initial guess covers a whole pair at 12.5 % density

@@ -46,7 +46,7 @@ struct PairDev {
 struct ChunkDev {
   unsigned long long total_edges;  // sum of E over the chunk (key pool demand)
   uint32_t overflow;               // 1: key pool too small; downstream kernels do nothing
-  uint32_t pad_;
+  uint32_t use_tensor;             // 1: S2 runs on the tensor cores for this chunk, 0: POPC bitset kernels
 };
 
 // Survives across calls (never zeroed by the pipeline): lets device-location calls report a
@@ -137,10 +137,14 @@ int launch_pack_soa(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int 
 int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, const float* d_soa,
                  uint32_t* d_adj, uint32_t* d_panel, uint32_t* d_ucount, int unit_pitch, float tau);
 int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state,
-                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world,
-                     int keys_appended);
-int launch_key_scan(const LaunchCtx& lc, int pairs, PairDev* d_state, ChunkDev* d_chunk, StickyDev* d_sticky,
-                    unsigned long long key_cap);
+                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world);
+// tri_mode: 0 = POPC kernels, 1 = tensor-core kernel, 2 = decided here from the chunk's edge density
+int launch_key_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state, ChunkDev* d_chunk,
+                    StickyDev* d_sticky, unsigned long long key_cap, int tri_mode);
+// density (edges per node pair) from which the tensor-core triangle kernel beats the POPC kernels, and the
+// smallest pair it is worth starting for (measured on B200)
+constexpr float kTensorMinDensity = 0.05f;
+constexpr int kTensorMinN = 1024;
 
 // kernels_triangles.cu — S2 triangle counts (POPC bitset path)
 int launch_triangles(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, int max_stride,
@@ -164,10 +168,12 @@ __host__ __device__ inline int mma_tiles_of_pair(int N) {
   for (int jq = 0; jq < nJ; ++jq) t += mma_tiles_of_jblock(N, jq);
   return t;
 }
-int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int total_tiles, int max_npad,
+int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
+                     const ChunkDev* d_chunk, uint32_t* d_theta, int Ke, int prune);
+int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_tiles, int total_tiles,
                          const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
-                         unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
-                         int Ke, int prune, int dbg);
+                         unsigned long long* d_keys, const uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
+                         int dbg);
 int triangles_mma_configure();
 
 // kernels_select.cu — S3 edge ranking + apex selection

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const PairDesc* __restr
                                                          PairDev* __restrict__ state,
                                                          const uint32_t* __restrict__ ucount,
                                                          uint32_t* __restrict__ ubase, int unit_pitch, int rank,
-                                                         int world, int keys_appended) {
+                                                         int world) {
   const int pair = blockIdx.x;
   const unsigned int U = unit_count(static_cast<unsigned int>(descs[pair].nblk));
   const uint32_t* cnt = ucount + static_cast<size_t>(pair) * unit_pitch;
@@ -338,17 +338,13 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const PairDesc* __restr
   }
   if (t == 0) {
     state[pair].num_edges = carry;
-    // POPC path: every edge gets a key at an exact offset.  Tensor-core path: the kernel appends the
-    // keys that pass its pruning threshold and counts them here.
-    state[pair].key_count = keys_appended ? 0ull : carry;
+    state[pair].key_count = carry;  // the key scan zeroes it again if the tensor-core kernel is chosen
   }
 }
 
 int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state,
-                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world,
-                     int keys_appended) {
-  unit_scan_kernel<<<pairs, 1024, 0, lc.stream>>>(d_desc, d_state, d_ucount, d_ubase, unit_pitch, rank, world,
-                                                  keys_appended);
+                     const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world) {
+  unit_scan_kernel<<<pairs, 1024, 0, lc.stream>>>(d_desc, d_state, d_ucount, d_ubase, unit_pitch, rank, world);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }
@@ -358,14 +354,33 @@ int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, Pai
 // too small the overflow flag is raised; every later kernel of the chunk then returns at once
 // and the host grows the pool and re-runs the chunk.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) key_scan_kernel(int pairs, PairDev* __restrict__ state,
-                                                        ChunkDev* __restrict__ chunk, StickyDev* __restrict__ sticky,
-                                                        unsigned long long key_cap) {
+__global__ void __launch_bounds__(1024) key_scan_kernel(const PairDesc* __restrict__ descs, int pairs,
+                                                        PairDev* __restrict__ state, ChunkDev* __restrict__ chunk,
+                                                        StickyDev* __restrict__ sticky, unsigned long long key_cap,
+                                                        int tri_mode) {
   __shared__ unsigned long long part[1024];
   __shared__ unsigned long long carry;
+  __shared__ unsigned long long node_pairs;  // sum of N (N - 1) / 2 over the chunk
+  __shared__ int max_n;
+  __shared__ uint32_t s_tensor;
   const int t = threadIdx.x;
-  if (t == 0) carry = 0;
+  if (t == 0) {
+    carry = 0;
+    node_pairs = 0;
+    max_n = 0;
+  }
   __syncthreads();
+  if (tri_mode == 2) {
+    unsigned long long np = 0;
+    int mn = 0;
+    for (int b = t; b < pairs; b += 1024) {
+      const unsigned long long n = static_cast<unsigned long long>(descs[b].N);
+      np += n * (n - 1) / 2;
+      mn = max(mn, descs[b].N);
+    }
+    if (np) atomicAdd(&node_pairs, np);
+    if (mn) atomicMax(&max_n, mn);
+  }
   for (int b0 = 0; b0 < pairs; b0 += 1024) {
     const int b = b0 + t;
     const unsigned long long e = b < pairs ? state[b].num_edges : 0ull;
@@ -383,6 +398,12 @@ __global__ void __launch_bounds__(1024) key_scan_kernel(int pairs, PairDev* __re
     __syncthreads();
   }
   if (t == 0) {
+    // S2 path of the chunk: the dense tensor-core kernel costs ~N^3, the POPC kernels ~E N / 32
+    uint32_t tensor = tri_mode == 1 ? 1u : 0u;
+    if (tri_mode == 2)
+      tensor = (max_n >= kTensorMinN && static_cast<float>(carry) >= kTensorMinDensity * static_cast<float>(node_pairs)) ? 1u : 0u;
+    s_tensor = tensor;
+    chunk->use_tensor = tensor;
     chunk->total_edges = carry;
     chunk->overflow = carry > key_cap ? 1u : 0u;
     if (carry > key_cap) {
@@ -390,11 +411,15 @@ __global__ void __launch_bounds__(1024) key_scan_kernel(int pairs, PairDev* __re
       atomicAdd(&sticky->overflow_count, 1u);
     }
   }
+  __syncthreads();
+  // the tensor-core kernel appends only the keys that pass its pruning threshold and counts them itself
+  if (s_tensor)
+    for (int b = t; b < pairs; b += 1024) state[b].key_count = 0ull;
 }
 
-int launch_key_scan(const LaunchCtx& lc, int pairs, PairDev* d_state, ChunkDev* d_chunk, StickyDev* d_sticky,
-                    unsigned long long key_cap) {
-  key_scan_kernel<<<1, 1024, 0, lc.stream>>>(pairs, d_state, d_chunk, d_sticky, key_cap);
+int launch_key_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state, ChunkDev* d_chunk,
+                    StickyDev* d_sticky, unsigned long long key_cap, int tri_mode) {
+  key_scan_kernel<<<1, 1024, 0, lc.stream>>>(d_desc, pairs, d_state, d_chunk, d_sticky, key_cap, tri_mode);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
     const PairDesc* __restrict__ descs, const uint32_t* __restrict__ adj, const PairDev* __restrict__ state,
     const ChunkDev* __restrict__ chunk, unsigned long long* __restrict__ keys, const uint32_t* __restrict__ ubase,
     int unit_pitch, uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2, int rank, int world) {
-  if (chunk->overflow) return;
+  if (chunk->overflow || chunk->use_tensor) return;
   const int pair = blockIdx.y;
   const PairDesc d = descs[pair];
   constexpr int NB = JB / 128;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kTriThreads) triangles_chunked_kernel(
     const PairDesc* __restrict__ descs, const uint32_t* __restrict__ adj, const PairDev* __restrict__ state,
     const ChunkDev* __restrict__ chunk, unsigned long long* __restrict__ keys, const uint32_t* __restrict__ ubase,
     int unit_pitch, uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2, int rank, int world) {
-  if (chunk->overflow) return;
+  if (chunk->overflow || chunk->use_tensor) return;
   const int pair = blockIdx.y;
   const PairDesc d = descs[pair];
   const unsigned int unit = blockIdx.x;

@@ -37,11 +37,16 @@ namespace saccot {
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kEpiWarps = 8;                          // warps 0..7: TMEM lane quadrant = warp & 3, column half = warp >> 2
+constexpr int kMmaWarp = 8;
+constexpr int kTmaWarp = 9;
+constexpr int kProdWarp0 = 10;
+constexpr int kProducerWarps = 8;                     // warps 10..17
+constexpr int kThreads = 32 * (kProdWarp0 + kProducerWarps);  // 576
 constexpr int kCtaM = 128;                            // rows of the pair tile owned by one CTA (one TMEM lane each)
 constexpr int kCtaNB = kMmaTileN / 2;                 // 120 rows of the B operand staged by one CTA
 constexpr int kStageK = 256;                          // K elements (adjacency columns) per stage
-constexpr int kStages = 4;                            // expanded operand stages
+constexpr int kStages = 4;                            // expanded operand stages (handed over in pairs)
 constexpr int kRawStages = 8;                         // raw (bit) stages
 constexpr int kRows = kCtaM + kCtaNB;                 // 248 rows expanded per stage and CTA
 constexpr int kGroups = kRows / 8;                    // 31 groups of 8 rows
@@ -50,14 +55,13 @@ constexpr int kSBO = (kStageK / 2 / 16) * 128;        // next 8-row group: 8 cor
 constexpr int kStageBytes = kGroups * kSBO;           // 31744
 constexpr int kRawBytes = kRows * 32;                 // 7936
 constexpr int kRawABytes = kCtaM * 32;                // 4096
-constexpr int kProducerWarps = 8;                     // warps 6..13 (14 and 15 idle)
 constexpr int kGroupsP = kProducerWarps / 2;          // producer groups of two warps; group = stage % kGroupsP
+constexpr int kTasksPerWarp = 8;                      // 16 warp tasks (16 rows x 2 quads) per stage, the last one half
 // A group must meet every phase of the barriers it waits on in order (mbarrier waits only know the phase
 // parity: a waiter two phases early passes at once).  With the group count dividing both ring sizes, a
 // group always returns to the same slots.
 static_assert(kStages % kGroupsP == 0 && kRawStages % kGroupsP == 0, "producer groups must divide the ring sizes");
-constexpr int kTasksPerWarp = 8;                      // 16 warp tasks (16 rows x 2 quads) per stage, the last one half
-constexpr int kKeyBuf = 640;                          // staged keys per epilogue warp (flush above 128)
+constexpr int kKeyBuf = 128;                          // staged keys per epilogue warp
 constexpr uint32_t kSfCol = 480;                      // scale factors: TMEM columns [480, 512)
 constexpr uint32_t kSfWord = 0x807F807Fu;             // UE8M0 per K block of 32: {1.0, 2.0, 1.0, 2.0}
 
@@ -65,9 +69,10 @@ constexpr uint32_t kSfWord = 0x807F807Fu;             // UE8M0 per K block of 32
 constexpr int kOffRaw = kStages * kStageBytes;                    // 126976
 constexpr int kOffHist = kOffRaw + kRawStages * kRawBytes;        // +63488
 constexpr int kOffKeys = kOffHist + kHistBins * 4;                // +16384
-constexpr int kOffBars = kOffKeys + 4 * kKeyBuf * 8;              // +20480
-constexpr int kNumBars = 2 * kStages + 2 * kRawStages + 4;
-constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 32;
+constexpr int kOffBars = kOffKeys + kEpiWarps * kKeyBuf * 8;      // +8192
+// barriers: full2[2] empty2[2] raw_full[8] raw_empty2[4] tmem_full[2] tmem_empty[2]
+constexpr int kNumBars = 2 + 2 + kRawStages + kRawStages / 2 + 2 + 2;
+constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + kEpiWarps * 32;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -141,24 +146,28 @@ __device__ __forceinline__ void expand_quad(const uint4 w, unsigned char* dst) {
   *reinterpret_cast<uint4*>(dst + 3 * kLBO) = make_uint4(sx & m1, sy & m1, sz & m1, sw & m1);
 }
 
-// tile index -> (pair, I0, J0); `pair` is a cursor that only moves forward
-__device__ __forceinline__ void decode_tile(int t, const PairDesc* __restrict__ descs, int pairs, int& pair, PairDesc& d,
-                                            int& I0, int& J0) {
-  bool moved = pair < 0;
-  if (pair < 0) pair = 0;
-  while (pair + 1 < pairs && t >= descs[pair + 1].tile_base) {
-    ++pair;
-    moved = true;
+// The fields of a PairDesc a role needs (a full copy per role costs ~20 registers and spills the epilogue).
+struct PairLite {
+  int32_t N, Npad, stride, npanel;
+  int64_t adj_off, node_off, panel_off;
+};
+// tile t of the chunk: tiles[t] = (pair, row block << 16 | column block); d follows the pair
+__device__ __forceinline__ void fetch_tile(int t, const uint2* __restrict__ tiles, const PairDesc* __restrict__ descs,
+                                           int& pair, PairLite& d, int& I0, int& J0) {
+  const uint2 e = tiles[t];
+  if (static_cast<int>(e.x) != pair) {
+    pair = static_cast<int>(e.x);
+    const PairDesc* pd = descs + pair;
+    d.N = pd->N;
+    d.Npad = pd->Npad;
+    d.stride = pd->stride;
+    d.npanel = pd->npanel;
+    d.adj_off = pd->adj_off;
+    d.node_off = pd->node_off;
+    d.panel_off = pd->panel_off;
   }
-  if (moved) d = descs[pair];
-  int u = t - d.tile_base, jq = 0;
-  for (;; ++jq) {
-    const int cnt = mma_tiles_of_jblock(d.N, jq);
-    if (u < cnt) break;
-    u -= cnt;
-  }
-  I0 = u * kMmaTileM;
-  J0 = jq * kMmaTileN;
+  I0 = static_cast<int>(e.y >> 16) * kMmaTileM;
+  J0 = static_cast<int>(e.y & 0xFFFFu) * kMmaTileN;
 }
 
 #define SACCOT_TMEM_LD16(v, taddr)                                                                                   \
@@ -202,6 +211,83 @@ __device__ __forceinline__ float colsum16(float (&m)[16], int lane) {
   return m[0] + __shfl_xor_sync(0xffffffffu, m[0], 1);
 }
 
+// Per-warp state of the epilogue's rare path, kept in shared memory so that the out-of-line functions take
+// few arguments (every live register of the hot loop is spilled around a call).
+struct EpiCtx {
+  unsigned long long* keyp;       // the pair's key list
+  unsigned long long* kcount;     // the pair's key counter
+  float thf;                      // pruning threshold
+  uint32_t fill;                  // keys staged in the warp's buffer
+};
+
+// staged keys of one epilogue warp -> the pair's key list (one reservation, coalesced copy)
+__device__ __noinline__ void flush_keys(unsigned long long* kb, EpiCtx* ctx) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  const uint32_t fill = ctx->fill;
+  if (fill) {
+    unsigned long long* keyp = ctx->keyp;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(ctx->kcount, static_cast<unsigned long long>(fill));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t k = lane; k < fill; k += 32) keyp[base + k] = kb[k];
+    __syncwarp();
+    if (lane == 0) ctx->fill = 0u;
+  }
+  __syncwarp();
+}
+
+// Rare path of the epilogue: append the edges of one 32 x 16 chunk whose count reaches the threshold.  Out of
+// line (and re-reading its 16 TMEM columns) so that the hot loop stays small.  Few keys are staged in the
+// warp's shared-memory buffer; a dense chunk (no pruning, or no clique in the pair) goes straight to the
+// key list with one reservation for the whole chunk.  rowcol = row i << 16 | first column of the chunk.
+__device__ __noinline__ void emit_chunk(uint32_t taddr, uint32_t bits16, uint32_t rowcol, unsigned long long* kb,
+                                        EpiCtx* ctx, uint32_t* hist_s) {
+  const int lane = threadIdx.x & 31;
+  uint32_t v[16];
+  SACCOT_TMEM_LD16(v, taddr);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  const float thf = ctx->thf;
+  uint32_t cand = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if ((bits16 & (1u << k)) && __uint_as_float(v[k]) >= thf) cand |= 1u << k;
+  const int nc = __popc(cand);
+  int incl = nc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  unsigned long long* dst;
+  uint32_t pos = static_cast<uint32_t>(incl - nc);
+  if (total > kKeyBuf / 2) {
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(ctx->kcount, static_cast<unsigned long long>(total));
+    dst = ctx->keyp + __shfl_sync(0xffffffffu, base, 31);
+  } else {
+    if (ctx->fill + static_cast<uint32_t>(total) > static_cast<uint32_t>(kKeyBuf)) flush_keys(kb, ctx);
+    const uint32_t fill = ctx->fill;
+    __syncwarp();
+    if (lane == 0) ctx->fill = fill + static_cast<uint32_t>(total);
+    dst = kb;
+    pos += fill;
+  }
+  const unsigned long long ikey = static_cast<unsigned long long>(0xFFFFu - (rowcol >> 16)) << 16;
+  const unsigned int jkey = 0xFFFFu - (rowcol & 0xFFFFu);
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    if (cand & (1u << k)) {
+      const unsigned int T = __float2uint_rn(__uint_as_float(v[k]));  // exact integer in fp32
+      dst[pos++] = (static_cast<unsigned long long>(T) << 32) | ikey | static_cast<unsigned long long>(jkey - k);
+      atomicAdd(&hist_s[T >> 4], 1u);
+    }
+  }
+  __syncwarp();
+}
+
 }  // namespace
 
 // PROF: experiments only — lane 0 of one warp per role accumulates the cycles it spends waiting on each
@@ -219,25 +305,25 @@ __device__ __forceinline__ float colsum16(float (&m)[16], int lane) {
 
 template <bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangles_mma_kernel(
-    const PairDesc* __restrict__ descs, int pairs, int total_tiles, const uint32_t* __restrict__ adj,
-    const uint32_t* __restrict__ panel, PairDev* __restrict__ state, const ChunkDev* __restrict__ chunk,
-    unsigned long long* __restrict__ keys, const uint32_t* __restrict__ theta, uint32_t* __restrict__ hist,
-    unsigned long long* __restrict__ t2, int dbg) {
-  if (chunk->overflow) return;
+    const PairDesc* __restrict__ descs, const uint2* __restrict__ tiles, int total_tiles,
+    const uint32_t* __restrict__ adj, const uint32_t* __restrict__ panel, PairDev* __restrict__ state,
+    const ChunkDev* __restrict__ chunk, unsigned long long* __restrict__ keys, const uint32_t* __restrict__ theta,
+    uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2, int dbg) {
+  if (chunk->overflow || !chunk->use_tensor) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stage_base = smem_raw;
   unsigned char* raw_base = smem_raw + kOffRaw;
   uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem_raw + kOffHist);
   unsigned long long* kbuf = reinterpret_cast<unsigned long long*>(smem_raw + kOffKeys);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kOffBars);
-  uint64_t* full = bars;                                 // [kStages]   producers of both CTAs -> MMA (leader's copy)
-  uint64_t* empty = full + kStages;                      // [kStages]   MMA commit (multicast) -> producers
-  uint64_t* raw_full = empty + kStages;                  // [kRawStages] bulk copies -> producers
-  uint64_t* raw_empty = raw_full + kRawStages;           // [kRawStages] producers -> bulk-copy issuer
-  uint64_t* tmem_full = raw_empty + kRawStages;          // [2] MMA commit (multicast) -> epilogue
+  uint64_t* full2 = bars;                                // [2] producers of both CTAs -> MMA (leader's copy); per stage pair
+  uint64_t* empty2 = full2 + 2;                          // [2] MMA commit (multicast) -> producers; per stage pair
+  uint64_t* raw_full = empty2 + 2;                       // [kRawStages] bulk copies -> producers
+  uint64_t* raw_empty2 = raw_full + kRawStages;          // [kRawStages/2] producers -> bulk-copy issuer; per stage pair
+  uint64_t* tmem_full = raw_empty2 + kRawStages / 2;     // [2] MMA commit (multicast) -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;                  // [2] epilogue warps of both CTAs -> MMA (leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
-  uint32_t* fill_s = tmem_slot + 1;                      // [4] staged-key counters of the epilogue warps
+  EpiCtx* ectx = reinterpret_cast<EpiCtx*>(tmem_slot + 4);  // [kEpiWarps] rare-path state of the epilogue warps
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t rank;
@@ -245,22 +331,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;  // cluster = CTA pair = one 256 x 240 tile at a time
 
   for (int k = tid; k < kHistBins; k += kThreads) hist_s[k] = 0;
+  if (tid < kEpiWarps) ectx[tid].fill = 0u;
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 4);  // two warps of the stage's group in each CTA
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full2[s], 8);  // two stages x two warps of each stage's group x two CTAs
+      mbar_init(&empty2[s], 1);
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * kEpiWarps);
     }
-    for (int s = 0; s < kRawStages; ++s) {
-      mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], 2);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 8);
-    }
+    for (int s = 0; s < kRawStages; ++s) mbar_init(&raw_full[s], 1);
+    for (int s = 0; s < kRawStages / 2; ++s) mbar_init(&raw_empty2[s], 4);
     mbar_fence_init();
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
@@ -282,119 +365,103 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;");
 
-  if (warp < 4) {
+  if (warp < kEpiWarps) {
     // ================================== epilogue warps ==================================
+    // warp = 4 h + q: TMEM lanes 32 q .. 32 q + 31 (rows), columns 128 h .. (8 chunks of 16, or 7 for h = 1)
+    const int q = warp & 3, h = warp >> 2;
+    const int nch = h ? kMmaTileN / 16 - 8 : 8;
     unsigned long long* kb = kbuf + warp * kKeyBuf;
-    uint32_t* fill_p = fill_s + warp;  // staged keys of this warp
-    if (lane == 0) *fill_p = 0u;
-    __syncwarp();
+    EpiCtx* ctx = ectx + warp;
     int cur_pair = -1, cur_bins = 0;
-    unsigned long long* keyp = nullptr;
-    unsigned long long* kcount = nullptr;
     float thf = 0.0f;
-    auto flush_keys = [&]() {
-      __syncwarp();
-      const uint32_t fill = *fill_p;
-      if (fill) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(kcount, static_cast<unsigned long long>(fill));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (uint32_t k = lane; k < fill; k += 32) keyp[base + k] = kb[k];
-        __syncwarp();
-        if (lane == 0) *fill_p = 0u;
-      }
-      __syncwarp();
-    };
-    auto flush_pair = [&]() {  // all four epilogue warps
-      flush_keys();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+    auto flush_pair = [&]() {  // all epilogue warps
+      flush_keys(kb, ctx);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       uint32_t* histp = hist + static_cast<size_t>(cur_pair) * kHistBins;
-      for (int k = tid; k < cur_bins; k += 128) {  // T <= N - 2: higher bins are empty
+      for (int k = tid; k < cur_bins; k += 32 * kEpiWarps) {  // T <= N - 2: higher bins are empty
         const uint32_t v = hist_s[k];
         if (v) {
           atomicAdd(&histp[k], v);
           hist_s[k] = 0;
         }
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");
     };
-    // raw edge-bit window of this thread's row for a tile: 9 words starting at the word that holds column J0
-    auto load_window = [&](const PairDesc& pd, int I0, int J0, uint32_t (&w)[9]) {
-      const int i = I0 + kCtaM * static_cast<int>(rank) + 32 * warp + lane;
+    // raw edge-bit window of this thread's row: 5 words starting at the word that holds column J0 + 128 h
+    auto load_window = [&](const PairLite& pd, int I0, int J0, uint32_t (&w)[5]) {
+      const int i = I0 + kCtaM * static_cast<int>(rank) + 32 * q + lane;
       const uint32_t* rowp = adj + pd.adj_off + static_cast<size_t>(i) * pd.stride;
-      const int w0 = J0 >> 5;
+      const int w0 = (J0 >> 5) + 4 * h;
       const bool row_ok = i < pd.Npad;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) w[k] = (row_ok && w0 + k < pd.stride) ? rowp[w0 + k] : 0u;
+      for (int k = 0; k < 5; ++k) w[k] = (row_ok && w0 + k < pd.stride) ? rowp[w0 + k] : 0u;
     };
 
     int n = 0, pair = -1;
-    PairDesc d;
+    PairLite d;
     long long w_tfull = 0, t_begin = PROF ? clock64() : 0;
     int t = cid, I0 = 0, J0 = 0;
-    uint32_t wraw[9];
+    uint32_t wraw[5];
     if (t < total_tiles) {
-      decode_tile(t, descs, pairs, pair, d, I0, J0);
+      fetch_tile(t, tiles, descs, pair, d, I0, J0);
       load_window(d, I0, J0, wraw);
     }
     for (; t < total_tiles; ++n) {
       // ---- this tile ----
-      const int tI0 = I0, tJ0 = J0;
+      const int tJ0 = J0;
       const long long node_off = d.node_off;
       if (pair != cur_pair) {
         if (cur_pair >= 0) flush_pair();
         cur_pair = pair;
         cur_bins = min(kHistBins, (d.N >> 4) + 1);
-        keyp = keys + state[pair].key_base;
-        kcount = &state[pair].key_count;
         thf = static_cast<float>(theta[pair]);
-      }
-      uint32_t win[8];
-      {
-        if (tJ0 & 16) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) win[k] = __funnelshift_r(wraw[k], wraw[k + 1], 16);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) win[k] = wraw[k];
+        __syncwarp();
+        if (lane == 0) {
+          ctx->keyp = keys + state[pair].key_base;
+          ctx->kcount = &state[pair].key_count;
+          ctx->thf = thf;
         }
-        win[7] &= 0xFFFFu;  // columns 240..255 of the window belong to the next J-block
+        __syncwarp();
       }
-      const int i = tI0 + kCtaM * static_cast<int>(rank) + 32 * warp + lane;
+      uint32_t win[4];
+      if (tJ0 & 16) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) win[k] = __funnelshift_r(wraw[k], wraw[k + 1], 16);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) win[k] = wraw[k];
+      }
+      if (h) win[3] &= 0xFFFFu;  // columns 240..255 of the window belong to the next J-block
+      const int i = I0 + kCtaM * static_cast<int>(rank) + 32 * q + lane;
+      const int cbase = tJ0 + 128 * h;  // first column of this warp's half
       {
-        const int dd = i - tJ0;  // keep j > i: clear window bits 0..dd
+        const int dd = i - cbase;  // keep j > i: clear window bits 0..dd
         if (dd >= 0) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < 4; ++k) {
             const int lo = 32 * k;
             if (dd >= lo + 31) win[k] = 0u;
             else if (dd >= lo) win[k] &= 0xFFFFFFFEu << (dd - lo);
           }
         }
       }
-      // ---- next tile: decode it and start loading its window now (hidden behind this tile's work) ----
+      // ---- next tile: look it up and start loading its window now (hidden behind this tile's work) ----
       t += ncl;
       if (t < total_tiles) {
-        decode_tile(t, descs, pairs, pair, d, I0, J0);
+        fetch_tile(t, tiles, descs, pair, d, I0, J0);
         load_window(d, I0, J0, wraw);
       }
-      const unsigned long long ikey = static_cast<unsigned long long>(0xFFFFu - static_cast<unsigned int>(i)) << 16;
 
       // ---- accumulators of tile n ----
       const int buf = n & 1;
       SACCOT_TIMED_WAIT(w_tfull, mbar_wait_wd(&tmem_full[buf], static_cast<uint32_t>((n >> 1) & 1), 1, n));
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t tbase = tmem + ((32u * warp) << 16) + static_cast<uint32_t>(kMmaTileN * buf);
+      const uint32_t tbase = tmem + ((32u * q) << 16) + static_cast<uint32_t>(kMmaTileN * buf + 128 * h);
       float rs0 = 0.0f, rs1 = 0.0f, rs2 = 0.0f, rs3 = 0.0f;
       uint32_t v[2][16];
-      if (!(dbg & 1)) SACCOT_TMEM_LD16(v[0], tbase);
-#pragma unroll
-      for (int c = 0; c < kMmaTileN / 16; ++c) {
-        if (dbg & 1) break;  // experiment: main loop without the epilogue work
-        uint32_t(&vc)[16] = v[c & 1];
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c + 1 < kMmaTileN / 16) SACCOT_TMEM_LD16(v[(c + 1) & 1], tbase + 16u * (c + 1));
-        const uint32_t bits16 = (win[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+      // One 16-column chunk.  Kept small and NOT unrolled over the chunks: the fully unrolled epilogue was
+      // 120 KB of straight-line code and spent most of its time in instruction-cache misses.
+      auto chunk16 = [&](const uint32_t(&vc)[16], uint32_t bits16, int c) {
         // masked counts (0 where there is no edge j > i)
         float m[16];
 #pragma unroll
@@ -406,25 +473,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         const float vmax = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
         const float vmax2 =
             fmaxf(fmaxf(fmaxf(m[8], m[9]), fmaxf(m[10], m[11])), fmaxf(fmaxf(m[12], m[13]), fmaxf(m[14], m[15])));
-        // rare (with a tight theta): some edge of these 32 x 16 entries reaches the pruning threshold
-        if (__any_sync(0xffffffffu, fmaxf(vmax, vmax2) >= thf)) {
-          const unsigned int jkey = 0xFFFFu - static_cast<unsigned int>(tJ0 + 16 * c);
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            if ((bits16 & (1u << k)) && __uint_as_float(vc[k]) >= thf) {
-              const unsigned int T = __float2uint_rn(__uint_as_float(vc[k]));  // exact integer in fp32
-              const uint32_t pos = atomicAdd(fill_p, 1u);
-              kb[pos] = (static_cast<unsigned long long>(T) << 32) | ikey | static_cast<unsigned long long>(jkey - k);
-              atomicAdd(&hist_s[T >> 4], 1u);
-            }
-          }
-          __syncwarp();
-          if (*fill_p > 128u) flush_keys();
-        }
+        const bool hit = __any_sync(0xffffffffu, fmaxf(vmax, vmax2) >= thf);
         // column sums (t2_j)
         const float cs = colsum16(m, lane);
         if (!(lane & 1) && cs > 0.0f)
-          atomicAdd(&t2[node_off + tJ0 + 16 * c + ((lane >> 1) & 15)], static_cast<unsigned long long>(cs));
+          atomicAdd(&t2[node_off + cbase + 16 * c + ((lane >> 1) & 15)], static_cast<unsigned long long>(cs));
+        // rare (with a tight theta): some edge of these 32 x 16 entries reaches the pruning threshold
+        if (hit)
+          emit_chunk(tbase + 16u * c, bits16, (static_cast<uint32_t>(i) << 16) | static_cast<uint32_t>(cbase + 16 * c), kb,
+                     ctx, hist_s);
+      };
+      if (!(dbg & 1)) {
+        SACCOT_TMEM_LD16(v[0], tbase);
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c + 1 < nch) SACCOT_TMEM_LD16(v[1], tbase + 16u * (c + 1));
+          chunk16(v[0], win[0] & 0xFFFFu, c);
+          if (c + 1 < nch) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c + 2 < nch) SACCOT_TMEM_LD16(v[0], tbase + 16u * (c + 2));
+            chunk16(v[1], win[0] >> 16, c + 1);
+          }
+          win[0] = win[1];  // next 32 columns of the window
+          win[1] = win[2];
+          win[2] = win[3];
+        }
       }
       // accumulator buffer is free again (the MMA issuer lives in the leader CTA)
       asm volatile("tcgen05.fence::before_thread_sync;");
@@ -436,35 +510,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     if (cur_pair >= 0) flush_pair();
     if (PROF && blockIdx.x < 2 && tid == 0)
       printf("cta %d epilogue: tiles %d total %lld wait_tmem_full %lld\n", blockIdx.x, n, clock64() - t_begin, w_tfull);
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ================================== MMA issuer (leader CTA only) ==================================
+    // One barrier wait and one commit per PAIR of stages: the issuing thread (not the tensor pipe) was the
+    // limit with a hand-over per stage.
     if (rank == 0) {
       // instruction descriptor: block-scaled, A/B = E2M1, UE8M0 scales, N = 240, M = 256 (2 x 128), K-major both
       const uint32_t idesc = (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kMmaTileN >> 3) << 17) | (1u << 23) | ((256u >> 4) << 24);
       const uint32_t sbase = smem_u32(stage_base);
       int pair = -1, n = 0;
       uint32_t g = 0;
-      PairDesc d;
+      PairLite d;
       long long w_full = 0, w_tempty = 0, t_begin = PROF ? clock64() : 0;
       for (int t = cid; t < total_tiles; t += ncl, ++n) {
         int I0, J0;
-        decode_tile(t, descs, pairs, pair, d, I0, J0);
+        fetch_tile(t, tiles, descs, pair, d, I0, J0);
+        const int np2 = (d.npanel + 1) >> 1;  // stage pairs (an odd last stage is padded with zeros)
         const int buf = n & 1;
         if (n >= 2) {
           SACCOT_TIMED_WAIT(w_tempty, mbar_wait_wd(&tmem_empty[buf], static_cast<uint32_t>(((n >> 1) - 1) & 1), 2, n));
           asm volatile("tcgen05.fence::after_thread_sync;");
         }
-        for (int it = 0; it < d.npanel; ++it, ++g) {
-          const uint32_t s = g % kStages;
-          SACCOT_TIMED_WAIT(w_full, mbar_wait_wd(&full[s], (g / kStages) & 1u, 3, g));
+        for (int ip = 0; ip < np2; ++ip, g += 2) {
+          const uint32_t pr = (g >> 1) & 1u;
+          SACCOT_TIMED_WAIT(w_full, mbar_wait_wd(&full2[pr], (g >> 2) & 1u, 3, g));
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (lane == 0) {
-            const uint32_t bA = sbase + s * kStageBytes, bB = bA + (kCtaM / 8) * kSBO;
 #pragma unroll
-            for (int ks = 0; ks < kStageK / 64; ++ks) {
-              if (dbg & 8) break;
-              const uint64_t da = umma_desc(bA + ks * 2 * kLBO), db = umma_desc(bB + ks * 2 * kLBO);
-              const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+            for (int ks = 0; ks < 2 * kStageK / 64; ++ks) {
+              const uint32_t bA = sbase + (2 * pr + (ks >> 2)) * kStageBytes + (ks & 3) * 2 * kLBO;
+              const uint64_t da = umma_desc(bA), db = umma_desc(bA + (kCtaM / 8) * kSBO);
+              const uint32_t acc = (ip > 0 || ks > 0) ? 1u : 0u;
               asm volatile(
                   "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                   "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(
@@ -472,8 +548,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
                   "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 16u)
                   : "memory");
             }
-            umma_commit_pair(&empty[s]);                              // stage reusable in both CTAs
-            if (it == d.npanel - 1) umma_commit_pair(&tmem_full[buf]);  // accumulators complete in both CTAs
+            umma_commit_pair(&empty2[pr]);                         // both stages reusable in both CTAs
+            if (ip == np2 - 1) umma_commit_pair(&tmem_full[buf]);  // accumulators complete in both CTAs
           }
           __syncwarp();
         }
@@ -483,93 +559,109 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
                w_full, w_tempty);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-  } else if (warp == 5) {
+  } else if (warp == kTmaWarp) {
     // ================================== bulk-copy issuer ==================================
     if (lane == 0) {
       int pair = -1;
       uint32_t g = 0;
-      PairDesc d;
+      PairLite d;
       long long w_rempty = 0, t_begin = PROF ? clock64() : 0;
       for (int t = cid; t < total_tiles; t += ncl) {
         int I0, J0;
-        decode_tile(t, descs, pairs, pair, d, I0, J0);
+        fetch_tile(t, tiles, descs, pair, d, I0, J0);
         const int a0 = I0 + kCtaM * static_cast<int>(rank), b0 = J0 + kCtaNB * static_cast<int>(rank);
         const uint32_t bytesA = a0 < d.Npad ? kRawABytes : 0u;  // Npad is a multiple of 128
-        uint32_t bytesB = static_cast<uint32_t>(max(0, min(kCtaNB, d.Npad - b0))) * 32u;
-        if (dbg & 16) bytesB = 0;                 // experiments: no B copy / a 16-byte B copy
-        if ((dbg & 32) && bytesB) bytesB = 16;
+        const uint32_t bytesB = static_cast<uint32_t>(max(0, min(kCtaNB, d.Npad - b0))) * 32u;
         const uint32_t* pp = panel + d.panel_off;
-        for (int it = 0; it < d.npanel; ++it, ++g) {
-          const uint32_t rs = g % kRawStages;
-          if (g >= kRawStages) SACCOT_TIMED_WAIT(w_rempty, mbar_wait_wd(&raw_empty[rs], ((g / kRawStages) - 1) & 1u, 4, g));
-          unsigned char* dst = raw_base + rs * kRawBytes;
-          const uint32_t* src = pp + static_cast<size_t>(it) * d.Npad * 8;
-          mbar_arrive_expect_tx(&raw_full[rs], bytesA + bytesB);
-          if (bytesA) bulk_g2s(dst, src + static_cast<size_t>(a0) * 8, bytesA, &raw_full[rs]);
-          if (bytesB) bulk_g2s(dst + kRawABytes, src + static_cast<size_t>(b0) * 8, bytesB, &raw_full[rs]);
+        const int np2 = (d.npanel + 1) >> 1;
+        for (int ip = 0; ip < np2; ++ip, g += 2) {
+          const uint32_t rp = (g % kRawStages) >> 1;
+          if (g >= kRawStages) SACCOT_TIMED_WAIT(w_rempty, mbar_wait_wd(&raw_empty2[rp], ((g / kRawStages) - 1) & 1u, 4, g));
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int it = 2 * ip + e;
+            const uint32_t rs = 2 * rp + e;
+            unsigned char* dst = raw_base + rs * kRawBytes;
+            const bool real = it < d.npanel;  // the padding stage of an odd panel count carries no data
+            const uint32_t nA = real ? bytesA : 0u, nB = real ? bytesB : 0u;
+            const uint32_t* src = pp + static_cast<size_t>(it) * d.Npad * 8;
+            mbar_arrive_expect_tx(&raw_full[rs], nA + nB);
+            if (nA) bulk_g2s(dst, src + static_cast<size_t>(a0) * 8, nA, &raw_full[rs]);
+            if (nB) bulk_g2s(dst + kRawABytes, src + static_cast<size_t>(b0) * 8, nB, &raw_full[rs]);
+          }
         }
       }
       if (PROF && blockIdx.x < 2)
         printf("cta %d bulk-copy issuer: stages %u total %lld wait_raw_empty %lld\n", blockIdx.x, g, clock64() - t_begin, w_rempty);
     }
-  } else if (warp < 6 + kProducerWarps) {
+  } else {
     // ================================== expansion warps ==================================
     // Stage g is expanded by group g % kGroupsP (two warps, eight 16-row tasks each): the fixed cost of a
     // stage hand-over (two barrier waits, proxy fence, two arrivals; ~350 cycles measured) is paid once
     // per kGroupsP stages by every warp instead of once per stage.
-    const int pw = warp - 6;
+    const int pw = warp - kProdWarp0;
     const int grp = pw >> 1, half = pw & 1;
     const int r8 = lane & 7, rg2 = (lane >> 3) & 1, q = lane >> 4;
     uint32_t g = 0;
     int pair = -1;
-    PairDesc d;
-    long long w_rfull = 0, w_empty = 0, t_begin = PROF ? clock64() : 0;
+    PairLite d;
+    long long w_rfull = 0, w_empty = 0, t_sts = 0, t_fence = 0, t_arr = 0, t_begin = PROF ? clock64() : 0;
     for (int t = cid; t < total_tiles; t += ncl) {
       int I0, J0;
-      decode_tile(t, descs, pairs, pair, d, I0, J0);
+      fetch_tile(t, tiles, descs, pair, d, I0, J0);
       const int a0 = I0 + kCtaM * static_cast<int>(rank), b0 = J0 + kCtaNB * static_cast<int>(rank);
       // rows past the end of the pair were not copied: they expand to zeros
       const int rowsA = a0 < d.Npad ? kCtaM : 0, rowsB = max(0, min(kCtaNB, d.Npad - b0));
-      for (int it = 0; it < d.npanel; ++it, ++g) {
+      const int np = (d.npanel + 1) & ~1;
+      for (int it = 0; it < np; ++it, ++g) {
         if (static_cast<int>(g % kGroupsP) != grp) continue;
         const uint32_t rs = g % kRawStages, s = g % kStages;
         SACCOT_TIMED_WAIT(w_rfull, mbar_wait_wd(&raw_full[rs], (g / kRawStages) & 1u, 5, g));
         const unsigned char* raw = raw_base + rs * kRawBytes;
+        const bool real = it < d.npanel;
         uint4 w[kTasksPerWarp];
 #pragma unroll
         for (int k = 0; k < kTasksPerWarp; ++k) {
           const int gr = 2 * (half + 2 * k) + rg2;  // 8-row group of this lane
           const int r = 8 * gr + r8;
-          const bool ok = gr < kGroups && (r < kCtaM ? r < rowsA : r - kCtaM < rowsB);
+          const bool ok = real && gr < kGroups && (r < kCtaM ? r < rowsA : r - kCtaM < rowsB);
           w[k] = ok ? *reinterpret_cast<const uint4*>(raw + r * 32 + q * 16) : make_uint4(0u, 0u, 0u, 0u);
         }
-        if (g >= kStages) SACCOT_TIMED_WAIT(w_empty, mbar_wait_wd(&empty[s], ((g / kStages) - 1) & 1u, 6, g));
+        if (g >= kStages) SACCOT_TIMED_WAIT(w_empty, mbar_wait_wd(&empty2[s >> 1], ((g / kStages) - 1) & 1u, 6, g));
         unsigned char* st = stage_base + s * kStageBytes;
+        const long long tp0 = PROF ? clock64() : 0;
 #pragma unroll
         for (int k = 0; k < kTasksPerWarp; ++k) {
           const int gr = 2 * (half + 2 * k) + rg2;
-          if (gr < kGroups && !(dbg & 4)) expand_quad(w[k], st + gr * kSBO + 4 * q * kLBO + r8 * 16);
+          if (gr < kGroups) expand_quad(w[k], st + gr * kSBO + 4 * q * kLBO + r8 * 16);
         }
+        const long long tp1 = PROF ? clock64() : 0;
         // generic-proxy writes -> visible to the tensor cores (async proxy), then one arrival per warp on the
         // leader's barrier: its MMAs read this CTA's stage too
-        if (!(dbg & 2)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
+        const long long tp2 = PROF ? clock64() : 0;
         if (lane == 0) {
-          mbar_arrive_cluster(&full[s], 0u);
-          mbar_arrive(&raw_empty[rs]);
+          mbar_arrive_cluster(&full2[s >> 1], 0u);
+          mbar_arrive(&raw_empty2[rs >> 1]);
+        }
+        if (PROF) {
+          t_sts += tp1 - tp0;
+          t_fence += tp2 - tp1;
+          t_arr += clock64() - tp2;
         }
       }
     }
     if (PROF && blockIdx.x < 2 && lane == 0 && (pw == 0 || pw == kProducerWarps - 1))
-      printf("cta %d producer %d: stages %u total %lld wait_raw_full %lld wait_empty %lld\n", blockIdx.x, pw, g,
-             clock64() - t_begin, w_rfull, w_empty);
+      printf("cta %d producer %d: stages %u total %lld wait_raw_full %lld wait_empty %lld expand+sts %lld fence %lld arrive %lld\n",
+             blockIdx.x, pw, g, clock64() - t_begin, w_rfull, w_empty, t_sts, t_fence, t_arr);
   }
 
   // no CTA of the pair may exit (or free its TMEM) while the other can still touch its memory
   asm volatile("tcgen05.fence::before_thread_sync;");
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;");
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -587,7 +679,9 @@ static size_t theta_smem_bytes(int max_npad) {
 
 __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restrict__ descs,
                                                          const uint32_t* __restrict__ adj,
+                                                         const ChunkDev* __restrict__ chunk,
                                                          uint32_t* __restrict__ theta, int Ke, int prune, int max_npad) {
+  if (chunk->overflow || !chunk->use_tensor) return;
   const int pair = blockIdx.x;
   if (!prune) {
     if (threadIdx.x == 0) theta[pair] = 0u;
@@ -727,24 +821,28 @@ int triangles_mma_configure() {
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
-int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int total_tiles, int max_npad,
+int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
+                     const ChunkDev* d_chunk, uint32_t* d_theta, int Ke, int prune) {
+  tri_theta_kernel<<<pairs, 1024, theta_smem_bytes(max_npad), lc.stream>>>(d_desc, d_adj, d_chunk, d_theta, Ke, prune, max_npad);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_tiles, int total_tiles,
                          const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
-                         unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
-                         int Ke, int prune, int dbg) {
-  tri_theta_kernel<<<pairs, 1024, theta_smem_bytes(max_npad), lc.stream>>>(d_desc, d_adj, d_theta, Ke, prune, max_npad);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return -static_cast<int>(e);
+                         unsigned long long* d_keys, const uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
+                         int dbg) {
   const int grid = 2 * std::min(total_tiles, lc.sm_count / 2);  // CTA pairs
   if (grid > 0) {
     if (dbg & 64)
-      triangles_mma_kernel<true><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, pairs, total_tiles, d_adj, d_panel,
+      triangles_mma_kernel<true><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_adj, d_panel,
                                                                            d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, dbg);
     else
-      triangles_mma_kernel<false><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, pairs, total_tiles, d_adj, d_panel,
+      triangles_mma_kernel<false><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_adj, d_panel,
                                                                             d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, dbg);
   }
-  e = cudaGetLastError();
-  return e == cudaSuccess ? 2 : -static_cast<int>(e);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }
 
 }  // namespace saccot

@@ -59,5 +59,8 @@ def gpu(gpu_lib):
     from sac_cot_b200.api import Registrar
     reg = Registrar(lib=gpu_lib, device=0)
     reg.set("keep_debug", 1)
+    # stage-parity tests compare every edge key and the full histogram: the POPC kernels provide them; the
+    # tensor-core kernel (which prunes keys) and the automatic choice have their own tests
+    reg.set("triangle_path", 0)
     yield reg
     reg.close()

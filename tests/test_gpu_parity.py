@@ -171,17 +171,20 @@ def test_batch_with_ragged_sizes_matches_oracle(gpu, oracle):
     np.testing.assert_array_equal(rc.inliers, rg.inliers)
 
 
-def test_key_pool_growth_retry(gpu_lib, oracle):
+@pytest.mark.parametrize("path", [0, 2])
+def test_key_pool_growth_retry(gpu_lib, oracle, path):
     # a dense graph (large tau) exceeds the 12.5 % initial key-pool guess: the library must grow
     # the pool and re-run transparently
     p = synth.make_pair(1200, 0.2, 7900)
     with Registrar(lib=gpu_lib, tau_compat=1.5, tau_inlier=0.1) as g:
         g.set("keep_debug", 1)
+        g.set("triangle_path", path)
         set_params(oracle, tau_compat=1.5, tau_inlier=0.1)
         out_g = g.register(p.src, p.dst)
         out_o = oracle.register(p.src, p.dst)
         assert g.get("retries") >= 1
-        compare_stages(g, oracle)
+        assert g.get("triangle_path_used") == (1 if path else 0)   # dense graph: the automatic choice is the tensor cores
+        (compare_pruned if path else compare_stages)(g, oracle)
         compare_pose(*out_g, *out_o)
 
 
@@ -198,6 +201,7 @@ def test_device_resident_entry_point(gpu_lib, oracle):
     d_i = torch.empty(5, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev)
     with Registrar(lib=gpu_lib, device=0, stream=stream.cuda_stream) as g:
+        g.set("triangle_path", 0)
         g.register_packed_ptr(d_src.data_ptr(), d_dst.data_ptr(), offsets, d_R.data_ptr(), d_t.data_ptr(),
                               d_i.data_ptr(), _abi.LOC_DEVICE)
         stream.synchronize()
@@ -346,8 +350,15 @@ def test_cfg5_single_pair_n50000_full_stage_parity(gpu_lib, oracle_omp_lib):
         for r in (g, o):
             r.set("keep_debug", 1)
             set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
-        out_g = g.register(p.src, p.dst)
         out_o = o.register(p.src, p.dst)
+        # the automatic choice at this density is the tensor-core kernel (390 tiles of 256 x 240 x 50176 MACs)
+        out_g = g.register(p.src, p.dst)
+        assert g.get("triangle_path_used") == 1
+        compare_pruned(g, o, stages=[s for s in PRUNED if s[0] != "adj"])
+        compare_pose(*out_g, *out_o)
+        # POPC kernels (chunked rows): every key and the whole histogram
+        g.set("triangle_path", 0)
+        out_g = g.register(p.src, p.dst)
         compare_stages(g, o, stages=[s for s in EXACT if s[0] != "adj"])
         # adjacency: 313 MB per side; compare through a checksum of 64-bit words plus the counts above
         ag = g.debug(0, _abi.DBG_ADJ).view(np.uint64)
@@ -385,11 +396,11 @@ def test_many_tiny_pairs_and_repeated_calls_on_one_ctx(gpu_lib, oracle_lib):
 PRUNED = [st for st in EXACT if st[0] != "hist"]
 
 
-def compare_pruned(gpu, oracle, pair_idx=0):
+def compare_pruned(gpu, oracle, pair_idx=0, stages=None):
     """With pruning the kernel keeps only edges whose T reaches a per-pair threshold that provably lies at
     or below the K_e-th largest T: every stage downstream is identical, the key list is a subset that
     contains every edge at or above the K_e-th key, and the histogram is exact above that key's digit."""
-    compare_stages(gpu, oracle, pair_idx, stages=PRUNED, edge_keys=False)
+    compare_stages(gpu, oracle, pair_idx, stages=PRUNED if stages is None else stages, edge_keys=False)
     kg = np.sort(gpu.debug(pair_idx, _abi.DBG_EDGE_KEYS))
     ko = np.sort(oracle.debug(pair_idx, _abi.DBG_EDGE_KEYS))
     assert len(np.unique(kg)) == len(kg) and np.isin(kg, ko).all(), "pruned keys are not a subset of the oracle's"
@@ -472,3 +483,44 @@ def test_tensor_core_path_batch_and_complete_graph(gpu, oracle, prune):
     for b in range(len(pairs)):
         check(gpu, oracle, b)
         compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
+
+
+# ---- automatic choice of the S2 kernels from the measured edge density ---------------------------
+def test_auto_path_picks_tensor_cores_for_dense_graphs_and_popc_for_sparse(gpu, oracle):
+    gpu.set("triangle_path", 2)
+    # indoor scale: ~7.6 % density at N = 5000 -> tensor cores
+    p = synth.make_config_pair("cfg2_3dmatch_256x5000", 5)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
+    out_g, out_o = gpu.register(p.src, p.dst), oracle.register(p.src, p.dst)
+    assert gpu.get("triangle_path_used") == 1
+    compare_pruned(gpu, oracle)
+    compare_pose(*out_g, *out_o)
+    # outdoor scale: ~2.3 % density -> POPC kernels, every key kept
+    p = synth.make_pair(4000, 0.03, 9911, box=(60.0, 60.0, 6.0), tau_compat=0.6)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
+    out_g, out_o = gpu.register(p.src, p.dst), oracle.register(p.src, p.dst)
+    assert gpu.get("triangle_path_used") == 0
+    compare_stages(gpu, oracle)
+    compare_pose(*out_g, *out_o)
+    # small pairs stay on the POPC kernels whatever their density
+    p = synth.make_pair(500, 0.5, 9912)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
+    gpu.register(p.src, p.dst), oracle.register(p.src, p.dst)
+    assert gpu.get("triangle_path_used") == 0
+    compare_stages(gpu, oracle)
+
+
+def test_default_ctx_uses_auto_path_and_matches_oracle_batch(gpu_lib, oracle):
+    ps = [synth.make_config_pair("cfg2_3dmatch_256x5000", b) for b in range(3)]
+    with Registrar(lib=gpu_lib, device=0) as reg:
+        assert reg.get("triangle_path") == 2
+        set_params(oracle, tau_compat=ps[0].tau_compat, tau_inlier=ps[0].tau_inlier)
+        set_params(reg, tau_compat=ps[0].tau_compat, tau_inlier=ps[0].tau_inlier)
+        rg = reg.register_batch([q.src for q in ps], [q.dst for q in ps])
+        ro = oracle.register_batch([q.src for q in ps], [q.dst for q in ps])
+        assert reg.get("triangle_path_used") == 1
+        for b in range(len(ps)):
+            compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
