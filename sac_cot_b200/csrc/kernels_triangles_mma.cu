@@ -64,6 +64,10 @@ static_assert(kStages % kGroupsP == 0 && kRawStages % kGroupsP == 0, "producer g
 constexpr int kKeyBuf = 128;                          // staged keys per epilogue warp
 constexpr uint32_t kSfCol = 480;                      // scale factors: TMEM columns [480, 512)
 constexpr uint32_t kSfWord = 0x807F807Fu;             // UE8M0 per K block of 32: {1.0, 2.0, 1.0, 2.0}
+// Every accumulator entry starts at 2^23 (written by the epilogue when it hands a buffer back) and every MMA
+// accumulates: the fp32 value 2^23 + T has the bit pattern kBias + T, so the epilogue works on integers
+// without a single conversion (T <= 65535 < 2^23: exact).
+constexpr uint32_t kBias = 0x4B000000u;
 
 // shared-memory carve-up (dynamic)
 constexpr int kOffRaw = kStages * kStageBytes;                    // 126976
@@ -177,46 +181,18 @@ __device__ __forceinline__ void fetch_tile(int t, const uint2* __restrict__ tile
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                      \
       : "r"(taddr))
 
-// sum over the 32 lanes (rows) of 16 per-lane values (columns): afterwards lane L holds column (L>>1)&15
-__device__ __forceinline__ float colsum16(float (&m)[16], int lane) {
-  {
-    const bool hi = (lane & 16) != 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float send = hi ? m[k] : m[k + 8], keep = hi ? m[k + 8] : m[k];
-      m[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool hi = (lane & 8) != 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float send = hi ? m[k] : m[k + 4], keep = hi ? m[k + 4] : m[k];
-      m[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool hi = (lane & 4) != 0;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float send = hi ? m[k] : m[k + 2], keep = hi ? m[k + 2] : m[k];
-      m[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-  {
-    const bool hi = (lane & 2) != 0;
-    const float send = hi ? m[0] : m[1], keep = hi ? m[1] : m[0];
-    m[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  return m[0] + __shfl_xor_sync(0xffffffffu, m[0], 1);
-}
+#define SACCOT_TMEM_ST16_BIAS(taddr)                                                                          \
+  asm volatile(                                                                                               \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), \
+      "r"(kBias)                                                                                              \
+      : "memory")
 
 // Per-warp state of the epilogue's rare path, kept in shared memory so that the out-of-line functions take
 // few arguments (every live register of the hot loop is spilled around a call).
 struct EpiCtx {
   unsigned long long* keyp;       // the pair's key list
   unsigned long long* kcount;     // the pair's key counter
-  float thf;                      // pruning threshold
+  uint32_t thb;                   // pruning threshold + kBias
   uint32_t fill;                  // keys staged in the warp's buffer
 };
 
@@ -247,11 +223,11 @@ __device__ __noinline__ void emit_chunk(uint32_t taddr, uint32_t bits16, uint32_
   uint32_t v[16];
   SACCOT_TMEM_LD16(v, taddr);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  const float thf = ctx->thf;
+  const uint32_t thb = ctx->thb;
   uint32_t cand = 0;
 #pragma unroll
   for (int k = 0; k < 16; ++k)
-    if ((bits16 & (1u << k)) && __uint_as_float(v[k]) >= thf) cand |= 1u << k;
+    if ((bits16 & (1u << k)) && v[k] >= thb) cand |= 1u << k;
   const int nc = __popc(cand);
   int incl = nc;
 #pragma unroll
@@ -280,7 +256,7 @@ __device__ __noinline__ void emit_chunk(uint32_t taddr, uint32_t bits16, uint32_
 #pragma unroll 4
   for (int k = 0; k < 16; ++k) {
     if (cand & (1u << k)) {
-      const unsigned int T = __float2uint_rn(__uint_as_float(v[k]));  // exact integer in fp32
+      const unsigned int T = v[k] - kBias;  // accumulators hold 2^23 + T
       dst[pos++] = (static_cast<unsigned long long>(T) << 32) | ikey | static_cast<unsigned long long>(jkey - k);
       atomicAdd(&hist_s[T >> 4], 1u);
     }
@@ -360,7 +336,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
-  // barriers initialised, TMEM allocated and scale factors written in BOTH CTAs before anyone proceeds
+  if (warp < kEpiWarps) {  // both accumulator buffers start at 2^23 (see kBias)
+    const int q = warp & 3, h = warp >> 2;
+    const int nch = h ? kMmaTileN / 16 - 8 : 8;
+    for (int b = 0; b < 2; ++b)
+      for (int c = 0; c < nch; ++c)
+        SACCOT_TMEM_ST16_BIAS(tmem + ((32u * q) << 16) + static_cast<uint32_t>(kMmaTileN * b + 128 * h + 16 * c));
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  // barriers initialised, TMEM allocated, scale factors and accumulator bias written in BOTH CTAs before
+  // anyone proceeds
   asm volatile("tcgen05.fence::before_thread_sync;");
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;");
@@ -373,7 +358,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     unsigned long long* kb = kbuf + warp * kKeyBuf;
     EpiCtx* ctx = ectx + warp;
     int cur_pair = -1, cur_bins = 0;
-    float thf = 0.0f;
+    uint32_t thb = kBias;
     auto flush_pair = [&]() {  // all epilogue warps
       flush_keys(kb, ctx);
       asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -399,7 +384,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
 
     int n = 0, pair = -1;
     PairLite d;
-    long long w_tfull = 0, t_begin = PROF ? clock64() : 0;
+    long long w_tfull = 0, t_ldw = 0, t_chunk = 0, t_emit = 0, t_pairchg = 0, t_win = 0, t_fetch = 0, t_tail = 0;
+    const long long t_begin = PROF ? clock64() : 0;
     int t = cid, I0 = 0, J0 = 0;
     uint32_t wraw[5];
     if (t < total_tiles) {
@@ -410,19 +396,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       // ---- this tile ----
       const int tJ0 = J0;
       const long long node_off = d.node_off;
+      const long long tq0 = PROF ? clock64() : 0;
       if (pair != cur_pair) {
         if (cur_pair >= 0) flush_pair();
         cur_pair = pair;
         cur_bins = min(kHistBins, (d.N >> 4) + 1);
-        thf = static_cast<float>(theta[pair]);
+        thb = theta[pair] + kBias;
         __syncwarp();
         if (lane == 0) {
           ctx->keyp = keys + state[pair].key_base;
           ctx->kcount = &state[pair].key_count;
-          ctx->thf = thf;
+          ctx->thb = thb;
         }
         __syncwarp();
       }
+      const long long tq1 = PROF ? clock64() : 0;
       uint32_t win[4];
       if (tJ0 & 16) {
 #pragma unroll
@@ -445,6 +433,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
           }
         }
       }
+      const long long tq2 = PROF ? clock64() : 0;
       // ---- next tile: look it up and start loading its window now (hidden behind this tile's work) ----
       t += ncl;
       if (t < total_tiles) {
@@ -452,64 +441,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         load_window(d, I0, J0, wraw);
       }
 
+      const long long tq3 = PROF ? clock64() : 0;
+      if (PROF) {
+        t_pairchg += tq1 - tq0;
+        t_win += tq2 - tq1;
+        t_fetch += tq3 - tq2;
+      }
       // ---- accumulators of tile n ----
       const int buf = n & 1;
       SACCOT_TIMED_WAIT(w_tfull, mbar_wait_wd(&tmem_full[buf], static_cast<uint32_t>((n >> 1) & 1), 1, n));
       asm volatile("tcgen05.fence::after_thread_sync;");
       const uint32_t tbase = tmem + ((32u * q) << 16) + static_cast<uint32_t>(kMmaTileN * buf + 128 * h);
-      float rs0 = 0.0f, rs1 = 0.0f, rs2 = 0.0f, rs3 = 0.0f;
+      uint32_t rsum = 0;  // row sum of this tile half, biased: + 16 kBias per chunk (mod 2^32)
       uint32_t v[2][16];
       // One 16-column chunk.  Kept small and NOT unrolled over the chunks: the fully unrolled epilogue was
       // 120 KB of straight-line code and spent most of its time in instruction-cache misses.
       auto chunk16 = [&](const uint32_t(&vc)[16], uint32_t bits16, int c) {
-        // masked counts (0 where there is no edge j > i)
-        float m[16];
+        // masked counts, biased: kBias + T where there is an edge j > i, kBias elsewhere
+        uint32_t m[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) m[k] = (bits16 & (1u << k)) ? __uint_as_float(vc[k]) : 0.0f;
-        rs0 += (m[0] + m[4]) + (m[8] + m[12]);
-        rs1 += (m[1] + m[5]) + (m[9] + m[13]);
-        rs2 += (m[2] + m[6]) + (m[10] + m[14]);
-        rs3 += (m[3] + m[7]) + (m[11] + m[15]);
-        const float vmax = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-        const float vmax2 =
-            fmaxf(fmaxf(fmaxf(m[8], m[9]), fmaxf(m[10], m[11])), fmaxf(fmaxf(m[12], m[13]), fmaxf(m[14], m[15])));
-        const bool hit = __any_sync(0xffffffffu, fmaxf(vmax, vmax2) >= thf);
-        // column sums (t2_j)
-        const float cs = colsum16(m, lane);
-        if (!(lane & 1) && cs > 0.0f)
-          atomicAdd(&t2[node_off + cbase + 16 * c + ((lane >> 1) & 15)], static_cast<unsigned long long>(cs));
+        for (int k = 0; k < 16; ++k) m[k] = (bits16 & (1u << k)) ? vc[k] : kBias;
+        rsum += ((m[0] + m[1] + m[2]) + (m[3] + m[4] + m[5])) + ((m[6] + m[7] + m[8]) + (m[9] + m[10] + m[11])) +
+                ((m[12] + m[13]) + (m[14] + m[15]));
+        const uint32_t vmax = max(max(max(m[0], m[1]), max(m[2], m[3])), max(max(m[4], m[5]), max(m[6], m[7])));
+        const uint32_t vmax2 = max(max(max(m[8], m[9]), max(m[10], m[11])), max(max(m[12], m[13]), max(m[14], m[15])));
+        const bool hit = __any_sync(0xffffffffu, max(vmax, vmax2) >= thb);
+        // column sums (t2_j): one warp reduction per column (16 independent REDUX), lane k keeps column k
+        uint32_t cs = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint32_t r = __reduce_add_sync(0xffffffffu, m[k]) - 32u * kBias;
+          if (lane == k) cs = r;
+        }
+        if (cs) atomicAdd(&t2[node_off + cbase + 16 * c + lane], static_cast<unsigned long long>(cs));
         // rare (with a tight theta): some edge of these 32 x 16 entries reaches the pruning threshold
         if (hit)
-          emit_chunk(tbase + 16u * c, bits16, (static_cast<uint32_t>(i) << 16) | static_cast<uint32_t>(cbase + 16 * c), kb,
-                     ctx, hist_s);
+          SACCOT_TIMED_WAIT(t_emit, emit_chunk(tbase + 16u * c, bits16,
+                                               (static_cast<uint32_t>(i) << 16) | static_cast<uint32_t>(cbase + 16 * c), kb, ctx,
+                                               hist_s));
+        // the columns go back to 2^23 for the tile after next
+        SACCOT_TMEM_ST16_BIAS(tbase + 16u * c);
       };
       if (!(dbg & 1)) {
         SACCOT_TMEM_LD16(v[0], tbase);
 #pragma unroll 1
         for (int c = 0; c < nch; c += 2) {
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          SACCOT_TIMED_WAIT(t_ldw, asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"));
           if (c + 1 < nch) SACCOT_TMEM_LD16(v[1], tbase + 16u * (c + 1));
-          chunk16(v[0], win[0] & 0xFFFFu, c);
+          SACCOT_TIMED_WAIT(t_chunk, chunk16(v[0], win[0] & 0xFFFFu, c));
           if (c + 1 < nch) {
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            SACCOT_TIMED_WAIT(t_ldw, asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"));
             if (c + 2 < nch) SACCOT_TMEM_LD16(v[0], tbase + 16u * (c + 2));
-            chunk16(v[1], win[0] >> 16, c + 1);
+            SACCOT_TIMED_WAIT(t_chunk, chunk16(v[1], win[0] >> 16, c + 1));
           }
           win[0] = win[1];  // next 32 columns of the window
           win[1] = win[2];
           win[2] = win[3];
         }
       }
-      // accumulator buffer is free again (the MMA issuer lives in the leader CTA)
+      // accumulator buffer is free (and back at its bias) again; the MMA issuer lives in the leader CTA
+      const long long tq4 = PROF ? clock64() : 0;
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0u);
-      const float rowsum = (rs0 + rs1) + (rs2 + rs3);
-      if (rowsum > 0.0f) atomicAdd(&t2[node_off + i], static_cast<unsigned long long>(rowsum));
+      const uint32_t rowsum = rsum - static_cast<uint32_t>(nch) * 16u * kBias;
+      if (rowsum && !(dbg & 1)) atomicAdd(&t2[node_off + i], static_cast<unsigned long long>(rowsum));
+      if (PROF) t_tail += clock64() - tq4;
     }
     if (cur_pair >= 0) flush_pair();
     if (PROF && blockIdx.x < 2 && tid == 0)
-      printf("cta %d epilogue: tiles %d total %lld wait_tmem_full %lld\n", blockIdx.x, n, clock64() - t_begin, w_tfull);
+      printf("cta %d epilogue: tiles %d total %lld wait_tmem_full %lld wait_ld %lld chunks %lld (emit %lld) pairchg %lld win %lld "
+             "fetch %lld tail %lld\n",
+             blockIdx.x, n, clock64() - t_begin, w_tfull, t_ldw, t_chunk, t_emit, t_pairchg, t_win, t_fetch, t_tail);
   } else if (warp == kMmaWarp) {
     // ================================== MMA issuer (leader CTA only) ==================================
     // One barrier wait and one commit per PAIR of stages: the issuing thread (not the tensor pipe) was the
@@ -517,7 +521,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     if (rank == 0) {
       // instruction descriptor: block-scaled, A/B = E2M1, UE8M0 scales, N = 240, M = 256 (2 x 128), K-major both
       const uint32_t idesc = (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kMmaTileN >> 3) << 17) | (1u << 23) | ((256u >> 4) << 24);
-      const uint32_t sbase = smem_u32(stage_base);
+      const uint64_t desc0 = umma_desc(smem_u32(stage_base));
+      const uint32_t desc_lo = static_cast<uint32_t>(desc0), desc_hi = static_cast<uint32_t>(desc0 >> 32);
       int pair = -1, n = 0;
       uint32_t g = 0;
       PairLite d;
@@ -536,16 +541,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
           SACCOT_TIMED_WAIT(w_full, mbar_wait_wd(&full2[pr], (g >> 2) & 1u, 3, g));
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (lane == 0) {
+            // shared-memory descriptors: only the 14-bit start-address field (16-byte units) changes
+            const uint32_t lo0 = desc_lo + pr * ((2 * kStageBytes) >> 4);
 #pragma unroll
             for (int ks = 0; ks < 2 * kStageK / 64; ++ks) {
-              const uint32_t bA = sbase + (2 * pr + (ks >> 2)) * kStageBytes + (ks & 3) * 2 * kLBO;
-              const uint64_t da = umma_desc(bA), db = umma_desc(bA + (kCtaM / 8) * kSBO);
-              const uint32_t acc = (ip > 0 || ks > 0) ? 1u : 0u;
+              const uint32_t loA = lo0 + static_cast<uint32_t>(((ks >> 2) * kStageBytes + (ks & 3) * 2 * kLBO) >> 4);
+              const uint32_t loB = loA + static_cast<uint32_t>(((kCtaM / 8) * kSBO) >> 4);
               asm volatile(
-                  "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                  "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(
+                  "{\n.reg .b64 da, db;\n.reg .pred p;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n"
+                  "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], da, db, %4, [%6], [%7], p;\n}" ::"r"(
                       tmem + static_cast<uint32_t>(kMmaTileN * buf)),
-                  "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 16u)
+                  "r"(loA), "r"(loB), "r"(desc_hi), "r"(idesc), "r"(1u), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 16u)
                   : "memory");
             }
             umma_commit_pair(&empty2[pr]);                         // both stages reusable in both CTAs
