@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--triangle-path", type=int, default=-1,
                     help="library knob triangle_path (0 POPC, 1 tensor core, 2 by edge density = library default)")
     ap.add_argument("--triangle-dbg", type=int, default=0, help="experiments only (library knob triangle_dbg)")
+    ap.add_argument("--tile-runs", type=int, default=-1, help="experiments only (library knob tile_runs)")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(synth.CONFIGS),
                     help="synthetic config (default: the headline config, BASELINE.json configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -230,6 +231,8 @@ def main():
         reg.set("triangle_path", args.triangle_path)
     if args.triangle_dbg:
         reg.set("triangle_dbg", args.triangle_dbg)
+    if args.tile_runs >= 0:
+        reg.set("tile_runs", args.tile_runs)
     K = reg.params.num_edges * reg.params.apex_per_edge
 
     # device-resident inputs / outputs

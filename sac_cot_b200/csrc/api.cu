@@ -144,6 +144,7 @@ struct Lane {
   Layout lay;                     // layout of the chunk most recently enqueued on this lane
   std::vector<PairDesc> descs;
   std::vector<uint2> tile_tab;    // host copy of the tensor-core path's tile list
+  std::vector<uint2> tile_scratch;
 };
 constexpr int kMaxLanes = 4;
 
@@ -156,6 +157,7 @@ struct sac_cot_ctx {
   int chunk_pairs = 0;
   int n_lanes = 2;
   int tri_path = 2;   // 0 = POPC bitset kernels, 1 = tensor-core (tcgen05 mxf4) kernel, 2 = by edge density per chunk
+  int tile_runs = 1;  // tensor-core path: deal tiles to the CTA pairs in runs (0: one at a time; experiments)
   int tri_dbg = 0;    // experiments only (bit 0: skip the tensor-core kernel's epilogue work; results are void)
   int tri_prune = 1;  // tensor-core path: drop edges below the per-pair threshold (exact for the selection)
   int64_t launches = 0;
@@ -479,6 +481,42 @@ int join_lanes(sac_cot_ctx* ctx, int n) {
   return 0;
 }
 
+// Tensor-core path: cluster c of the kernel walks entries c, c + ncl, c + 2 ncl, ... of the tile list.  plan()
+// emits the list sorted by (pair, column block, row block); dealt out one tile at a time, every cluster
+// would touch every pair (a pair change costs the epilogue a histogram flush and two barriers, and its
+// first window load a dependent descriptor fetch).  Reorder it so that a cluster gets runs of B consecutive
+// tiles: few pair changes per cluster, while the pairs in flight at any time (about ncl * B / tiles per
+// pair) still fit the L2 with their K-panel copies.  The tail that does not fill a whole round of runs is
+// dealt out tile by tile, so the clusters' tile counts differ by at most one, exactly as before.
+void interleave_tile_runs(std::vector<uint2>& tab, std::vector<uint2>& scratch, const std::vector<PairDesc>& descs,
+                          int sm_count) {
+  const int T = static_cast<int>(tab.size());
+  const int ncl = mma_clusters(T, sm_count);
+  if (ncl <= 1 || T < 2 * ncl) return;
+  size_t panel_bytes = 0;
+  for (const PairDesc& d : descs) panel_bytes += static_cast<size_t>(d.npanel) * d.Npad * 32;
+  const double pairs = static_cast<double>(descs.size());
+  const double pairs_in_flight = std::max(1.0, 32.0e6 / (static_cast<double>(panel_bytes) / pairs));
+  const int rounds = T / ncl;
+  int B = static_cast<int>(std::min<double>(rounds, std::max(1.0, pairs_in_flight * (T / pairs) / ncl)));
+  B = std::min(B, 256);
+  if (B < rounds) {  // a run length near B that leaves the smallest tail
+    int best = B;
+    for (int c = B; c >= std::max(1, (3 * B) / 4); --c)
+      if (T % (c * ncl) < T % (best * ncl)) best = c;
+    B = best;
+  }
+  if (B <= 1) return;
+  const int per_cluster = (T / (B * ncl)) * B, bulk = per_cluster * ncl;
+  scratch.resize(tab.size());
+  for (int o = 0; o < bulk; ++o) {
+    const int r = o / B;
+    scratch[static_cast<size_t>(r % ncl) + static_cast<size_t>((r / ncl) * B + o % B) * ncl] = tab[o];
+  }
+  for (int o = bulk; o < T; ++o) scratch[static_cast<size_t>((o - bulk) % ncl) + static_cast<size_t>(per_cluster + (o - bulk) / ncl) * ncl] = tab[o];
+  tab.swap(scratch);
+}
+
 // Enqueues one chunk [b0,b1) on a lane.  offsets are absolute (whole call).
 int enqueue_chunk(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst, const int64_t* offsets, int b0,
                   int b1, const sac_cot_params& prm, float* R, float* t, int32_t* inliers, bool host,
@@ -488,6 +526,7 @@ int enqueue_chunk(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst
   for (int b = 0; b < pairs; ++b) Ns[b] = static_cast<int32_t>(offsets[b0 + b + 1] - offsets[b0 + b]);
   const bool tensor = ctx->tri_path != 0;
   plan(Ns.data(), pairs, prm, host, tensor, ln.descs, ln.tile_tab, ln.lay);
+  if (tensor && ctx->tile_runs) interleave_tile_runs(ln.tile_tab, ln.tile_scratch, ln.descs, ctx->sm_count);
   if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
   if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
   bind(ln.lay, ln.arena, host, tensor);
@@ -714,6 +753,10 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
   }
   if (!std::strcmp(name, "triangle_prune")) {
     ctx->tri_prune = value != 0;
+    return SAC_COT_OK;
+  }
+  if (!std::strcmp(name, "tile_runs")) {
+    ctx->tile_runs = value != 0;
     return SAC_COT_OK;
   }
   if (!std::strcmp(name, "triangle_dbg")) {

@@ -168,6 +168,8 @@ __host__ __device__ inline int mma_tiles_of_pair(int N) {
   for (int jq = 0; jq < nJ; ++jq) t += mma_tiles_of_jblock(N, jq);
   return t;
 }
+// CTA pairs (clusters) the tensor-core kernel runs with; cluster c walks entries c, c + n, c + 2 n, ... of the tile list
+inline int mma_clusters(int total_tiles, int sm_count) { return total_tiles < sm_count / 2 ? total_tiles : sm_count / 2; }
 int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                      const ChunkDev* d_chunk, uint32_t* d_theta, int Ke, int prune);
 int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_tiles, int total_tiles,

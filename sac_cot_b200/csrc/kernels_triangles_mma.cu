@@ -55,8 +55,9 @@ constexpr int kSBO = (kStageK / 2 / 16) * 128;        // next 8-row group: 8 cor
 constexpr int kStageBytes = kGroups * kSBO;           // 31744
 constexpr int kRawBytes = kRows * 32;                 // 7936
 constexpr int kRawABytes = kCtaM * 32;                // 4096
-constexpr int kGroupsP = kProducerWarps / 2;          // producer groups of two warps; group = stage % kGroupsP
-constexpr int kTasksPerWarp = 8;                      // 16 warp tasks (16 rows x 2 quads) per stage, the last one half
+constexpr int kWarpsPerGroup = 2;                     // producer warps that share a stage
+constexpr int kGroupsP = kProducerWarps / kWarpsPerGroup;  // producer groups; group = stage % kGroupsP
+constexpr int kTasksPerWarp = 16 / kWarpsPerGroup;    // 16 warp tasks (16 rows x 2 quads) per stage, the last one half
 // A group must meet every phase of the barriers it waits on in order (mbarrier waits only know the phase
 // parity: a waiter two phases early passes at once).  With the group count dividing both ring sizes, a
 // group always returns to the same slots.
@@ -73,10 +74,12 @@ constexpr uint32_t kBias = 0x4B000000u;
 constexpr int kOffRaw = kStages * kStageBytes;                    // 126976
 constexpr int kOffHist = kOffRaw + kRawStages * kRawBytes;        // +63488
 constexpr int kOffKeys = kOffHist + kHistBins * 4;                // +16384
-constexpr int kOffBars = kOffKeys + kEpiWarps * kKeyBuf * 8;      // +8192
+constexpr int kOffWin = kOffKeys + kEpiWarps * (kKeyBuf + 16) * 8;  // +9216
+constexpr int kWinBytes = 2 * kEpiWarps * 5 * 32 * 4;             // edge-bit windows [2][warp][5][lane]
+constexpr int kOffBars = kOffWin + kWinBytes;                     // +10240
 // barriers: full2[2] empty2[2] raw_full[8] raw_empty2[4] tmem_full[2] tmem_empty[2]
 constexpr int kNumBars = 2 + 2 + kRawStages + kRawStages / 2 + 2 + 2;
-constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + kEpiWarps * 32;
+constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + kEpiWarps * 32;  // 32 = sizeof(EpiCtx)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -130,11 +133,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       : "memory");
 }
 // completion of every tcgen05 operation issued so far -> one arrival on `bar` in both CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(static_cast<uint16_t>(3))
-               : "memory");
+__device__ __forceinline__ void umma_commit_pair_if(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3)), "r"(leader)
+      : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -155,10 +160,10 @@ struct PairLite {
   int32_t N, Npad, stride, npanel;
   int64_t adj_off, node_off, panel_off;
 };
-// tile t of the chunk: tiles[t] = (pair, row block << 16 | column block); d follows the pair
-__device__ __forceinline__ void fetch_tile(int t, const uint2* __restrict__ tiles, const PairDesc* __restrict__ descs,
-                                           int& pair, PairLite& d, int& I0, int& J0) {
-  const uint2 e = tiles[t];
+// tile entry e = (pair, row block << 16 | column block); d follows the pair.  The roles load the entry of
+// their NEXT tile one tile ahead (a dependent L2 round trip per tile otherwise sits in front of every role).
+__device__ __forceinline__ void decode_tile(const uint2 e, const PairDesc* __restrict__ descs, int& pair, PairLite& d,
+                                            int& I0, int& J0) {
   if (static_cast<int>(e.x) != pair) {
     pair = static_cast<int>(e.x);
     const PairDesc* pd = descs + pair;
@@ -187,20 +192,34 @@ __device__ __forceinline__ void fetch_tile(int t, const uint2* __restrict__ tile
       "r"(kBias)                                                                                              \
       : "memory")
 
-// Per-warp state of the epilogue's rare path, kept in shared memory so that the out-of-line functions take
-// few arguments (every live register of the hot loop is spilled around a call).
+// 16 TMEM lanes x 32 columns in the accumulator-fragment layout (tcgen05.ld 16x256b.x4): with t4 = lane & 3,
+// t8 = lane >> 2, register 4 b + 2 rh + e holds lane (row) t8 + 8 rh, column 8 b + 2 t4 + e.  A thread then
+// owns 2 (4 with both lane halves) rows of each of its 8 columns: column sums need a quarter of the adds and
+// three shuffle levels instead of five.
+#define SACCOT_TMEM_LDF4(v, taddr)                                                                                   \
+  asm volatile(                                                                                                      \
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),  \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                      \
+      : "r"(taddr))
+
+// Per-warp state of the epilogue's rare path (edges that reach the pruning threshold), kept in shared memory:
+// it costs the hot loop no registers.
 struct EpiCtx {
   unsigned long long* keyp;       // the pair's key list
   unsigned long long* kcount;     // the pair's key counter
   uint32_t thb;                   // pruning threshold + kBias
-  uint32_t fill;                  // keys staged in the warp's buffer
+  uint32_t fill;                  // slots reserved in the warp's buffer (reservations past the end included)
+  uint32_t limit;                 // first reserved slot that was turned away (buffer full), else 0xFFFFFFFF
+  uint32_t pad_;
 };
+constexpr int kKeySlots = kKeyBuf + 16;  // a reservation (<= 16 keys) is taken if it STARTS below kKeyBuf
 
 // staged keys of one epilogue warp -> the pair's key list (one reservation, coalesced copy)
 __device__ __noinline__ void flush_keys(unsigned long long* kb, EpiCtx* ctx) {
   const int lane = threadIdx.x & 31;
   __syncwarp();
-  const uint32_t fill = ctx->fill;
+  const uint32_t fill = min(ctx->fill, ctx->limit);  // reservations are contiguous: [0, first one turned away)
   if (fill) {
     unsigned long long* keyp = ctx->keyp;
     unsigned long long base = 0;
@@ -208,60 +227,45 @@ __device__ __noinline__ void flush_keys(unsigned long long* kb, EpiCtx* ctx) {
     base = __shfl_sync(0xffffffffu, base, 0);
     for (uint32_t k = lane; k < fill; k += 32) keyp[base + k] = kb[k];
     __syncwarp();
-    if (lane == 0) ctx->fill = 0u;
+    if (lane == 0) {
+      ctx->fill = 0u;
+      ctx->limit = 0xFFFFFFFFu;
+    }
   }
   __syncwarp();
 }
 
-// Rare path of the epilogue: append the edges of one 32 x 16 chunk whose count reaches the threshold.  Out of
-// line (and re-reading its 16 TMEM columns) so that the hot loop stays small.  Few keys are staged in the
-// warp's shared-memory buffer; a dense chunk (no pruning, or no clique in the pair) goes straight to the
-// key list with one reservation for the whole chunk.  rowcol = row i << 16 | first column of the chunk.
-__device__ __noinline__ void emit_chunk(uint32_t taddr, uint32_t bits16, uint32_t rowcol, unsigned long long* kb,
-                                        EpiCtx* ctx, uint32_t* hist_s) {
-  const int lane = threadIdx.x & 31;
-  uint32_t v[16];
-  SACCOT_TMEM_LD16(v, taddr);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+// Rare path of the epilogue (with a tight theta): some of this thread's 16 masked values m (kBias + T) of a
+// fragment half reach the pruning threshold.  One slot reservation per thread in the warp's staging buffer
+// (shared-memory atomic); if the buffer is full the keys go straight to the pair's list.  lo0 = key bits of
+// the thread's first row and column, (0xFFFF - i) << 16 | (0xFFFF - j); fa / fb = edge bits of its two rows
+// (with theta = 0 a masked-off entry, kBias, passes the threshold test too).
+__device__ __forceinline__ void push16(const uint32_t (&m)[16], uint32_t fa, uint32_t fb, uint32_t lo0,
+                                       unsigned long long* kb, EpiCtx* ctx, uint32_t* hist_s) {
   const uint32_t thb = ctx->thb;
   uint32_t cand = 0;
 #pragma unroll
   for (int k = 0; k < 16; ++k)
-    if ((bits16 & (1u << k)) && v[k] >= thb) cand |= 1u << k;
-  const int nc = __popc(cand);
-  int incl = nc;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int u = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += u;
-  }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) return;
-  unsigned long long* dst;
-  uint32_t pos = static_cast<uint32_t>(incl - nc);
-  if (total > kKeyBuf / 2) {
-    unsigned long long base = 0;
-    if (lane == 31) base = atomicAdd(ctx->kcount, static_cast<unsigned long long>(total));
-    dst = ctx->keyp + __shfl_sync(0xffffffffu, base, 31);
+    if (m[k] >= thb && ((((k & 2) ? fb : fa) >> (8 * (k >> 2) + (k & 1))) & 1u)) cand |= 1u << k;
+  if (cand == 0) return;
+  const uint32_t nc = __popc(cand);
+  const uint32_t pos = atomicAdd(&ctx->fill, nc);
+  unsigned long long* dst;  // generic: shared (staging buffer) or global (key list)
+  if (pos < static_cast<uint32_t>(kKeyBuf)) {
+    dst = kb + pos;
   } else {
-    if (ctx->fill + static_cast<uint32_t>(total) > static_cast<uint32_t>(kKeyBuf)) flush_keys(kb, ctx);
-    const uint32_t fill = ctx->fill;
-    __syncwarp();
-    if (lane == 0) ctx->fill = fill + static_cast<uint32_t>(total);
-    dst = kb;
-    pos += fill;
+    atomicMin(&ctx->limit, pos);
+    dst = ctx->keyp + atomicAdd(ctx->kcount, static_cast<unsigned long long>(nc));
   }
-  const unsigned long long ikey = static_cast<unsigned long long>(0xFFFFu - (rowcol >> 16)) << 16;
-  const unsigned int jkey = 0xFFFFu - (rowcol & 0xFFFFu);
-#pragma unroll 4
+#pragma unroll
   for (int k = 0; k < 16; ++k) {
     if (cand & (1u << k)) {
-      const unsigned int T = v[k] - kBias;  // accumulators hold 2^23 + T
-      dst[pos++] = (static_cast<unsigned long long>(T) << 32) | ikey | static_cast<unsigned long long>(jkey - k);
+      const uint32_t T = m[k] - kBias;
+      const uint32_t lo = lo0 - ((static_cast<uint32_t>((k >> 1) & 1) * 8u) << 16) - static_cast<uint32_t>(8 * (k >> 2) + (k & 1));
+      *dst++ = (static_cast<unsigned long long>(T) << 32) | lo;
       atomicAdd(&hist_s[T >> 4], 1u);
     }
   }
-  __syncwarp();
 }
 
 }  // namespace
@@ -291,6 +295,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
   unsigned char* raw_base = smem_raw + kOffRaw;
   uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem_raw + kOffHist);
   unsigned long long* kbuf = reinterpret_cast<unsigned long long*>(smem_raw + kOffKeys);
+  uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem_raw + kOffWin);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kOffBars);
   uint64_t* full2 = bars;                                // [2] producers of both CTAs -> MMA (leader's copy); per stage pair
   uint64_t* empty2 = full2 + 2;                          // [2] MMA commit (multicast) -> producers; per stage pair
@@ -307,16 +312,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;  // cluster = CTA pair = one 256 x 240 tile at a time
 
   for (int k = tid; k < kHistBins; k += kThreads) hist_s[k] = 0;
-  if (tid < kEpiWarps) ectx[tid].fill = 0u;
+  if (tid < kEpiWarps) {
+    ectx[tid].fill = 0u;
+    ectx[tid].limit = 0xFFFFFFFFu;
+  }
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&full2[s], 8);  // two stages x two warps of each stage's group x two CTAs
+      mbar_init(&full2[s], 4 * kWarpsPerGroup);  // two stages x the warps of each stage's group x two CTAs
       mbar_init(&empty2[s], 1);
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 2 * kEpiWarps);
     }
     for (int s = 0; s < kRawStages; ++s) mbar_init(&raw_full[s], 1);
-    for (int s = 0; s < kRawStages / 2; ++s) mbar_init(&raw_empty2[s], 4);
+    for (int s = 0; s < kRawStages / 2; ++s) mbar_init(&raw_empty2[s], 2 * kWarpsPerGroup);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) {
@@ -352,10 +360,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
 
   if (warp < kEpiWarps) {
     // ================================== epilogue warps ==================================
-    // warp = 4 h + q: TMEM lanes 32 q .. 32 q + 31 (rows), columns 128 h .. (8 chunks of 16, or 7 for h = 1)
+    // warp = 4 h + q: TMEM lanes 32 q .. 32 q + 31 (rows), columns 128 h .. 128 h + 127 of the accumulator
+    // (h = 1: the last 16 lie outside the tile and are masked off), four units of 32 columns each.
     const int q = warp & 3, h = warp >> 2;
-    const int nch = h ? kMmaTileN / 16 - 8 : 8;
-    unsigned long long* kb = kbuf + warp * kKeyBuf;
+    const int t4 = lane & 3, t8 = lane >> 2;
+    unsigned long long* kb = kbuf + warp * kKeySlots;
     EpiCtx* ctx = ectx + warp;
     int cur_pair = -1, cur_bins = 0;
     uint32_t thb = kBias;
@@ -372,25 +381,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");
     };
-    // raw edge-bit window of this thread's row: 5 words starting at the word that holds column J0 + 128 h
-    auto load_window = [&](const PairLite& pd, int I0, int J0, uint32_t (&w)[5]) {
+    // Raw edge-bit window of this thread's row: 5 words starting at the word that holds column J0 + 128 h.
+    // Copied asynchronously into the thread's own slots of a double-buffered shared-memory area one tile
+    // ahead: as register loads the compiler spilled them right after issue, which exposed the full
+    // global-load latency on every tile.
+    uint32_t* wmine = wbuf + warp * (5 * 32) + lane;
+    auto load_window = [&](const PairLite& pd, int I0, int J0, int slot) {
       const int i = I0 + kCtaM * static_cast<int>(rank) + 32 * q + lane;
-      const uint32_t* rowp = adj + pd.adj_off + static_cast<size_t>(i) * pd.stride;
-      const int w0 = (J0 >> 5) + 4 * h;
       const bool row_ok = i < pd.Npad;
+      const uint32_t* rowp = adj + pd.adj_off + static_cast<size_t>(row_ok ? i : 0) * pd.stride;
+      const int w0 = (J0 >> 5) + 4 * h;
+      const uint32_t dst = smem_u32(wmine + slot * (kEpiWarps * 5 * 32));
 #pragma unroll
-      for (int k = 0; k < 5; ++k) w[k] = (row_ok && w0 + k < pd.stride) ? rowp[w0 + k] : 0u;
+      for (int k = 0; k < 5; ++k) {
+        const bool ok = row_ok && w0 + k < pd.stride;  // not ok: nothing is read, the slot is filled with zeros
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 128u * k), "l"(rowp + (ok ? w0 + k : 0)),
+                     "r"(ok ? 4u : 0u)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     int n = 0, pair = -1;
     PairLite d;
-    long long w_tfull = 0, t_ldw = 0, t_chunk = 0, t_emit = 0, t_pairchg = 0, t_win = 0, t_fetch = 0, t_tail = 0;
+    long long w_tfull = 0, t_ldw = 0, t_emit = 0, t_pairchg = 0, t_win = 0, t_fetch = 0, t_tail = 0;
     const long long t_begin = PROF ? clock64() : 0;
     int t = cid, I0 = 0, J0 = 0;
-    uint32_t wraw[5];
+    uint2 en = make_uint2(0u, 0u);  // entry of the tile after this one
     if (t < total_tiles) {
-      fetch_tile(t, tiles, descs, pair, d, I0, J0);
-      load_window(d, I0, J0, wraw);
+      decode_tile(tiles[t], descs, pair, d, I0, J0);
+      load_window(d, I0, J0, 0);
+      if (t + ncl < total_tiles) en = tiles[t + ncl];
     }
     for (; t < total_tiles; ++n) {
       // ---- this tile ----
@@ -412,6 +433,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       }
       const long long tq1 = PROF ? clock64() : 0;
       uint32_t win[4];
+      uint32_t wraw[5];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < 5; ++k) wraw[k] = wmine[(n & 1) * (kEpiWarps * 5 * 32) + 32 * k];
       if (tJ0 & 16) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) win[k] = __funnelshift_r(wraw[k], wraw[k + 1], 16);
@@ -420,7 +445,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         for (int k = 0; k < 4; ++k) win[k] = wraw[k];
       }
       if (h) win[3] &= 0xFFFFu;  // columns 240..255 of the window belong to the next J-block
-      const int i = I0 + kCtaM * static_cast<int>(rank) + 32 * q + lane;
+      const int rbase = I0 + kCtaM * static_cast<int>(rank) + 32 * q;  // first row of this warp
+      const int i = rbase + lane;
       const int cbase = tJ0 + 128 * h;  // first column of this warp's half
       {
         const int dd = i - cbase;  // keep j > i: clear window bits 0..dd
@@ -434,11 +460,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         }
       }
       const long long tq2 = PROF ? clock64() : 0;
-      // ---- next tile: look it up and start loading its window now (hidden behind this tile's work) ----
+      // ---- next tile: its entry arrived during the previous tile; start loading its window now (hidden
+      //      behind this tile's work) and fetch the entry of the tile after it ----
       t += ncl;
       if (t < total_tiles) {
-        fetch_tile(t, tiles, descs, pair, d, I0, J0);
-        load_window(d, I0, J0, wraw);
+        decode_tile(en, descs, pair, d, I0, J0);
+        load_window(d, I0, J0, (n + 1) & 1);
+        if (t + ncl < total_tiles) en = tiles[t + ncl];
       }
 
       const long long tq3 = PROF ? clock64() : 0;
@@ -452,48 +480,90 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       SACCOT_TIMED_WAIT(w_tfull, mbar_wait_wd(&tmem_full[buf], static_cast<uint32_t>((n >> 1) & 1), 1, n));
       asm volatile("tcgen05.fence::after_thread_sync;");
       const uint32_t tbase = tmem + ((32u * q) << 16) + static_cast<uint32_t>(kMmaTileN * buf + 128 * h);
-      uint32_t rsum = 0;  // row sum of this tile half, biased: + 16 kBias per chunk (mod 2^32)
+      // biased row sums of the four fragment rows t8 + 8 s of this thread (32 values each per tile)
+      uint32_t rs0 = 0, rs1 = 0, rs2 = 0, rs3 = 0;
       uint32_t v[2][16];
-      // One 16-column chunk.  Kept small and NOT unrolled over the chunks: the fully unrolled epilogue was
-      // 120 KB of straight-line code and spent most of its time in instruction-cache misses.
-      auto chunk16 = [&](const uint32_t(&vc)[16], uint32_t bits16, int c) {
-        // masked counts, biased: kBias + T where there is an edge j > i, kBias elsewhere
+      // 16 rows x 32 columns in fragment layout: masked values (kBias + T on an edge j > i, kBias elsewhere),
+      // row sums, the sums of this thread's two rows per column.  lo0 = key bits of (row t8 of the half, column
+      // 2 t4 of the unit): (0xFFFF - i) << 16 | (0xFFFF - j).
+      auto half16 = [&](const uint32_t(&vv)[16], uint32_t fa, uint32_t fb, uint32_t& ra, uint32_t& rb, uint32_t(&c)[8],
+                        uint32_t lo0, bool first) {
         uint32_t m[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) m[k] = (bits16 & (1u << k)) ? vc[k] : kBias;
-        rsum += ((m[0] + m[1] + m[2]) + (m[3] + m[4] + m[5])) + ((m[6] + m[7] + m[8]) + (m[9] + m[10] + m[11])) +
-                ((m[12] + m[13]) + (m[14] + m[15]));
-        const uint32_t vmax = max(max(max(m[0], m[1]), max(m[2], m[3])), max(max(m[4], m[5]), max(m[6], m[7])));
-        const uint32_t vmax2 = max(max(max(m[8], m[9]), max(m[10], m[11])), max(max(m[12], m[13]), max(m[14], m[15])));
-        const bool hit = __any_sync(0xffffffffu, max(vmax, vmax2) >= thb);
-        // column sums (t2_j): one warp reduction per column (16 independent REDUX), lane k keeps column k
-        uint32_t cs = 0;
+        for (int b = 0; b < 4; ++b)
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const uint32_t r = __reduce_add_sync(0xffffffffu, m[k]) - 32u * kBias;
-          if (lane == k) cs = r;
+          for (int e = 0; e < 2; ++e) {
+            m[4 * b + e] = ((fa >> (8 * b + e)) & 1u) ? vv[4 * b + e] : kBias;
+            m[4 * b + 2 + e] = ((fb >> (8 * b + e)) & 1u) ? vv[4 * b + 2 + e] : kBias;
+          }
+        ra += ((m[0] + m[1] + m[4]) + (m[5] + m[8] + m[9])) + (m[12] + m[13]);
+        rb += ((m[2] + m[3] + m[6]) + (m[7] + m[10] + m[11])) + (m[14] + m[15]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const uint32_t cc = m[4 * b + e] + m[4 * b + 2 + e];
+            c[2 * b + e] = first ? cc : c[2 * b + e] + cc;
+          }
+        const uint32_t a = max(max(max(m[0], m[1]), max(m[2], m[3])), max(max(m[4], m[5]), max(m[6], m[7])));
+        const uint32_t bb = max(max(max(m[8], m[9]), max(m[10], m[11])), max(max(m[12], m[13]), max(m[14], m[15])));
+        // rare (with a tight theta): one of this thread's 16 edges reaches the pruning threshold
+        if (max(a, bb) >= thb) {
+          const long long te0 = PROF ? clock64() : 0;
+          push16(m, fa, fb, lo0, kb, ctx, hist_s);
+          if (PROF) t_emit += clock64() - te0;
         }
-        if (cs) atomicAdd(&t2[node_off + cbase + 16 * c + lane], static_cast<unsigned long long>(cs));
-        // rare (with a tight theta): some edge of these 32 x 16 entries reaches the pruning threshold
-        if (hit)
-          SACCOT_TIMED_WAIT(t_emit, emit_chunk(tbase + 16u * c, bits16,
-                                               (static_cast<uint32_t>(i) << 16) | static_cast<uint32_t>(cbase + 16 * c), kb, ctx,
-                                               hist_s));
-        // the columns go back to 2^23 for the tile after next
-        SACCOT_TMEM_ST16_BIAS(tbase + 16u * c);
       };
       if (!(dbg & 1)) {
-        SACCOT_TMEM_LD16(v[0], tbase);
+        SACCOT_TMEM_LDF4(v[0], tbase);
 #pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
+        for (int u = 0; u < 4; ++u) {
+          // edge bits of the four fragment rows for these 32 columns, aligned to this thread's columns
+          const uint32_t wown = win[0];
+          const uint32_t f0 = __shfl_sync(0xffffffffu, wown, t8) >> (2 * t4);
+          const uint32_t f1 = __shfl_sync(0xffffffffu, wown, t8 + 8) >> (2 * t4);
+          const uint32_t f2 = __shfl_sync(0xffffffffu, wown, t8 + 16) >> (2 * t4);
+          const uint32_t f3 = __shfl_sync(0xffffffffu, wown, t8 + 24) >> (2 * t4);
+          uint32_t c[8];
+          const uint32_t lo0 = ((0xFFFFu - static_cast<uint32_t>(rbase + t8)) << 16) |
+                               (0xFFFFu - static_cast<uint32_t>(cbase + 32 * u + 2 * t4));
           SACCOT_TIMED_WAIT(t_ldw, asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"));
-          if (c + 1 < nch) SACCOT_TMEM_LD16(v[1], tbase + 16u * (c + 1));
-          SACCOT_TIMED_WAIT(t_chunk, chunk16(v[0], win[0] & 0xFFFFu, c));
-          if (c + 1 < nch) {
-            SACCOT_TIMED_WAIT(t_ldw, asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"));
-            if (c + 2 < nch) SACCOT_TMEM_LD16(v[0], tbase + 16u * (c + 2));
-            SACCOT_TIMED_WAIT(t_chunk, chunk16(v[1], win[0] >> 16, c + 1));
+          SACCOT_TMEM_LDF4(v[1], tbase + (16u << 16) + 32u * u);
+          half16(v[0], f0, f1, rs0, rs1, c, lo0, true);
+          SACCOT_TIMED_WAIT(t_ldw, asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"));
+          if (u + 1 < 4) SACCOT_TMEM_LDF4(v[0], tbase + 32u * (u + 1));
+          half16(v[1], f2, f3, rs2, rs3, c, lo0 - (16u << 16), false);
+          // column sums (t2_j): c[2 b + e] covers 4 of the 32 rows; reduce-scatter over the lanes that share t4
+          {
+            const bool hi = (lane & 16) != 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t send = hi ? c[k] : c[k + 4], keep = hi ? c[k + 4] : c[k];
+              c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
           }
+          {
+            const bool hi = (lane & 8) != 0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t send = hi ? c[k] : c[k + 2], keep = hi ? c[k + 2] : c[k];
+              c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+          }
+          {
+            const bool hi = (lane & 4) != 0;
+            const uint32_t send = hi ? c[0] : c[1], keep = hi ? c[1] : c[0];
+            // 32 rows x kBias = 0x60000000 (mod 2^32); the thread ends up with column 2 b + e = t8
+            const uint32_t cs = keep + __shfl_xor_sync(0xffffffffu, send, 4) - 32u * kBias;
+            if (cs)
+              atomicAdd(&t2[node_off + cbase + 32 * u + 8 * (t8 >> 1) + 2 * t4 + (t8 & 1)], static_cast<unsigned long long>(cs));
+          }
+          // staged keys: drain the buffer once it is half full (warp-uniform: every push happened before the barrier)
+          __syncwarp();
+          if (ctx->fill >= static_cast<uint32_t>(kKeyBuf / 2)) flush_keys(kb, ctx);
+          // the columns go back to 2^23 for the tile after next (h = 1: the last 16 are not this tile's)
+          SACCOT_TMEM_ST16_BIAS(tbase + 32u * u);
+          if (!(h && u == 3)) SACCOT_TMEM_ST16_BIAS(tbase + 32u * u + 16u);
           win[0] = win[1];  // next 32 columns of the window
           win[1] = win[2];
           win[2] = win[3];
@@ -505,15 +575,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0u);
-      const uint32_t rowsum = rsum - static_cast<uint32_t>(nch) * 16u * kBias;
-      if (rowsum && !(dbg & 1)) atomicAdd(&t2[node_off + i], static_cast<unsigned long long>(rowsum));
+      if (!(dbg & 1)) {
+        // row sums (t2_i): reduce-scatter over the four lanes that share t8; the thread ends up with row t8 + 8 t4
+        const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
+        const uint32_t a0 = (hi2 ? rs2 : rs0) + __shfl_xor_sync(0xffffffffu, hi2 ? rs0 : rs2, 2);
+        const uint32_t a1 = (hi2 ? rs3 : rs1) + __shfl_xor_sync(0xffffffffu, hi2 ? rs1 : rs3, 2);
+        // 128 values x kBias = 0x80000000 (mod 2^32)
+        const uint32_t rowsum = (hi1 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi1 ? a0 : a1, 1) - 128u * kBias;
+        if (rowsum) atomicAdd(&t2[node_off + rbase + t8 + 8 * t4], static_cast<unsigned long long>(rowsum));
+      }
       if (PROF) t_tail += clock64() - tq4;
     }
     if (cur_pair >= 0) flush_pair();
     if (PROF && blockIdx.x < 2 && tid == 0)
-      printf("cta %d epilogue: tiles %d total %lld wait_tmem_full %lld wait_ld %lld chunks %lld (emit %lld) pairchg %lld win %lld "
+      printf("cta %d epilogue: tiles %d total %lld wait_tmem_full %lld wait_ld %lld emit %lld pairchg %lld win %lld "
              "fetch %lld tail %lld\n",
-             blockIdx.x, n, clock64() - t_begin, w_tfull, t_ldw, t_chunk, t_emit, t_pairchg, t_win, t_fetch, t_tail);
+             blockIdx.x, n, clock64() - t_begin, w_tfull, t_ldw, t_emit, t_pairchg, t_win, t_fetch, t_tail);
   } else if (warp == kMmaWarp) {
     // ================================== MMA issuer (leader CTA only) ==================================
     // One barrier wait and one commit per PAIR of stages: the issuing thread (not the tensor pipe) was the
@@ -526,10 +603,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       int pair = -1, n = 0;
       uint32_t g = 0;
       PairLite d;
+      uint32_t leader;  // 1 in the one lane that issues the tensor-core instructions
+      asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(leader));
       long long w_full = 0, w_tempty = 0, t_begin = PROF ? clock64() : 0;
+      uint2 en = cid < total_tiles ? tiles[cid] : make_uint2(0u, 0u);
       for (int t = cid; t < total_tiles; t += ncl, ++n) {
         int I0, J0;
-        fetch_tile(t, tiles, descs, pair, d, I0, J0);
+        const uint2 e = en;
+        if (t + ncl < total_tiles) en = tiles[t + ncl];
+        decode_tile(e, descs, pair, d, I0, J0);
         const int np2 = (d.npanel + 1) >> 1;  // stage pairs (an odd last stage is padded with zeros)
         const int buf = n & 1;
         if (n >= 2) {
@@ -540,23 +622,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
           const uint32_t pr = (g >> 1) & 1u;
           SACCOT_TIMED_WAIT(w_full, mbar_wait_wd(&full2[pr], (g >> 2) & 1u, 3, g));
           asm volatile("tcgen05.fence::after_thread_sync;");
-          if (lane == 0) {
-            // shared-memory descriptors: only the 14-bit start-address field (16-byte units) changes
-            const uint32_t lo0 = desc_lo + pr * ((2 * kStageBytes) >> 4);
+          // Every lane runs this code and one elected lane issues: inside an `if (lane == 0)` branch the
+          // compiler paid an ELECT + PLOP3 + R2UR.BROADCAST sequence per operand, ~17 instructions per MMA
+          // (now ~11), which made the issuing thread as slow as the tensor pipe itself.
+          // shared-memory descriptors: only the 14-bit start-address field (16-byte units) changes
+          const uint32_t lo0 = desc_lo + pr * ((2 * kStageBytes) >> 4);
 #pragma unroll
-            for (int ks = 0; ks < 2 * kStageK / 64; ++ks) {
-              const uint32_t loA = lo0 + static_cast<uint32_t>(((ks >> 2) * kStageBytes + (ks & 3) * 2 * kLBO) >> 4);
-              const uint32_t loB = loA + static_cast<uint32_t>(((kCtaM / 8) * kSBO) >> 4);
-              asm volatile(
-                  "{\n.reg .b64 da, db;\n.reg .pred p;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n"
-                  "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], da, db, %4, [%6], [%7], p;\n}" ::"r"(
-                      tmem + static_cast<uint32_t>(kMmaTileN * buf)),
-                  "r"(loA), "r"(loB), "r"(desc_hi), "r"(idesc), "r"(1u), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 16u)
-                  : "memory");
-            }
-            umma_commit_pair(&empty2[pr]);                         // both stages reusable in both CTAs
-            if (ip == np2 - 1) umma_commit_pair(&tmem_full[buf]);  // accumulators complete in both CTAs
+          for (int ks = 0; ks < 2 * kStageK / 64; ++ks) {
+            const uint32_t loA = lo0 + static_cast<uint32_t>(((ks >> 2) * kStageBytes + (ks & 3) * 2 * kLBO) >> 4);
+            const uint32_t loB = loA + static_cast<uint32_t>(((kCtaM / 8) * kSBO) >> 4);
+            asm volatile(
+                "{\n.reg .b64 da, db;\n.reg .pred p, q;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
+                "setp.ne.b32 q, %5, 0;\nsetp.eq.u32 p, 1, 1;\n"
+                "@q tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], da, db, %4, [%6], [%7], p;\n}" ::"r"(
+                    tmem + static_cast<uint32_t>(kMmaTileN * buf)),
+                "r"(loA), "r"(loB), "r"(desc_hi), "r"(idesc), "r"(leader), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 16u)
+                : "memory");
           }
+          umma_commit_pair_if(&empty2[pr], leader);                         // both stages reusable in both CTAs
+          if (ip == np2 - 1) umma_commit_pair_if(&tmem_full[buf], leader);  // accumulators complete in both CTAs
           __syncwarp();
         }
       }
@@ -572,9 +656,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       uint32_t g = 0;
       PairLite d;
       long long w_rempty = 0, t_begin = PROF ? clock64() : 0;
+      uint2 en = cid < total_tiles ? tiles[cid] : make_uint2(0u, 0u);
       for (int t = cid; t < total_tiles; t += ncl) {
         int I0, J0;
-        fetch_tile(t, tiles, descs, pair, d, I0, J0);
+        const uint2 e = en;
+        if (t + ncl < total_tiles) en = tiles[t + ncl];
+        decode_tile(e, descs, pair, d, I0, J0);
         const int a0 = I0 + kCtaM * static_cast<int>(rank), b0 = J0 + kCtaNB * static_cast<int>(rank);
         const uint32_t bytesA = a0 < d.Npad ? kRawABytes : 0u;  // Npad is a multiple of 128
         const uint32_t bytesB = static_cast<uint32_t>(max(0, min(kCtaNB, d.Npad - b0))) * 32u;
@@ -602,19 +689,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     }
   } else {
     // ================================== expansion warps ==================================
-    // Stage g is expanded by group g % kGroupsP (two warps, eight 16-row tasks each): the fixed cost of a
-    // stage hand-over (two barrier waits, proxy fence, two arrivals; ~350 cycles measured) is paid once
-    // per kGroupsP stages by every warp instead of once per stage.
+    // Stage g is expanded by group g % kGroupsP (kWarpsPerGroup warps, kTasksPerWarp 16-row tasks each).  The
+    // stages are handed to the MMA issuer in pairs, so with two groups all eight warps work on the pair that was
+    // just released: with four groups of two warps only half of them did, a refill (~870 cycles of stores plus
+    // ~350 of hand-over) took longer than the MMAs of the other pair (1008 cycles) and the tensor pipe waited
+    // on `full` for 46 % of the time.
     const int pw = warp - kProdWarp0;
-    const int grp = pw >> 1, half = pw & 1;
+    const int grp = pw / kWarpsPerGroup, wq = pw % kWarpsPerGroup;
     const int r8 = lane & 7, rg2 = (lane >> 3) & 1, q = lane >> 4;
     uint32_t g = 0;
     int pair = -1;
     PairLite d;
     long long w_rfull = 0, w_empty = 0, t_sts = 0, t_fence = 0, t_arr = 0, t_begin = PROF ? clock64() : 0;
+    uint2 en = cid < total_tiles ? tiles[cid] : make_uint2(0u, 0u);
     for (int t = cid; t < total_tiles; t += ncl) {
       int I0, J0;
-      fetch_tile(t, tiles, descs, pair, d, I0, J0);
+      const uint2 e = en;
+      if (t + ncl < total_tiles) en = tiles[t + ncl];
+      decode_tile(e, descs, pair, d, I0, J0);
       const int a0 = I0 + kCtaM * static_cast<int>(rank), b0 = J0 + kCtaNB * static_cast<int>(rank);
       // rows past the end of the pair were not copied: they expand to zeros
       const int rowsA = a0 < d.Npad ? kCtaM : 0, rowsB = max(0, min(kCtaNB, d.Npad - b0));
@@ -628,7 +720,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         uint4 w[kTasksPerWarp];
 #pragma unroll
         for (int k = 0; k < kTasksPerWarp; ++k) {
-          const int gr = 2 * (half + 2 * k) + rg2;  // 8-row group of this lane
+          const int gr = 2 * (wq + kWarpsPerGroup * k) + rg2;  // 8-row group of this lane
           const int r = 8 * gr + r8;
           const bool ok = real && gr < kGroups && (r < kCtaM ? r < rowsA : r - kCtaM < rowsB);
           w[k] = ok ? *reinterpret_cast<const uint4*>(raw + r * 32 + q * 16) : make_uint4(0u, 0u, 0u, 0u);
@@ -638,7 +730,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         const long long tp0 = PROF ? clock64() : 0;
 #pragma unroll
         for (int k = 0; k < kTasksPerWarp; ++k) {
-          const int gr = 2 * (half + 2 * k) + rg2;
+          const int gr = 2 * (wq + kWarpsPerGroup * k) + rg2;
           if (gr < kGroups) expand_quad(w[k], st + gr * kSBO + 4 * q * kLBO + r8 * 16);
         }
         const long long tp1 = PROF ? clock64() : 0;
@@ -838,7 +930,7 @@ int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint
                          const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
                          unsigned long long* d_keys, const uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
                          int dbg) {
-  const int grid = 2 * std::min(total_tiles, lc.sm_count / 2);  // CTA pairs
+  const int grid = 2 * mma_clusters(total_tiles, lc.sm_count);  // CTA pairs
   if (grid > 0) {
     if (dbg & 64)
       triangles_mma_kernel<true><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_adj, d_panel,
