@@ -39,29 +39,26 @@ namespace {
 
 constexpr int kEpiWarps = 8;                          // warps 0..7: TMEM lane quadrant = warp & 3, column half = warp >> 2
 constexpr int kMmaWarp = 8;
-constexpr int kTmaWarp = 9;
-constexpr int kProdWarp0 = 10;
-constexpr int kProducerWarps = 8;                     // warps 10..17
-constexpr int kThreads = 32 * (kProdWarp0 + kProducerWarps);  // 576
+constexpr int kProdWarp0 = 9;
+constexpr int kProducerWarps = 6;                     // warps 9..14: 15 warps => 128 registers per thread
+constexpr int kThreads = 32 * (kProdWarp0 + kProducerWarps);  // 480
 constexpr int kCtaM = 128;                            // rows of the pair tile owned by one CTA (one TMEM lane each)
 constexpr int kCtaNB = kMmaTileN / 2;                 // 120 rows of the B operand staged by one CTA
 constexpr int kStageK = 256;                          // K elements (adjacency columns) per stage
-constexpr int kStages = 4;                            // expanded operand stages (handed over in pairs)
-constexpr int kRawStages = 8;                         // raw (bit) stages
+constexpr int kStages = 6;                            // expanded operand stages (handed over in pairs)
+constexpr int kPairs = kStages / 2;
 constexpr int kRows = kCtaM + kCtaNB;                 // 248 rows expanded per stage and CTA
 constexpr int kGroups = kRows / 8;                    // 31 groups of 8 rows
 constexpr int kLBO = 128;                             // next 16-byte K chunk (core matrices contiguous along K)
 constexpr int kSBO = (kStageK / 2 / 16) * 128;        // next 8-row group: 8 core matrices = 1024 B
 constexpr int kStageBytes = kGroups * kSBO;           // 31744
-constexpr int kRawBytes = kRows * 32;                 // 7936
-constexpr int kRawABytes = kCtaM * 32;                // 4096
 constexpr int kWarpsPerGroup = 2;                     // producer warps that share a stage
 constexpr int kGroupsP = kProducerWarps / kWarpsPerGroup;  // producer groups; group = stage % kGroupsP
 constexpr int kTasksPerWarp = 16 / kWarpsPerGroup;    // 16 warp tasks (16 rows x 2 quads) per stage, the last one half
 // A group must meet every phase of the barriers it waits on in order (mbarrier waits only know the phase
 // parity: a waiter two phases early passes at once).  With the group count dividing both ring sizes, a
 // group always returns to the same slots.
-static_assert(kStages % kGroupsP == 0 && kRawStages % kGroupsP == 0, "producer groups must divide the ring sizes");
+static_assert(kStages % kGroupsP == 0, "producer groups must divide the ring size");
 constexpr int kKeyBuf = 128;                          // staged keys per epilogue warp
 constexpr uint32_t kSfCol = 480;                      // scale factors: TMEM columns [480, 512)
 constexpr uint32_t kSfWord = 0x807F807Fu;             // UE8M0 per K block of 32: {1.0, 2.0, 1.0, 2.0}
@@ -71,14 +68,13 @@ constexpr uint32_t kSfWord = 0x807F807Fu;             // UE8M0 per K block of 32
 constexpr uint32_t kBias = 0x4B000000u;
 
 // shared-memory carve-up (dynamic)
-constexpr int kOffRaw = kStages * kStageBytes;                    // 126976
-constexpr int kOffHist = kOffRaw + kRawStages * kRawBytes;        // +63488
+constexpr int kOffHist = kStages * kStageBytes;                   // 190464
 constexpr int kOffKeys = kOffHist + kHistBins * 4;                // +16384
 constexpr int kOffWin = kOffKeys + kEpiWarps * (kKeyBuf + 16) * 8;  // +9216
 constexpr int kWinBytes = 2 * kEpiWarps * 5 * 32 * 4;             // edge-bit windows [2][warp][5][lane]
 constexpr int kOffBars = kOffWin + kWinBytes;                     // +10240
-// barriers: full2[2] empty2[2] raw_full[8] raw_empty2[4] tmem_full[2] tmem_empty[2]
-constexpr int kNumBars = 2 + 2 + kRawStages + kRawStages / 2 + 2 + 2;
+// barriers: full2[kPairs] empty2[kPairs] tmem_full[2] tmem_empty[2]
+constexpr int kNumBars = 2 * kPairs + 2 + 2;
 constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + kEpiWarps * 32;  // 32 = sizeof(EpiCtx)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
@@ -91,9 +87,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return d;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // Barrier wait with a watchdog: a protocol bug must end the kernel with an error, not hang the GPU.
 // Default (CTA-scope) semantics also for barriers that peer-CTA threads arrive on, as in CUTLASS's
 // ClusterBarrier: cluster-scope release/acquire compiles to MEMBAR.ALL.GPU / CCTL.IVALL per arrival
@@ -292,16 +285,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
   if (chunk->overflow || !chunk->use_tensor) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stage_base = smem_raw;
-  unsigned char* raw_base = smem_raw + kOffRaw;
   uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem_raw + kOffHist);
   unsigned long long* kbuf = reinterpret_cast<unsigned long long*>(smem_raw + kOffKeys);
   uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem_raw + kOffWin);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kOffBars);
-  uint64_t* full2 = bars;                                // [2] producers of both CTAs -> MMA (leader's copy); per stage pair
-  uint64_t* empty2 = full2 + 2;                          // [2] MMA commit (multicast) -> producers; per stage pair
-  uint64_t* raw_full = empty2 + 2;                       // [kRawStages] bulk copies -> producers
-  uint64_t* raw_empty2 = raw_full + kRawStages;          // [kRawStages/2] producers -> bulk-copy issuer; per stage pair
-  uint64_t* tmem_full = raw_empty2 + kRawStages / 2;     // [2] MMA commit (multicast) -> epilogue
+  uint64_t* full2 = bars;                                // [kPairs] producers of both CTAs -> MMA (leader's copy); per stage pair
+  uint64_t* empty2 = full2 + kPairs;                     // [kPairs] MMA commit (multicast) -> producers; per stage pair
+  uint64_t* tmem_full = empty2 + kPairs;                 // [2] MMA commit (multicast) -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;                  // [2] epilogue warps of both CTAs -> MMA (leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   EpiCtx* ectx = reinterpret_cast<EpiCtx*>(tmem_slot + 4);  // [kEpiWarps] rare-path state of the epilogue warps
@@ -317,14 +307,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     ectx[tid].limit = 0xFFFFFFFFu;
   }
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kPairs; ++s) {
       mbar_init(&full2[s], 4 * kWarpsPerGroup);  // two stages x the warps of each stage's group x two CTAs
       mbar_init(&empty2[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 2 * kEpiWarps);
     }
-    for (int s = 0; s < kRawStages; ++s) mbar_init(&raw_full[s], 1);
-    for (int s = 0; s < kRawStages / 2; ++s) mbar_init(&raw_empty2[s], 2 * kWarpsPerGroup);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) {
@@ -619,8 +609,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
           asm volatile("tcgen05.fence::after_thread_sync;");
         }
         for (int ip = 0; ip < np2; ++ip, g += 2) {
-          const uint32_t pr = (g >> 1) & 1u;
-          SACCOT_TIMED_WAIT(w_full, mbar_wait_wd(&full2[pr], (g >> 2) & 1u, 3, g));
+          const uint32_t pr = (g >> 1) % kPairs;
+          SACCOT_TIMED_WAIT(w_full, mbar_wait_wd(&full2[pr], (g / kStages) & 1u, 3, g));
           asm volatile("tcgen05.fence::after_thread_sync;");
           // Every lane runs this code and one elected lane issues: inside an `if (lane == 0)` branch the
           // compiler paid an ELECT + PLOP3 + R2UR.BROADCAST sequence per operand, ~17 instructions per MMA
@@ -649,110 +639,116 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
                w_full, w_tempty);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-  } else if (warp == kTmaWarp) {
-    // ================================== bulk-copy issuer ==================================
-    if (lane == 0) {
-      int pair = -1;
-      uint32_t g = 0;
-      PairLite d;
-      long long w_rempty = 0, t_begin = PROF ? clock64() : 0;
-      uint2 en = cid < total_tiles ? tiles[cid] : make_uint2(0u, 0u);
-      for (int t = cid; t < total_tiles; t += ncl) {
-        int I0, J0;
-        const uint2 e = en;
-        if (t + ncl < total_tiles) en = tiles[t + ncl];
-        decode_tile(e, descs, pair, d, I0, J0);
-        const int a0 = I0 + kCtaM * static_cast<int>(rank), b0 = J0 + kCtaNB * static_cast<int>(rank);
-        const uint32_t bytesA = a0 < d.Npad ? kRawABytes : 0u;  // Npad is a multiple of 128
-        const uint32_t bytesB = static_cast<uint32_t>(max(0, min(kCtaNB, d.Npad - b0))) * 32u;
-        const uint32_t* pp = panel + d.panel_off;
-        const int np2 = (d.npanel + 1) >> 1;
-        for (int ip = 0; ip < np2; ++ip, g += 2) {
-          const uint32_t rp = (g % kRawStages) >> 1;
-          if (g >= kRawStages) SACCOT_TIMED_WAIT(w_rempty, mbar_wait_wd(&raw_empty2[rp], ((g / kRawStages) - 1) & 1u, 4, g));
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int it = 2 * ip + e;
-            const uint32_t rs = 2 * rp + e;
-            unsigned char* dst = raw_base + rs * kRawBytes;
-            const bool real = it < d.npanel;  // the padding stage of an odd panel count carries no data
-            const uint32_t nA = real ? bytesA : 0u, nB = real ? bytesB : 0u;
-            const uint32_t* src = pp + static_cast<size_t>(it) * d.Npad * 8;
-            mbar_arrive_expect_tx(&raw_full[rs], nA + nB);
-            if (nA) bulk_g2s(dst, src + static_cast<size_t>(a0) * 8, nA, &raw_full[rs]);
-            if (nB) bulk_g2s(dst + kRawABytes, src + static_cast<size_t>(b0) * 8, nB, &raw_full[rs]);
-          }
-        }
-      }
-      if (PROF && blockIdx.x < 2)
-        printf("cta %d bulk-copy issuer: stages %u total %lld wait_raw_empty %lld\n", blockIdx.x, g, clock64() - t_begin, w_rempty);
-    }
   } else {
     // ================================== expansion warps ==================================
-    // Stage g is expanded by group g % kGroupsP (kWarpsPerGroup warps, kTasksPerWarp 16-row tasks each).  The
-    // stages are handed to the MMA issuer in pairs, so with two groups all eight warps work on the pair that was
-    // just released: with four groups of two warps only half of them did, a refill (~870 cycles of stores plus
-    // ~350 of hand-over) took longer than the MMAs of the other pair (1008 cycles) and the tensor pipe waited
-    // on `full` for 46 % of the time.
+    // Stage g is expanded by group g % kGroupsP (kWarpsPerGroup warps, kTasksPerWarp 16-row tasks each): the
+    // fixed cost of a stage hand-over (barrier wait, proxy fence, arrival; ~350 cycles measured) is paid once
+    // per kGroupsP stages by every warp instead of once per stage.
+    // The raw adjacency bits come straight from the K-panel copy in L2 into registers, one group-stage ahead
+    // (two register sets, loop unrolled by two).  An earlier version staged them in shared memory with bulk
+    // copies; the kernel is bound by shared-memory bandwidth (operand stores 31.7 KB + tensor-core operand reads
+    // 31.7 KB per stage and SM against 128 B/clk), and the raw ring added a quarter to that traffic.
     const int pw = warp - kProdWarp0;
     const int grp = pw / kWarpsPerGroup, wq = pw % kWarpsPerGroup;
     const int r8 = lane & 7, rg2 = (lane >> 3) & 1, q = lane >> 4;
-    uint32_t g = 0;
-    int pair = -1;
-    PairLite d;
-    long long w_rfull = 0, w_empty = 0, t_sts = 0, t_fence = 0, t_arr = 0, t_begin = PROF ? clock64() : 0;
-    uint2 en = cid < total_tiles ? tiles[cid] : make_uint2(0u, 0u);
-    for (int t = cid; t < total_tiles; t += ncl) {
-      int I0, J0;
-      const uint2 e = en;
-      if (t + ncl < total_tiles) en = tiles[t + ncl];
-      decode_tile(e, descs, pair, d, I0, J0);
+    long long w_empty = 0, t_sts = 0, t_fence = 0, t_arr = 0, t_begin = PROF ? clock64() : 0;
+    // ---- load cursor: the group's next stage (tile lt, stage lit of it) ----
+    int lt = cid, lit = grp, lnp = 0, lnpanel = 0, lNpad = 0, rowsA = 0, rowsB = 0, lpair = -1;
+    const uint4* lbase = nullptr;  // the pair's K-panel copy
+    const uint4* lsrcA = nullptr;  // panel 0, row a0 (+ this lane's quad)
+    const uint4* lsrcB = nullptr;  // panel 0, row b0 (+ this lane's quad)
+    uint2 len = make_uint2(0u, 0u);
+    auto enter_tile = [&](const uint2 e) {  // tile lt
+      if (static_cast<int>(e.x) != lpair) {
+        lpair = static_cast<int>(e.x);
+        const PairDesc* pd = descs + lpair;
+        lNpad = pd->Npad;
+        lnpanel = pd->npanel;
+        lnp = (lnpanel + 1) & ~1;
+        lbase = reinterpret_cast<const uint4*>(panel + pd->panel_off);
+      }
+      const int I0 = static_cast<int>(e.y >> 16) * kMmaTileM, J0 = static_cast<int>(e.y & 0xFFFFu) * kMmaTileN;
       const int a0 = I0 + kCtaM * static_cast<int>(rank), b0 = J0 + kCtaNB * static_cast<int>(rank);
-      // rows past the end of the pair were not copied: they expand to zeros
-      const int rowsA = a0 < d.Npad ? kCtaM : 0, rowsB = max(0, min(kCtaNB, d.Npad - b0));
-      const int np = (d.npanel + 1) & ~1;
-      for (int it = 0; it < np; ++it, ++g) {
-        if (static_cast<int>(g % kGroupsP) != grp) continue;
-        const uint32_t rs = g % kRawStages, s = g % kStages;
-        SACCOT_TIMED_WAIT(w_rfull, mbar_wait_wd(&raw_full[rs], (g / kRawStages) & 1u, 5, g));
-        const unsigned char* raw = raw_base + rs * kRawBytes;
-        const bool real = it < d.npanel;
-        uint4 w[kTasksPerWarp];
-#pragma unroll
-        for (int k = 0; k < kTasksPerWarp; ++k) {
-          const int gr = 2 * (wq + kWarpsPerGroup * k) + rg2;  // 8-row group of this lane
-          const int r = 8 * gr + r8;
-          const bool ok = real && gr < kGroups && (r < kCtaM ? r < rowsA : r - kCtaM < rowsB);
-          w[k] = ok ? *reinterpret_cast<const uint4*>(raw + r * 32 + q * 16) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (g >= kStages) SACCOT_TIMED_WAIT(w_empty, mbar_wait_wd(&empty2[s >> 1], ((g / kStages) - 1) & 1u, 6, g));
-        unsigned char* st = stage_base + s * kStageBytes;
-        const long long tp0 = PROF ? clock64() : 0;
-#pragma unroll
-        for (int k = 0; k < kTasksPerWarp; ++k) {
-          const int gr = 2 * (wq + kWarpsPerGroup * k) + rg2;
-          if (gr < kGroups) expand_quad(w[k], st + gr * kSBO + 4 * q * kLBO + r8 * 16);
-        }
-        const long long tp1 = PROF ? clock64() : 0;
-        // generic-proxy writes -> visible to the tensor cores (async proxy), then one arrival per warp on the
-        // leader's barrier: its MMAs read this CTA's stage too
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        const long long tp2 = PROF ? clock64() : 0;
-        if (lane == 0) {
-          mbar_arrive_cluster(&full2[s >> 1], 0u);
-          mbar_arrive(&raw_empty2[rs >> 1]);
-        }
-        if (PROF) {
-          t_sts += tp1 - tp0;
-          t_fence += tp2 - tp1;
-          t_arr += clock64() - tp2;
+      // rows past the end of the pair expand to zeros
+      rowsA = a0 < lNpad ? kCtaM : 0;
+      rowsB = max(0, min(kCtaNB, lNpad - b0));
+      lsrcA = lbase + static_cast<size_t>(a0) * 2 + q;
+      lsrcB = lbase + static_cast<size_t>(b0) * 2 + q;
+    };
+    if (lt < total_tiles) {
+      enter_tile(tiles[lt]);
+      if (lt + ncl < total_tiles) len = tiles[lt + ncl];
+      while (lt < total_tiles && lit >= lnp) {  // (lnp >= 2 > grp only fails for kGroupsP > 2)
+        lit -= lnp;
+        lt += ncl;
+        if (lt < total_tiles) {
+          enter_tile(len);
+          if (lt + ncl < total_tiles) len = tiles[lt + ncl];
         }
       }
     }
+    // loads the raw bits of the group's next stage; false when the group has no stage left
+    auto load_stage = [&](uint4(&w)[kTasksPerWarp]) -> bool {
+      if (lt >= total_tiles) return false;
+      const bool real = lit < lnpanel;  // the padding stage of an odd panel count carries no data
+      const size_t poff = static_cast<size_t>(lit) * lNpad * 2;  // uint4 units: panel lit
+#pragma unroll
+      for (int k = 0; k < kTasksPerWarp; ++k) {
+        const int gr = 2 * (wq + kWarpsPerGroup * k) + rg2;  // 8-row group of this lane
+        const int r = 8 * gr + r8;
+        const bool isA = r < kCtaM;
+        const bool ok = real && gr < kGroups && (isA ? r < rowsA : r - kCtaM < rowsB);
+        const uint4* src = (isA ? lsrcA + static_cast<size_t>(r) * 2 : lsrcB + static_cast<size_t>(r - kCtaM) * 2) + poff;
+        w[k] = ok ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      lit += kGroupsP;
+      while (lt < total_tiles && lit >= lnp) {
+        lit -= lnp;
+        lt += ncl;
+        if (lt < total_tiles) {
+          enter_tile(len);
+          if (lt + ncl < total_tiles) len = tiles[lt + ncl];
+        }
+      }
+      return true;
+    };
+    uint32_t g = static_cast<uint32_t>(grp);
+    auto store_stage = [&](const uint4(&w)[kTasksPerWarp]) {
+      const uint32_t s = g % kStages;
+      if (g >= kStages) SACCOT_TIMED_WAIT(w_empty, mbar_wait_wd(&empty2[s >> 1], ((g / kStages) - 1) & 1u, 6, g));
+      unsigned char* st = stage_base + s * kStageBytes;
+      const long long tp0 = PROF ? clock64() : 0;
+#pragma unroll
+      for (int k = 0; k < kTasksPerWarp; ++k) {
+        const int gr = 2 * (wq + kWarpsPerGroup * k) + rg2;
+        if (gr < kGroups) expand_quad(w[k], st + gr * kSBO + 4 * q * kLBO + r8 * 16);
+      }
+      const long long tp1 = PROF ? clock64() : 0;
+      // generic-proxy writes -> visible to the tensor cores (async proxy), then one arrival per warp on the
+      // leader's barrier: its MMAs read this CTA's stage too
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      const long long tp2 = PROF ? clock64() : 0;
+      if (lane == 0) mbar_arrive_cluster(&full2[s >> 1], 0u);
+      if (PROF) {
+        t_sts += tp1 - tp0;
+        t_fence += tp2 - tp1;
+        t_arr += clock64() - tp2;
+      }
+      g += kGroupsP;
+    };
+    uint4 w0[kTasksPerWarp], w1[kTasksPerWarp];
+    bool have = load_stage(w0);
+    while (have) {
+      const bool have1 = load_stage(w1);
+      store_stage(w0);
+      if (!have1) break;
+      have = load_stage(w0);
+      store_stage(w1);
+    }
     if (PROF && blockIdx.x < 2 && lane == 0 && (pw == 0 || pw == kProducerWarps - 1))
-      printf("cta %d producer %d: stages %u total %lld wait_raw_full %lld wait_empty %lld expand+sts %lld fence %lld arrive %lld\n",
-             blockIdx.x, pw, g, clock64() - t_begin, w_rfull, w_empty, t_sts, t_fence, t_arr);
+      printf("cta %d producer %d: stages %u total %lld wait_empty %lld expand+sts %lld fence %lld arrive %lld\n", blockIdx.x, pw,
+             g, clock64() - t_begin, w_empty, t_sts, t_fence, t_arr);
   }
 
   // no CTA of the pair may exit (or free its TMEM) while the other can still touch its memory
