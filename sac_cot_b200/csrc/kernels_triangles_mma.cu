@@ -13,16 +13,27 @@
 // That is 5 ALU instructions per 32 adjacency bits (profiles/microbench/umma_contend.cu checks the result
 // against popcounts and shows the MMA pipe at 99.6 % with the shared-memory stores running flat out).
 //
-// Kernel structure (persistent, one CTA per SM, 512 threads):
-//   tile        = 128 rows (i) x 240 columns (j), full K; only tiles that hold some i < j are visited
-//   warp  4     MMA issuer: per K stage (256 columns) 4 x tcgen05.mma M=128 N=240 K=64, two TMEM
-//               accumulators (2 x 240 columns) so that the epilogue of tile n overlaps the MMAs of n+1
-//   warp  5     bulk-copy (TMA) issuer: per stage the 128 + 240 raw rows of the K-panel copy of A
-//               (32 bytes per row, contiguous per operand block) into a 4-deep raw ring
-//   warps 6-15  expansion: raw ring -> 3-deep ring of canonical (no-swizzle, K-major) operand stages
-//   warps 0-3   epilogue: tcgen05.ld 16 columns at a time; mask with the edge bits (j > i), row sums
-//               (t2_i), column sums by a shuffle butterfly (t2_j), and edges whose T reaches the pair's
-//               pruning threshold are appended (key, histogram) through a per-warp staging buffer
+// Kernel structure (persistent, one CTA PAIR per two SMs, cta_group::2; 15 warps = 480 threads per CTA so
+// that every thread may use 128 registers):
+//   tile        = 256 rows (i; 128 per CTA = TMEM lanes) x 240 columns (j), full K; only tiles that hold some
+//                 i < j are visited.  The host deals the (pair, J, I)-sorted tile list to the CTA pairs in runs
+//                 (api.cu::interleave_tile_runs): few pair changes per CTA pair, L2-resident panels.
+//   warp  8     MMA issuer (leader CTA): per stage pair (2 x 256 columns of K) 8 x tcgen05.mma M=256 N=240
+//               K=64 by one elected lane, two TMEM accumulators (2 x 240 columns) that start every tile at
+//               2^23 (kBias): the epilogue of tile n overlaps the MMAs of tile n+1 and works on integers
+//   warps 9-14  expansion (3 groups of 2 warps, group = stage % 3): raw rows of the K-panel copy of A straight
+//               from L2 into registers one group-stage ahead -> 6-deep ring of canonical (no-swizzle,
+//               K-major) operand stages, handed to the issuer in pairs
+//   warps 0-7   epilogue: tcgen05.ld 16x256b (accumulator-fragment layout: a thread holds 4 rows of each of
+//               its 8 columns of a 32 x 32 block); mask with the edge bits (j > i, prefetched into shared
+//               memory with cp.async one tile ahead), row sums (t2_i), column sums by a 3-level shuffle
+//               reduce-scatter (t2_j), accumulator reset to kBias; edges whose T reaches the pair's pruning
+//               threshold are staged (key, histogram) in a per-warp shared-memory buffer
+//
+// Measured limits (profiles/README.md): the MMAs alone would take 15.6 us per N=5000 pair; the kernel runs
+// at ~24 us.  With the epilogue switched off it is 22 us and with three quarters of the operand stores
+// removed 17.8 us: the expansion warps' STS.128 stream (31.7 KB per stage and SM, next to the tensor cores'
+// own operand reads) is what the tensor pipe waits for, not the ALU work and not the epilogue.
 //
 // Pruning threshold (tri_theta_kernel): exact T of the edges among the ~128 highest-degree nodes; if at
 // least K_e of them exist, theta = the K_e-th largest of those counts.  Then at least K_e edges of the
