@@ -453,7 +453,7 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   mark(ST_SELECT);
   if (stop_after_edges) return 0;
   const float tau2 = prm.tau_inlier * prm.tau_inlier;
-  KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
+  KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
   mark(ST_APEX);
   KL_TRY(launch_kabsch(lc, L.desc, L.pairs, L.soa, L.tri, L.rt, L.K));
   mark(ST_KABSCH);
@@ -707,6 +707,7 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
   std::memset(ctx->h_sticky, 0, sizeof(StickyDev));
   int rc = triangles_configure();
   if (rc >= 0) rc = triangles_mma_configure();
+  if (rc >= 0) rc = select_configure();
   if (rc < 0) { sac_cot_ctx_destroy(ctx); return -rc; }
   *out = ctx;
   return SAC_COT_OK;
@@ -946,7 +947,7 @@ int sac_cot_sharded_phase2(sac_cot_ctx* ctx, const uint64_t* t_all, const uint64
     CU_TRY(cudaMemsetAsync(L.hyp_key, 0, sizeof(unsigned long long) * L.K, ln.stream));
     LaunchCtx lc{ln.stream, ctx->sm_count};
     const float tau2 = ctx->prm.tau_inlier * ctx->prm.tau_inlier;
-    KL_TRY(launch_select_apex(lc, L.desc, 1, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
+    KL_TRY(launch_select_apex(lc, L.desc, 1, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
     KL_TRY(launch_kabsch(lc, L.desc, 1, L.soa, L.tri, L.rt, L.K));
     const int per = (L.K + world - 1) / world;
     const int h0 = std::min(L.K, ctx->sh_rank * per), h1 = std::min(L.K, h0 + per);

@@ -15,6 +15,8 @@
 //      m best by (t_k desc, k asc); hypothesis id h = r*m + q.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace saccot {
 
 constexpr int kSelThreads = 256;
@@ -286,13 +288,243 @@ __global__ void __launch_bounds__(128) select_apex_kernel(const PairDesc* __rest
   }
 }
 
-int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const uint32_t* d_adj,
+// Staged variant (the one normally used): the pair's node counts t_k = t2_k / 2 are copied once per CTA into
+// shared memory as 32-bit values (t_k <= (N-1)(N-2)/2 < 2^31) and a CTA of 32 warps walks many edges of ONE pair.
+// The warp-per-edge kernel above looks every candidate up in global memory: 8 useful bytes per 32-byte L2
+// sector, ~290 candidates per edge.  ncu showed that kernel (and a first staged version) bound by the ALU pipe
+// (88 %): 1600 warp instructions per edge, almost all of them the 64-bit insertion network, run divergently for
+// every candidate.  Hence two passes: a 32-bit maximum per lane first, the insertion only for candidates that
+// reach the resulting lower bound.  Rows are read eight words per lane at a time (independent loads).
+constexpr int kApexThreads = 1024;
+constexpr int kApexRank = 256;   // nodes the rank list aims for
+constexpr int kApexCap = 512;    // its capacity (ties at the cut)
+constexpr int kApexMaxSmem = 200 * 1024;
+template <int M>
+__global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const PairDesc* __restrict__ descs,
+                                                                          const uint32_t* __restrict__ adj,
+                                                                          const unsigned long long* __restrict__ t2,
+                                                                          const unsigned long long* __restrict__ top,
+                                                                          int32_t* __restrict__ tri, int Ke, int m) {
+  extern __shared__ uint32_t apex_ts[];  // [Npad] node counts, then the rank list
+  __shared__ int s_cnt, s_len;
+  __shared__ uint32_t s_max;
+  const int pair = blockIdx.y;
+  const PairDesc d = descs[pair];
+  const int lane = threadIdx.x & 31, tid = threadIdx.x;
+  unsigned long long* rank_list = reinterpret_cast<unsigned long long*>(apex_ts + d.Npad);  // [kApexCap]
+  {
+    const unsigned long long* t2p = t2 + d.node_off;
+    uint32_t mx = 0;
+    for (int k = tid; k < d.Npad; k += kApexThreads) {
+      const uint32_t v = static_cast<uint32_t>(t2p[k] >> 1);
+      apex_ts[k] = v;
+      mx = max(mx, v);
+    }
+    if (tid == 0) {
+      s_max = 0u;
+      s_len = 0;
+    }
+    for (int k = tid; k < kApexCap; k += kApexThreads) rank_list[k] = 0ull;
+    __syncthreads();
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0 && mx) atomicMax(&s_max, mx);
+  }
+  __syncthreads();
+  // ---- rank list: every node with t_k >= tcut, sorted by (t_k descending, k ascending) — the order apexes are
+  //      ranked in.  It holds ALL nodes down to tcut, so the first m common neighbours found while walking it are
+  //      exactly the m best ones; an edge that finds fewer than m takes the exhaustive path below. ----
+  auto count_ge = [&](uint32_t v) {
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int k = tid; k < d.Npad; k += kApexThreads) c += apex_ts[k] >= v ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    const int r = s_cnt;
+    __syncthreads();
+    return r;
+  };
+  uint32_t tcut = 1;
+  if (count_ge(1u) > kApexRank) {
+    uint32_t lo = 1, hi = s_max + 1;  // count_ge(lo) >= kApexRank > count_ge(hi)
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (count_ge(mid) >= kApexRank) lo = mid;
+      else hi = mid;
+    }
+    tcut = count_ge(lo) <= kApexCap ? lo : lo + 1;  // many ties at lo: keep only what is strictly above
+  }
+  for (int k = tid; k < d.Npad; k += kApexThreads) {
+    const uint32_t v = apex_ts[k];
+    if (v >= tcut)
+      rank_list[atomicAdd(&s_len, 1)] = (static_cast<unsigned long long>(v) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned int>(k));
+  }
+  __syncthreads();
+  const int nrank = s_len;
+  // bitonic sort, descending, kApexCap slots (empty slots are 0 and sink to the end)
+  for (int sz = 2; sz <= kApexCap; sz <<= 1) {
+    for (int st = sz >> 1; st > 0; st >>= 1) {
+      for (int idx = tid; idx < kApexCap / 2; idx += kApexThreads) {
+        const int a = 2 * idx - (idx & (st - 1)), b = a + st;
+        const unsigned long long x = rank_list[a], y = rank_list[b];
+        const bool desc = (a & sz) == 0;
+        if (desc ? x < y : x > y) {
+          rank_list[a] = y;
+          rank_list[b] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int wstep = gridDim.x * (kApexThreads >> 5);
+  for (int r = blockIdx.x * (kApexThreads >> 5) + (threadIdx.x >> 5); r < Ke; r += wstep) {
+    int32_t* out = tri + (static_cast<size_t>(pair) * Ke + r) * m * 3;
+    const unsigned long long ekey = top[static_cast<size_t>(pair) * Ke + r];
+    if (ekey == 0) {  // fewer than K_e edges: slot unused
+      for (int k = lane; k < m * 3; k += 32) out[k] = -1;
+      continue;
+    }
+    const int i = static_cast<int>(0xFFFFu - static_cast<unsigned int>((ekey >> 16) & 0xFFFFu));
+    const int j = static_cast<int>(0xFFFFu - static_cast<unsigned int>(ekey & 0xFFFFu));
+    const uint32_t* ri = adj + d.adj_off + static_cast<size_t>(i) * d.stride;
+    const uint32_t* rj = adj + d.adj_off + static_cast<size_t>(j) * d.stride;
+    // ---- fast path: walk the rank list, 32 nodes at a time ----
+    int found = 0;
+    for (int base = 0; base < nrank && found < m; base += 32) {
+      const unsigned long long key = base + lane < nrank ? rank_list[base + lane] : 0ull;
+      bool hit = false;
+      const unsigned int k = 0xFFFFFFFFu - static_cast<unsigned int>(key & 0xFFFFFFFFull);
+      if (key) hit = (((ri[k >> 5] & rj[k >> 5]) >> (k & 31)) & 1u) != 0u;
+      const unsigned hm = __ballot_sync(0xffffffffu, hit);
+      const int q = found + __popc(hm & ((1u << lane) - 1u));
+      if (hit && q < m) {
+        out[q * 3 + 0] = i;
+        out[q * 3 + 1] = j;
+        out[q * 3 + 2] = static_cast<int>(k);
+      }
+      found += __popc(hm);
+    }
+    if (found >= m) continue;
+    // ---- exhaustive path (the rank list held fewer than m common neighbours of this edge) ----
+    // Pass 1: per-lane maximum of t_k over the candidates (one IMNMX per candidate), then a lower bound L on the
+    // m-th best count: the value at which the lane maxima, taken from the top, cover m lanes (each of them holds
+    // a candidate >= L).  Every candidate is in a triangle with (i, j), so t_k >= 1 and 0 means "none".
+    uint32_t lmax = 0;
+    for (int w0 = 0; w0 < d.stride; w0 += 256) {
+      uint32_t bw[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int w = w0 + 32 * c + lane;
+        bw[c] = w < d.stride ? (ri[w] & rj[w]) : 0u;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t bits = bw[c];
+        const uint32_t* tw = apex_ts + (w0 + 32 * c + lane) * 32;
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          lmax = max(lmax, tw[b]);
+        }
+      }
+    }
+    uint32_t L = 1;
+    {
+      uint32_t v = lmax;
+      int got = 0;
+      for (int q = 0; q < m && got < m; ++q) {
+        const uint32_t wm = __reduce_max_sync(0xffffffffu, v);
+        if (wm == 0) break;
+        L = wm;
+        got += __popc(__ballot_sync(0xffffffffu, v == wm));
+        if (v == wm) v = 0;
+      }
+      if (got < m) L = 1;  // fewer than m lanes hold candidates: keep them all
+    }
+    // Pass 2: per-lane best-M among the few candidates with t_k >= L, sorted descending;
+    // candidate key = t_k << 32 | (0xFFFFFFFF - k)
+    unsigned long long best[M];
+#pragma unroll
+    for (int q = 0; q < M; ++q) best[q] = 0ull;
+    for (int w0 = 0; w0 < d.stride; w0 += 256) {
+      uint32_t bw[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int w = w0 + 32 * c + lane;
+        bw[c] = w < d.stride ? (ri[w] & rj[w]) : 0u;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t bits = bw[c];
+        const unsigned int kb = static_cast<unsigned int>((w0 + 32 * c + lane) * 32);
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const unsigned int k = kb + static_cast<unsigned int>(b);
+          const uint32_t tk = apex_ts[k];
+          if (tk >= L) {
+            unsigned long long cnd = (static_cast<unsigned long long>(tk) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - k);
+#pragma unroll
+            for (int q = 0; q < M; ++q) {
+              if (cnd > best[q]) {
+                const unsigned long long tmp = best[q];
+                best[q] = cnd;
+                cnd = tmp;
+              }
+            }
+          }
+        }
+      }
+    }
+    // warp merge: m rounds of "global max, owner pops"
+    for (int q = 0; q < m; ++q) {
+      const unsigned long long mine = best[0];
+      const unsigned long long wmax = warp_max_u64(mine);
+      if (wmax == 0ull) {
+        if (lane == 0) { out[q * 3 + 0] = -1; out[q * 3 + 1] = -1; out[q * 3 + 2] = -1; }
+        continue;
+      }
+      // candidate keys are unique (distinct k), so exactly one lane owns the maximum
+      if (mine == wmax) {
+        out[q * 3 + 0] = i;
+        out[q * 3 + 1] = j;
+        out[q * 3 + 2] = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned int>(wmax & 0xFFFFFFFFull));
+#pragma unroll
+        for (int s = 0; s < M - 1; ++s) best[s] = best[s + 1];
+        best[M - 1] = 0ull;
+      }
+    }
+  }
+}
+
+int select_configure() {
+  cudaError_t e = cudaFuncSetAttribute(select_apex_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(select_apex_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(select_apex_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(select_apex_staged_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
+  return e == cudaSuccess ? 0 : -static_cast<int>(e);
+}
+
+int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                        const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m) {
-  dim3 grid((Ke + 3) / 4, pairs);
-  if (m <= 1) select_apex_kernel<1><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
-  else if (m <= 2) select_apex_kernel<2><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
-  else if (m <= 4) select_apex_kernel<4><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
-  else select_apex_kernel<8><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+  const size_t smem = static_cast<size_t>(max_npad) * 4 + kApexCap * 8;
+  if (smem <= static_cast<size_t>(kApexMaxSmem)) {
+    // enough CTAs to fill the GPU (every CTA of a pair rebuilds the pair's rank list), at most one per 32 edges
+    int split = (lc.sm_count + pairs - 1) / pairs;
+    split = std::max(1, std::min(split, (Ke + 31) / 32));
+    dim3 grid(split, pairs);
+    if (m <= 1) select_apex_staged_kernel<1><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+    else if (m <= 2) select_apex_staged_kernel<2><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+    else if (m <= 4) select_apex_staged_kernel<4><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+    else select_apex_staged_kernel<8><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+  } else {  // node counts do not fit shared memory (N > 51200): look them up in global memory
+    dim3 grid((Ke + 3) / 4, pairs);
+    if (m <= 1) select_apex_kernel<1><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+    else if (m <= 2) select_apex_kernel<2><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+    else if (m <= 4) select_apex_kernel<4><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+    else select_apex_kernel<8><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+  }
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }

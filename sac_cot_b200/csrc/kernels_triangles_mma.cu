@@ -867,13 +867,23 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
   __syncthreads();
   const int nsel = s_nsel;
 
-  // 4a. edges among the sample nodes
-  for (int idx = t; idx < nsel * nsel; idx += 1024) {
+  // 4a. edges among the sample nodes (one shared-memory reservation per warp and round: with one atomic per
+  //     edge the ~8000 edges of a clique sample serialised on the counter and dominated the kernel)
+  for (int base = 0; base < nsel * nsel; base += 1024) {
+    const int idx = base + t;
     const int x = idx / nsel, y = idx - x * nsel;
-    if (x < y) {
+    bool is_edge = false;
+    if (idx < nsel * nsel && x < y) {
       const int a = nodes[x], b = nodes[y];
-      if ((adjp[static_cast<size_t>(a) * d.stride + (b >> 5)] >> (b & 31)) & 1u) {
-        const int pos = atomicAdd(&s_nts, 1);
+      is_edge = ((adjp[static_cast<size_t>(a) * d.stride + (b >> 5)] >> (b & 31)) & 1u) != 0u;
+    }
+    const unsigned em = __ballot_sync(0xffffffffu, is_edge);
+    if (em) {
+      int pos0 = 0;
+      if (lane == 0) pos0 = atomicAdd(&s_nts, __popc(em));
+      pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+      if (is_edge) {
+        const int pos = pos0 + __popc(em & ((1u << lane) - 1u));
         cand[pos] = (static_cast<uint32_t>(x) << 16) | static_cast<uint32_t>(y);
         ts[pos] = 0;
       }

@@ -17,6 +17,8 @@ def main():
     sizes = (3, 129, 300, 777, 1000) + ((11500,) if big else ())
     pairs = [synth.make_pair(n, 0.2, 100 + k) for k, n in enumerate(sizes)]
     with Registrar(device=0, num_edges=128, apex_per_edge=4) as reg:
+        if "--tensor" in sys.argv:  # force S2 onto the tensor-core kernel (default: by edge density)
+            reg.set("triangle_path", 1)
         res = reg.register_batch([p.src for p in pairs], [p.dst for p in pairs])
         print("batch inliers", res.inliers.tolist())
         reg.params.score_mode = 1
