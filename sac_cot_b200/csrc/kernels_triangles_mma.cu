@@ -774,12 +774,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
 // arranged so that its global loads are independent (the kernel is latency-, not throughput-bound).
 // ------------------------------------------------------------------------------------------
 constexpr int kThetaNodes = 128;
-constexpr int kThetaSamples = kThetaNodes * (kThetaNodes - 1) / 2;  // 8128
+constexpr int kThetaSamples = kThetaNodes * kThetaNodes;            // dense [x][y] table, x < y used
 constexpr int kThetaChunkW = 192;                                   // adjacency words per staged row chunk
 
 static size_t theta_smem_bytes(int max_npad) {
   const int cw = std::min(max_npad / 32, kThetaChunkW);
-  return static_cast<size_t>(max_npad) + static_cast<size_t>(kThetaNodes) * cw * 4 + kThetaSamples * 6 + 16;
+  return static_cast<size_t>(max_npad) + static_cast<size_t>(kThetaNodes) * cw * 4 + kThetaSamples * 2 + kThetaNodes * 16 + 16;
 }
 
 __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restrict__ descs,
@@ -796,8 +796,8 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
   extern __shared__ __align__(16) unsigned char th_smem[];
   const int cw_max = min(max_npad / 32, kThetaChunkW);
   uint32_t* rows_s = reinterpret_cast<uint32_t*>(th_smem);                         // [128][cw]
-  uint32_t* cand = rows_s + static_cast<size_t>(kThetaNodes) * cw_max;             // [8128] x << 16 | y
-  unsigned short* ts = reinterpret_cast<unsigned short*>(cand + kThetaSamples);   // [8128] exact T (<= 65535)
+  uint32_t* emask = rows_s + static_cast<size_t>(kThetaNodes) * cw_max;            // [128][4] edge bits among the sample nodes (y > x)
+  unsigned short* ts = reinterpret_cast<unsigned short*>(emask + kThetaNodes * 4); // [128][128] exact T + 1 of sample edge (x, y), 0 = no edge
   unsigned char* deg = reinterpret_cast<unsigned char*>(ts + kThetaSamples);      // [Npad] proxy degrees, saturated
   __shared__ int nodes[kThetaNodes];
   __shared__ int s_cnt, s_nsel, s_nts;
@@ -867,8 +867,10 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
   __syncthreads();
   const int nsel = s_nsel;
 
-  // 4a. edges among the sample nodes (one shared-memory reservation per warp and round: with one atomic per
-  //     edge the ~8000 edges of a clique sample serialised on the counter and dominated the kernel)
+  // 4a. edges among the sample nodes: a bit mask per sample row and a dense table of counts (T + 1, 0 = no edge)
+  for (int k = t; k < kThetaNodes * 4; k += 1024) emask[k] = 0u;
+  for (int k = t; k < kThetaSamples; k += 1024) ts[k] = 0;
+  __syncthreads();
   for (int base = 0; base < nsel * nsel; base += 1024) {
     const int idx = base + t;
     const int x = idx / nsel, y = idx - x * nsel;
@@ -877,48 +879,65 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
       const int a = nodes[x], b = nodes[y];
       is_edge = ((adjp[static_cast<size_t>(a) * d.stride + (b >> 5)] >> (b & 31)) & 1u) != 0u;
     }
-    const unsigned em = __ballot_sync(0xffffffffu, is_edge);
-    if (em) {
-      int pos0 = 0;
-      if (lane == 0) pos0 = atomicAdd(&s_nts, __popc(em));
-      pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-      if (is_edge) {
-        const int pos = pos0 + __popc(em & ((1u << lane) - 1u));
-        cand[pos] = (static_cast<uint32_t>(x) << 16) | static_cast<uint32_t>(y);
-        ts[pos] = 0;
-      }
+    if (is_edge) {
+      atomicOr(&emask[x * 4 + (y >> 5)], 1u << (y & 31));
+      ts[x * kThetaNodes + y] = 1;
     }
+    const unsigned em = __ballot_sync(0xffffffffu, is_edge);
+    if (lane == 0 && em) atomicAdd(&s_nts, __popc(em));
   }
   __syncthreads();
   const int nts = s_nts;
 
-  // 4b. exact T of those edges: the sample rows are staged chunk by chunk, one warp per edge
+  // 4b. exact T of those edges.  The sample rows are staged chunk by chunk; a warp keeps sample row x in
+  //     registers (six words per lane at most) and walks its partners y > x: per edge 6 LDS, AND, a carry-save
+  //     adder tree (3 POPC instead of 6: POPC and REDUX share the slow XU pipe) and one warp reduction.  Rows are
+  //     dealt so that every warp gets the same number of partners (x, 63 - x, 64 + x, 127 - x).
   for (int c0 = 0; c0 < d.stride; c0 += cw_max) {
     const int cw = min(cw_max, d.stride - c0);
     for (int r = warp; r < nsel; r += 32) {
       const uint32_t* rp = adjp + static_cast<size_t>(nodes[r]) * d.stride + c0;
-      for (int w = lane; w < cw; w += 32) rows_s[r * cw_max + w] = rp[w];
+      for (int w = lane; w < cw_max; w += 32) rows_s[r * cw_max + w] = w < cw ? rp[w] : 0u;
     }
     __syncthreads();
-    for (int e = warp; e < nts; e += 32) {
-      const uint32_t xy = cand[e];
-      const uint32_t* ra = rows_s + (xy >> 16) * cw_max;
-      const uint32_t* rb = rows_s + (xy & 0xFFFFu) * cw_max;
-      int c = 0;
-      for (int w = lane; w < cw; w += 32) c += __popc(ra[w] & rb[w]);
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0) ts[e] = static_cast<unsigned short>(ts[e] + c);
+    for (int j = 0; j < 4; ++j) {
+      const int x = (j == 0) ? warp : (j == 1) ? 63 - warp : (j == 2) ? 64 + warp : 127 - warp;
+      if (x >= nsel) continue;
+      uint32_t rx[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) rx[r] = lane + 32 * r < cw_max ? rows_s[x * cw_max + lane + 32 * r] : 0u;
+      for (int wq = 0; wq < 4; ++wq) {
+        uint32_t bits = emask[x * 4 + wq];
+        while (bits) {
+          const int y = 32 * wq + __ffs(bits) - 1;
+          bits &= bits - 1;
+          const uint32_t* ry = rows_s + y * cw_max + lane;
+          uint32_t a[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) a[r] = lane + 32 * r < cw_max ? (rx[r] & ry[32 * r]) : 0u;
+          // two carry-save adders: a0+a1+a2 -> (s1, c1), a3+a4+a5 -> (s2, c2); sum = popc(s1)+popc(s2) + 2 popc(c1)+2 popc(c2)
+          const uint32_t s1 = a[0] ^ a[1] ^ a[2], c1 = (a[0] & a[1]) | (a[2] & (a[0] ^ a[1]));
+          const uint32_t s2 = a[3] ^ a[4] ^ a[5], c2 = (a[3] & a[4]) | (a[5] & (a[3] ^ a[4]));
+          // third adder over (s1, s2, 0) and the carries: sum = popc(s1 ^ s2) + 2 (popc(s1 & s2) + popc(c1) + popc(c2))
+          const uint32_t lo1 = s1 ^ s2, hi1 = s1 & s2;
+          // carries c1, c2, hi1 all weigh 2: one more adder -> (s3, c3) with weights 2 and 4
+          const uint32_t s3 = c1 ^ c2 ^ hi1, c3 = (c1 & c2) | (hi1 & (c1 ^ c2));
+          int c = __popc(lo1) + 2 * __popc(s3) + 4 * __popc(c3);
+          c = __reduce_add_sync(0xffffffffu, c);
+          if (lane == 0) ts[x * kThetaNodes + y] = static_cast<unsigned short>(ts[x * kThetaNodes + y] + c);
+        }
+      }
     }
     __syncthreads();
   }
 
-  // 5. theta = K_e-th largest sample count (0 if the sample holds fewer than K_e edges)
+  // 5. theta = K_e-th largest sample count (0 if the sample holds fewer than K_e edges); table entries are T + 1
   uint32_t th = 0;
   if (nts >= Ke) {
-    int l2 = 0, h2 = 65536;
+    int l2 = 0, h2 = 65535;
     while (h2 - l2 > 1) {
       const int mid = (l2 + h2) >> 1;
-      if (block_count([&](int k) { return ts[k] >= mid; }, nts) >= Ke) l2 = mid;
+      if (block_count([&](int k) { return ts[k] > mid; }, kThetaSamples) >= Ke) l2 = mid;
       else h2 = mid;
     }
     th = static_cast<uint32_t>(l2);
