@@ -103,7 +103,11 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *        a per-pair threshold proven to lie at or below the K_e-th largest count; results are
  *        unchanged, SAC_COT_DBG_EDGE_KEYS / _HIST then cover the kept edges only; GPU only),
  *        "stage_timing" (0/1: bracket every pipeline stage with CUDA events on the ctx
- *        stream; setting it also clears the accumulated times; GPU only)
+ *        stream; setting it also clears the accumulated times; GPU only),
+ *        test switches that never change a result (GPU only): "tile_runs" (tensor-core path, default 1:
+ *        tiles dealt to the CTA pairs in runs; 0 = one at a time), "apex_path" (0 = shared-memory
+ *        kernel with the per-pair rank list (default), 1 = same kernel, exhaustive scan of every edge,
+ *        2 = the global-lookup kernel that N > 51200 falls back to), "triangle_dbg" (experiments)
  *   get: "triangle_path_used" (0/1: which S2 kernels the latest chunk ran; synchronises; GPU only),
  *        "launches" (kernels launched since ctx creation), "workspace_bytes",
  *        "device", "sm_count", "retries" (workspace-growth re-runs),

@@ -157,6 +157,7 @@ struct sac_cot_ctx {
   int chunk_pairs = 0;
   int n_lanes = 2;
   int tri_path = 2;   // 0 = POPC bitset kernels, 1 = tensor-core (tcgen05 mxf4) kernel, 2 = by edge density per chunk
+  int apex_path = 0;  // tests: 0 rank list, 1 exhaustive scan, 2 global-lookup kernel (kernels_select.cu)
   int tile_runs = 1;  // tensor-core path: deal tiles to the CTA pairs in runs (0: one at a time; experiments)
   int tri_dbg = 0;    // experiments only (bit 0: skip the tensor-core kernel's epilogue work; results are void)
   int tri_prune = 1;  // tensor-core path: drop edges below the per-pair threshold (exact for the selection)
@@ -453,7 +454,7 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   mark(ST_SELECT);
   if (stop_after_edges) return 0;
   const float tau2 = prm.tau_inlier * prm.tau_inlier;
-  KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
+  KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path));
   mark(ST_APEX);
   KL_TRY(launch_kabsch(lc, L.desc, L.pairs, L.soa, L.tri, L.rt, L.K));
   mark(ST_KABSCH);
@@ -756,6 +757,11 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     ctx->tri_prune = value != 0;
     return SAC_COT_OK;
   }
+  if (!std::strcmp(name, "apex_path")) {
+    if (value < 0 || value > 2) return SAC_COT_E_UNSUPPORTED;
+    ctx->apex_path = static_cast<int>(value);
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "tile_runs")) {
     ctx->tile_runs = value != 0;
     return SAC_COT_OK;
@@ -947,7 +953,7 @@ int sac_cot_sharded_phase2(sac_cot_ctx* ctx, const uint64_t* t_all, const uint64
     CU_TRY(cudaMemsetAsync(L.hyp_key, 0, sizeof(unsigned long long) * L.K, ln.stream));
     LaunchCtx lc{ln.stream, ctx->sm_count};
     const float tau2 = ctx->prm.tau_inlier * ctx->prm.tau_inlier;
-    KL_TRY(launch_select_apex(lc, L.desc, 1, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m));
+    KL_TRY(launch_select_apex(lc, L.desc, 1, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path));
     KL_TRY(launch_kabsch(lc, L.desc, 1, L.soa, L.tri, L.rt, L.K));
     const int per = (L.K + world - 1) / world;
     const int h0 = std::min(L.K, ctx->sh_rank * per), h1 = std::min(L.K, h0 + per);

@@ -184,7 +184,8 @@ int launch_select_edges(const LaunchCtx& lc, int pairs, PairDev* d_state, const 
                         unsigned long long* d_tie, unsigned long long* d_top, int Ke);
 int select_configure();  // opt-in dynamic shared memory; call once per device
 int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
-                       const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m);
+                       const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m,
+                       int apex_path);
 
 // kernels_hypo.cu — S4 Kabsch, S5/S6 scoring + argmax, S7 refit
 int launch_kabsch(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const float* d_soa, const int32_t* d_tri,

@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const 
                                                                           const uint32_t* __restrict__ adj,
                                                                           const unsigned long long* __restrict__ t2,
                                                                           const unsigned long long* __restrict__ top,
-                                                                          int32_t* __restrict__ tri, int Ke, int m) {
+                                                                          int32_t* __restrict__ tri, int Ke, int m,
+                                                                          int use_rank_list) {
   extern __shared__ uint32_t apex_ts[];  // [Npad] node counts, then the rank list
   __shared__ int s_cnt, s_len;
   __shared__ uint32_t s_max;
@@ -346,7 +347,8 @@ __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const 
     return r;
   };
   uint32_t tcut = 1;
-  if (count_ge(1u) > kApexRank) {
+  if (!use_rank_list) tcut = 0xFFFFFFFFu;  // tests: empty list, every edge takes the exhaustive path
+  else if (count_ge(1u) > kApexRank) {
     uint32_t lo = 1, hi = s_max + 1;  // count_ge(lo) >= kApexRank > count_ge(hi)
     while (hi - lo > 1) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
@@ -507,17 +509,21 @@ int select_configure() {
 }
 
 int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
-                       const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m) {
+                       const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m,
+                       int apex_path) {
+  // apex_path (tests): 0 = staged kernel with the rank list (default), 1 = staged kernel, exhaustive path only,
+  // 2 = the global-lookup kernel that large N falls back to
   const size_t smem = static_cast<size_t>(max_npad) * 4 + kApexCap * 8;
-  if (smem <= static_cast<size_t>(kApexMaxSmem)) {
+  const int rl = apex_path == 0 ? 1 : 0;
+  if (smem <= static_cast<size_t>(kApexMaxSmem) && apex_path != 2) {
     // enough CTAs to fill the GPU (every CTA of a pair rebuilds the pair's rank list), at most one per 32 edges
     int split = (lc.sm_count + pairs - 1) / pairs;
     split = std::max(1, std::min(split, (Ke + 31) / 32));
     dim3 grid(split, pairs);
-    if (m <= 1) select_apex_staged_kernel<1><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
-    else if (m <= 2) select_apex_staged_kernel<2><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
-    else if (m <= 4) select_apex_staged_kernel<4><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
-    else select_apex_staged_kernel<8><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
+    if (m <= 1) select_apex_staged_kernel<1><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl);
+    else if (m <= 2) select_apex_staged_kernel<2><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl);
+    else if (m <= 4) select_apex_staged_kernel<4><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl);
+    else select_apex_staged_kernel<8><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl);
   } else {  // node counts do not fit shared memory (N > 51200): look them up in global memory
     dim3 grid((Ke + 3) / 4, pairs);
     if (m <= 1) select_apex_kernel<1><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);

@@ -524,3 +524,60 @@ def test_default_ctx_uses_auto_path_and_matches_oracle_batch(gpu_lib, oracle):
         assert reg.get("triangle_path_used") == 1
         for b in range(len(ps)):
             compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
+
+
+# ---------------------------------------------------------------------------------------------
+# apex selection: rank list, exhaustive scan and the global-lookup fallback give the same triangles
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("apex_path", [0, 1, 2])
+@pytest.mark.parametrize("N,ratio,m", [(700, 0.1, 4), (5000, 0.05, 4), (5000, 0.01, 8), (2000, 0.0, 2)])
+def test_apex_paths_match_oracle(gpu, oracle, apex_path, N, ratio, m):
+    # 1 % / 0 % inliers: most selected edges have fewer than m common neighbours among the ~256 best-ranked
+    # nodes, so the rank-list kernel takes its exhaustive path for them
+    gpu.set("apex_path", apex_path)
+    p = synth.make_pair(N, ratio, 9100 + N + m)
+    run_both(gpu, oracle, p, num_edges=512, apex_per_edge=m)
+
+
+@pytest.mark.parametrize("apex_path", [0, 1, 2])
+def test_apex_paths_on_ties(gpu, oracle, apex_path):
+    # complete graph: every node count is equal, the rank list is cut inside one huge tie (ties go to the lowest k)
+    gpu.set("apex_path", apex_path)
+    N = 600
+    rng = np.random.default_rng(77)
+    src = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=0.5, tau_inlier=0.1, num_edges=300, apex_per_edge=8)
+    out_g = gpu.register(src, src.copy())
+    out_o = oracle.register(src, src.copy())
+    compare_stages(gpu, oracle)
+    compare_pose(*out_g, *out_o)
+
+
+def test_apex_path_rejects_unknown_value(gpu):
+    from sac_cot_b200.api import SacCotError
+    with pytest.raises(SacCotError):
+        gpu.set("apex_path", 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core path: the tile schedule (runs vs one at a time) does not change anything
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tile_runs", [0, 1])
+def test_tensor_core_tile_schedule_is_invisible(gpu_lib, oracle_lib, tile_runs):
+    from sac_cot_b200.api import Registrar
+    # enough tiles for several runs per CTA pair, ragged sizes so that runs straddle pairs of different K
+    sizes = [1500, 2600, 1030, 3100, 2048, 1800, 2900, 1200, 2500, 1700, 3000, 1100]
+    ps = [synth.make_pair(n, 0.08, 9300 + k) for k, n in enumerate(sizes)]
+    with Registrar(lib=gpu_lib, device=0) as g, Registrar(lib=oracle_lib) as o:
+        for r in (g, o):
+            r.set("keep_debug", 1)
+            set_params(r, tau_compat=ps[0].tau_compat, tau_inlier=ps[0].tau_inlier, num_edges=256, apex_per_edge=4)
+        g.set("triangle_path", 1)
+        g.set("tile_runs", tile_runs)
+        rg = g.register_batch([p.src for p in ps], [p.dst for p in ps])
+        ro = o.register_batch([p.src for p in ps], [p.dst for p in ps])
+        assert g.get("triangle_path_used") == 1
+        assert (rg.inliers == ro.inliers).all()
+        for b in range(len(ps)):
+            compare_pruned(g, o, pair_idx=b)
