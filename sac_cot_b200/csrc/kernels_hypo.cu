@@ -259,9 +259,9 @@ __device__ __forceinline__ f32x2 residual2_x2(const f32x2 (&rt2)[12], f32x2 px, 
   return fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
 }
 
-// Two phases per 32 correspondences.  Phase 1 (packed, every correspondence): x' and ex*ex only — 5 packed FP
-// instructions per two points instead of 15.  r2 = fma(ez,ez,fma(ey,ey,ex*ex)) >= ex*ex in fp32 as in real
-// arithmetic (each fma adds a non-negative term and rounding is monotone), so a point with ex*ex >= tau^2 (or NaN)
+// Two phases per 32 correspondences.  Phase 1 (packed, every correspondence): x' and the sign of ex^2 - tau^2 only —
+// 5 packed FP instructions per two points instead of 15.  r2 = fma(ez,ez,fma(ey,ey,ex*ex)) >= RN(ex*ex) in fp32 as
+// in real arithmetic (each fma adds a non-negative term and rounding is monotone), so a point with ex^2 >= tau^2
 // cannot be an inlier and contributes the constant 2^20 in mode 1; ~93 % of the points of a 3 m scene leave here.
 // Phase 2 (scalar, the survivors, one bit per point in a register mask): the full specified chain, bit-identical to
 // the oracle's.  ncu before (`profiles/ncu_score_r01a.txt`): FP32 pipe saturated by 15 FFMA2-class instructions per
@@ -327,10 +327,13 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
     }
     __syncthreads();
     for (int kc = 0; kc < npairs; kc += 16) {
-      // ---- phase 1: 32 correspondences, candidate bit 2 j + p for point pair kc + j, parity p ----
+      // ---- phase 1: 32 correspondences.  The candidate bit of a point is the sign of ex*ex - tau^2, shifted into the
+      //      mask with one funnel shift: point 2 j + p of the chunk ends up at bit 31 - (2 j + p).  (A NaN may land
+      //      either way; phase 2 is exact for whatever it is given.) ----
       uint32_t m[kScoreHyp];
 #pragma unroll
       for (int u = 0; u < kScoreHyp; ++u) m[u] = 0u;
+      const f32x2 ntau2 = pk(-tau2, -tau2);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float4 a = slab[kc + j][0], b = slab[kc + j][1];
@@ -339,10 +342,12 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
         for (int u = 0; u < kScoreHyp; ++u) {
           const f32x2 xp = fma2(rx2[u][0], px, fma2(rx2[u][1], py, fma2(rx2[u][2], pz, rx2[u][3])));
           const f32x2 ex = sub2(xp, qx);
-          float e0, e1;
-          unpk(mul2(ex, ex), e0, e1);
-          m[u] |= (e0 < tau2 ? 1u : 0u) << (2 * j);  // NaN -> false
-          m[u] |= (e1 < tau2 ? 1u : 0u) << (2 * j + 1);
+          // RN(ex^2 - tau^2) with ONE rounding: its sign is the sign of the exact difference, and
+          // RN(ex*ex) < tau^2 implies ex^2 < tau^2 (rounding is monotone, tau^2 is a float): no inlier is lost
+          float d0, d1;
+          unpk(fma2(ex, ex, ntau2), d0, d1);
+          m[u] = __funnelshift_l(__float_as_uint(d0), m[u], 1);
+          m[u] = __funnelshift_l(__float_as_uint(d1), m[u], 1);
         }
       }
       // ---- phase 2: the full chain for the candidates ----
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
         uint32_t bits = m[u];
         if (MODE == 1) cnt[u] += __popc(bits);
         while (bits) {
-          const int bpos = __ffs(bits) - 1;
+          const int bpos = 31 - (__ffs(bits) - 1);  // index of the point within the chunk
           bits &= bits - 1;
           const float* sp = reinterpret_cast<const float*>(&slab[kc + (bpos >> 1)][0]) + (bpos & 1);
           const float4 pa = make_float4(sp[0], sp[2], sp[4], sp[6]);  // sx, sy, sz, dx
