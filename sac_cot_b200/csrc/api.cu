@@ -444,7 +444,7 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
     KL_TRY(launch_tri_theta(lc, L.desc, L.pairs, L.max_npad, L.adj, L.chunk, L.theta, L.Ke, ctx->tri_prune));
     mark(ST_THETA);
     KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, L.adj, L.panel, L.state, L.chunk, ln.keys, L.theta,
-                                L.hist, L.t2, ctx->tri_dbg));
+                                L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg));
   }
   if (tri_mode != 1)
     KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ln.keys, L.ubase,

@@ -174,8 +174,8 @@ int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
                      const ChunkDev* d_chunk, uint32_t* d_theta, int Ke, int prune);
 int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_tiles, int total_tiles,
                          const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
-                         unsigned long long* d_keys, const uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
-                         int dbg);
+                         unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
+                         int Ke, int raise, int dbg);
 int triangles_mma_configure();
 
 // kernels_select.cu — S3 edge ranking + apex selection

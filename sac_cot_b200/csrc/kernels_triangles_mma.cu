@@ -272,6 +272,26 @@ __device__ __forceinline__ void push16(const uint32_t (&m)[16], uint32_t fa, uin
   }
 }
 
+// One warp: highest histogram bin b with at least Ke kept keys in bins >= b -> the pair's threshold becomes
+// max(threshold, 16 b).  Out of line: it runs once per tile in one warp and must not fatten the hot loop.
+__device__ __noinline__ void raise_threshold(const uint32_t* hist_s, int cur_bins, int Ke, uint32_t thb, uint32_t* theta_pair) {
+  const int lane = threadIdx.x & 31;
+  int carry = 0, found = -1;
+  for (int c0 = (cur_bins - 1) & ~31; c0 >= 0 && found < 0; c0 -= 32) {
+    const int k = c0 + lane;
+    int v = k < cur_bins ? static_cast<int>(hist_s[k]) : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {  // suffix sums: lane l gets bins c0 + l .. c0 + 31
+      const int u = __shfl_down_sync(0xffffffffu, v, o);
+      if (lane + o < 32) v += u;
+    }
+    const unsigned ok = __ballot_sync(0xffffffffu, carry + v >= Ke);
+    if (ok) found = c0 + 31 - __clz(ok);
+    carry += __shfl_sync(0xffffffffu, v, 0);
+  }
+  if (found > 0 && 16u * static_cast<uint32_t>(found) + kBias > thb && lane == 0) atomicMax(theta_pair, 16u * static_cast<uint32_t>(found));
+}
+
 }  // namespace
 
 // PROF: experiments only — lane 0 of one warp per role accumulates the cycles it spends waiting on each
@@ -291,8 +311,8 @@ template <bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangles_mma_kernel(
     const PairDesc* __restrict__ descs, const uint2* __restrict__ tiles, int total_tiles,
     const uint32_t* __restrict__ adj, const uint32_t* __restrict__ panel, PairDev* __restrict__ state,
-    const ChunkDev* __restrict__ chunk, unsigned long long* __restrict__ keys, const uint32_t* __restrict__ theta,
-    uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2, int dbg) {
+    const ChunkDev* __restrict__ chunk, unsigned long long* __restrict__ keys, uint32_t* __restrict__ theta,
+    uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2, int Ke, int raise, int dbg) {
   if (chunk->overflow || !chunk->use_tensor) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stage_base = smem_raw;
@@ -368,6 +388,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     unsigned long long* kb = kbuf + warp * kKeySlots;
     EpiCtx* ctx = ectx + warp;
     int cur_pair = -1, cur_bins = 0;
+    bool dyn = false;  // this pair's threshold may still be raised while the kernel runs
     uint32_t thb = kBias;
     auto flush_pair = [&]() {  // all epilogue warps
       flush_keys(kb, ctx);
@@ -423,7 +444,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         if (cur_pair >= 0) flush_pair();
         cur_pair = pair;
         cur_bins = min(kHistBins, (d.N >> 4) + 1);
-        thb = theta[pair] + kBias;
+        // bit 31: tri_theta_kernel certified the threshold with a fat sample (>= 4 K_e edges): tight, leave it alone
+        const uint32_t traw = theta[pair];
+        dyn = raise != 0 && (traw >> 31) == 0u;
+        thb = (traw & 0x7FFFFFFFu) + kBias;
         __syncwarp();
         if (lane == 0) {
           ctx->keyp = keys + state[pair].key_base;
@@ -432,6 +456,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         }
         __syncwarp();
       }
+      // the pair's threshold as it stands now: other CTA pairs (and this one, below) raise it while they run
+      const uint32_t theta_now = dyn ? __ldcg(theta + cur_pair) : 0u;
       const long long tq1 = PROF ? clock64() : 0;
       uint32_t win[4];
       uint32_t wraw[5];
@@ -481,6 +507,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       SACCOT_TIMED_WAIT(w_tfull, mbar_wait_wd(&tmem_full[buf], static_cast<uint32_t>((n >> 1) & 1), 1, n));
       asm volatile("tcgen05.fence::after_thread_sync;");
       const uint32_t tbase = tmem + ((32u * q) << 16) + static_cast<uint32_t>(kMmaTileN * buf + 128 * h);
+      if (theta_now + kBias > thb) {  // warp-uniform
+        thb = theta_now + kBias;
+        __syncwarp();
+        if (lane == 0) ctx->thb = thb;
+        __syncwarp();
+      }
       // biased row sums of the four fragment rows t8 + 8 s of this thread (32 values each per tile)
       uint32_t rs0 = 0, rs1 = 0, rs2 = 0, rs3 = 0;
       uint32_t v[2][16];
@@ -576,6 +608,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0u);
+      // Dynamic pruning threshold.  hist_s counts (by T >> 4) the keys this CTA has kept for the pair since it last
+      // changed pairs; if K_e of them lie in bins >= b, then K_e edges with T >= 16 b exist and nothing below 16 b can
+      // be selected: raise the pair's threshold for everybody.  One warp per tile takes its turn.  (The sample-based
+      // threshold of tri_theta_kernel is loose when the inliers are few or the 512-column degree proxy misses them.)
+      if (dyn && warp == (n & (kEpiWarps - 1))) raise_threshold(hist_s, cur_bins, Ke, thb, theta + cur_pair);
       if (!(dbg & 1)) {
         // row sums (t2_i): reduce-scatter over the four lanes that share t8; the thread ends up with row t8 + 8 t4
         const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
@@ -942,7 +979,8 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
     }
     th = static_cast<uint32_t>(l2);
   }
-  if (t == 0) theta[pair] = th;
+  // bit 31: certified by a fat sample, the triangle kernel need not try to raise it
+  if (t == 0) theta[pair] = th | (nts >= 4 * Ke ? 0x80000000u : 0u);
 }
 
 int triangles_mma_configure() {
@@ -964,16 +1002,16 @@ int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
 
 int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_tiles, int total_tiles,
                          const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
-                         unsigned long long* d_keys, const uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
-                         int dbg) {
+                         unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
+                         int Ke, int raise, int dbg) {
   const int grid = 2 * mma_clusters(total_tiles, lc.sm_count);  // CTA pairs
   if (grid > 0) {
     if (dbg & 64)
       triangles_mma_kernel<true><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_adj, d_panel,
-                                                                           d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, dbg);
+                                                                           d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, Ke, raise, dbg);
     else
       triangles_mma_kernel<false><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_adj, d_panel,
-                                                                            d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, dbg);
+                                                                            d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, Ke, raise, dbg);
   }
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
