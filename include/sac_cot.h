@@ -96,7 +96,7 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
 /* Tunables/inspection by name; unknown names return SAC_COT_E_WHICH.
  *   set: "keep_debug" (0/1: retain per-pair intermediates for sac_cot_debug_get; forces
  *        chunk = whole batch), "chunk_pairs" (pairs per kernel wave, 0 = auto), "lanes" (1..4
- *        internal streams the chunks of a batch are dealt to, default 2; GPU only),
+ *        internal streams the chunks of a batch are dealt to, default 3; GPU only),
  *        "triangle_path" (0 = POPC bitset kernels, 1 = tensor-core dense kernel, 2 = chosen per chunk
  *        from the measured edge density (default); GPU only),
  *        "triangle_prune" (tensor-core path, default 1: keep only edge keys whose count reaches

@@ -155,7 +155,7 @@ struct sac_cot_ctx {
   int sm_count = 0;
   bool keep_debug = false;
   int chunk_pairs = 0;
-  int n_lanes = 2;
+  int n_lanes = 3;  // 3 chunks of ~86 pairs per 256-pair call: the uploads of later chunks hide behind the kernels of earlier ones
   int tri_path = 2;   // 0 = POPC bitset kernels, 1 = tensor-core (tcgen05 mxf4) kernel, 2 = by edge density per chunk
   int apex_path = 0;  // tests: 0 rank list, 1 exhaustive scan, 2 global-lookup kernel (kernels_select.cu)
   int tile_runs = 1;  // tensor-core path: deal tiles to the CTA pairs in runs (0: one at a time; experiments)

@@ -202,6 +202,7 @@ def test_device_resident_entry_point(gpu_lib, oracle):
     stream = torch.cuda.current_stream(dev)
     with Registrar(lib=gpu_lib, device=0, stream=stream.cuda_stream) as g:
         g.set("triangle_path", 0)
+        g.set("lanes", 2)
         g.register_packed_ptr(d_src.data_ptr(), d_dst.data_ptr(), offsets, d_R.data_ptr(), d_t.data_ptr(),
                               d_i.data_ptr(), _abi.LOC_DEVICE)
         stream.synchronize()
