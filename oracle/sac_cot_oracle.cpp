@@ -124,19 +124,15 @@ void build_graph(PairState& st) {
 // ---------------------------------------------------------------------------------------
 // S2 — compatibility-triangle counts.
 //   T_ij = popc(row_i & row_j) for every edge i<j;  t_i = 1/2 * sum_j A_ij T_ij.
-// `unit_filter`: sharded mode evaluates only the edges whose work unit belongs to this rank
-// (unit = (j>>7 column block, i>>8 row chunk); unit index % world == rank).  With world = 1
-// every edge is evaluated.  t_node then holds this rank's partial contribution.
+// `unit_filter`: sharded mode evaluates only the edges this rank owns (owner = (j / 1920) % world, j the larger
+// endpoint).  With world = 1 every edge is evaluated.  t_node then holds this rank's partial contribution.
 // ---------------------------------------------------------------------------------------
 inline uint32_t unit_owner(int i, int j, int world) {
-  // deterministic map of edge (i<j) to a rank; must match the GPU library's unit numbering
-  const uint32_t jb = static_cast<uint32_t>(j) >> 7;  // 128-column block of j
-  const uint32_t ic = static_cast<uint32_t>(i) >> 8;  // 256-row chunk of i
-  // triangular enumeration of (jb, ic) with ic <= jb/2 (since i<j): unit id = ic + offset(jb)
-  // offset(jb) = sum_{b<jb} (b/2+1)
-  const uint32_t h = jb >> 1;
-  const uint32_t offset = (jb & 1u) ? (h + 1) * (h + 1) : h * (h + 1);
-  return (offset + ic) % static_cast<uint32_t>(world);
+  // deterministic map of edge (i<j) to a rank; must match the GPU library: the owner of an edge is decided by
+  // the block of 1920 columns its larger endpoint j lies in (1920 = lcm(128, 240): whole 128-column units of the
+  // bitset kernels and whole 240-column tiles of the tensor-core kernel), dealt round-robin to the ranks
+  (void)i;
+  return (static_cast<uint32_t>(j) / 1920u) % static_cast<uint32_t>(world);
 }
 
 void count_triangles(PairState& st) {

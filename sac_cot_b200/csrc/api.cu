@@ -896,16 +896,35 @@ int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
     if (int rc = ensure_chunk_headers(ctx, 1)) return rc;
     ChunkDev* h_chunk = ctx->h_chunks[0];
     for (int attempt = 0; attempt < 3; ++attempt) {
-      plan(&N, 1, *params, true, false, ln.descs, ln.tile_tab, ln.lay);  // sharded phases use the POPC kernels
+      // S2 path as in the unsharded call (tensor cores for dense graphs); a rank owns the edges whose larger endpoint
+      // lies in its blocks of 1920 columns (common.cuh: owner_of_jb), i.e. whole 240-column tiles
+      const bool tensor = ctx->tri_path != 0;
+      plan(&N, 1, *params, true, tensor, ln.descs, ln.tile_tab, ln.lay);
+      if (tensor) {
+        if (world > 1) {
+          std::vector<uint2>& tab = ln.tile_tab;
+          size_t kept = 0;
+          for (size_t k = 0; k < tab.size(); ++k) {
+            const unsigned int jq = tab[k].y & 0xFFFFu;  // column block of the tile
+            if ((jq * static_cast<unsigned int>(kMmaTileN) / kOwnerCols) % static_cast<unsigned int>(world) == static_cast<unsigned int>(rank))
+              tab[kept++] = tab[k];
+          }
+          tab.resize(kept);
+          ln.lay.total_tiles = static_cast<int>(kept);
+        }
+        if (ctx->tile_runs) interleave_tile_runs(ln.tile_tab, ln.tile_scratch, ln.descs, ctx->sm_count);
+      }
       if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
       // a rank evaluates ~1/world of the edges: the unit scan counts only the owned units, so the
       // pool demand is ~E/world; the initial guess covers a whole pair at 12.5 % density
       if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
-      bind(ln.lay, ln.arena, true, false);
+      bind(ln.lay, ln.arena, true, tensor);
       ctx->prm = *params;
       Layout& L = ln.lay;
       if (int rc = fork_lanes(ctx, 1)) return rc;
       CU_TRY(cudaMemcpyAsync(L.desc, ln.descs.data(), sizeof(PairDesc), cudaMemcpyHostToDevice, ln.stream));
+      if (tensor && !ln.tile_tab.empty())
+        CU_TRY(cudaMemcpyAsync(L.tile_tab, ln.tile_tab.data(), sizeof(uint2) * ln.tile_tab.size(), cudaMemcpyHostToDevice, ln.stream));
       CU_TRY(cudaMemcpyAsync(L.in_src, src, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ln.stream));
       CU_TRY(cudaMemcpyAsync(L.in_dst, dst, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ln.stream));
       if (int rc = enqueue_pipeline(ctx, ln, L.in_src, L.in_dst, nullptr, nullptr, nullptr, rank, world, true)) return rc;

@@ -41,6 +41,7 @@ struct PairDev {
   uint32_t tie_inplace;          // 1: tie bucket too large for the tie list, scan keys in place
   uint32_t n_sel;                // number of selected edges = min(K_e, evaluated edges)
   uint32_t pad_;
+  unsigned long long all_edges;  // edges of the whole pair (== num_edges unless sharded): decides the S2 path
 };
 
 struct ChunkDev {
@@ -125,6 +126,21 @@ __host__ __device__ inline unsigned int unit_offset(unsigned int jb) {
   return (jb & 1u) ? (h + 1) * (h + 1) : h * (h + 1);
 }
 __host__ __device__ inline unsigned int unit_count(unsigned int nblk) { return unit_offset(nblk); }
+// Sharded single-pair runs: the owner of an edge (i < j) is decided by the block of 1920 columns j lies in
+// (1920 = lcm(128, 240): whole 128-column units of the bitset kernels and whole 240-column tiles of the
+// tensor-core kernel), dealt round-robin to the ranks.  The oracle uses the same rule.
+constexpr unsigned int kOwnerCols = 1920;
+__host__ __device__ inline unsigned int owner_of_jb(unsigned int jb, unsigned int world) {
+  return (jb / (kOwnerCols / 128u)) % world;
+}
+// column block jb of unit id u (inverse of unit_offset)
+__host__ __device__ inline unsigned int unit_jb(unsigned int u) {
+  unsigned int jb = static_cast<unsigned int>(2.0f * sqrtf(static_cast<float>(u)));
+  while (unit_offset(jb) > u) --jb;
+  while (unit_offset(jb + 1) <= u) ++jb;
+  return jb;
+}
+__host__ __device__ inline unsigned int owner_of_unit(unsigned int u, unsigned int world) { return owner_of_jb(unit_jb(u), world); }
 
 struct LaunchCtx {
   cudaStream_t stream;

@@ -310,13 +310,23 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const PairDesc* __restr
   const uint32_t* cnt = ucount + static_cast<size_t>(pair) * unit_pitch;
   uint32_t* out = ubase + static_cast<size_t>(pair) * unit_pitch;
   __shared__ unsigned int wsum[32];
-  __shared__ unsigned long long carry;
+  __shared__ unsigned long long carry, all_edges;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (t == 0) carry = 0;
+  if (t == 0) {
+    carry = 0;
+    all_edges = 0;
+  }
   __syncthreads();
+  {  // edges of the whole pair, whoever owns them
+    unsigned long long a = 0;
+    for (unsigned int u = t; u < U; u += 1024) a += cnt[u];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0 && a) atomicAdd(&all_edges, a);
+  }
   for (unsigned int u0 = 0; u0 < U; u0 += 1024) {
     const unsigned int u = u0 + t;
-    const bool owned = u < U && (world <= 1 || (u % static_cast<unsigned int>(world)) == static_cast<unsigned int>(rank));
+    const bool owned = u < U && (world <= 1 || owner_of_unit(u, static_cast<unsigned int>(world)) == static_cast<unsigned int>(rank));
     const unsigned int v = owned ? cnt[u] : 0u;
     unsigned int incl = v;  // warp inclusive scan
 #pragma unroll
@@ -344,6 +354,7 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const PairDesc* __restr
   }
   if (t == 0) {
     state[pair].num_edges = carry;
+    state[pair].all_edges = all_edges;
     state[pair].key_count = carry;  // the key scan zeroes it again if the tensor-core kernel is chosen
   }
 }
@@ -367,24 +378,28 @@ __global__ void __launch_bounds__(1024) key_scan_kernel(const PairDesc* __restri
   __shared__ unsigned long long part[1024];
   __shared__ unsigned long long carry;
   __shared__ unsigned long long node_pairs;  // sum of N (N - 1) / 2 over the chunk
+  __shared__ unsigned long long all_total;   // sum of the pairs' edge counts (owned or not)
   __shared__ int max_n;
   __shared__ uint32_t s_tensor;
   const int t = threadIdx.x;
   if (t == 0) {
     carry = 0;
     node_pairs = 0;
+    all_total = 0;
     max_n = 0;
   }
   __syncthreads();
   if (tri_mode == 2) {
-    unsigned long long np = 0;
+    unsigned long long np = 0, ae = 0;
     int mn = 0;
     for (int b = t; b < pairs; b += 1024) {
       const unsigned long long n = static_cast<unsigned long long>(descs[b].N);
       np += n * (n - 1) / 2;
       mn = max(mn, descs[b].N);
+      ae += state[b].all_edges;
     }
     if (np) atomicAdd(&node_pairs, np);
+    if (ae) atomicAdd(&all_total, ae);
     if (mn) atomicMax(&max_n, mn);
   }
   for (int b0 = 0; b0 < pairs; b0 += 1024) {
@@ -407,7 +422,7 @@ __global__ void __launch_bounds__(1024) key_scan_kernel(const PairDesc* __restri
     // S2 path of the chunk: the dense tensor-core kernel costs ~N^3, the POPC kernels ~E N / 32
     uint32_t tensor = tri_mode == 1 ? 1u : 0u;
     if (tri_mode == 2)
-      tensor = (max_n >= kTensorMinN && static_cast<float>(carry) >= kTensorMinDensity * static_cast<float>(node_pairs)) ? 1u : 0u;
+      tensor = (max_n >= kTensorMinN && static_cast<float>(all_total) >= kTensorMinDensity * static_cast<float>(node_pairs)) ? 1u : 0u;  // density of the whole graph: the same decision on every rank of a sharded run
     s_tensor = tensor;
     chunk->use_tensor = tensor;
     chunk->total_edges = carry;

@@ -134,11 +134,9 @@ struct EdgeBits {
       else if (li >= 32 * k) w[k] &= 0xffffffffu << ((li & 31) + 1);
     }
     if (world > 1) {
-      const unsigned int ic = static_cast<unsigned int>(i) >> 8;
 #pragma unroll
       for (int s = 0; s < NB; ++s) {
-        const unsigned int unit = unit_offset(jb0 + s) + ic;
-        if ((unit % static_cast<unsigned int>(world)) != static_cast<unsigned int>(rank)) {
+        if (owner_of_jb(jb0 + s, static_cast<unsigned int>(world)) != static_cast<unsigned int>(rank)) {
           w[4 * s + 0] = 0u; w[4 * s + 1] = 0u; w[4 * s + 2] = 0u; w[4 * s + 3] = 0u;
         }
       }
@@ -252,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) triangles_block_kernel(
     }
     if (world > 1) {  // sharded: keep only the sub-blocks whose unit this rank owns
       const uint32_t unit = ((NB == 2 && lane >= 16) ? unit1 : unit0) + (static_cast<unsigned int>(i) >> 8);
-      if ((unit % static_cast<unsigned int>(world)) != static_cast<unsigned int>(rank)) bits = 0u;
+      if (owner_of_unit(unit, static_cast<unsigned int>(world)) != static_cast<unsigned int>(rank)) bits = 0u;
     }
     // ordinal of each lane's first edge: inclusive warp scan of the per-byte counts
     const int cnt = __popc(bits);
@@ -361,7 +359,7 @@ __global__ void __launch_bounds__(kTriThreads) triangles_chunked_kernel(
   const PairDesc d = descs[pair];
   const unsigned int unit = blockIdx.x;
   if (unit >= unit_count(static_cast<unsigned int>(d.nblk))) return;
-  if (world > 1 && (unit % static_cast<unsigned int>(world)) != static_cast<unsigned int>(rank)) return;
+  if (world > 1 && owner_of_unit(unit, static_cast<unsigned int>(world)) != static_cast<unsigned int>(rank)) return;
   unsigned int jb = static_cast<unsigned int>(2.0f * sqrtf(static_cast<float>(unit)));
   if (jb >= static_cast<unsigned int>(d.nblk)) jb = d.nblk - 1;
   while (unit_offset(jb) > unit) --jb;

@@ -213,9 +213,12 @@ def test_device_resident_entry_point(gpu_lib, oracle):
         compare_pose(d_R[b].cpu().numpy(), d_t[b].cpu().numpy(), int(d_i[b]), ro.R[b], ro.t[b], ro.inliers[b])
 
 
+@pytest.mark.parametrize("path", [0, 2])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_phases_match_unsharded_and_oracle(gpu_lib, oracle_lib, world):
-    # ranks emulated one after the other on the single GPU (no kernel waits on another)
+def test_sharded_phases_match_unsharded_and_oracle(gpu_lib, oracle_lib, world, path):
+    # ranks emulated one after the other on the single GPU (no kernel waits on another).
+    # path 0: POPC kernels; path 2: the library's choice, the tensor-core kernel at this size and density
+    # (a rank then runs the 240-column tiles of its blocks of 1920 columns).
     N = 6000
     p = synth.make_pair(N, 0.05, 8100)
     with Registrar(lib=gpu_lib) as one:
@@ -223,16 +226,31 @@ def test_sharded_phases_match_unsharded_and_oracle(gpu_lib, oracle_lib, world):
     ranks = [Registrar(lib=gpu_lib) for _ in range(world)]
     oranks = [Registrar(lib=oracle_lib) for _ in range(world)]
     try:
+        for r in ranks:
+            r.set("triangle_path", path)
         ph = [r.sharded_phase1(p.src, p.dst, g, world) for g, r in enumerate(ranks)]
         oph = [r.sharded_phase1(p.src, p.dst, g, world) for g, r in enumerate(oranks)]
+        used = [r.get("triangle_path_used") for r in ranks]
+        assert used == [1 if path else 0] * world   # decided by the density of the whole graph: the same on every rank
+        # the global K_e-th key: what a rank's list must contain at least
+        union = np.sort(np.concatenate([x[1] for x in oph]))[::-1]
+        kth = union[len(ph[0][1]) - 1]
         for g in range(world):
             np.testing.assert_array_equal(ph[g][0], oph[g][0])   # partial node sums, bit-exact per rank
-            np.testing.assert_array_equal(ph[g][1], oph[g][1])   # local top-K_e candidates
+            if path == 0:
+                np.testing.assert_array_equal(ph[g][1], oph[g][1])   # local top-K_e candidates
+            else:
+                # pruned: a rank keeps its edges at or above a threshold that at least K_e edges of the WHOLE graph
+                # reach: its list is sorted, duplicate-free, and holds every local candidate that can be selected
+                mine, ref = ph[g][1], oph[g][1]
+                nz = mine[mine != 0]
+                assert (np.diff(nz.astype(np.int64)) < 0).all() if len(nz) > 1 else True
+                assert np.isin(ref[ref >= kth], nz).all()
         t_all = np.stack([x[0] for x in ph])
         c_all = np.stack([x[1] for x in ph])
         keys = [r.sharded_phase2(t_all, c_all) for r in ranks]
-        okeys = [r.sharded_phase2(t_all, c_all) for r in oranks]
-        assert keys == okeys
+        okeys = [r.sharded_phase2(np.stack([x[0] for x in oph]), np.stack([x[1] for x in oph])) for r in oranks]
+        assert keys == okeys   # merged selection, hypotheses and scores are the same with either candidate lists
         best = max(keys)
         for r in ranks:
             R, t, inl = r.sharded_phase3(best)
