@@ -193,18 +193,23 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
   uint32_t words[4];
 #pragma unroll
   for (int cw = 0; cw < 4; ++cw) {
+    // The word is assembled by shifting one sign bit in per test (one funnel shift each): column groups from the
+    // top of the word down, and the four columns of a group from the last to the first, so that every bit ends
+    // up at its column's position.
     uint32_t wbits = 0;
 #pragma unroll 2
-    for (int b = 0; b < 32; b += 4) {
+    for (int b = 28; b >= 0; b -= 4) {
       const int c = cw * 32 + b;
-      if (c >= ncv || !row_valid) continue;  // c >= ncv is uniform over the CTA
+      if (c >= ncv || !row_valid) {  // c >= ncv is uniform over the CTA
+        wbits <<= 4;
+        continue;
+      }
       float4 cj[6];  // four staged columns per 128-bit broadcast load
 #pragma unroll
       for (int k = 0; k < 6; ++k) cj[k] = *reinterpret_cast<const float4*>(&cs[k][c]);
       bool sure = true;
-      uint32_t nib = 0;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {  // two packed column pairs
+      for (int h = 1; h >= 0; --h) {  // two packed column pairs: columns c+2, c+3 first
         f32x2 col[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) col[k] = h == 0 ? pack2(cj[k].x, cj[k].y) : pack2(cj[k].z, cj[k].w);
@@ -223,12 +228,11 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
         unpack2(T, t0, t1);
         unpack2(S, s0, s1);
         sure = sure && fabsf(q0) > t0 && s0 > lo && fabsf(q1) > t1 && s1 > lo;
-        nib |= (__float_as_uint(q0) >> 31) << (2 * h);      // bit = (Q < 0) when sure
-        nib |= (__float_as_uint(q1) >> 31) << (2 * h + 1);
+        wbits = __funnelshift_l(__float_as_uint(q1), wbits, 1);  // bit = (Q < 0) when sure
+        wbits = __funnelshift_l(__float_as_uint(q0), wbits, 1);
       }
       if (!sure)  // rare: inside the rounding band, out-of-range magnitudes, or NaN (pad columns)
-        nib = compat_literal4(cs, c, rv[0], rv[1], rv[2], rv[3], rv[4], rv[5], tau);
-      wbits |= nib << b;
+        wbits = (wbits & ~0xFu) | compat_literal4(cs, c, rv[0], rv[1], rv[2], rv[3], rv[4], rv[5], tau);
     }
     words[cw] = wbits;
   }
