@@ -272,14 +272,21 @@ __device__ __forceinline__ void push16(const uint32_t (&m)[16], uint32_t fa, uin
   }
 }
 
-// One warp: highest histogram bin b with at least Ke kept keys in bins >= b -> the pair's threshold becomes
+// One warp: moves this CTA's histogram of kept keys (by T >> 4) into the pair's global histogram and finds, in the
+// GLOBAL counts, the highest bin b with at least Ke keys in bins >= b: then Ke edges with T >= 16 b exist (every
+// counted key is in a key list or in a staging buffer on its way there) and the pair's threshold becomes
 // max(threshold, 16 b).  Out of line: it runs once per tile in one warp and must not fatten the hot loop.
-__device__ __noinline__ void raise_threshold(const uint32_t* hist_s, int cur_bins, int Ke, uint32_t thb, uint32_t* theta_pair) {
+__device__ __noinline__ void raise_threshold(uint32_t* hist_s, uint32_t* histp, int cur_bins, int Ke, uint32_t thb,
+                                             uint32_t* theta_pair) {
   const int lane = threadIdx.x & 31;
   int carry = 0, found = -1;
   for (int c0 = (cur_bins - 1) & ~31; c0 >= 0 && found < 0; c0 -= 32) {
     const int k = c0 + lane;
-    int v = k < cur_bins ? static_cast<int>(hist_s[k]) : 0;
+    int v = 0;
+    if (k < cur_bins) {
+      const uint32_t delta = hist_s[k] ? atomicExch(&hist_s[k], 0u) : 0u;
+      v = static_cast<int>(delta ? atomicAdd(&histp[k], delta) + delta : __ldcg(&histp[k]));
+    }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {  // suffix sums: lane l gets bins c0 + l .. c0 + 31
       const int u = __shfl_down_sync(0xffffffffu, v, o);
@@ -612,7 +619,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       // changed pairs; if K_e of them lie in bins >= b, then K_e edges with T >= 16 b exist and nothing below 16 b can
       // be selected: raise the pair's threshold for everybody.  One warp per tile takes its turn.  (The sample-based
       // threshold of tri_theta_kernel is loose when the inliers are few or the 512-column degree proxy misses them.)
-      if (dyn && warp == (n & (kEpiWarps - 1))) raise_threshold(hist_s, cur_bins, Ke, thb, theta + cur_pair);
+      if (dyn && warp == (n & (kEpiWarps - 1))) raise_threshold(hist_s, hist + static_cast<size_t>(cur_pair) * kHistBins, cur_bins, Ke, thb, theta + cur_pair);
       if (!(dbg & 1)) {
         // row sums (t2_i): reduce-scatter over the four lanes that share t8; the thread ends up with row t8 + 8 t4
         const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
