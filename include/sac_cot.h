@@ -55,7 +55,9 @@ enum {
   SAC_COT_E_UNSUPPORTED  = -5,  /* entry point not provided by this implementation         */
   SAC_COT_E_WHICH        = -6,  /* debug_get: unknown selector or pair index               */
   SAC_COT_E_CAPACITY     = -7,  /* debug_get: caller buffer too small (written = needed)   */
-  SAC_COT_E_NOMEM        = -8   /* workspace could not be allocated                        */
+  SAC_COT_E_NOMEM        = -8,  /* workspace could not be allocated                        */
+  SAC_COT_E_COMM         = -9   /* GPU library only: no communicator on the ctx, NCCL not
+                                   loadable, or an NCCL call failed                        */
   /* > 0 : cudaError_t of the failing CUDA call (GPU library only)                          */
 };
 
@@ -111,9 +113,15 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *   get: "triangle_path_used" (0/1: which S2 kernels the latest chunk ran; synchronises; GPU only),
  *        "launches" (kernels launched since ctx creation), "workspace_bytes",
  *        "device", "sm_count", "retries" (workspace-growth re-runs),
- *        "last_status" (deferred status of the latest SAC_COT_LOC_DEVICE call; synchronises),
- *        "stage_us_<s>" / "stage_calls_<s>" with <s> in pack, graph, scan, triangles, select,
- *        apex, kabsch, score, finalize: accumulated device microseconds / launches      */
+ *        "last_status" (deferred status of the SAC_COT_LOC_DEVICE calls since the previous query: SAC_COT_E_NOMEM
+ *        if a chunk of any of them ran out of key-pool space — its outputs read "no result" and the pool has been
+ *        grown for the next call; synchronises),
+ *        "probe_mxf4_gflops" (measures, now, the dense rate of the tensor-core triangle kernel's MMA shape with
+ *        nothing else running: the roofline denominator bench.py reports against; synchronises; GPU only),
+ *        "stage_us_<s>" / "stage_calls_<s>" with <s> in pack, graph, scan, theta, triangles, select,
+ *        apex, kabsch, score, finalize, exchange1 (sharded: record + all-gather + merge), exchange2
+ *        (sharded: all-reduce): accumulated device microseconds / launches,
+ *        "comm_rank", "comm_world" (0 = no communicator)                                 */
 SAC_COT_API int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value);
 SAC_COT_API int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value);
 
@@ -142,21 +150,56 @@ SAC_COT_API int sac_cot_register_packed(sac_cot_ctx* ctx,
                                         int32_t location);
 
 /* ------------------------------------------------------------------ one large pair, sharded */
-/* A single pair whose triangle-count work units and hypothesis ranges are split over
- * `world` ranks (one process per GPU).  The library never communicates: the host layer
- * above it performs exactly two exchanges between the three phases:
+/* A single pair whose triangle-count work and hypothesis ranges are split over `world` ranks, one
+ * process (or thread) per GPU, every rank holding the same src/dst (BASELINE.json
+ * configs[4]).  Exactly two exchanges:
  *
- *   phase 1  graph (full, local) + triangle counts for this rank's work units
- *            -> t_partial[N] (u64, sum of T_ij over this rank's edges incident to node i;
- *               summed over ranks it equals 2*t_i)
- *            -> cand[K_e] (u64 edge keys, this rank's top-K_e, descending, 0-padded)
- *   exchange #1: all-gather t_partial and cand over ranks
- *   phase 2  merge (sum of t_partial; top-K_e of the gathered candidates), apexes, Kabsch,
- *            score this rank's hypothesis range -> best_key (u64, 0 = none)
- *   exchange #2: all-reduce(max) of best_key
- *   phase 3  inlier mask + refit of the global winner (every rank computes the same result)
+ *   part 1   graph (full, local) + triangle counts of the cells this rank owns
+ *            -> partial node sums (u64[N]; summed over the ranks they equal 2*t_i)
+ *            -> this rank's top-K_e edge keys (descending, 0-padded)
+ *   exchange #1: all-gather of both
+ *   part 2   merge (sum; top-K_e of the union), apexes, Kabsch, scoring of this rank's hypothesis
+ *            range -> best key of the range
+ *   exchange #2: all-reduce(max) of the packed (score, hypothesis id) key
+ *   part 3   inlier mask + refit of the global winner; every rank returns the same (R, t, inliers),
+ *            bit-identical to the unsharded call.
  *
- * All buffers are host arrays; t_all is world x N, cand_all is world x K_e.            */
+ * "S2 partition" (normative): edge (i < j) lies in cell (cb, ic) = (j / 1920, i / 256) and cell
+ * (cb, ic) belongs to rank (257*cb + ic) mod world; hypothesis h belongs to rank h / ceil(K/world).
+ *
+ * Two ways to run it:
+ *
+ * (a) sac_cot_register_sharded — the GPU library does everything, collectives included: the ctx
+ *     holds an NCCL communicator (created once by sac_cot_ctx_comm_init, or adopted with
+ *     sac_cot_ctx_set_comm) and ncclAllGather / ncclAllReduce(ncclUint64, ncclMax) are enqueued
+ *     on the ctx's own stream between the kernels, device buffer to device buffer, with no host
+ *     synchronisation between the parts.  Collective call: every rank of the communicator calls it
+ *     with the same src/dst/N/params.
+ *
+ * (b) sac_cot_sharded_phase{1,2,3} — the three parts with host arrays in between, for callers
+ *     that bring their own transport (MPI, gloo, a test harness emulating the ranks).            */
+
+/* ---- (a) in-library collectives (GPU library only; NCCL is loaded with dlopen("libnccl.so.2")
+ * on first use, so the library itself has no link-time NCCL dependency) */
+#define SAC_COT_COMM_ID_BYTES 128   /* sizeof(ncclUniqueId) */
+/* Rank 0 creates an id (ncclGetUniqueId) and hands the 128 bytes to every rank by any means
+ * (torch.distributed broadcast, MPI_Bcast, a file); then every rank calls comm_init
+ * (ncclCommInitRank on the ctx device; collective, blocks until all ranks have joined). */
+SAC_COT_API int sac_cot_comm_unique_id(void* id_out /* SAC_COT_COMM_ID_BYTES */);
+SAC_COT_API int sac_cot_ctx_comm_init(sac_cot_ctx* ctx, const void* id, int32_t rank, int32_t world);
+/* Adopts an existing ncclComm_t whose device is the ctx device (the caller keeps ownership and
+ * must keep it alive while the ctx uses it); comm = NULL detaches. */
+SAC_COT_API int sac_cot_ctx_set_comm(sac_cot_ctx* ctx, void* nccl_comm, int32_t rank, int32_t world);
+/* location = SAC_COT_LOC_HOST: host buffers, the call returns when (R, t, inliers) are written; a key
+ * pool that proves too small on ANY rank is grown on every rank and the pair re-run, in step.
+ * location = SAC_COT_LOC_DEVICE: device buffers on the ctx device, enqueue only (status through
+ * sac_cot_ctx_get("last_status"), the same on every rank).
+ * Without a communicator: SAC_COT_E_COMM.  The oracle implements it for world = 1 only. */
+SAC_COT_API int sac_cot_register_sharded(sac_cot_ctx* ctx, const float* src, const float* dst, int32_t N,
+                                         const sac_cot_params* params,
+                                         float R[9], float t[3], int32_t* inliers, int32_t location);
+
+/* ---- (b) the parts, host arrays in and out; t_all is world x N, cand_all is world x K_e */
 SAC_COT_API int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
                                        int32_t N, const sac_cot_params* params,
                                        int32_t rank, int32_t world,

@@ -124,15 +124,14 @@ void build_graph(PairState& st) {
 // ---------------------------------------------------------------------------------------
 // S2 — compatibility-triangle counts.
 //   T_ij = popc(row_i & row_j) for every edge i<j;  t_i = 1/2 * sum_j A_ij T_ij.
-// `unit_filter`: sharded mode evaluates only the edges this rank owns (owner = (j / 1920) % world, j the larger
-// endpoint).  With world = 1 every edge is evaluated.  t_node then holds this rank's partial contribution.
+// Sharded mode ("S2 partition") evaluates only the edges this rank owns: edge (i < j) lies in cell
+// (cb, ic) = (j / 1920, i / 256) and cell (cb, ic) belongs to rank (257 cb + ic) mod world.  The partition only
+// decides WHO counts an edge, never a value: summed over the ranks the results are those of world = 1.  With
+// world = 1 every edge is evaluated.  t_node then holds this rank's partial contribution.
 // ---------------------------------------------------------------------------------------
-inline uint32_t unit_owner(int i, int j, int world) {
-  // deterministic map of edge (i<j) to a rank; must match the GPU library: the owner of an edge is decided by
-  // the block of 1920 columns its larger endpoint j lies in (1920 = lcm(128, 240): whole 128-column units of the
-  // bitset kernels and whole 240-column tiles of the tensor-core kernel), dealt round-robin to the ranks
-  (void)i;
-  return (static_cast<uint32_t>(j) / 1920u) % static_cast<uint32_t>(world);
+inline uint32_t edge_owner(int i, int j, int world) {
+  const uint32_t cb = static_cast<uint32_t>(j) / 1920u, ic = static_cast<uint32_t>(i) / 256u;
+  return (257u * cb + ic) % static_cast<uint32_t>(world);
 }
 
 void count_triangles(PairState& st) {
@@ -153,7 +152,7 @@ void count_triangles(PairState& st) {
     std::vector<uint64_t>& out = per_row[i];
     for (int j = i + 1; j < N; ++j) {
       if (!((A[static_cast<size_t>(i) * W + (j >> 5)] >> (j & 31)) & 1u)) continue;
-      if (st.world > 1 && unit_owner(i, j, st.world) != static_cast<uint32_t>(st.rank)) continue;
+      if (st.world > 1 && edge_owner(i, j, st.world) != static_cast<uint32_t>(st.rank)) continue;
       const uint64_t* rj = reinterpret_cast<const uint64_t*>(A + static_cast<size_t>(j) * W);
       uint32_t T = 0;
       for (int w = 0; w < W64; ++w) T += static_cast<uint32_t>(__builtin_popcountll(ri[w] & rj[w]));
@@ -551,6 +550,14 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return SAC_COT_E_NULL;
   if (!std::strcmp(name, "keep_debug")) { ctx->keep_debug = value != 0; return SAC_COT_OK; }
   if (!std::strcmp(name, "chunk_pairs") || !std::strcmp(name, "triangle_path")) return SAC_COT_OK;
+  if (!std::strcmp(name, "threads")) {  // OpenMP build: worker threads of the calls that follow (a launcher may have
+                                        // exported OMP_NUM_THREADS=1); ignored by the single-thread build
+    if (value < 1) return SAC_COT_E_SIZE;
+#ifdef _OPENMP
+    omp_set_num_threads(static_cast<int>(value));
+#endif
+    return SAC_COT_OK;
+  }
   return SAC_COT_E_WHICH;
 }
 
@@ -695,6 +702,32 @@ int sac_cot_sharded_phase3(sac_cot_ctx* ctx, uint64_t best_key_global, float R[9
   return SAC_COT_OK;
 }
 
+// ---- in-library collectives: the oracle is a single process; it has no communicator ---------
+int sac_cot_comm_unique_id(void* id_out) { return id_out ? SAC_COT_E_UNSUPPORTED : SAC_COT_E_NULL; }
+int sac_cot_ctx_comm_init(sac_cot_ctx* ctx, const void* id, int32_t, int32_t) {
+  return (ctx && id) ? SAC_COT_E_UNSUPPORTED : SAC_COT_E_NULL;
+}
+int sac_cot_ctx_set_comm(sac_cot_ctx* ctx, void*, int32_t, int32_t) { return ctx ? SAC_COT_E_UNSUPPORTED : SAC_COT_E_NULL; }
+
+// world = 1: the three parts back to back (the partition then holds every edge and every hypothesis)
+int sac_cot_register_sharded(sac_cot_ctx* ctx, const float* src, const float* dst, int32_t N,
+                             const sac_cot_params* params, float R[9], float t[3], int32_t* inliers,
+                             int32_t location) {
+  if (!ctx || !src || !dst || !R || !t || !inliers) return SAC_COT_E_NULL;
+  if (location != SAC_COT_LOC_HOST) return SAC_COT_E_UNSUPPORTED;
+  if (N < 3 || N > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
+  if (int rc = check_params(params)) return rc;
+  try {
+    std::vector<uint64_t> t_partial(static_cast<size_t>(N)), cand(static_cast<size_t>(params->num_edges));
+    if (int rc = sac_cot_sharded_phase1(ctx, src, dst, N, params, 0, 1, t_partial.data(), cand.data())) return rc;
+    uint64_t best = 0;
+    if (int rc = sac_cot_sharded_phase2(ctx, t_partial.data(), cand.data(), &best)) return rc;
+    return sac_cot_sharded_phase3(ctx, best, R, t, inliers);
+  } catch (const std::bad_alloc&) {
+    return SAC_COT_E_NOMEM;
+  }
+}
+
 // ---- debug getter -------------------------------------------------------------------
 int sac_cot_debug_get(sac_cot_ctx* ctx, int32_t pair, int32_t which, void* out, size_t cap,
                       size_t* written) {
@@ -738,6 +771,7 @@ const char* sac_cot_strerror(int status) {
     case SAC_COT_E_WHICH: return "unknown selector / index";
     case SAC_COT_E_CAPACITY: return "output buffer too small";
     case SAC_COT_E_NOMEM: return "out of memory";
+    case SAC_COT_E_COMM: return "no communicator (the oracle is a single process)";
     default: return "unknown status";
   }
 }

@@ -17,7 +17,8 @@ MAX_APEX = 8
 MAX_HYPOTHESES = 32768
 
 OK = 0
-E_NULL, E_SIZE, E_PARAMS, E_NODEVICE, E_UNSUPPORTED, E_WHICH, E_CAPACITY, E_NOMEM = -1, -2, -3, -4, -5, -6, -7, -8
+E_NULL, E_SIZE, E_PARAMS, E_NODEVICE, E_UNSUPPORTED, E_WHICH, E_CAPACITY, E_NOMEM, E_COMM = -1, -2, -3, -4, -5, -6, -7, -8, -9
+COMM_ID_BYTES = 128
 
 SCORE_INLIER_COUNT = 0
 SCORE_TRUNCATED_RESIDUAL = 1
@@ -65,6 +66,11 @@ SYMBOLS = {
                                          C.POINTER(Params), _f32p, _f32p, _i32p]),
     "sac_cot_register_packed": (C.c_int, [_ctxp, C.c_void_p, C.c_void_p, _i64p, C.c_int32,
                                           C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "sac_cot_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "sac_cot_ctx_comm_init": (C.c_int, [_ctxp, C.c_void_p, C.c_int32, C.c_int32]),
+    "sac_cot_ctx_set_comm": (C.c_int, [_ctxp, C.c_void_p, C.c_int32, C.c_int32]),
+    "sac_cot_register_sharded": (C.c_int, [_ctxp, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(Params),
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "sac_cot_sharded_phase1": (C.c_int, [_ctxp, _f32p, _f32p, C.c_int32, C.POINTER(Params), C.c_int32,
                                          C.c_int32, _u64p, _u64p]),
     "sac_cot_sharded_phase2": (C.c_int, [_ctxp, _u64p, _u64p, _u64p]),

@@ -56,10 +56,11 @@ def _pack(pairs_src, pairs_dst):
     ns = [int(np.asarray(s).shape[0]) for s in pairs_src]
     offsets = np.zeros(len(ns) + 1, dtype=np.int64)
     np.cumsum(ns, out=offsets[1:])
+    nd = [int(np.asarray(d).shape[0]) for d in pairs_dst]
+    if ns != nd:
+        raise ValueError("src and dst must hold the same number of points per pair")
     src = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float32).reshape(-1, 3) for s in pairs_src]))
     dst = np.ascontiguousarray(np.concatenate([np.asarray(d, dtype=np.float32).reshape(-1, 3) for d in pairs_dst]))
-    if src.shape != dst.shape:
-        raise ValueError("src and dst must hold the same number of points per pair")
     return src, dst, offsets
 
 
@@ -122,6 +123,10 @@ class Registrar:
     def register_packed(self, src: np.ndarray, dst: np.ndarray, offsets: np.ndarray) -> Result:
         """Pairs packed back to back in host arrays; see sac_cot_register_packed."""
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        src = np.ascontiguousarray(src, dtype=np.float32).reshape(-1, 3)
+        dst = np.ascontiguousarray(dst, dtype=np.float32).reshape(-1, 3)
+        if offsets.ndim != 1 or len(offsets) < 1 or offsets[0] != 0 or not (len(src) == len(dst) == offsets[-1]):
+            raise ValueError("offsets must start at 0 and end at the number of points of src and of dst")
         B = len(offsets) - 1
         R = np.empty((B, 3, 3), np.float32)
         t = np.empty((B, 3), np.float32)
@@ -194,13 +199,67 @@ class Registrar:
             raise SacCotError(rc, "sac_cot_sharded_phase3", self.lib)
         return R, t, int(inl.value)
 
-    def register_sharded(self, src, dst, group=None):
-        """One large pair split over the ranks of a torch.distributed process group.
+    # -- in-library collectives (GPU library: NCCL communicator held by the ctx) -------------
+    def comm_init(self, group=None, rank: int | None = None, world: int | None = None, unique_id: bytes | None = None):
+        """Creates the ctx's NCCL communicator (sac_cot_ctx_comm_init; collective over the ranks).
 
-        Exactly two exchanges: all-gather of the per-node partial triangle
-        sums and each rank's top-K_e edge candidates, then all-reduce(max) of the packed
-        (score, hypothesis id) key.  Works on any backend (NCCL over NVLink on GPUs; gloo in
-        the CPU tests).  Every rank returns the same (R, t, inliers)."""
+        With a torch.distributed process group (default: the world group) rank 0 draws the unique id
+        (sac_cot_comm_unique_id) and broadcasts its 128 bytes over that group — any backend will do, the id is
+        plain data.  Without torch.distributed pass rank, world and the id obtained on rank 0."""
+        if unique_id is None:
+            import torch
+            import torch.distributed as dist
+
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            buf = (C.c_ubyte * _abi.COMM_ID_BYTES)()
+            if rank == 0:
+                rc = self.lib.sac_cot_comm_unique_id(buf)
+                if rc != _abi.OK:
+                    raise SacCotError(rc, "sac_cot_comm_unique_id", self.lib)
+            dev = torch.device("cuda", self.get("device")) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            tid = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+            dist.broadcast(tid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            unique_id = bytes(tid.cpu().tolist())
+        if len(unique_id) != _abi.COMM_ID_BYTES:
+            raise ValueError(f"unique_id must be {_abi.COMM_ID_BYTES} bytes")
+        rc = self.lib.sac_cot_ctx_comm_init(self._ctx, unique_id, int(rank), int(world))
+        if rc != _abi.OK:
+            raise SacCotError(rc, "sac_cot_ctx_comm_init", self.lib)
+
+    def set_comm(self, nccl_comm: int, rank: int, world: int):
+        """Adopts an existing ncclComm_t (raw handle); 0 detaches."""
+        rc = self.lib.sac_cot_ctx_set_comm(self._ctx, C.c_void_p(nccl_comm), rank, world)
+        if rc != _abi.OK:
+            raise SacCotError(rc, "sac_cot_ctx_set_comm", self.lib)
+
+    def register_sharded_ptr(self, src_ptr: int, dst_ptr: int, N: int, R_ptr: int, t_ptr: int, inl_ptr: int,
+                             location: int):
+        """Raw-pointer form of sac_cot_register_sharded (host or device buffers); enqueue-only for LOC_DEVICE."""
+        rc = self.lib.sac_cot_register_sharded(self._ctx, src_ptr, dst_ptr, int(N), C.byref(self.params), R_ptr, t_ptr,
+                                               inl_ptr, location)
+        if rc != _abi.OK:
+            raise SacCotError(rc, "sac_cot_register_sharded", self.lib)
+
+    def register_sharded(self, src, dst, group=None):
+        """One large pair split over the ranks: exactly two exchanges — all-gather of the
+        per-node partial triangle sums and each rank's top-K_e edge candidates, then all-reduce(max) of the
+        packed (score, hypothesis id) key.  Every rank returns the same (R, t, inliers).
+
+        If the ctx holds a communicator (comm_init / set_comm) this is a call-through to
+        sac_cot_register_sharded: the library enqueues kernels and NCCL collectives on its own stream, device to
+        device.  Otherwise the three phase calls are driven from here and torch.distributed carries the two
+        exchanges (gloo in the CPU tests, where the compute runs on the oracle)."""
+        src = np.ascontiguousarray(src, dtype=np.float32).reshape(-1, 3)
+        dst = np.ascontiguousarray(dst, dtype=np.float32).reshape(-1, 3)
+        if src.shape != dst.shape:
+            raise ValueError("src and dst must have the same shape")
+        if self.get("device") >= 0 and self.get("comm_world") > 0:
+            R = np.empty((3, 3), np.float32)
+            t = np.empty(3, np.float32)
+            inl = np.zeros(1, np.int32)
+            self.register_sharded_ptr(src.ctypes.data, dst.ctypes.data, src.shape[0], R.ctypes.data, t.ctypes.data,
+                                      inl.ctypes.data, _abi.LOC_HOST)
+            return R, t, int(inl[0])
         import torch
         import torch.distributed as dist
 

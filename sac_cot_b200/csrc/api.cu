@@ -8,6 +8,9 @@
 #include "../../include/sac_cot.h"
 #include "common.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>  // types and enums only: the functions are resolved with dlopen/dlsym (see NcclApi)
+
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -69,6 +72,11 @@ struct Layout {
   float* outT = nullptr;
   int32_t* outInl = nullptr;
   unsigned long long* best_override = nullptr;
+  // sharded single pair with in-library collectives: this rank's record, the gathered records, the merge summary
+  unsigned long long* xsend = nullptr;
+  unsigned long long* xrecv = nullptr;
+  unsigned long long* xsum = nullptr;
+  size_t xrec_len = 0;  // u64 entries per record = Npad + Ke + 2
   size_t total_bytes = 0;
   unsigned long long key_guess = 0;  // initial key-pool demand estimate
 };
@@ -87,8 +95,39 @@ size_t pair_bytes_estimate(int N, int K, int Ke, bool tensor_path) {
 }
 
 // Optional per-stage timing with CUDA events on the ctx stream ("stage_timing" knob).
-enum Stage { ST_PACK = 0, ST_GRAPH, ST_SCAN, ST_THETA, ST_TRIANGLES, ST_SELECT, ST_APEX, ST_KABSCH, ST_SCORE, ST_FINALIZE, ST_COUNT };
-const char* const kStageNames[ST_COUNT] = {"pack", "graph", "scan", "theta", "triangles", "select", "apex", "kabsch", "score", "finalize"};
+enum Stage { ST_PACK = 0, ST_GRAPH, ST_SCAN, ST_THETA, ST_TRIANGLES, ST_SELECT, ST_APEX, ST_KABSCH, ST_SCORE, ST_FINALIZE, ST_EXCH1, ST_EXCH2, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"pack", "graph", "scan", "theta", "triangles", "select", "apex", "kabsch", "score", "finalize", "exchange1", "exchange2"};
+
+// NCCL, bound at run time: the library carries no link-time dependency on it (a process that already loaded
+// libnccl.so.2 — torch does — gets that copy; otherwise the system one).
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  bool ok = false;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) return;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce;
+  });
+  return api.ok ? &api : nullptr;
+}
+static_assert(sizeof(ncclUniqueId) == SAC_COT_COMM_ID_BYTES, "SAC_COT_COMM_ID_BYTES must equal sizeof(ncclUniqueId)");
 
 struct StageTimer {
   bool enabled = false;
@@ -145,6 +184,15 @@ struct Lane {
   std::vector<PairDesc> descs;
   std::vector<uint2> tile_tab;    // host copy of the tensor-core path's tile list
   std::vector<uint2> tile_scratch;
+  // What the lane's arena holds descriptors and a tile list for.  A chunk with the same shapes, parameters and
+  // partition as the previous one on this lane (every step of a steady workload) re-uses both: no plan(), no upload.
+  std::vector<int32_t> plan_Ns;
+  int plan_sig[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  // pinned staging of the descriptor / tile-list uploads (a pageable source would be staged by the driver and could
+  // serialise the lanes); `uploaded` guards its re-use
+  unsigned char* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  cudaEvent_t uploaded = nullptr;
 };
 constexpr int kMaxLanes = 4;
 
@@ -169,8 +217,9 @@ struct sac_cot_ctx {
   cudaEvent_t fork_event = nullptr;
   std::vector<ChunkDev*> h_chunks;  // pinned read-backs of the chunk headers (host-location calls)
   StickyDev* d_sticky = nullptr;    // device: overflow record that survives across calls
-  StickyDev* h_sticky = nullptr;    // pinned mirror, refreshed asynchronously after device-location calls
-  uint32_t seen_overflows = 0;
+  StickyDev* h_sticky = nullptr;    // pinned [2]: the record before / after the device-location calls whose verdict is open
+  cudaEvent_t sticky_event = nullptr;
+  bool sticky_pending = false;
 
   // what is resident in lane 0's workspace (debug_get / sharded phases)
   sac_cot_params prm{};
@@ -181,6 +230,12 @@ struct sac_cot_ctx {
   // host staging for the pointer-array batch entry point
   std::vector<float> stage_src, stage_dst;
   StageTimer timer;
+
+  // sharded single pair with in-library collectives
+  ncclComm_t comm = nullptr;
+  bool own_comm = false;
+  int comm_rank = 0, comm_world = 0;   // world 0 = no communicator
+  unsigned long long* h_xsum = nullptr;  // pinned: merge summary {any rank overflowed, largest key-pool demand}
 };
 
 namespace {
@@ -199,7 +254,7 @@ int check_params(const sac_cot_params* p) {
 }
 
 // Builds the descriptors and the arena layout for pairs with the given sizes.
-void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_input_copy, bool tensor_path,
+void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_input_copy, bool tensor_path, int xworld,
           std::vector<PairDesc>& descs, std::vector<uint2>& tile_tab, Layout& L) {
   L = Layout();
   L.pairs = pairs;
@@ -280,6 +335,10 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_T = take(sizeof(float) * 3 * pairs);
   const size_t o_inl = take(sizeof(int32_t) * pairs);
   const size_t o_bo = take(sizeof(unsigned long long));
+  L.xrec_len = xworld > 0 ? node + static_cast<size_t>(L.Ke) + 2 : 0;
+  const size_t o_xsend = xworld > 0 ? take(sizeof(unsigned long long) * L.xrec_len) : 0;
+  const size_t o_xrecv = xworld > 0 ? take(sizeof(unsigned long long) * L.xrec_len * xworld) : 0;
+  const size_t o_xsum = xworld > 0 ? take(sizeof(unsigned long long) * 2) : 0;
   L.total_bytes = off;
   // stash offsets as pointers relative to nullptr; bind() adds the arena base
   L.state = reinterpret_cast<PairDev*>(o_state);
@@ -307,6 +366,9 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.outT = reinterpret_cast<float*>(o_T);
   L.outInl = reinterpret_cast<int32_t*>(o_inl);
   L.best_override = reinterpret_cast<unsigned long long*>(o_bo);
+  L.xsend = xworld > 0 ? reinterpret_cast<unsigned long long*>(o_xsend) : nullptr;
+  L.xrecv = xworld > 0 ? reinterpret_cast<unsigned long long*>(o_xrecv) : nullptr;
+  L.xsum = xworld > 0 ? reinterpret_cast<unsigned long long*>(o_xsum) : nullptr;
 }
 
 template <typename T>
@@ -340,6 +402,10 @@ void bind(Layout& L, unsigned char* base, bool has_input, bool tensor_path) {
   L.outT = rebase(L.outT, base);
   L.outInl = rebase(L.outInl, base);
   L.best_override = rebase(L.best_override, base);
+  const bool x = L.xrec_len != 0;
+  L.xsend = rebase(L.xsend, base, x);
+  L.xrecv = rebase(L.xrecv, base, x);
+  L.xsum = rebase(L.xsum, base, x);
 }
 
 int sync_all(sac_cot_ctx* ctx) {
@@ -355,6 +421,7 @@ int ensure_arena(sac_cot_ctx* ctx, Lane& ln, size_t bytes) {
   if (ln.arena) CU_TRY(cudaFree(ln.arena));
   ln.arena = nullptr;
   ln.arena_bytes = 0;
+  ln.plan_sig[0] = -1;  // descriptors and tile list went with the arena
   const size_t want = align_up(bytes + bytes / 8, 1 << 20);
   cudaError_t e = cudaMalloc(&ln.arena, want);
   if (e != cudaSuccess) {
@@ -389,19 +456,36 @@ int ensure_keys(sac_cot_ctx* ctx, Lane& ln, unsigned long long cap) {
   return 0;
 }
 
-// Picks up key-pool overflows of earlier device-location calls from the pinned mirror of the
-// sticky record.  block = false never waits: it sees whatever has been copied back so far (the
-// record only grows, so a stale view is merely late).  On a new overflow every lane's pool is
-// grown to the recorded demand, so the caller's next call succeeds; the overflowed call's outputs
-// are void and "last_status" reports SAC_COT_E_NOMEM for it.
+// Deferred status of device-location calls.  The device-side sticky record (overflowing chunks so far, largest
+// demand) is copied to pinned memory on the ctx stream BEFORE the first call whose verdict is still open and AFTER
+// the latest one, with an event behind the second copy.  The pinned copies are read only once that event has
+// completed; a changed overflow count means some chunk of those calls ran out of key-pool space: their outputs are
+// void, "last_status" reports SAC_COT_E_NOMEM once, and every lane's pool is grown to the recorded demand so the
+// caller's next call succeeds.  block = false never waits (a verdict that is not in yet is merely late).
+int sticky_before(sac_cot_ctx* ctx) {
+  if (ctx->sticky_pending) return 0;  // an open verdict keeps its "before" snapshot and will cover this call too
+  CU_TRY(cudaMemcpyAsync(&ctx->h_sticky[0], ctx->d_sticky, sizeof(StickyDev), cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+int sticky_after(sac_cot_ctx* ctx) {
+  CU_TRY(cudaMemcpyAsync(&ctx->h_sticky[1], ctx->d_sticky, sizeof(StickyDev), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaEventRecord(ctx->sticky_event, ctx->stream));
+  ctx->sticky_pending = true;
+  return 0;
+}
 int resolve_pending(sac_cot_ctx* ctx, bool block) {
   if (block)
     if (int rc = sync_all(ctx)) return rc;
-  const uint32_t count = *reinterpret_cast<volatile uint32_t*>(&ctx->h_sticky->overflow_count);
-  if (count != ctx->seen_overflows) {
-    ctx->seen_overflows = count;
+  if (!ctx->sticky_pending) return 0;
+  if (!block) {
+    const cudaError_t q = cudaEventQuery(ctx->sticky_event);
+    if (q == cudaErrorNotReady) return 0;
+    if (q != cudaSuccess) return static_cast<int>(q);
+  }
+  ctx->sticky_pending = false;
+  if (ctx->h_sticky[1].overflow_count != ctx->h_sticky[0].overflow_count) {
     ctx->deferred_status = SAC_COT_E_NOMEM;
-    const unsigned long long demand = *reinterpret_cast<volatile unsigned long long*>(&ctx->h_sticky->max_total_edges);
+    const unsigned long long demand = ctx->h_sticky[1].max_total_edges;
     ++ctx->retries;
     for (int l = 0; l < ctx->n_lanes; ++l)
       if (int rc = ensure_keys(ctx, ctx->lanes[l], demand + demand / 8 + 1024)) return rc;
@@ -518,6 +602,65 @@ void interleave_tile_runs(std::vector<uint2>& tab, std::vector<uint2>& scratch, 
   tab.swap(scratch);
 }
 
+// Makes the lane ready for a chunk of `pairs` pairs of sizes Ns: layout planned and bound to the arena, descriptors
+// and (tensor-core path) tile list resident on the device.  rank / world: sharded single pair, only the tiles of the
+// cells this rank owns are listed.  xworld > 0 adds the exchange buffers of the in-library collectives.
+// A chunk with the same shapes, parameters and partition as the lane's previous one costs nothing here.
+int prepare_lane(sac_cot_ctx* ctx, Lane& ln, const int32_t* Ns, int pairs, const sac_cot_params& prm, bool host,
+                 bool tensor, int rank, int world, int xworld) {
+  const int sig[8] = {pairs, prm.num_edges, prm.apex_per_edge, (host ? 1 : 0) | (tensor ? 2 : 0) | (ctx->tile_runs ? 4 : 0),
+                      rank, world, xworld, 0};
+  if (ln.arena && !std::memcmp(sig, ln.plan_sig, sizeof(sig)) && ln.plan_Ns.size() == static_cast<size_t>(pairs) &&
+      std::equal(Ns, Ns + pairs, ln.plan_Ns.begin()))
+    return 0;
+  ln.plan_sig[0] = -1;
+  plan(Ns, pairs, prm, host, tensor, xworld, ln.descs, ln.tile_tab, ln.lay);
+  if (tensor) {
+    if (world > 1) {  // keep the tiles of this rank's cells (common.cuh: owner_of_cell; a tile never straddles two cells)
+      std::vector<uint2>& tab = ln.tile_tab;
+      size_t kept = 0;
+      for (size_t k = 0; k < tab.size(); ++k) {
+        const unsigned int jq = tab[k].y & 0xFFFFu, ib = tab[k].y >> 16;
+        if (owner_of_cell(jq * static_cast<unsigned int>(kMmaTileN) / kOwnerCols, ib * static_cast<unsigned int>(kMmaTileM) / kOwnerRows,
+                          static_cast<unsigned int>(world)) == static_cast<unsigned int>(rank))
+          tab[kept++] = tab[k];
+      }
+      tab.resize(kept);
+      ln.lay.total_tiles = static_cast<int>(kept);
+    }
+    if (ctx->tile_runs) interleave_tile_runs(ln.tile_tab, ln.tile_scratch, ln.descs, ctx->sm_count);
+  }
+  if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
+  if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
+  bind(ln.lay, ln.arena, host, tensor);
+  Layout& L = ln.lay;
+  // uploads go through the lane's pinned staging buffer; the previous upload must have left it
+  const size_t desc_bytes = sizeof(PairDesc) * static_cast<size_t>(pairs);
+  const size_t tile_bytes = tensor ? sizeof(uint2) * ln.tile_tab.size() : 0;
+  if (ln.h_stage) CU_TRY(cudaEventSynchronize(ln.uploaded));
+  if (desc_bytes + tile_bytes > ln.h_stage_bytes) {
+    if (ln.h_stage) CU_TRY(cudaFreeHost(ln.h_stage));
+    ln.h_stage = nullptr;
+    ln.h_stage_bytes = 0;
+    const size_t want = align_up(desc_bytes + tile_bytes + (desc_bytes + tile_bytes) / 4, 4096);
+    if (cudaMallocHost(&ln.h_stage, want) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return SAC_COT_E_NOMEM;
+    }
+    ln.h_stage_bytes = want;
+  }
+  std::memcpy(ln.h_stage, ln.descs.data(), desc_bytes);
+  CU_TRY(cudaMemcpyAsync(L.desc, ln.h_stage, desc_bytes, cudaMemcpyHostToDevice, ln.stream));
+  if (tile_bytes) {
+    std::memcpy(ln.h_stage + desc_bytes, ln.tile_tab.data(), tile_bytes);
+    CU_TRY(cudaMemcpyAsync(L.tile_tab, ln.h_stage + desc_bytes, tile_bytes, cudaMemcpyHostToDevice, ln.stream));
+  }
+  CU_TRY(cudaEventRecord(ln.uploaded, ln.stream));
+  std::memcpy(ln.plan_sig, sig, sizeof(sig));
+  ln.plan_Ns.assign(Ns, Ns + pairs);
+  return 0;
+}
+
 // Enqueues one chunk [b0,b1) on a lane.  offsets are absolute (whole call).
 int enqueue_chunk(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst, const int64_t* offsets, int b0,
                   int b1, const sac_cot_params& prm, float* R, float* t, int32_t* inliers, bool host,
@@ -526,15 +669,8 @@ int enqueue_chunk(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst
   std::vector<int32_t> Ns(pairs);
   for (int b = 0; b < pairs; ++b) Ns[b] = static_cast<int32_t>(offsets[b0 + b + 1] - offsets[b0 + b]);
   const bool tensor = ctx->tri_path != 0;
-  plan(Ns.data(), pairs, prm, host, tensor, ln.descs, ln.tile_tab, ln.lay);
-  if (tensor && ctx->tile_runs) interleave_tile_runs(ln.tile_tab, ln.tile_scratch, ln.descs, ctx->sm_count);
-  if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
-  if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
-  bind(ln.lay, ln.arena, host, tensor);
+  if (int rc = prepare_lane(ctx, ln, Ns.data(), pairs, prm, host, tensor, 0, 1, 0)) return rc;
   Layout& L = ln.lay;
-  CU_TRY(cudaMemcpyAsync(L.desc, ln.descs.data(), sizeof(PairDesc) * pairs, cudaMemcpyHostToDevice, ln.stream));
-  if (tensor && !ln.tile_tab.empty())
-    CU_TRY(cudaMemcpyAsync(L.tile_tab, ln.tile_tab.data(), sizeof(uint2) * ln.tile_tab.size(), cudaMemcpyHostToDevice, ln.stream));
   const int64_t p0 = offsets[b0];
   if (host) {
     CU_TRY(cudaMemcpyAsync(L.in_src, src + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ln.stream));
@@ -610,6 +746,8 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
 
   std::vector<int> todo(nchunks);
   for (int c = 0; c < nchunks; ++c) todo[c] = c;
+  if (!host)
+    if (int rc = sticky_before(ctx)) return rc;
   for (int attempt = 0; attempt < 3 && !todo.empty(); ++attempt) {
     if (int rc = fork_lanes(ctx, lanes)) return rc;
     for (size_t k = 0; k < todo.size(); ++k) {
@@ -623,7 +761,7 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
     if (int rc = join_lanes(ctx, lanes)) return rc;
     if (!host) {
       // enqueue only; an overflow (if any) surfaces through resolve_pending()
-      CU_TRY(cudaMemcpyAsync(ctx->h_sticky, ctx->d_sticky, sizeof(StickyDev), cudaMemcpyDeviceToHost, ctx->stream));
+      if (int rc = sticky_after(ctx)) return rc;
       ctx->ws_valid = nchunks == 1;
       return SAC_COT_OK;
     }
@@ -696,16 +834,19 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
     if (e != cudaSuccess) { delete ctx; return static_cast<int>(e); }
     ctx->own_stream = true;
   }
-  cudaError_t e = cudaMallocHost(&ctx->h_sticky, sizeof(StickyDev));
+  cudaError_t e = cudaMallocHost(&ctx->h_sticky, 2 * sizeof(StickyDev));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->sticky_event, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_sticky, sizeof(StickyDev));
   if (e == cudaSuccess) e = cudaMemset(ctx->d_sticky, 0, sizeof(StickyDev));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming);
   for (int l = 0; l < kMaxLanes && e == cudaSuccess; ++l) {
     e = cudaStreamCreateWithFlags(&ctx->lanes[l].stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].uploaded, cudaEventDisableTiming);
   }
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_xsum, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) { sac_cot_ctx_destroy(ctx); return static_cast<int>(e); }
-  std::memset(ctx->h_sticky, 0, sizeof(StickyDev));
+  std::memset(ctx->h_sticky, 0, 2 * sizeof(StickyDev));
   int rc = triangles_configure();
   if (rc >= 0) rc = triangles_mma_configure();
   if (rc >= 0) rc = select_configure();
@@ -722,12 +863,18 @@ int sac_cot_ctx_destroy(sac_cot_ctx* ctx) {
     Lane& ln = ctx->lanes[l];
     if (ln.arena) cudaFree(ln.arena);
     if (ln.keys) cudaFree(ln.keys);
+    if (ln.h_stage) cudaFreeHost(ln.h_stage);
     if (ln.done) cudaEventDestroy(ln.done);
+    if (ln.uploaded) cudaEventDestroy(ln.uploaded);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
+  if (ctx->comm && ctx->own_comm)
+    if (NcclApi* nc = nccl_api()) nc->CommDestroy(ctx->comm);
+  if (ctx->h_xsum) cudaFreeHost(ctx->h_xsum);
   for (ChunkDev* h : ctx->h_chunks) cudaFreeHost(h);
   if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   if (ctx->h_sticky) cudaFreeHost(ctx->h_sticky);
+  if (ctx->sticky_event) cudaEventDestroy(ctx->sticky_event);
   if (ctx->d_sticky) cudaFree(ctx->d_sticky);
   ctx->timer.destroy();
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -807,6 +954,8 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
     return SAC_COT_OK;
   }
   if (!std::strcmp(name, "threads")) { *value = 0; return SAC_COT_OK; }
+  if (!std::strcmp(name, "comm_rank")) { *value = ctx->comm_rank; return SAC_COT_OK; }
+  if (!std::strcmp(name, "comm_world")) { *value = ctx->comm_world; return SAC_COT_OK; }
   if (!std::strncmp(name, "stage_us_", 9) || !std::strncmp(name, "stage_calls_", 12)) {
     const bool us = name[6] == 'u';
     const char* stage = name + (us ? 9 : 12);
@@ -818,6 +967,37 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
         return SAC_COT_OK;
       }
     return SAC_COT_E_WHICH;
+  }
+  if (!std::strcmp(name, "probe_mxf4_gflops")) {
+    // dense rate of the triangle kernel's MMA (mxf4, cta_group::2, M 256 x N 240 x K 64) with nothing else
+    // running: three timed launches on every CTA pair of the device, best of three; synchronises
+    CU_TRY(cudaSetDevice(ctx->device));
+    if (int rc = sync_all(ctx)) return rc;
+    cudaEvent_t a = nullptr, b = nullptr;
+    CU_TRY(cudaEventCreate(&a));
+    cudaError_t ce = cudaEventCreate(&b);
+    if (ce != cudaSuccess) { cudaEventDestroy(a); return static_cast<int>(ce); }
+    LaunchCtx lc{ctx->stream, ctx->sm_count};
+    const int clusters = ctx->sm_count / 2, stage_pairs = 2048;
+    double best_ms = 0.0;
+    int rc = 0;
+    for (int rep = 0; rep < 4 && rc == 0; ++rep) {  // rep 0 warms up
+      cudaEventRecord(a, ctx->stream);
+      const int n = launch_mma_peak_probe(lc, clusters, stage_pairs);
+      if (n < 0) { rc = -n; break; }
+      ctx->launches += n;
+      cudaEventRecord(b, ctx->stream);
+      ce = cudaEventSynchronize(b);
+      if (ce != cudaSuccess) { rc = static_cast<int>(ce); break; }
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, a, b);
+      if (rep > 0 && (best_ms == 0.0 || ms < best_ms)) best_ms = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (rc) return rc;
+    *value = static_cast<int64_t>(mma_peak_probe_flops(clusters, stage_pairs) / (best_ms * 1e-3) / 1e9);
+    return SAC_COT_OK;
   }
   if (!std::strcmp(name, "last_status")) {
     // status of the most recent device-location call; synchronises with it
@@ -880,6 +1060,179 @@ int sac_cot_register(const float* src, const float* dst, int32_t N, const sac_co
 }
 
 // ---- sharded single pair ------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// Part 1 on lane 0: inputs -> full graph -> triangle counts of this rank's cells -> its top-K_e edge keys.
+// host_inputs: src/dst are host arrays (copied into the arena), else device arrays on the ctx device.
+int shard_part1(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst, int32_t N, const sac_cot_params& prm,
+                int rank, int world, int xworld, bool host_inputs) {
+  // S2 path as in the unsharded call (tensor cores for dense graphs, decided by the density of the WHOLE graph, the
+  // same on every rank); a rank counts the edges of the cells it owns (common.cuh: owner_of_cell)
+  const bool tensor = ctx->tri_path != 0;
+  if (int rc = prepare_lane(ctx, ln, &N, 1, prm, host_inputs, tensor, rank, world, xworld)) return rc;
+  ctx->prm = prm;
+  Layout& L = ln.lay;
+  if (int rc = fork_lanes(ctx, 1)) return rc;
+  if (host_inputs) {
+    CU_TRY(cudaMemcpyAsync(L.in_src, src, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ln.stream));
+    CU_TRY(cudaMemcpyAsync(L.in_dst, dst, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ln.stream));
+    src = L.in_src;
+    dst = L.in_dst;
+  }
+  return enqueue_pipeline(ctx, ln, src, dst, nullptr, nullptr, nullptr, rank, world, true);
+}
+
+int run_sharded(sac_cot_ctx* ctx, const float* src, const float* dst, int32_t N, const sac_cot_params* params,
+                float* R, float* t, int32_t* inliers, int32_t location) {
+  if (!ctx || !src || !dst || !R || !t || !inliers) return SAC_COT_E_NULL;
+  if (location != SAC_COT_LOC_HOST && location != SAC_COT_LOC_DEVICE) return SAC_COT_E_UNSUPPORTED;
+  if (N < 3 || N > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
+  if (int rc = check_params(params)) return rc;
+  NcclApi* nc = nccl_api();
+  if (!ctx->comm || ctx->comm_world < 1 || !nc) return SAC_COT_E_COMM;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (int rc = resolve_pending(ctx, false)) return rc;
+  const bool host = location == SAC_COT_LOC_HOST;
+  const int rank = ctx->comm_rank, world = ctx->comm_world;
+  ctx->sh_valid = false;
+  ctx->ws_valid = false;
+  Lane& ln = ctx->lanes[0];
+  StageTimer& tm = ctx->timer;
+  if (!host)
+    if (int rc = sticky_before(ctx)) return rc;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if (int rc = shard_part1(ctx, ln, src, dst, N, *params, rank, world, world, host)) return rc;
+    Layout& L = ln.lay;
+    LaunchCtx lc{ln.stream, ctx->sm_count};
+    const int npad = ln.descs[0].Npad, Ke = L.Ke;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto span_begin = [&]() {
+      if (tm.enabled && (e0 = tm.next())) cudaEventRecord(e0, ln.stream);
+    };
+    auto span_end = [&](int stage) {
+      if (tm.enabled && e0 && (e1 = tm.next())) {
+        cudaEventRecord(e1, ln.stream);
+        tm.pending.push_back({stage, e0, e1});
+      }
+      e0 = nullptr;
+    };
+    // ---- exchange #1: every rank's record (partial node sums | its top-K_e | overflow flag, demand), device to
+    //      device on the lane stream, then the merge: summed node sums, global top-K_e
+    span_begin();
+    KL_TRY(launch_shard_pack(lc, L.t2, L.top, L.chunk, L.xsend, npad, Ke));
+    if (nc->AllGather(L.xsend, L.xrecv, L.xrec_len, ncclUint64, ctx->comm, ln.stream) != ncclSuccess) return SAC_COT_E_COMM;
+    CU_TRY(cudaMemsetAsync(L.top, 0, sizeof(unsigned long long) * Ke, ln.stream));
+    CU_TRY(cudaMemsetAsync(&L.state[0].best_key, 0, sizeof(unsigned long long), ln.stream));
+    CU_TRY(cudaMemsetAsync(L.hyp_key, 0, sizeof(unsigned long long) * L.K, ln.stream));
+    KL_TRY(launch_shard_merge(lc, L.xrecv, world, npad, Ke, L.t2, L.top, L.state, L.chunk, host ? nullptr : ctx->d_sticky,
+                              L.xsum));
+    span_end(ST_EXCH1);
+    // ---- part 2: apexes and hypotheses everywhere (cheap, identical), scores of this rank's hypothesis range
+    const float tau2 = params->tau_inlier * params->tau_inlier;
+    span_begin();
+    KL_TRY(launch_select_apex(lc, L.desc, 1, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path));
+    span_end(ST_APEX);
+    span_begin();
+    KL_TRY(launch_kabsch(lc, L.desc, 1, L.soa, L.tri, L.rt, L.K));
+    span_end(ST_KABSCH);
+    const int per = (L.K + world - 1) / world;
+    const int h0 = std::min(L.K, rank * per), h1 = std::min(L.K, h0 + per);
+    span_begin();
+    KL_TRY(launch_score(lc, L.desc, 1, L.max_n, L.soa, L.tri, L.rt, L.hyp_key, L.state, tau2, L.K, h0, h1, params->score_mode));
+    span_end(ST_SCORE);
+    // ---- exchange #2: all-reduce(max) of the packed (score, hypothesis id) key
+    span_begin();
+    if (nc->AllReduce(&L.state[0].best_key, L.best_override, 1, ncclUint64, ncclMax, ctx->comm, ln.stream) != ncclSuccess)
+      return SAC_COT_E_COMM;
+    CU_TRY(cudaMemcpyAsync(&L.state[0].best_key, L.best_override, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ln.stream));
+    span_end(ST_EXCH2);
+    // ---- part 3: inlier mask + refit of the global winner, on every rank
+    span_begin();
+    KL_TRY(launch_finalize(lc, L.desc, 1, L.soa, L.rt, L.state, L.best_override, L.mask, host ? L.outR : R, host ? L.outT : t,
+                           host ? L.outInl : inliers, tau2, L.K, params->refit));
+    span_end(ST_FINALIZE);
+    if (!host) {
+      if (int rc = join_lanes(ctx, 1)) return rc;
+      if (int rc = sticky_after(ctx)) return rc;
+      ctx->ws_valid = true;
+      return SAC_COT_OK;
+    }
+    CU_TRY(cudaMemcpyAsync(R, L.outR, sizeof(float) * 9, cudaMemcpyDeviceToHost, ln.stream));
+    CU_TRY(cudaMemcpyAsync(t, L.outT, sizeof(float) * 3, cudaMemcpyDeviceToHost, ln.stream));
+    CU_TRY(cudaMemcpyAsync(inliers, L.outInl, sizeof(int32_t), cudaMemcpyDeviceToHost, ln.stream));
+    CU_TRY(cudaMemcpyAsync(ctx->h_xsum, L.xsum, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ln.stream));
+    if (int rc = join_lanes(ctx, 1)) return rc;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->h_xsum[0]) {
+      ctx->ws_valid = true;  // the pair is resident: debug_get(pair 0) works
+      return SAC_COT_OK;
+    }
+    // some rank ran out of key-pool space; every rank saw the same summary: grow and re-run in step
+    ++ctx->retries;
+    const unsigned long long demand = ctx->h_xsum[1];
+    if (int rc = ensure_keys(ctx, ln, demand + demand / 16 + 1024)) return rc;
+  }
+  return SAC_COT_E_NOMEM;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sac_cot_comm_unique_id(void* id_out) {
+  if (!id_out) return SAC_COT_E_NULL;
+  NcclApi* nc = nccl_api();
+  if (!nc) return SAC_COT_E_COMM;
+  ncclUniqueId id;
+  if (nc->GetUniqueId(&id) != ncclSuccess) return SAC_COT_E_COMM;
+  std::memcpy(id_out, &id, sizeof(id));
+  return SAC_COT_OK;
+}
+
+int sac_cot_ctx_set_comm(sac_cot_ctx* ctx, void* nccl_comm, int32_t rank, int32_t world) {
+  if (!ctx) return SAC_COT_E_NULL;
+  if (nccl_comm && (world < 1 || world > 64 || rank < 0 || rank >= world)) return SAC_COT_E_SIZE;
+  NcclApi* nc = nccl_api();
+  if (nccl_comm && !nc) return SAC_COT_E_COMM;
+  cudaSetDevice(ctx->device);
+  (void)sync_all(ctx);
+  if (ctx->comm && ctx->own_comm && nc) nc->CommDestroy(ctx->comm);
+  ctx->comm = static_cast<ncclComm_t>(nccl_comm);
+  ctx->own_comm = false;
+  ctx->comm_rank = nccl_comm ? rank : 0;
+  ctx->comm_world = nccl_comm ? world : 0;
+  return SAC_COT_OK;
+}
+
+int sac_cot_ctx_comm_init(sac_cot_ctx* ctx, const void* id, int32_t rank, int32_t world) {
+  if (!ctx || !id) return SAC_COT_E_NULL;
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return SAC_COT_E_SIZE;
+  NcclApi* nc = nccl_api();
+  if (!nc) return SAC_COT_E_COMM;
+  if (int rc = sac_cot_ctx_set_comm(ctx, nullptr, 0, 0)) return rc;
+  CU_TRY(cudaSetDevice(ctx->device));
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  ncclComm_t comm = nullptr;
+  if (nc->CommInitRank(&comm, world, uid, rank) != ncclSuccess) return SAC_COT_E_COMM;
+  ctx->comm = comm;
+  ctx->own_comm = true;
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  return SAC_COT_OK;
+}
+
+int sac_cot_register_sharded(sac_cot_ctx* ctx, const float* src, const float* dst, int32_t N,
+                             const sac_cot_params* params, float R[9], float t[3], int32_t* inliers, int32_t location) {
+  try {
+    return run_sharded(ctx, src, dst, N, params, R, t, inliers, location);
+  } catch (const std::bad_alloc&) {
+    return SAC_COT_E_NOMEM;
+  }
+}
+
 int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst, int32_t N,
                            const sac_cot_params* params, int32_t rank, int32_t world, uint64_t* t_partial,
                            uint64_t* cand) {
@@ -896,38 +1249,8 @@ int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
     if (int rc = ensure_chunk_headers(ctx, 1)) return rc;
     ChunkDev* h_chunk = ctx->h_chunks[0];
     for (int attempt = 0; attempt < 3; ++attempt) {
-      // S2 path as in the unsharded call (tensor cores for dense graphs); a rank owns the edges whose larger endpoint
-      // lies in its blocks of 1920 columns (common.cuh: owner_of_jb), i.e. whole 240-column tiles
-      const bool tensor = ctx->tri_path != 0;
-      plan(&N, 1, *params, true, tensor, ln.descs, ln.tile_tab, ln.lay);
-      if (tensor) {
-        if (world > 1) {
-          std::vector<uint2>& tab = ln.tile_tab;
-          size_t kept = 0;
-          for (size_t k = 0; k < tab.size(); ++k) {
-            const unsigned int jq = tab[k].y & 0xFFFFu;  // column block of the tile
-            if ((jq * static_cast<unsigned int>(kMmaTileN) / kOwnerCols) % static_cast<unsigned int>(world) == static_cast<unsigned int>(rank))
-              tab[kept++] = tab[k];
-          }
-          tab.resize(kept);
-          ln.lay.total_tiles = static_cast<int>(kept);
-        }
-        if (ctx->tile_runs) interleave_tile_runs(ln.tile_tab, ln.tile_scratch, ln.descs, ctx->sm_count);
-      }
-      if (int rc = ensure_arena(ctx, ln, ln.lay.total_bytes)) return rc;
-      // a rank evaluates ~1/world of the edges: the unit scan counts only the owned units, so the
-      // pool demand is ~E/world; the initial guess covers a whole pair at 12.5 % density
-      if (int rc = ensure_keys(ctx, ln, ln.lay.key_guess)) return rc;
-      bind(ln.lay, ln.arena, true, tensor);
-      ctx->prm = *params;
+      if (int rc = shard_part1(ctx, ln, src, dst, N, *params, rank, world, 0, true)) return rc;
       Layout& L = ln.lay;
-      if (int rc = fork_lanes(ctx, 1)) return rc;
-      CU_TRY(cudaMemcpyAsync(L.desc, ln.descs.data(), sizeof(PairDesc), cudaMemcpyHostToDevice, ln.stream));
-      if (tensor && !ln.tile_tab.empty())
-        CU_TRY(cudaMemcpyAsync(L.tile_tab, ln.tile_tab.data(), sizeof(uint2) * ln.tile_tab.size(), cudaMemcpyHostToDevice, ln.stream));
-      CU_TRY(cudaMemcpyAsync(L.in_src, src, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ln.stream));
-      CU_TRY(cudaMemcpyAsync(L.in_dst, dst, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ln.stream));
-      if (int rc = enqueue_pipeline(ctx, ln, L.in_src, L.in_dst, nullptr, nullptr, nullptr, rank, world, true)) return rc;
       CU_TRY(cudaMemcpyAsync(h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ln.stream));
       CU_TRY(cudaMemcpyAsync(t_partial, L.t2, sizeof(uint64_t) * N, cudaMemcpyDeviceToHost, ln.stream));
       CU_TRY(cudaMemcpyAsync(cand, L.top, sizeof(uint64_t) * params->num_edges, cudaMemcpyDeviceToHost, ln.stream));
@@ -1073,10 +1396,11 @@ const char* sac_cot_strerror(int status) {
     case SAC_COT_E_WHICH: return "unknown selector / index, or nothing resident";
     case SAC_COT_E_CAPACITY: return "output buffer too small";
     case SAC_COT_E_NOMEM: return "out of device memory / workspace overflow";
+    case SAC_COT_E_COMM: return "no communicator on the ctx, NCCL not loadable, or an NCCL call failed";
     default: return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown status";
   }
 }
 
-const char* sac_cot_version(void) { return "sac-cot-b200 0.1 (cuda sm_100a)"; }
+const char* sac_cot_version(void) { return "sac-cot-b200 0.2 (cuda sm_100a)"; }
 
 }  // extern "C"

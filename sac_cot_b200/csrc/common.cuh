@@ -120,18 +120,23 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 // ------------------------------------------------------------------------------------------
 // Triangle work units: unit (jb, ic) = columns [128 jb, 128 jb + 128) x rows [256 ic, 256 ic + 256)
 // with ic <= jb/2 (only i < j matters).  unit id = unit_offset(jb) + ic; the oracle uses the same
-// numbering to assign edges to ranks in sharded mode (unit id % world).
+// numbering; in sharded mode a unit belongs to the rank owner_of_unit() names.
 __host__ __device__ inline unsigned int unit_offset(unsigned int jb) {
   const unsigned int h = jb >> 1;  // sum_{b<jb} (b/2+1) = h(h+1) for jb=2h, (h+1)^2 for jb=2h+1
   return (jb & 1u) ? (h + 1) * (h + 1) : h * (h + 1);
 }
 __host__ __device__ inline unsigned int unit_count(unsigned int nblk) { return unit_offset(nblk); }
-// Sharded single-pair runs: the owner of an edge (i < j) is decided by the block of 1920 columns j lies in
-// (1920 = lcm(128, 240): whole 128-column units of the bitset kernels and whole 240-column tiles of the
-// tensor-core kernel), dealt round-robin to the ranks.  The oracle uses the same rule.
+// Sharded single-pair runs (normative, DESIGN.md §2 "S2 partition"): the owner of an edge (i < j) is decided by the
+// cell it lies in — cell (cb, ic) = columns [1920 cb, 1920 cb + 1920) x rows [256 ic, 256 ic + 256) — and cells are
+// dealt to the ranks as (257 cb + ic) mod world.  1920 = lcm(128, 240) columns are whole 128-column units of the
+// bitset kernels and whole 240-column tiles of the tensor-core kernel; 256 rows are one row block of either.  A
+// column block holds ~7.5 (cb + 1/2) cells, so every rank gets the same share of every column block to within one
+// cell (the triangular work profile over j does not unbalance the ranks), and 257 = 1 (mod 2, 4, 8) shifts the deal
+// from one column block to the next.  The oracle restates the same rule.
 constexpr unsigned int kOwnerCols = 1920;
-__host__ __device__ inline unsigned int owner_of_jb(unsigned int jb, unsigned int world) {
-  return (jb / (kOwnerCols / 128u)) % world;
+constexpr unsigned int kOwnerRows = 256;
+__host__ __device__ inline unsigned int owner_of_cell(unsigned int cb, unsigned int ic, unsigned int world) {
+  return (257u * cb + ic) % world;
 }
 // column block jb of unit id u (inverse of unit_offset)
 __host__ __device__ inline unsigned int unit_jb(unsigned int u) {
@@ -140,7 +145,10 @@ __host__ __device__ inline unsigned int unit_jb(unsigned int u) {
   while (unit_offset(jb + 1) <= u) ++jb;
   return jb;
 }
-__host__ __device__ inline unsigned int owner_of_unit(unsigned int u, unsigned int world) { return owner_of_jb(unit_jb(u), world); }
+__host__ __device__ inline unsigned int owner_of_unit(unsigned int u, unsigned int world) {
+  const unsigned int jb = unit_jb(u);
+  return owner_of_cell(jb / (kOwnerCols / 128u), u - unit_offset(jb), world);
+}
 
 struct LaunchCtx {
   cudaStream_t stream;
@@ -193,6 +201,9 @@ int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint
                          unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
                          int Ke, int raise, int dbg);
 int triangles_mma_configure();
+// tensor-pipe peak probe (the triangle kernel's MMA shape, issued back to back): bench.py's roofline denominator
+int launch_mma_peak_probe(const LaunchCtx& lc, int clusters, int stage_pairs);
+double mma_peak_probe_flops(int clusters, int stage_pairs);
 
 // kernels_select.cu — S3 edge ranking + apex selection
 int launch_select_edges(const LaunchCtx& lc, int pairs, PairDev* d_state, const ChunkDev* d_chunk,
@@ -202,6 +213,13 @@ int select_configure();  // opt-in dynamic shared memory; call once per device
 int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                        const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m,
                        int apex_path);
+
+// sharded single pair: record of a rank for exchange #1 and the merge of the gathered records (kernels_select.cu)
+int launch_shard_pack(const LaunchCtx& lc, const unsigned long long* d_t2, const unsigned long long* d_top,
+                      const ChunkDev* d_chunk, unsigned long long* d_rec, int npad, int Ke);
+int launch_shard_merge(const LaunchCtx& lc, const unsigned long long* d_recs, int world, int npad, int Ke,
+                       unsigned long long* d_t2, unsigned long long* d_top, PairDev* d_state, ChunkDev* d_chunk,
+                       StickyDev* d_sticky, unsigned long long* d_summary);
 
 // kernels_hypo.cu — S4 Kabsch, S5/S6 scoring + argmax, S7 refit
 int launch_kabsch(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const float* d_soa, const int32_t* d_tri,

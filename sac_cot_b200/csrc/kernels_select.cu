@@ -113,7 +113,13 @@ __global__ void __launch_bounds__(1024) select_final_kernel(
     unsigned long long* __restrict__ top, int Ke) {
   const int pair = blockIdx.x;
   unsigned long long* topp = top + static_cast<size_t>(pair) * Ke;
-  if (chunk->overflow) return;
+  if (chunk->overflow) {
+    // key pool too small: the triangle kernels did nothing and `top` still holds whatever the arena held.  Every
+    // slot becomes "unused" (key 0), so the apex / Kabsch / scoring / refit kernels that follow touch nothing outside
+    // the pair's buffers and the chunk's outputs read R = I, t = 0, inliers = 0 until the re-run replaces them.
+    for (int k = threadIdx.x; k < Ke; k += 1024) topp[k] = 0ull;
+    return;
+  }
   PairDev* st = state + pair;
   __shared__ unsigned long long sbuf[kMaxEdges];
   __shared__ unsigned int h256[256];
@@ -531,6 +537,107 @@ int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, i
     else if (m <= 4) select_apex_kernel<4><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
     else select_apex_kernel<8><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
   }
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+// ------------------------------------------------------------------------------------------
+// Sharded single pair: the two device-side ends of exchange #1.
+//   record of one rank (u64 units): [0, Npad) partial node sums | [Npad, Npad + Ke) its top-K_e edge keys, descending,
+//   0-padded | overflow flag | key-pool demand.  shard_pack builds the record next to the pipeline's buffers (one
+//   contiguous send buffer for ncclAllGather); shard_merge turns the `world` gathered records into the pair's node
+//   sums and the global top-K_e list:
+//     - node sums add up (integers: order-free);
+//     - the global top-K_e restricted to a rank lies inside that rank's top-K_e, so the top-K_e of the union is
+//       exact.  Keys are unique (an edge is owned by exactly one rank) and every list is sorted, so the position of a
+//       key in the merged order is the number of keys above it, found by one binary search per list: no sort, no
+//       atomics, no dependence on the gather order.
+//   If any rank ran out of key-pool space the merged list stays empty (every slot unused), the chunk is flagged on
+//   EVERY rank alike and the sticky record takes the largest demand: all ranks then grow and re-run in step.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shard_pack_kernel(const unsigned long long* __restrict__ t2,
+                                                         const unsigned long long* __restrict__ top,
+                                                         const ChunkDev* __restrict__ chunk,
+                                                         unsigned long long* __restrict__ rec, int npad, int Ke) {
+  const int n = npad + Ke;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    rec[k] = k < npad ? t2[k] : top[k - npad];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    rec[n] = chunk->overflow;
+    rec[n + 1] = chunk->total_edges;
+  }
+}
+
+__global__ void __launch_bounds__(256) shard_merge_kernel(const unsigned long long* __restrict__ recs, int world,
+                                                          int npad, int Ke, unsigned long long* __restrict__ t2,
+                                                          unsigned long long* __restrict__ top /* zeroed */,
+                                                          PairDev* __restrict__ state, ChunkDev* __restrict__ chunk,
+                                                          StickyDev* __restrict__ sticky,
+                                                          unsigned long long* __restrict__ summary /* [2] */) {
+  const size_t rec_len = static_cast<size_t>(npad) + Ke + 2;
+  unsigned long long any = 0, demand = 0;
+  for (int g = 0; g < world; ++g) {
+    const unsigned long long* r = recs + g * rec_len + npad + Ke;
+    any |= r[0];
+    demand = r[1] > demand ? r[1] : demand;
+  }
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstep = gridDim.x * blockDim.x;
+  for (int i = gtid; i < npad; i += gstep) {
+    unsigned long long s = 0;
+    for (int g = 0; g < world; ++g) s += recs[g * rec_len + i];
+    t2[i] = s;
+  }
+  // number of keys of a (descending, 0-padded) list that are larger than `key`
+  auto count_above = [&](const unsigned long long* list, unsigned long long key) {
+    int lo = 0, hi = Ke;  // list[lo - 1] > key >= list[hi]
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (list[mid] > key) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo;
+  };
+  if (!any) {
+    for (int c = gtid; c < world * Ke; c += gstep) {
+      const unsigned long long key = recs[(c / Ke) * rec_len + npad + (c % Ke)];
+      if (key == 0ull) continue;
+      int pos = 0;
+      for (int g = 0; g < world && pos < Ke; ++g) pos += count_above(recs + g * rec_len + npad, key);
+      if (pos < Ke) top[pos] = key;
+    }
+  }
+  if (gtid == 0) {
+    int total = 0;
+    for (int g = 0; g < world; ++g) total += count_above(recs + g * rec_len + npad, 0ull);
+    state[0].n_sel = any ? 0u : static_cast<uint32_t>(total < Ke ? total : Ke);
+    summary[0] = any;
+    summary[1] = demand;
+    if (any) {
+      chunk->overflow = 1u;
+      chunk->total_edges = demand;
+      if (sticky) {
+        atomicMax(&sticky->max_total_edges, demand);
+        atomicAdd(&sticky->overflow_count, 1u);
+      }
+    }
+  }
+}
+
+int launch_shard_pack(const LaunchCtx& lc, const unsigned long long* d_t2, const unsigned long long* d_top,
+                      const ChunkDev* d_chunk, unsigned long long* d_rec, int npad, int Ke) {
+  const int blocks = std::min(lc.sm_count, (npad + Ke + 255) / 256);
+  shard_pack_kernel<<<blocks, 256, 0, lc.stream>>>(d_t2, d_top, d_chunk, d_rec, npad, Ke);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+int launch_shard_merge(const LaunchCtx& lc, const unsigned long long* d_recs, int world, int npad, int Ke,
+                       unsigned long long* d_t2, unsigned long long* d_top, PairDev* d_state, ChunkDev* d_chunk,
+                       StickyDev* d_sticky, unsigned long long* d_summary) {
+  const int work = std::max(npad, world * Ke);
+  const int blocks = std::min(lc.sm_count, (work + 255) / 256);
+  shard_merge_kernel<<<blocks, 256, 0, lc.stream>>>(d_recs, world, npad, Ke, d_t2, d_top, d_state, d_chunk, d_sticky,
+                                                    d_summary);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }

@@ -112,7 +112,7 @@ struct LaneWords {
 };
 
 // Edge bits of row i inside a block of NB x 128 columns starting at column J0, restricted to
-// j > i and (sharded mode) to the 128-column sub-blocks whose unit this rank owns.
+// j > i (sharded mode: the callers skip the units this rank does not own).
 template <int NB>
 struct EdgeBits {
   uint32_t w[4 * NB];
@@ -126,20 +126,12 @@ struct EdgeBits {
       w[4 * s + 0] = v.x; w[4 * s + 1] = v.y; w[4 * s + 2] = v.z; w[4 * s + 3] = v.w;
     }
   }
-  __device__ __forceinline__ void restrict_to(int i, int J0, unsigned int jb0, int rank, int world) {
+  __device__ __forceinline__ void restrict_to(int i, int J0) {
     const int li = i - J0;  // clear bits <= li
 #pragma unroll
     for (int k = 0; k < 4 * NB; ++k) {
       if (li >= 32 * k + 31) w[k] = 0u;
       else if (li >= 32 * k) w[k] &= 0xffffffffu << ((li & 31) + 1);
-    }
-    if (world > 1) {
-#pragma unroll
-      for (int s = 0; s < NB; ++s) {
-        if (owner_of_jb(jb0 + s, static_cast<unsigned int>(world)) != static_cast<unsigned int>(rank)) {
-          w[4 * s + 0] = 0u; w[4 * s + 1] = 0u; w[4 * s + 2] = 0u; w[4 * s + 3] = 0u;
-        }
-      }
     }
   }
   __device__ __forceinline__ int count(int s) const {
@@ -421,7 +413,7 @@ __global__ void __launch_bounds__(kTriThreads) triangles_chunked_kernel(
       const int i = I0 + rr;
       EdgeBits<1> eb;
       eb.load(adjp + static_cast<size_t>(i) * stride + jb * 4, 1);
-      eb.restrict_to(i, J0, jb, 0, 1);
+      eb.restrict_to(i, J0);
       const int n = eb.count(0);
       if (n == 0) continue;
       LaneWords<R> ri;
@@ -468,7 +460,7 @@ __global__ void __launch_bounds__(kTriThreads) triangles_chunked_kernel(
     const int i = I0 + rr;
     EdgeBits<1> eb;
     eb.load(adjp + static_cast<size_t>(i) * stride + jb * 4, 1);
-    eb.restrict_to(i, J0, jb, 0, 1);
+    eb.restrict_to(i, J0);
     const int n = eb.count(0);
     if (n == 0) continue;
     uint32_t base = 0;

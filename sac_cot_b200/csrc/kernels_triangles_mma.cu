@@ -990,10 +990,91 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
   if (t == 0) theta[pair] = th | (nts >= 4 * Ke ? 0x80000000u : 0u);
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-pipe peak probe: the triangle kernel's MMA (cta_group::2, kind::mxf4.block_scale, M = 256, N = 240,
+// K = 64, the same canonical K-major shared-memory operand layout) issued back to back by one elected thread per
+// CTA pair, nothing else running.  bench.py divides the triangle kernel's rate by THIS number, measured in the
+// same process on the same GPU (MEASURED_PEAKS.json carries no 4-bit figure).  Operands are zeros: the MMA rate
+// does not depend on the data.
+// ------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_peak_kernel(int stage_pairs) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // two operand stages
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  for (int k = tid; k < 2 * kStageBytes / 16; k += 128) reinterpret_cast<uint4*>(smem_raw)[k] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    mbar_init(&done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_slot;
+  {
+    const uint32_t taddr = tmem + ((32u * warp) << 16) + kSfCol;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
+            taddr),
+        "r"(kSfWord)
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp == 0 && rank == 0) {
+    const uint32_t idesc = (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kMmaTileN >> 3) << 17) | (1u << 23) | ((256u >> 4) << 24);
+    const uint64_t desc0 = umma_desc(smem_u32(smem_raw));
+    const uint32_t desc_lo = static_cast<uint32_t>(desc0), desc_hi = static_cast<uint32_t>(desc0 >> 32);
+    uint32_t leader;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(leader));
+    for (int ip = 0; ip < stage_pairs; ++ip) {
+#pragma unroll
+      for (int ks = 0; ks < 2 * kStageK / 64; ++ks) {
+        const uint32_t loA = desc_lo + static_cast<uint32_t>(((ks >> 2) * kStageBytes + (ks & 3) * 2 * kLBO) >> 4);
+        const uint32_t loB = loA + static_cast<uint32_t>(((kCtaM / 8) * kSBO) >> 4);
+        asm volatile(
+            "{\n.reg .b64 da, db;\n.reg .pred p, q;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
+            "setp.ne.b32 q, %5, 0;\nsetp.eq.u32 p, 1, 1;\n"
+            "@q tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], da, db, %4, [%6], [%7], p;\n}" ::"r"(
+                tmem + static_cast<uint32_t>(kMmaTileN * (ip & 1))),
+            "r"(loA), "r"(loB), "r"(desc_hi), "r"(idesc), "r"(leader), "r"(tmem + kSfCol), "r"(tmem + kSfCol + 16u)
+            : "memory");
+      }
+      __syncwarp();
+    }
+    umma_commit_pair_if(&done_bar, leader);
+  }
+  if (warp == 0) mbar_wait_wd(&done_bar, 0u, 9, 0u);
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// flops of one launch: clusters x stage_pairs x 8 MMAs x (256 x 240 x 64 MAC) x 2
+double mma_peak_probe_flops(int clusters, int stage_pairs) {
+  return static_cast<double>(clusters) * stage_pairs * 8.0 * 256.0 * kMmaTileN * 64.0 * 2.0;
+}
+int launch_mma_peak_probe(const LaunchCtx& lc, int clusters, int stage_pairs) {
+  mma_peak_kernel<<<2 * clusters, 128, 2 * kStageBytes, lc.stream>>>(stage_pairs);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
 int triangles_mma_configure() {
   cudaError_t e = cudaFuncSetAttribute(triangles_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(triangles_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kStageBytes);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tri_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(theta_smem_bytes(65536)));

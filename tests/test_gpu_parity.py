@@ -600,3 +600,149 @@ def test_tensor_core_tile_schedule_is_invisible(gpu_lib, oracle_lib, tile_runs):
         assert (rg.inliers == ro.inliers).all()
         for b in range(len(ps)):
             compare_pruned(g, o, pair_idx=b)
+
+
+# ---------------------------------------------------------------------------------------------
+# Sharded single pair with the collectives inside the library (sac_cot_register_sharded)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path,N", [(0, 3000), (2, 6000)])
+def test_register_sharded_in_library_world1_matches_unsharded(gpu_lib, oracle, path, N):
+    # a one-rank communicator on the single GPU: pack -> ncclAllGather -> merge -> ... -> ncclAllReduce(max) all run
+    p = synth.make_pair(N, 0.05, 8400)
+    ident = (C.c_ubyte * _abi.COMM_ID_BYTES)()
+    assert gpu_lib.sac_cot_comm_unique_id(ident) == _abi.OK
+    with Registrar(lib=gpu_lib) as one, Registrar(lib=gpu_lib) as sh:
+        for r in (one, sh):
+            r.set("triangle_path", path)
+            r.set("keep_debug", 1)
+        with pytest.raises(SacCotError) as ei:   # no communicator yet
+            sh.register_sharded_ptr(p.src.ctypes.data, p.dst.ctypes.data, N, 0, 0, 0, _abi.LOC_HOST)
+        assert ei.value.status in (_abi.E_NULL, _abi.E_COMM)
+        sh.comm_init(rank=0, world=1, unique_id=bytes(ident))
+        assert sh.get("comm_world") == 1 and sh.get("comm_rank") == 0
+        R1, t1, i1 = one.register(p.src, p.dst)
+        launches0 = sh.get("launches")
+        R, t, inl = sh.register_sharded(p.src, p.dst)
+        np.testing.assert_array_equal(R, R1)
+        np.testing.assert_array_equal(t, t1)
+        assert inl == i1
+        assert sh.get("launches") - launches0 >= 12   # the pipeline plus the record and merge kernels
+        for name, which in [("t_node", _abi.DBG_T_NODE), ("top_edges", _abi.DBG_TOP_EDGES), ("triangles", _abi.DBG_TRIANGLES),
+                            ("hyp_score", _abi.DBG_HYP_SCORE), ("best_key", _abi.DBG_BEST_KEY), ("mask", _abi.DBG_MASK)]:
+            np.testing.assert_array_equal(sh.debug(0, which), one.debug(0, which), err_msg=name)
+        set_params(oracle, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
+        Ro, to, io = oracle.register(p.src, p.dst)
+        compare_pose(R, t, inl, Ro, to, io)
+        # a second call re-uses the resident plan (no descriptor upload) and gives the same bits
+        R2, t2, i2 = sh.register_sharded(p.src, p.dst)
+        np.testing.assert_array_equal(R2, R1)
+        assert i2 == i1
+
+
+def test_register_sharded_in_library_grows_key_pool_in_step(gpu_lib):
+    # dense graph: the first attempt overflows the 12.5 % key-pool guess; the merged summary tells every rank to
+    # grow and re-run
+    p = synth.make_pair(1500, 0.2, 8500)
+    ident = (C.c_ubyte * _abi.COMM_ID_BYTES)()
+    assert gpu_lib.sac_cot_comm_unique_id(ident) == _abi.OK
+    with Registrar(lib=gpu_lib, tau_compat=1.5) as one, Registrar(lib=gpu_lib, tau_compat=1.5) as sh:
+        sh.comm_init(rank=0, world=1, unique_id=bytes(ident))
+        R1, t1, i1 = one.register(p.src, p.dst)
+        R, t, inl = sh.register_sharded(p.src, p.dst)
+        assert sh.get("retries") >= 1
+        np.testing.assert_array_equal(R, R1)
+        np.testing.assert_array_equal(t, t1)
+        assert inl == i1
+
+
+def _sharded_worker(rank, world, port, N, ratio, seed, path, out_dir):
+    import os
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # carries the 128-byte NCCL id only
+    p = synth.make_pair(N, ratio, seed)
+    with Registrar(device=rank) as reg:
+        reg.set("triangle_path", path)
+        reg.comm_init()
+        R, t, inl = reg.register_sharded(p.src, p.dst)
+        used = reg.get("triangle_path_used")
+        # device-resident form: enqueue only, outputs in device buffers
+        dev = torch.device("cuda", rank)
+        d_src, d_dst = torch.from_numpy(p.src).to(dev), torch.from_numpy(p.dst).to(dev)
+        d_R = torch.zeros(9, dtype=torch.float32, device=dev)
+        d_t = torch.zeros(3, dtype=torch.float32, device=dev)
+        d_i = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        reg.register_sharded_ptr(d_src.data_ptr(), d_dst.data_ptr(), N, d_R.data_ptr(), d_t.data_ptr(), d_i.data_ptr(),
+                                 _abi.LOC_DEVICE)
+        status = reg.get("last_status")   # synchronises
+        R1, t1, i1 = reg.register(p.src, p.dst)   # unsharded, same GPU
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), R=R, t=t, inl=inl, R1=R1, t1=t1, i1=i1, used=used, status=status,
+             dR=d_R.cpu().numpy().reshape(3, 3), dt=d_t.cpu().numpy(), di=int(d_i.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("path,N,ratio", [(0, 4000, 0.05), (2, 9000, 0.05)])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_register_sharded_in_library_multi_gpu(gpu_lib, tmp_path, world, path, N, ratio):
+    # one process per GPU, NCCL inside the library; needs `world` GPUs (gpurun --gpus N)
+    import socket
+
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_sharded_worker, args=(world, port, N, ratio, 8600 + world, path, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(tmp_path / f"rank{r}.npz")
+        np.testing.assert_array_equal(got["R"], got["R1"])   # every rank: bit-identical to the unsharded result
+        np.testing.assert_array_equal(got["t"], got["t1"])
+        assert int(got["inl"]) == int(got["i1"])
+        assert int(got["status"]) == 0
+        np.testing.assert_array_equal(got["dR"], got["R1"])
+        np.testing.assert_array_equal(got["dt"], got["t1"])
+        assert int(got["di"]) == int(got["i1"])
+        assert int(got["used"]) == (1 if path else 0)
+
+
+def test_overflowing_device_call_leaves_defined_outputs_and_reports(gpu_lib):
+    # a key-pool overflow must stop every later kernel of the chunk.  The arena is poisoned by a larger,
+    # different batch first; the overflowing device-location call must then neither fault nor write garbage:
+    # its outputs read "no result" (R = I, t = 0, inliers = 0), last_status reports the overflow once, and the next
+    # call (pool grown) is correct.
+    import torch
+    dev = torch.device("cuda", 0)
+    big = [synth.make_pair(2000, 0.1, 8700 + k) for k in range(3)]
+    p = synth.make_pair(900, 0.3, 8710)
+    stream = torch.cuda.current_stream(dev)
+    with Registrar(lib=gpu_lib, device=0, stream=stream.cuda_stream) as g, Registrar(lib=gpu_lib) as ref:
+        g.set("lanes", 1)
+        g.register_batch([q.src for q in big], [q.dst for q in big])      # fills the arena with other pairs' data
+        set_params(g, tau_compat=2.0)
+        set_params(ref, tau_compat=2.0)
+        d_src, d_dst = torch.from_numpy(p.src).to(dev), torch.from_numpy(p.dst).to(dev)
+        d_R = torch.full((9,), 7.0, dtype=torch.float32, device=dev)
+        d_t = torch.full((3,), 7.0, dtype=torch.float32, device=dev)
+        d_i = torch.full((1,), 7, dtype=torch.int32, device=dev)
+        offsets = np.array([0, 900], dtype=np.int64)
+        g.register_packed_ptr(d_src.data_ptr(), d_dst.data_ptr(), offsets, d_R.data_ptr(), d_t.data_ptr(), d_i.data_ptr(),
+                              _abi.LOC_DEVICE)
+        assert g.get("last_status") == _abi.E_NOMEM
+        assert g.get("last_status") == 0                                   # reported once
+        np.testing.assert_array_equal(d_R.cpu().numpy(), np.eye(3, dtype=np.float32).ravel())
+        np.testing.assert_array_equal(d_t.cpu().numpy(), np.zeros(3, np.float32))
+        assert int(d_i.item()) == 0
+        g.register_packed_ptr(d_src.data_ptr(), d_dst.data_ptr(), offsets, d_R.data_ptr(), d_t.data_ptr(), d_i.data_ptr(),
+                              _abi.LOC_DEVICE)
+        assert g.get("last_status") == 0
+        R1, t1, i1 = ref.register(p.src, p.dst)
+        np.testing.assert_array_equal(d_R.cpu().numpy().reshape(3, 3), R1)
+        assert int(d_i.item()) == i1
