@@ -59,6 +59,7 @@ struct Layout {
   uint32_t* adj = nullptr;
   uint32_t* panel = nullptr;   // K-panel copy of the adjacency (tensor-core triangle path only)
   uint32_t* theta = nullptr;   // per-pair pruning threshold (tensor-core triangle path only)
+  void* theta_ws = nullptr;    // scratch of the multi-CTA threshold kernels (calls with very few pairs)
   uint2* tile_tab = nullptr;   // tensor-core path: (pair, row block << 16 | column block) per tile
   int total_tiles = 0;         // tensor-core path: tiles of the whole chunk
   unsigned long long* sel = nullptr;
@@ -323,6 +324,8 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_adj = take(sizeof(uint32_t) * adj);
   const size_t o_panel = tensor_path ? take(sizeof(uint32_t) * panel) : 0;
   const size_t o_theta = tensor_path ? take(sizeof(uint32_t) * pairs) : 0;
+  const size_t theta_ws_bytes = tensor_path ? theta_scratch_bytes(pairs) : 0;
+  const size_t o_theta_ws = theta_ws_bytes ? take(theta_ws_bytes) : 0;
   const size_t o_tiles = tensor_path ? take(sizeof(uint2) * std::max(1, tiles)) : 0;
   const size_t o_sel = take(sizeof(unsigned long long) * L.Ke * pairs);
   const size_t o_tie = take(sizeof(unsigned long long) * kTieCap * pairs);
@@ -354,6 +357,7 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.adj = reinterpret_cast<uint32_t*>(o_adj);
   L.panel = tensor_path ? reinterpret_cast<uint32_t*>(o_panel) : nullptr;
   L.theta = tensor_path ? reinterpret_cast<uint32_t*>(o_theta) : nullptr;
+  L.theta_ws = theta_ws_bytes ? reinterpret_cast<void*>(o_theta_ws + 1) : nullptr;  // +1: offset 0 must not read as "absent"
   L.tile_tab = tensor_path ? reinterpret_cast<uint2*>(o_tiles) : nullptr;
   L.sel = reinterpret_cast<unsigned long long*>(o_sel);
   L.tie = reinterpret_cast<unsigned long long*>(o_tie);
@@ -390,6 +394,7 @@ void bind(Layout& L, unsigned char* base, bool has_input, bool tensor_path) {
   L.adj = rebase(L.adj, base);
   L.panel = rebase(L.panel, base, tensor_path);
   L.theta = rebase(L.theta, base, tensor_path);
+  L.theta_ws = L.theta_ws ? static_cast<void*>(base + (reinterpret_cast<size_t>(L.theta_ws) - 1)) : nullptr;
   L.tile_tab = rebase(L.tile_tab, base, tensor_path);
   L.sel = rebase(L.sel, base);
   L.tie = rebase(L.tie, base);
@@ -525,7 +530,7 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   KL_TRY(launch_key_scan(lc, L.desc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap, tri_mode));
   mark(ST_SCAN);
   if (tri_mode != 0) {
-    KL_TRY(launch_tri_theta(lc, L.desc, L.pairs, L.max_npad, L.adj, L.chunk, L.theta, L.Ke, ctx->tri_prune));
+    KL_TRY(launch_tri_theta(lc, L.desc, L.pairs, L.max_npad, L.adj, L.chunk, L.theta, L.theta_ws, L.Ke, ctx->tri_prune));
     mark(ST_THETA);
     KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, L.adj, L.panel, L.state, L.chunk, ln.keys, L.theta,
                                 L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg));

@@ -194,8 +194,12 @@ __host__ __device__ inline int mma_tiles_of_pair(int N) {
 }
 // CTA pairs (clusters) the tensor-core kernel runs with; cluster c walks entries c, c + n, c + 2 n, ... of the tile list
 inline int mma_clusters(int total_tiles, int sm_count) { return total_tiles < sm_count / 2 ? total_tiles : sm_count / 2; }
+// d_scratch (theta_scratch_bytes(pairs) bytes, or null): calls with at most kThetaSplitMaxPairs large pairs spread
+// the sample evaluation over many CTAs (three launches instead of one)
+constexpr int kThetaSplitMaxPairs = 4;
+size_t theta_scratch_bytes(int pairs);
 int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
-                     const ChunkDev* d_chunk, uint32_t* d_theta, int Ke, int prune);
+                     const ChunkDev* d_chunk, uint32_t* d_theta, void* d_scratch, int Ke, int prune);
 int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_tiles, int total_tiles,
                          const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
                          unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,

@@ -9,6 +9,8 @@
 // integers.  Only the fp64 refit is tolerance-compared.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace saccot {
 
 #define FADD(a, b) __fadd_rn((a), (b))
@@ -266,13 +268,25 @@ __device__ __forceinline__ f32x2 residual2_x2(const f32x2 (&rt2)[12], f32x2 px, 
 // Phase 2 (scalar, the survivors, one bit per point in a register mask): the full specified chain, bit-identical to
 // the oracle's.  ncu before (`profiles/ncu_score_r01a.txt`): FP32 pipe saturated by 15 FFMA2-class instructions per
 // point pair and hypothesis, issue slots 56 % used.
+//
+// nsplit > 1 (few pairs, many points: the single-pair calls): the hypothesis blocks alone would leave most SMs idle,
+// so the correspondences are cut into nsplit ranges of whole slabs, one CTA per (hypothesis block, range); a CTA adds
+// its partial integer score to hyp_key[h] (zeroed by the launcher; integer adds commute, so the total is exact and
+// order-free) and score_finish_kernel turns the totals into keys and takes the argmax.
 template <int MODE>
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(
     const PairDesc* __restrict__ descs, const float* __restrict__ soa, const int32_t* __restrict__ tri,
     const float* __restrict__ rt_all, unsigned long long* __restrict__ hyp_key, PairDev* __restrict__ state,
-    float tau2, int K, int h_begin, int h_end) {
+    float tau2, int K, int h_begin, int h_end, int nsplit) {
   const int pair = blockIdx.y;
   const PairDesc d = descs[pair];
+  const int hblock = static_cast<int>(blockIdx.x) / nsplit, split = static_cast<int>(blockIdx.x) % nsplit;
+  int n_begin = 0, n_end = d.N;
+  if (nsplit > 1) {
+    const int slabs = (d.N + kScoreSlab - 1) / kScoreSlab, per = (slabs + nsplit - 1) / nsplit;
+    n_begin = min(d.N, split * per * kScoreSlab);
+    n_end = min(d.N, n_begin + per * kScoreSlab);
+  }
   // slab[p] holds correspondences 2p and 2p+1:  {sx0,sx1,sy0,sy1} {sz0,sz1,dx0,dx1} {dy0,dy1,dz0,dz1}
   __shared__ float4 slab[kScoreSlab / 2][3];
   __shared__ unsigned long long wbest[kScoreThreads / 32];
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
   f32x2 rx2[kScoreHyp][4];  // packed copies of R00, R01, R02, tx for phase 1
 #pragma unroll
   for (int u = 0; u < kScoreHyp; ++u) {
-    hid[u] = h_begin + blockIdx.x * (kScoreThreads * kScoreHyp) + u * kScoreThreads + tid;
+    hid[u] = h_begin + hblock * (kScoreThreads * kScoreHyp) + u * kScoreThreads + tid;
     valid[u] = hid[u] < h_end && tri[(static_cast<size_t>(pair) * K + (hid[u] < K ? hid[u] : 0)) * 3] >= 0;
     const float* src_rt = rt_all + (static_cast<size_t>(pair) * K + (hid[u] < K ? hid[u] : 0)) * 12;
 #pragma unroll
@@ -302,8 +316,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
   const float* base = soa + d.soa_off;
   const size_t np = static_cast<size_t>(d.Npad);
   const float nan = __int_as_float(0x7fc00000);
-  for (int n0 = 0; n0 < d.N; n0 += kScoreSlab) {
-    const int nn = min(kScoreSlab, d.N - n0);
+  for (int n0 = n_begin; n0 < n_end; n0 += kScoreSlab) {
+    const int nn = min(kScoreSlab, n_end - n0);
     const int npairs = (nn + 1) / 2;
     __syncthreads();  // previous slab fully consumed
     for (int k = tid; k < kScoreSlab / 2; k += kScoreThreads) {
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
                      sz = *reinterpret_cast<const float2*>(base + 2 * np + n);
         float2 dx = *reinterpret_cast<const float2*>(base + 3 * np + n), dy = *reinterpret_cast<const float2*>(base + 4 * np + n),
                dz = *reinterpret_cast<const float2*>(base + 5 * np + n);
-        if (n + 1 >= d.N) { dx.y = nan; dy.y = nan; dz.y = nan; }
+        if (n + 1 >= n_end) { dx.y = nan; dy.y = nan; dz.y = nan; }
         slab[k][0] = make_float4(sx.x, sx.y, sy.x, sy.y);
         slab[k][1] = make_float4(sz.x, sz.y, dx.x, dx.y);
         slab[k][2] = make_float4(dy.x, dy.y, dz.x, dz.y);
@@ -378,7 +392,15 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
     const unsigned int far = static_cast<unsigned int>(FMUL(FDIV(tau2, tau2), 1048576.0f));
 #pragma unroll
     for (int u = 0; u < kScoreHyp; ++u)
-      fsum[u] += static_cast<unsigned long long>(static_cast<unsigned int>(d.N) - cnt[u]) * far;
+      fsum[u] += static_cast<unsigned long long>(static_cast<unsigned int>(n_end - n_begin) - cnt[u]) * far;
+  }
+  if (nsplit > 1) {  // partial integer scores; score_finish_kernel builds the keys
+#pragma unroll
+    for (int u = 0; u < kScoreHyp; ++u) {
+      const unsigned long long part = MODE == 0 ? static_cast<unsigned long long>(cnt[u]) : fsum[u];
+      if (valid[u] && part) atomicAdd(&hyp_key[static_cast<size_t>(pair) * K + hid[u]], part);
+    }
+    return;
   }
 
   unsigned long long best = 0;
@@ -403,20 +425,70 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
   }
 }
 
-int launch_score(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int /*max_n*/, const float* d_soa,
+// Split scoring, second half: hyp_key[h] holds the integer total (mode 0: inliers, mode 1: sum of the fixed-point
+// residuals) of hypothesis h; turn it into the selection key and max-reduce into the pair's best key.
+template <int MODE>
+__global__ void __launch_bounds__(256) score_finish_kernel(const PairDesc* __restrict__ descs,
+                                                           const int32_t* __restrict__ tri,
+                                                           unsigned long long* __restrict__ hyp_key,
+                                                           PairDev* __restrict__ state, int K, int h_begin, int h_end) {
+  const int pair = blockIdx.y;
+  const int h = h_begin + blockIdx.x * 256 + threadIdx.x;
+  __shared__ unsigned long long wbest[8];
+  unsigned long long key = 0;
+  if (h < h_end) {
+    if (tri[(static_cast<size_t>(pair) * K + h) * 3] >= 0) {
+      const unsigned long long total = hyp_key[static_cast<size_t>(pair) * K + h];
+      const unsigned long long score = MODE == 0 ? total + 1ull
+                                                 : (static_cast<unsigned long long>(descs[pair].N) << 20) - total + 1ull;
+      key = (score << 16) | static_cast<unsigned long long>(0xFFFFu - static_cast<unsigned int>(h));
+    }
+    hyp_key[static_cast<size_t>(pair) * K + h] = key;
+  }
+  unsigned long long best = warp_max_u64(key);
+  if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) best = wbest[w] > best ? wbest[w] : best;
+    if (best) atomicMax(&state[pair].best_key, best);
+  }
+}
+
+int launch_score(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_n, const float* d_soa,
                  const int32_t* d_tri, const float* d_rt, unsigned long long* d_hyp_key, PairDev* d_state, float tau2,
                  int K, int h_begin, int h_end, int mode) {
   const int span = h_end - h_begin;
   if (span <= 0) return 0;
-  dim3 grid((span + kScoreThreads * kScoreHyp - 1) / (kScoreThreads * kScoreHyp), pairs);
+  const int hblocks = (span + kScoreThreads * kScoreHyp - 1) / (kScoreThreads * kScoreHyp);
+  // too few CTAs for the device: split the correspondences as well (at least 2 slabs per range)
+  int nsplit = 1;
+  const int slabs = (max_n + kScoreSlab - 1) / kScoreSlab;
+  if (hblocks * pairs < lc.sm_count && slabs >= 8) {
+    nsplit = std::min((2 * lc.sm_count + hblocks * pairs - 1) / (hblocks * pairs), slabs / 2);
+    if (nsplit < 2) nsplit = 1;
+  }
+  if (nsplit > 1) {
+    for (int b = 0; b < pairs; ++b) {
+      const cudaError_t me = cudaMemsetAsync(d_hyp_key + static_cast<size_t>(b) * K + h_begin, 0, sizeof(unsigned long long) * span, lc.stream);
+      if (me != cudaSuccess) return -static_cast<int>(me);
+    }
+  }
+  dim3 grid(hblocks * nsplit, pairs);
   if (mode == 0)
     score_kernel<0><<<grid, kScoreThreads, 0, lc.stream>>>(d_desc, d_soa, d_tri, d_rt, d_hyp_key, d_state, tau2, K,
-                                                           h_begin, h_end);
+                                                           h_begin, h_end, nsplit);
   else
     score_kernel<1><<<grid, kScoreThreads, 0, lc.stream>>>(d_desc, d_soa, d_tri, d_rt, d_hyp_key, d_state, tau2, K,
-                                                           h_begin, h_end);
-  const cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+                                                           h_begin, h_end, nsplit);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  if (nsplit == 1) return 1;
+  dim3 fgrid((span + 255) / 256, pairs);
+  if (mode == 0) score_finish_kernel<0><<<fgrid, 256, 0, lc.stream>>>(d_desc, d_tri, d_hyp_key, d_state, K, h_begin, h_end);
+  else score_finish_kernel<1><<<fgrid, 256, 0, lc.stream>>>(d_desc, d_tri, d_hyp_key, d_state, K, h_begin, h_end);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 2 : -static_cast<int>(e);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -826,6 +826,156 @@ static size_t theta_smem_bytes(int max_npad) {
   return static_cast<size_t>(max_npad) + static_cast<size_t>(kThetaNodes) * cw * 4 + kThetaSamples * 2 + kThetaNodes * 16 + 16;
 }
 
+// block-wide count of a per-element predicate over n entries (1024 threads)
+template <typename Pred>
+__device__ __forceinline__ int theta_block_count(Pred pred, int n, int* s_cnt) {
+  const int t = threadIdx.x, lane = t & 31;
+  if (t == 0) *s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int k = t; k < n; k += 1024) c += pred(k) ? 1 : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0 && c) atomicAdd(s_cnt, c);
+  __syncthreads();
+  const int r = *s_cnt;
+  __syncthreads();
+  return r;
+}
+
+// Steps 1-4a: the sample nodes (the S = min(N, 128) rows with the largest proxy degree, ties by index), the edges
+// among them as a bit mask per sample row (y > x) and their number.  Returns the number of sample nodes; *nts_out =
+// the number of sample edges.  deg: [Npad] bytes, nodes: [128], emask: [128][4], all in shared memory.
+__device__ __forceinline__ int theta_sample(const PairDesc& d, const uint32_t* __restrict__ adjp, unsigned char* deg,
+                                            int* nodes, uint32_t* emask, int* s_cnt, int* s_nsel, int* s_nts,
+                                            int* nts_out) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int S = d.N < kThetaNodes ? d.N : kThetaNodes;
+  // 1. proxy degree: popcount of the first min(stride, 16) words (512 columns) of every row
+  {
+    const int nq = min(d.stride, 16) / 4;  // stride is a multiple of 4
+    for (int i = t; i < d.Npad; i += 1024) {
+      int c = 0;
+      if (i < d.N) {
+        const uint4* rp = reinterpret_cast<const uint4*>(adjp + static_cast<size_t>(i) * d.stride);
+        for (int k = 0; k < nq; ++k) {
+          const uint4 w = rp[k];
+          c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+        }
+      }
+      deg[i] = static_cast<unsigned char>(min(c, 255));
+    }
+  }
+  if (t == 0) *s_nts = 0;
+  __syncthreads();
+  // 2. largest degree threshold that still leaves >= S nodes
+  int lo = 0, hi = 256;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (theta_block_count([&](int k) { return deg[k] >= mid; }, d.N, s_cnt) >= S) lo = mid;
+    else hi = mid;
+  }
+  const int thr = lo;
+  const int n_above = theta_block_count([&](int k) { return deg[k] > thr; }, d.N, s_cnt);
+  // 3. the S sample nodes in index order: every node above the threshold, then ties until S are taken
+  if (warp == 0) {
+    int nsel = 0, quota = S - n_above;
+    for (int i0 = 0; i0 < d.N && nsel < S; i0 += 32) {
+      const int i = i0 + lane;
+      const int dg = i < d.N ? deg[i] : -1;
+      const bool tie = dg == thr;
+      const unsigned tmask = __ballot_sync(0xffffffffu, tie);
+      const int tie_rank = __popc(tmask & ((1u << lane) - 1u));
+      const bool take = dg > thr || (tie && tie_rank < quota);
+      const unsigned smask = __ballot_sync(0xffffffffu, take);
+      if (take) nodes[nsel + __popc(smask & ((1u << lane) - 1u))] = i;
+      nsel += __popc(smask);
+      quota -= min(quota, __popc(tmask));
+    }
+    if (lane == 0) *s_nsel = nsel;
+  }
+  __syncthreads();
+  const int nsel = *s_nsel;
+  // 4a. edges among the sample nodes: a bit mask per sample row
+  for (int k = t; k < kThetaNodes * 4; k += 1024) emask[k] = 0u;
+  __syncthreads();
+  for (int base = 0; base < nsel * nsel; base += 1024) {
+    const int idx = base + t;
+    const int x = idx / nsel, y = idx - x * nsel;
+    bool is_edge = false;
+    if (idx < nsel * nsel && x < y) {
+      const int a = nodes[x], b = nodes[y];
+      is_edge = ((adjp[static_cast<size_t>(a) * d.stride + (b >> 5)] >> (b & 31)) & 1u) != 0u;
+    }
+    if (is_edge) atomicOr(&emask[x * 4 + (y >> 5)], 1u << (y & 31));
+    const unsigned em = __ballot_sync(0xffffffffu, is_edge);
+    if (lane == 0 && em) atomicAdd(s_nts, __popc(em));
+  }
+  __syncthreads();
+  *nts_out = *s_nts;
+  return nsel;
+}
+
+// Step 4b for the adjacency words [c0, c0 + cw): the sample rows are staged in shared memory; a warp keeps sample
+// row x in registers (six words per lane at most) and walks its partners y > x: per edge 6 LDS, AND, a carry-save
+// adder tree (3 POPC instead of 6: POPC and REDUX share the slow XU pipe) and one warp reduction.  Rows are dealt so
+// that every warp gets the same number of partners (x, 63 - x, 64 + x, 127 - x).  add(x, y, c) receives the count.
+template <typename Add>
+__device__ __forceinline__ void theta_count_chunk(const PairDesc& d, const uint32_t* __restrict__ adjp, const int* nodes,
+                                                  const uint32_t* emask, uint32_t* rows_s, int nsel, int c0, int cw,
+                                                  int cw_max, Add add) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int r = warp; r < nsel; r += 32) {
+    const uint32_t* rp = adjp + static_cast<size_t>(nodes[r]) * d.stride + c0;
+    for (int w = lane; w < cw_max; w += 32) rows_s[r * cw_max + w] = w < cw ? rp[w] : 0u;
+  }
+  __syncthreads();
+  for (int j = 0; j < 4; ++j) {
+    const int x = (j == 0) ? warp : (j == 1) ? 63 - warp : (j == 2) ? 64 + warp : 127 - warp;
+    if (x >= nsel) continue;
+    uint32_t rx[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) rx[r] = lane + 32 * r < cw_max ? rows_s[x * cw_max + lane + 32 * r] : 0u;
+    for (int wq = 0; wq < 4; ++wq) {
+      uint32_t bits = emask[x * 4 + wq];
+      while (bits) {
+        const int y = 32 * wq + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t* ry = rows_s + y * cw_max + lane;
+        uint32_t a[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) a[r] = lane + 32 * r < cw_max ? (rx[r] & ry[32 * r]) : 0u;
+        // two carry-save adders: a0+a1+a2 -> (s1, c1), a3+a4+a5 -> (s2, c2); sum = popc(s1)+popc(s2) + 2 popc(c1)+2 popc(c2)
+        const uint32_t s1 = a[0] ^ a[1] ^ a[2], c1 = (a[0] & a[1]) | (a[2] & (a[0] ^ a[1]));
+        const uint32_t s2 = a[3] ^ a[4] ^ a[5], c2 = (a[3] & a[4]) | (a[5] & (a[3] ^ a[4]));
+        // third adder over (s1, s2, 0) and the carries: sum = popc(s1 ^ s2) + 2 (popc(s1 & s2) + popc(c1) + popc(c2))
+        const uint32_t lo1 = s1 ^ s2, hi1 = s1 & s2;
+        // carries c1, c2, hi1 all weigh 2: one more adder -> (s3, c3) with weights 2 and 4
+        const uint32_t s3 = c1 ^ c2 ^ hi1, c3 = (c1 & c2) | (hi1 & (c1 ^ c2));
+        int c = __popc(lo1) + 2 * __popc(s3) + 4 * __popc(c3);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) add(x, y, c);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Step 5: theta = K_e-th largest sample count (0 if the sample holds fewer than K_e edges); ts entries are T + 1,
+// 0 = no edge.  bit 31: certified by a fat sample, the triangle kernel need not try to raise it.
+__device__ __forceinline__ uint32_t theta_pick(const unsigned short* ts, int nts, int Ke, int* s_cnt) {
+  uint32_t th = 0;
+  if (nts >= Ke) {
+    int l2 = 0, h2 = 65535;
+    while (h2 - l2 > 1) {
+      const int mid = (l2 + h2) >> 1;
+      if (theta_block_count([&](int k) { return ts[k] > mid; }, kThetaSamples, s_cnt) >= Ke) l2 = mid;
+      else h2 = mid;
+    }
+    th = static_cast<uint32_t>(l2);
+  }
+  return th | (nts >= 4 * Ke ? 0x80000000u : 0u);
+}
+
 __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restrict__ descs,
                                                          const uint32_t* __restrict__ adj,
                                                          const ChunkDev* __restrict__ chunk,
@@ -845,149 +995,102 @@ __global__ void __launch_bounds__(1024) tri_theta_kernel(const PairDesc* __restr
   unsigned char* deg = reinterpret_cast<unsigned char*>(ts + kThetaSamples);      // [Npad] proxy degrees, saturated
   __shared__ int nodes[kThetaNodes];
   __shared__ int s_cnt, s_nsel, s_nts;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x;
   const uint32_t* adjp = adj + d.adj_off;
-  const int S = d.N < kThetaNodes ? d.N : kThetaNodes;
-
-  // 1. proxy degree: popcount of the first min(stride, 16) words (512 columns) of every row
-  {
-    const int nq = min(d.stride, 16) / 4;  // stride is a multiple of 4
-    for (int i = t; i < d.Npad; i += 1024) {
-      int c = 0;
-      if (i < d.N) {
-        const uint4* rp = reinterpret_cast<const uint4*>(adjp + static_cast<size_t>(i) * d.stride);
-        for (int k = 0; k < nq; ++k) {
-          const uint4 w = rp[k];
-          c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
-        }
-      }
-      deg[i] = static_cast<unsigned char>(min(c, 255));
-    }
-  }
-  if (t == 0) s_nts = 0;
-  __syncthreads();
-
-  // block-wide count of a per-element predicate over n entries
-  auto block_count = [&](auto pred, int n) {
-    if (t == 0) s_cnt = 0;
-    __syncthreads();
-    int c = 0;
-    for (int k = t; k < n; k += 1024) c += pred(k) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0 && c) atomicAdd(&s_cnt, c);
-    __syncthreads();
-    const int r = s_cnt;
-    __syncthreads();
-    return r;
-  };
-
-  // 2. largest degree threshold that still leaves >= S nodes
-  int lo = 0, hi = 256;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (block_count([&](int k) { return deg[k] >= mid; }, d.N) >= S) lo = mid;
-    else hi = mid;
-  }
-  const int thr = lo;
-  const int n_above = block_count([&](int k) { return deg[k] > thr; }, d.N);
-
-  // 3. the S sample nodes in index order: every node above the threshold, then ties until S are taken
-  if (warp == 0) {
-    int nsel = 0, quota = S - n_above;
-    for (int i0 = 0; i0 < d.N && nsel < S; i0 += 32) {
-      const int i = i0 + lane;
-      const int dg = i < d.N ? deg[i] : -1;
-      const bool tie = dg == thr;
-      const unsigned tmask = __ballot_sync(0xffffffffu, tie);
-      const int tie_rank = __popc(tmask & ((1u << lane) - 1u));
-      const bool take = dg > thr || (tie && tie_rank < quota);
-      const unsigned smask = __ballot_sync(0xffffffffu, take);
-      if (take) nodes[nsel + __popc(smask & ((1u << lane) - 1u))] = i;
-      nsel += __popc(smask);
-      quota -= min(quota, __popc(tmask));
-    }
-    if (lane == 0) s_nsel = nsel;
+  int nts = 0;
+  const int nsel = theta_sample(d, adjp, deg, nodes, emask, &s_cnt, &s_nsel, &s_nts, &nts);
+  // dense table of counts (T + 1, 0 = no edge)
+  for (int k = t; k < kThetaSamples; k += 1024) {
+    const int x = k >> 7, y = k & 127;
+    ts[k] = static_cast<unsigned short>((emask[x * 4 + (y >> 5)] >> (y & 31)) & 1u);
   }
   __syncthreads();
-  const int nsel = s_nsel;
+  // 4b. exact T of those edges, the sample rows staged chunk by chunk
+  for (int c0 = 0; c0 < d.stride; c0 += cw_max)
+    theta_count_chunk(d, adjp, nodes, emask, rows_s, nsel, c0, min(cw_max, d.stride - c0), cw_max,
+                      [&](int x, int y, int c) { ts[x * kThetaNodes + y] = static_cast<unsigned short>(ts[x * kThetaNodes + y] + c); });
+  const uint32_t th = theta_pick(ts, nts, Ke, &s_cnt);
+  if (t == 0) theta[pair] = th;
+}
 
-  // 4a. edges among the sample nodes: a bit mask per sample row and a dense table of counts (T + 1, 0 = no edge)
-  for (int k = t; k < kThetaNodes * 4; k += 1024) emask[k] = 0u;
-  for (int k = t; k < kThetaSamples; k += 1024) ts[k] = 0;
+// The same computation for calls with very few (large) pairs, where one CTA per pair leaves the device idle for a
+// millisecond at N = 50 000: (a) one CTA per pair samples, (b) one CTA per (64-word chunk of the rows, pair) adds its
+// share of the exact counts into a global table, (c) one CTA per pair picks the threshold.  Identical result: the
+// counts are integers.
+struct ThetaScratch {
+  int nodes[kThetaNodes];
+  uint32_t emask[kThetaNodes * 4];
+  int nsel, nts, pad0, pad1;
+  uint32_t ts[kThetaSamples];  // exact T of sample edge (x, y)
+};
+constexpr int kThetaSplitW = 64;
+
+__global__ void __launch_bounds__(1024) tri_theta_sample_kernel(const PairDesc* __restrict__ descs,
+                                                                const uint32_t* __restrict__ adj,
+                                                                const ChunkDev* __restrict__ chunk,
+                                                                ThetaScratch* __restrict__ scratch, int prune) {
+  if (chunk->overflow || !chunk->use_tensor || !prune) return;
+  const int pair = blockIdx.x;
+  const PairDesc d = descs[pair];
+  extern __shared__ __align__(16) unsigned char th_smem[];
+  unsigned char* deg = th_smem;  // [Npad]
+  __shared__ int nodes[kThetaNodes];
+  __shared__ uint32_t emask[kThetaNodes * 4];
+  __shared__ int s_cnt, s_nsel, s_nts;
+  int nts = 0;
+  const int nsel = theta_sample(d, adj + d.adj_off, deg, nodes, emask, &s_cnt, &s_nsel, &s_nts, &nts);
+  ThetaScratch* sc = scratch + pair;
+  const int t = threadIdx.x;
+  if (t < kThetaNodes) sc->nodes[t] = t < nsel ? nodes[t] : 0;
+  if (t < kThetaNodes * 4) sc->emask[t] = emask[t];
+  if (t == 0) {
+    sc->nsel = nsel;
+    sc->nts = nts;
+  }
+  for (int k = t; k < kThetaSamples; k += 1024) sc->ts[k] = 0u;
+}
+
+__global__ void __launch_bounds__(1024) tri_theta_count_kernel(const PairDesc* __restrict__ descs,
+                                                               const uint32_t* __restrict__ adj,
+                                                               const ChunkDev* __restrict__ chunk,
+                                                               ThetaScratch* __restrict__ scratch, int prune) {
+  if (chunk->overflow || !chunk->use_tensor || !prune) return;
+  const int pair = blockIdx.y;
+  const PairDesc d = descs[pair];
+  const int c0 = static_cast<int>(blockIdx.x) * kThetaSplitW;
+  if (c0 >= d.stride) return;
+  __shared__ uint32_t rows_s[kThetaNodes * kThetaSplitW];  // 32 KB
+  __shared__ int nodes[kThetaNodes];
+  __shared__ uint32_t emask[kThetaNodes * 4];
+  ThetaScratch* sc = scratch + pair;
+  const int t = threadIdx.x;
+  if (t < kThetaNodes) nodes[t] = sc->nodes[t];
+  if (t < kThetaNodes * 4) emask[t] = sc->emask[t];
   __syncthreads();
-  for (int base = 0; base < nsel * nsel; base += 1024) {
-    const int idx = base + t;
-    const int x = idx / nsel, y = idx - x * nsel;
-    bool is_edge = false;
-    if (idx < nsel * nsel && x < y) {
-      const int a = nodes[x], b = nodes[y];
-      is_edge = ((adjp[static_cast<size_t>(a) * d.stride + (b >> 5)] >> (b & 31)) & 1u) != 0u;
-    }
-    if (is_edge) {
-      atomicOr(&emask[x * 4 + (y >> 5)], 1u << (y & 31));
-      ts[x * kThetaNodes + y] = 1;
-    }
-    const unsigned em = __ballot_sync(0xffffffffu, is_edge);
-    if (lane == 0 && em) atomicAdd(&s_nts, __popc(em));
+  theta_count_chunk(d, adj + d.adj_off, nodes, emask, rows_s, sc->nsel, c0, min(kThetaSplitW, d.stride - c0), kThetaSplitW,
+                    [&](int x, int y, int c) { if (c) atomicAdd(&sc->ts[x * kThetaNodes + y], static_cast<uint32_t>(c)); });
+}
+
+__global__ void __launch_bounds__(1024) tri_theta_pick_kernel(const ChunkDev* __restrict__ chunk,
+                                                              const ThetaScratch* __restrict__ scratch,
+                                                              uint32_t* __restrict__ theta, int Ke, int prune) {
+  if (chunk->overflow || !chunk->use_tensor) return;
+  const int pair = blockIdx.x;
+  if (!prune) {
+    if (threadIdx.x == 0) theta[pair] = 0u;
+    return;
+  }
+  __shared__ unsigned short ts[kThetaSamples];
+  __shared__ int s_cnt;
+  const ThetaScratch* sc = scratch + pair;
+  for (int k = threadIdx.x; k < kThetaSamples; k += 1024) {
+    const int x = k >> 7, y = k & 127;
+    const uint32_t e = (sc->emask[x * 4 + (y >> 5)] >> (y & 31)) & 1u;
+    ts[k] = static_cast<unsigned short>(e ? sc->ts[k] + 1u : 0u);
   }
   __syncthreads();
-  const int nts = s_nts;
-
-  // 4b. exact T of those edges.  The sample rows are staged chunk by chunk; a warp keeps sample row x in
-  //     registers (six words per lane at most) and walks its partners y > x: per edge 6 LDS, AND, a carry-save
-  //     adder tree (3 POPC instead of 6: POPC and REDUX share the slow XU pipe) and one warp reduction.  Rows are
-  //     dealt so that every warp gets the same number of partners (x, 63 - x, 64 + x, 127 - x).
-  for (int c0 = 0; c0 < d.stride; c0 += cw_max) {
-    const int cw = min(cw_max, d.stride - c0);
-    for (int r = warp; r < nsel; r += 32) {
-      const uint32_t* rp = adjp + static_cast<size_t>(nodes[r]) * d.stride + c0;
-      for (int w = lane; w < cw_max; w += 32) rows_s[r * cw_max + w] = w < cw ? rp[w] : 0u;
-    }
-    __syncthreads();
-    for (int j = 0; j < 4; ++j) {
-      const int x = (j == 0) ? warp : (j == 1) ? 63 - warp : (j == 2) ? 64 + warp : 127 - warp;
-      if (x >= nsel) continue;
-      uint32_t rx[6];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) rx[r] = lane + 32 * r < cw_max ? rows_s[x * cw_max + lane + 32 * r] : 0u;
-      for (int wq = 0; wq < 4; ++wq) {
-        uint32_t bits = emask[x * 4 + wq];
-        while (bits) {
-          const int y = 32 * wq + __ffs(bits) - 1;
-          bits &= bits - 1;
-          const uint32_t* ry = rows_s + y * cw_max + lane;
-          uint32_t a[6];
-#pragma unroll
-          for (int r = 0; r < 6; ++r) a[r] = lane + 32 * r < cw_max ? (rx[r] & ry[32 * r]) : 0u;
-          // two carry-save adders: a0+a1+a2 -> (s1, c1), a3+a4+a5 -> (s2, c2); sum = popc(s1)+popc(s2) + 2 popc(c1)+2 popc(c2)
-          const uint32_t s1 = a[0] ^ a[1] ^ a[2], c1 = (a[0] & a[1]) | (a[2] & (a[0] ^ a[1]));
-          const uint32_t s2 = a[3] ^ a[4] ^ a[5], c2 = (a[3] & a[4]) | (a[5] & (a[3] ^ a[4]));
-          // third adder over (s1, s2, 0) and the carries: sum = popc(s1 ^ s2) + 2 (popc(s1 & s2) + popc(c1) + popc(c2))
-          const uint32_t lo1 = s1 ^ s2, hi1 = s1 & s2;
-          // carries c1, c2, hi1 all weigh 2: one more adder -> (s3, c3) with weights 2 and 4
-          const uint32_t s3 = c1 ^ c2 ^ hi1, c3 = (c1 & c2) | (hi1 & (c1 ^ c2));
-          int c = __popc(lo1) + 2 * __popc(s3) + 4 * __popc(c3);
-          c = __reduce_add_sync(0xffffffffu, c);
-          if (lane == 0) ts[x * kThetaNodes + y] = static_cast<unsigned short>(ts[x * kThetaNodes + y] + c);
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  // 5. theta = K_e-th largest sample count (0 if the sample holds fewer than K_e edges); table entries are T + 1
-  uint32_t th = 0;
-  if (nts >= Ke) {
-    int l2 = 0, h2 = 65535;
-    while (h2 - l2 > 1) {
-      const int mid = (l2 + h2) >> 1;
-      if (block_count([&](int k) { return ts[k] > mid; }, kThetaSamples) >= Ke) l2 = mid;
-      else h2 = mid;
-    }
-    th = static_cast<uint32_t>(l2);
-  }
-  // bit 31: certified by a fat sample, the triangle kernel need not try to raise it
-  if (t == 0) theta[pair] = th | (nts >= 4 * Ke ? 0x80000000u : 0u);
+  const uint32_t th = theta_pick(ts, sc->nts, Ke, &s_cnt);
+  if (threadIdx.x == 0) theta[pair] = th;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1078,11 +1181,27 @@ int triangles_mma_configure() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tri_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(theta_smem_bytes(65536)));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tri_theta_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
+size_t theta_scratch_bytes(int pairs) { return pairs <= kThetaSplitMaxPairs ? sizeof(ThetaScratch) * static_cast<size_t>(pairs) : 0; }
+
 int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
-                     const ChunkDev* d_chunk, uint32_t* d_theta, int Ke, int prune) {
+                     const ChunkDev* d_chunk, uint32_t* d_theta, void* d_scratch, int Ke, int prune) {
+  if (d_scratch && pairs <= kThetaSplitMaxPairs && max_npad / 32 > 2 * kThetaSplitW) {
+    ThetaScratch* sc = static_cast<ThetaScratch*>(d_scratch);
+    tri_theta_sample_kernel<<<pairs, 1024, static_cast<size_t>(max_npad), lc.stream>>>(d_desc, d_adj, d_chunk, sc, prune);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    const int nchunks = (max_npad / 32 + kThetaSplitW - 1) / kThetaSplitW;
+    tri_theta_count_kernel<<<dim3(nchunks, pairs), 1024, 0, lc.stream>>>(d_desc, d_adj, d_chunk, sc, prune);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    tri_theta_pick_kernel<<<pairs, 1024, 0, lc.stream>>>(d_chunk, sc, d_theta, Ke, prune);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 3 : -static_cast<int>(e);
+  }
   tri_theta_kernel<<<pairs, 1024, theta_smem_bytes(max_npad), lc.stream>>>(d_desc, d_adj, d_chunk, d_theta, Ke, prune, max_npad);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);

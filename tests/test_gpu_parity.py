@@ -720,7 +720,9 @@ def test_overflowing_device_call_leaves_defined_outputs_and_reports(gpu_lib):
     # call (pool grown) is correct.
     import torch
     dev = torch.device("cuda", 0)
-    big = [synth.make_pair(2000, 0.1, 8700 + k) for k in range(3)]
+    # three N=700 pairs: a larger arena than the single N=900 pair needs (so it is re-used, stale contents and
+    # all) but a smaller key pool (12.5 % guess: 3 x 30 k keys) than its near-complete graph fills (~400 k edges)
+    big = [synth.make_pair(700, 0.1, 8700 + k) for k in range(3)]
     p = synth.make_pair(900, 0.3, 8710)
     stream = torch.cuda.current_stream(dev)
     with Registrar(lib=gpu_lib, device=0, stream=stream.cuda_stream) as g, Registrar(lib=gpu_lib) as ref:
