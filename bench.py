@@ -508,6 +508,81 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
     reg.close()
 
 
+def run_group(args, emit, torch):
+    """One process, --gpus N devices, ONE call per step: sac_cot_group_register_packed deals pair b of the batch to
+    device b mod N (strong scaling of a fixed batch)."""
+    from sac_cot_b200.api import Group
+    cfg = synth.CONFIGS[WORKLOAD]
+    pairs = args.pairs or cfg["pairs"]
+    N = cfg["N"]
+    G = args.gpus
+    ps, src, dst, offsets = make_batch(range(pairs))
+    grp = Group(range(G), tau_compat=cfg["tau"], tau_inlier=cfg["tau"])
+    if args.lanes:
+        grp.set("lanes", args.lanes)
+    if args.chunk_pairs:
+        grp.set("chunk_pairs", args.chunk_pairs)
+    K = grp.params.num_edges * grp.params.apex_per_edge
+    h_src, h_dst = torch.from_numpy(src).pin_memory(), torch.from_numpy(dst).pin_memory()
+    h_R = torch.empty((pairs, 3, 3), dtype=torch.float32).pin_memory()
+    h_t = torch.empty((pairs, 3), dtype=torch.float32).pin_memory()
+    h_i = torch.empty(pairs, dtype=torch.int32).pin_memory()
+
+    def step():
+        grp.register_packed_ptr(h_src.data_ptr(), h_dst.data_ptr(), offsets, h_R.data_ptr(), h_t.data_ptr(), h_i.data_ptr())
+
+    for _ in range(args.warmup + 2):
+        step()
+    launches0 = sum(grp.get(g, "launches") for g in range(G))
+    sampler = ClockSampler(0)
+    sampler.start()
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        step()   # returns when every device has delivered its results
+        ts.append(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    launches = sum(grp.get(g, "launches") for g in range(G)) - launches0
+    value = pairs * args.steps / sum(ts)
+    ok = 0
+    for b in range(pairs):
+        ang, dt_ = synth.pose_error(h_R[b].numpy(), h_t[b].numpy(), ps[b].R_gt, ps[b].t_gt)
+        ok += ang < np.deg2rad(5.0) and dt_ < 1.5 * cfg["tau"]
+    # the same batch through one device of the group: identical bits, and the 1-device time of the same call
+    with Registrar(device=0, tau_compat=cfg["tau"], tau_inlier=cfg["tau"]) as one:
+        r1R = torch.empty((pairs, 3, 3), dtype=torch.float32).pin_memory()
+        r1t = torch.empty((pairs, 3), dtype=torch.float32).pin_memory()
+        r1i = torch.empty(pairs, dtype=torch.int32).pin_memory()
+        t1 = []
+        for k in range(args.warmup + 2 + args.steps):
+            t0 = time.perf_counter()
+            one.register_packed_ptr(h_src.data_ptr(), h_dst.data_ptr(), offsets, r1R.data_ptr(), r1t.data_ptr(),
+                                    r1i.data_ptr(), _abi.LOC_HOST)
+            if k >= args.warmup + 2:
+                t1.append(time.perf_counter() - t0)
+        same = bool((r1R.numpy() == h_R.numpy()).all() and (r1t.numpy() == h_t.numpy()).all()
+                    and (r1i.numpy() == h_i.numpy()).all())
+    one_value = pairs * args.steps / sum(t1)
+    line = {
+        "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(ts) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: ONE batch of {pairs} pairs x N={N}, {ratio_label(cfg)} inliers, tau_c={cfg['tau']}",
+                   "parallelism": f"one process, one sac_cot_group_register_packed call per step: pair b on GPU b mod {G}, "
+                                  "one enqueueing thread per device, no collective",
+                   "pairs_per_step_whole_job": pairs, "N": N, "hypotheses_per_pair": K,
+                   "timing": "wall clock around the call (host buffers in, results out); `value` equals `e2e` because the "
+                             "group entry point takes host buffers only"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(src.nbytes + dst.nbytes),
+                "d2h_bytes_per_step": int(pairs * 52)},
+        "same_call_on_one_gpu": {"value": one_value, "speedup": value / one_value, "bit_identical": same},
+        "gpu_launches": int(launches), "clocks": clocks, "recall_vs_ground_truth": ok / pairs,
+        "ms_steps": [1e3 * x for x in ts],
+    }
+    emit(line)
+    grp.close()
+
+
 def run_single_sharded(args, rank, local_rank, world, emit, torch, dist, dev):
     """cfg5: one N = 50 000 pair through sac_cot_register_sharded (collectives inside the library)."""
     cfg = synth.CONFIGS[WORKLOAD]
@@ -720,7 +795,11 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if synth.CONFIGS[WORKLOAD]["pairs"] == 1 and WORKLOAD != "cfg1_single_n1000":
+    if world == 1 and args.gpus > 1:
+        if torch.cuda.device_count() < args.gpus:
+            raise SystemExit(f"bench.py: --gpus {args.gpus} without torchrun needs that many visible devices")
+        run_group(args, emit, torch)
+    elif synth.CONFIGS[WORKLOAD]["pairs"] == 1 and WORKLOAD != "cfg1_single_n1000":
         run_single_sharded(args, rank, local_rank, world, emit, torch, dist, dev)
     else:
         run_batched(args, rank, local_rank, world, emit, torch, dist, dev)

@@ -149,6 +149,27 @@ SAC_COT_API int sac_cot_register_packed(sac_cot_ctx* ctx,
                                         float* R, float* t, int32_t* inliers,
                                         int32_t location);
 
+/* ------------------------------------------------------------------ several GPUs of one box, batched pairs */
+/* A group owns one ctx per listed CUDA device and an enqueueing thread for each.  A batch is dealt round-robin —
+ * pair b to member (b mod G) — with no communication between the devices (independent pairs
+ * shard naturally); each member gathers its share straight from the caller's host arrays (a strided 2-D copy when
+ * the pairs are of equal size) and scatters its results into the caller's R / t / inliers.  Host buffers only
+ * (pinned memory makes the copies asynchronous); the call returns when every device has finished.  Results are
+ * those of sac_cot_register_packed on one device, bit for bit.  GPU library only. */
+typedef struct sac_cot_group sac_cot_group;
+SAC_COT_API int sac_cot_group_create(sac_cot_group** out, const int32_t* devices, int32_t n_devices);
+SAC_COT_API int sac_cot_group_destroy(sac_cot_group* group);
+SAC_COT_API int32_t sac_cot_group_size(const sac_cot_group* group);
+/* member ctx `index` (owned by the group): for sac_cot_ctx_get / per-device knobs */
+SAC_COT_API sac_cot_ctx* sac_cot_group_ctx(sac_cot_group* group, int32_t index);
+/* sac_cot_ctx_set on every member */
+SAC_COT_API int sac_cot_group_set(sac_cot_group* group, const char* name, int64_t value);
+SAC_COT_API int sac_cot_group_register_packed(sac_cot_group* group,
+                                              const float* src, const float* dst,
+                                              const int64_t* offsets, int32_t B,
+                                              const sac_cot_params* params,
+                                              float* R, float* t, int32_t* inliers);
+
 /* ------------------------------------------------------------------ one large pair, sharded */
 /* A single pair whose triangle-count work and hypothesis ranges are split over `world` ranks, one
  * process (or thread) per GPU, every rank holding the same src/dst (BASELINE.json

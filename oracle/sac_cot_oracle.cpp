@@ -702,6 +702,20 @@ int sac_cot_sharded_phase3(sac_cot_ctx* ctx, uint64_t best_key_global, float R[9
   return SAC_COT_OK;
 }
 
+// ---- device groups: GPU library only -----------------------------------------------------
+int sac_cot_group_create(sac_cot_group** out, const int32_t*, int32_t) {
+  if (out) *out = nullptr;
+  return out ? SAC_COT_E_UNSUPPORTED : SAC_COT_E_NULL;
+}
+int sac_cot_group_destroy(sac_cot_group*) { return SAC_COT_OK; }
+int32_t sac_cot_group_size(const sac_cot_group*) { return 0; }
+sac_cot_ctx* sac_cot_group_ctx(sac_cot_group*, int32_t) { return nullptr; }
+int sac_cot_group_set(sac_cot_group*, const char*, int64_t) { return SAC_COT_E_UNSUPPORTED; }
+int sac_cot_group_register_packed(sac_cot_group*, const float*, const float*, const int64_t*, int32_t,
+                                  const sac_cot_params*, float*, float*, int32_t*) {
+  return SAC_COT_E_UNSUPPORTED;
+}
+
 // ---- in-library collectives: the oracle is a single process; it has no communicator ---------
 int sac_cot_comm_unique_id(void* id_out) { return id_out ? SAC_COT_E_UNSUPPORTED : SAC_COT_E_NULL; }
 int sac_cot_ctx_comm_init(sac_cot_ctx* ctx, const void* id, int32_t, int32_t) {

@@ -66,6 +66,13 @@ SYMBOLS = {
                                          C.POINTER(Params), _f32p, _f32p, _i32p]),
     "sac_cot_register_packed": (C.c_int, [_ctxp, C.c_void_p, C.c_void_p, _i64p, C.c_int32,
                                           C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "sac_cot_group_create": (C.c_int, [C.POINTER(_ctxp), _i32p, C.c_int32]),
+    "sac_cot_group_destroy": (C.c_int, [_ctxp]),
+    "sac_cot_group_size": (C.c_int32, [_ctxp]),
+    "sac_cot_group_ctx": (_ctxp, [_ctxp, C.c_int32]),
+    "sac_cot_group_set": (C.c_int, [_ctxp, C.c_char_p, C.c_int64]),
+    "sac_cot_group_register_packed": (C.c_int, [_ctxp, C.c_void_p, C.c_void_p, _i64p, C.c_int32,
+                                                C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sac_cot_comm_unique_id": (C.c_int, [C.c_void_p]),
     "sac_cot_ctx_comm_init": (C.c_int, [_ctxp, C.c_void_p, C.c_int32, C.c_int32]),
     "sac_cot_ctx_set_comm": (C.c_int, [_ctxp, C.c_void_p, C.c_int32, C.c_int32]),

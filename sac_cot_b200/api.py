@@ -294,6 +294,71 @@ class Registrar:
         return out
 
 
+class Group:
+    """sac_cot_group: one batch over several GPUs of the box, pair b on device b mod G, no communication."""
+
+    def __init__(self, devices, lib: C.CDLL | None = None, **params):
+        self.lib = lib if lib is not None else load_library()
+        self._grp = C.c_void_p()
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+        rc = self.lib.sac_cot_group_create(C.byref(self._grp), devs.ctypes.data_as(C.POINTER(C.c_int32)), len(devs))
+        if rc != _abi.OK:
+            self._grp = C.c_void_p()
+            raise SacCotError(rc, "sac_cot_group_create", self.lib)
+        self.params = _abi.default_params(self.lib, **params)
+
+    def close(self):
+        if getattr(self, "_grp", None) is not None and self._grp:
+            self.lib.sac_cot_group_destroy(self._grp)
+            self._grp = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __len__(self):
+        return int(self.lib.sac_cot_group_size(self._grp))
+
+    def set(self, name: str, value: int):
+        rc = self.lib.sac_cot_group_set(self._grp, name.encode(), int(value))
+        if rc != _abi.OK:
+            raise SacCotError(rc, f"sac_cot_group_set({name})", self.lib)
+
+    def get(self, index: int, name: str) -> int:
+        """sac_cot_ctx_get on member `index`."""
+        ctx = self.lib.sac_cot_group_ctx(self._grp, index)
+        v = C.c_int64()
+        rc = self.lib.sac_cot_ctx_get(ctx, name.encode(), C.byref(v))
+        if rc != _abi.OK:
+            raise SacCotError(rc, f"sac_cot_ctx_get({name})", self.lib)
+        return int(v.value)
+
+    def register_packed_ptr(self, src_ptr: int, dst_ptr: int, offsets: np.ndarray, R_ptr: int, t_ptr: int, inl_ptr: int):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        rc = self.lib.sac_cot_group_register_packed(
+            self._grp, src_ptr, dst_ptr, offsets.ctypes.data_as(C.POINTER(C.c_int64)), len(offsets) - 1,
+            C.byref(self.params), R_ptr, t_ptr, inl_ptr)
+        if rc != _abi.OK:
+            raise SacCotError(rc, "sac_cot_group_register_packed", self.lib)
+
+    def register_batch(self, pairs_src, pairs_dst) -> Result:
+        B = len(pairs_src)
+        if B != len(pairs_dst):
+            raise ValueError("need as many dst as src arrays")
+        if B == 0:
+            return Result(np.zeros((0, 3, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros(0, np.int32))
+        src, dst, offsets = _pack(pairs_src, pairs_dst)
+        R = np.empty((B, 3, 3), np.float32)
+        t = np.empty((B, 3), np.float32)
+        inl = np.empty(B, np.int32)
+        self.register_packed_ptr(src.ctypes.data, dst.ctypes.data, offsets, R.ctypes.data, t.ctypes.data, inl.ctypes.data)
+        return Result(R, t, inl)
+
+
 # ---- module-level convenience on the CUDA product library ---------------------------------
 def register(src, dst, **params):
     """sac_cot_register: one pair on the process-global ctx of the CUDA library (device 0)."""

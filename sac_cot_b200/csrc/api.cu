@@ -12,9 +12,11 @@
 #include <nccl.h>  // types and enums only: the functions are resolved with dlopen/dlsym (see NcclApi)
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 using namespace saccot;
@@ -666,30 +668,65 @@ int prepare_lane(sac_cot_ctx* ctx, Lane& ln, const int32_t* Ns, int pairs, const
   return 0;
 }
 
-// Enqueues one chunk [b0,b1) on a lane.  offsets are absolute (whole call).
-int enqueue_chunk(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst, const int64_t* offsets, int b0,
-                  int b1, const sac_cot_params& prm, float* R, float* t, int32_t* inliers, bool host,
+// The pairs a call works on: pair k of the call is pair first + k * stride of the caller's arrays (stride 1 = all of
+// them, in order; stride G = the round-robin share of device `first` in a group of G).
+struct PairSel {
+  int first, stride, count;
+  int id(int k) const { return first + k * stride; }
+};
+
+// Enqueues one chunk [k0,k1) of the selection on a lane.  offsets are absolute (whole call).
+int enqueue_chunk(sac_cot_ctx* ctx, Lane& ln, const float* src, const float* dst, const int64_t* offsets, PairSel sel,
+                  int k0, int k1, const sac_cot_params& prm, float* R, float* t, int32_t* inliers, bool host,
                   ChunkDev* h_chunk) {
-  const int pairs = b1 - b0;
+  const int pairs = k1 - k0;
   std::vector<int32_t> Ns(pairs);
-  for (int b = 0; b < pairs; ++b) Ns[b] = static_cast<int32_t>(offsets[b0 + b + 1] - offsets[b0 + b]);
+  for (int k = 0; k < pairs; ++k) Ns[k] = static_cast<int32_t>(offsets[sel.id(k0 + k) + 1] - offsets[sel.id(k0 + k)]);
   const bool tensor = ctx->tri_path != 0;
   if (int rc = prepare_lane(ctx, ln, Ns.data(), pairs, prm, host, tensor, 0, 1, 0)) return rc;
   Layout& L = ln.lay;
-  const int64_t p0 = offsets[b0];
+  const int id0 = sel.id(k0);
+  const int64_t p0 = offsets[id0];
   if (host) {
-    CU_TRY(cudaMemcpyAsync(L.in_src, src + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ln.stream));
-    CU_TRY(cudaMemcpyAsync(L.in_dst, dst + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ln.stream));
+    if (sel.stride == 1) {
+      CU_TRY(cudaMemcpyAsync(L.in_src, src + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ln.stream));
+      CU_TRY(cudaMemcpyAsync(L.in_dst, dst + 3 * p0, sizeof(float) * 3 * L.sum_n, cudaMemcpyHostToDevice, ln.stream));
+    } else {
+      // the chunk's pairs lie `stride` pairs apart in the caller's arrays; equal sizes (the usual batch) make that a
+      // constant pitch: one 2-D copy per side gathers them into the chunk's contiguous input block
+      bool uniform = true;
+      const int64_t pitch = pairs > 1 ? offsets[sel.id(k0 + 1)] - p0 : 0;
+      for (int k = 0; k < pairs && uniform; ++k)
+        uniform = Ns[k] == Ns[0] && offsets[sel.id(k0 + k)] - p0 == pitch * k;
+      if (uniform) {
+        const size_t width = sizeof(float) * 3 * static_cast<size_t>(Ns[0]);
+        const size_t spitch = pairs > 1 ? sizeof(float) * 3 * static_cast<size_t>(pitch) : width;
+        CU_TRY(cudaMemcpy2DAsync(L.in_src, width, src + 3 * p0, spitch, width, pairs, cudaMemcpyHostToDevice, ln.stream));
+        CU_TRY(cudaMemcpy2DAsync(L.in_dst, width, dst + 3 * p0, spitch, width, pairs, cudaMemcpyHostToDevice, ln.stream));
+      } else {
+        for (int k = 0; k < pairs; ++k) {
+          const int64_t pk = offsets[sel.id(k0 + k)];
+          const size_t bytes = sizeof(float) * 3 * static_cast<size_t>(Ns[k]);
+          CU_TRY(cudaMemcpyAsync(L.in_src + 3 * ln.descs[k].pt_off, src + 3 * pk, bytes, cudaMemcpyHostToDevice, ln.stream));
+          CU_TRY(cudaMemcpyAsync(L.in_dst + 3 * ln.descs[k].pt_off, dst + 3 * pk, bytes, cudaMemcpyHostToDevice, ln.stream));
+        }
+      }
+    }
     if (int rc = enqueue_pipeline(ctx, ln, L.in_src, L.in_dst, L.outR, L.outT, L.outInl, 0, 1, false)) return rc;
     CU_TRY(cudaMemcpyAsync(h_chunk, L.chunk, sizeof(ChunkDev), cudaMemcpyDeviceToHost, ln.stream));
-    CU_TRY(cudaMemcpyAsync(R + 9 * static_cast<size_t>(b0), L.outR, sizeof(float) * 9 * pairs, cudaMemcpyDeviceToHost,
-                           ln.stream));
-    CU_TRY(cudaMemcpyAsync(t + 3 * static_cast<size_t>(b0), L.outT, sizeof(float) * 3 * pairs, cudaMemcpyDeviceToHost,
-                           ln.stream));
-    CU_TRY(cudaMemcpyAsync(inliers + b0, L.outInl, sizeof(int32_t) * pairs, cudaMemcpyDeviceToHost, ln.stream));
+    if (sel.stride == 1) {
+      CU_TRY(cudaMemcpyAsync(R + 9 * static_cast<size_t>(id0), L.outR, sizeof(float) * 9 * pairs, cudaMemcpyDeviceToHost, ln.stream));
+      CU_TRY(cudaMemcpyAsync(t + 3 * static_cast<size_t>(id0), L.outT, sizeof(float) * 3 * pairs, cudaMemcpyDeviceToHost, ln.stream));
+      CU_TRY(cudaMemcpyAsync(inliers + id0, L.outInl, sizeof(int32_t) * pairs, cudaMemcpyDeviceToHost, ln.stream));
+    } else {  // scatter: results of pair k go to slot first + k * stride of the caller's arrays
+      const size_t st = static_cast<size_t>(sel.stride);
+      CU_TRY(cudaMemcpy2DAsync(R + 9 * static_cast<size_t>(id0), 36 * st, L.outR, 36, 36, pairs, cudaMemcpyDeviceToHost, ln.stream));
+      CU_TRY(cudaMemcpy2DAsync(t + 3 * static_cast<size_t>(id0), 12 * st, L.outT, 12, 12, pairs, cudaMemcpyDeviceToHost, ln.stream));
+      CU_TRY(cudaMemcpy2DAsync(inliers + id0, 4 * st, L.outInl, 4, 4, pairs, cudaMemcpyDeviceToHost, ln.stream));
+    }
   } else {
-    if (int rc = enqueue_pipeline(ctx, ln, src + 3 * p0, dst + 3 * p0, R + 9 * static_cast<size_t>(b0),
-                                  t + 3 * static_cast<size_t>(b0), inliers + b0, 0, 1, false))
+    if (int rc = enqueue_pipeline(ctx, ln, src + 3 * p0, dst + 3 * p0, R + 9 * static_cast<size_t>(id0),
+                                  t + 3 * static_cast<size_t>(id0), inliers + id0, 0, 1, false))
       return rc;
   }
   return 0;
@@ -704,18 +741,12 @@ int ensure_chunk_headers(sac_cot_ctx* ctx, size_t n) {
   return 0;
 }
 
-int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_t* offsets, int32_t B,
-               const sac_cot_params* params, float* R, float* t, int32_t* inliers, int32_t location) {
-  if (!ctx || !offsets) return SAC_COT_E_NULL;
-  if (location != SAC_COT_LOC_HOST && location != SAC_COT_LOC_DEVICE) return SAC_COT_E_UNSUPPORTED;
-  if (B < 0) return SAC_COT_E_SIZE;
-  if (int rc = check_params(params)) return rc;
-  if (B > 0 && (!src || !dst || !R || !t || !inliers)) return SAC_COT_E_NULL;
-  for (int b = 0; b < B; ++b) {
-    const int64_t n = offsets[b + 1] - offsets[b];
-    if (n < 3 || n > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
-  }
+// The selected pairs of a packed batch on one ctx (arguments already validated).
+int run_selected(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_t* offsets, PairSel sel,
+                 const sac_cot_params* params, float* R, float* t, int32_t* inliers, int32_t location) {
+  const int B = sel.count;
   if (B == 0) return SAC_COT_OK;
+  if (location == SAC_COT_LOC_DEVICE && sel.stride != 1) return SAC_COT_E_UNSUPPORTED;
   CU_TRY(cudaSetDevice(ctx->device));
   if (int rc = resolve_pending(ctx, false)) return rc;
   const bool host = location == SAC_COT_LOC_HOST;
@@ -729,8 +760,8 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
       chunk = std::min(B, ctx->chunk_pairs);
     } else {
       size_t total = 0;
-      for (int b = 0; b < B; ++b)
-        total += pair_bytes_estimate(static_cast<int>(offsets[b + 1] - offsets[b]), K, params->num_edges, ctx->tri_path != 0);
+      for (int k = 0; k < B; ++k)
+        total += pair_bytes_estimate(static_cast<int>(offsets[sel.id(k) + 1] - offsets[sel.id(k)]), K, params->num_edges, ctx->tri_path != 0);
       const size_t budget = static_cast<size_t>(3) << 30;  // ~3 GB of workspace per chunk (larger chunks measured faster)
       int nchunks = static_cast<int>((total + budget - 1) / budget);
       if (nchunks < lanes && B >= 2 * lanes) nchunks = lanes;  // give every lane something to overlap
@@ -757,9 +788,9 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
     if (int rc = fork_lanes(ctx, lanes)) return rc;
     for (size_t k = 0; k < todo.size(); ++k) {
       const int c = todo[k];
-      const int b0 = c * chunk, b1 = std::min(B, b0 + chunk);
+      const int k0 = c * chunk, k1 = std::min(B, k0 + chunk);
       Lane& ln = ctx->lanes[k % lanes];
-      if (int rc = enqueue_chunk(ctx, ln, src, dst, offsets, b0, b1, *params, R, t, inliers, host,
+      if (int rc = enqueue_chunk(ctx, ln, src, dst, offsets, sel, k0, k1, *params, R, t, inliers, host,
                                  host ? ctx->h_chunks[c] : nullptr))
         return rc;
     }
@@ -790,6 +821,26 @@ int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64
   if (!todo.empty()) return SAC_COT_E_NOMEM;
   ctx->ws_valid = nchunks == 1;
   return SAC_COT_OK;
+}
+
+int check_packed_args(const void* handle, const float* src, const float* dst, const int64_t* offsets, int32_t B,
+                      const sac_cot_params* params, const float* R, const float* t, const int32_t* inliers, int32_t location) {
+  if (!handle || !offsets) return SAC_COT_E_NULL;
+  if (location != SAC_COT_LOC_HOST && location != SAC_COT_LOC_DEVICE) return SAC_COT_E_UNSUPPORTED;
+  if (B < 0) return SAC_COT_E_SIZE;
+  if (int rc = check_params(params)) return rc;
+  if (B > 0 && (!src || !dst || !R || !t || !inliers)) return SAC_COT_E_NULL;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = offsets[b + 1] - offsets[b];
+    if (n < 3 || n > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
+  }
+  return SAC_COT_OK;
+}
+
+int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_t* offsets, int32_t B,
+               const sac_cot_params* params, float* R, float* t, int32_t* inliers, int32_t location) {
+  if (int rc = check_packed_args(ctx, src, dst, offsets, B, params, R, t, inliers, location)) return rc;
+  return run_selected(ctx, src, dst, offsets, PairSel{0, 1, B}, params, R, t, inliers, location);
 }
 
 std::mutex g_mutex;
@@ -1062,6 +1113,137 @@ int sac_cot_register(const float* src, const float* dst, int32_t N, const sac_co
   }
   const int64_t offsets[2] = {0, N};
   return sac_cot_register_packed(g_ctx, src, dst, offsets, 1, params, R, t, inliers, SAC_COT_LOC_HOST);
+}
+
+// ---- device groups: one batch over several GPUs of the box, no communication ------------------
+}  // extern "C"
+
+// One worker thread per member device: enqueueing a chunk costs the host ~0.1 ms and a step of the headline batch on
+// eight GPUs lasts ~1.5 ms, so a single enqueueing thread would be the bottleneck.  Workers sleep on a condition
+// variable between calls.
+struct sac_cot_group {
+  std::vector<sac_cot_ctx*> ctxs;
+  std::vector<std::thread> workers;
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  uint64_t epoch = 0;
+  int pending = 0;
+  bool stop = false;
+  // the call in flight
+  const float* src = nullptr;
+  const float* dst = nullptr;
+  const int64_t* offsets = nullptr;
+  int32_t B = 0;
+  const sac_cot_params* params = nullptr;
+  float* R = nullptr;
+  float* t = nullptr;
+  int32_t* inliers = nullptr;
+  std::vector<int> rc;
+};
+
+namespace {
+void group_worker(sac_cot_group* g, int idx) {
+  uint64_t seen = 0;
+  const int G = static_cast<int>(g->ctxs.size());
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(g->m);
+      g->cv_go.wait(lk, [&] { return g->stop || g->epoch != seen; });
+      if (g->stop) return;
+      seen = g->epoch;
+    }
+    int rc;
+    try {
+      const int count = g->B > idx ? (g->B - idx + G - 1) / G : 0;
+      rc = run_selected(g->ctxs[idx], g->src, g->dst, g->offsets, PairSel{idx, G, count}, g->params, g->R, g->t, g->inliers,
+                        SAC_COT_LOC_HOST);
+    } catch (const std::bad_alloc&) {
+      rc = SAC_COT_E_NOMEM;
+    }
+    {
+      std::lock_guard<std::mutex> lk(g->m);
+      g->rc[idx] = rc;
+      if (--g->pending == 0) g->cv_done.notify_all();
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int sac_cot_group_destroy(sac_cot_group* g) {
+  if (!g) return SAC_COT_OK;
+  {
+    std::lock_guard<std::mutex> lk(g->m);
+    g->stop = true;
+  }
+  g->cv_go.notify_all();
+  for (std::thread& th : g->workers)
+    if (th.joinable()) th.join();
+  for (sac_cot_ctx* c : g->ctxs) sac_cot_ctx_destroy(c);
+  delete g;
+  return SAC_COT_OK;
+}
+
+int sac_cot_group_create(sac_cot_group** out, const int32_t* devices, int32_t n_devices) {
+  if (!out || !devices) return SAC_COT_E_NULL;
+  *out = nullptr;
+  if (n_devices < 1 || n_devices > 64) return SAC_COT_E_SIZE;
+  sac_cot_group* g = new (std::nothrow) sac_cot_group();
+  if (!g) return SAC_COT_E_NOMEM;
+  try {
+    for (int k = 0; k < n_devices; ++k) {
+      sac_cot_ctx* c = nullptr;
+      const int rc = sac_cot_ctx_create(&c, devices[k], nullptr);
+      if (rc) {
+        sac_cot_group_destroy(g);
+        return rc;
+      }
+      g->ctxs.push_back(c);
+    }
+    g->rc.assign(static_cast<size_t>(n_devices), 0);
+    for (int k = 0; k < n_devices; ++k) g->workers.emplace_back(group_worker, g, k);
+  } catch (...) {
+    sac_cot_group_destroy(g);
+    return SAC_COT_E_NOMEM;
+  }
+  *out = g;
+  return SAC_COT_OK;
+}
+
+int32_t sac_cot_group_size(const sac_cot_group* g) { return g ? static_cast<int32_t>(g->ctxs.size()) : 0; }
+
+sac_cot_ctx* sac_cot_group_ctx(sac_cot_group* g, int32_t index) {
+  return (g && index >= 0 && index < static_cast<int32_t>(g->ctxs.size())) ? g->ctxs[index] : nullptr;
+}
+
+int sac_cot_group_set(sac_cot_group* g, const char* name, int64_t value) {
+  if (!g || !name) return SAC_COT_E_NULL;
+  for (sac_cot_ctx* c : g->ctxs)
+    if (int rc = sac_cot_ctx_set(c, name, value)) return rc;
+  return SAC_COT_OK;
+}
+
+int sac_cot_group_register_packed(sac_cot_group* g, const float* src, const float* dst, const int64_t* offsets, int32_t B,
+                                  const sac_cot_params* params, float* R, float* t, int32_t* inliers) {
+  if (int rc = check_packed_args(g, src, dst, offsets, B, params, R, t, inliers, SAC_COT_LOC_HOST)) return rc;
+  if (B == 0) return SAC_COT_OK;
+  std::unique_lock<std::mutex> lk(g->m);
+  g->src = src;
+  g->dst = dst;
+  g->offsets = offsets;
+  g->B = B;
+  g->params = params;
+  g->R = R;
+  g->t = t;
+  g->inliers = inliers;
+  g->pending = static_cast<int>(g->ctxs.size());
+  ++g->epoch;
+  g->cv_go.notify_all();
+  g->cv_done.wait(lk, [&] { return g->pending == 0; });
+  for (int rc : g->rc)
+    if (rc) return rc;
+  return SAC_COT_OK;
 }
 
 // ---- sharded single pair ------------------------------------------------------------------

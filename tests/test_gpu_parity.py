@@ -748,3 +748,39 @@ def test_overflowing_device_call_leaves_defined_outputs_and_reports(gpu_lib):
         R1, t1, i1 = ref.register(p.src, p.dst)
         np.testing.assert_array_equal(d_R.cpu().numpy().reshape(3, 3), R1)
         assert int(d_i.item()) == i1
+
+
+# ---------------------------------------------------------------------------------------------
+# Device groups: one batch dealt round-robin over the member contexts
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sizes", [(1000,) * 7, (300, 1000, 129, 2048, 64, 777, 1500)])
+def test_group_round_robin_matches_single_ctx(gpu_lib, sizes):
+    # members may share a device: two contexts on GPU 0 exercise the strided gather / scatter (uniform sizes: one 2-D
+    # copy per side; ragged sizes: one copy per pair) on a one-GPU box; with more GPUs the members spread out
+    import torch
+    from sac_cot_b200.api import Group
+    ndev = torch.cuda.device_count()
+    pairs = [synth.make_pair(n, 0.1, 8800 + k) for k, n in enumerate(sizes)]
+    with Registrar(lib=gpu_lib) as one:
+        ref = one.register_batch([p.src for p in pairs], [p.dst for p in pairs])
+    for devices in ([0], [0, 0], [0, 0, 0], list(range(min(ndev, 4))) if ndev > 1 else [0, 0, 0, 0]):
+        with Group(devices, lib=gpu_lib) as grp:
+            assert len(grp) == len(devices)
+            grp.set("chunk_pairs", 2)
+            got = grp.register_batch([p.src for p in pairs], [p.dst for p in pairs])
+            np.testing.assert_array_equal(got.R, ref.R)
+            np.testing.assert_array_equal(got.t, ref.t)
+            np.testing.assert_array_equal(got.inliers, ref.inliers)
+            assert sum(grp.get(g, "launches") for g in range(len(devices))) > 0
+            # fewer pairs than members: some members get nothing
+            few = grp.register_batch([p.src for p in pairs[:2]], [p.dst for p in pairs[:2]])
+            np.testing.assert_array_equal(few.R, ref.R[:2])
+            np.testing.assert_array_equal(few.inliers, ref.inliers[:2])
+
+
+def test_group_rejects_bad_arguments(gpu_lib):
+    from sac_cot_b200.api import Group
+    with pytest.raises(SacCotError):
+        Group([], lib=gpu_lib)
+    with pytest.raises(SacCotError):
+        Group([99], lib=gpu_lib)
