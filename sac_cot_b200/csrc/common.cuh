@@ -167,7 +167,7 @@ int launch_key_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, Pair
                     StickyDev* d_sticky, unsigned long long key_cap, int tri_mode);
 // density (edges per node pair) from which the tensor-core triangle kernel beats the POPC kernels, and the
 // smallest pair it is worth starting for (measured on B200)
-constexpr float kTensorMinDensity = 0.05f;
+constexpr float kTensorMinDensity = 0.02f;
 constexpr int kTensorMinN = 1024;
 
 // kernels_triangles.cu — S2 triangle counts (POPC bitset path)
@@ -194,9 +194,9 @@ __host__ __device__ inline int mma_tiles_of_pair(int N) {
 }
 // CTA pairs (clusters) the tensor-core kernel runs with; cluster c walks entries c, c + n, c + 2 n, ... of the tile list
 inline int mma_clusters(int total_tiles, int sm_count) { return total_tiles < sm_count / 2 ? total_tiles : sm_count / 2; }
-// d_scratch (theta_scratch_bytes(pairs) bytes, or null): calls with at most kThetaSplitMaxPairs large pairs spread
-// the sample evaluation over many CTAs (three launches instead of one)
-constexpr int kThetaSplitMaxPairs = 4;
+// d_scratch (theta_scratch_bytes(pairs) bytes, or null): chunks of fewer pairs than the device has SMs spread the
+// sample evaluation over many CTAs (three launches instead of one)
+constexpr int kThetaSplitMaxPairs = 147;
 size_t theta_scratch_bytes(int pairs);
 int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                      const ChunkDev* d_chunk, uint32_t* d_theta, void* d_scratch, int Ke, int prune);
