@@ -63,19 +63,32 @@ enum {
 
 /* ------------------------------------------------------------------ params */
 enum { SAC_COT_SCORE_INLIER_COUNT = 0, SAC_COT_SCORE_TRUNCATED_RESIDUAL = 1 };
+/* Compatibility graph the ranking runs on:
+ *   FIRST_ORDER   A_ij  = | |s_i - s_j| - |d_i - d_j| | < tau_c                                  (S1, the default)
+ *   SECOND_ORDER  A2_ij = A_ij and C_ij >= so_min_common, where C_ij = popc(row_i(A) & row_j(A)) is the number of
+ *                 correspondences compatible with BOTH i and j — the second-order (SC^2-style) measure, (A.A) o A.
+ *                 Triangle counts, edge ranking, apex selection (S2, S3) then run on A2 instead of A; hypotheses,
+ *                 scoring and refit (S4-S7) are unchanged.  so_min_common = 0 makes A2 = A. */
+enum { SAC_COT_COMPAT_FIRST_ORDER = 0, SAC_COT_COMPAT_SECOND_ORDER = 1 };
 
 typedef struct sac_cot_params {
-  uint32_t struct_size;    /* = sizeof(sac_cot_params); ABI version check                    */
+  uint32_t struct_size;    /* = sizeof(sac_cot_params); ABI version check (see below)                */
   float    tau_compat;     /* tau_c : |len_src - len_dst| < tau_c  => compatible  (S1)        */
   float    tau_inlier;     /* tau_in: |R s + t - d|^2 < tau_in^2   => inlier      (S5)        */
   int32_t  num_edges;      /* K_e   : top-ranked edges used as triangle bases     (S3)        */
   int32_t  apex_per_edge;  /* m     : apexes per edge; K = K_e*m hypotheses       (S3)        */
   int32_t  score_mode;     /* SAC_COT_SCORE_*                                     (S5)        */
   int32_t  refit;          /* 1: fp64 Kabsch over the winner's inliers (S7); 0: return winner */
+  int32_t  compat_mode;    /* SAC_COT_COMPAT_*  (version 1 of the struct called this `reserved`, must be 0) */
+  /* ---- version 2 (struct_size 40) ---- */
+  int32_t  so_min_common;  /* SECOND_ORDER: smallest C_ij an edge of A must reach to stay in A2, 0 .. 65535 */
   int32_t  reserved;       /* must be 0                                                       */
 } sac_cot_params;
+/* struct_size versioning: both libraries accept 32 (version 1: the fields up to compat_mode, which must then be 0)
+ * and 40 (version 2).  A caller compiled against version 1 keeps working unchanged. */
+#define SAC_COT_PARAMS_SIZE_V1 32u
 
-/* Fills *p with the defaults (tau 0.1/0.1, K_e 1024, m 4, inlier count, refit on). */
+/* Fills *p with the defaults (tau 0.1/0.1, K_e 1024, m 4, inlier count, refit on, first-order graph). */
 SAC_COT_API int sac_cot_params_default(sac_cot_params* p);
 
 /* ------------------------------------------------------------------ one pair */
@@ -245,7 +258,9 @@ enum {
   SAC_COT_DBG_HYP_SCORE  = 7, /* u64[K]  packed selection key per hypothesis (0 = invalid)   */
   SAC_COT_DBG_BEST_KEY   = 8, /* u64     max of HYP_SCORE                                    */
   SAC_COT_DBG_MASK       = 9, /* u32[ceil(N/32)] inlier bits of the winning hypothesis       */
-  SAC_COT_DBG_HIST       = 10 /* u32[4096] histogram of (T_ij >> 4) over all edges           */
+  SAC_COT_DBG_HIST       = 10, /* u32[4096] histogram of (T_ij >> 4) over all edges           */
+  SAC_COT_DBG_ADJ_FIRST  = 11  /* SECOND_ORDER mode: the first-order graph A, same layout as ADJ (ADJ is then A2,
+                                  the graph every later stage ran on); FIRST_ORDER mode: identical to ADJ       */
 };
 SAC_COT_API int sac_cot_debug_get(sac_cot_ctx* ctx, int32_t pair, int32_t which,
                                   void* out, size_t cap, size_t* written);

@@ -54,7 +54,8 @@ struct PairState {
   int stride = 0;                     // 32-bit words per adjacency row
   sac_cot_params prm{};
   std::vector<float> src, dst;        // copies (sharded phases need them later)
-  std::vector<uint32_t> adj;          // N x stride
+  std::vector<uint32_t> adj;          // N x stride: the graph S2/S3 run on (A, or A2 in second-order mode)
+  std::vector<uint32_t> adj_first;    // second-order mode: the first-order graph A
   std::vector<uint32_t> t_node;       // N
   std::vector<uint64_t> t2;           // N: sum of T over evaluated incident edges (= 2 t_i if world == 1)
   std::vector<uint64_t> edge_keys;    // E (row-major order of (i,j), i<j)
@@ -476,31 +477,62 @@ void finalize(PairState& st, uint64_t best_key, float R[9], float t[3], int32_t*
 // ---------------------------------------------------------------------------------------
 // argument checks shared by every entry point
 // ---------------------------------------------------------------------------------------
+// struct_size versioning: version 1 (32 bytes) ends with compat_mode (then called `reserved`, must be 0)
 int check_params(const sac_cot_params* p) {
   if (!p) return SAC_COT_E_NULL;
-  if (p->struct_size != sizeof(sac_cot_params)) return SAC_COT_E_PARAMS;
+  if (p->struct_size != sizeof(sac_cot_params) && p->struct_size != SAC_COT_PARAMS_SIZE_V1) return SAC_COT_E_PARAMS;
   if (!(p->tau_compat > 0.0f) || !(p->tau_inlier > 0.0f)) return SAC_COT_E_PARAMS;
   if (p->num_edges < 1 || p->num_edges > SAC_COT_MAX_EDGES) return SAC_COT_E_PARAMS;
   if (p->apex_per_edge < 1 || p->apex_per_edge > SAC_COT_MAX_APEX) return SAC_COT_E_PARAMS;
   if (p->num_edges * p->apex_per_edge > SAC_COT_MAX_HYPOTHESES) return SAC_COT_E_PARAMS;
   if (p->score_mode != 0 && p->score_mode != 1) return SAC_COT_E_PARAMS;
   if (p->refit != 0 && p->refit != 1) return SAC_COT_E_PARAMS;
+  if (p->struct_size == SAC_COT_PARAMS_SIZE_V1) return p->compat_mode == 0 ? SAC_COT_OK : SAC_COT_E_PARAMS;
+  if (p->compat_mode != SAC_COT_COMPAT_FIRST_ORDER && p->compat_mode != SAC_COT_COMPAT_SECOND_ORDER) return SAC_COT_E_PARAMS;
+  if (p->so_min_common < 0 || p->so_min_common > 65535) return SAC_COT_E_PARAMS;
   if (p->reserved != 0) return SAC_COT_E_PARAMS;
   return SAC_COT_OK;
+}
+
+// the caller's struct (either version) as the current one
+sac_cot_params normalized(const sac_cot_params& in) {
+  sac_cot_params out{};
+  std::memcpy(&out, &in, std::min<size_t>(in.struct_size, sizeof(out)));
+  out.struct_size = sizeof(out);
+  return out;
 }
 
 void load_pair(PairState& st, const float* src, const float* dst, int N, const sac_cot_params& prm) {
   st.N = N;
   st.stride = stride_words_for(N);
-  st.prm = prm;
+  st.prm = normalized(prm);
   st.src.assign(src, src + static_cast<size_t>(N) * 3);
   st.dst.assign(dst, dst + static_cast<size_t>(N) * 3);
   st.rank = 0;
   st.world = 1;
 }
 
+// Second-order graph: A2_ij = A_ij and popc(row_i(A) & row_j(A)) >= so_min_common.  The counts of
+// pass 1 are exactly the per-edge triangle counts T_ij of the first-order graph (the SC^2 measure (A.A) o A).
+void second_order_graph(PairState& st) {
+  const int N = st.N, W = st.stride;
+  count_triangles(st);  // T of every edge of A (world = 1 here)
+  const uint32_t cmin = static_cast<uint32_t>(st.prm.so_min_common);
+  st.adj_first = st.adj;
+  std::vector<uint32_t> a2(static_cast<size_t>(N) * W, 0u);
+  for (uint64_t key : st.edge_keys) {
+    if (static_cast<uint32_t>(key >> 32) < cmin) continue;
+    const int i = static_cast<int>(0xFFFFu - ((key >> 16) & 0xFFFFu)), j = static_cast<int>(0xFFFFu - (key & 0xFFFFu));
+    a2[static_cast<size_t>(i) * W + (j >> 5)] |= 1u << (j & 31);
+    a2[static_cast<size_t>(j) * W + (i >> 5)] |= 1u << (i & 31);
+  }
+  st.adj.swap(a2);
+}
+
 void run_pair(PairState& st, float R[9], float t[3], int32_t* inliers) {
   build_graph(st);
+  st.adj_first.clear();
+  if (st.prm.compat_mode == SAC_COT_COMPAT_SECOND_ORDER) second_order_graph(st);
   count_triangles(st);
   top_k_desc(st.edge_keys, static_cast<size_t>(st.prm.num_edges), st.top_edges);
   select_triangles(st);
@@ -531,6 +563,8 @@ int sac_cot_params_default(sac_cot_params* p) {
   p->apex_per_edge = 4;
   p->score_mode = SAC_COT_SCORE_INLIER_COUNT;
   p->refit = 1;
+  p->compat_mode = SAC_COT_COMPAT_FIRST_ORDER;
+  p->so_min_common = 0;
   p->reserved = 0;
   return SAC_COT_OK;
 }
@@ -646,6 +680,7 @@ int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
   if (N < 3 || N > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
   if (world < 1 || rank < 0 || rank >= world) return SAC_COT_E_SIZE;
   if (int rc = check_params(params)) return rc;
+  if (normalized(*params).compat_mode != SAC_COT_COMPAT_FIRST_ORDER) return SAC_COT_E_UNSUPPORTED;  // A2 needs every rank's counts
   try {
     PairState& st = ctx->sharded;
     load_pair(st, src, dst, N, *params);
@@ -755,6 +790,12 @@ int sac_cot_debug_get(sac_cot_ctx* ctx, int32_t pair, int32_t which, void* out, 
   uint64_t scalar = 0;
   switch (which) {
     case SAC_COT_DBG_ADJ: p = st->adj.data(); bytes = st->adj.size() * 4; break;
+    case SAC_COT_DBG_ADJ_FIRST: {
+      const std::vector<uint32_t>& a = st->adj_first.empty() ? st->adj : st->adj_first;
+      p = a.data();
+      bytes = a.size() * 4;
+      break;
+    }
     case SAC_COT_DBG_T_NODE: p = st->t_node.data(); bytes = st->t_node.size() * 4; break;
     case SAC_COT_DBG_NUM_EDGES: scalar = st->edge_keys.size(); p = &scalar; bytes = 8; break;
     case SAC_COT_DBG_EDGE_KEYS: p = st->edge_keys.data(); bytes = st->edge_keys.size() * 8; break;

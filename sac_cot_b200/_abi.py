@@ -25,12 +25,15 @@ SCORE_TRUNCATED_RESIDUAL = 1
 LOC_HOST, LOC_DEVICE = 0, 1
 
 DBG_ADJ, DBG_T_NODE, DBG_NUM_EDGES, DBG_EDGE_KEYS, DBG_TOP_EDGES, DBG_TRIANGLES, DBG_HYP_RT, \
-    DBG_HYP_SCORE, DBG_BEST_KEY, DBG_MASK, DBG_HIST = range(11)
+    DBG_HYP_SCORE, DBG_BEST_KEY, DBG_MASK, DBG_HIST, DBG_ADJ_FIRST = range(12)
+COMPAT_FIRST_ORDER, COMPAT_SECOND_ORDER = 0, 1
+PARAMS_SIZE_V1 = 32
 
 DBG_DTYPES = {
     DBG_ADJ: np.uint32, DBG_T_NODE: np.uint32, DBG_NUM_EDGES: np.uint64, DBG_EDGE_KEYS: np.uint64,
     DBG_TOP_EDGES: np.uint64, DBG_TRIANGLES: np.int32, DBG_HYP_RT: np.float32,
     DBG_HYP_SCORE: np.uint64, DBG_BEST_KEY: np.uint64, DBG_MASK: np.uint32, DBG_HIST: np.uint32,
+    DBG_ADJ_FIRST: np.uint32,
 }
 
 
@@ -44,6 +47,8 @@ class Params(C.Structure):
         ("apex_per_edge", C.c_int32),
         ("score_mode", C.c_int32),
         ("refit", C.c_int32),
+        ("compat_mode", C.c_int32),     # version 1 of the struct (32 bytes) ends here
+        ("so_min_common", C.c_int32),
         ("reserved", C.c_int32),
     ]
 

@@ -60,6 +60,12 @@ struct Layout {
   float* soa = nullptr;
   uint32_t* adj = nullptr;
   uint32_t* panel = nullptr;   // K-panel copy of the adjacency (tensor-core triangle path only)
+  // second-order compatibility mode: A2 (+ its K-panel copy) and the saved [state | chunk] of the first pass
+  uint32_t* adj2 = nullptr;
+  uint32_t* panel2 = nullptr;
+  unsigned char* pass1 = nullptr;
+  size_t pass1_bytes = 0, adj_bytes = 0, panel_bytes = 0;
+  uint32_t* adj_rank = nullptr;  // the graph S2/S3 ran on: adj, or adj2 in second-order mode
   uint32_t* theta = nullptr;   // per-pair pruning threshold (tensor-core triangle path only)
   void* theta_ws = nullptr;    // scratch of the multi-CTA threshold kernels (calls with very few pairs)
   uint2* tile_tab = nullptr;   // tensor-core path: (pair, row block << 16 | column block) per tile
@@ -91,9 +97,9 @@ unsigned long long key_guess_for(int N) {
   return g < P ? g : P;
 }
 
-size_t pair_bytes_estimate(int N, int K, int Ke, bool tensor_path) {
+size_t pair_bytes_estimate(int N, int K, int Ke, bool tensor_path, bool second_order) {
   const size_t npad = align_up(static_cast<size_t>(N), 128);
-  return npad * (npad / 32) * 4 * (tensor_path ? 2 : 1) + key_guess_for(N) * 8 + npad * (6 * 4 + 8 + 24) + static_cast<size_t>(K) * (12 + 48 + 8) +
+  return npad * (npad / 32) * 4 * (tensor_path ? 2 : 1) * (second_order ? 2 : 1) + key_guess_for(N) * 8 + npad * (6 * 4 + 8 + 24) + static_cast<size_t>(K) * (12 + 48 + 8) +
          static_cast<size_t>(Ke) * 16 + static_cast<size_t>(kTieCap) * 8 + kHistBins * 4 + 4096;
 }
 
@@ -243,17 +249,28 @@ struct sac_cot_ctx {
 
 namespace {
 
+// struct_size versioning: version 1 (32 bytes) ends with compat_mode (then called `reserved`, must be 0)
 int check_params(const sac_cot_params* p) {
   if (!p) return SAC_COT_E_NULL;
-  if (p->struct_size != sizeof(sac_cot_params)) return SAC_COT_E_PARAMS;
+  if (p->struct_size != sizeof(sac_cot_params) && p->struct_size != SAC_COT_PARAMS_SIZE_V1) return SAC_COT_E_PARAMS;
   if (!(p->tau_compat > 0.0f) || !(p->tau_inlier > 0.0f)) return SAC_COT_E_PARAMS;
   if (p->num_edges < 1 || p->num_edges > SAC_COT_MAX_EDGES) return SAC_COT_E_PARAMS;
   if (p->apex_per_edge < 1 || p->apex_per_edge > SAC_COT_MAX_APEX) return SAC_COT_E_PARAMS;
   if (p->num_edges * p->apex_per_edge > SAC_COT_MAX_HYPOTHESES) return SAC_COT_E_PARAMS;
   if (p->score_mode != 0 && p->score_mode != 1) return SAC_COT_E_PARAMS;
   if (p->refit != 0 && p->refit != 1) return SAC_COT_E_PARAMS;
+  if (p->struct_size == SAC_COT_PARAMS_SIZE_V1) return p->compat_mode == 0 ? SAC_COT_OK : SAC_COT_E_PARAMS;
+  if (p->compat_mode != SAC_COT_COMPAT_FIRST_ORDER && p->compat_mode != SAC_COT_COMPAT_SECOND_ORDER) return SAC_COT_E_PARAMS;
+  if (p->so_min_common < 0 || p->so_min_common > 65535) return SAC_COT_E_PARAMS;
   if (p->reserved != 0) return SAC_COT_E_PARAMS;
   return SAC_COT_OK;
+}
+// the caller's (validated) struct of either version as the current one
+sac_cot_params normalized(const sac_cot_params* in) {
+  sac_cot_params out{};
+  std::memcpy(&out, in, std::min<size_t>(in->struct_size, sizeof(out)));
+  out.struct_size = sizeof(out);
+  return out;
 }
 
 // Builds the descriptors and the arena layout for pairs with the given sizes.
@@ -313,6 +330,7 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   // zero region first
   const size_t o_state = take(sizeof(PairDev) * pairs);
   const size_t o_chunk = take(sizeof(ChunkDev));
+  L.pass1_bytes = off;  // [state | chunk]: what the second-order mode saves of its first pass
   const size_t o_hist = take(sizeof(uint32_t) * kHistBins * pairs);
   const size_t o_t2 = take(sizeof(unsigned long long) * node);
   L.unit_pitch = static_cast<int>(unit_count(static_cast<unsigned int>(L.max_nblk)));
@@ -325,6 +343,12 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_soa = take(sizeof(float) * soa);
   const size_t o_adj = take(sizeof(uint32_t) * adj);
   const size_t o_panel = tensor_path ? take(sizeof(uint32_t) * panel) : 0;
+  const bool so = prm.compat_mode == SAC_COT_COMPAT_SECOND_ORDER;
+  L.adj_bytes = sizeof(uint32_t) * adj;
+  L.panel_bytes = tensor_path ? sizeof(uint32_t) * panel : 0;
+  const size_t o_adj2 = so ? take(L.adj_bytes) : 0;
+  const size_t o_panel2 = so && tensor_path ? take(L.panel_bytes) : 0;
+  const size_t o_pass1 = so ? take(L.pass1_bytes) : 0;
   const size_t o_theta = tensor_path ? take(sizeof(uint32_t) * pairs) : 0;
   const size_t theta_ws_bytes = tensor_path ? theta_scratch_bytes(pairs) : 0;
   const size_t o_theta_ws = theta_ws_bytes ? take(theta_ws_bytes) : 0;
@@ -358,6 +382,9 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.soa = reinterpret_cast<float*>(o_soa);
   L.adj = reinterpret_cast<uint32_t*>(o_adj);
   L.panel = tensor_path ? reinterpret_cast<uint32_t*>(o_panel) : nullptr;
+  L.adj2 = so ? reinterpret_cast<uint32_t*>(o_adj2) : nullptr;
+  L.panel2 = so && tensor_path ? reinterpret_cast<uint32_t*>(o_panel2) : nullptr;
+  L.pass1 = so ? reinterpret_cast<unsigned char*>(o_pass1) : nullptr;
   L.theta = tensor_path ? reinterpret_cast<uint32_t*>(o_theta) : nullptr;
   L.theta_ws = theta_ws_bytes ? reinterpret_cast<void*>(o_theta_ws + 1) : nullptr;  // +1: offset 0 must not read as "absent"
   L.tile_tab = tensor_path ? reinterpret_cast<uint2*>(o_tiles) : nullptr;
@@ -395,6 +422,11 @@ void bind(Layout& L, unsigned char* base, bool has_input, bool tensor_path) {
   L.soa = rebase(L.soa, base);
   L.adj = rebase(L.adj, base);
   L.panel = rebase(L.panel, base, tensor_path);
+  const bool so = L.pass1 != nullptr;
+  L.adj2 = rebase(L.adj2, base, so);
+  L.panel2 = rebase(L.panel2, base, so && tensor_path);
+  L.pass1 = rebase(L.pass1, base, so);
+  L.adj_rank = so ? L.adj2 : L.adj;
   L.theta = rebase(L.theta, base, tensor_path);
   L.theta_ws = L.theta_ws ? static_cast<void*>(base + (reinterpret_cast<size_t>(L.theta_ws) - 1)) : nullptr;
   L.tile_tab = rebase(L.tile_tab, base, tensor_path);
@@ -529,23 +561,51 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.panel, L.ucount, L.unit_pitch, prm.tau_compat));
   mark(ST_GRAPH);
   KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world));
-  KL_TRY(launch_key_scan(lc, L.desc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap, tri_mode));
+  KL_TRY(launch_key_scan(lc, L.desc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap, tri_mode, nullptr));
   mark(ST_SCAN);
+  const uint32_t* adj_use = L.adj;
+  const uint32_t* panel_use = L.panel;
+  if (L.adj2 != nullptr) {
+    // ---- second-order compatibility: a first counting pass over A leaves C_ij = T_ij(A) of every edge that reaches
+    //      so_min_common in the key list (the tensor-core kernel's pruning threshold IS that cut; the POPC kernels
+    //      keep every key and the scatter filters); the list becomes A2 and everything below runs on A2 ----
+    const uint32_t cmin = static_cast<uint32_t>(prm.so_min_common);
+    if (tri_mode != 0) {
+      KL_TRY(launch_fill_u32(lc, L.theta, cmin | 0x80000000u, L.pairs));  // bit 31: fixed, never raised
+      KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, L.adj, L.panel, L.state, L.chunk, ln.keys, L.theta,
+                                  L.hist, L.t2, L.Ke, 0, ctx->tri_dbg));
+    }
+    if (tri_mode != 1)
+      KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ln.keys, L.ubase,
+                              L.unit_pitch, L.hist, L.t2, rank, world));
+    CU_TRY(cudaMemcpyAsync(L.pass1, L.state, L.pass1_bytes, cudaMemcpyDeviceToDevice, ln.stream));
+    CU_TRY(cudaMemsetAsync(L.state, 0, L.zero_bytes, ln.stream));
+    CU_TRY(cudaMemsetAsync(L.adj2, 0, L.adj_bytes, ln.stream));
+    if (L.panel2) CU_TRY(cudaMemsetAsync(L.panel2, 0, L.panel_bytes, ln.stream));
+    const PairDev* state1 = reinterpret_cast<const PairDev*>(L.pass1);
+    const ChunkDev* chunk1 = reinterpret_cast<const ChunkDev*>(L.pass1 + (reinterpret_cast<unsigned char*>(L.chunk) - reinterpret_cast<unsigned char*>(L.state)));
+    KL_TRY(launch_second_order_scatter(lc, L.desc, L.pairs, state1, chunk1, ln.keys, cmin, L.adj2, L.panel2, L.ucount, L.unit_pitch));
+    KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world));
+    KL_TRY(launch_key_scan(lc, L.desc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap, tri_mode, chunk1));
+    adj_use = L.adj2;
+    panel_use = L.panel2;
+    mark(ST_GRAPH);  // the first pass and the rebuild count as graph construction
+  }
   if (tri_mode != 0) {
-    KL_TRY(launch_tri_theta(lc, L.desc, L.pairs, L.max_npad, L.adj, L.chunk, L.theta, L.theta_ws, L.Ke, ctx->tri_prune));
+    KL_TRY(launch_tri_theta(lc, L.desc, L.pairs, L.max_npad, adj_use, L.chunk, L.theta, L.theta_ws, L.Ke, ctx->tri_prune));
     mark(ST_THETA);
-    KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, L.adj, L.panel, L.state, L.chunk, ln.keys, L.theta,
+    KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, adj_use, panel_use, L.state, L.chunk, ln.keys, L.theta,
                                 L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg));
   }
   if (tri_mode != 1)
-    KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, L.adj, L.state, L.chunk, ln.keys, L.ubase,
+    KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, adj_use, L.state, L.chunk, ln.keys, L.ubase,
                             L.unit_pitch, L.hist, L.t2, rank, world));
   mark(ST_TRIANGLES);
   KL_TRY(launch_select_edges(lc, L.pairs, L.state, L.chunk, ln.keys, L.hist, L.sel, L.tie, L.top, L.Ke));
   mark(ST_SELECT);
   if (stop_after_edges) return 0;
   const float tau2 = prm.tau_inlier * prm.tau_inlier;
-  KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path));
+  KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.max_npad, adj_use, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path));
   mark(ST_APEX);
   KL_TRY(launch_kabsch(lc, L.desc, L.pairs, L.soa, L.tri, L.rt, L.K));
   mark(ST_KABSCH);
@@ -616,7 +676,7 @@ void interleave_tile_runs(std::vector<uint2>& tab, std::vector<uint2>& scratch, 
 int prepare_lane(sac_cot_ctx* ctx, Lane& ln, const int32_t* Ns, int pairs, const sac_cot_params& prm, bool host,
                  bool tensor, int rank, int world, int xworld) {
   const int sig[8] = {pairs, prm.num_edges, prm.apex_per_edge, (host ? 1 : 0) | (tensor ? 2 : 0) | (ctx->tile_runs ? 4 : 0),
-                      rank, world, xworld, 0};
+                      rank, world, xworld, prm.compat_mode};
   if (ln.arena && !std::memcmp(sig, ln.plan_sig, sizeof(sig)) && ln.plan_Ns.size() == static_cast<size_t>(pairs) &&
       std::equal(Ns, Ns + pairs, ln.plan_Ns.begin()))
     return 0;
@@ -761,7 +821,8 @@ int run_selected(sac_cot_ctx* ctx, const float* src, const float* dst, const int
     } else {
       size_t total = 0;
       for (int k = 0; k < B; ++k)
-        total += pair_bytes_estimate(static_cast<int>(offsets[sel.id(k) + 1] - offsets[sel.id(k)]), K, params->num_edges, ctx->tri_path != 0);
+        total += pair_bytes_estimate(static_cast<int>(offsets[sel.id(k) + 1] - offsets[sel.id(k)]), K, params->num_edges, ctx->tri_path != 0,
+                                     params->compat_mode == SAC_COT_COMPAT_SECOND_ORDER);
       const size_t budget = static_cast<size_t>(3) << 30;  // ~3 GB of workspace per chunk (larger chunks measured faster)
       int nchunks = static_cast<int>((total + budget - 1) / budget);
       if (nchunks < lanes && B >= 2 * lanes) nchunks = lanes;  // give every lane something to overlap
@@ -840,7 +901,8 @@ int check_packed_args(const void* handle, const float* src, const float* dst, co
 int run_packed(sac_cot_ctx* ctx, const float* src, const float* dst, const int64_t* offsets, int32_t B,
                const sac_cot_params* params, float* R, float* t, int32_t* inliers, int32_t location) {
   if (int rc = check_packed_args(ctx, src, dst, offsets, B, params, R, t, inliers, location)) return rc;
-  return run_selected(ctx, src, dst, offsets, PairSel{0, 1, B}, params, R, t, inliers, location);
+  const sac_cot_params prm = normalized(params);
+  return run_selected(ctx, src, dst, offsets, PairSel{0, 1, B}, &prm, R, t, inliers, location);
 }
 
 std::mutex g_mutex;
@@ -862,6 +924,8 @@ int sac_cot_params_default(sac_cot_params* p) {
   p->apex_per_edge = 4;
   p->score_mode = SAC_COT_SCORE_INLIER_COUNT;
   p->refit = 1;
+  p->compat_mode = SAC_COT_COMPAT_FIRST_ORDER;
+  p->so_min_common = 0;
   p->reserved = 0;
   return SAC_COT_OK;
 }
@@ -1135,6 +1199,7 @@ struct sac_cot_group {
   const int64_t* offsets = nullptr;
   int32_t B = 0;
   const sac_cot_params* params = nullptr;
+  sac_cot_params prm{};  // the caller's params, normalised to the current struct version
   float* R = nullptr;
   float* t = nullptr;
   int32_t* inliers = nullptr;
@@ -1233,7 +1298,8 @@ int sac_cot_group_register_packed(sac_cot_group* g, const float* src, const floa
   g->dst = dst;
   g->offsets = offsets;
   g->B = B;
-  g->params = params;
+  g->prm = normalized(params);
+  g->params = &g->prm;
   g->R = R;
   g->t = t;
   g->inliers = inliers;
@@ -1277,6 +1343,9 @@ int run_sharded(sac_cot_ctx* ctx, const float* src, const float* dst, int32_t N,
   if (location != SAC_COT_LOC_HOST && location != SAC_COT_LOC_DEVICE) return SAC_COT_E_UNSUPPORTED;
   if (N < 3 || N > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
   if (int rc = check_params(params)) return rc;
+  const sac_cot_params prm_n = normalized(params);
+  params = &prm_n;
+  if (params->compat_mode != SAC_COT_COMPAT_FIRST_ORDER) return SAC_COT_E_UNSUPPORTED;  // A2 would need every rank's counts
   NcclApi* nc = nccl_api();
   if (!ctx->comm || ctx->comm_world < 1 || !nc) return SAC_COT_E_COMM;
   CU_TRY(cudaSetDevice(ctx->device));
@@ -1427,6 +1496,9 @@ int sac_cot_sharded_phase1(sac_cot_ctx* ctx, const float* src, const float* dst,
   if (N < 3 || N > SAC_COT_MAX_N) return SAC_COT_E_SIZE;
   if (world < 1 || rank < 0 || rank >= world) return SAC_COT_E_SIZE;
   if (int rc = check_params(params)) return rc;
+  const sac_cot_params prm_n = normalized(params);
+  params = &prm_n;
+  if (params->compat_mode != SAC_COT_COMPAT_FIRST_ORDER) return SAC_COT_E_UNSUPPORTED;  // A2 would need every rank's counts
   CU_TRY(cudaSetDevice(ctx->device));
   if (int rc = resolve_pending(ctx, false)) return rc;
   ctx->sh_valid = false;
@@ -1536,7 +1608,8 @@ int sac_cot_debug_get(sac_cot_ctx* ctx, int32_t pair, int32_t which, void* out, 
   uint64_t scalar = 0;
   std::vector<uint32_t> tmp32;
   switch (which) {
-    case SAC_COT_DBG_ADJ: dsrc = L.adj + d.adj_off; bytes = static_cast<size_t>(d.N) * d.stride * 4; break;
+    case SAC_COT_DBG_ADJ: dsrc = L.adj_rank + d.adj_off; bytes = static_cast<size_t>(d.N) * d.stride * 4; break;
+    case SAC_COT_DBG_ADJ_FIRST: dsrc = L.adj + d.adj_off; bytes = static_cast<size_t>(d.N) * d.stride * 4; break;
     case SAC_COT_DBG_T_NODE: bytes = static_cast<size_t>(d.N) * 4; break;
     case SAC_COT_DBG_NUM_EDGES: scalar = st.num_edges; bytes = 8; break;
     case SAC_COT_DBG_EDGE_KEYS: dsrc = ln.keys + st.key_base; bytes = static_cast<size_t>(st.key_count) * 8; break;

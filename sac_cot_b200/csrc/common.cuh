@@ -163,8 +163,14 @@ int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max
 int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state,
                      const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world);
 // tri_mode: 0 = POPC kernels, 1 = tensor-core kernel, 2 = decided here from the chunk's edge density
+// d_prev (or null): chunk header of an earlier pass over the same chunk whose overflow carries over
 int launch_key_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state, ChunkDev* d_chunk,
-                    StickyDev* d_sticky, unsigned long long key_cap, int tri_mode);
+                    StickyDev* d_sticky, unsigned long long key_cap, int tri_mode, const ChunkDev* d_prev);
+// second-order compatibility: key list of the first pass -> A2 (+ its K-panel copy) and A2's per-unit edge counts
+int launch_second_order_scatter(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const PairDev* d_state1,
+                                const ChunkDev* d_chunk1, const unsigned long long* d_keys, uint32_t cmin,
+                                uint32_t* d_adj2, uint32_t* d_panel2, uint32_t* d_ucount, int unit_pitch);
+int launch_fill_u32(const LaunchCtx& lc, uint32_t* d_p, uint32_t v, int n);
 // density (edges per node pair) from which the tensor-core triangle kernel beats the POPC kernels, and the
 // smallest pair it is worth starting for (measured on B200)
 constexpr float kTensorMinDensity = 0.02f;

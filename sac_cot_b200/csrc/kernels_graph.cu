@@ -378,7 +378,7 @@ int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, Pai
 __global__ void __launch_bounds__(1024) key_scan_kernel(const PairDesc* __restrict__ descs, int pairs,
                                                         PairDev* __restrict__ state, ChunkDev* __restrict__ chunk,
                                                         StickyDev* __restrict__ sticky, unsigned long long key_cap,
-                                                        int tri_mode) {
+                                                        int tri_mode, const ChunkDev* __restrict__ prev) {
   __shared__ unsigned long long part[1024];
   __shared__ unsigned long long carry;
   __shared__ unsigned long long node_pairs;  // sum of N (N - 1) / 2 over the chunk
@@ -435,6 +435,11 @@ __global__ void __launch_bounds__(1024) key_scan_kernel(const PairDesc* __restri
       atomicMax(&sticky->max_total_edges, carry);
       atomicAdd(&sticky->overflow_count, 1u);
     }
+    // second pass of the second-order mode: an overflow of the first pass (already recorded) voids this one too
+    if (prev && prev->overflow) {
+      chunk->overflow = 1u;
+      chunk->total_edges = prev->total_edges > carry ? prev->total_edges : carry;
+    }
   }
   __syncthreads();
   // the tensor-core kernel appends only the keys that pass its pruning threshold and counts them itself
@@ -443,8 +448,64 @@ __global__ void __launch_bounds__(1024) key_scan_kernel(const PairDesc* __restri
 }
 
 int launch_key_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state, ChunkDev* d_chunk,
-                    StickyDev* d_sticky, unsigned long long key_cap, int tri_mode) {
-  key_scan_kernel<<<1, 1024, 0, lc.stream>>>(d_desc, pairs, d_state, d_chunk, d_sticky, key_cap, tri_mode);
+                    StickyDev* d_sticky, unsigned long long key_cap, int tri_mode, const ChunkDev* d_prev) {
+  key_scan_kernel<<<1, 1024, 0, lc.stream>>>(d_desc, pairs, d_state, d_chunk, d_sticky, key_cap, tri_mode, d_prev);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+// ------------------------------------------------------------------------------------------
+// Second-order compatibility: A2_ij = A_ij and C_ij >= cmin with C_ij = popc(row_i(A) & row_j(A)),
+// which is exactly the per-edge count T_ij the triangle kernels leave in the key list of a first pass over A.
+// This kernel turns that key list into A2 (both orientations, plus the K-panel copy the tensor-core kernel reads)
+// and into the per-unit edge counts of A2 the second pass starts from.  Bits are set with atomicOr: the result does
+// not depend on the (unordered) key list.  adj2 / panel2 / ucount arrive zeroed.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) second_order_scatter_kernel(
+    const PairDesc* __restrict__ descs, const PairDev* __restrict__ state1, const ChunkDev* __restrict__ chunk1,
+    const unsigned long long* __restrict__ keys, uint32_t cmin, uint32_t* __restrict__ adj2, uint32_t* __restrict__ panel2,
+    uint32_t* __restrict__ ucount, int unit_pitch) {
+  if (chunk1->overflow) return;
+  const int pair = blockIdx.y;
+  const PairDesc d = descs[pair];
+  const unsigned long long n = state1[pair].key_count;
+  const unsigned long long* kp = keys + state1[pair].key_base;
+  uint32_t* a2 = adj2 + d.adj_off;
+  uint32_t* p2 = panel2 ? panel2 + d.panel_off : nullptr;
+  uint32_t* uc = ucount + static_cast<size_t>(pair) * unit_pitch;
+  for (unsigned long long idx = static_cast<unsigned long long>(blockIdx.x) * 256 + threadIdx.x; idx < n;
+       idx += static_cast<unsigned long long>(gridDim.x) * 256) {
+    const unsigned long long key = kp[idx];
+    if (static_cast<uint32_t>(key >> 32) < cmin) continue;
+    const unsigned int i = 0xFFFFu - static_cast<unsigned int>((key >> 16) & 0xFFFFu);
+    const unsigned int j = 0xFFFFu - static_cast<unsigned int>(key & 0xFFFFu);
+    atomicOr(&a2[static_cast<size_t>(i) * d.stride + (j >> 5)], 1u << (j & 31));
+    atomicOr(&a2[static_cast<size_t>(j) * d.stride + (i >> 5)], 1u << (i & 31));
+    if (p2) {  // panel p = columns [256 p, 256 p + 256): [Npad rows][8 words]
+      atomicOr(&p2[(static_cast<size_t>(j >> 8) * d.Npad + i) * 8 + ((j & 255u) >> 5)], 1u << (j & 31));
+      atomicOr(&p2[(static_cast<size_t>(i >> 8) * d.Npad + j) * 8 + ((i & 255u) >> 5)], 1u << (i & 31));
+    }
+    atomicAdd(&uc[unit_offset(j >> 7) + (i >> 8)], 1u);  // unit = 128 columns x 256 rows, i < j
+  }
+}
+
+int launch_second_order_scatter(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const PairDev* d_state1,
+                                const ChunkDev* d_chunk1, const unsigned long long* d_keys, uint32_t cmin,
+                                uint32_t* d_adj2, uint32_t* d_panel2, uint32_t* d_ucount, int unit_pitch) {
+  int gx = (8 * lc.sm_count + pairs - 1) / pairs;
+  if (gx < 8) gx = 8;
+  second_order_scatter_kernel<<<dim3(gx, pairs), 256, 0, lc.stream>>>(d_desc, d_state1, d_chunk1, d_keys, cmin, d_adj2,
+                                                                      d_panel2, d_ucount, unit_pitch);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint32_t v, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) p[k] = v;
+}
+int launch_fill_u32(const LaunchCtx& lc, uint32_t* d_p, uint32_t v, int n) {
+  fill_u32_kernel<<<(n + 255) / 256, 256, 0, lc.stream>>>(d_p, v, n);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }

@@ -461,12 +461,12 @@ int launch_score(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max
   const int span = h_end - h_begin;
   if (span <= 0) return 0;
   const int hblocks = (span + kScoreThreads * kScoreHyp - 1) / (kScoreThreads * kScoreHyp);
-  // Few CTAs per SM (every CTA lasts equally long: with 3.5 per SM the SMs that got 4 decide the time) or fewer
-  // CTAs than SMs: split the correspondences as well, aiming at >= 8 CTAs per SM, at least 2 slabs per range.
+  // fewer CTAs than SMs (the single-pair calls): split the correspondences as well, at least 2 slabs per range.
+  // (Splitting merely to even out 3-4 CTAs per SM was measured slower: 334 -> 356 us for 32 pairs.)
   int nsplit = 1;
   const int slabs = (max_n + kScoreSlab - 1) / kScoreSlab;
-  if (hblocks * pairs < 8 * lc.sm_count && slabs >= 8) {
-    nsplit = std::min((8 * lc.sm_count + hblocks * pairs - 1) / (hblocks * pairs), slabs / 2);
+  if (hblocks * pairs < lc.sm_count && slabs >= 8) {
+    nsplit = std::min((2 * lc.sm_count + hblocks * pairs - 1) / (hblocks * pairs), slabs / 2);
     if (nsplit < 2) nsplit = 1;
   }
   if (nsplit > 1) {

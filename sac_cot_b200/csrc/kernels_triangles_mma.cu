@@ -1189,7 +1189,11 @@ size_t theta_scratch_bytes(int pairs) { return pairs <= kThetaSplitMaxPairs ? si
 
 int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                      const ChunkDev* d_chunk, uint32_t* d_theta, void* d_scratch, int Ke, int prune) {
-  if (d_scratch && pairs <= kThetaSplitMaxPairs && max_npad / 32 > 2 * kThetaSplitW) {
+  // measured (us per step): 1 pair N=50000 1102 -> 379; 43-pair chunks N=10000 992 -> 778; 32 pairs N=5000 138 -> 128;
+  // but 86-pair chunks N=5000 290 -> 423: many pairs of moderate size are better off with one CTA each
+  const bool split = d_scratch && pairs <= kThetaSplitMaxPairs && max_npad / 32 > 2 * kThetaSplitW &&
+                     (pairs <= 32 || max_npad > 8192);
+  if (split) {
     ThetaScratch* sc = static_cast<ThetaScratch*>(d_scratch);
     tri_theta_sample_kernel<<<pairs, 1024, static_cast<size_t>(max_npad), lc.stream>>>(d_desc, d_adj, d_chunk, sc, prune);
     cudaError_t e = cudaGetLastError();

@@ -794,3 +794,112 @@ def test_group_rejects_bad_arguments(gpu_lib):
         Group([], lib=gpu_lib)
     with pytest.raises(SacCotError):
         Group([99], lib=gpu_lib)
+
+
+# ---------------------------------------------------------------------------------------------
+# Tensor-native front (sac_cot_b200.torch_api): device and stream inferred from the inputs
+# ---------------------------------------------------------------------------------------------
+def test_torch_api_matches_registrar(gpu_lib):
+    import torch
+    from sac_cot_b200 import torch_api
+    pairs = [synth.make_pair(1500, 0.1, 8900 + k) for k in range(4)]
+    with Registrar(lib=gpu_lib) as one:
+        ref = one.register_batch([p.src for p in pairs], [p.dst for p in pairs])
+    dev = torch.device("cuda", 0)
+    src = torch.from_numpy(np.stack([p.src for p in pairs])).to(dev)
+    dst = torch.from_numpy(np.stack([p.dst for p in pairs])).to(dev)
+    try:
+        # (B, N, 3) CUDA tensors on a side stream: enqueue only, results on the same device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            R, t, inl = torch_api.register(src, dst)
+            assert R.is_cuda and R.shape == (4, 3, 3) and inl.dtype == torch.int32
+            side.synchronize()
+            assert torch_api.last_status(src) == 0
+        np.testing.assert_array_equal(R.cpu().numpy(), ref.R)
+        np.testing.assert_array_equal(t.cpu().numpy(), ref.t)
+        np.testing.assert_array_equal(inl.cpu().numpy(), ref.inliers)
+        # one pair, ragged list, CPU tensors
+        R0, t0, i0 = torch_api.register(src[0], dst[0])
+        torch.cuda.synchronize(dev)
+        np.testing.assert_array_equal(R0.cpu().numpy(), ref.R[0])
+        assert int(i0) == int(ref.inliers[0])
+        Rr, tr, ir = torch_api.register([src[0], src[1][:1000]], [dst[0], dst[1][:1000]])
+        torch.cuda.synchronize(dev)
+        np.testing.assert_array_equal(Rr[0].cpu().numpy(), ref.R[0])
+        Rc, tc, ic = torch_api.register(src.cpu(), dst.cpu())
+        assert not Rc.is_cuda
+        np.testing.assert_array_equal(Rc.numpy(), ref.R)
+        np.testing.assert_array_equal(ic.numpy(), ref.inliers)
+        with pytest.raises(ValueError):
+            torch_api.register(src, dst[:, :100])
+    finally:
+        torch_api.release_contexts()
+
+
+# ---------------------------------------------------------------------------------------------
+# Second-order compatibility (params.compat_mode = SAC_COT_COMPAT_SECOND_ORDER)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", [0, 1, 2])
+@pytest.mark.parametrize("N,ratio,cmin", [(64, 0.3, 3), (500, 0.2, 0), (1000, 0.1, 12), (2048, 0.1, 30), (5000, 0.05, 60),
+                                          (700, 0.1, 60000)])
+def test_second_order_mode_matches_oracle(gpu, oracle, path, N, ratio, cmin):
+    gpu.set("triangle_path", path)
+    p = synth.make_pair(N, ratio, 9000 + N)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier, num_edges=256, apex_per_edge=4,
+                   compat_mode=_abi.COMPAT_SECOND_ORDER, so_min_common=cmin)
+    out_g = gpu.register(p.src, p.dst)
+    out_o = oracle.register(p.src, p.dst)
+    np.testing.assert_array_equal(gpu.debug(0, _abi.DBG_ADJ_FIRST), oracle.debug(0, _abi.DBG_ADJ_FIRST))
+    np.testing.assert_array_equal(gpu.debug(0, _abi.DBG_ADJ), oracle.debug(0, _abi.DBG_ADJ))   # A2
+    if gpu.get("triangle_path_used") == 1:
+        compare_pruned(gpu, oracle)
+    else:
+        compare_stages(gpu, oracle)
+    compare_pose(*out_g, *out_o)
+    if cmin == 0:
+        np.testing.assert_array_equal(gpu.debug(0, _abi.DBG_ADJ), gpu.debug(0, _abi.DBG_ADJ_FIRST))
+
+
+def test_second_order_mode_batch_and_pool_growth(gpu_lib, oracle):
+    sizes = (300, 1000, 129, 2048, 777)
+    pairs = [synth.make_pair(n, 0.15, 9100 + k) for k, n in enumerate(sizes)]
+    with Registrar(lib=gpu_lib, compat_mode=_abi.COMPAT_SECOND_ORDER, so_min_common=8, tau_compat=0.6) as g:
+        g.set("keep_debug", 1)
+        set_params(oracle, compat_mode=_abi.COMPAT_SECOND_ORDER, so_min_common=8, tau_compat=0.6, tau_inlier=0.1)
+        rg = g.register_batch([p.src for p in pairs], [p.dst for p in pairs])   # tau 0.6 in a 3 m box: dense, the pool grows
+        ro = oracle.register_batch([p.src for p in pairs], [p.dst for p in pairs])
+        assert g.get("retries") >= 1
+        for b in range(len(pairs)):
+            np.testing.assert_array_equal(g.debug(b, _abi.DBG_ADJ), oracle.debug(b, _abi.DBG_ADJ))
+            np.testing.assert_array_equal(g.debug(b, _abi.DBG_T_NODE), oracle.debug(b, _abi.DBG_T_NODE))
+            np.testing.assert_array_equal(g.debug(b, _abi.DBG_TOP_EDGES), oracle.debug(b, _abi.DBG_TOP_EDGES))
+            np.testing.assert_array_equal(g.debug(b, _abi.DBG_HYP_SCORE), oracle.debug(b, _abi.DBG_HYP_SCORE))
+            compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
+        # chunked / multi-lane execution gives the same bits
+        g.set("keep_debug", 0)
+        g.set("chunk_pairs", 2)
+        rc = g.register_batch([p.src for p in pairs], [p.dst for p in pairs])
+        np.testing.assert_array_equal(rc.R, rg.R)
+        np.testing.assert_array_equal(rc.inliers, rg.inliers)
+
+
+def test_second_order_mode_rejected_where_unsupported_and_v1_struct_accepted(gpu_lib):
+    p = synth.make_pair(600, 0.1, 9200)
+    with Registrar(lib=gpu_lib, compat_mode=_abi.COMPAT_SECOND_ORDER, so_min_common=5) as g:
+        with pytest.raises(SacCotError) as ei:
+            g.sharded_phase1(p.src, p.dst, 0, 2)     # A2 needs every rank's counts: not available sharded
+        assert ei.value.status == _abi.E_UNSUPPORTED
+        g.params.so_min_common = -1
+        with pytest.raises(SacCotError) as ei:
+            g.register(p.src, p.dst)
+        assert ei.value.status == _abi.E_PARAMS
+    with Registrar(lib=gpu_lib) as g:
+        R1, t1, i1 = g.register(p.src, p.dst)
+        g.params.struct_size = _abi.PARAMS_SIZE_V1   # a caller compiled against version 1 of the struct
+        g.params.so_min_common = 777                 # lies beyond it: ignored
+        R2, t2, i2 = g.register(p.src, p.dst)
+        np.testing.assert_array_equal(R1, R2)
+        assert i1 == i2

@@ -45,8 +45,9 @@ def test_oracle_exports_every_header_symbol(oracle_lib):
 def test_params_struct_layout(product_lib, oracle_lib):
     for lib in (product_lib, oracle_lib):
         p = _abi.default_params(lib)
-        assert p.struct_size == C.sizeof(_abi.Params) == 32
-        assert (p.num_edges, p.apex_per_edge, p.score_mode, p.refit, p.reserved) == (1024, 4, 0, 1, 0)
+        assert p.struct_size == C.sizeof(_abi.Params) == 40
+        assert (p.num_edges, p.apex_per_edge, p.score_mode, p.refit, p.compat_mode, p.so_min_common, p.reserved) == \
+            (1024, 4, 0, 1, 0, 0, 0)
         assert abs(p.tau_compat - 0.1) < 1e-7 and abs(p.tau_inlier - 0.1) < 1e-7
 
 

@@ -157,3 +157,66 @@ def test_inliers_form_a_clique_in_fp32(oracle):
         A = W.graph_dense(p.src, p.dst, p.tau_compat)
         sub = A[np.ix_(p.inlier_idx, p.inlier_idx)]
         assert sub.sum() == len(p.inlier_idx) * (len(p.inlier_idx) - 1)
+
+
+# ---- second-order compatibility: A2 = A and ((A.A) o A >= c) ---------------------------
+@pytest.mark.parametrize("N,ratio,cmin,seed", [(200, 0.2, 0, 31), (200, 0.2, 12, 32), (500, 0.05, 6, 33), (300, 0.1, 10 ** 4, 34)])
+def test_second_order_graph_matches_matmul_witness(oracle, N, ratio, cmin, seed):
+    p = synth.make_pair(N, ratio, seed)
+    R, t, inl = run(oracle, p, num_edges=64, apex_per_edge=4, compat_mode=_abi.COMPAT_SECOND_ORDER, so_min_common=cmin)
+    A, _ = W.unpack_adj(oracle.debug(0, _abi.DBG_ADJ_FIRST), N)
+    np.testing.assert_array_equal(A, W.graph_dense(p.src, p.dst, p.tau_compat))
+    C1, _ = W.triangle_counts(A)                      # (A.A) o A: common neighbours on the edges of A
+    A2_want = A & (C1 >= cmin)
+    A2, pad = W.unpack_adj(oracle.debug(0, _abi.DBG_ADJ), N)
+    assert not pad.any()
+    np.testing.assert_array_equal(A2, A2_want)
+    if cmin == 0:
+        np.testing.assert_array_equal(A2, A)
+    # every later stage ran on A2
+    T2, t2 = W.triangle_counts(A2)
+    np.testing.assert_array_equal(oracle.debug(0, _abi.DBG_T_NODE), t2)
+    keys = np.sort(oracle.debug(0, _abi.DBG_EDGE_KEYS))
+    np.testing.assert_array_equal(keys, np.sort(W.edge_keys(A2, T2)))
+    want_top = np.sort(W.edge_keys(A2, T2))[::-1][:64]
+    np.testing.assert_array_equal(oracle.debug(0, _abi.DBG_TOP_EDGES), want_top)
+    tri = oracle.debug(0, _abi.DBG_TRIANGLES).reshape(-1, 3)
+    np.testing.assert_array_equal(tri, W.select_triangles(A2, t2, want_top, 4, 64 * 4))
+    if not A2.any():
+        assert inl == 0   # no edge survives: "no valid triangle" is a result
+
+
+def test_second_order_mode_filters_outlier_edges_and_recovers_the_pose(oracle):
+    # at 5 % inliers the inlier-inlier edges share ~N_in neighbours, random edges ~p^2 N: a threshold in between keeps
+    # the inlier clique and drops most of the rest
+    N = 1500
+    p = synth.make_pair(N, 0.05, 35)
+    run(oracle, p, compat_mode=_abi.COMPAT_FIRST_ORDER)
+    e1 = int(oracle.debug(0, _abi.DBG_NUM_EDGES)[0])
+    R, t, inl = run(oracle, p, compat_mode=_abi.COMPAT_SECOND_ORDER, so_min_common=40)
+    e2 = int(oracle.debug(0, _abi.DBG_NUM_EDGES)[0])
+    assert e2 < e1 / 5
+    A2, _ = W.unpack_adj(oracle.debug(0, _abi.DBG_ADJ), N)
+    idx = p.inlier_idx
+    assert A2[np.ix_(idx, idx)].sum() == len(idx) * (len(idx) - 1)   # the inlier clique survives
+    ang, dt = synth.pose_error(R, t, p.R_gt, p.t_gt)
+    assert ang < np.deg2rad(1.0) and dt < 0.02 and inl >= len(idx)
+
+
+def test_version1_params_struct_still_accepted(oracle_lib):
+    import ctypes as C
+    p = synth.make_pair(200, 0.2, 36)
+    R = np.zeros(9, np.float32); t = np.zeros(3, np.float32); inl = C.c_int32()
+    prm = _abi.default_params(oracle_lib)
+    want = oracle_lib.sac_cot_register(_abi.fptr(p.src), _abi.fptr(p.dst), 200, C.byref(prm), _abi.fptr(R), _abi.fptr(t), C.byref(inl))
+    assert want == 0
+    R2 = np.zeros(9, np.float32); t2 = np.zeros(3, np.float32); inl2 = C.c_int32()
+    prm.struct_size = _abi.PARAMS_SIZE_V1
+    prm.so_min_common = 12345          # beyond the version-1 struct: must be ignored
+    assert oracle_lib.sac_cot_register(_abi.fptr(p.src), _abi.fptr(p.dst), 200, C.byref(prm), _abi.fptr(R2), _abi.fptr(t2), C.byref(inl2)) == 0
+    np.testing.assert_array_equal(R, R2)
+    assert inl.value == inl2.value
+    prm.compat_mode = 1                # version 1 called this field `reserved`: must be 0
+    assert oracle_lib.sac_cot_register(_abi.fptr(p.src), _abi.fptr(p.dst), 200, C.byref(prm), _abi.fptr(R2), _abi.fptr(t2), C.byref(inl2)) == _abi.E_PARAMS
+    prm.struct_size = 36
+    assert oracle_lib.sac_cot_register(_abi.fptr(p.src), _abi.fptr(p.dst), 200, C.byref(prm), _abi.fptr(R2), _abi.fptr(t2), C.byref(inl2)) == _abi.E_PARAMS
