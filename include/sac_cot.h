@@ -44,6 +44,8 @@ extern "C" {
 #define SAC_COT_MAX_EDGES        4096    /* K_e  */
 #define SAC_COT_MAX_APEX         8       /* m    */
 #define SAC_COT_MAX_HYPOTHESES   32768   /* K_e*m; hypothesis ids are packed in 16 bit      */
+#define SAC_COT_MAX_DESC_DIM     256     /* descriptor width of the matching front end       */
+#define SAC_COT_MAX_KEYPOINTS    1048576 /* keypoints per cloud of the matching front end    */
 
 /* ------------------------------------------------------------------ status */
 enum {
@@ -133,7 +135,8 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *        nothing else running: the roofline denominator bench.py reports against; synchronises; GPU only),
  *        "stage_us_<s>" / "stage_calls_<s>" with <s> in pack, graph, scan, theta, triangles, select,
  *        apex, kabsch, score, finalize, exchange1 (sharded: record + all-gather + merge), exchange2
- *        (sharded: all-reduce): accumulated device microseconds / launches,
+ *        (sharded: all-reduce), match_prep, match_sweep, match_exact (front end): accumulated device
+ *        microseconds / launches,
  *        "comm_rank", "comm_world" (0 = no communicator)                                 */
 SAC_COT_API int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value);
 SAC_COT_API int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value);
@@ -161,6 +164,29 @@ SAC_COT_API int sac_cot_register_packed(sac_cot_ctx* ctx,
                                         const sac_cot_params* params,
                                         float* R, float* t, int32_t* inliers,
                                         int32_t location);
+
+/* ------------------------------------------------------------------ correspondence front end */
+/* Nearest-neighbour matching of local descriptors (33-D FPFH-like): the stage that produces the N
+ * putative correspondences sac_cot_register* consumes.  For every source keypoint i of pair b
+ *     D_ij  = sum_c (f_ic - g_jc)^2 in fp32:  D = 0; for c = 0 .. dim-1: e = f_ic - g_jc; D = fma(e, e, D)
+ *     nn[i] = argmin_j D_ij over the pair's target keypoints, ties -> lowest j   (index local to the pair)
+ *     corr_src[i] = xyz_src[i],  corr_dst[i] = xyz_dst[nn[i]]
+ * so pair b gets Ns_b correspondences at offs_src[b]: corr_src / corr_dst / offs_src are exactly the src / dst /
+ * offsets of sac_cot_register_packed (with SAC_COT_LOC_DEVICE the hand-off never leaves the device).
+ * Descriptors must be finite.  desc_*: rows x dim, xyz_*: rows x 3, row-major, packed over the pairs; offs_* (B+1
+ * entries) are host arrays.  location as in sac_cot_register_packed (DEVICE: enqueue only on the ctx stream).
+ * GPU library: dim <= 40 runs the search on the tensor cores (bf16x3 split operands, tcgen05.mma, candidates within a
+ * proven margin) and decides with the specified fp32 chain — results are bit-identical to the oracle's brute force;
+ * wider descriptors are scanned exhaustively with that chain.  ctx knob "match_path" = 0 forces the exhaustive scan. */
+SAC_COT_API int sac_cot_match_packed(sac_cot_ctx* ctx,
+                                     const float* desc_src, const float* xyz_src, const int64_t* offs_src,
+                                     const float* desc_dst, const float* xyz_dst, const int64_t* offs_dst,
+                                     int32_t B, int32_t dim,
+                                     int32_t* nn, float* corr_src, float* corr_dst, int32_t location);
+/* One pair, host buffers, process-global ctx (as sac_cot_register). */
+SAC_COT_API int sac_cot_match(const float* desc_src, const float* xyz_src, int32_t Ns,
+                              const float* desc_dst, const float* xyz_dst, int32_t Nd, int32_t dim,
+                              int32_t* nn, float* corr_src, float* corr_dst);
 
 /* ------------------------------------------------------------------ several GPUs of one box, batched pairs */
 /* A group owns one ctx per listed CUDA device and an enqueueing thread for each.  A batch is dealt round-robin —

@@ -583,7 +583,7 @@ int sac_cot_ctx_destroy(sac_cot_ctx* ctx) {
 int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return SAC_COT_E_NULL;
   if (!std::strcmp(name, "keep_debug")) { ctx->keep_debug = value != 0; return SAC_COT_OK; }
-  if (!std::strcmp(name, "chunk_pairs") || !std::strcmp(name, "triangle_path")) return SAC_COT_OK;
+  if (!std::strcmp(name, "chunk_pairs") || !std::strcmp(name, "triangle_path") || !std::strcmp(name, "match_path")) return SAC_COT_OK;
   if (!std::strcmp(name, "threads")) {  // OpenMP build: worker threads of the calls that follow (a launcher may have
                                         // exported OMP_NUM_THREADS=1); ignored by the single-thread build
     if (value < 1) return SAC_COT_E_SIZE;
@@ -735,6 +735,61 @@ int sac_cot_sharded_phase3(sac_cot_ctx* ctx, uint64_t best_key_global, float R[9
   st.best_key = best_key_global;
   finalize(st, best_key_global, R, t, inliers);
   return SAC_COT_OK;
+}
+
+// ---- correspondence front end (DESIGN.md §2 "S-1") --------------------------
+//   D_ij = sum_c (f_ic - g_jc)^2 in fp32: D = 0; for c ascending: e = f_ic - g_jc; D = fma(e, e, D)
+//   nn[i] = argmin_j D_ij, ties -> lowest j (strict < while j ascends); corr = (xyz_src[i], xyz_dst[nn[i]])
+int sac_cot_match_packed(sac_cot_ctx* ctx, const float* desc_src, const float* xyz_src, const int64_t* offs_src,
+                         const float* desc_dst, const float* xyz_dst, const int64_t* offs_dst, int32_t B, int32_t dim,
+                         int32_t* nn, float* corr_src, float* corr_dst, int32_t location) {
+  if (!ctx || !offs_src || !offs_dst) return SAC_COT_E_NULL;
+  if (location != SAC_COT_LOC_HOST) return SAC_COT_E_UNSUPPORTED;
+  if (B < 0 || B > 65535) return SAC_COT_E_SIZE;
+  if (dim < 1 || dim > SAC_COT_MAX_DESC_DIM) return SAC_COT_E_SIZE;
+  if (B > 0 && (!desc_src || !xyz_src || !desc_dst || !xyz_dst || !nn || !corr_src || !corr_dst)) return SAC_COT_E_NULL;
+  for (int b = 0; b < B; ++b) {
+    const int64_t ns = offs_src[b + 1] - offs_src[b], nd = offs_dst[b + 1] - offs_dst[b];
+    if (ns < 1 || nd < 1 || ns > SAC_COT_MAX_KEYPOINTS || nd > SAC_COT_MAX_KEYPOINTS) return SAC_COT_E_SIZE;
+  }
+  for (int b = 0; b < B; ++b) {
+    const int64_t s0 = offs_src[b], d0 = offs_dst[b];
+    const int ns = static_cast<int>(offs_src[b + 1] - s0), nd = static_cast<int>(offs_dst[b + 1] - d0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int i = 0; i < ns; ++i) {
+      const float* f = desc_src + static_cast<size_t>(s0 + i) * dim;
+      float best = 0.0f;
+      int arg = 0;
+      for (int j = 0; j < nd; ++j) {
+        const float* g = desc_dst + static_cast<size_t>(d0 + j) * dim;
+        float D = 0.0f;
+        for (int c = 0; c < dim; ++c) {
+          const float e = f[c] - g[c];
+          D = std::fmaf(e, e, D);
+        }
+        if (j == 0 || D < best) {
+          best = D;
+          arg = j;
+        }
+      }
+      nn[s0 + i] = arg;
+      for (int a = 0; a < 3; ++a) {
+        corr_src[static_cast<size_t>(s0 + i) * 3 + a] = xyz_src[static_cast<size_t>(s0 + i) * 3 + a];
+        corr_dst[static_cast<size_t>(s0 + i) * 3 + a] = xyz_dst[static_cast<size_t>(d0 + arg) * 3 + a];
+      }
+    }
+  }
+  return SAC_COT_OK;
+}
+
+int sac_cot_match(const float* desc_src, const float* xyz_src, int32_t Ns, const float* desc_dst, const float* xyz_dst,
+                  int32_t Nd, int32_t dim, int32_t* nn, float* corr_src, float* corr_dst) {
+  static sac_cot_ctx global_ctx;
+  const int64_t os[2] = {0, Ns}, od[2] = {0, Nd};
+  return sac_cot_match_packed(&global_ctx, desc_src, xyz_src, os, desc_dst, xyz_dst, od, 1, dim, nn, corr_src, corr_dst,
+                              SAC_COT_LOC_HOST);
 }
 
 // ---- device groups: GPU library only -----------------------------------------------------

@@ -15,6 +15,8 @@ MAX_N = 65535
 MAX_EDGES = 4096
 MAX_APEX = 8
 MAX_HYPOTHESES = 32768
+MAX_DESC_DIM = 256
+MAX_KEYPOINTS = 1048576
 
 OK = 0
 E_NULL, E_SIZE, E_PARAMS, E_NODEVICE, E_UNSUPPORTED, E_WHICH, E_CAPACITY, E_NOMEM, E_COMM = -1, -2, -3, -4, -5, -6, -7, -8, -9
@@ -71,6 +73,9 @@ SYMBOLS = {
                                          C.POINTER(Params), _f32p, _f32p, _i32p]),
     "sac_cot_register_packed": (C.c_int, [_ctxp, C.c_void_p, C.c_void_p, _i64p, C.c_int32,
                                           C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "sac_cot_match_packed": (C.c_int, [_ctxp, C.c_void_p, C.c_void_p, _i64p, C.c_void_p, C.c_void_p, _i64p, C.c_int32,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "sac_cot_match": (C.c_int, [_f32p, _f32p, C.c_int32, _f32p, _f32p, C.c_int32, C.c_int32, _i32p, _f32p, _f32p]),
     "sac_cot_group_create": (C.c_int, [C.POINTER(_ctxp), _i32p, C.c_int32]),
     "sac_cot_group_destroy": (C.c_int, [_ctxp]),
     "sac_cot_group_size": (C.c_int32, [_ctxp]),

@@ -166,6 +166,54 @@ class Registrar:
             raise SacCotError(rc, "sac_cot_register_batch", self.lib)
         return Result(R, t, inl)
 
+    # -- correspondence front end --------------------------------------
+    def match_packed_ptr(self, desc_src: int, xyz_src: int, offs_src: np.ndarray, desc_dst: int, xyz_dst: int,
+                         offs_dst: np.ndarray, dim: int, nn: int, corr_src: int, corr_dst: int, location: int):
+        """Raw-pointer form of sac_cot_match_packed (host or device buffers); enqueue-only for LOC_DEVICE."""
+        offs_src = np.ascontiguousarray(offs_src, dtype=np.int64)
+        offs_dst = np.ascontiguousarray(offs_dst, dtype=np.int64)
+        if len(offs_src) != len(offs_dst):
+            raise ValueError("offs_src and offs_dst must describe the same number of pairs")
+        rc = self.lib.sac_cot_match_packed(
+            self._ctx, desc_src, xyz_src, offs_src.ctypes.data_as(C.POINTER(C.c_int64)), desc_dst, xyz_dst,
+            offs_dst.ctypes.data_as(C.POINTER(C.c_int64)), len(offs_src) - 1, int(dim), nn, corr_src, corr_dst, location)
+        if rc != _abi.OK:
+            raise SacCotError(rc, "sac_cot_match_packed", self.lib)
+
+    def match_batch(self, desc_src, xyz_src, desc_dst, xyz_dst):
+        """Nearest-neighbour matching of descriptors, one entry per pair: sequences of (Ns_b, dim) / (Ns_b, 3) source and
+        (Nd_b, dim) / (Nd_b, 3) target arrays (host).  Returns (nn, corr_src, corr_dst, offsets): nn[i] is the matched
+        target keypoint (index local to the pair) of source keypoint i; corr_src / corr_dst / offsets feed
+        register_packed as they are."""
+        B = len(desc_src)
+        if not (B == len(xyz_src) == len(desc_dst) == len(xyz_dst)) or B == 0:
+            raise ValueError("need the same (non-zero) number of pairs in every argument")
+        ds = [np.ascontiguousarray(a, dtype=np.float32) for a in desc_src]
+        dd = [np.ascontiguousarray(a, dtype=np.float32) for a in desc_dst]
+        dim = ds[0].shape[1]
+        if any(a.ndim != 2 or a.shape[1] != dim for a in ds + dd):
+            raise ValueError("descriptors must be (rows, dim) arrays of one width")
+        xs = [np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in xyz_src]
+        xd = [np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in xyz_dst]
+        if any(len(a) != len(b) for a, b in zip(ds, xs)) or any(len(a) != len(b) for a, b in zip(dd, xd)):
+            raise ValueError("every keypoint needs a descriptor")
+        os_ = np.zeros(B + 1, np.int64)
+        od_ = np.zeros(B + 1, np.int64)
+        np.cumsum([len(a) for a in ds], out=os_[1:])
+        np.cumsum([len(a) for a in dd], out=od_[1:])
+        DS, DD, XS, XD = (np.ascontiguousarray(np.concatenate(v)) for v in (ds, dd, xs, xd))
+        nn = np.empty(int(os_[-1]), np.int32)
+        cs = np.empty((int(os_[-1]), 3), np.float32)
+        cd = np.empty((int(os_[-1]), 3), np.float32)
+        self.match_packed_ptr(DS.ctypes.data, XS.ctypes.data, os_, DD.ctypes.data, XD.ctypes.data, od_, dim, nn.ctypes.data,
+                              cs.ctypes.data, cd.ctypes.data, _abi.LOC_HOST)
+        return nn, cs, cd, os_
+
+    def match(self, desc_src, xyz_src, desc_dst, xyz_dst):
+        """One pair: (nn, corr_src, corr_dst)."""
+        nn, cs, cd, _ = self.match_batch([desc_src], [xyz_src], [desc_dst], [xyz_dst])
+        return nn, cs, cd
+
     # -- sharded single pair (SURVEY.md §8e) ------------------------------------------
     def sharded_phase1(self, src, dst, rank: int, world: int):
         src = np.ascontiguousarray(src, dtype=np.float32).reshape(-1, 3)

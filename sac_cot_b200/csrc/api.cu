@@ -104,8 +104,10 @@ size_t pair_bytes_estimate(int N, int K, int Ke, bool tensor_path, bool second_o
 }
 
 // Optional per-stage timing with CUDA events on the ctx stream ("stage_timing" knob).
-enum Stage { ST_PACK = 0, ST_GRAPH, ST_SCAN, ST_THETA, ST_TRIANGLES, ST_SELECT, ST_APEX, ST_KABSCH, ST_SCORE, ST_FINALIZE, ST_EXCH1, ST_EXCH2, ST_COUNT };
-const char* const kStageNames[ST_COUNT] = {"pack", "graph", "scan", "theta", "triangles", "select", "apex", "kabsch", "score", "finalize", "exchange1", "exchange2"};
+enum Stage { ST_PACK = 0, ST_GRAPH, ST_SCAN, ST_THETA, ST_TRIANGLES, ST_SELECT, ST_APEX, ST_KABSCH, ST_SCORE, ST_FINALIZE, ST_EXCH1, ST_EXCH2,
+             ST_MATCH_PREP, ST_MATCH_SWEEP, ST_MATCH_EXACT, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"pack", "graph", "scan", "theta", "triangles", "select", "apex", "kabsch", "score", "finalize", "exchange1", "exchange2",
+                                           "match_prep", "match_sweep", "match_exact"};
 
 // NCCL, bound at run time: the library carries no link-time dependency on it (a process that already loaded
 // libnccl.so.2 — torch does — gets that copy; otherwise the system one).
@@ -239,6 +241,15 @@ struct sac_cot_ctx {
   // host staging for the pointer-array batch entry point
   std::vector<float> stage_src, stage_dst;
   StageTimer timer;
+
+  // correspondence front end (sac_cot_match_packed): its own grow-only workspace on the ctx stream
+  unsigned char* match_arena = nullptr;
+  size_t match_arena_bytes = 0;
+  unsigned char* h_match = nullptr;   // pinned staging of the pair table
+  size_t h_match_bytes = 0;
+  cudaEvent_t match_uploaded = nullptr;
+  std::vector<int64_t> match_sig;     // shapes the resident pair table was built for
+  int match_path = 1;                 // 1: tensor-core sweep + exact decision (dim <= kMatchMaxDim); 0: exhaustive exact scan
 
   // sharded single pair with in-library collectives
   ncclComm_t comm = nullptr;
@@ -965,11 +976,13 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lanes[l].uploaded, cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_xsum, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->match_uploaded, cudaEventDisableTiming);
   if (e != cudaSuccess) { sac_cot_ctx_destroy(ctx); return static_cast<int>(e); }
   std::memset(ctx->h_sticky, 0, 2 * sizeof(StickyDev));
   int rc = triangles_configure();
   if (rc >= 0) rc = triangles_mma_configure();
   if (rc >= 0) rc = select_configure();
+  if (rc >= 0) rc = match_configure();
   if (rc < 0) { sac_cot_ctx_destroy(ctx); return -rc; }
   *out = ctx;
   return SAC_COT_OK;
@@ -991,6 +1004,9 @@ int sac_cot_ctx_destroy(sac_cot_ctx* ctx) {
   if (ctx->comm && ctx->own_comm)
     if (NcclApi* nc = nccl_api()) nc->CommDestroy(ctx->comm);
   if (ctx->h_xsum) cudaFreeHost(ctx->h_xsum);
+  if (ctx->match_arena) cudaFree(ctx->match_arena);
+  if (ctx->h_match) cudaFreeHost(ctx->h_match);
+  if (ctx->match_uploaded) cudaEventDestroy(ctx->match_uploaded);
   for (ChunkDev* h : ctx->h_chunks) cudaFreeHost(h);
   if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   if (ctx->h_sticky) cudaFreeHost(ctx->h_sticky);
@@ -1033,6 +1049,11 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     ctx->tile_runs = value != 0;
     return SAC_COT_OK;
   }
+  if (!std::strcmp(name, "match_path")) {
+    if (value < 0 || value > 1) return SAC_COT_E_UNSUPPORTED;
+    ctx->match_path = static_cast<int>(value);
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "triangle_dbg")) {
     ctx->tri_dbg = static_cast<int>(value);
     return SAC_COT_OK;
@@ -1062,6 +1083,7 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
   if (!std::strcmp(name, "lanes")) { *value = ctx->n_lanes; return SAC_COT_OK; }
   if (!std::strcmp(name, "triangle_path")) { *value = ctx->tri_path; return SAC_COT_OK; }
   if (!std::strcmp(name, "triangle_prune")) { *value = ctx->tri_prune; return SAC_COT_OK; }
+  if (!std::strcmp(name, "match_path")) { *value = ctx->match_path; return SAC_COT_OK; }
   if (!std::strcmp(name, "triangle_path_used")) {
     // which S2 kernels the most recent chunk on lane 0 ran (0 = POPC, 1 = tensor core); synchronises
     Lane& ln = ctx->lanes[0];
@@ -1177,6 +1199,202 @@ int sac_cot_register(const float* src, const float* dst, int32_t N, const sac_co
   }
   const int64_t offsets[2] = {0, N};
   return sac_cot_register_packed(g_ctx, src, dst, offsets, 1, params, R, t, inliers, SAC_COT_LOC_HOST);
+}
+
+// ---- correspondence front end: descriptor nearest-neighbour matching -------
+}  // extern "C"
+
+namespace {
+
+int run_match(sac_cot_ctx* ctx, const float* desc_src, const float* xyz_src, const int64_t* offs_src, const float* desc_dst,
+              const float* xyz_dst, const int64_t* offs_dst, int32_t B, int32_t dim, int32_t* nn, float* corr_src,
+              float* corr_dst, int32_t location) {
+  if (!ctx || !offs_src || !offs_dst) return SAC_COT_E_NULL;
+  if (location != SAC_COT_LOC_HOST && location != SAC_COT_LOC_DEVICE) return SAC_COT_E_UNSUPPORTED;
+  if (B < 0 || B > 65535) return SAC_COT_E_SIZE;
+  if (dim < 1 || dim > SAC_COT_MAX_DESC_DIM) return SAC_COT_E_SIZE;
+  if (B > 0 && (!desc_src || !xyz_src || !desc_dst || !xyz_dst || !nn || !corr_src || !corr_dst)) return SAC_COT_E_NULL;
+  for (int b = 0; b < B; ++b) {
+    const int64_t ns = offs_src[b + 1] - offs_src[b], nd = offs_dst[b + 1] - offs_dst[b];
+    if (ns < 1 || nd < 1 || ns > SAC_COT_MAX_KEYPOINTS || nd > SAC_COT_MAX_KEYPOINTS) return SAC_COT_E_SIZE;
+  }
+  if (B == 0) return SAC_COT_OK;
+  CU_TRY(cudaSetDevice(ctx->device));
+  const bool host = location == SAC_COT_LOC_HOST;
+  const bool tensor = ctx->match_path == 1 && dim <= kMatchMaxDim;
+  const int chunks = match_chunks(dim);
+  const int64_t tot_s = offs_src[B] - offs_src[0], tot_d = offs_dst[B] - offs_dst[0];
+
+  // ---- pair table + workspace layout (offsets relative to the arena) ----
+  std::vector<MatchPair> tab(static_cast<size_t>(B));
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t o_tab = take(sizeof(MatchPair) * B);
+  const size_t o_bmax = take(sizeof(uint32_t) * B);
+  size_t norm_rows = 0, img_bytes = 0;
+  int max_s_tiles = 0, max_d_tiles = 0, max_ns = 0;
+  for (int b = 0; b < B; ++b) {
+    MatchPair& m = tab[b];
+    m.Ns = static_cast<int32_t>(offs_src[b + 1] - offs_src[b]);
+    m.Nd = static_cast<int32_t>(offs_dst[b + 1] - offs_dst[b]);
+    m.s_tiles = (m.Ns + kMatchTileM - 1) / kMatchTileM;
+    m.d_tiles = (m.Nd + kMatchTileN - 1) / kMatchTileN;
+    m.s_off = offs_src[b] - offs_src[0];
+    m.d_off = offs_dst[b] - offs_dst[0];
+    m.s_norm = static_cast<int64_t>(norm_rows);
+    m.cand_off = m.s_off;
+    m.s_img = static_cast<int64_t>(img_bytes);
+    img_bytes += static_cast<size_t>(m.s_tiles) * kMatchTileM * chunks * 16;
+    m.d_img = static_cast<int64_t>(img_bytes);
+    img_bytes += static_cast<size_t>(m.d_tiles) * kMatchTileN * chunks * 16;
+    norm_rows += static_cast<size_t>(m.s_tiles) * kMatchTileM;
+    max_s_tiles = std::max(max_s_tiles, m.s_tiles);
+    max_d_tiles = std::max(max_d_tiles, m.d_tiles);
+    max_ns = std::max(max_ns, m.Ns);
+  }
+  const size_t o_norm = tensor ? take(sizeof(float) * norm_rows) : 0;
+  const size_t o_img = tensor ? take(img_bytes) : 0;
+  const size_t o_cand = tensor ? take(sizeof(int32_t) * kMatchCand * tot_s) : 0;
+  const size_t o_cnt = tensor ? take(sizeof(int32_t) * tot_s) : 0;
+  const size_t o_ds = host ? take(sizeof(float) * dim * tot_s) : 0;
+  const size_t o_dd = host ? take(sizeof(float) * dim * tot_d) : 0;
+  const size_t o_xs = host ? take(sizeof(float) * 3 * tot_s) : 0;
+  const size_t o_xd = host ? take(sizeof(float) * 3 * tot_d) : 0;
+  const size_t o_nn = host ? take(sizeof(int32_t) * tot_s) : 0;
+  const size_t o_cs = host ? take(sizeof(float) * 3 * tot_s) : 0;
+  const size_t o_cd = host ? take(sizeof(float) * 3 * tot_s) : 0;
+  if (off > ctx->match_arena_bytes) {
+    if (int rc = sync_all(ctx)) return rc;
+    if (ctx->match_arena) CU_TRY(cudaFree(ctx->match_arena));
+    ctx->match_arena = nullptr;
+    ctx->match_arena_bytes = 0;
+    ctx->match_sig.clear();
+    const size_t want = align_up(off + off / 8, 1 << 20);
+    if (cudaMalloc(&ctx->match_arena, want) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return SAC_COT_E_NOMEM;
+    }
+    ctx->match_arena_bytes = want;
+  }
+  unsigned char* base = ctx->match_arena;
+  // images hold offsets relative to the image block
+  MatchPair* d_tab = reinterpret_cast<MatchPair*>(base + o_tab);
+  uint32_t* d_bmax = reinterpret_cast<uint32_t*>(base + o_bmax);
+  float* d_norm = reinterpret_cast<float*>(base + o_norm);
+  unsigned char* d_img = base + o_img;
+  int32_t* d_cand = tensor ? reinterpret_cast<int32_t*>(base + o_cand) : nullptr;
+  int32_t* d_cnt = tensor ? reinterpret_cast<int32_t*>(base + o_cnt) : nullptr;
+  cudaStream_t stream = ctx->stream;
+  // ---- pair table upload (skipped when the shapes repeat) ----
+  std::vector<int64_t> sig;
+  sig.reserve(2 * static_cast<size_t>(B) + 4);
+  sig.push_back(B);
+  sig.push_back(dim);
+  sig.push_back((host ? 1 : 0) | (tensor ? 2 : 0));
+  for (int b = 0; b < B; ++b) {
+    sig.push_back(tab[b].Ns);
+    sig.push_back(tab[b].Nd);
+  }
+  if (sig != ctx->match_sig) {
+    const size_t bytes = sizeof(MatchPair) * B;
+    CU_TRY(cudaEventSynchronize(ctx->match_uploaded));
+    if (bytes > ctx->h_match_bytes) {
+      if (ctx->h_match) CU_TRY(cudaFreeHost(ctx->h_match));
+      ctx->h_match = nullptr;
+      ctx->h_match_bytes = 0;
+      if (cudaMallocHost(&ctx->h_match, align_up(bytes * 2, 4096)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return SAC_COT_E_NOMEM;
+      }
+      ctx->h_match_bytes = align_up(bytes * 2, 4096);
+    }
+    std::memcpy(ctx->h_match, tab.data(), bytes);
+    CU_TRY(cudaMemcpyAsync(d_tab, ctx->h_match, bytes, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaEventRecord(ctx->match_uploaded, stream));
+    ctx->match_sig.swap(sig);
+  }
+  const float* ds = desc_src + static_cast<size_t>(offs_src[0]) * dim;
+  const float* dd = desc_dst + static_cast<size_t>(offs_dst[0]) * dim;
+  const float* xs = xyz_src + static_cast<size_t>(offs_src[0]) * 3;
+  const float* xd = xyz_dst + static_cast<size_t>(offs_dst[0]) * 3;
+  int32_t* o_nn_p = nn + offs_src[0];
+  float* o_cs_p = corr_src + static_cast<size_t>(offs_src[0]) * 3;
+  float* o_cd_p = corr_dst + static_cast<size_t>(offs_src[0]) * 3;
+  if (host) {
+    CU_TRY(cudaMemcpyAsync(base + o_ds, ds, sizeof(float) * dim * tot_s, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(base + o_dd, dd, sizeof(float) * dim * tot_d, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(base + o_xs, xs, sizeof(float) * 3 * tot_s, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(base + o_xd, xd, sizeof(float) * 3 * tot_d, cudaMemcpyHostToDevice, stream));
+    ds = reinterpret_cast<const float*>(base + o_ds);
+    dd = reinterpret_cast<const float*>(base + o_dd);
+    xs = reinterpret_cast<const float*>(base + o_xs);
+    xd = reinterpret_cast<const float*>(base + o_xd);
+  }
+  int32_t* k_nn = host ? reinterpret_cast<int32_t*>(base + o_nn) : o_nn_p;
+  float* k_cs = host ? reinterpret_cast<float*>(base + o_cs) : o_cs_p;
+  float* k_cd = host ? reinterpret_cast<float*>(base + o_cd) : o_cd_p;
+  LaunchCtx lc{stream, ctx->sm_count};
+  StageTimer& tm = ctx->timer;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto span_begin = [&]() {
+    if (tm.enabled && (e0 = tm.next())) cudaEventRecord(e0, stream);
+  };
+  auto span_end = [&](int stage) {
+    if (tm.enabled && e0 && (e1 = tm.next())) {
+      cudaEventRecord(e1, stream);
+      tm.pending.push_back({stage, e0, e1});
+    }
+    e0 = nullptr;
+  };
+  if (tensor) {
+    span_begin();
+    CU_TRY(cudaMemsetAsync(d_bmax, 0, sizeof(uint32_t) * B, stream));
+    KL_TRY(launch_match_prep(lc, d_tab, B, max_s_tiles * kMatchTileM, ds, 0, dim, d_img, d_norm, d_bmax));
+    KL_TRY(launch_match_prep(lc, d_tab, B, max_d_tiles * kMatchTileN, dd, 1, dim, d_img, d_norm, d_bmax));
+    span_end(ST_MATCH_PREP);
+    span_begin();
+    KL_TRY(launch_match_mma(lc, d_tab, B, max_s_tiles, dim, d_img, d_norm, d_bmax, d_cand, d_cnt));
+    span_end(ST_MATCH_SWEEP);
+  }
+  span_begin();
+  KL_TRY(launch_match_exact(lc, d_tab, B, max_ns, ds, dd, xs, xd, dim, d_cand, d_cnt, k_nn, k_cs, k_cd));
+  span_end(ST_MATCH_EXACT);
+  if (host) {
+    CU_TRY(cudaMemcpyAsync(o_nn_p, k_nn, sizeof(int32_t) * tot_s, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaMemcpyAsync(o_cs_p, k_cs, sizeof(float) * 3 * tot_s, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaMemcpyAsync(o_cd_p, k_cd, sizeof(float) * 3 * tot_s, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+  }
+  return SAC_COT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sac_cot_match_packed(sac_cot_ctx* ctx, const float* desc_src, const float* xyz_src, const int64_t* offs_src,
+                         const float* desc_dst, const float* xyz_dst, const int64_t* offs_dst, int32_t B, int32_t dim,
+                         int32_t* nn, float* corr_src, float* corr_dst, int32_t location) {
+  try {
+    return run_match(ctx, desc_src, xyz_src, offs_src, desc_dst, xyz_dst, offs_dst, B, dim, nn, corr_src, corr_dst, location);
+  } catch (const std::bad_alloc&) {
+    return SAC_COT_E_NOMEM;
+  }
+}
+
+int sac_cot_match(const float* desc_src, const float* xyz_src, int32_t Ns, const float* desc_dst, const float* xyz_dst,
+                  int32_t Nd, int32_t dim, int32_t* nn, float* corr_src, float* corr_dst) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (!g_ctx) {
+    const int rc = sac_cot_ctx_create(&g_ctx, 0, nullptr);
+    if (rc) return rc;
+  }
+  const int64_t os[2] = {0, Ns}, od[2] = {0, Nd};
+  return sac_cot_match_packed(g_ctx, desc_src, xyz_src, os, desc_dst, xyz_dst, od, 1, dim, nn, corr_src, corr_dst, SAC_COT_LOC_HOST);
 }
 
 // ---- device groups: one batch over several GPUs of the box, no communication ------------------

@@ -231,6 +231,31 @@ int launch_shard_merge(const LaunchCtx& lc, const unsigned long long* d_recs, in
                        unsigned long long* d_t2, unsigned long long* d_top, PairDev* d_state, ChunkDev* d_chunk,
                        StickyDev* d_sticky, unsigned long long* d_summary);
 
+// kernels_match.cu — correspondence front end (descriptor nearest-neighbour matching)
+struct MatchPair {
+  int32_t Ns, Nd;          // source / target keypoints of the pair
+  int32_t s_tiles, d_tiles;  // ceil(Ns / 128), ceil(Nd / 256)
+  int64_t s_off, d_off;    // first row of the pair in the packed source / target arrays
+  int64_t s_img, d_img;    // byte offsets of the pair's operand images
+  int64_t s_norm;          // first entry of the pair's source norms (rows padded to whole tiles)
+  int64_t cand_off;        // first row of the pair in the candidate lists (== s_off)
+};
+constexpr int kMatchTileM = 128;    // source rows per CTA (TMEM lanes)
+constexpr int kMatchTileN = 256;    // target rows per tile (TMEM columns of one accumulator)
+constexpr int kMatchMaxDim = 40;    // widest descriptor the tensor-core sweep takes (K = 3 dim + 3 <= 128); wider ones are scanned exhaustively
+constexpr int kMatchCand = 8;       // candidate columns kept per source row
+int match_chunks(int dim);          // 16-byte K chunks per operand row
+int match_configure();
+int launch_match_prep(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_tiles_rows, const float* d_desc,
+                      int side, int dim, unsigned char* d_img, float* d_norms, uint32_t* d_bmax);
+int launch_match_mma(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_s_tiles, int dim,
+                     const unsigned char* d_img, const float* d_norms, const uint32_t* d_bmax, int32_t* d_cand,
+                     int32_t* d_cand_cnt);
+int launch_match_exact(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_ns, const float* d_desc_src,
+                       const float* d_desc_dst, const float* d_xyz_src, const float* d_xyz_dst, int dim,
+                       const int32_t* d_cand, const int32_t* d_cand_cnt, int32_t* d_nn, float* d_corr_src,
+                       float* d_corr_dst);
+
 // kernels_hypo.cu — S4 Kabsch, S5/S6 scoring + argmax, S7 refit
 int launch_kabsch(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const float* d_soa, const int32_t* d_tri,
                   float* d_rt, int K);

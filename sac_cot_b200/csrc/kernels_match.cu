@@ -1,0 +1,406 @@
+// kernels_match.cu — correspondence front end: nearest-neighbour matching of local descriptors
+// (33-D FPFH-like), the stage that PRODUCES the N putative correspondences the hot path registers.  The reference
+// has no such code either (/root/reference/README.md:1-2); the specification is DESIGN.md §2 "S-1":
+//
+//     D_ij = sum_c (f_ic - g_jc)^2   in fp32:  D = 0;  for c = 0 .. dim-1:  e = f_ic - g_jc;  D = fma(e, e, D)
+//     nn(i) = argmin_j D_ij, ties -> lowest j;   correspondence i = (xyz_src[i], xyz_dst[nn(i)])
+//
+// The search is a dense contraction (|f|^2 + |g|^2 - 2 f.g), so it runs on the tensor cores; the DECISION is exact:
+//   1. match_prep_kernel   descriptors -> bf16 operand images in the UMMA canonical (no-swizzle, K-major) layout, one
+//                          contiguous image per tile, so the matching kernel stages a tile with ONE bulk copy.  Every
+//                          fp32 value is split into bf16 hi + lo; the K dimension carries [f_hi | f_lo | f_hi] against
+//                          [g_hi | g_hi | g_lo] (the three products that matter) plus three columns (-1,-1,-1) against
+//                          the three bf16 pieces of |g_j|^2 / 2: the accumulator is C_ij ~ f_i.g_j - |g_j|^2/2, and
+//                          maximising C_ij over j is minimising D_ij.
+//   2. match_mma_kernel    one CTA per 128 source rows: tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), M 128 x
+//                          N 256 per tile, K = 3 dim + 3 padded to 16; a producer warp feeds a 3-stage bulk-copy ring
+//                          and issues the MMAs into two TMEM accumulators; four epilogue warps (thread = row = TMEM
+//                          lane) read them back with tcgen05.ld and keep, per row, the running maximum and the SHORT
+//                          LIST of columns within a margin of it.  |C~ - C| <= 2.6e-5 (|f|^2 + |g|^2) (bf16x3 split
+//                          2^-15.5, tensor-core accumulation <= 128 x 2^-22) and the fp32 chain of the specification
+//                          is within 4.2e-6 of the real distance, so the true nearest neighbour under the SPECIFIED
+//                          arithmetic lies within 2^-12 (|f_i|^2 + max_j |g_j|^2) of the best approximate value: the
+//                          list contains it (DESIGN.md §4 "match").
+//   3. match_exact_kernel  the specified fp32 chain for the listed columns (typically one or two per row), lowest j on
+//                          ties; a row whose list overflowed (many near-identical descriptors) is scanned exhaustively
+//                          with the same chain.  Then the gather of the matched points.
+// Descriptors wider than kMatchMaxDim skip 1-2: every row is scanned exhaustively (CUDA cores).
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace saccot {
+
+namespace {
+
+constexpr int kMatchThreads = 160;                   // warps 0-3 epilogue (128 rows), warp 4 producer / MMA issuer
+constexpr int kStagesB = 3;
+constexpr float kHugeNorm = 1.0e38f;                 // |g|^2 / 2 of a pad row: its C is -1e38, never a candidate
+constexpr float kMarginRel = 1.0f / 4096.0f;         // 2^-12, in units of C (see the header comment)
+
+__device__ __forceinline__ uint64_t match_desc(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((128u >> 4) & 0x3FFF) << 16;        // LBO: next 16-byte K chunk
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;   // SBO: next 8-row group
+  d |= 1ull << 46;                                               // descriptor version (Blackwell); SWIZZLE_NONE
+  return d;
+}
+
+// bounded barrier wait: a protocol bug must end the kernel, not hang the GPU
+__device__ __forceinline__ void match_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (int spins = 0;; ++spins) {
+    uint32_t done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+    if (done) return;
+    if (spins == 0) t0 = clock64();
+    else if (clock64() - t0 > 2000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void match_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void match_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+#define SACCOT_MATCH_LD32(v, taddr)                                                                                    \
+  asm volatile(                                                                                                        \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19," \
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                       \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),    \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),          \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),         \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                       \
+      : "r"(taddr))
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// 1. operand images.  side 0: source rows, tiles of 128, K sections [hi | lo | hi | -1 -1 -1]; also |f_i|^2.
+//                     side 1: target rows, tiles of 256, K sections [hi | hi | lo | pieces of |g_j|^2 / 2]; also the
+//                             pair's max |g_j|^2 (atomicMax on the bit pattern: norms are non-negative floats).
+//    One thread per (row, 16-byte chunk); image of a tile: [8-row group][chunk][8 rows][16 B].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) match_prep_kernel(const MatchPair* __restrict__ pairs, const float* __restrict__ desc,
+                                                         int side, int dim, int chunks, unsigned char* __restrict__ img,
+                                                         float* __restrict__ norms, uint32_t* __restrict__ bmax) {
+  const MatchPair mp = pairs[blockIdx.y];
+  const int TR = side ? kMatchTileN : kMatchTileM;
+  const int n = side ? mp.Nd : mp.Ns;
+  const int tiles = side ? mp.d_tiles : mp.s_tiles;
+  const long long item = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (item >= static_cast<long long>(tiles) * TR * chunks) return;
+  const int c = static_cast<int>(item % chunks);
+  const int r = static_cast<int>(item / chunks);  // row of the pair, pad rows included
+  const float* row = desc + (static_cast<size_t>(side ? mp.d_off : mp.s_off) + static_cast<size_t>(r < n ? r : 0)) * dim;
+  // the row's squared norm (every chunk thread of a target row needs its pieces only in the chunk that holds them;
+  // computing it in the one thread that stores it keeps the chain's order fixed: c ascending, one fma each)
+  const int k_norm = 3 * dim;  // first of the three norm columns
+  float nrm = 0.0f;
+  const bool need_norm = c == 0 || (8 * c <= k_norm + 2 && 8 * c + 7 >= k_norm);
+  if (need_norm && r < n)
+    for (int k = 0; k < dim; ++k) nrm = __fmaf_rn(row[k], row[k], nrm);
+  float half = side ? (r < n ? __fmul_rn(nrm, 0.5f) : kHugeNorm) : 0.0f;
+  // three bf16 pieces of |g|^2 / 2 (hi, mid, lo: 24 mantissa bits)
+  const __nv_bfloat16 p0 = __float2bfloat16_rn(half);
+  const float r1 = __fsub_rn(half, __bfloat162float(p0));
+  const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 p2 = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(p1)));
+  __nv_bfloat16 out[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = 8 * c + e;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.0f);
+    if (k < k_norm) {
+      if (r < n) {
+        const int sec = k / dim, col = k - sec * dim;
+        const float f = row[col];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(f, __bfloat162float(hi)));
+        const bool want_lo = side ? sec == 2 : sec == 1;
+        v = want_lo ? lo : hi;
+      }
+    } else if (k < k_norm + 3) {
+      if (side) v = k == k_norm ? p0 : (k == k_norm + 1 ? p1 : p2);
+      else v = __float2bfloat16_rn(-1.0f);
+    }
+    out[e] = v;
+  }
+  const int tt = r / TR, rt = r - tt * TR;
+  unsigned char* dst = img + (side ? mp.d_img : mp.s_img) + static_cast<size_t>(tt) * TR * chunks * 16 +
+                       static_cast<size_t>(rt >> 3) * chunks * 128 + static_cast<size_t>(c) * 128 + (rt & 7) * 16;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
+  if (c == 0) {
+    if (!side) norms[mp.s_norm + r] = r < n ? nrm : 0.0f;
+    else if (r < n) atomicMax(bmax + blockIdx.y, __float_as_uint(nrm));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. tensor-core sweep.  grid (max source tiles, pairs).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const MatchPair* __restrict__ pairs,
+                                                                     const unsigned char* __restrict__ img,
+                                                                     const float* __restrict__ norms,
+                                                                     const uint32_t* __restrict__ bmax, int chunks,
+                                                                     int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
+  const MatchPair mp = pairs[blockIdx.y];
+  const int st = blockIdx.x;
+  if (st >= mp.s_tiles) return;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int a_bytes = kMatchTileM * chunks * 16, b_bytes = kMatchTileN * chunks * 16;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + a_bytes;                                      // kStagesB stages
+  int32_t* lists = reinterpret_cast<int32_t*>(sB + kStagesB * b_bytes);    // [128][kMatchCand]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kMatchTileM * kMatchCand);
+  uint64_t* a_full = bars;                 // A image landed
+  uint64_t* full = bars + 1;               // [3] B stage landed
+  uint64_t* stage_free = full + kStagesB;  // [3] MMAs that read the stage have completed
+  uint64_t* mma_done = stage_free + kStagesB;  // [2] accumulator complete
+  uint64_t* acc_free = mma_done + 2;       // [2] epilogue has drained the accumulator (4 warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(a_full, 1);
+    for (int s = 0; s < kStagesB; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&stage_free[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&mma_done[b], 1);
+      mbar_init(&acc_free[b], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tmem_slot;
+  const int T = mp.d_tiles;
+  const unsigned char* gA = img + mp.s_img + static_cast<size_t>(st) * a_bytes;
+  const unsigned char* gB = img + mp.d_img;
+
+  if (warp == 4) {
+    // ================================ producer + MMA issuer (one lane) ================================
+    if (lane == 0) {
+      // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kMatchTileN >> 3) << 17) |
+                             (static_cast<uint32_t>(kMatchTileM >> 4) << 24);
+      const uint32_t sbo = static_cast<uint32_t>(chunks) * 128u;
+      mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(a_bytes));
+      bulk_g2s(sA, gA, static_cast<uint32_t>(a_bytes), a_full);
+      for (int n = 0; n < 2 && n < T; ++n) {
+        mbar_arrive_expect_tx(&full[n], static_cast<uint32_t>(b_bytes));
+        bulk_g2s(sB + n * b_bytes, gB + static_cast<size_t>(n) * b_bytes, static_cast<uint32_t>(b_bytes), &full[n]);
+      }
+      match_wait(a_full, 0u);
+      const uint64_t dA0 = match_desc(smem_u32(sA), sbo);
+      for (int n = 0; n < T; ++n) {
+        const int s = n % kStagesB, b = n & 1;
+        match_wait(&full[s], static_cast<uint32_t>((n / kStagesB) & 1));
+        if (n >= 2) match_wait(&acc_free[b], static_cast<uint32_t>(((n >> 1) - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint64_t dB0 = match_desc(smem_u32(sB + s * b_bytes), sbo);
+        for (int k = 0; k < chunks / 2; ++k) {  // K = 16 per instruction = two 16-byte chunks
+          const uint64_t da = dA0 + static_cast<uint64_t>((k * 256) >> 4), db = dB0 + static_cast<uint64_t>((k * 256) >> 4);
+          const uint32_t acc = k ? 1u : 0u;      // the first instruction of a tile overwrites the accumulator
+          asm volatile(
+              "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem + static_cast<uint32_t>(kMatchTileN * b)),
+              "l"(da), "l"(db), "r"(idesc), "r"(acc)
+              : "memory");
+        }
+        match_commit(&mma_done[b]);
+        match_commit(&stage_free[s]);
+        // tile n + 2 goes into the stage tile n - 1 used, as soon as its MMAs have completed
+        if (n + 2 < T) {
+          const int s2 = (n + 2) % kStagesB;
+          if (n >= 1) match_wait(&stage_free[s2], static_cast<uint32_t>(((n - 1) / kStagesB) & 1));
+          mbar_arrive_expect_tx(&full[s2], static_cast<uint32_t>(b_bytes));
+          bulk_g2s(sB + s2 * b_bytes, gB + static_cast<size_t>(n + 2) * b_bytes, static_cast<uint32_t>(b_bytes), &full[s2]);
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue: thread = source row = TMEM lane ================================
+    const int row = st * kMatchTileM + tid;  // row of the pair (pad rows of the last tile run along, results unused)
+    const float a_i = norms[mp.s_norm + row];
+    const float margin = __fmul_rn(kMarginRel, __fadd_rn(a_i, __uint_as_float(bmax[blockIdx.y])));
+    int32_t* lst = lists + tid * kMatchCand;
+    float best = -3.0e38f, thr = -3.0e38f;  // thr = best - margin
+    int cnt = 0;
+    for (int n = 0; n < T; ++n) {
+      const int b = n & 1;
+      match_wait(&mma_done[b], static_cast<uint32_t>((n >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t tbase = tmem + ((32u * warp) << 16) + static_cast<uint32_t>(kMatchTileN * b);
+      uint32_t v[2][32];
+      SACCOT_MATCH_LD32(v[0], tbase);
+#pragma unroll
+      for (int u = 0; u < kMatchTileN / 32; ++u) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (u + 1 < kMatchTileN / 32) SACCOT_MATCH_LD32(v[(u + 1) & 1], tbase + 32u * (u + 1));
+        const uint32_t* vv = v[u & 1];
+        // common case: nothing in these 32 columns comes within the margin of the row's best
+        float m32 = __uint_as_float(vv[0]);
+#pragma unroll
+        for (int e = 1; e < 32; ++e) m32 = fmaxf(m32, __uint_as_float(vv[e]));
+        if (m32 >= thr) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float c = __uint_as_float(vv[e]);
+            if (c >= thr) {
+              if (c > best) {
+                if (c - margin > best) cnt = 0;  // everything listed so far is now out of range
+                best = c;
+                thr = c - margin;
+              }
+              if (cnt < kMatchCand) lst[cnt] = n * kMatchTileN + 32 * u + e;
+              ++cnt;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) match_arrive(&acc_free[b]);
+    }
+    if (row < mp.Ns) {
+      const size_t o = static_cast<size_t>(mp.cand_off) + row;
+      cand_cnt[o] = cnt;
+      for (int k = 0; k < kMatchCand; ++k) cand[o * kMatchCand + k] = k < cnt ? lst[k] : -1;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. exact decision + gather.  One warp per source row.  cand == nullptr: every row is scanned exhaustively.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float match_dist(const float* __restrict__ f, const float* __restrict__ g, int dim) {
+  float D = 0.0f;
+  for (int c = 0; c < dim; ++c) {
+    const float e = __fsub_rn(f[c], g[c]);
+    D = __fmaf_rn(e, e, D);
+  }
+  return D;
+}
+
+__global__ void __launch_bounds__(256) match_exact_kernel(const MatchPair* __restrict__ pairs,
+                                                          const float* __restrict__ desc_src,
+                                                          const float* __restrict__ desc_dst,
+                                                          const float* __restrict__ xyz_src,
+                                                          const float* __restrict__ xyz_dst, int dim,
+                                                          const int32_t* __restrict__ cand,
+                                                          const int32_t* __restrict__ cand_cnt, int32_t* __restrict__ nn,
+                                                          float* __restrict__ corr_src, float* __restrict__ corr_dst) {
+  const MatchPair mp = pairs[blockIdx.y];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int i = blockIdx.x * 8 + wib;
+  extern __shared__ float frow[];  // [8 warps][dim]
+  if (i >= mp.Ns) return;
+  float* f = frow + wib * dim;
+  const float* fi = desc_src + (static_cast<size_t>(mp.s_off) + i) * dim;
+  for (int c = lane; c < dim; c += 32) f[c] = fi[c];
+  __syncwarp();
+  const float* G = desc_dst + static_cast<size_t>(mp.d_off) * dim;
+  float bestD = __int_as_float(0x7f800000);  // +inf
+  int bestJ = 0x7fffffff;
+  const int cnt = cand ? cand_cnt[mp.cand_off + i] : kMatchCand + 1;
+  if (cnt <= kMatchCand) {
+    if (lane < cnt) {
+      const int j = cand[(static_cast<size_t>(mp.cand_off) + i) * kMatchCand + lane];
+      if (j >= 0 && j < mp.Nd) {
+        bestD = match_dist(f, G + static_cast<size_t>(j) * dim, dim);
+        bestJ = j;
+      }
+    }
+  } else {
+    for (int j = lane; j < mp.Nd; j += 32) {  // ascending j per lane: strict < keeps the lowest j of equal distances
+      const float D = match_dist(f, G + static_cast<size_t>(j) * dim, dim);
+      if (D < bestD || bestJ == 0x7fffffff) {
+        bestD = D;
+        bestJ = j;
+      }
+    }
+  }
+  // lexicographic minimum of (D, j) over the warp.  A NaN distance never wins against a number.
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float oD = __shfl_xor_sync(0xffffffffu, bestD, o);
+    const int oJ = __shfl_xor_sync(0xffffffffu, bestJ, o);
+    const bool take = oJ != 0x7fffffff && (bestJ == 0x7fffffff || oD < bestD || (oD == bestD && oJ < bestJ) ||
+                                           (bestD != bestD && oD == oD));
+    if (take) {
+      bestD = oD;
+      bestJ = oJ;
+    }
+  }
+  if (bestJ == 0x7fffffff) bestJ = 0;
+  if (lane == 0) nn[mp.s_off + i] = bestJ;
+  if (lane < 3) {
+    corr_src[(static_cast<size_t>(mp.s_off) + i) * 3 + lane] = xyz_src[(static_cast<size_t>(mp.s_off) + i) * 3 + lane];
+    corr_dst[(static_cast<size_t>(mp.s_off) + i) * 3 + lane] = xyz_dst[(static_cast<size_t>(mp.d_off) + bestJ) * 3 + lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int match_chunks(int dim) { return ((3 * dim + 3 + 15) / 16) * 2; }  // 16-byte chunks of 8 bf16; K padded to 16
+
+size_t match_smem_bytes(int chunks) {
+  return static_cast<size_t>(kMatchTileM + kStagesB * kMatchTileN) * chunks * 16 + kMatchTileM * kMatchCand * 4 + 16 * 8 + 16;
+}
+
+int match_configure() {
+  const cudaError_t e = cudaFuncSetAttribute(match_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(match_smem_bytes(match_chunks(kMatchMaxDim))));
+  return e == cudaSuccess ? 0 : -static_cast<int>(e);
+}
+
+int launch_match_prep(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_tiles_rows, const float* d_desc,
+                      int side, int dim, unsigned char* d_img, float* d_norms, uint32_t* d_bmax) {
+  const int chunks = match_chunks(dim);
+  const long long items = static_cast<long long>(max_tiles_rows) * chunks;
+  match_prep_kernel<<<dim3(static_cast<unsigned>((items + 255) / 256), pairs), 256, 0, lc.stream>>>(d_pairs, d_desc, side, dim,
+                                                                                                 chunks, d_img, d_norms, d_bmax);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+int launch_match_mma(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_s_tiles, int dim,
+                     const unsigned char* d_img, const float* d_norms, const uint32_t* d_bmax, int32_t* d_cand,
+                     int32_t* d_cand_cnt) {
+  const int chunks = match_chunks(dim);
+  match_mma_kernel<<<dim3(max_s_tiles, pairs), kMatchThreads, match_smem_bytes(chunks), lc.stream>>>(
+      d_pairs, d_img, d_norms, d_bmax, chunks, d_cand, d_cand_cnt);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+int launch_match_exact(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_ns, const float* d_desc_src,
+                       const float* d_desc_dst, const float* d_xyz_src, const float* d_xyz_dst, int dim,
+                       const int32_t* d_cand, const int32_t* d_cand_cnt, int32_t* d_nn, float* d_corr_src,
+                       float* d_corr_dst) {
+  match_exact_kernel<<<dim3((max_ns + 7) / 8, pairs), 256, static_cast<size_t>(8) * dim * sizeof(float), lc.stream>>>(
+      d_pairs, d_desc_src, d_desc_dst, d_xyz_src, d_xyz_dst, dim, d_cand, d_cand_cnt, d_nn, d_corr_src, d_corr_dst);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+}  // namespace saccot

@@ -147,3 +147,22 @@ def pose_error(R: np.ndarray, t: np.ndarray, R_gt: np.ndarray, t_gt: np.ndarray)
     sk = 0.5 * np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])
     ang = float(np.arctan2(np.linalg.norm(sk), c))
     return ang, float(np.linalg.norm(np.asarray(t, dtype=np.float64).ravel() - np.asarray(t_gt).ravel()))
+
+
+def make_descriptors(pair: Pair, dim: int = 33, seed: int = 0, noise: float = 0.05):
+    """FPFH-like descriptors for a synthetic pair (no descriptor data is available offline).
+
+    Target keypoint j gets a random non-negative histogram-like descriptor g_j (uniform in [0, 1), scaled to sum 100 as
+    FPFH bins are); source keypoint i gets the descriptor of the target keypoint it truly corresponds to plus uniform
+    noise of relative size `noise` for the inliers, and an unrelated random descriptor otherwise.  Returns
+    (desc_src (N, dim), desc_dst (N, dim)) float32: brute-force nearest-neighbour matching src -> dst then recovers
+    the inlier correspondences and assigns the outliers arbitrary (wrong) partners, like a real front end."""
+    N = pair.src.shape[0]
+    st_g, st_n, st_o = (Stream(seed * 7919 + 17, k) for k in range(3))
+    g = st_g.uniform(N * dim).reshape(N, dim)
+    g = g / g.sum(axis=1, keepdims=True) * 100.0
+    f = st_o.uniform(N * dim).reshape(N, dim)
+    f = f / f.sum(axis=1, keepdims=True) * 100.0
+    eps = (st_n.uniform(N * dim).reshape(N, dim) * 2.0 - 1.0) * noise * (100.0 / dim)
+    f[pair.inlier_idx] = g[pair.inlier_idx] + eps[pair.inlier_idx]
+    return np.ascontiguousarray(f, dtype=np.float32), np.ascontiguousarray(g, dtype=np.float32)
