@@ -29,12 +29,14 @@
 
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 namespace saccot {
 
 namespace {
 
 constexpr int kMatchThreads = 160;                   // warps 0-3 epilogue (128 rows), warp 4 producer / MMA issuer
-constexpr int kStagesB = 3;
+constexpr int kStagesB = 3;                           // most B stages (wide descriptors get 2: shared-memory budget)
 constexpr float kHugeNorm = 1.0e38f;                 // |g|^2 / 2 of a pad row: its C is -1e38, never a candidate
 constexpr float kMarginRel = 1.0f / 4096.0f;         // 2^-12, in units of C (see the header comment)
 
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(256) match_prep_kernel(const MatchPair* __rest
 __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const MatchPair* __restrict__ pairs,
                                                                      const unsigned char* __restrict__ img,
                                                                      const float* __restrict__ norms,
-                                                                     const uint32_t* __restrict__ bmax, int chunks,
+                                                                     const uint32_t* __restrict__ bmax, int chunks, int S,
                                                                      int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
   const MatchPair mp = pairs[blockIdx.y];
   const int st = blockIdx.x;
@@ -156,8 +158,8 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const Match
   extern __shared__ __align__(1024) unsigned char smem[];
   const int a_bytes = kMatchTileM * chunks * 16, b_bytes = kMatchTileN * chunks * 16;
   unsigned char* sA = smem;
-  unsigned char* sB = smem + a_bytes;                                      // kStagesB stages
-  int32_t* lists = reinterpret_cast<int32_t*>(sB + kStagesB * b_bytes);    // [128][kMatchCand]
+  unsigned char* sB = smem + a_bytes;                                      // S stages
+  int32_t* lists = reinterpret_cast<int32_t*>(sB + S * b_bytes);           // [128][kMatchCand]
   uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kMatchTileM * kMatchCand);
   uint64_t* a_full = bars;                 // A image landed
   uint64_t* full = bars + 1;               // [3] B stage landed
@@ -207,8 +209,8 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const Match
       match_wait(a_full, 0u);
       const uint64_t dA0 = match_desc(smem_u32(sA), sbo);
       for (int n = 0; n < T; ++n) {
-        const int s = n % kStagesB, b = n & 1;
-        match_wait(&full[s], static_cast<uint32_t>((n / kStagesB) & 1));
+        const int s = n % S, b = n & 1;
+        match_wait(&full[s], static_cast<uint32_t>((n / S) & 1));
         if (n >= 2) match_wait(&acc_free[b], static_cast<uint32_t>(((n >> 1) - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint64_t dB0 = match_desc(smem_u32(sB + s * b_bytes), sbo);
@@ -223,10 +225,10 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const Match
         }
         match_commit(&mma_done[b]);
         match_commit(&stage_free[s]);
-        // tile n + 2 goes into the stage tile n - 1 used, as soon as its MMAs have completed
+        // tile n + 2 goes into the stage tile n + 2 - S used, as soon as the MMAs that read it have completed
         if (n + 2 < T) {
-          const int s2 = (n + 2) % kStagesB;
-          if (n >= 1) match_wait(&stage_free[s2], static_cast<uint32_t>(((n - 1) / kStagesB) & 1));
+          const int s2 = (n + 2) % S, prev = n + 2 - S;
+          if (prev >= 0) match_wait(&stage_free[s2], static_cast<uint32_t>((prev / S) & 1));
           mbar_arrive_expect_tx(&full[s2], static_cast<uint32_t>(b_bytes));
           bulk_g2s(sB + s2 * b_bytes, gB + static_cast<size_t>(n + 2) * b_bytes, static_cast<uint32_t>(b_bytes), &full[s2]);
         }
@@ -363,13 +365,15 @@ __global__ void __launch_bounds__(256) match_exact_kernel(const MatchPair* __res
 // ------------------------------------------------------------------------------------------
 int match_chunks(int dim) { return ((3 * dim + 3 + 15) / 16) * 2; }  // 16-byte chunks of 8 bf16; K padded to 16
 
+int match_stages(int chunks) { return chunks <= 14 ? kStagesB : 2; }  // 3 x 64 KB stages + the A tile exceed 227 KB
 size_t match_smem_bytes(int chunks) {
-  return static_cast<size_t>(kMatchTileM + kStagesB * kMatchTileN) * chunks * 16 + kMatchTileM * kMatchCand * 4 + 16 * 8 + 16;
+  return static_cast<size_t>(kMatchTileM + match_stages(chunks) * kMatchTileN) * chunks * 16 + kMatchTileM * kMatchCand * 4 + 16 * 8 + 16;
 }
 
 int match_configure() {
-  const cudaError_t e = cudaFuncSetAttribute(match_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(match_smem_bytes(match_chunks(kMatchMaxDim))));
+  size_t most = 0;
+  for (int dim = 1; dim <= kMatchMaxDim; ++dim) most = std::max(most, match_smem_bytes(match_chunks(dim)));
+  const cudaError_t e = cudaFuncSetAttribute(match_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(most));
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
@@ -388,7 +392,7 @@ int launch_match_mma(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, i
                      int32_t* d_cand_cnt) {
   const int chunks = match_chunks(dim);
   match_mma_kernel<<<dim3(max_s_tiles, pairs), kMatchThreads, match_smem_bytes(chunks), lc.stream>>>(
-      d_pairs, d_img, d_norms, d_bmax, chunks, d_cand, d_cand_cnt);
+      d_pairs, d_img, d_norms, d_bmax, chunks, match_stages(chunks), d_cand, d_cand_cnt);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }
