@@ -583,6 +583,159 @@ def run_group(args, emit, torch):
     grp.close()
 
 
+def run_match_bench(args, emit, torch, dev):
+    """--stage match: the correspondence front end on the workload's shape — per pair N source and N
+    target keypoints with 33-D FPFH-like descriptors — and the front end + registration chain with a device-resident
+    hand-off.  One GPU."""
+    cfg = synth.CONFIGS[WORKLOAD]
+    pairs = args.pairs or cfg["pairs"]
+    N, dim = cfg["N"], 33
+    ps = [synth.make_config_pair(WORKLOAD, b) for b in range(pairs)]
+    descs = [synth.make_descriptors(p, dim, seed=b) for b, p in enumerate(ps)]
+    offs = np.arange(pairs + 1, dtype=np.int64) * N
+    lib = load_library()
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    reg = Registrar(lib=lib, device=dev.index, stream=stream.cuda_stream, tau_compat=cfg["tau"], tau_inlier=cfg["tau"])
+    T = lambda parts: torch.from_numpy(np.ascontiguousarray(np.concatenate(parts))).to(dev)  # noqa: E731
+    d_f, d_g = T([d[0] for d in descs]), T([d[1] for d in descs])
+    d_xs, d_xd = T([p.src for p in ps]), T([p.dst for p in ps])
+    d_nn = torch.empty(pairs * N, dtype=torch.int32, device=dev)
+    d_cs = torch.empty((pairs * N, 3), dtype=torch.float32, device=dev)
+    d_cd = torch.empty((pairs * N, 3), dtype=torch.float32, device=dev)
+    d_R = torch.empty((pairs, 3, 3), dtype=torch.float32, device=dev)
+    d_t = torch.empty((pairs, 3), dtype=torch.float32, device=dev)
+    d_i = torch.empty(pairs, dtype=torch.int32, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def match():
+        reg.match_packed_ptr(d_f.data_ptr(), d_xs.data_ptr(), offs, d_g.data_ptr(), d_xd.data_ptr(), offs, dim,
+                             d_nn.data_ptr(), d_cs.data_ptr(), d_cd.data_ptr(), _abi.LOC_DEVICE)
+
+    def register():
+        reg.register_packed_ptr(d_cs.data_ptr(), d_cd.data_ptr(), offs, d_R.data_ptr(), d_t.data_ptr(), d_i.data_ptr(),
+                                _abi.LOC_DEVICE)
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
+            flush.fill_(k & 0xFF)
+            ev[k][0].record(stream)
+            fn()
+            ev[k][1].record(stream)
+        torch.cuda.synchronize(dev)
+        return [a.elapsed_time(b) for a, b in ev]
+
+    for _ in range(args.warmup):
+        match()
+        register()
+        torch.cuda.synchronize(dev)
+        reg.get("last_status")
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    launches0 = reg.get("launches")
+    ms_match = timed(match, args.steps)
+    launches = reg.get("launches") - launches0
+    ms_chain = timed(lambda: (match(), register()), args.steps)
+    clocks = sampler.stop()
+    assert reg.get("last_status") == 0
+    nn = d_nn.cpu().numpy().reshape(pairs, N)
+    inl_found = float(np.mean([(nn[b][ps[b].inlier_idx] == ps[b].inlier_idx).mean() for b in range(pairs)]))
+    R_chk, t_chk = d_R.cpu().numpy(), d_t.cpu().numpy()
+    ok = sum(1 for b in range(pairs)
+             if (lambda e: e[0] < np.deg2rad(5.0) and e[1] < 1.5 * cfg["tau"])(synth.pose_error(R_chk[b], t_chk[b], ps[b].R_gt, ps[b].t_gt)))
+    # stage times
+    reg.set("stage_timing", 1)
+    for _ in range(args.steps):
+        match()
+    torch.cuda.synchronize(dev)
+    stage_us = {s: reg.get(f"stage_us_{s}") / args.steps for s in ("match_prep", "match_sweep", "match_exact")}
+    reg.set("stage_timing", 0)
+    # the exhaustive CUDA-core scan of the same batch (the library's own alternative path), on a sample
+    reg.set("match_path", 0)
+    small = min(pairs, 16)
+    offs_s = offs[: small + 1]
+
+    def match_small():
+        reg.match_packed_ptr(d_f.data_ptr(), d_xs.data_ptr(), offs_s, d_g.data_ptr(), d_xd.data_ptr(), offs_s, dim,
+                             d_nn.data_ptr(), d_cs.data_ptr(), d_cd.data_ptr(), _abi.LOC_DEVICE)
+    match_small()
+    torch.cuda.synchronize(dev)
+    ms_scan = timed(match_small, 3)
+    nn_scan = d_nn.cpu().numpy()[: small * N].reshape(small, N)
+    same = bool((nn_scan == nn[:small]).all())
+    reg.set("match_path", 1)
+    # end to end: host descriptors in, correspondences out
+    h = [torch.from_numpy(np.ascontiguousarray(np.concatenate(x))).pin_memory()
+         for x in ([d[0] for d in descs], [p.src for p in ps], [d[1] for d in descs], [p.dst for p in ps])]
+    h_nn = torch.empty(pairs * N, dtype=torch.int32).pin_memory()
+    h_cs = torch.empty((pairs * N, 3), dtype=torch.float32).pin_memory()
+    h_cd = torch.empty((pairs * N, 3), dtype=torch.float32).pin_memory()
+
+    def match_host():
+        reg.match_packed_ptr(h[0].data_ptr(), h[1].data_ptr(), offs, h[2].data_ptr(), h[3].data_ptr(), offs, dim,
+                             h_nn.data_ptr(), h_cs.data_ptr(), h_cd.data_ptr(), _abi.LOC_HOST)
+    match_host()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        match_host()
+    e2e = pairs * args.steps / (time.perf_counter() - t0)
+    # CPU baseline: the oracle's brute force on a bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        ol = load_oracle(omp=True)
+        with Registrar(lib=ol) as o:
+            o.set("threads", os.cpu_count() or 1)
+            k = min(pairs, 4)
+            t0 = time.perf_counter()
+            nn_o, _, _, _ = o.match_batch([d[0] for d in descs[:k]], [p.src for p in ps[:k]], [d[1] for d in descs[:k]],
+                                          [p.dst for p in ps[:k]])
+            dt = time.perf_counter() - t0
+            cpu = {"value": k / dt, "unit": "pairs matched/s", "cores": o.get("threads"), "kind": "port",
+                   "sample": f"first {k} pairs, from-paper oracle brute force (fp32 chain), OpenMP build",
+                   "indices_match_gpu": bool((nn_o.reshape(k, N) == nn[:k]).all())}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    kprime = ((3 * dim + 3 + 15) // 16) * 16
+    flop_pair = 2.0 * N * N * kprime                # executed: bf16x3 split operands, K = 3 dim + 3 padded to 16
+    sweep_us = stage_us["match_sweep"]
+    achieved = flop_pair * pairs / (sweep_us * 1e-6) / 1e12
+    bf16 = peaks.get("bf16_tflops_sustained") or 2250.0
+    value = pairs * args.steps / (sum(ms_match) * 1e-3)
+    line = {
+        "metric": f"descriptor matchings/sec at {N} x {N} keypoints, {dim}-D", "value": value, "unit": "pairs matched/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms_match) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 search, f32 decision",
+        "data": "synthetic",
+        "config": {"workload": f"front end of {WORKLOAD}: {pairs} pairs x ({N} source, {N} target) keypoints, {dim}-D FPFH-like "
+                               "descriptors (synth.make_descriptors)", "stage": "match (SURVEY.md 8f-1)",
+                   "l2": "512 MB flush write between timed steps"},
+        "e2e": {"value": e2e, "unit": "pairs matched/s", "h2d_bytes_per_step": int(sum(x.numel() * 4 for x in h)),
+                "d2h_bytes_per_step": int(pairs * N * 28)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {
+            "kernel": "match_mma_kernel (tcgen05 kind::f16, bf16 x bf16 -> f32 in TMEM, M128 N256, candidate epilogue)",
+            "bound": "tensor", "achieved": achieved, "peak": bf16, "unit": "TFLOP/s", "frac": achieved / bf16, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
+            "note": "K is only 112: a tile is 7 MMAs against 32 768 accumulator values read back and compared, so the "
+                    "kernel is bound by the epilogue (tcgen05.ld + 2 instructions per value), not by the tensor pipe; "
+                    "`epilogue` relates the compared values to the FP32/ALU lane rate",
+            "epilogue": {"values_per_s": float(N) * N * pairs / (sweep_us * 1e-6),
+                         "frac_of_lane_rate_at_3_instr": 3.0 * N * N * pairs / (sweep_us * 1e-6) / fp32_lane_rate(clocks.get("sm_mhz") or 1965.0)},
+            "stage_us_per_step": stage_us, "executed_flop_per_pair": flop_pair,
+        },
+        "cpu_baseline": cpu,
+        "exhaustive_cuda_core_scan": {"pairs_per_s": small * 3 / (sum(ms_scan) * 1e-3), "sample_pairs": small,
+                                      "same_indices": same, "speedup_of_tensor_path": value / (small * 3 / (sum(ms_scan) * 1e-3))},
+        "chain_match_then_register": {"registrations_per_s": pairs * args.steps / (sum(ms_chain) * 1e-3),
+                                      "ms_per_step": sum(ms_chain) / args.steps, "recall_vs_ground_truth": ok / pairs,
+                                      "what": "descriptors -> correspondences -> (R, t), device-resident hand-off"},
+        "inliers_matched_to_true_partner": inl_found,
+    }
+    emit(line)
+    reg.close()
+
+
 def run_single_sharded(args, rank, local_rank, world, emit, torch, dist, dev):
     """cfg5: one N = 50 000 pair through sac_cot_register_sharded (collectives inside the library)."""
     cfg = synth.CONFIGS[WORKLOAD]
@@ -762,6 +915,8 @@ def main():
     ap.add_argument("--tile-runs", type=int, default=-1, help="experiments only (library knob tile_runs)")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(synth.CONFIGS),
                     help="synthetic config (default: the headline config, BASELINE.json configs[1])")
+    ap.add_argument("--stage", default="register", choices=["register", "match"],
+                    help="register = the hot path (default); match = the descriptor-matching front end on the workload's shape")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
@@ -795,7 +950,9 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if world == 1 and args.gpus > 1:
+    if args.stage == "match":
+        run_match_bench(args, emit, torch, dev)
+    elif world == 1 and args.gpus > 1:
         if torch.cuda.device_count() < args.gpus:
             raise SystemExit(f"bench.py: --gpus {args.gpus} without torchrun needs that many visible devices")
         run_group(args, emit, torch)

@@ -249,6 +249,7 @@ struct sac_cot_ctx {
   size_t h_match_bytes = 0;
   cudaEvent_t match_uploaded = nullptr;
   std::vector<int64_t> match_sig;     // shapes the resident pair table was built for
+  int match_dbg = 0;                  // experiments: the sweep kernel prints its barrier wait cycles (CTA 0)
   int match_path = 1;                 // 1: tensor-core sweep + exact decision (dim <= kMatchMaxDim); 0: exhaustive exact scan
 
   // sharded single pair with in-library collectives
@@ -1049,6 +1050,7 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     ctx->tile_runs = value != 0;
     return SAC_COT_OK;
   }
+  if (!std::strcmp(name, "match_dbg")) { ctx->match_dbg = static_cast<int>(value); return SAC_COT_OK; }
   if (!std::strcmp(name, "match_path")) {
     if (value < 0 || value > 1) return SAC_COT_E_UNSUPPORTED;
     ctx->match_path = static_cast<int>(value);
@@ -1258,7 +1260,7 @@ int run_match(sac_cot_ctx* ctx, const float* desc_src, const float* xyz_src, con
   }
   const size_t o_norm = tensor ? take(sizeof(float) * norm_rows) : 0;
   const size_t o_img = tensor ? take(img_bytes) : 0;
-  const size_t o_cand = tensor ? take(sizeof(int32_t) * kMatchCand * tot_s) : 0;
+  const size_t o_cand = tensor ? take(sizeof(int32_t) * kMatchUnion * tot_s) : 0;
   const size_t o_cnt = tensor ? take(sizeof(int32_t) * tot_s) : 0;
   const size_t o_ds = host ? take(sizeof(float) * dim * tot_s) : 0;
   const size_t o_dd = host ? take(sizeof(float) * dim * tot_d) : 0;
@@ -1357,7 +1359,7 @@ int run_match(sac_cot_ctx* ctx, const float* desc_src, const float* xyz_src, con
     KL_TRY(launch_match_prep(lc, d_tab, B, max_d_tiles * kMatchTileN, dd, 1, dim, d_img, d_norm, d_bmax));
     span_end(ST_MATCH_PREP);
     span_begin();
-    KL_TRY(launch_match_mma(lc, d_tab, B, max_s_tiles, dim, d_img, d_norm, d_bmax, d_cand, d_cnt));
+    KL_TRY(launch_match_mma(lc, d_tab, B, max_s_tiles, dim, d_img, d_norm, d_bmax, d_cand, d_cnt, ctx->match_dbg));
     span_end(ST_MATCH_SWEEP);
   }
   span_begin();

@@ -243,14 +243,15 @@ struct MatchPair {
 constexpr int kMatchTileM = 128;    // source rows per CTA (TMEM lanes)
 constexpr int kMatchTileN = 256;    // target rows per tile (TMEM columns of one accumulator)
 constexpr int kMatchMaxDim = 40;    // widest descriptor the tensor-core sweep takes (K = 3 dim + 3 <= 128); wider ones are scanned exhaustively
-constexpr int kMatchCand = 8;       // candidate columns kept per source row
+constexpr int kMatchCand = 8;       // candidate columns one epilogue thread keeps (four threads sweep a row)
+constexpr int kMatchUnion = 16;     // candidate columns kept per source row (union of the four lists)
 int match_chunks(int dim);          // 16-byte K chunks per operand row
 int match_configure();
 int launch_match_prep(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_tiles_rows, const float* d_desc,
                       int side, int dim, unsigned char* d_img, float* d_norms, uint32_t* d_bmax);
 int launch_match_mma(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_s_tiles, int dim,
                      const unsigned char* d_img, const float* d_norms, const uint32_t* d_bmax, int32_t* d_cand,
-                     int32_t* d_cand_cnt);
+                     int32_t* d_cand_cnt, int dbg);
 int launch_match_exact(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_ns, const float* d_desc_src,
                        const float* d_desc_dst, const float* d_xyz_src, const float* d_xyz_dst, int dim,
                        const int32_t* d_cand, const int32_t* d_cand_cnt, int32_t* d_nn, float* d_corr_src,

@@ -30,12 +30,12 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
 
 namespace saccot {
 
 namespace {
 
-constexpr int kMatchThreads = 160;                   // warps 0-3 epilogue (128 rows), warp 4 producer / MMA issuer
 constexpr int kStagesB = 3;                           // most B stages (wide descriptors get 2: shared-memory budget)
 constexpr float kHugeNorm = 1.0e38f;                 // |g|^2 / 2 of a pad row: its C is -1e38, never a candidate
 constexpr float kMarginRel = 1.0f / 4096.0f;         // 2^-12, in units of C (see the header comment)
@@ -146,12 +146,28 @@ __global__ void __launch_bounds__(256) match_prep_kernel(const MatchPair* __rest
 
 // ------------------------------------------------------------------------------------------
 // 2. tensor-core sweep.  grid (max source tiles, pairs).
+//    Warps 0-15: epilogue.  Warp w reads TMEM lanes 32 (w % 4) .. + 31 (the rows a warp may touch are fixed by its
+//    index modulo 4) and the column block w / 4 (64 of the tile's 256 columns): a row is swept by four threads, each
+//    with its own running best and short list — a thread's list holds everything within the margin of ITS best, which
+//    is at most the row's best, so the union of the four lists holds everything within the margin of the row's best.
+//    Per 32 columns a thread takes the maximum (FMNMX3 tree) and compares it with its threshold; only then does it
+//    look at the individual values (predicated scan, inline).  With 32 rows per warp SOME lane sets a new record in
+//    most steps, so that scan must be cheap: two earlier versions — the scan through a local-memory array in an
+//    out-of-line function, and one warp per scheduler — ran at 7-10 k cycles per tile against 950 for the tile's
+//    MMAs (in-kernel cycle counters, `match_dbg`).
+//    Warp 16: producer + MMA issuer (one lane).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const MatchPair* __restrict__ pairs,
-                                                                     const unsigned char* __restrict__ img,
-                                                                     const float* __restrict__ norms,
-                                                                     const uint32_t* __restrict__ bmax, int chunks, int S,
-                                                                     int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
+constexpr int kEpiBlocks = 4;                               // column blocks of a tile = epilogue warps per lane quadrant
+constexpr int kEpiCols = kMatchTileN / kEpiBlocks;          // 64
+constexpr int kMatchEpiThreads = kMatchTileM * kEpiBlocks;  // 512
+constexpr int kMatchThreadsAll = kMatchEpiThreads + 32;     // 544
+
+__global__ void __launch_bounds__(kMatchThreadsAll, 1) match_mma_kernel(const MatchPair* __restrict__ pairs,
+                                                                        const unsigned char* __restrict__ img,
+                                                                        const float* __restrict__ norms,
+                                                                        const uint32_t* __restrict__ bmax, int chunks, int S,
+                                                                        int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt,
+                                                                        int dbg) {
   const MatchPair mp = pairs[blockIdx.y];
   const int st = blockIdx.x;
   if (st >= mp.s_tiles) return;
@@ -159,16 +175,18 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const Match
   const int a_bytes = kMatchTileM * chunks * 16, b_bytes = kMatchTileN * chunks * 16;
   unsigned char* sA = smem;
   unsigned char* sB = smem + a_bytes;                                      // S stages
-  int32_t* lists = reinterpret_cast<int32_t*>(sB + S * b_bytes);           // [128][kMatchCand]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kMatchTileM * kMatchCand);
+  int32_t* lists = reinterpret_cast<int32_t*>(sB + S * b_bytes);           // [512 threads][kMatchCand]
+  int32_t* counts = lists + kMatchEpiThreads * kMatchCand;                 // [512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(counts + kMatchEpiThreads);
   uint64_t* a_full = bars;                 // A image landed
   uint64_t* full = bars + 1;               // [3] B stage landed
   uint64_t* stage_free = full + kStagesB;  // [3] MMAs that read the stage have completed
   uint64_t* mma_done = stage_free + kStagesB;  // [2] accumulator complete
-  uint64_t* acc_free = mma_done + 2;       // [2] epilogue has drained the accumulator (4 warps arrive)
+  uint64_t* acc_free = mma_done + 2;       // [2] epilogue has drained the accumulator (16 warps arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kProdWarp = kMatchEpiThreads / 32;
   if (tid == 0) {
     mbar_init(a_full, 1);
     for (int s = 0; s < kStagesB; ++s) {
@@ -177,11 +195,11 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const Match
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&mma_done[b], 1);
-      mbar_init(&acc_free[b], 4);
+      mbar_init(&acc_free[b], kProdWarp);
     }
     mbar_fence_init();
   }
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -193,7 +211,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const Match
   const unsigned char* gA = img + mp.s_img + static_cast<size_t>(st) * a_bytes;
   const unsigned char* gB = img + mp.d_img;
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     // ================================ producer + MMA issuer (one lane) ================================
     if (lane == 0) {
       // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = 256, M = 128
@@ -206,12 +224,19 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const Match
         mbar_arrive_expect_tx(&full[n], static_cast<uint32_t>(b_bytes));
         bulk_g2s(sB + n * b_bytes, gB + static_cast<size_t>(n) * b_bytes, static_cast<uint32_t>(b_bytes), &full[n]);
       }
+      long long w_a = 0, w_full = 0, w_acc = 0, w_stage = 0;  // dbg: cycles waited on each barrier
+      const long long t_begin = clock64();
       match_wait(a_full, 0u);
+      w_a = clock64() - t_begin;
       const uint64_t dA0 = match_desc(smem_u32(sA), sbo);
       for (int n = 0; n < T; ++n) {
         const int s = n % S, b = n & 1;
+        long long tq = clock64();
         match_wait(&full[s], static_cast<uint32_t>((n / S) & 1));
+        w_full += clock64() - tq;
+        tq = clock64();
         if (n >= 2) match_wait(&acc_free[b], static_cast<uint32_t>(((n >> 1) - 1) & 1));
+        w_acc += clock64() - tq;
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint64_t dB0 = match_desc(smem_u32(sB + s * b_bytes), sbo);
         for (int k = 0; k < chunks / 2; ++k) {  // K = 16 per instruction = two 16-byte chunks
@@ -228,48 +253,74 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const Match
         // tile n + 2 goes into the stage tile n + 2 - S used, as soon as the MMAs that read it have completed
         if (n + 2 < T) {
           const int s2 = (n + 2) % S, prev = n + 2 - S;
+          const long long tq2 = clock64();
           if (prev >= 0) match_wait(&stage_free[s2], static_cast<uint32_t>((prev / S) & 1));
+          w_stage += clock64() - tq2;
           mbar_arrive_expect_tx(&full[s2], static_cast<uint32_t>(b_bytes));
           bulk_g2s(sB + s2 * b_bytes, gB + static_cast<size_t>(n + 2) * b_bytes, static_cast<uint32_t>(b_bytes), &full[s2]);
         }
       }
+      if (dbg && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("match producer: tiles %d total %lld wait_A %lld wait_full %lld wait_acc_free %lld wait_stage_free %lld\n", T,
+               clock64() - t_begin, w_a, w_full, w_acc, w_stage);
     }
   } else {
-    // ================================ epilogue: thread = source row = TMEM lane ================================
-    const int row = st * kMatchTileM + tid;  // row of the pair (pad rows of the last tile run along, results unused)
+    // ================================ epilogue ================================
+    const int q = warp & 3, eb = warp >> 2;          // lane quadrant, column block
+    const int trow = 32 * q + lane;                  // row of the tile = TMEM lane
+    const int row = st * kMatchTileM + trow;         // row of the pair (pad rows of the last tile run along, results unused)
     const float a_i = norms[mp.s_norm + row];
+    int32_t* lst = lists + (trow * kEpiBlocks + eb) * kMatchCand;
     const float margin = __fmul_rn(kMarginRel, __fadd_rn(a_i, __uint_as_float(bmax[blockIdx.y])));
-    int32_t* lst = lists + tid * kMatchCand;
     float best = -3.0e38f, thr = -3.0e38f;  // thr = best - margin
     int cnt = 0;
+    long long w_mma = 0, w_ld = 0;
+    const long long t_begin = clock64();
     for (int n = 0; n < T; ++n) {
       const int b = n & 1;
+      const long long tq = clock64();
       match_wait(&mma_done[b], static_cast<uint32_t>((n >> 1) & 1));
+      w_mma += clock64() - tq;
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t tbase = tmem + ((32u * warp) << 16) + static_cast<uint32_t>(kMatchTileN * b);
+      const uint32_t tbase = tmem + ((32u * q) << 16) + static_cast<uint32_t>(kMatchTileN * b + kEpiCols * eb);
       uint32_t v[2][32];
       SACCOT_MATCH_LD32(v[0], tbase);
 #pragma unroll
-      for (int u = 0; u < kMatchTileN / 32; ++u) {
+      for (int u = 0; u < kEpiCols / 32; ++u) {
+        const long long tl = dbg ? clock64() : 0;
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (u + 1 < kMatchTileN / 32) SACCOT_MATCH_LD32(v[(u + 1) & 1], tbase + 32u * (u + 1));
+        if (dbg) w_ld += clock64() - tl;
+        if (u + 1 < kEpiCols / 32) SACCOT_MATCH_LD32(v[(u + 1) & 1], tbase + 32u * (u + 1));
         const uint32_t* vv = v[u & 1];
-        // common case: nothing in these 32 columns comes within the margin of the row's best
-        float m32 = __uint_as_float(vv[0]);
+        float m0 = __uint_as_float(vv[0]), m1 = __uint_as_float(vv[1]), m2 = __uint_as_float(vv[2]), m3 = __uint_as_float(vv[3]);
 #pragma unroll
-        for (int e = 1; e < 32; ++e) m32 = fmaxf(m32, __uint_as_float(vv[e]));
-        if (m32 >= thr) {
+        for (int e = 4; e < 32; e += 8) {
+          m0 = fmaxf(fmaxf(m0, __uint_as_float(vv[e])), __uint_as_float(vv[e + 4]));
+          m1 = fmaxf(fmaxf(m1, __uint_as_float(vv[e + 1])), __uint_as_float(vv[e + 5]));
+          m2 = fmaxf(fmaxf(m2, __uint_as_float(vv[e + 2])), __uint_as_float(vv[e + 6]));
+          m3 = fmaxf(fmaxf(m3, __uint_as_float(vv[e + 3])), __uint_as_float(vv[e + 7]));
+        }
+        if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) >= thr) {
+          // some lane of the warp gets here in most steps (32 rows, each setting ~8 records per sweep), so only the
+          // group(s) of eight values (e = k mod 4) whose maximum reaches the threshold are looked at
+          const int col0 = n * kMatchTileN + kEpiCols * eb + 32 * u;
+          const float mk[4] = {m0, m1, m2, m3};
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float c = __uint_as_float(vv[e]);
-            if (c >= thr) {
-              if (c > best) {
-                if (c - margin > best) cnt = 0;  // everything listed so far is now out of range
-                best = c;
-                thr = c - margin;
+          for (int k = 0; k < 4; ++k) {
+            if (mk[k] >= thr) {
+#pragma unroll
+              for (int e = k; e < 32; e += 4) {
+                const float c = __uint_as_float(vv[e]);
+                if (c >= thr) {
+                  if (c > best) {
+                    if (c - margin > best) cnt = 0;  // everything listed so far is now out of range
+                    best = c;
+                    thr = c - margin;
+                  }
+                  if (cnt < kMatchCand) lst[cnt] = col0 + e;
+                  ++cnt;
+                }
               }
-              if (cnt < kMatchCand) lst[cnt] = n * kMatchTileN + 32 * u + e;
-              ++cnt;
             }
           }
         }
@@ -278,65 +329,120 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_mma_kernel(const Match
       __syncwarp();
       if (lane == 0) match_arrive(&acc_free[b]);
     }
-    if (row < mp.Ns) {
-      const size_t o = static_cast<size_t>(mp.cand_off) + row;
-      cand_cnt[o] = cnt;
-      for (int k = 0; k < kMatchCand; ++k) cand[o * kMatchCand + k] = k < cnt ? lst[k] : -1;
-    }
+    counts[trow * kEpiBlocks + eb] = cnt;
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
+      printf("match epilogue: total %lld wait_mma_done %lld wait_tmem_ld %lld\n", clock64() - t_begin, w_mma, w_ld);
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  if (warp == kProdWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  // union of the row's four lists (an overflowing list, or more than kMatchUnion in total, sends the row to the
+  // exhaustive scan)
+  if (tid < kMatchTileM) {
+    const int row = st * kMatchTileM + tid;
+    if (row < mp.Ns) {
+      const size_t o = static_cast<size_t>(mp.cand_off) + row;
+      int total = 0;
+      bool over = false;
+      for (int eb = 0; eb < kEpiBlocks; ++eb) {
+        const int c = counts[tid * kEpiBlocks + eb];
+        over |= c > kMatchCand;
+        for (int k = 0; k < c && k < kMatchCand; ++k) {
+          if (total < kMatchUnion) cand[o * kMatchUnion + total] = lists[(tid * kEpiBlocks + eb) * kMatchCand + k];
+          ++total;
+        }
+      }
+      for (int k = total; k < kMatchUnion; ++k) cand[o * kMatchUnion + k] = -1;
+      cand_cnt[o] = over ? kMatchUnion + 1 : total;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // 3. exact decision + gather.  One warp per source row.  cand == nullptr: every row is scanned exhaustively.
+//    A target row's chain D = fma(e, e, D) is sequential in c by specification, so one lane evaluates one target
+//    row; what the warp shares is the LOADING: target rows are fetched coalesced (a row is contiguous) into a
+//    shared-memory stage, 64 columns at a time, and each lane then runs its chain from there.  (Per-lane global
+//    loads, the first version, exposed one L2 round trip per element: 260 us for a single 5000-row pair.)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float match_dist(const float* __restrict__ f, const float* __restrict__ g, int dim) {
-  float D = 0.0f;
-  for (int c = 0; c < dim; ++c) {
-    const float e = __fsub_rn(f[c], g[c]);
-    D = __fmaf_rn(e, e, D);
-  }
-  return D;
-}
+constexpr int kExactWarps = 8;
+constexpr int kExactCols = 64;                       // columns staged at a time
+constexpr int kExactPitch = kExactCols + 1;          // odd: lanes reading different rows hit different banks
+constexpr int kExactStageFloats = 32 * kExactPitch;  // 32 target rows
+static size_t match_exact_smem(int dim) { return static_cast<size_t>(kExactWarps) * (kExactStageFloats + dim) * sizeof(float); }
 
-__global__ void __launch_bounds__(256) match_exact_kernel(const MatchPair* __restrict__ pairs,
-                                                          const float* __restrict__ desc_src,
-                                                          const float* __restrict__ desc_dst,
-                                                          const float* __restrict__ xyz_src,
-                                                          const float* __restrict__ xyz_dst, int dim,
-                                                          const int32_t* __restrict__ cand,
-                                                          const int32_t* __restrict__ cand_cnt, int32_t* __restrict__ nn,
-                                                          float* __restrict__ corr_src, float* __restrict__ corr_dst) {
+__global__ void __launch_bounds__(kExactWarps * 32) match_exact_kernel(const MatchPair* __restrict__ pairs,
+                                                                       const float* __restrict__ desc_src,
+                                                                       const float* __restrict__ desc_dst,
+                                                                       const float* __restrict__ xyz_src,
+                                                                       const float* __restrict__ xyz_dst, int dim,
+                                                                       const int32_t* __restrict__ cand,
+                                                                       const int32_t* __restrict__ cand_cnt,
+                                                                       int32_t* __restrict__ nn, float* __restrict__ corr_src,
+                                                                       float* __restrict__ corr_dst) {
   const MatchPair mp = pairs[blockIdx.y];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int i = blockIdx.x * 8 + wib;
-  extern __shared__ float frow[];  // [8 warps][dim]
+  const int i = blockIdx.x * kExactWarps + wib;
+  extern __shared__ float ex_smem[];
   if (i >= mp.Ns) return;
-  float* f = frow + wib * dim;
+  float* stage = ex_smem + wib * (kExactStageFloats + dim);  // [32][kExactPitch]
+  float* f = stage + kExactStageFloats;                      // [dim]
   const float* fi = desc_src + (static_cast<size_t>(mp.s_off) + i) * dim;
   for (int c = lane; c < dim; c += 32) f[c] = fi[c];
-  __syncwarp();
   const float* G = desc_dst + static_cast<size_t>(mp.d_off) * dim;
   float bestD = __int_as_float(0x7f800000);  // +inf
   int bestJ = 0x7fffffff;
-  const int cnt = cand ? cand_cnt[mp.cand_off + i] : kMatchCand + 1;
-  if (cnt <= kMatchCand) {
-    if (lane < cnt) {
-      const int j = cand[(static_cast<size_t>(mp.cand_off) + i) * kMatchCand + lane];
-      if (j >= 0 && j < mp.Nd) {
-        bestD = match_dist(f, G + static_cast<size_t>(j) * dim, dim);
-        bestJ = j;
+  const int cnt = cand ? cand_cnt[mp.cand_off + i] : kMatchUnion + 1;
+  // lane l evaluates target row jl (-1: none); block0 >= 0: the lanes hold the consecutive rows block0 + l
+  auto evaluate = [&](int jl, int block0) {
+    float D = 0.0f;
+    for (int c0 = 0; c0 < dim; c0 += kExactCols) {
+      const int cw = min(kExactCols, dim - c0);
+      __syncwarp();  // the previous chunk has been consumed
+      if (block0 >= 0 && cw == dim) {
+        // 32 consecutive whole rows are one contiguous run: independent, fully coalesced loads
+        const int nrows = min(32, mp.Nd - block0);
+        const float* g = G + static_cast<size_t>(block0) * dim;
+        for (int t = lane; t < nrows * dim; t += 32) stage[(t / dim) * kExactPitch + t % dim] = g[t];
+      } else {
+        for (int r = 0; r < 32; ++r) {
+          const int jr = __shfl_sync(0xffffffffu, jl, r);
+          if (jr < 0) continue;  // warp-uniform
+          const float* g = G + static_cast<size_t>(jr) * dim + c0;
+          if (lane < cw) stage[r * kExactPitch + lane] = g[lane];
+          if (lane + 32 < cw) stage[r * kExactPitch + lane + 32] = g[lane + 32];
+        }
+      }
+      __syncwarp();
+      if (jl >= 0) {
+        const float* sr = stage + lane * kExactPitch;
+        for (int c = 0; c < cw; ++c) {
+          const float e = __fsub_rn(f[c0 + c], sr[c]);
+          D = __fmaf_rn(e, e, D);
+        }
       }
     }
+    return D;
+  };
+  if (cnt <= kMatchUnion) {
+    int jl = -1;
+    if (lane < cnt) {
+      jl = cand[(static_cast<size_t>(mp.cand_off) + i) * kMatchUnion + lane];
+      if (jl >= mp.Nd) jl = -1;
+    }
+    const float D = evaluate(jl, -1);
+    if (jl >= 0) {
+      bestD = D;
+      bestJ = jl;
+    }
   } else {
-    for (int j = lane; j < mp.Nd; j += 32) {  // ascending j per lane: strict < keeps the lowest j of equal distances
-      const float D = match_dist(f, G + static_cast<size_t>(j) * dim, dim);
-      if (D < bestD || bestJ == 0x7fffffff) {
+    for (int j0 = 0; j0 < mp.Nd; j0 += 32) {  // ascending j per lane: strict < keeps the lowest j of equal distances
+      const int jl = j0 + lane < mp.Nd ? j0 + lane : -1;
+      const float D = evaluate(jl, j0);
+      if (jl >= 0 && (D < bestD || bestJ == 0x7fffffff)) {
         bestD = D;
-        bestJ = j;
+        bestJ = jl;
       }
     }
   }
@@ -367,13 +473,16 @@ int match_chunks(int dim) { return ((3 * dim + 3 + 15) / 16) * 2; }  // 16-byte 
 
 int match_stages(int chunks) { return chunks <= 14 ? kStagesB : 2; }  // 3 x 64 KB stages + the A tile exceed 227 KB
 size_t match_smem_bytes(int chunks) {
-  return static_cast<size_t>(kMatchTileM + match_stages(chunks) * kMatchTileN) * chunks * 16 + kMatchTileM * kMatchCand * 4 + 16 * 8 + 16;
+  return static_cast<size_t>(kMatchTileM + match_stages(chunks) * kMatchTileN) * chunks * 16 +
+         static_cast<size_t>(kMatchEpiThreads) * (kMatchCand + 1) * 4 + 16 * 8 + 16;
 }
 
 int match_configure() {
   size_t most = 0;
   for (int dim = 1; dim <= kMatchMaxDim; ++dim) most = std::max(most, match_smem_bytes(match_chunks(dim)));
-  const cudaError_t e = cudaFuncSetAttribute(match_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(most));
+  cudaError_t e = cudaFuncSetAttribute(match_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(most));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(match_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(match_exact_smem(256)));
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
@@ -389,10 +498,10 @@ int launch_match_prep(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, 
 
 int launch_match_mma(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_s_tiles, int dim,
                      const unsigned char* d_img, const float* d_norms, const uint32_t* d_bmax, int32_t* d_cand,
-                     int32_t* d_cand_cnt) {
+                     int32_t* d_cand_cnt, int dbg) {
   const int chunks = match_chunks(dim);
-  match_mma_kernel<<<dim3(max_s_tiles, pairs), kMatchThreads, match_smem_bytes(chunks), lc.stream>>>(
-      d_pairs, d_img, d_norms, d_bmax, chunks, match_stages(chunks), d_cand, d_cand_cnt);
+  match_mma_kernel<<<dim3(max_s_tiles, pairs), kMatchThreadsAll, match_smem_bytes(chunks), lc.stream>>>(
+      d_pairs, d_img, d_norms, d_bmax, chunks, match_stages(chunks), d_cand, d_cand_cnt, dbg);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }
@@ -401,7 +510,7 @@ int launch_match_exact(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs,
                        const float* d_desc_dst, const float* d_xyz_src, const float* d_xyz_dst, int dim,
                        const int32_t* d_cand, const int32_t* d_cand_cnt, int32_t* d_nn, float* d_corr_src,
                        float* d_corr_dst) {
-  match_exact_kernel<<<dim3((max_ns + 7) / 8, pairs), 256, static_cast<size_t>(8) * dim * sizeof(float), lc.stream>>>(
+  match_exact_kernel<<<dim3((max_ns + kExactWarps - 1) / kExactWarps, pairs), kExactWarps * 32, match_exact_smem(dim), lc.stream>>>(
       d_pairs, d_desc_src, d_desc_dst, d_xyz_src, d_xyz_dst, dim, d_cand, d_cand_cnt, d_nn, d_corr_src, d_corr_dst);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
