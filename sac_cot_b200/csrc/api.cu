@@ -1262,6 +1262,7 @@ int run_match(sac_cot_ctx* ctx, const float* desc_src, const float* xyz_src, con
   const size_t o_img = tensor ? take(img_bytes) : 0;
   const size_t o_cand = tensor ? take(sizeof(int32_t) * kMatchUnion * tot_s) : 0;
   const size_t o_cnt = tensor ? take(sizeof(int32_t) * tot_s) : 0;
+  const size_t o_work = tensor ? take(sizeof(int32_t) * 2 * tot_s + 16) : 0;  // work list of the scan kernel + its counter
   const size_t o_ds = host ? take(sizeof(float) * dim * tot_s) : 0;
   const size_t o_dd = host ? take(sizeof(float) * dim * tot_d) : 0;
   const size_t o_xs = host ? take(sizeof(float) * 3 * tot_s) : 0;
@@ -1363,7 +1364,9 @@ int run_match(sac_cot_ctx* ctx, const float* desc_src, const float* xyz_src, con
     span_end(ST_MATCH_SWEEP);
   }
   span_begin();
-  KL_TRY(launch_match_exact(lc, d_tab, B, max_ns, ds, dd, xs, xd, dim, d_cand, d_cnt, k_nn, k_cs, k_cd));
+  uint32_t* d_work_count = tensor ? reinterpret_cast<uint32_t*>(base + o_work) : nullptr;
+  int32_t* d_work_list = tensor ? reinterpret_cast<int32_t*>(base + o_work + 16) : nullptr;
+  KL_TRY(launch_match_exact(lc, d_tab, B, max_ns, ds, dd, xs, xd, dim, d_cand, d_cnt, k_nn, k_cs, k_cd, d_work_list, d_work_count));
   span_end(ST_MATCH_EXACT);
   if (host) {
     CU_TRY(cudaMemcpyAsync(o_nn_p, k_nn, sizeof(int32_t) * tot_s, cudaMemcpyDeviceToHost, stream));

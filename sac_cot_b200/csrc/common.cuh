@@ -255,7 +255,7 @@ int launch_match_mma(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, i
 int launch_match_exact(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_ns, const float* d_desc_src,
                        const float* d_desc_dst, const float* d_xyz_src, const float* d_xyz_dst, int dim,
                        const int32_t* d_cand, const int32_t* d_cand_cnt, int32_t* d_nn, float* d_corr_src,
-                       float* d_corr_dst);
+                       float* d_corr_dst, int32_t* d_work_list, uint32_t* d_work_count);
 
 // kernels_hypo.cu — S4 Kabsch, S5/S6 scoring + argmax, S7 refit
 int launch_kabsch(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const float* d_soa, const int32_t* d_tri,

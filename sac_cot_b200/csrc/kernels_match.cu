@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(kMatchThreadsAll, 1) match_mma_kernel(const Ma
   unsigned char* sB = smem + a_bytes;                                      // S stages
   int32_t* lists = reinterpret_cast<int32_t*>(sB + S * b_bytes);           // [512 threads][kMatchCand]
   int32_t* counts = lists + kMatchEpiThreads * kMatchCand;                 // [512]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(counts + kMatchEpiThreads);
+  float* bests = reinterpret_cast<float*>(counts + kMatchEpiThreads);      // [512] each epilogue thread's best value
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bests + kMatchEpiThreads);
   uint64_t* a_full = bars;                 // A image landed
   uint64_t* full = bars + 1;               // [3] B stage landed
   uint64_t* stage_free = full + kStagesB;  // [3] MMAs that read the stage have completed
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(kMatchThreadsAll, 1) match_mma_kernel(const Ma
       if (lane == 0) match_arrive(&acc_free[b]);
     }
     counts[trow * kEpiBlocks + eb] = cnt;
+    bests[trow * kEpiBlocks + eb] = best;
     if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
       printf("match epilogue: total %lld wait_mma_done %lld wait_tmem_ld %lld\n", clock64() - t_begin, w_mma, w_ld);
   }
@@ -345,7 +347,12 @@ __global__ void __launch_bounds__(kMatchThreadsAll, 1) match_mma_kernel(const Ma
       const size_t o = static_cast<size_t>(mp.cand_off) + row;
       int total = 0;
       bool over = false;
+      // a list whose best lies more than the margin below the row's best holds nothing within the margin of it
+      float rb = bests[tid * kEpiBlocks];
+      for (int eb = 1; eb < kEpiBlocks; ++eb) rb = fmaxf(rb, bests[tid * kEpiBlocks + eb]);
+      const float cut = rb - __fmul_rn(kMarginRel, __fadd_rn(norms[mp.s_norm + row], __uint_as_float(bmax[blockIdx.y])));
       for (int eb = 0; eb < kEpiBlocks; ++eb) {
+        if (bests[tid * kEpiBlocks + eb] < cut) continue;
         const int c = counts[tid * kEpiBlocks + eb];
         over |= c > kMatchCand;
         for (int k = 0; k < c && k < kMatchCand; ++k) {
@@ -360,93 +367,32 @@ __global__ void __launch_bounds__(kMatchThreadsAll, 1) match_mma_kernel(const Ma
 }
 
 // ------------------------------------------------------------------------------------------
-// 3. exact decision + gather.  One warp per source row.  cand == nullptr: every row is scanned exhaustively.
-//    A target row's chain D = fma(e, e, D) is sequential in c by specification, so one lane evaluates one target
-//    row; what the warp shares is the LOADING: target rows are fetched coalesced (a row is contiguous) into a
-//    shared-memory stage, 64 columns at a time, and each lane then runs its chain from there.  (Per-lane global
-//    loads, the first version, exposed one L2 round trip per element: 260 us for a single 5000-row pair.)
+// 3. exact decision + gather.
+//    match_exact_kernel: one warp per source row; lane k evaluates the k-th listed candidate with the specified
+//    chain (D = fma(e, e, D), c ascending — sequential by specification, so one lane per target row), reading the
+//    target row straight from global memory eight independent loads at a time.  Rows whose list overflowed are
+//    appended to a work list.
+//    match_scan_kernel: the exhaustive scan, one CTA per row of the work list (or per row of the batch when there are
+//    no lists at all: descriptors too wide for the sweep, or match_path = 0).  Eight warps split the target rows;
+//    32 consecutive rows are one contiguous run, fetched coalesced into a shared-memory stage 64 columns at a time.
 // ------------------------------------------------------------------------------------------
 constexpr int kExactWarps = 8;
-constexpr int kExactCols = 64;                       // columns staged at a time
+constexpr int kExactCols = 64;                       // columns staged at a time (scan kernel)
 constexpr int kExactPitch = kExactCols + 1;          // odd: lanes reading different rows hit different banks
 constexpr int kExactStageFloats = 32 * kExactPitch;  // 32 target rows
-static size_t match_exact_smem(int dim) { return static_cast<size_t>(kExactWarps) * (kExactStageFloats + dim) * sizeof(float); }
+static size_t match_scan_smem(int dim) { return (static_cast<size_t>(kExactWarps) * kExactStageFloats + dim) * sizeof(float); }
 
-__global__ void __launch_bounds__(kExactWarps * 32) match_exact_kernel(const MatchPair* __restrict__ pairs,
-                                                                       const float* __restrict__ desc_src,
-                                                                       const float* __restrict__ desc_dst,
-                                                                       const float* __restrict__ xyz_src,
-                                                                       const float* __restrict__ xyz_dst, int dim,
-                                                                       const int32_t* __restrict__ cand,
-                                                                       const int32_t* __restrict__ cand_cnt,
-                                                                       int32_t* __restrict__ nn, float* __restrict__ corr_src,
-                                                                       float* __restrict__ corr_dst) {
-  const MatchPair mp = pairs[blockIdx.y];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int i = blockIdx.x * kExactWarps + wib;
-  extern __shared__ float ex_smem[];
-  if (i >= mp.Ns) return;
-  float* stage = ex_smem + wib * (kExactStageFloats + dim);  // [32][kExactPitch]
-  float* f = stage + kExactStageFloats;                      // [dim]
-  const float* fi = desc_src + (static_cast<size_t>(mp.s_off) + i) * dim;
-  for (int c = lane; c < dim; c += 32) f[c] = fi[c];
-  const float* G = desc_dst + static_cast<size_t>(mp.d_off) * dim;
-  float bestD = __int_as_float(0x7f800000);  // +inf
-  int bestJ = 0x7fffffff;
-  const int cnt = cand ? cand_cnt[mp.cand_off + i] : kMatchUnion + 1;
-  // lane l evaluates target row jl (-1: none); block0 >= 0: the lanes hold the consecutive rows block0 + l
-  auto evaluate = [&](int jl, int block0) {
-    float D = 0.0f;
-    for (int c0 = 0; c0 < dim; c0 += kExactCols) {
-      const int cw = min(kExactCols, dim - c0);
-      __syncwarp();  // the previous chunk has been consumed
-      if (block0 >= 0 && cw == dim) {
-        // 32 consecutive whole rows are one contiguous run: independent, fully coalesced loads
-        const int nrows = min(32, mp.Nd - block0);
-        const float* g = G + static_cast<size_t>(block0) * dim;
-        for (int t = lane; t < nrows * dim; t += 32) stage[(t / dim) * kExactPitch + t % dim] = g[t];
-      } else {
-        for (int r = 0; r < 32; ++r) {
-          const int jr = __shfl_sync(0xffffffffu, jl, r);
-          if (jr < 0) continue;  // warp-uniform
-          const float* g = G + static_cast<size_t>(jr) * dim + c0;
-          if (lane < cw) stage[r * kExactPitch + lane] = g[lane];
-          if (lane + 32 < cw) stage[r * kExactPitch + lane + 32] = g[lane + 32];
-        }
-      }
-      __syncwarp();
-      if (jl >= 0) {
-        const float* sr = stage + lane * kExactPitch;
-        for (int c = 0; c < cw; ++c) {
-          const float e = __fsub_rn(f[c0 + c], sr[c]);
-          D = __fmaf_rn(e, e, D);
-        }
-      }
-    }
-    return D;
-  };
-  if (cnt <= kMatchUnion) {
-    int jl = -1;
-    if (lane < cnt) {
-      jl = cand[(static_cast<size_t>(mp.cand_off) + i) * kMatchUnion + lane];
-      if (jl >= mp.Nd) jl = -1;
-    }
-    const float D = evaluate(jl, -1);
-    if (jl >= 0) {
-      bestD = D;
-      bestJ = jl;
-    }
-  } else {
-    for (int j0 = 0; j0 < mp.Nd; j0 += 32) {  // ascending j per lane: strict < keeps the lowest j of equal distances
-      const int jl = j0 + lane < mp.Nd ? j0 + lane : -1;
-      const float D = evaluate(jl, j0);
-      if (jl >= 0 && (D < bestD || bestJ == 0x7fffffff)) {
-        bestD = D;
-        bestJ = jl;
-      }
-    }
+__device__ __forceinline__ void match_write(const MatchPair& mp, int i, int bestJ, const float* __restrict__ xyz_src,
+                                            const float* __restrict__ xyz_dst, int32_t* __restrict__ nn,
+                                            float* __restrict__ corr_src, float* __restrict__ corr_dst, int lane) {
+  if (lane == 0) nn[mp.s_off + i] = bestJ;
+  if (lane < 3) {
+    corr_src[(static_cast<size_t>(mp.s_off) + i) * 3 + lane] = xyz_src[(static_cast<size_t>(mp.s_off) + i) * 3 + lane];
+    corr_dst[(static_cast<size_t>(mp.s_off) + i) * 3 + lane] = xyz_dst[(static_cast<size_t>(mp.d_off) + bestJ) * 3 + lane];
   }
-  // lexicographic minimum of (D, j) over the warp.  A NaN distance never wins against a number.
+}
+// lexicographic minimum of (D, j) over the warp (0x7fffffff = no entry).  A NaN distance never wins against a number.
+__device__ __forceinline__ void match_warp_min(float& bestD, int& bestJ) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float oD = __shfl_xor_sync(0xffffffffu, bestD, o);
@@ -458,11 +404,141 @@ __global__ void __launch_bounds__(kExactWarps * 32) match_exact_kernel(const Mat
       bestJ = oJ;
     }
   }
+}
+
+__global__ void __launch_bounds__(kExactWarps * 32) match_exact_kernel(const MatchPair* __restrict__ pairs,
+                                                                       const float* __restrict__ desc_src,
+                                                                       const float* __restrict__ desc_dst,
+                                                                       const float* __restrict__ xyz_src,
+                                                                       const float* __restrict__ xyz_dst, int dim,
+                                                                       const int32_t* __restrict__ cand,
+                                                                       const int32_t* __restrict__ cand_cnt,
+                                                                       int32_t* __restrict__ nn, float* __restrict__ corr_src,
+                                                                       float* __restrict__ corr_dst,
+                                                                       int32_t* __restrict__ work_list,
+                                                                       uint32_t* __restrict__ work_count) {
+  const MatchPair mp = pairs[blockIdx.y];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int i = blockIdx.x * kExactWarps + wib;
+  extern __shared__ float ex_smem[];  // [kExactWarps][dim]
+  if (i >= mp.Ns) return;
+  const int cnt = cand_cnt[mp.cand_off + i];
+  if (cnt > kMatchUnion) {  // overflowed list: the scan kernel takes the row
+    if (lane == 0) {
+      const uint32_t k = atomicAdd(work_count, 1u);
+      work_list[2 * k] = static_cast<int32_t>(blockIdx.y);
+      work_list[2 * k + 1] = i;
+    }
+    return;
+  }
+  float* f = ex_smem + wib * dim;
+  const float* fi = desc_src + (static_cast<size_t>(mp.s_off) + i) * dim;
+  for (int c = lane; c < dim; c += 32) f[c] = fi[c];
+  __syncwarp();
+  float bestD = __int_as_float(0x7f800000);  // +inf
+  int bestJ = 0x7fffffff;
+  if (lane < cnt) {
+    const int j = cand[(static_cast<size_t>(mp.cand_off) + i) * kMatchUnion + lane];
+    if (j >= 0 && j < mp.Nd) {
+      const float* g = desc_dst + (static_cast<size_t>(mp.d_off) + j) * dim;
+      float D = 0.0f;
+      int c0 = 0;
+      for (; c0 + 8 <= dim; c0 += 8) {
+        float gv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[k] = g[c0 + k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float e = __fsub_rn(f[c0 + k], gv[k]);
+          D = __fmaf_rn(e, e, D);
+        }
+      }
+      for (; c0 < dim; ++c0) {
+        const float e = __fsub_rn(f[c0], g[c0]);
+        D = __fmaf_rn(e, e, D);
+      }
+      bestD = D;
+      bestJ = j;
+    }
+  }
+  match_warp_min(bestD, bestJ);
   if (bestJ == 0x7fffffff) bestJ = 0;
-  if (lane == 0) nn[mp.s_off + i] = bestJ;
-  if (lane < 3) {
-    corr_src[(static_cast<size_t>(mp.s_off) + i) * 3 + lane] = xyz_src[(static_cast<size_t>(mp.s_off) + i) * 3 + lane];
-    corr_dst[(static_cast<size_t>(mp.s_off) + i) * 3 + lane] = xyz_dst[(static_cast<size_t>(mp.d_off) + bestJ) * 3 + lane];
+  match_write(mp, i, bestJ, xyz_src, xyz_dst, nn, corr_src, corr_dst, lane);
+}
+
+__global__ void __launch_bounds__(kExactWarps * 32) match_scan_kernel(const MatchPair* __restrict__ pairs,
+                                                                      const float* __restrict__ desc_src,
+                                                                      const float* __restrict__ desc_dst,
+                                                                      const float* __restrict__ xyz_src,
+                                                                      const float* __restrict__ xyz_dst, int dim,
+                                                                      const int32_t* __restrict__ work_list,
+                                                                      const uint32_t* __restrict__ work_count,
+                                                                      int32_t* __restrict__ nn, float* __restrict__ corr_src,
+                                                                      float* __restrict__ corr_dst) {
+  extern __shared__ float sc_smem[];  // [kExactWarps][32][kExactPitch] stages, then f[dim]
+  __shared__ float s_D[kExactWarps];
+  __shared__ int s_J[kExactWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* stage = sc_smem + wib * kExactStageFloats;
+  float* f = sc_smem + kExactWarps * kExactStageFloats;
+  const uint32_t items = work_list ? *work_count : gridDim.x * gridDim.y;
+  for (uint32_t it = work_list ? blockIdx.x : blockIdx.y * gridDim.x + blockIdx.x; it < items;
+       it += work_list ? gridDim.x : items) {
+    const int pair = work_list ? work_list[2 * it] : static_cast<int>(blockIdx.y);
+    const int i = work_list ? work_list[2 * it + 1] : static_cast<int>(blockIdx.x);
+    const MatchPair mp = pairs[pair];
+    if (i >= mp.Ns) break;  // (only without a work list: the grid spans the largest pair)
+    __syncthreads();        // the previous row's f and reduction slots have been consumed
+    const float* fi = desc_src + (static_cast<size_t>(mp.s_off) + i) * dim;
+    for (int c = threadIdx.x; c < dim; c += kExactWarps * 32) f[c] = fi[c];
+    __syncthreads();
+    const float* G = desc_dst + static_cast<size_t>(mp.d_off) * dim;
+    float bestD = __int_as_float(0x7f800000);
+    int bestJ = 0x7fffffff;
+    for (int j0 = 32 * wib; j0 < mp.Nd; j0 += 32 * kExactWarps) {  // ascending j per lane: strict < keeps the lowest j
+      const int nrows = min(32, mp.Nd - j0);
+      const int jl = lane < nrows ? j0 + lane : -1;
+      float D = 0.0f;
+      for (int c0 = 0; c0 < dim; c0 += kExactCols) {
+        const int cw = min(kExactCols, dim - c0);
+        __syncwarp();
+        if (cw == dim) {  // whole rows: one contiguous run
+          const float* g = G + static_cast<size_t>(j0) * dim;
+          for (int t = lane; t < nrows * dim; t += 32) stage[(t / dim) * kExactPitch + t % dim] = g[t];
+        } else {
+          for (int r = 0; r < nrows; ++r) {
+            const float* g = G + static_cast<size_t>(j0 + r) * dim + c0;
+            if (lane < cw) stage[r * kExactPitch + lane] = g[lane];
+            if (lane + 32 < cw) stage[r * kExactPitch + lane + 32] = g[lane + 32];
+          }
+        }
+        __syncwarp();
+        if (jl >= 0) {
+          const float* sr = stage + lane * kExactPitch;
+          for (int c = 0; c < cw; ++c) {
+            const float e = __fsub_rn(f[c0 + c], sr[c]);
+            D = __fmaf_rn(e, e, D);
+          }
+        }
+      }
+      if (jl >= 0 && (D < bestD || bestJ == 0x7fffffff)) {
+        bestD = D;
+        bestJ = jl;
+      }
+    }
+    match_warp_min(bestD, bestJ);
+    if (lane == 0) {
+      s_D[wib] = bestD;
+      s_J[wib] = bestJ;
+    }
+    __syncthreads();
+    if (wib == 0) {
+      bestD = lane < kExactWarps ? s_D[lane] : __int_as_float(0x7f800000);
+      bestJ = lane < kExactWarps ? s_J[lane] : 0x7fffffff;
+      match_warp_min(bestD, bestJ);
+      if (bestJ == 0x7fffffff) bestJ = 0;
+      match_write(mp, i, bestJ, xyz_src, xyz_dst, nn, corr_src, corr_dst, lane);
+    }
   }
 }
 
@@ -474,7 +550,7 @@ int match_chunks(int dim) { return ((3 * dim + 3 + 15) / 16) * 2; }  // 16-byte 
 int match_stages(int chunks) { return chunks <= 14 ? kStagesB : 2; }  // 3 x 64 KB stages + the A tile exceed 227 KB
 size_t match_smem_bytes(int chunks) {
   return static_cast<size_t>(kMatchTileM + match_stages(chunks) * kMatchTileN) * chunks * 16 +
-         static_cast<size_t>(kMatchEpiThreads) * (kMatchCand + 1) * 4 + 16 * 8 + 16;
+         static_cast<size_t>(kMatchEpiThreads) * (kMatchCand + 2) * 4 + 16 * 8 + 16;
 }
 
 int match_configure() {
@@ -482,7 +558,7 @@ int match_configure() {
   for (int dim = 1; dim <= kMatchMaxDim; ++dim) most = std::max(most, match_smem_bytes(match_chunks(dim)));
   cudaError_t e = cudaFuncSetAttribute(match_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(most));
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(match_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(match_exact_smem(256)));
+    e = cudaFuncSetAttribute(match_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(match_scan_smem(256)));
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
@@ -509,11 +585,26 @@ int launch_match_mma(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, i
 int launch_match_exact(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs, int max_ns, const float* d_desc_src,
                        const float* d_desc_dst, const float* d_xyz_src, const float* d_xyz_dst, int dim,
                        const int32_t* d_cand, const int32_t* d_cand_cnt, int32_t* d_nn, float* d_corr_src,
-                       float* d_corr_dst) {
-  match_exact_kernel<<<dim3((max_ns + kExactWarps - 1) / kExactWarps, pairs), kExactWarps * 32, match_exact_smem(dim), lc.stream>>>(
-      d_pairs, d_desc_src, d_desc_dst, d_xyz_src, d_xyz_dst, dim, d_cand, d_cand_cnt, d_nn, d_corr_src, d_corr_dst);
-  const cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+                       float* d_corr_dst, int32_t* d_work_list, uint32_t* d_work_count) {
+  if (d_cand == nullptr) {  // no lists: every row is scanned
+    match_scan_kernel<<<dim3(max_ns, pairs), kExactWarps * 32, match_scan_smem(dim), lc.stream>>>(
+        d_pairs, d_desc_src, d_desc_dst, d_xyz_src, d_xyz_dst, dim, nullptr, nullptr, d_nn, d_corr_src, d_corr_dst);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -static_cast<int>(e);
+  }
+  cudaError_t e = cudaMemsetAsync(d_work_count, 0, sizeof(uint32_t), lc.stream);
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  match_exact_kernel<<<dim3((max_ns + kExactWarps - 1) / kExactWarps, pairs), kExactWarps * 32,
+                       static_cast<size_t>(kExactWarps) * dim * sizeof(float), lc.stream>>>(
+      d_pairs, d_desc_src, d_desc_dst, d_xyz_src, d_xyz_dst, dim, d_cand, d_cand_cnt, d_nn, d_corr_src, d_corr_dst, d_work_list,
+      d_work_count);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  // rows whose list overflowed (rare: near-identical descriptors); the CTAs find the count on the device
+  match_scan_kernel<<<dim3(2 * lc.sm_count, 1), kExactWarps * 32, match_scan_smem(dim), lc.stream>>>(
+      d_pairs, d_desc_src, d_desc_dst, d_xyz_src, d_xyz_dst, dim, d_work_list, d_work_count, d_nn, d_corr_src, d_corr_dst);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 2 : -static_cast<int>(e);
 }
 
 }  // namespace saccot

@@ -101,7 +101,7 @@ def test_ragged_batch_and_device_resident_handoff(gpu_lib, oracle):
         np.testing.assert_array_equal(offs, offs_g)
         np.testing.assert_array_equal(ng, no)
         np.testing.assert_array_equal(cdg, cdo)
-        assert g.get("launches") == 4   # two operand-image kernels, the tensor-core sweep, the exact decision
+        assert g.get("launches") == 5   # two operand-image kernels, the tensor-core sweep, the exact decision, the (idle) scan
     # device-resident: descriptors and keypoints in HBM, correspondences stay there
     dev = torch.device("cuda", 0)
     stream = torch.cuda.current_stream(dev)
