@@ -867,31 +867,95 @@ __device__ __forceinline__ int theta_sample(const PairDesc& d, const uint32_t* _
   }
   if (t == 0) *s_nts = 0;
   __syncthreads();
-  // 2. largest degree threshold that still leaves >= S nodes
-  int lo = 0, hi = 256;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (theta_block_count([&](int k) { return deg[k] >= mid; }, d.N, s_cnt) >= S) lo = mid;
-    else hi = mid;
-  }
-  const int thr = lo;
-  const int n_above = theta_block_count([&](int k) { return deg[k] > thr; }, d.N, s_cnt);
-  // 3. the S sample nodes in index order: every node above the threshold, then ties until S are taken
+  // 2. largest degree threshold that still leaves >= S nodes, and the number of nodes above it: one histogram
+  //    pass over the (saturated, 8-bit) proxy degrees and a suffix scan by one warp.  (Eight block-wide counting
+  //    passes of a binary search before: ~15 us of a single N = 5000 pair.)
+  __shared__ int s_dh[256];
+  __shared__ int s_thr, s_above;
+  if (t < 256) s_dh[t] = 0;
+  __syncthreads();
+  for (int k = t; k < d.N; k += 1024) atomicAdd(&s_dh[deg[k]], 1);
+  __syncthreads();
   if (warp == 0) {
-    int nsel = 0, quota = S - n_above;
-    for (int i0 = 0; i0 < d.N && nsel < S; i0 += 32) {
-      const int i = i0 + lane;
-      const int dg = i < d.N ? deg[i] : -1;
-      const bool tie = dg == thr;
-      const unsigned tmask = __ballot_sync(0xffffffffu, tie);
-      const int tie_rank = __popc(tmask & ((1u << lane) - 1u));
-      const bool take = dg > thr || (tie && tie_rank < quota);
-      const unsigned smask = __ballot_sync(0xffffffffu, take);
-      if (take) nodes[nsel + __popc(smask & ((1u << lane) - 1u))] = i;
-      nsel += __popc(smask);
-      quota -= min(quota, __popc(tmask));
+    // lane l owns degrees 8 l .. 8 l + 7; suffix sums from the top
+    int mine[8], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mine[k] = s_dh[8 * lane + k];
+      tot += mine[k];
     }
-    if (lane == 0) *s_nsel = nsel;
+    int above = 0;  // nodes with a degree in a higher lane's range
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_down_sync(0xffffffffu, tot, o);
+      if (lane + o < 32) tot += u;
+    }
+    above = tot;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) above -= mine[k];
+    // the threshold lies in the one lane where the suffix count crosses S
+    if (above < S && tot >= S) {
+      int cum = above;
+      for (int k = 7; k >= 0; --k) {
+        if (cum + mine[k] >= S) {
+          s_thr = 8 * lane + k;
+          s_above = cum;
+          break;
+        }
+        cum += mine[k];
+      }
+    }
+  }
+  __syncthreads();
+  const int thr = s_thr;
+  const int n_above = s_above;
+  // 3. the S sample nodes in index order: every node above the threshold, then ties until S are taken.  The slot of
+  //    a selected node = nodes above the threshold before it + min(ties before it, quota).  Every warp takes a
+  //    contiguous segment of the rows: counts first, then (after a prefix over the warps) the slots.  (One warp
+  //    walking all N rows was ~100 us of the single N = 50 000 pair's 380.)
+  {
+    __shared__ int s_wa[32], s_wt[32];
+    const int seg = ((d.N + 31) / 32 + 31) & ~31;  // rows per warp, a multiple of 32
+    const int r0 = warp * seg, r1 = min(d.N, r0 + seg);
+    int na = 0, nt = 0;
+    for (int i0 = r0; i0 < r1; i0 += 32) {
+      const int i = i0 + lane;
+      const int dg = i < r1 ? deg[i] : -1;
+      na += __popc(__ballot_sync(0xffffffffu, dg > thr));
+      nt += __popc(__ballot_sync(0xffffffffu, dg == thr));
+    }
+    if (lane == 0) {
+      s_wa[warp] = na;
+      s_wt[warp] = nt;
+    }
+    __syncthreads();
+    int a_before = 0, t_before = 0;
+    for (int w = 0; w < warp; ++w) {
+      a_before += s_wa[w];
+      t_before += s_wt[w];
+    }
+    const int quota = S - n_above;  // ties to take (>= 0 by the choice of thr)
+    for (int i0 = r0; i0 < r1; i0 += 32) {
+      const int i = i0 + lane;
+      const int dg = i < r1 ? deg[i] : -1;
+      const unsigned amask = __ballot_sync(0xffffffffu, dg > thr);
+      const unsigned tmask = __ballot_sync(0xffffffffu, dg == thr);
+      const unsigned below = (1u << lane) - 1u;
+      const int a_here = a_before + __popc(amask & below), t_here = t_before + __popc(tmask & below);
+      const bool take = dg > thr || (dg == thr && t_here < quota);
+      const int slot = a_here + min(t_here, quota);
+      if (take && slot < kThetaNodes) nodes[slot] = i;
+      a_before += __popc(amask);
+      t_before += __popc(tmask);
+    }
+    if (t == 0) {
+      int ta = 0, tt = 0;
+      for (int w = 0; w < 32; ++w) {
+        ta += s_wa[w];
+        tt += s_wt[w];
+      }
+      *s_nsel = min(kThetaNodes, ta + min(tt, quota));
+    }
   }
   __syncthreads();
   const int nsel = *s_nsel;
@@ -961,18 +1025,49 @@ __device__ __forceinline__ void theta_count_chunk(const PairDesc& d, const uint3
 }
 
 // Step 5: theta = K_e-th largest sample count (0 if the sample holds fewer than K_e edges); ts entries are T + 1,
-// 0 = no edge.  bit 31: certified by a fat sample, the triangle kernel need not try to raise it.
+// 0 = no edge.  Two histogram passes (high byte, then the low byte inside the bucket that holds the K_e-th value)
+// instead of a 16-step binary search over the value range.  bit 31: certified by a fat sample, the triangle kernel
+// need not try to raise it.
 __device__ __forceinline__ uint32_t theta_pick(const unsigned short* ts, int nts, int Ke, int* s_cnt) {
+  __shared__ int s_h[256];
+  __shared__ int s_hi, s_need;
+  const int t = threadIdx.x;
   uint32_t th = 0;
-  if (nts >= Ke) {
-    int l2 = 0, h2 = 65535;
-    while (h2 - l2 > 1) {
-      const int mid = (l2 + h2) >> 1;
-      if (theta_block_count([&](int k) { return ts[k] > mid; }, kThetaSamples, s_cnt) >= Ke) l2 = mid;
-      else h2 = mid;
+  if (nts >= Ke) {  // block-uniform
+    // which of the 256 steps selects the bucket: thread 0 walks the histogram from the top
+    auto pick_bucket = [&](int need) {
+      __syncthreads();
+      if (t == 0) {
+        int cum = 0, b = 255;
+        for (; b > 0; --b) {
+          if (cum + s_h[b] >= need) break;
+          cum += s_h[b];
+        }
+        s_hi = b;
+        s_need = need - cum;  // still needed inside bucket b
+      }
+      __syncthreads();
+    };
+    if (t < 256) s_h[t] = 0;
+    __syncthreads();
+    for (int k = t; k < kThetaSamples; k += 1024) {
+      const unsigned int v = ts[k];
+      if (v) atomicAdd(&s_h[v >> 8], 1);
     }
-    th = static_cast<uint32_t>(l2);
+    pick_bucket(Ke);
+    const int hi = s_hi, need = s_need;
+    __syncthreads();
+    if (t < 256) s_h[t] = 0;
+    __syncthreads();
+    for (int k = t; k < kThetaSamples; k += 1024) {
+      const unsigned int v = ts[k];
+      if (v && static_cast<int>(v >> 8) == hi) atomicAdd(&s_h[v & 255u], 1);
+    }
+    pick_bucket(need);
+    // the K_e-th largest entry is T + 1 = 256 hi + lo; theta = T
+    th = static_cast<uint32_t>(256 * hi + s_hi) - 1u;
   }
+  (void)s_cnt;
   return th | (nts >= 4 * Ke ? 0x80000000u : 0u);
 }
 
