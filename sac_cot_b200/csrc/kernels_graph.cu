@@ -63,10 +63,11 @@ int launch_pack_soa(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int 
 //     S = x + y;  U = S - tau2f;  Q = U*U - 4*(x*y);  Theta = (S*S) * 2^-19
 // with tau2f = RN(tau*tau).  In real arithmetic  Q* = ((a-b)^2 - tau^2)((a+b)^2 - tau^2), a = sqrt x,
 // b = sqrt y, so for (a+b) > 2 tau its sign is the sign of |a-b| - tau.  Error analysis (DESIGN.md
-// "S1 exact filter"): if S > lo = max(4 tau2f, 2^-50) then |Q - Q*| <= 7.6u (x+y)^2, and whenever
+// "S1 exact filter"): if S > lo = max(4 tau2f, 2^-50) then |Q - Q*| <= 7.6u (x+y)^2 (+ 8u (x+y)^2 because the
+// filter forms x and y with fused multiply-adds, within 4u of the specified values), and whenever
 // the literal predicate could disagree with sign(|a-b| - tau) (rounding of the two square roots
 // and of their difference, at most 2.1u (a+b) in total) one has |Q*| <= 8.5u (x+y)^2.  Hence
-//     |Q| > Theta  (Theta >= 31.9u (x+y)^2)   ==>   P(x, y) == (Q < 0)          exactly.
+//     |Q| > Theta  (Theta >= 31.9u (x+y)^2 > 7.6u + 8u + 8.5u)   ==>   P(x, y) == (Q < 0)          exactly.
 // Everything else — the ~1e-4 fraction of pairs inside the band, tiny/huge/NaN inputs, tau so
 // large that lo overflows — takes the literal sqrt.rn evaluation.  The result is bit-identical to
 // the oracle's for every input; tests/test_gpu_parity.py has adversarial near-threshold sets.
@@ -101,14 +102,12 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   return r;
 }
 
-// (a*a + b*b) + c*c per packed lane with individually rounded operations
-__device__ __forceinline__ f32x2 sum_sq(f32x2 a, f32x2 b, f32x2 c) {
-  float aa0, aa1, bb0, bb1, cc0, cc1;
-  unpack2(mul2(a, a), aa0, aa1);
-  unpack2(mul2(b, b), bb0, bb1);
-  unpack2(mul2(c, c), cc0, cc1);
-  return pack2(__fadd_rn(__fadd_rn(aa0, bb0), cc0), __fadd_rn(__fadd_rn(aa1, bb1), cc1));
-}
+// Squared length for the FILTER only: a*a, then two fused multiply-adds (3 packed instructions instead of 3 packed
+// multiplies and 4 scalar additions: the kernel is bound by the FP32 pipe, 23 -> 19 pipe cycles per pair test).  It
+// differs from the specified sum ((a*a + b*b) + c*c, every operation rounded) by at most 4u relative; the filter's
+// threshold Theta absorbs that, and whatever the filter is not sure about is decided by
+// compat_literal4, which computes the SPECIFIED squared lengths itself.
+__device__ __forceinline__ f32x2 sum_sq_fused(f32x2 a, f32x2 b, f32x2 c) { return fma2(c, c, fma2(b, b, mul2(a, a))); }
 
 // Literal evaluation of the specified predicate for the four columns c..c+3 of the staged tile:
 // the rare fallback of the filter.  Out of line and self-contained (recomputes the squared lengths
@@ -213,11 +212,9 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
         f32x2 col[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) col[k] = h == 0 ? pack2(cj[k].x, cj[k].y) : pack2(cj[k].z, cj[k].w);
-        // squared lengths, op order of the specification:  (a*a + b*b) + c*c.  Differences and
-        // squares are packed; the two additions are scalar add.rn.f32, which ptxas never contracts
-        // (it does fuse mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would break the rounding spec).
-        const f32x2 x = sum_sq(sub2(ri[0], col[0]), sub2(ri[1], col[1]), sub2(ri[2], col[2]));
-        const f32x2 y = sum_sq(sub2(ri[3], col[3]), sub2(ri[4], col[4]), sub2(ri[5], col[5]));
+        // squared lengths for the filter (fused; within 4u of the specified (a*a + b*b) + c*c)
+        const f32x2 x = sum_sq_fused(sub2(ri[0], col[0]), sub2(ri[1], col[1]), sub2(ri[2], col[2]));
+        const f32x2 y = sum_sq_fused(sub2(ri[3], col[3]), sub2(ri[4], col[4]), sub2(ri[5], col[5]));
         // exact filter: trust sign(Q) iff |Q| > Theta and S > lo
         const f32x2 S = add2(x, y);
         const f32x2 U = add2(S, ntau2);

@@ -63,6 +63,26 @@ def test_sure_verdicts_equal_literal_predicate(tau, scale):
     assert sure[big].mean() > 0.995
 
 
+@pytest.mark.parametrize("tau,scale", [(0.1, 5.0), (0.6, 90.0), (0.01, 0.3), (1e-3, 1e3)])
+def test_filter_on_fused_squared_lengths_still_agrees_with_the_literal_predicate(tau, scale):
+    """The kernel's filter forms x and y with fused multiply-adds (within 4u of the specified values, i.e. at most two
+    ulps away); the literal predicate — and the fallback — use the specified ones.  A sure verdict on the perturbed
+    values must still equal the literal predicate on the exact ones."""
+    rng = np.random.default_rng(4321)
+    n = 2_000_000
+    x, y = near_boundary_pairs(rng, n, tau, scale)
+    lit = literal(x, y, f32(tau))
+    for _ in range(2):   # up to two ulps, independent directions per element and per operand
+        xp = np.nextafter(x, np.where(rng.random(n) < 0.5, f32(np.inf), f32(-np.inf)).astype(f32))
+        yp = np.nextafter(y, np.where(rng.random(n) < 0.5, f32(np.inf), f32(-np.inf)).astype(f32))
+        xp = np.nextafter(xp, np.where(rng.random(n) < 0.5, f32(np.inf), f32(-np.inf)).astype(f32))
+        yp = np.nextafter(yp, np.where(rng.random(n) < 0.5, f32(np.inf), f32(-np.inf)).astype(f32))
+        sure, neg = fast_filter(xp, yp, f32(tau))
+        wrong = sure & (neg != lit)
+        assert not wrong.any(), (int(wrong.sum()), x[wrong][:4], y[wrong][:4])
+        assert sure.any()          # (the sample sits right on the boundary: most of it is NOT sure, by design)
+
+
 def test_exact_ties_and_degenerate_inputs_fall_through():
     tau = f32(0.5)
     # |a-b| == tau exactly: Q* = 0 -> never "sure"
