@@ -274,8 +274,6 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
         reg.set("triangle_dbg", args.triangle_dbg)
     if args.tile_runs >= 0:
         reg.set("tile_runs", args.tile_runs)
-    if args.graph_path >= 0:
-        reg.set("graph_path", args.graph_path)
     K = reg.params.num_edges * reg.params.apex_per_edge
 
     # device-resident inputs / outputs
@@ -490,8 +488,6 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
                 "parallelism": (f"the same {total_pairs}-pair batch, pair b on GPU b mod {world}, no collective" if strong
                                 else f"{world} x independent batches, no collective"),
                 "triangle_path": "tensor cores (tcgen05 mxf4)" if path_used == 1 else "POPC bitset",
-                "graph_path": "squared distances from the tensor cores (tcgen05 bf16x3), exact decision" if reg.get("graph_path") == 1
-                              else "CUDA-core filter kernel",
                 "l2": "512 MB flush write between timed steps; per-step workspace (~3 GB) also exceeds the 126 MB L2",
             },
             "hypotheses_per_sec": {
@@ -915,8 +911,6 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="library knob lanes (0 = library default)")
     ap.add_argument("--triangle-path", type=int, default=-1,
                     help="library knob triangle_path (0 POPC, 1 tensor core, 2 by edge density = library default)")
-    ap.add_argument("--graph-path", type=int, default=-1,
-                    help="library knob graph_path (0 CUDA-core S1 kernel, 1 squared distances from the tensor cores; default: library's)")
     ap.add_argument("--triangle-dbg", type=int, default=0, help="experiments only (library knob triangle_dbg)")
     ap.add_argument("--tile-runs", type=int, default=-1, help="experiments only (library knob tile_runs)")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(synth.CONFIGS),

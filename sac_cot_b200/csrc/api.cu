@@ -68,11 +68,6 @@ struct Layout {
   unsigned char* pass1 = nullptr;
   size_t pass1_bytes = 0, adj_bytes = 0, panel_bytes = 0;
   uint32_t* adj_rank = nullptr;  // the graph S2/S3 ran on: adj, or adj2 in second-order mode
-  // tensor-core graph kernel: operand images (row / column form), per-block largest squared norm, error probe
-  unsigned char* gimg_row = nullptr;
-  unsigned char* gimg_col = nullptr;
-  uint32_t* gnmax = nullptr;
-  float* gerr = nullptr;
   uint32_t* theta = nullptr;   // per-pair pruning threshold (tensor-core triangle path only)
   void* theta_ws = nullptr;    // scratch of the multi-CTA threshold kernels (calls with very few pairs)
   uint2* tile_tab = nullptr;   // tensor-core path: (pair, row block << 16 | column block) per tile
@@ -256,8 +251,6 @@ struct sac_cot_ctx {
   size_t h_match_bytes = 0;
   cudaEvent_t match_uploaded = nullptr;
   std::vector<int64_t> match_sig;     // shapes the resident pair table was built for
-  int graph_path = 0;                 // S1: 0 = CUDA-core kernel, 1 = squared distances from the tensor cores
-  int graph_dbg = 0;                  // tests: the tensor-core graph kernel records its largest distance error
   int match_dbg = 0;                  // experiments: the sweep kernel prints its barrier wait cycles (CTA 0)
   int match_path = 1;                 // 1: tensor-core sweep + exact decision (dim <= kMatchMaxDim); 0: exhaustive exact scan
 
@@ -296,14 +289,14 @@ sac_cot_params normalized(const sac_cot_params* in) {
 
 // Builds the descriptors and the arena layout for pairs with the given sizes.
 void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_input_copy, bool tensor_path, int xworld,
-          bool graph_mma, std::vector<PairDesc>& descs, std::vector<uint2>& tile_tab, Layout& L) {
+          std::vector<PairDesc>& descs, std::vector<uint2>& tile_tab, Layout& L) {
   L = Layout();
   L.pairs = pairs;
   L.Ke = prm.num_edges;
   L.m = prm.apex_per_edge;
   L.K = L.Ke * L.m;
   descs.resize(pairs);
-  size_t pt = 0, soa = 0, adj = 0, node = 0, mask = 0, panel = 0, gimg = 0;
+  size_t pt = 0, soa = 0, adj = 0, node = 0, mask = 0, panel = 0;
   int tiles = 0;
   tile_tab.clear();
   for (int b = 0; b < pairs; ++b) {
@@ -320,8 +313,6 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
     d.panel_off = static_cast<int64_t>(panel);
     d.npanel = (d.Npad + 255) / 256;
     d.tile_base = tiles;
-    d.gimg_off = static_cast<int64_t>(gimg);
-    if (graph_mma) gimg += graph_mma_image_bytes(d.nblk);
     if (tensor_path) {
       panel += static_cast<size_t>(d.npanel) * d.Npad * 8;
       const int nJ = (d.N + kMmaTileN - 1) / kMmaTileN;
@@ -387,10 +378,6 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_T = take(sizeof(float) * 3 * pairs);
   const size_t o_inl = take(sizeof(int32_t) * pairs);
   const size_t o_bo = take(sizeof(unsigned long long));
-  const size_t o_girow = graph_mma ? take(gimg) : 0;
-  const size_t o_gicol = graph_mma ? take(gimg) : 0;
-  const size_t o_gnmax = graph_mma ? take(sizeof(uint32_t) * static_cast<size_t>(L.max_nblk) * pairs) : 0;
-  const size_t o_gerr = graph_mma ? take(32) : 0;  // probe: max error (f32), groups decided (u64), groups sent to the literal path (u64)
   L.xrec_len = xworld > 0 ? node + static_cast<size_t>(L.Ke) + 2 : 0;
   const size_t o_xsend = xworld > 0 ? take(sizeof(unsigned long long) * L.xrec_len) : 0;
   const size_t o_xrecv = xworld > 0 ? take(sizeof(unsigned long long) * L.xrec_len * xworld) : 0;
@@ -426,10 +413,6 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.outT = reinterpret_cast<float*>(o_T);
   L.outInl = reinterpret_cast<int32_t*>(o_inl);
   L.best_override = reinterpret_cast<unsigned long long*>(o_bo);
-  L.gimg_row = graph_mma ? reinterpret_cast<unsigned char*>(o_girow + 1) : nullptr;  // +1: offset 0 must not read as "absent"
-  L.gimg_col = graph_mma ? reinterpret_cast<unsigned char*>(o_gicol + 1) : nullptr;
-  L.gnmax = graph_mma ? reinterpret_cast<uint32_t*>(o_gnmax + 1) : nullptr;
-  L.gerr = graph_mma ? reinterpret_cast<float*>(o_gerr + 1) : nullptr;
   L.xsend = xworld > 0 ? reinterpret_cast<unsigned long long*>(o_xsend) : nullptr;
   L.xrecv = xworld > 0 ? reinterpret_cast<unsigned long long*>(o_xrecv) : nullptr;
   L.xsum = xworld > 0 ? reinterpret_cast<unsigned long long*>(o_xsum) : nullptr;
@@ -472,12 +455,6 @@ void bind(Layout& L, unsigned char* base, bool has_input, bool tensor_path) {
   L.outT = rebase(L.outT, base);
   L.outInl = rebase(L.outInl, base);
   L.best_override = rebase(L.best_override, base);
-  if (L.gimg_row) {
-    L.gimg_row = base + (reinterpret_cast<size_t>(L.gimg_row) - 1);
-    L.gimg_col = base + (reinterpret_cast<size_t>(L.gimg_col) - 1);
-    L.gnmax = reinterpret_cast<uint32_t*>(base + (reinterpret_cast<size_t>(L.gnmax) - 1));
-    L.gerr = reinterpret_cast<float*>(base + (reinterpret_cast<size_t>(L.gerr) - 1));
-  }
   const bool x = L.xrec_len != 0;
   L.xsend = rebase(L.xsend, base, x);
   L.xrecv = rebase(L.xrecv, base, x);
@@ -595,13 +572,7 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   // planned with the tensor-core buffers: mode 1 (forced) or 2 (the key scan decides from the edge density);
   // both triangle kernels are then enqueued and the one not chosen returns at once
   const int tri_mode = L.panel != nullptr ? ctx->tri_path : 0;
-  if (L.gimg_row != nullptr) {
-    if (ctx->graph_dbg) CU_TRY(cudaMemsetAsync(L.gerr, 0, 32, ln.stream));
-    KL_TRY(launch_graph_mma(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.gimg_row, L.gimg_col, L.gnmax, L.max_nblk, L.adj, L.panel,
-                            L.ucount, L.unit_pitch, prm.tau_compat, ctx->graph_dbg ? L.gerr : nullptr));
-  } else {
-    KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.panel, L.ucount, L.unit_pitch, prm.tau_compat));
-  }
+  KL_TRY(launch_graph(lc, L.desc, L.pairs, L.max_nblk, L.soa, L.adj, L.panel, L.ucount, L.unit_pitch, prm.tau_compat));
   mark(ST_GRAPH);
   KL_TRY(launch_unit_scan(lc, L.desc, L.pairs, L.state, L.ucount, L.ubase, L.unit_pitch, rank, world));
   KL_TRY(launch_key_scan(lc, L.desc, L.pairs, L.state, L.chunk, ctx->d_sticky, ln.key_cap, tri_mode, nullptr));
@@ -718,15 +689,13 @@ void interleave_tile_runs(std::vector<uint2>& tab, std::vector<uint2>& scratch, 
 // A chunk with the same shapes, parameters and partition as the lane's previous one costs nothing here.
 int prepare_lane(sac_cot_ctx* ctx, Lane& ln, const int32_t* Ns, int pairs, const sac_cot_params& prm, bool host,
                  bool tensor, int rank, int world, int xworld) {
-  const bool graph_mma = ctx->graph_path == 1;
-  const int sig[8] = {pairs, prm.num_edges, prm.apex_per_edge,
-                      (host ? 1 : 0) | (tensor ? 2 : 0) | (ctx->tile_runs ? 4 : 0) | (graph_mma ? 8 : 0), rank, world, xworld,
-                      prm.compat_mode};
+  const int sig[8] = {pairs, prm.num_edges, prm.apex_per_edge, (host ? 1 : 0) | (tensor ? 2 : 0) | (ctx->tile_runs ? 4 : 0),
+                      rank, world, xworld, prm.compat_mode};
   if (ln.arena && !std::memcmp(sig, ln.plan_sig, sizeof(sig)) && ln.plan_Ns.size() == static_cast<size_t>(pairs) &&
       std::equal(Ns, Ns + pairs, ln.plan_Ns.begin()))
     return 0;
   ln.plan_sig[0] = -1;
-  plan(Ns, pairs, prm, host, tensor, xworld, graph_mma, ln.descs, ln.tile_tab, ln.lay);
+  plan(Ns, pairs, prm, host, tensor, xworld, ln.descs, ln.tile_tab, ln.lay);
   if (tensor) {
     if (world > 1) {  // keep the tiles of this rank's cells (common.cuh: owner_of_cell; a tile never straddles two cells)
       std::vector<uint2>& tab = ln.tile_tab;
@@ -1017,7 +986,6 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
   if (rc >= 0) rc = triangles_mma_configure();
   if (rc >= 0) rc = select_configure();
   if (rc >= 0) rc = match_configure();
-  if (rc >= 0) rc = graph_mma_configure();
   if (rc < 0) { sac_cot_ctx_destroy(ctx); return -rc; }
   *out = ctx;
   return SAC_COT_OK;
@@ -1085,12 +1053,6 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     return SAC_COT_OK;
   }
   if (!std::strcmp(name, "match_dbg")) { ctx->match_dbg = static_cast<int>(value); return SAC_COT_OK; }
-  if (!std::strcmp(name, "graph_dbg")) { ctx->graph_dbg = value != 0; return SAC_COT_OK; }
-  if (!std::strcmp(name, "graph_path")) {
-    if (value < 0 || value > 1) return SAC_COT_E_UNSUPPORTED;
-    ctx->graph_path = static_cast<int>(value);
-    return SAC_COT_OK;
-  }
   if (!std::strcmp(name, "match_path")) {
     if (value < 0 || value > 1) return SAC_COT_E_UNSUPPORTED;
     ctx->match_path = static_cast<int>(value);
@@ -1126,30 +1088,6 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
   if (!std::strcmp(name, "triangle_path")) { *value = ctx->tri_path; return SAC_COT_OK; }
   if (!std::strcmp(name, "triangle_prune")) { *value = ctx->tri_prune; return SAC_COT_OK; }
   if (!std::strcmp(name, "match_path")) { *value = ctx->match_path; return SAC_COT_OK; }
-  if (!std::strcmp(name, "graph_path")) { *value = ctx->graph_path; return SAC_COT_OK; }
-  if (!std::strcmp(name, "graph_groups") || !std::strcmp(name, "graph_unsure_groups")) {
-    // tensor-core graph kernel, graph_dbg = 1: four-column groups decided / sent to the literal path (latest chunk, lane 0)
-    Lane& ln = ctx->lanes[0];
-    if (!ln.arena || !ln.lay.gerr) return SAC_COT_E_WHICH;
-    cudaSetDevice(ctx->device);
-    if (int rc = sync_all(ctx)) return rc;
-    unsigned long long v[4] = {0, 0, 0, 0};
-    CU_TRY(cudaMemcpy(v, ln.lay.gerr, 32, cudaMemcpyDeviceToHost));
-    *value = static_cast<int64_t>(name[6] == 'g' ? v[1] : v[2]);
-    return SAC_COT_OK;
-  }
-  if (!std::strcmp(name, "graph_err_e12")) {
-    // tensor-core graph kernel, graph_dbg = 1: largest |x~ - exact| / (|p_i|^2 + |p_j|^2) of the latest chunk on lane 0,
-    // in units of 1e-12; synchronises
-    Lane& ln = ctx->lanes[0];
-    if (!ln.arena || !ln.lay.gerr) return SAC_COT_E_WHICH;
-    cudaSetDevice(ctx->device);
-    if (int rc = sync_all(ctx)) return rc;
-    float e = 0.0f;
-    CU_TRY(cudaMemcpy(&e, ln.lay.gerr, sizeof(e), cudaMemcpyDeviceToHost));
-    *value = static_cast<int64_t>(static_cast<double>(e) * 1e12);
-    return SAC_COT_OK;
-  }
   if (!std::strcmp(name, "triangle_path_used")) {
     // which S2 kernels the most recent chunk on lane 0 ran (0 = POPC, 1 = tensor core); synchronises
     Lane& ln = ctx->lanes[0];

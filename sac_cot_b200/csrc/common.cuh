@@ -26,7 +26,6 @@ struct PairDesc {
   int64_t panel_off; // first u32 word of this pair's K-panel copy of the adjacency (tensor-core path)
   int32_t npanel;    // 256-column panels = ceil(Npad / 256); panel p holds [Npad rows][8 words]
   int32_t tile_base; // first tile index of this pair in the chunk's tile list (tensor-core path)
-  int64_t gimg_off;  // first byte of this pair's operand images of the tensor-core graph kernel (nblk x 16 KB each)
 };
 
 struct PairDev {
@@ -161,12 +160,6 @@ int launch_pack_soa(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int 
                     const float* d_dst, float* d_soa);
 int launch_graph(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, const float* d_soa,
                  uint32_t* d_adj, uint32_t* d_panel, uint32_t* d_ucount, int unit_pitch, float tau);
-// kernels_graph_mma.cu — S1 with the squared distances from the tensor cores (bf16x3 tcgen05.mma, exact decision)
-size_t graph_mma_image_bytes(int nblk);
-int graph_mma_configure();
-int launch_graph_mma(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_nblk, const float* d_soa,
-                     unsigned char* d_img_row, unsigned char* d_img_col, uint32_t* d_nmax, int nmax_pitch, uint32_t* d_adj,
-                     uint32_t* d_panel, uint32_t* d_ucount, int unit_pitch, float tau, float* d_dbg_err);
 int launch_unit_scan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, PairDev* d_state,
                      const uint32_t* d_ucount, uint32_t* d_ubase, int unit_pitch, int rank, int world);
 // tri_mode: 0 = POPC kernels, 1 = tensor-core kernel, 2 = decided here from the chunk's edge density

@@ -59,9 +59,7 @@ def run_both(gpu, oracle, p, **kw):
 
 
 @pytest.mark.parametrize("N", [3, 4, 31, 32, 33, 100, 127, 128, 129, 255, 256, 257, 300, 1000, 1025])
-@pytest.mark.parametrize("gpath", [0, 1])
-def test_stage_parity_small_and_ragged_sizes(gpu, oracle, N, gpath):
-    gpu.set("graph_path", gpath)   # S1: CUDA-core kernel / squared distances from the tensor cores
+def test_stage_parity_small_and_ragged_sizes(gpu, oracle, N):
     p = synth.make_pair(N, 0.3, 7000 + N)
     run_both(gpu, oracle, p, num_edges=64, apex_per_edge=4)
 
@@ -81,9 +79,7 @@ def test_cfg1_single_pair_n1000(gpu, oracle):
 
 @pytest.mark.parametrize("cfg,b", [("cfg2_3dmatch_256x5000", 0), ("cfg2_3dmatch_256x5000", 1),
                                    ("cfg3_3dlomatch_256x5000", 0), ("cfg3_3dlomatch_256x5000", 1)])
-@pytest.mark.parametrize("gpath", [0, 1])
-def test_n5000_pairs_full_stage_parity(gpu, oracle, cfg, b, gpath):
-    gpu.set("graph_path", gpath)   # S1: CUDA-core kernel / squared distances from the tensor cores
+def test_n5000_pairs_full_stage_parity(gpu, oracle, cfg, b):
     p = synth.make_config_pair(cfg, b)
     R, t, inl = run_both(gpu, oracle, p)
     ang, dt = synth.pose_error(R, t, p.R_gt, p.t_gt)
@@ -91,16 +87,12 @@ def test_n5000_pairs_full_stage_parity(gpu, oracle, cfg, b, gpath):
     assert inl >= len(p.inlier_idx)
 
 
-@pytest.mark.parametrize("gpath", [0, 1])
-def test_kitti_scale_pair_n10000(gpu, oracle, gpath):
-    gpu.set("graph_path", gpath)   # S1: CUDA-core kernel / squared distances from the tensor cores
+def test_kitti_scale_pair_n10000(gpu, oracle):
     p = synth.make_config_pair("cfg4_kitti_128x10000", 0)
     run_both(gpu, oracle, p)
 
 
-@pytest.mark.parametrize("gpath", [0, 1])
-def test_chunked_row_path_n13000(gpu, oracle, gpath):
-    gpu.set("graph_path", gpath)   # S1: CUDA-core kernel / squared distances from the tensor cores
+def test_chunked_row_path_n13000(gpu, oracle):
     # stride 408 words > 352: the triangle kernel runs its 256-word chunk / accumulate mode
     p = synth.make_pair(13000, 0.03, 7300)
     run_both(gpu, oracle, p)
@@ -158,9 +150,7 @@ def test_fewer_edges_than_requested(gpu, oracle):
     run_both(gpu, oracle, p, num_edges=256, apex_per_edge=8)
 
 
-@pytest.mark.parametrize("gpath", [0, 1])
-def test_batch_with_ragged_sizes_matches_oracle(gpu, oracle, gpath):
-    gpu.set("graph_path", gpath)   # S1: CUDA-core kernel / squared distances from the tensor cores
+def test_batch_with_ragged_sizes_matches_oracle(gpu, oracle):
     sizes = (300, 1000, 129, 2048, 64, 777)
     pairs = [synth.make_pair(n, 0.1, 7800 + k) for k, n in enumerate(sizes)]
     rg = gpu.register_batch([p.src for p in pairs], [p.dst for p in pairs])
@@ -324,9 +314,7 @@ def _adj_parity(gpu, oracle, src, dst, tau):
     return int(gpu.debug(0, _abi.DBG_NUM_EDGES)[0])
 
 
-@pytest.mark.parametrize("gpath", [0, 1])
-def test_graph_near_threshold_scaled_cloud(gpu, oracle, gpath):
-    gpu.set("graph_path", gpath)   # S1: CUDA-core kernel / squared distances from the tensor cores
+def test_graph_near_threshold_scaled_cloud(gpu, oracle):
     # dst = rotated (1+eps) * src: |ld - ls| = eps * ls, so every pair with ls ~ tau/eps sits on the
     # decision boundary; thousands of pairs land inside the filter's rounding band
     rng = np.random.default_rng(5)
@@ -340,9 +328,7 @@ def test_graph_near_threshold_scaled_cloud(gpu, oracle, gpath):
         assert 0 < E < N * (N - 1) // 2
 
 
-@pytest.mark.parametrize("gpath", [0, 1])
-def test_graph_exact_ties_on_a_lattice(gpu, oracle, gpath):
-    gpu.set("graph_path", gpath)   # S1: CUDA-core kernel / squared distances from the tensor cores
+def test_graph_exact_ties_on_a_lattice(gpu, oracle):
     # collinear integer lattice, dst stretched by 1 + 2^-6: ld - ls = |i-j| * 2^-6 exactly, so with
     # tau = k * 2^-6 every pair at lattice distance k is an exact tie (strict '<' => no edge)
     N = 700
@@ -356,9 +342,7 @@ def test_graph_exact_ties_on_a_lattice(gpu, oracle, gpath):
 
 
 @pytest.mark.parametrize("scale", [1e-18, 1e-9, 1e-3, 1e6, 1e15])
-@pytest.mark.parametrize("gpath", [0, 1])
-def test_graph_extreme_magnitudes_and_duplicates(gpu, oracle, scale, gpath):
-    gpu.set("graph_path", gpath)   # S1: CUDA-core kernel / squared distances from the tensor cores
+def test_graph_extreme_magnitudes_and_duplicates(gpu, oracle, scale):
     rng = np.random.default_rng(9)
     N = 300
     src = (rng.random((N, 3)) * scale).astype(np.float32)
@@ -370,9 +354,7 @@ def test_graph_extreme_magnitudes_and_duplicates(gpu, oracle, scale, gpath):
     _adj_parity(gpu, oracle, src, dst, float(np.float32(1e-3 * scale)))
 
 
-@pytest.mark.parametrize("gpath", [0, 1])
-def test_graph_huge_threshold_takes_literal_path(gpu, oracle, gpath):
-    gpu.set("graph_path", gpath)   # S1: CUDA-core kernel / squared distances from the tensor cores
+def test_graph_huge_threshold_takes_literal_path(gpu, oracle):
     p = synth.make_pair(257, 0.2, 77)
     E = _adj_parity(gpu, oracle, p.src, p.dst, 1e30)   # 4*tau^2 overflows: every pair decided literally
     assert E == 257 * 256 // 2
@@ -921,20 +903,3 @@ def test_second_order_mode_rejected_where_unsupported_and_v1_struct_accepted(gpu
         R2, t2, i2 = g.register(p.src, p.dst)
         np.testing.assert_array_equal(R1, R2)
         assert i1 == i2
-
-
-def test_tensor_core_graph_kernel_distance_error_stays_inside_its_budget(gpu_lib, oracle):
-    # kernels_graph_mma.cu trusts |x~ - |p_i - p_j|^2| <= 2^-15 (|p_i|^2 + |p_j|^2); the probe build of the kernel
-    # compares every accumulator value with float64 arithmetic on the coordinates
-    for cfg, tau in (("cfg2_3dmatch_256x5000", 0.1), ("cfg4_kitti_128x10000", 0.6)):
-        p = synth.make_config_pair(cfg, 1)
-        with Registrar(lib=gpu_lib, tau_compat=tau, tau_inlier=tau) as g:
-            g.set("keep_debug", 1)
-            g.set("graph_path", 1)
-            g.set("graph_dbg", 1)
-            g.register(p.src, p.dst)
-            err = g.get("graph_err_e12") * 1e-12
-            assert 0.0 < err < 2.0 ** -17, err     # a quarter of the budget at most
-            set_params(oracle, tau_compat=tau, tau_inlier=tau)
-            oracle.register(p.src, p.dst)
-            np.testing.assert_array_equal(g.debug(0, _abi.DBG_ADJ), oracle.debug(0, _abi.DBG_ADJ))
