@@ -183,6 +183,17 @@ SAC_COT_API int sac_cot_match_packed(sac_cot_ctx* ctx,
                                      const float* desc_dst, const float* xyz_dst, const int64_t* offs_dst,
                                      int32_t B, int32_t dim,
                                      int32_t* nn, float* corr_src, float* corr_dst, int32_t location);
+/* Mutual-nearest-neighbour filter (optional second step).  nn is the result of matching source -> target, nn_back the
+ * result of a second sac_cot_match_packed call with the two clouds swapped (target -> source); correspondence i of pair
+ * b survives iff nn_back[nn[i]] == i.  The survivors are written, in order and packed over the pairs, to out_src /
+ * out_dst (room for offs_src[B] x 3 floats each) and out_offsets (B + 1 entries: pair b owns [out_offsets[b],
+ * out_offsets[b+1])) — again exactly the src / dst / offsets of sac_cot_register_packed, whose offsets must be a host
+ * array: with SAC_COT_LOC_DEVICE out_offsets is a device array the caller copies back.  A pair may end up with fewer
+ * than three correspondences: leave it out of the registration call. */
+SAC_COT_API int sac_cot_match_mutual(sac_cot_ctx* ctx, const int32_t* nn, const int32_t* nn_back,
+                                     const float* corr_src, const float* corr_dst,
+                                     const int64_t* offs_src, const int64_t* offs_dst, int32_t B,
+                                     float* out_src, float* out_dst, int64_t* out_offsets, int32_t location);
 /* One pair, host buffers, process-global ctx (as sac_cot_register). */
 SAC_COT_API int sac_cot_match(const float* desc_src, const float* xyz_src, int32_t Ns,
                               const float* desc_dst, const float* xyz_dst, int32_t Nd, int32_t dim,

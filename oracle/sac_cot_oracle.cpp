@@ -784,6 +784,36 @@ int sac_cot_match_packed(sac_cot_ctx* ctx, const float* desc_src, const float* x
   return SAC_COT_OK;
 }
 
+int sac_cot_match_mutual(sac_cot_ctx* ctx, const int32_t* nn, const int32_t* nn_back, const float* corr_src,
+                         const float* corr_dst, const int64_t* offs_src, const int64_t* offs_dst, int32_t B, float* out_src,
+                         float* out_dst, int64_t* out_offsets, int32_t location) {
+  if (!ctx || !offs_src || !offs_dst || !out_offsets) return SAC_COT_E_NULL;
+  if (location != SAC_COT_LOC_HOST) return SAC_COT_E_UNSUPPORTED;
+  if (B < 0 || B > 65535) return SAC_COT_E_SIZE;
+  if (B > 0 && (!nn || !nn_back || !corr_src || !corr_dst || !out_src || !out_dst)) return SAC_COT_E_NULL;
+  for (int b = 0; b < B; ++b) {
+    const int64_t ns = offs_src[b + 1] - offs_src[b], nd = offs_dst[b + 1] - offs_dst[b];
+    if (ns < 1 || nd < 1 || ns > SAC_COT_MAX_KEYPOINTS || nd > SAC_COT_MAX_KEYPOINTS) return SAC_COT_E_SIZE;
+  }
+  int64_t o = 0;
+  for (int b = 0; b < B; ++b) {
+    out_offsets[b] = o;
+    const int64_t s0 = offs_src[b], d0 = offs_dst[b];
+    const int64_t ns = offs_src[b + 1] - s0, nd = offs_dst[b + 1] - d0;
+    for (int64_t i = 0; i < ns; ++i) {
+      const int64_t j = nn[s0 + i];
+      if (j < 0 || j >= nd || nn_back[d0 + j] != i) continue;
+      for (int a = 0; a < 3; ++a) {
+        out_src[o * 3 + a] = corr_src[(s0 + i) * 3 + a];
+        out_dst[o * 3 + a] = corr_dst[(s0 + i) * 3 + a];
+      }
+      ++o;
+    }
+  }
+  out_offsets[B] = o;
+  return SAC_COT_OK;
+}
+
 int sac_cot_match(const float* desc_src, const float* xyz_src, int32_t Ns, const float* desc_dst, const float* xyz_dst,
                   int32_t Nd, int32_t dim, int32_t* nn, float* corr_src, float* corr_dst) {
   static sac_cot_ctx global_ctx;

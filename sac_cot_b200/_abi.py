@@ -75,6 +75,8 @@ SYMBOLS = {
                                           C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "sac_cot_match_packed": (C.c_int, [_ctxp, C.c_void_p, C.c_void_p, _i64p, C.c_void_p, C.c_void_p, _i64p, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "sac_cot_match_mutual": (C.c_int, [_ctxp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i64p, _i64p, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "sac_cot_match": (C.c_int, [_f32p, _f32p, C.c_int32, _f32p, _f32p, C.c_int32, C.c_int32, _i32p, _f32p, _f32p]),
     "sac_cot_group_create": (C.c_int, [C.POINTER(_ctxp), _i32p, C.c_int32]),
     "sac_cot_group_destroy": (C.c_int, [_ctxp]),

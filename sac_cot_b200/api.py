@@ -209,6 +209,24 @@ class Registrar:
                               cs.ctypes.data, cd.ctypes.data, _abi.LOC_HOST)
         return nn, cs, cd, os_
 
+    def match_mutual_batch(self, desc_src, xyz_src, desc_dst, xyz_dst):
+        """Matching in both directions + the mutual-nearest-neighbour filter (sac_cot_match_mutual): returns
+        (corr_src, corr_dst, offsets) holding, per pair and in order, the correspondences i with
+        nn_back[nn[i]] == i.  Pairs left with fewer than three correspondences cannot be registered."""
+        nn, cs, cd, os_ = self.match_batch(desc_src, xyz_src, desc_dst, xyz_dst)
+        nb, _, _, od_ = self.match_batch(desc_dst, xyz_dst, desc_src, xyz_src)
+        out_s = np.empty_like(cs)
+        out_d = np.empty_like(cd)
+        out_off = np.zeros(len(os_), np.int64)
+        rc = self.lib.sac_cot_match_mutual(
+            self._ctx, nn.ctypes.data, nb.ctypes.data, cs.ctypes.data, cd.ctypes.data,
+            os_.ctypes.data_as(C.POINTER(C.c_int64)), od_.ctypes.data_as(C.POINTER(C.c_int64)), len(os_) - 1,
+            out_s.ctypes.data, out_d.ctypes.data, out_off.ctypes.data, _abi.LOC_HOST)
+        if rc != _abi.OK:
+            raise SacCotError(rc, "sac_cot_match_mutual", self.lib)
+        n = int(out_off[-1])
+        return out_s[:n], out_d[:n], out_off
+
     def match(self, desc_src, xyz_src, desc_dst, xyz_dst):
         """One pair: (nn, corr_src, corr_dst)."""
         nn, cs, cd, _ = self.match_batch([desc_src], [xyz_src], [desc_dst], [xyz_dst])

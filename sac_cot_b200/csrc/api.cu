@@ -1379,9 +1379,125 @@ int run_match(sac_cot_ctx* ctx, const float* desc_src, const float* xyz_src, con
   return SAC_COT_OK;
 }
 
+int run_match_mutual(sac_cot_ctx* ctx, const int32_t* nn, const int32_t* nn_back, const float* corr_src, const float* corr_dst,
+                     const int64_t* offs_src, const int64_t* offs_dst, int32_t B, float* out_src, float* out_dst,
+                     int64_t* out_offsets, int32_t location) {
+  if (!ctx || !offs_src || !offs_dst || !out_offsets) return SAC_COT_E_NULL;
+  if (location != SAC_COT_LOC_HOST && location != SAC_COT_LOC_DEVICE) return SAC_COT_E_UNSUPPORTED;
+  if (B < 0 || B > 65535) return SAC_COT_E_SIZE;
+  if (B > 0 && (!nn || !nn_back || !corr_src || !corr_dst || !out_src || !out_dst)) return SAC_COT_E_NULL;
+  for (int b = 0; b < B; ++b) {
+    const int64_t ns = offs_src[b + 1] - offs_src[b], nd = offs_dst[b + 1] - offs_dst[b];
+    if (ns < 1 || nd < 1 || ns > SAC_COT_MAX_KEYPOINTS || nd > SAC_COT_MAX_KEYPOINTS) return SAC_COT_E_SIZE;
+  }
+  const bool host = location == SAC_COT_LOC_HOST;
+  if (B == 0) {
+    if (host) out_offsets[0] = 0;
+    return SAC_COT_OK;
+  }
+  CU_TRY(cudaSetDevice(ctx->device));
+  const int64_t tot_s = offs_src[B] - offs_src[0], tot_d = offs_dst[B] - offs_dst[0];
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t o_tab = take(sizeof(MutualPair) * B);
+  const size_t o_kept = take(sizeof(unsigned long long) * B);
+  const size_t o_offs = take(sizeof(long long) * (static_cast<size_t>(B) + 1));
+  const size_t o_nn = host ? take(sizeof(int32_t) * tot_s) : 0;
+  const size_t o_nb = host ? take(sizeof(int32_t) * tot_d) : 0;
+  const size_t o_cs = host ? take(sizeof(float) * 3 * tot_s) : 0;
+  const size_t o_cd = host ? take(sizeof(float) * 3 * tot_s) : 0;
+  const size_t o_os = host ? take(sizeof(float) * 3 * tot_s) : 0;
+  const size_t o_od = host ? take(sizeof(float) * 3 * tot_s) : 0;
+  if (off > ctx->match_arena_bytes) {
+    if (int rc = sync_all(ctx)) return rc;
+    if (ctx->match_arena) CU_TRY(cudaFree(ctx->match_arena));
+    ctx->match_arena = nullptr;
+    ctx->match_arena_bytes = 0;
+    const size_t want = align_up(off + off / 8, 1 << 20);
+    if (cudaMalloc(&ctx->match_arena, want) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return SAC_COT_E_NOMEM;
+    }
+    ctx->match_arena_bytes = want;
+  }
+  ctx->match_sig.clear();  // the arena no longer holds the matching call's pair table
+  unsigned char* base = ctx->match_arena;
+  cudaStream_t stream = ctx->stream;
+  std::vector<MutualPair> tab(static_cast<size_t>(B));
+  for (int b = 0; b < B; ++b) {
+    tab[b].Ns = static_cast<int32_t>(offs_src[b + 1] - offs_src[b]);
+    tab[b].Nd = static_cast<int32_t>(offs_dst[b + 1] - offs_dst[b]);
+    tab[b].s_off = offs_src[b] - offs_src[0];
+    tab[b].d_off = offs_dst[b] - offs_dst[0];
+  }
+  const size_t tab_bytes = sizeof(MutualPair) * B;
+  CU_TRY(cudaEventSynchronize(ctx->match_uploaded));
+  if (tab_bytes > ctx->h_match_bytes) {
+    if (ctx->h_match) CU_TRY(cudaFreeHost(ctx->h_match));
+    ctx->h_match = nullptr;
+    ctx->h_match_bytes = 0;
+    if (cudaMallocHost(&ctx->h_match, align_up(tab_bytes * 2, 4096)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return SAC_COT_E_NOMEM;
+    }
+    ctx->h_match_bytes = align_up(tab_bytes * 2, 4096);
+  }
+  std::memcpy(ctx->h_match, tab.data(), tab_bytes);
+  CU_TRY(cudaMemcpyAsync(base + o_tab, ctx->h_match, tab_bytes, cudaMemcpyHostToDevice, stream));
+  CU_TRY(cudaEventRecord(ctx->match_uploaded, stream));
+  const int32_t* k_nn = nn + offs_src[0];
+  const int32_t* k_nb = nn_back + offs_dst[0];
+  const float* k_cs = corr_src + static_cast<size_t>(offs_src[0]) * 3;
+  const float* k_cd = corr_dst + static_cast<size_t>(offs_src[0]) * 3;
+  float* k_os = out_src;
+  float* k_od = out_dst;
+  long long* k_off = reinterpret_cast<long long*>(out_offsets);
+  if (host) {
+    CU_TRY(cudaMemcpyAsync(base + o_nn, k_nn, sizeof(int32_t) * tot_s, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(base + o_nb, k_nb, sizeof(int32_t) * tot_d, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(base + o_cs, k_cs, sizeof(float) * 3 * tot_s, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(base + o_cd, k_cd, sizeof(float) * 3 * tot_s, cudaMemcpyHostToDevice, stream));
+    k_nn = reinterpret_cast<const int32_t*>(base + o_nn);
+    k_nb = reinterpret_cast<const int32_t*>(base + o_nb);
+    k_cs = reinterpret_cast<const float*>(base + o_cs);
+    k_cd = reinterpret_cast<const float*>(base + o_cd);
+    k_os = reinterpret_cast<float*>(base + o_os);
+    k_od = reinterpret_cast<float*>(base + o_od);
+    k_off = reinterpret_cast<long long*>(base + o_offs);
+  }
+  LaunchCtx lc{stream, ctx->sm_count};
+  KL_TRY(launch_match_mutual(lc, reinterpret_cast<const MutualPair*>(base + o_tab), B, k_nn, k_nb, k_cs, k_cd,
+                             reinterpret_cast<unsigned long long*>(base + o_kept), k_off, k_os, k_od));
+  if (host) {
+    CU_TRY(cudaMemcpyAsync(out_offsets, k_off, sizeof(long long) * (static_cast<size_t>(B) + 1), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    const size_t kept = static_cast<size_t>(out_offsets[B]);
+    if (kept) {
+      CU_TRY(cudaMemcpyAsync(out_src, k_os, sizeof(float) * 3 * kept, cudaMemcpyDeviceToHost, stream));
+      CU_TRY(cudaMemcpyAsync(out_dst, k_od, sizeof(float) * 3 * kept, cudaMemcpyDeviceToHost, stream));
+      CU_TRY(cudaStreamSynchronize(stream));
+    }
+  }
+  return SAC_COT_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int sac_cot_match_mutual(sac_cot_ctx* ctx, const int32_t* nn, const int32_t* nn_back, const float* corr_src,
+                         const float* corr_dst, const int64_t* offs_src, const int64_t* offs_dst, int32_t B, float* out_src,
+                         float* out_dst, int64_t* out_offsets, int32_t location) {
+  try {
+    return run_match_mutual(ctx, nn, nn_back, corr_src, corr_dst, offs_src, offs_dst, B, out_src, out_dst, out_offsets, location);
+  } catch (const std::bad_alloc&) {
+    return SAC_COT_E_NOMEM;
+  }
+}
 
 int sac_cot_match_packed(sac_cot_ctx* ctx, const float* desc_src, const float* xyz_src, const int64_t* offs_src,
                          const float* desc_dst, const float* xyz_dst, const int64_t* offs_dst, int32_t B, int32_t dim,

@@ -257,6 +257,15 @@ int launch_match_exact(const LaunchCtx& lc, const MatchPair* d_pairs, int pairs,
                        const int32_t* d_cand, const int32_t* d_cand_cnt, int32_t* d_nn, float* d_corr_src,
                        float* d_corr_dst, int32_t* d_work_list, uint32_t* d_work_count);
 
+// mutual-nearest-neighbour filter of the matched correspondences (kernels_match.cu)
+struct MutualPair {
+  int32_t Ns, Nd;
+  int64_t s_off, d_off;  // first row of the pair in the packed source / target arrays
+};
+int launch_match_mutual(const LaunchCtx& lc, const MutualPair* d_pairs, int B, const int32_t* d_nn, const int32_t* d_nn_back,
+                        const float* d_corr_src, const float* d_corr_dst, unsigned long long* d_kept, long long* d_out_offsets,
+                        float* d_out_src, float* d_out_dst);
+
 // kernels_hypo.cu — S4 Kabsch, S5/S6 scoring + argmax, S7 refit
 int launch_kabsch(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, const float* d_soa, const int32_t* d_tri,
                   float* d_rt, int K);

@@ -543,6 +543,116 @@ __global__ void __launch_bounds__(kExactWarps * 32) match_scan_kernel(const Matc
 }
 
 // ------------------------------------------------------------------------------------------
+// 4. mutual-nearest-neighbour filter: correspondence i of a pair is kept iff nn_back[nn[i]] == i (nn: source ->
+//    target, nn_back: target -> source, both local to the pair).  Ordered, packed across the pairs:
+//      mutual_count_kernel  one CTA per pair: kept[b]
+//      mutual_scan_kernel   one CTA: out_offsets = exclusive scan of kept (B + 1 entries)
+//      mutual_write_kernel  one CTA per pair: flags again, block-wide ordered compaction into out_src / out_dst
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool mutual_keep(const MutualPair& mp, const int32_t* __restrict__ nn,
+                                            const int32_t* __restrict__ nn_back, int i) {
+  const int j = nn[mp.s_off + i];
+  return j >= 0 && j < mp.Nd && nn_back[mp.d_off + j] == i;
+}
+
+__global__ void __launch_bounds__(1024) mutual_count_kernel(const MutualPair* __restrict__ pairs,
+                                                            const int32_t* __restrict__ nn,
+                                                            const int32_t* __restrict__ nn_back,
+                                                            unsigned long long* __restrict__ kept) {
+  const MutualPair mp = pairs[blockIdx.x];
+  __shared__ unsigned int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  unsigned int c = 0;
+  for (int i = threadIdx.x; i < mp.Ns; i += 1024) c += mutual_keep(mp, nn, nn_back, i) ? 1u : 0u;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) kept[blockIdx.x] = s_cnt;
+}
+
+__global__ void __launch_bounds__(1024) mutual_scan_kernel(const unsigned long long* __restrict__ kept, int B,
+                                                           long long* __restrict__ out_offsets) {
+  __shared__ unsigned long long part[1024];
+  __shared__ unsigned long long carry;
+  const int t = threadIdx.x;
+  if (t == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + t;
+    const unsigned long long v = b < B ? kept[b] : 0ull;
+    part[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const unsigned long long add = t >= o ? part[t - o] : 0ull;
+      __syncthreads();
+      part[t] += add;
+      __syncthreads();
+    }
+    if (b < B) out_offsets[b] = static_cast<long long>(carry + part[t] - v);
+    __syncthreads();
+    if (t == 1023) carry += part[1023];
+    __syncthreads();
+  }
+  if (t == 0) out_offsets[B] = static_cast<long long>(carry);
+}
+
+__global__ void __launch_bounds__(1024) mutual_write_kernel(const MutualPair* __restrict__ pairs,
+                                                            const int32_t* __restrict__ nn,
+                                                            const int32_t* __restrict__ nn_back,
+                                                            const float* __restrict__ corr_src,
+                                                            const float* __restrict__ corr_dst,
+                                                            const long long* __restrict__ out_offsets,
+                                                            float* __restrict__ out_src, float* __restrict__ out_dst) {
+  const MutualPair mp = pairs[blockIdx.x];
+  __shared__ unsigned int wsum[32];
+  __shared__ unsigned int s_base;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_base = 0;
+  __syncthreads();
+  const long long o0 = out_offsets[blockIdx.x];
+  for (int i0 = 0; i0 < mp.Ns; i0 += 1024) {
+    const int i = i0 + t;
+    const bool keep = i < mp.Ns && mutual_keep(mp, nn, nn_back, i);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[warp] = __popc(m);
+    __syncthreads();
+    unsigned int before = s_base;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    if (keep) {
+      const long long o = o0 + before + __popc(m & ((1u << lane) - 1u));
+      const size_t si = (static_cast<size_t>(mp.s_off) + i) * 3;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        out_src[o * 3 + a] = corr_src[si + a];
+        out_dst[o * 3 + a] = corr_dst[si + a];
+      }
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += wsum[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+}
+
+int launch_match_mutual(const LaunchCtx& lc, const MutualPair* d_pairs, int B, const int32_t* d_nn, const int32_t* d_nn_back,
+                        const float* d_corr_src, const float* d_corr_dst, unsigned long long* d_kept, long long* d_out_offsets,
+                        float* d_out_src, float* d_out_dst) {
+  mutual_count_kernel<<<B, 1024, 0, lc.stream>>>(d_pairs, d_nn, d_nn_back, d_kept);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  mutual_scan_kernel<<<1, 1024, 0, lc.stream>>>(d_kept, B, d_out_offsets);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  mutual_write_kernel<<<B, 1024, 0, lc.stream>>>(d_pairs, d_nn, d_nn_back, d_corr_src, d_corr_dst, d_out_offsets, d_out_src, d_out_dst);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 3 : -static_cast<int>(e);
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 int match_chunks(int dim) { return ((3 * dim + 3 + 15) / 16) * 2; }  // 16-byte chunks of 8 bf16; K padded to 16

@@ -130,3 +130,52 @@ def test_argument_checks(mgpu):
         mgpu.match(f, x, np.zeros((4, 32), np.float32), x)
     with pytest.raises(SacCotError):
         mgpu.set("match_path", 2)
+
+
+def test_mutual_filter_matches_oracle(gpu_lib, oracle):
+    import torch
+    sizes = [(500, 640), (129, 77), (1000, 1000)]
+    rng = np.random.default_rng(21)
+    G = [(rng.random((b, 33)) * 10).astype(np.float32) for _, b in sizes]
+    F = []
+    for (a, b), g in zip(sizes, G):
+        f = (rng.random((a, 33)) * 10).astype(np.float32)
+        k = min(a, b) // 2
+        f[:k] = g[:k] + (rng.standard_normal((k, 33)) * 0.01).astype(np.float32)   # half of the rows have a true partner
+        F.append(f)
+    XS = [rng.random((a, 3)).astype(np.float32) for a, _ in sizes]
+    XD = [rng.random((b, 3)).astype(np.float32) for _, b in sizes]
+    cso, cdo, offo = oracle.match_mutual_batch(F, XS, G, XD)
+    with Registrar(lib=gpu_lib) as g:
+        csg, cdg, offg = g.match_mutual_batch(F, XS, G, XD)
+    np.testing.assert_array_equal(offg, offo)
+    np.testing.assert_array_equal(csg, cso)
+    np.testing.assert_array_equal(cdg, cdo)
+    assert all(offo[b + 1] - offo[b] >= min(a, c) // 2 for b, (a, c) in enumerate(sizes))
+    # device-resident form: everything stays in HBM, the offsets come back with one small copy
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream(dev)
+    os_ = np.zeros(len(sizes) + 1, np.int64); np.cumsum([a for a, _ in sizes], out=os_[1:])
+    od_ = np.zeros(len(sizes) + 1, np.int64); np.cumsum([b for _, b in sizes], out=od_[1:])
+    T = lambda parts: torch.from_numpy(np.concatenate(parts)).to(dev)  # noqa: E731
+    dF, dG, dXS, dXD = T(F), T(G), T(XS), T(XD)
+    ns, nd = int(os_[-1]), int(od_[-1])
+    d_nn = torch.empty(ns, dtype=torch.int32, device=dev); d_nb = torch.empty(nd, dtype=torch.int32, device=dev)
+    d_cs = torch.empty((ns, 3), device=dev); d_cd = torch.empty((ns, 3), device=dev)
+    d_bs = torch.empty((nd, 3), device=dev); d_bd = torch.empty((nd, 3), device=dev)
+    d_os = torch.empty((ns, 3), device=dev); d_od = torch.empty((ns, 3), device=dev)
+    d_off = torch.empty(len(sizes) + 1, dtype=torch.int64, device=dev)
+    i64p = lambda a: a.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_int64))  # noqa: E731
+    with Registrar(lib=gpu_lib, device=0, stream=stream.cuda_stream) as g:
+        g.match_packed_ptr(dF.data_ptr(), dXS.data_ptr(), os_, dG.data_ptr(), dXD.data_ptr(), od_, 33, d_nn.data_ptr(),
+                           d_cs.data_ptr(), d_cd.data_ptr(), _abi.LOC_DEVICE)
+        g.match_packed_ptr(dG.data_ptr(), dXD.data_ptr(), od_, dF.data_ptr(), dXS.data_ptr(), os_, 33, d_nb.data_ptr(),
+                           d_bs.data_ptr(), d_bd.data_ptr(), _abi.LOC_DEVICE)
+        rc = gpu_lib.sac_cot_match_mutual(g._ctx, d_nn.data_ptr(), d_nb.data_ptr(), d_cs.data_ptr(), d_cd.data_ptr(), i64p(os_),
+                                          i64p(od_), len(sizes), d_os.data_ptr(), d_od.data_ptr(), d_off.data_ptr(), _abi.LOC_DEVICE)
+        assert rc == 0
+        stream.synchronize()
+    np.testing.assert_array_equal(d_off.cpu().numpy(), offo)
+    n = int(offo[-1])
+    np.testing.assert_array_equal(d_os.cpu().numpy()[:n], cso)
+    np.testing.assert_array_equal(d_od.cpu().numpy()[:n], cdo)

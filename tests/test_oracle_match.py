@@ -107,3 +107,24 @@ def test_batch_and_argument_checks(oracle, oracle_lib):
     assert oracle_lib.sac_cot_match_packed(ctx, buf.ctypes.data, buf.ctypes.data, empty, buf.ctypes.data, buf.ctypes.data, o, 1, 33,
                                            nnb.ctypes.data, out.ctypes.data, out.ctypes.data, _abi.LOC_HOST) == _abi.E_SIZE
     oracle_lib.sac_cot_ctx_destroy(ctx)
+
+
+def test_mutual_filter_matches_numpy_and_raises_the_inlier_ratio(oracle):
+    ps = [synth.make_pair(600, 0.2, 50 + k) for k in range(3)]
+    ds = [synth.make_descriptors(p, 33, seed=k) for k, p in enumerate(ps)]
+    F, G = [d[0] for d in ds], [d[1] for d in ds]
+    XS, XD = [p.src for p in ps], [p.dst for p in ps]
+    cs, cd, offs = oracle.match_mutual_batch(F, XS, G, XD)
+    for b, p in enumerate(ps):
+        D = witness_d64(F[b], G[b])
+        nn, nb = D.argmin(axis=1), D.argmin(axis=0)
+        keep = np.nonzero(nb[nn] == np.arange(600))[0]
+        assert offs[b + 1] - offs[b] == len(keep)
+        np.testing.assert_array_equal(cs[offs[b]:offs[b + 1]], p.src[keep])
+        np.testing.assert_array_equal(cd[offs[b]:offs[b + 1]], p.dst[nn[keep]])
+        assert np.isin(p.inlier_idx, keep).all()                       # every true match is mutual
+        assert len(p.inlier_idx) / len(keep) > 0.3                     # 20 % inliers before the filter
+        oracle.params.tau_compat = oracle.params.tau_inlier = 0.1
+        R, t, inl = oracle.register(cs[offs[b]:offs[b + 1]], cd[offs[b]:offs[b + 1]])
+        ang, dt = synth.pose_error(R, t, p.R_gt, p.t_gt)
+        assert ang < np.deg2rad(1.0) and dt < 0.02
