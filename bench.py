@@ -45,7 +45,7 @@ from sac_cot_b200.api import Registrar, load_library  # noqa: E402
 
 WORKLOAD = "cfg2_3dmatch_256x5000"   # BASELINE.json configs[1]; --workload selects another config
 UNIT = "registrations/s"
-STAGES = ("pack", "graph", "scan", "theta", "triangles", "select", "apex", "kabsch", "score", "finalize",
+STAGES = ("pack", "graph", "scan", "theta", "triangles", "triangles_kept", "select", "apex", "kabsch", "score", "finalize",
           "exchange1", "exchange2")
 SM_COUNT = 148
 FP32_LANES = 128   # FP32 lanes per SM
@@ -274,6 +274,8 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
         reg.set("triangle_dbg", args.triangle_dbg)
     if args.tile_runs >= 0:
         reg.set("tile_runs", args.tile_runs)
+    if args.node_prune >= 0:
+        reg.set("node_prune", args.node_prune)
     K = reg.params.num_edges * reg.params.apex_per_edge
 
     # device-resident inputs / outputs
@@ -361,6 +363,11 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
     stage_us, stage_calls, stage_common = stage_report(reg, args.steps)
     reg.set("stage_timing", 0)
     reg.set("lanes", lanes_default)
+    # exact node pruning of S2 (kernels_prune.cu) in the last chunk of the pass above
+    node_prune = {"mode": reg.get("node_prune"), "pruned_pairs_last_chunk": reg.get("pruned_pairs"),
+                  "kept_nodes_last_chunk": reg.get("kept_nodes"),
+                  "what": "pairs whose selectable edges provably join few high-degree nodes count triangles for those "
+                          "nodes' rows only (exact; --node-prune 0 switches it off)"}
 
     # ---- timed region 2: end to end through the host-buffer C-ABI call (e2e) ----
     step_host()  # warm the host path (arena regrows once: it now also holds the input copy)
@@ -488,6 +495,7 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
                 "parallelism": (f"the same {total_pairs}-pair batch, pair b on GPU b mod {world}, no collective" if strong
                                 else f"{world} x independent batches, no collective"),
                 "triangle_path": "tensor cores (tcgen05 mxf4)" if path_used == 1 else "POPC bitset",
+                "node_prune": node_prune,
                 "l2": "512 MB flush write between timed steps; per-step workspace (~3 GB) also exceeds the 126 MB L2",
             },
             "hypotheses_per_sec": {
@@ -880,6 +888,7 @@ def run_single_sharded(args, rank, local_rank, world, emit, torch, dist, dev):
                 "parallelism": f"sac_cot_register_sharded over {world} rank(s): triangle cells (1920 cols x 256 rows) and "
                                "hypothesis ranges split; ncclAllGather + ncclAllReduce(max) enqueued by the library",
                 "triangle_path": "tensor cores (tcgen05 mxf4)" if path_used == 1 else "POPC bitset",
+                "node_prune": node_prune,
                 "l2": "512 MB flush write between timed steps; the adjacency alone (313 MB) exceeds the 126 MB L2",
             },
             "ms_per_registration": total_ms / args.steps,
@@ -913,6 +922,9 @@ def main():
                     help="library knob triangle_path (0 POPC, 1 tensor core, 2 by edge density = library default)")
     ap.add_argument("--triangle-dbg", type=int, default=0, help="experiments only (library knob triangle_dbg)")
     ap.add_argument("--tile-runs", type=int, default=-1, help="experiments only (library knob tile_runs)")
+    ap.add_argument("--node-prune", type=int, default=-1,
+                    help="library knob node_prune: 0 = every pair counts all N x N triangles (round-1 behaviour), "
+                         "1 = exact node pruning (library default)")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(synth.CONFIGS),
                     help="synthetic config (default: the headline config, BASELINE.json configs[1])")
     ap.add_argument("--stage", default="register", choices=["register", "match"],

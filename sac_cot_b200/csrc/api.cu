@@ -15,6 +15,8 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -31,11 +33,24 @@ namespace {
     if (e__ != cudaSuccess) return static_cast<int>(e__); \
   } while (0)
 
-#define KL_TRY(expr)                 \
-  do {                               \
-    const int n__ = (expr);          \
-    if (n__ < 0) return -n__;        \
-    ctx->launches += n__;            \
+// SAC_COT_TRACE=1 in the environment (diagnostics): the device is synchronised after every launcher and the first
+// one whose kernels fail is named on stderr.
+static const bool g_trace = std::getenv("SAC_COT_TRACE") != nullptr;
+#define KL_TRY(expr)                                                                          \
+  do {                                                                                        \
+    const int n__ = (expr);                                                                   \
+    if (n__ < 0) {                                                                            \
+      if (g_trace) std::fprintf(stderr, "sac_cot trace: launch failed (%d): %s\n", -n__, #expr); \
+      return -n__;                                                                            \
+    }                                                                                         \
+    ctx->launches += n__;                                                                     \
+    if (g_trace) {                                                                            \
+      const cudaError_t e__ = cudaDeviceSynchronize();                                        \
+      if (e__ != cudaSuccess) {                                                               \
+        std::fprintf(stderr, "sac_cot trace: %s after %s\n", cudaGetErrorString(e__), #expr); \
+        return static_cast<int>(e__);                                                         \
+      }                                                                                       \
+    }                                                                                         \
   } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -72,6 +87,14 @@ struct Layout {
   void* theta_ws = nullptr;    // scratch of the multi-CTA threshold kernels (calls with very few pairs)
   uint2* tile_tab = nullptr;   // tensor-core path: (pair, row block << 16 | column block) per tile
   int total_tiles = 0;         // tensor-core path: tiles of the whole chunk
+  // exact node pruning (kernels_prune.cu): plan per pair (in the zero region), degrees, kept lists, the tile list
+  // without the pruned pairs' tiles and its length
+  NodePlan* nplan = nullptr;
+  unsigned short* deg = nullptr;
+  unsigned short* kept = nullptr;
+  uint32_t* keptbits = nullptr;  // [sum of Npad / 32], indexed like the inlier masks (PairDesc::mask_off)
+  uint2* tile_tab2 = nullptr;
+  int* tile_total = nullptr;
   unsigned long long* sel = nullptr;
   unsigned long long* tie = nullptr;
   unsigned long long* top = nullptr;
@@ -106,9 +129,9 @@ size_t pair_bytes_estimate(int N, int K, int Ke, bool tensor_path, bool second_o
 }
 
 // Optional per-stage timing with CUDA events on the ctx stream ("stage_timing" knob).
-enum Stage { ST_PACK = 0, ST_GRAPH, ST_SCAN, ST_THETA, ST_TRIANGLES, ST_SELECT, ST_APEX, ST_KABSCH, ST_SCORE, ST_FINALIZE, ST_EXCH1, ST_EXCH2,
+enum Stage { ST_PACK = 0, ST_GRAPH, ST_SCAN, ST_THETA, ST_TRIANGLES, ST_KEPT, ST_SELECT, ST_APEX, ST_KABSCH, ST_SCORE, ST_FINALIZE, ST_EXCH1, ST_EXCH2,
              ST_MATCH_PREP, ST_MATCH_SWEEP, ST_MATCH_EXACT, ST_COUNT };
-const char* const kStageNames[ST_COUNT] = {"pack", "graph", "scan", "theta", "triangles", "select", "apex", "kabsch", "score", "finalize", "exchange1", "exchange2",
+const char* const kStageNames[ST_COUNT] = {"pack", "graph", "scan", "theta", "triangles", "triangles_kept", "select", "apex", "kabsch", "score", "finalize", "exchange1", "exchange2",
                                            "match_prep", "match_sweep", "match_exact"};
 
 // NCCL, bound at run time: the library carries no link-time dependency on it (a process that already loaded
@@ -222,6 +245,11 @@ struct sac_cot_ctx {
   int tile_runs = 1;  // tensor-core path: deal tiles to the CTA pairs in runs (0: one at a time; experiments)
   int tri_dbg = 0;    // experiments only (bit 0: skip the tensor-core kernel's epilogue work; results are void)
   int tri_prune = 1;  // tensor-core path: drop edges below the per-pair threshold (exact for the selection)
+  // tensor-core path: pairs whose selectable edges join few high-degree nodes count triangles for those nodes only
+  // (kernels_prune.cu; exact).  0 off, 1 on unless keep_debug is set (the T_NODE / EDGE_KEYS / HIST dumps then cover
+  // the kept nodes only), 2 on whenever the kept list fits (tests)
+  int node_prune = 1;
+  int node_prune_cost = 200;  // a pair is pruned if (sum of kept degrees) x cost <= Npad^2
   int64_t launches = 0;
   int64_t retries = 0;
   int deferred_status = 0;  // device-location calls: status discovered after the fact
@@ -349,6 +377,8 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_t2 = take(sizeof(unsigned long long) * node);
   L.unit_pitch = static_cast<int>(unit_count(static_cast<unsigned int>(L.max_nblk)));
   const size_t o_ucount = take(sizeof(uint32_t) * L.unit_pitch * pairs);
+  const size_t o_nplan = take(sizeof(NodePlan) * pairs);
+  const size_t o_ttotal = take(2 * sizeof(int));
   L.zero_bytes = off;
   const size_t o_ubase = take(sizeof(uint32_t) * L.unit_pitch * pairs);
   const size_t o_desc = take(sizeof(PairDesc) * pairs);
@@ -367,6 +397,10 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t theta_ws_bytes = tensor_path ? theta_scratch_bytes(pairs) : 0;
   const size_t o_theta_ws = theta_ws_bytes ? take(theta_ws_bytes) : 0;
   const size_t o_tiles = tensor_path ? take(sizeof(uint2) * std::max(1, tiles)) : 0;
+  const size_t o_tiles2 = tensor_path ? take(sizeof(uint2) * std::max(1, tiles)) : 0;
+  const size_t o_deg = tensor_path ? take(sizeof(unsigned short) * node) : 0;
+  const size_t o_kept = tensor_path ? take(sizeof(unsigned short) * kNodeKeepMax * pairs) : 0;
+  const size_t o_keptbits = tensor_path ? take(sizeof(uint32_t) * mask) : 0;
   const size_t o_sel = take(sizeof(unsigned long long) * L.Ke * pairs);
   const size_t o_tie = take(sizeof(unsigned long long) * kTieCap * pairs);
   const size_t o_top = take(sizeof(unsigned long long) * L.Ke * pairs);
@@ -402,6 +436,12 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.theta = tensor_path ? reinterpret_cast<uint32_t*>(o_theta) : nullptr;
   L.theta_ws = theta_ws_bytes ? reinterpret_cast<void*>(o_theta_ws + 1) : nullptr;  // +1: offset 0 must not read as "absent"
   L.tile_tab = tensor_path ? reinterpret_cast<uint2*>(o_tiles) : nullptr;
+  L.nplan = reinterpret_cast<NodePlan*>(o_nplan);
+  L.tile_tab2 = tensor_path ? reinterpret_cast<uint2*>(o_tiles2) : nullptr;
+  L.tile_total = reinterpret_cast<int*>(o_ttotal);
+  L.deg = tensor_path ? reinterpret_cast<unsigned short*>(o_deg) : nullptr;
+  L.kept = tensor_path ? reinterpret_cast<unsigned short*>(o_kept) : nullptr;
+  L.keptbits = tensor_path ? reinterpret_cast<uint32_t*>(o_keptbits) : nullptr;
   L.sel = reinterpret_cast<unsigned long long*>(o_sel);
   L.tie = reinterpret_cast<unsigned long long*>(o_tie);
   L.top = reinterpret_cast<unsigned long long*>(o_top);
@@ -444,6 +484,12 @@ void bind(Layout& L, unsigned char* base, bool has_input, bool tensor_path) {
   L.theta = rebase(L.theta, base, tensor_path);
   L.theta_ws = L.theta_ws ? static_cast<void*>(base + (reinterpret_cast<size_t>(L.theta_ws) - 1)) : nullptr;
   L.tile_tab = rebase(L.tile_tab, base, tensor_path);
+  L.nplan = rebase(L.nplan, base);
+  L.tile_tab2 = rebase(L.tile_tab2, base, tensor_path);
+  L.tile_total = rebase(L.tile_total, base);
+  L.deg = rebase(L.deg, base, tensor_path);
+  L.kept = rebase(L.kept, base, tensor_path);
+  L.keptbits = rebase(L.keptbits, base, tensor_path);
   L.sel = rebase(L.sel, base);
   L.tie = rebase(L.tie, base);
   L.top = rebase(L.top, base);
@@ -586,7 +632,7 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
     const uint32_t cmin = static_cast<uint32_t>(prm.so_min_common);
     if (tri_mode != 0) {
       KL_TRY(launch_fill_u32(lc, L.theta, cmin | 0x80000000u, L.pairs));  // bit 31: fixed, never raised
-      KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, L.adj, L.panel, L.state, L.chunk, ln.keys, L.theta,
+      KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, nullptr, nullptr, L.adj, L.panel, L.state, L.chunk, ln.keys, L.theta,
                                   L.hist, L.t2, L.Ke, 0, ctx->tri_dbg));
     }
     if (tri_mode != 1)
@@ -605,11 +651,23 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
     panel_use = L.panel2;
     mark(ST_GRAPH);  // the first pass and the rebuild count as graph construction
   }
+  // exact node pruning: first-order graph, unsharded, rows short enough for the kept-row kernel
+  const bool node_prune = tri_mode != 0 && ctx->tri_prune && ctx->node_prune != 0 && L.adj2 == nullptr && world <= 1 &&
+                          L.max_npad <= kNodePruneMaxNpad && L.total_tiles > 0 && ctx->apex_path != 2 &&
+                          (ctx->node_prune >= 2 || !ctx->keep_debug);
   if (tri_mode != 0) {
     KL_TRY(launch_tri_theta(lc, L.desc, L.pairs, L.max_npad, adj_use, L.chunk, L.theta, L.theta_ws, L.Ke, ctx->tri_prune));
+    if (node_prune)
+      KL_TRY(launch_node_plan(lc, L.desc, L.pairs, L.max_npad, adj_use, L.chunk, L.state, L.theta, L.deg, L.nplan, L.kept, L.keptbits, L.tile_tab,
+                              L.total_tiles, L.tile_tab2, L.tile_total, ctx->node_prune_cost, ctx->node_prune));
     mark(ST_THETA);
-    KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, adj_use, panel_use, L.state, L.chunk, ln.keys, L.theta,
-                                L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg));
+    KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, node_prune ? L.tile_total : nullptr, L.tile_tab2,
+                                adj_use, panel_use, L.state, L.chunk, ln.keys, L.theta, L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg));
+    if (node_prune) mark(ST_TRIANGLES);
+    if (node_prune)
+      KL_TRY(launch_triangles_kept(lc, L.desc, L.pairs, L.max_n, L.max_stride, adj_use, L.nplan, L.kept, L.chunk, L.state, ln.keys,
+                                   L.hist, L.t2));
+    if (node_prune) mark(ST_KEPT);
   }
   if (tri_mode != 1)
     KL_TRY(launch_triangles(lc, L.desc, L.pairs, L.max_nblk, L.max_stride, adj_use, L.state, L.chunk, ln.keys, L.ubase,
@@ -619,7 +677,8 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   mark(ST_SELECT);
   if (stop_after_edges) return 0;
   const float tau2 = prm.tau_inlier * prm.tau_inlier;
-  KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.max_npad, adj_use, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path));
+  KL_TRY(launch_select_apex(lc, L.desc, L.pairs, L.max_npad, adj_use, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path,
+                            node_prune ? L.nplan : nullptr, node_prune ? L.deg : nullptr, node_prune ? L.keptbits : nullptr));
   mark(ST_APEX);
   KL_TRY(launch_kabsch(lc, L.desc, L.pairs, L.soa, L.tri, L.rt, L.K));
   mark(ST_KABSCH);
@@ -985,6 +1044,7 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
   int rc = triangles_configure();
   if (rc >= 0) rc = triangles_mma_configure();
   if (rc >= 0) rc = select_configure();
+  if (rc >= 0) rc = node_prune_configure();
   if (rc >= 0) rc = match_configure();
   if (rc < 0) { sac_cot_ctx_destroy(ctx); return -rc; }
   *out = ctx;
@@ -1048,6 +1108,16 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     ctx->apex_path = static_cast<int>(value);
     return SAC_COT_OK;
   }
+  if (!std::strcmp(name, "node_prune")) {
+    if (value < 0 || value > 2) return SAC_COT_E_UNSUPPORTED;
+    ctx->node_prune = static_cast<int>(value);
+    return SAC_COT_OK;
+  }
+  if (!std::strcmp(name, "node_prune_cost")) {
+    if (value < 1 || value > 1000000) return SAC_COT_E_SIZE;
+    ctx->node_prune_cost = static_cast<int>(value);
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "tile_runs")) {
     ctx->tile_runs = value != 0;
     return SAC_COT_OK;
@@ -1097,6 +1167,26 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
     ChunkDev c;
     CU_TRY(cudaMemcpy(&c, ln.lay.chunk, sizeof(c), cudaMemcpyDeviceToHost));
     *value = c.use_tensor;
+    return SAC_COT_OK;
+  }
+  if (!std::strcmp(name, "node_prune")) { *value = ctx->node_prune; return SAC_COT_OK; }
+  if (!std::strcmp(name, "node_prune_cost")) { *value = ctx->node_prune_cost; return SAC_COT_OK; }
+  if (!std::strcmp(name, "pruned_pairs") || !std::strcmp(name, "kept_nodes")) {
+    // exact node pruning in the most recent chunk on lane 0: pairs that took the kept-row kernel / the nodes they
+    // kept in total; synchronises
+    Lane& ln = ctx->lanes[0];
+    if (!ln.arena || !ln.lay.nplan || ln.lay.pairs == 0) return SAC_COT_E_WHICH;
+    cudaSetDevice(ctx->device);
+    if (int rc = sync_all(ctx)) return rc;
+    std::vector<NodePlan> pl(ln.lay.pairs);
+    CU_TRY(cudaMemcpy(pl.data(), ln.lay.nplan, sizeof(NodePlan) * pl.size(), cudaMemcpyDeviceToHost));
+    int64_t np = 0, nk = 0;
+    for (const NodePlan& q : pl)
+      if (q.pruned) {
+        ++np;
+        nk += q.n_keep;
+      }
+    *value = name[0] == 'p' ? np : nk;
     return SAC_COT_OK;
   }
   if (!std::strcmp(name, "threads")) { *value = 0; return SAC_COT_OK; }
@@ -1750,7 +1840,7 @@ int run_sharded(sac_cot_ctx* ctx, const float* src, const float* dst, int32_t N,
     // ---- part 2: apexes and hypotheses everywhere (cheap, identical), scores of this rank's hypothesis range
     const float tau2 = params->tau_inlier * params->tau_inlier;
     span_begin();
-    KL_TRY(launch_select_apex(lc, L.desc, 1, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path));
+    KL_TRY(launch_select_apex(lc, L.desc, 1, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path, nullptr, nullptr, nullptr));
     span_end(ST_APEX);
     span_begin();
     KL_TRY(launch_kabsch(lc, L.desc, 1, L.soa, L.tri, L.rt, L.K));
@@ -1916,7 +2006,7 @@ int sac_cot_sharded_phase2(sac_cot_ctx* ctx, const uint64_t* t_all, const uint64
     CU_TRY(cudaMemsetAsync(L.hyp_key, 0, sizeof(unsigned long long) * L.K, ln.stream));
     LaunchCtx lc{ln.stream, ctx->sm_count};
     const float tau2 = ctx->prm.tau_inlier * ctx->prm.tau_inlier;
-    KL_TRY(launch_select_apex(lc, L.desc, 1, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path));
+    KL_TRY(launch_select_apex(lc, L.desc, 1, L.max_npad, L.adj, L.t2, L.top, L.tri, L.Ke, L.m, ctx->apex_path, nullptr, nullptr, nullptr));
     KL_TRY(launch_kabsch(lc, L.desc, 1, L.soa, L.tri, L.rt, L.K));
     const int per = (L.K + world - 1) / world;
     const int h0 = std::min(L.K, ctx->sh_rank * per), h1 = std::min(L.K, h0 + per);

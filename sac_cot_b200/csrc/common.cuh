@@ -206,23 +206,50 @@ constexpr int kThetaSplitMaxPairs = 147;
 size_t theta_scratch_bytes(int pairs);
 int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                      const ChunkDev* d_chunk, uint32_t* d_theta, void* d_scratch, int Ke, int prune);
+// d_total / d_tiles2 (or null): if *d_total >= 0 the kernel walks the *d_total entries of d_tiles2 instead (the list
+// without the tiles of node-pruned pairs, compacted on the device)
 int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_tiles, int total_tiles,
-                         const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
-                         unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
-                         int Ke, int raise, int dbg);
+                         const int* d_total, const uint2* d_tiles2, const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state,
+                         const ChunkDev* d_chunk, unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist,
+                         unsigned long long* d_t2, int Ke, int raise, int dbg);
 int triangles_mma_configure();
 // tensor-pipe peak probe (the triangle kernel's MMA shape, issued back to back): bench.py's roofline denominator
 int launch_mma_peak_probe(const LaunchCtx& lc, int clusters, int stage_pairs);
 double mma_peak_probe_flops(int clusters, int stage_pairs);
+
+// kernels_prune.cu — exact node pruning of S2 on the tensor-core path: pairs whose selectable edges join few
+// high-degree nodes count triangles for those nodes' rows only
+struct NodePlan {
+  uint32_t pruned;   // 1: the pair takes the kept-row kernel, the tensor-core kernel skips its tiles
+  uint32_t n_keep;   // nodes of degree >= min_deg, listed ascending in the pair's slice of the kept list
+  uint32_t ub_rest;  // D (D - 1) / 2 >= t_k of every node outside the kept set, D = their largest degree (diagnostic)
+  uint32_t min_deg;  // theta0 + 1
+};
+constexpr int kNodeKeepMax = 2048;         // kept-list slots per pair
+constexpr int kNodePruneMaxNpad = 10240;   // longest row the kept-row kernel holds in registers (10 words per lane)
+int node_prune_configure();
+// exact degrees -> per-pair plan + kept list -> tile list without the pruned pairs' tiles (three launches).
+// cost: a pair is pruned if (sum of kept degrees) x cost <= Npad^2; force >= 2: whenever the kept list fits (tests)
+// d_total: int[2] in the chunk's zero region: [0] tiles left (-1: nothing pruned, use the original list), [1] pruned pairs
+int launch_node_plan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
+                     const ChunkDev* d_chunk, const PairDev* d_state, const uint32_t* d_theta, unsigned short* d_deg, NodePlan* d_plan,
+                     unsigned short* d_kept, uint32_t* d_keptbits, const uint2* d_tiles, int total_tiles, uint2* d_tiles_out,
+                     int* d_total, int cost, int force);
+int launch_triangles_kept(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_n, int max_stride,
+                          const uint32_t* d_adj, const NodePlan* d_plan, const unsigned short* d_kept,
+                          const ChunkDev* d_chunk, PairDev* d_state, unsigned long long* d_keys, uint32_t* d_hist,
+                          unsigned long long* d_t2);
 
 // kernels_select.cu — S3 edge ranking + apex selection
 int launch_select_edges(const LaunchCtx& lc, int pairs, PairDev* d_state, const ChunkDev* d_chunk,
                         const unsigned long long* d_keys, const uint32_t* d_hist, unsigned long long* d_sel,
                         unsigned long long* d_tie, unsigned long long* d_top, int Ke);
 int select_configure();  // opt-in dynamic shared memory; call once per device
+// d_plan / d_deg / d_keptbits (or null): pairs whose node sums cover the kept nodes only, the exact degrees and the
+// kept-node bit masks (kernels_prune.cu)
 int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                        const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m,
-                       int apex_path);
+                       int apex_path, const NodePlan* d_plan, const unsigned short* d_deg, const uint32_t* d_keptbits);
 
 // sharded single pair: record of a rank for exchange #1 and the merge of the gathered records (kernels_select.cu)
 int launch_shard_pack(const LaunchCtx& lc, const unsigned long long* d_t2, const unsigned long long* d_top,

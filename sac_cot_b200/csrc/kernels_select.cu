@@ -294,6 +294,84 @@ __global__ void __launch_bounds__(128) select_apex_kernel(const PairDesc* __rest
   }
 }
 
+// Node-pruned pairs (kernels_prune.cu), one warp: walks the candidates of edge (ri, rj) that lie OUTSIDE the kept set
+// (kb = the pair's kept-node bit mask) and returns whether one of them has a count >= bound.  ts[k] of such a node is
+// 0 (nothing known), an upper bound with kApexBoundFlag set, or the exact count (evaluated for an earlier edge of this
+// CTA).  Bounds, cheapest first:
+//   t_k <= deg_k (deg_k - 1) / 2                                   (every T_kn <= deg_k - 1)
+//   t_k <= 1/2 sum_{n in N(k)} (min(deg_k, deg_n) - 1)             (one degree lookup per neighbour)
+// and only a node whose second bound still reaches `bound` is evaluated exactly,
+//   t_k = 1/2 sum_{n in N(k)} popc(row_k & row_n).
+// Control flow is warp-uniform throughout: the words that hold such candidates are found with one ballot per 32
+// words and their bits are walked by the whole warp.  Only the PRUNED instance of the apex kernel carries this code.
+constexpr uint32_t kApexBoundFlag = 0x80000000u;  // counts are < 2^31
+__device__ __forceinline__ bool apex_outside_candidates(const uint32_t* __restrict__ adjp, int stride,
+                                                        const uint32_t* __restrict__ ri, const uint32_t* __restrict__ rj,
+                                                        const uint32_t* __restrict__ kb,
+                                                        const unsigned short* __restrict__ degp, uint32_t* ts,
+                                                        uint32_t bound) {
+  const int lane = threadIdx.x & 31;
+  bool upset = false;  // warp-uniform
+  for (int w0 = 0; w0 < stride; w0 += 32) {
+    const int w = w0 + lane;
+    const uint32_t mine = w < stride ? (ri[w] & rj[w] & ~kb[w]) : 0u;
+    unsigned act = __ballot_sync(0xffffffffu, mine != 0u);
+    while (act) {
+      const int src = __ffs(act) - 1;
+      act &= act - 1u;
+      uint32_t bits = __shfl_sync(0xffffffffu, mine, src);
+      while (bits) {
+        const int k = 32 * (w0 + src) + __ffs(bits) - 1;
+        bits &= bits - 1u;
+        uint32_t v = ts[k];  // one shared-memory word: the same value in every lane
+        const uint32_t* rk = adjp + static_cast<size_t>(k) * stride;
+        if (v == 0u) {
+          const uint32_t dk = degp[k];
+          if (dk * (dk - 1u) / 2u < bound) continue;
+          unsigned long long ub = 0;  // second bound
+          for (int x = lane; x < stride; x += 32) {
+            uint32_t nb = rk[x];
+            while (nb) {
+              const int b2 = __ffs(nb) - 1;
+              nb &= nb - 1u;
+              ub += min(dk, static_cast<uint32_t>(degp[32 * x + b2])) - 1u;  // an edge: both degrees >= 1
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ub += __shfl_xor_sync(0xffffffffu, ub, o);
+          v = static_cast<uint32_t>(ub >> 1) | kApexBoundFlag;
+          __syncwarp();
+          if (lane == 0) ts[k] = v;  // another warp of the CTA may store this or the exact count: either is valid
+          __syncwarp();
+        }
+        if (v & kApexBoundFlag) {
+          if ((v & ~kApexBoundFlag) < bound) continue;
+          unsigned long long sum = 0;  // exact count
+          for (int w2 = 0; w2 < stride; ++w2) {
+            uint32_t nb = rk[w2];  // warp-uniform
+            while (nb) {
+              const int b2 = __ffs(nb) - 1;
+              nb &= nb - 1u;
+              const uint32_t* rn = adjp + static_cast<size_t>(32 * w2 + b2) * stride;
+              uint32_t c = 0;
+              for (int x = lane; x < stride; x += 32) c += __popc(rk[x] & rn[x]);
+              sum += c;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          v = static_cast<uint32_t>(sum >> 1);
+          __syncwarp();
+          if (lane == 0) ts[k] = v;
+          __syncwarp();
+        }
+        upset |= v >= bound;
+      }
+    }
+  }
+  return upset;
+}
+
 // Staged variant (the one normally used): the pair's node counts t_k = t2_k / 2 are copied once per CTA into
 // shared memory as 32-bit values (t_k <= (N-1)(N-2)/2 < 2^31) and a CTA of 32 warps walks many edges of ONE pair.
 // The warp-per-edge kernel above looks every candidate up in global memory: 8 useful bytes per 32-byte L2
@@ -305,18 +383,29 @@ constexpr int kApexThreads = 1024;
 constexpr int kApexRank = 256;   // nodes the rank list aims for
 constexpr int kApexCap = 512;    // its capacity (ties at the cut)
 constexpr int kApexMaxSmem = 200 * 1024;
-template <int M>
+template <int M, bool PRUNED>
 __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const PairDesc* __restrict__ descs,
                                                                           const uint32_t* __restrict__ adj,
                                                                           const unsigned long long* __restrict__ t2,
                                                                           const unsigned long long* __restrict__ top,
                                                                           int32_t* __restrict__ tri, int Ke, int m,
-                                                                          int use_rank_list) {
+                                                                          int use_rank_list,
+                                                                          const NodePlan* __restrict__ plan,
+                                                                          const unsigned short* __restrict__ deg,
+                                                                          const uint32_t* __restrict__ keptbits) {
   extern __shared__ uint32_t apex_ts[];  // [Npad] node counts, then the rank list
   __shared__ int s_cnt, s_len;
   __shared__ uint32_t s_max;
   const int pair = blockIdx.y;
   const PairDesc d = descs[pair];
+  // Node-pruned pair (kernels_prune.cu): t2 holds the sums of the kept nodes only, the others read 0 and their
+  // t_k is at most ub_rest.  A candidate apex is in a triangle with its edge, so its true t_k is >= 1: among the
+  // candidates 0 means "not evaluated".
+  // The PRUNED instance handles those pairs, the plain one all the others (both are launched when the chunk may
+  // hold pruned pairs; a CTA of the wrong kind leaves at once).
+  if ((plan != nullptr && plan[pair].pruned != 0u) != PRUNED) return;
+  const unsigned short* degp = PRUNED ? deg + d.node_off : nullptr;
+  const uint32_t* kbp = PRUNED ? keptbits + d.mask_off : nullptr;
   const int lane = threadIdx.x & 31, tid = threadIdx.x;
   unsigned long long* rank_list = reinterpret_cast<unsigned long long*>(apex_ts + d.Npad);  // [kApexCap]
   {
@@ -399,6 +488,7 @@ __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const 
     const uint32_t* rj = adj + d.adj_off + static_cast<size_t>(j) * d.stride;
     // ---- fast path: walk the rank list, 32 nodes at a time ----
     int found = 0;
+    uint32_t t_mth = 0u;  // count of the m-th hit
     for (int base = 0; base < nrank && found < m; base += 32) {
       const unsigned long long key = base + lane < nrank ? rank_list[base + lane] : 0ull;
       bool hit = false;
@@ -411,9 +501,22 @@ __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const 
         out[q * 3 + 1] = j;
         out[q * 3 + 2] = static_cast<int>(k);
       }
+      const unsigned last = __ballot_sync(0xffffffffu, hit && q == m - 1);
+      if (last) t_mth = __shfl_sync(0xffffffffu, static_cast<uint32_t>(key >> 32), __ffs(last) - 1);
       found += __popc(hm);
     }
-    if (found >= m) continue;
+    if constexpr (!PRUNED) {
+      if (found >= m) continue;
+    } else {
+      // Pruned pair: the list ranks the kept nodes only.  The m hits stand iff no candidate OUTSIDE the kept set
+      // reaches the m-th hit's count (a tie would go to the lower index: be strict).  Without m hits every unknown
+      // candidate is evaluated (bound 0).
+      const uint32_t bound = found >= m ? t_mth : 0u;
+      const bool upset = apex_outside_candidates(adj + d.adj_off, d.stride, ri, rj, kbp, degp, apex_ts, bound);
+      if (found >= m && !upset) continue;
+      // otherwise the exhaustive path below decides among the known candidates: with m hits, the ones left unknown
+      // (count 0) lie strictly below the m-th hit and cannot be selected
+    }
     // ---- exhaustive path (the rank list held fewer than m common neighbours of this edge) ----
     // Pass 1: per-lane maximum of t_k over the candidates (one IMNMX per candidate), then a lower bound L on the
     // m-th best count: the value at which the lane maxima, taken from the top, cover m lanes (each of them holds
@@ -433,7 +536,9 @@ __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const 
         while (bits) {
           const int b = __ffs(bits) - 1;
           bits &= bits - 1;
-          lmax = max(lmax, tw[b]);
+          uint32_t tk = tw[b];
+          if (PRUNED && (tk & kApexBoundFlag)) tk = 0u;  // only an upper bound is known: below the m-th hit (see above)
+          lmax = max(lmax, tk);
         }
       }
     }
@@ -470,7 +575,8 @@ __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const 
           const int b = __ffs(bits) - 1;
           bits &= bits - 1;
           const unsigned int k = kb + static_cast<unsigned int>(b);
-          const uint32_t tk = apex_ts[k];
+          uint32_t tk = apex_ts[k];
+          if (PRUNED && (tk & kApexBoundFlag)) tk = 0u;
           if (tk >= L) {
             unsigned long long cnd = (static_cast<unsigned long long>(tk) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - k);
 #pragma unroll
@@ -506,30 +612,45 @@ __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const 
   }
 }
 
+template <int M>
+static cudaError_t apex_configure_one() {
+  cudaError_t e = cudaFuncSetAttribute(select_apex_staged_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(select_apex_staged_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
+  return e;
+}
 int select_configure() {
-  cudaError_t e = cudaFuncSetAttribute(select_apex_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(select_apex_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(select_apex_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(select_apex_staged_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApexMaxSmem);
+  cudaError_t e = apex_configure_one<1>();
+  if (e == cudaSuccess) e = apex_configure_one<2>();
+  if (e == cudaSuccess) e = apex_configure_one<4>();
+  if (e == cudaSuccess) e = apex_configure_one<8>();
   return e == cudaSuccess ? 0 : -static_cast<int>(e);
 }
 
 int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                        const unsigned long long* d_t2, const unsigned long long* d_top, int32_t* d_tri, int Ke, int m,
-                       int apex_path) {
+                       int apex_path, const NodePlan* d_plan, const unsigned short* d_deg, const uint32_t* d_keptbits) {
   // apex_path (tests): 0 = staged kernel with the rank list (default), 1 = staged kernel, exhaustive path only,
   // 2 = the global-lookup kernel that large N falls back to
   const size_t smem = static_cast<size_t>(max_npad) * 4 + kApexCap * 8;
   const int rl = apex_path == 0 ? 1 : 0;
+  int launched = 1;
   if (smem <= static_cast<size_t>(kApexMaxSmem) && apex_path != 2) {
     // enough CTAs to fill the GPU (every CTA of a pair rebuilds the pair's rank list), at most one per 32 edges
     int split = (lc.sm_count + pairs - 1) / pairs;
     split = std::max(1, std::min(split, (Ke + 31) / 32));
     dim3 grid(split, pairs);
-    if (m <= 1) select_apex_staged_kernel<1><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl);
-    else if (m <= 2) select_apex_staged_kernel<2><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl);
-    else if (m <= 4) select_apex_staged_kernel<4><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl);
-    else select_apex_staged_kernel<8><<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl);
+    auto go = [&](auto kernel_plain, auto kernel_pruned) {
+      kernel_plain<<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl, d_plan, d_deg, d_keptbits);
+      if (d_plan) {
+        kernel_pruned<<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl, d_plan, d_deg, d_keptbits);
+        launched = 2;
+      }
+    };
+    if (m <= 1) go(select_apex_staged_kernel<1, false>, select_apex_staged_kernel<1, true>);
+    else if (m <= 2) go(select_apex_staged_kernel<2, false>, select_apex_staged_kernel<2, true>);
+    else if (m <= 4) go(select_apex_staged_kernel<4, false>, select_apex_staged_kernel<4, true>);
+    else go(select_apex_staged_kernel<8, false>, select_apex_staged_kernel<8, true>);
   } else {  // node counts do not fit shared memory (N > 51200): look them up in global memory
     dim3 grid((Ke + 3) / 4, pairs);
     if (m <= 1) select_apex_kernel<1><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
@@ -538,7 +659,7 @@ int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, i
     else select_apex_kernel<8><<<grid, 128, 0, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m);
   }
   const cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+  return e == cudaSuccess ? launched : -static_cast<int>(e);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -316,11 +316,18 @@ __device__ __noinline__ void raise_threshold(uint32_t* hist_s, uint32_t* histp, 
 
 template <bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangles_mma_kernel(
-    const PairDesc* __restrict__ descs, const uint2* __restrict__ tiles, int total_tiles,
+    const PairDesc* __restrict__ descs, const uint2* __restrict__ tiles, int total_tiles, const int* __restrict__ d_total,
+    const uint2* __restrict__ tiles2,
     const uint32_t* __restrict__ adj, const uint32_t* __restrict__ panel, PairDev* __restrict__ state,
     const ChunkDev* __restrict__ chunk, unsigned long long* __restrict__ keys, uint32_t* __restrict__ theta,
     uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2, int Ke, int raise, int dbg) {
   if (chunk->overflow || !chunk->use_tensor) return;
+  // the list was compacted on the device (kernels_prune.cu): fewer tiles than the grid was sized for, possibly none
+  if (d_total && *d_total >= 0) {
+    total_tiles = *d_total;
+    tiles = tiles2;
+  }
+  if (total_tiles == 0) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stage_base = smem_raw;
   uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem_raw + kOffHist);
@@ -1307,16 +1314,16 @@ int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
 }
 
 int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_tiles, int total_tiles,
-                         const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state, const ChunkDev* d_chunk,
-                         unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist, unsigned long long* d_t2,
-                         int Ke, int raise, int dbg) {
+                         const int* d_total, const uint2* d_tiles2, const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state,
+                         const ChunkDev* d_chunk, unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist,
+                         unsigned long long* d_t2, int Ke, int raise, int dbg) {
   const int grid = 2 * mma_clusters(total_tiles, lc.sm_count);  // CTA pairs
   if (grid > 0) {
     if (dbg & 64)
-      triangles_mma_kernel<true><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_adj, d_panel,
+      triangles_mma_kernel<true><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_total, d_tiles2, d_adj, d_panel,
                                                                            d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, Ke, raise, dbg);
     else
-      triangles_mma_kernel<false><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_adj, d_panel,
+      triangles_mma_kernel<false><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_total, d_tiles2, d_adj, d_panel,
                                                                             d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, Ke, raise, dbg);
   }
   const cudaError_t e = cudaGetLastError();

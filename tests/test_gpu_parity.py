@@ -903,3 +903,128 @@ def test_second_order_mode_rejected_where_unsupported_and_v1_struct_accepted(gpu
         R2, t2, i2 = g.register(p.src, p.dst)
         np.testing.assert_array_equal(R1, R2)
         assert i1 == i2
+
+
+# ---------------------------------------------------------------------------------------------
+# exact node pruning of S2 (kernels_prune.cu): triangle counts for the rows of the high-degree nodes only
+# ---------------------------------------------------------------------------------------------
+NODE_PRUNED = [st for st in EXACT if st[0] not in ("hist", "t_node")]
+
+
+def compare_node_pruned(gpu, oracle, pair_idx=0):
+    """Everything downstream of S2 is identical; keys / histogram obey the same subset rules as with the threshold
+    pruning; node counts are exact where they were computed (0 elsewhere) and computed for every node a selected
+    edge touches."""
+    compare_pruned(gpu, oracle, pair_idx, stages=NODE_PRUNED)
+    tg, to = gpu.debug(pair_idx, _abi.DBG_T_NODE), oracle.debug(pair_idx, _abi.DBG_T_NODE)
+    assert ((tg == to) | (tg == 0)).all(), "a computed node count differs from the oracle's"
+    top = oracle.debug(pair_idx, _abi.DBG_TOP_EDGES)
+    ends = np.unique(np.concatenate([0xFFFF - ((top >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.int64),
+                                     0xFFFF - (top & np.uint64(0xFFFF)).astype(np.int64)]))
+    assert (tg[ends] == to[ends]).all(), "an endpoint of a selected edge has no node count"
+
+
+KITTI = dict(box=(60.0, 60.0, 6.0), tau_compat=0.6)   # ~2.3 % edge density: outlier degrees stay below the clique's counts
+
+
+@pytest.mark.parametrize("apex_path", [0, 1])
+@pytest.mark.parametrize("N,ratio,Ke,m,kw", [
+    (1200, 0.10, 256, 4, {}), (2048, 0.10, 256, 4, {}), (3000, 0.30, 512, 2, {}), (5000, 0.05, 1024, 4, KITTI),
+    (5000, 0.05, 4096, 8, KITTI), (4999, 0.04, 64, 8, KITTI), (1500, 0.08, 1, 1, {}), (6000, 0.03, 1024, 4, KITTI),
+    (10000, 0.03, 1024, 4, KITTI),
+])
+def test_node_pruned_path_matches_oracle(gpu, oracle, N, ratio, Ke, m, kw, apex_path):
+    gpu.set("triangle_path", 1)
+    gpu.set("node_prune", 2)
+    gpu.set("apex_path", apex_path)   # 1: no rank list, every edge evaluates its unknown candidates on demand
+    assert gpu.get("node_prune") == 2
+    p = synth.make_pair(N, ratio, 9300 + N + Ke, **kw)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier, num_edges=Ke, apex_per_edge=m)
+    out_g = gpu.register(p.src, p.dst)
+    out_o = oracle.register(p.src, p.dst)
+    assert gpu.get("pruned_pairs") == 1, "the pair was expected to take the kept-row kernel"
+    assert 2 <= gpu.get("kept_nodes") <= 2048
+    compare_node_pruned(gpu, oracle)
+    compare_pose(*out_g, *out_o)
+
+
+def test_node_pruning_leaves_dense_outlier_graphs_alone(gpu, oracle):
+    """Indoor scale (7.6 % density): the outliers' degrees exceed the clique's counts, every node would be kept."""
+    gpu.set("triangle_path", 1)
+    for mode in (1, 2):
+        gpu.set("node_prune", mode)
+        p = synth.make_config_pair("cfg2_3dmatch_256x5000", 11)
+        for r in (gpu, oracle):
+            set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
+        out_g, out_o = gpu.register(p.src, p.dst), oracle.register(p.src, p.dst)
+        assert gpu.get("pruned_pairs") == 0
+        compare_pruned(gpu, oracle)
+        compare_pose(*out_g, *out_o)
+
+
+def test_node_pruning_mixed_batch_and_cost_model(gpu, oracle):
+    """Pairs that prune and pairs that do not share a chunk: the tensor-core kernel runs the compacted tile list."""
+    gpu.set("triangle_path", 1)
+    gpu.set("node_prune", 2)
+    specs = [(1500, 0.10), (1400, 0.0), (2048, 0.10), (1300, 0.9), (3000, 0.02), (1100, 0.0)]
+    pairs = [synth.make_pair(n, r, 9400 + k) for k, (n, r) in enumerate(specs)]
+    for r in (gpu, oracle):
+        set_params(r, num_edges=256, apex_per_edge=4)
+    rg = gpu.register_batch([q.src for q in pairs], [q.dst for q in pairs])
+    ro = oracle.register_batch([q.src for q in pairs], [q.dst for q in pairs])
+    npr = gpu.get("pruned_pairs")
+    assert 1 <= npr < len(pairs), npr
+    for b in range(len(pairs)):
+        compare_node_pruned(gpu, oracle, b)
+        compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
+    # the cost model (node_prune = 1 would apply it; keep_debug turns that mode off, so drive it through the knob):
+    # an absurd cost prunes nothing, and the results do not move
+    gpu.set("node_prune_cost", 1000000)
+    gpu.set("node_prune", 2)
+    rg2 = gpu.register_batch([q.src for q in pairs], [q.dst for q in pairs])
+    np.testing.assert_array_equal(rg.R, rg2.R)
+    np.testing.assert_array_equal(rg.inliers, rg2.inliers)
+
+
+def test_node_pruning_is_the_default_and_invisible(gpu_lib, oracle):
+    """Default ctx (no keep_debug): outdoor-scale pairs prune down to their inlier cliques; poses equal the oracle's and
+    those of a ctx with the pruning switched off, bit for bit."""
+    ps = [synth.make_pair(6000, 0.03, 9450 + b, **KITTI) for b in range(3)]
+    set_params(oracle, tau_compat=ps[0].tau_compat, tau_inlier=ps[0].tau_inlier)
+    ro = oracle.register_batch([q.src for q in ps], [q.dst for q in ps])
+    outs = []
+    for mode in (1, 0):
+        with Registrar(lib=gpu_lib, device=0) as reg:
+            assert reg.get("node_prune") == 1
+            reg.set("node_prune", mode)
+            set_params(reg, tau_compat=ps[0].tau_compat, tau_inlier=ps[0].tau_inlier)
+            rg = reg.register_batch([q.src for q in ps], [q.dst for q in ps])
+            assert reg.get("triangle_path_used") == 1
+            assert reg.get("pruned_pairs") == (len(ps) if mode else 0)
+            if mode:   # the inlier cliques and a few central (high-degree) outliers
+                n_in = sum(len(q.inlier_idx) for q in ps)
+                assert n_in <= reg.get("kept_nodes") <= 3 * n_in
+            for b in range(len(ps)):
+                compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
+            outs.append(rg)
+    np.testing.assert_array_equal(outs[0].R, outs[1].R)
+    np.testing.assert_array_equal(outs[0].t, outs[1].t)
+    np.testing.assert_array_equal(outs[0].inliers, outs[1].inliers)
+
+
+def test_node_pruning_off_for_second_order_and_debug_dumps(gpu, oracle):
+    gpu.set("triangle_path", 1)   # keep_debug is set by the fixture, node_prune is at its default (1)
+    p = synth.make_pair(2048, 0.1, 9500)
+    for r in (gpu, oracle):
+        set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier, num_edges=256, apex_per_edge=4)
+    gpu.register(p.src, p.dst)
+    oracle.register(p.src, p.dst)
+    assert gpu.get("pruned_pairs") == 0
+    compare_pruned(gpu, oracle)   # full node counts
+    gpu.set("node_prune", 2)
+    for r in (gpu, oracle):
+        set_params(r, compat_mode=_abi.COMPAT_SECOND_ORDER, so_min_common=10)
+    out_g, out_o = gpu.register(p.src, p.dst), oracle.register(p.src, p.dst)
+    assert gpu.get("pruned_pairs") == 0
+    compare_pose(*out_g, *out_o)
