@@ -431,7 +431,33 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
     P = N * (N - 1) / 2.0
     floors = {"graph_us": 21.0 * P / lane_rate * 1e6,          # 21 individually rounded fp32 ops per node pair
               "score_us": 16.0 * K * N / lane_rate * 1e6}      # 16 FP32 instructions per (hypothesis, point)
-    if path_used == 1:
+    node_pruned = path_used == 1 and node_prune["pruned_pairs_last_chunk"] > 0
+    if node_pruned:
+        # S2 ran on the kept rows only (exact node pruning): the dominant kernel is the compatibility graph.  It is
+        # bound by FP32 issue (21 individually rounded fp32 operations per node pair, packed two per instruction
+        # where the order of operations allows), neither by HBM nor by the tensor cores; both views are given.
+        g_calls = max(1, stage_calls["graph"])
+        g_us = stage_us["graph"] / g_calls
+        g_pairs = pairs * args.steps / g_calls
+        peak_gbs = peaks.get("hbm_gbs") or 6650.0
+        g_bytes_pair = npad * stride * 4 * 2 + 24 * npad        # adjacency + its K-panel copy written, SoA points read
+        ops = 21.0 * P * g_pairs
+        roofline = {
+            "kernel": "graph_kernel (S1, compatibility graph; S2 runs on the kept rows only)", "bound": "fp32",
+            "achieved": ops / (g_us * 1e-6) / 1e12, "peak": lane_rate / 1e12, "unit": "Tops/s (fp32 lane operations)",
+            "frac": ops / (g_us * 1e-6) / lane_rate, "traffic": None,
+            "peak_source": f"148 SMs x 128 FP32 lanes x {sm_mhz:.0f} MHz (this run's clock under load)",
+            "algorithmic_ops_per_launch": ops, "launch_us": g_us, "pairs_per_launch": g_pairs,
+            "hbm": {"algorithmic_bytes_per_launch": g_bytes_pair * g_pairs,
+                    "achieved_gbs": g_bytes_pair * g_pairs / (g_us * 1e-6) / 1e9, "peak_gbs": peak_gbs,
+                    "frac": g_bytes_pair * g_pairs / (g_us * 1e-6) / 1e9 / peak_gbs},
+            "note": "the contract's bound is hbm | tensor; this kernel is bound by neither (arithmetic intensity ~ 40 fp32 "
+                    "operations per byte written), so the binding resource is reported and the HBM view given beside it",
+            "edges_per_pair": E_mean,
+            "triangles_kept_us_per_step": stage_us["triangles_kept"] / args.steps,
+        }
+        floors["triangles_us"] = 0.0   # the kept rows' share of S2 is not modelled (data dependent)
+    elif path_used == 1:
         traffic = None
         if "triangles_mma_kernel" in tj_all:
             tj = tj_all["triangles_mma_kernel"]

@@ -119,6 +119,12 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *        "triangle_prune" (tensor-core path, default 1: keep only edge keys whose count reaches
  *        a per-pair threshold proven to lie at or below the K_e-th largest count; results are
  *        unchanged, SAC_COT_DBG_EDGE_KEYS / _HIST then cover the kept edges only; GPU only),
+ *        "node_prune" (tensor-core path, default 1: a pair whose selectable edges provably join few
+ *        high-degree nodes — degree >= that threshold + 1, e.g. an inlier clique in a sparse outlier graph —
+ *        counts triangles for those nodes' rows only; results are unchanged; off while "keep_debug" is set,
+ *        because SAC_COT_DBG_T_NODE then covers the kept nodes only; 2 = on whenever the kept list fits, also
+ *        with keep_debug (tests); 0 = off; GPU only), "node_prune_cost" (default 200: a pair is pruned if
+ *        (sum of the kept nodes' degrees) x cost <= Npad^2; GPU only),
  *        "stage_timing" (0/1: bracket every pipeline stage with CUDA events on the ctx
  *        stream; setting it also clears the accumulated times; GPU only),
  *        test switches that never change a result (GPU only): "tile_runs" (tensor-core path, default 1:
@@ -126,6 +132,8 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *        kernel with the per-pair rank list (default), 1 = same kernel, exhaustive scan of every edge,
  *        2 = the global-lookup kernel that N > 51200 falls back to), "triangle_dbg" (experiments)
  *   get: "triangle_path_used" (0/1: which S2 kernels the latest chunk ran; synchronises; GPU only),
+ *        "pruned_pairs" / "kept_nodes" (node pruning in the latest chunk: pairs that took the kept-row kernel and
+ *        the nodes they kept in total; synchronises; GPU only),
  *        "launches" (kernels launched since ctx creation), "workspace_bytes",
  *        "device", "sm_count", "retries" (workspace-growth re-runs),
  *        "last_status" (deferred status of the SAC_COT_LOC_DEVICE calls since the previous query: SAC_COT_E_NOMEM
@@ -133,11 +141,13 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *        grown for the next call; synchronises),
  *        "probe_mxf4_gflops" (measures, now, the dense rate of the tensor-core triangle kernel's MMA shape with
  *        nothing else running: the roofline denominator bench.py reports against; synchronises; GPU only),
- *        "stage_us_<s>" / "stage_calls_<s>" with <s> in pack, graph, scan, theta, triangles, select,
+ *        "stage_us_<s>" / "stage_calls_<s>" with <s> in pack, graph, scan, theta, triangles, triangles_kept, select,
  *        apex, kabsch, score, finalize, exchange1 (sharded: record + all-gather + merge), exchange2
  *        (sharded: all-reduce), match_prep, match_sweep, match_exact (front end): accumulated device
  *        microseconds / launches,
- *        "comm_rank", "comm_world" (0 = no communicator)                                 */
+ *        "comm_rank", "comm_world" (0 = no communicator)
+ * Diagnostics: with SAC_COT_TRACE set in the environment the GPU library synchronises the device after every
+ * kernel launcher and names, on stderr, the first one whose kernels failed.               */
 SAC_COT_API int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value);
 SAC_COT_API int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value);
 

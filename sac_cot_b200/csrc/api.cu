@@ -665,7 +665,7 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
                                 adj_use, panel_use, L.state, L.chunk, ln.keys, L.theta, L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg));
     if (node_prune) mark(ST_TRIANGLES);
     if (node_prune)
-      KL_TRY(launch_triangles_kept(lc, L.desc, L.pairs, L.max_n, L.max_stride, adj_use, L.nplan, L.kept, L.chunk, L.state, ln.keys,
+      KL_TRY(launch_triangles_kept(lc, L.desc, L.pairs, L.max_n, L.max_stride, adj_use, L.nplan, L.kept, L.keptbits, L.chunk, L.state, ln.keys,
                                    L.hist, L.t2));
     if (node_prune) mark(ST_KEPT);
   }

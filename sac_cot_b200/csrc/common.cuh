@@ -218,7 +218,7 @@ int launch_mma_peak_probe(const LaunchCtx& lc, int clusters, int stage_pairs);
 double mma_peak_probe_flops(int clusters, int stage_pairs);
 
 // kernels_prune.cu — exact node pruning of S2 on the tensor-core path: pairs whose selectable edges join few
-// high-degree nodes count triangles for those nodes' rows only (DESIGN.md §6d)
+// high-degree nodes count triangles for those nodes' rows only (DESIGN.md §6c)
 struct NodePlan {
   uint32_t pruned;   // 1: the pair takes the kept-row kernel, the tensor-core kernel skips its tiles
   uint32_t n_keep;   // nodes of degree >= min_deg, listed ascending in the pair's slice of the kept list
@@ -237,7 +237,7 @@ int launch_node_plan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
                      int* d_total, int cost, int force);
 int launch_triangles_kept(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_n, int max_stride,
                           const uint32_t* d_adj, const NodePlan* d_plan, const unsigned short* d_kept,
-                          const ChunkDev* d_chunk, PairDev* d_state, unsigned long long* d_keys, uint32_t* d_hist,
+                          const uint32_t* d_keptbits, const ChunkDev* d_chunk, PairDev* d_state, unsigned long long* d_keys, uint32_t* d_hist,
                           unsigned long long* d_t2);
 
 // kernels_select.cu — S3 edge ranking + apex selection

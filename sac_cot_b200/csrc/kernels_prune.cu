@@ -1,4 +1,4 @@
-// kernels_prune.cu — exact node pruning of S2 (tensor-core path, DESIGN.md §6d).
+// kernels_prune.cu — exact node pruning of S2 (tensor-core path, DESIGN.md §6c).
 //
 // tri_theta_kernel certifies, per pair, a lower bound theta0 on the K_e-th largest edge count: at least K_e edges with
 // T >= theta0 exist, so no edge below theta0 can be selected.  An edge (i, j) has T_ij = |N(i) ∩ N(j)| <= deg_i - 1
@@ -15,8 +15,8 @@
 //   node_degree_kernel   exact degrees (one warp per row)
 //   node_plan_kernel     per pair: kept list (ascending), D, and the decision (cost model below)
 //   tile_compact_kernel  tile list of the tensor-core kernel without the tiles of pruned pairs
-//   triangles_kept_kernel the loop above: a warp holds R kept rows in registers, the CTA streams all rows of the pair
-//                        through shared memory in batches of 32 (cp.async, double buffered)
+//   triangles_kept_kernel the loop above: a warp holds 4 kept rows in registers, a producer warp streams all rows of
+//                        the pair through a shared-memory ring in batches of 32 (bulk copies, mbarriers)
 #include "common.cuh"
 
 #include <algorithm>
@@ -28,7 +28,6 @@ namespace {
 constexpr int kKeptThreads = 512;   // 16 warps
 constexpr int kKeptRows = 4;        // kept rows per warp
 constexpr int kKeptRowsPerCta = (kKeptThreads / 32) * kKeptRows;  // 64
-constexpr int kKeptKeyCap = 2 * kKeptRowsPerCta * 32;             // staged keys: two batches' worst case
 
 // A pair whose AVERAGE degree already reaches theta0 + 1 keeps most of its nodes: not worth a look (the degree pass
 // reads the whole adjacency).  Skipping a pair is always exact — it then takes the tensor-core kernel.
@@ -51,20 +50,31 @@ __global__ void __launch_bounds__(256) node_degree_kernel(const PairDesc* __rest
   const uint4* base = reinterpret_cast<const uint4*>(adj + d.adj_off);
   const int q4 = d.stride >> 2;  // uint4 per row
   unsigned short* out = deg + d.node_off;
-  for (int r = blockIdx.x * 8 + warp; r < d.N; r += gridDim.x * 8) {
-    const uint4* rp = base + static_cast<size_t>(r) * q4;
-    int c = 0;
+  // four rows per warp and step: the pass is bound by HBM (the whole adjacency is read once), so every lane keeps
+  // several independent 16-byte loads in flight
+  constexpr int kRows = 4;
+  for (int r0 = (blockIdx.x * 8 + warp) * kRows; r0 < d.N; r0 += gridDim.x * 8 * kRows) {
+    int c[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) c[k] = 0;
     for (int q = lane; q < q4; q += 32) {
-      const uint4 w = __ldg(rp + q);
-      c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+      uint4 w[kRows];
+#pragma unroll
+      for (int k = 0; k < kRows; ++k)
+        w[k] = r0 + k < d.N ? __ldg(base + static_cast<size_t>(r0 + k) * q4 + q) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) c[k] += __popc(w[k].x) + __popc(w[k].y) + __popc(w[k].z) + __popc(w[k].w);
     }
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0) out[r] = static_cast<unsigned short>(c);  // deg <= N - 1 <= 65534
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int v = __reduce_add_sync(0xffffffffu, c[k]);
+      if (lane == 0 && r0 + k < d.N) out[r0 + k] = static_cast<unsigned short>(v);  // deg <= N - 1 <= 65534
+    }
   }
 }
 
 // One CTA per pair.  Decision: the kept-row kernel costs ~ sum of the kept degrees x row length, the tensor-core
-// kernel ~ Npad^3, so the pair is pruned if (sum of kept degrees) x cost <= Npad^2 (cost: api.cu, DESIGN.md §6d).
+// kernel ~ Npad^3, so the pair is pruned if (sum of kept degrees) x cost <= Npad^2 (cost: api.cu, DESIGN.md §6c).
 __global__ void __launch_bounds__(1024) node_plan_kernel(const PairDesc* __restrict__ descs,
                                                          const ChunkDev* __restrict__ chunk,
                                                          const PairDev* __restrict__ state,
@@ -179,144 +189,231 @@ __global__ void __launch_bounds__(1024) tile_compact_kernel(const uint2* __restr
   if (t == 0) *out_total = s_base;
 }
 
-// popc(a & b) summed over WPL words per lane with carry-save adders (POPC shares the slow XU pipe with REDUX)
+// popc(x & y) summed over WPL words per lane.  POPC runs on the XU pipe at a quarter of the ALU rate (16 lanes per
+// clock and SM), so the words first go through a carry-save adder tree (two LOP3 per adder): 10 words need 4 POPC
+// instead of 10, 5 words need 3.
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+  sum = a ^ b ^ c;
+  carry = (a & b) | (c & (a ^ b));
+}
 template <int WPL>
-__device__ __forceinline__ int and_popc(const uint32_t (&x)[WPL], const uint32_t* __restrict__ y) {
+__device__ __forceinline__ uint32_t and_popc(const uint32_t (&x)[WPL], const uint32_t (&y)[WPL]) {
   uint32_t a[WPL];
 #pragma unroll
-  for (int s = 0; s < WPL; ++s) a[s] = x[s] & y[32 * s];
-  int c = 0;
-  int s = 0;
+  for (int s = 0; s < WPL; ++s) a[s] = x[s] & y[s];
+  if constexpr (WPL == 10) {
+    uint32_t s0, c0, s1, c1, s2, c2, S, c3, t0, f0, T, f1;
+    csa(a[0], a[1], a[2], s0, c0);
+    csa(a[3], a[4], a[5], s1, c1);
+    csa(a[6], a[7], a[8], s2, c2);
+    csa(s0, s1, s2, S, c3);
+    const uint32_t ones = S ^ a[9], c4 = S & a[9];
+    csa(c0, c1, c2, t0, f0);   // weight 2 -> sum of weight 2, carry of weight 4
+    csa(c3, c4, t0, T, f1);
+    return __popc(ones) + 2 * __popc(T) + 4 * (__popc(f0) + __popc(f1));
+  } else if constexpr (WPL == 5) {
+    uint32_t s0, c0, ones, c1;
+    csa(a[0], a[1], a[2], s0, c0);
+    csa(s0, a[3], a[4], ones, c1);
+    return __popc(ones) + 2 * (__popc(c0) + __popc(c1));
+  } else {
+    uint32_t c = 0;
 #pragma unroll
-  for (; s + 2 < WPL; s += 3) {
-    const uint32_t lo = a[s] ^ a[s + 1] ^ a[s + 2];
-    const uint32_t hi = (a[s] & a[s + 1]) | (a[s + 2] & (a[s] ^ a[s + 1]));
-    c += __popc(lo) + 2 * __popc(hi);
+    for (int s = 0; s < WPL; ++s) c += __popc(a[s]);
+    return c;
   }
-#pragma unroll
-  for (; s < WPL; ++s) c += __popc(a[s]);
-  return c;
 }
 
-// grid (row blocks, pairs, row slices): with few pairs in the chunk the streamed rows are split over gridDim.z CTAs
-// (a single pair would otherwise keep a handful of SMs busy) and the node sums are added atomically.
-// Shared memory: row buffers [2][32][stride] | staged keys [kKeptKeyCap] | histogram.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// grid (row slices, pairs, block lanes): a CTA takes one slice of the pair's rows as the streamed operand and walks the
+// kept rows of the pair against it, 64 at a time (blocks blockIdx.z, blockIdx.z + gridDim.z, ...); node sums are added
+// atomically.  Slices and block lanes follow from the pairs in the chunk (about four CTAs per SM): a single pair
+// fills the device, and a chunk without any pruned pair costs one wave of CTAs that leave at once.
+// 16 warps with 4 kept rows each in registers; the pair's rows stream through a ring of kKeptStages shared-memory
+// buffers, 32 at a time (contiguous in memory: one bulk copy, SASS UBLKCP, issued by one lane two batches ahead),
+// guarded by full / empty mbarriers — no CTA-wide barrier inside the loop.  For kept row k and a neighbour j of it the consumers form
+// popc(row_k & row_j) per lane; the warp-wide sum T_kj is only needed where a key can arise (j kept too, j > k),
+// everything else goes into per-lane partial node sums that are reduced once at the end.  Keys are staged per warp.
+// Shared memory: ring [kKeptStages][32 * max_stride] | key buffers [16][kKeptWarpKeys] | histogram | barriers.
+constexpr int kKeptStages = 3;
+constexpr int kKeptWarpKeys = 64;
+constexpr int kKeptConsumers = kKeptThreads / 32;       // 16
+
 template <int WPL>
-__global__ void __launch_bounds__(kKeptThreads) triangles_kept_kernel(
+__global__ void __launch_bounds__(kKeptThreads, 1) triangles_kept_kernel(
     const PairDesc* __restrict__ descs, const uint32_t* __restrict__ adj, const NodePlan* __restrict__ plan,
-    const unsigned short* __restrict__ kept, const ChunkDev* __restrict__ chunk, PairDev* __restrict__ state,
-    unsigned long long* __restrict__ keys, uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2,
-    int max_stride, int bins) {
+    const unsigned short* __restrict__ kept, const uint32_t* __restrict__ keptbits, const ChunkDev* __restrict__ chunk,
+    PairDev* __restrict__ state, unsigned long long* __restrict__ keys, uint32_t* __restrict__ hist,
+    unsigned long long* __restrict__ t2, int max_stride, int bins) {
   if (chunk->overflow || !chunk->use_tensor) return;
   const int pair = blockIdx.y;
   const NodePlan pl = plan[pair];
-  const int a0 = blockIdx.x * kKeptRowsPerCta;
-  if (!pl.pruned || a0 >= static_cast<int>(pl.n_keep)) return;
+  if (!pl.pruned) return;
   const PairDesc d = descs[pair];
   if (d.stride > 32 * WPL) return;  // launched with the instance that fits the chunk's longest row
+  // batches of 32 rows: row block b <-> adjacency word b of a kept row; this CTA's slice of them
+  const int b_begin = static_cast<int>((static_cast<long long>(d.stride) * blockIdx.x) / gridDim.x);
+  const int b_end = static_cast<int>((static_cast<long long>(d.stride) * (blockIdx.x + 1)) / gridDim.x);
+  if (b_begin >= b_end) return;
   const uint32_t* adjp = adj + d.adj_off;
-  extern __shared__ __align__(16) unsigned char kp_smem[];
-  uint32_t* buf = reinterpret_cast<uint32_t*>(kp_smem);  // [2][32 * stride]
-  unsigned long long* kst = reinterpret_cast<unsigned long long*>(buf + static_cast<size_t>(2) * 32 * max_stride);
-  uint32_t* hist_s = reinterpret_cast<uint32_t*>(kst + kKeptKeyCap);
-  __shared__ uint32_t s_nkeys;
-  __shared__ unsigned long long s_kbase;
+  extern __shared__ __align__(128) unsigned char kp_smem[];
+  uint32_t* ring = reinterpret_cast<uint32_t*>(kp_smem);
+  const size_t slot_words = static_cast<size_t>(32) * max_stride;
+  unsigned long long* kbuf = reinterpret_cast<unsigned long long*>(ring + kKeptStages * slot_words);
+  uint32_t* hist_s = reinterpret_cast<uint32_t*>(kbuf + kKeptConsumers * kKeptWarpKeys);
+  uint64_t* full = reinterpret_cast<uint64_t*>(hist_s + ((bins + 1) & ~1));
+  uint64_t* empty = full + kKeptStages;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int my_bins = min(bins, (d.N >> 4) + 1);
   for (int k = t; k < my_bins; k += kKeptThreads) hist_s[k] = 0u;
-  if (t == 0) s_nkeys = 0u;
-
-  // this warp's kept rows, resident in registers
-  int krow[kKeptRows];
-  uint32_t rk[kKeptRows][WPL];
-#pragma unroll
-  for (int r = 0; r < kKeptRows; ++r) {
-    const int a = a0 + warp * kKeptRows + r;
-    const bool valid = a < static_cast<int>(pl.n_keep);
-    krow[r] = valid ? static_cast<int>(kept[static_cast<size_t>(pair) * kNodeKeepMax + a]) : -1;
-#pragma unroll
-    for (int s = 0; s < WPL; ++s) {
-      const int w = lane + 32 * s;
-      rk[r][s] = (valid && w < d.stride) ? __ldg(adjp + static_cast<size_t>(krow[r]) * d.stride + w) : 0u;
+  if (t == 0) {
+    for (int s = 0; s < kKeptStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kKeptConsumers);
     }
+    mbar_fence_init();
   }
-  unsigned long long acc[kKeptRows];
-#pragma unroll
-  for (int r = 0; r < kKeptRows; ++r) acc[r] = 0ull;
-  const uint32_t thr = pl.min_deg - 1u;  // theta0
-  // batches of 32 rows: row block b <-> adjacency word b of a kept row; this CTA's slice of them
-  const int nb_all = d.stride;
-  const int b_begin = static_cast<int>((static_cast<long long>(nb_all) * blockIdx.z) / gridDim.z);
-  const int nb = static_cast<int>((static_cast<long long>(nb_all) * (blockIdx.z + 1)) / gridDim.z);
-  if (b_begin >= nb) return;
-  const int q4 = (32 * d.stride) >> 2;   // uint4 per batch (the 32 rows are contiguous in memory)
-  auto issue = [&](int b) {
-    const uint4* src = reinterpret_cast<const uint4*>(adjp + static_cast<size_t>(b) * 32 * d.stride);
-    const uint32_t dst = smem_u32(buf + static_cast<size_t>((b - b_begin) & 1) * 32 * max_stride);
-    for (int q = t; q < q4; q += kKeptThreads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * q), "l"(src + q) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  __syncthreads();
+  const uint32_t batch_bytes = static_cast<uint32_t>(32 * d.stride * 4);
+
+  // The CTA walks the pair's kept rows 64 at a time and streams its slice of the rows once per such block (from
+  // the L2 after the first time).  The ring's use counter runs on across the blocks (q0 = batches streamed so far).
+  // lane 0 of warp 0 also issues the bulk copies, kKeptStages - 1 batches ahead of the batch the warps work on
+  int q0 = 0;
+  auto issue = [&](int bn) {
+    const int qn = q0 + bn - b_begin, sn = qn % kKeptStages;
+    if (qn >= kKeptStages) mbar_wait(&empty[sn], static_cast<uint32_t>((qn / kKeptStages - 1) & 1));
+    mbar_arrive_expect_tx(&full[sn], batch_bytes);
+    bulk_g2s(ring + sn * slot_words, adjp + static_cast<size_t>(bn) * 32 * d.stride, batch_bytes, &full[sn]);
   };
-  auto flush = [&]() {  // all threads; s_nkeys is stable (read after a barrier)
-    const uint32_t n = s_nkeys;
-    if (n == 0u) return;
-    if (t == 0) s_kbase = state[pair].key_base + atomicAdd(&state[pair].key_count, static_cast<unsigned long long>(n));
-    __syncthreads();
-    unsigned long long* dst = keys + s_kbase;
-    for (uint32_t k = t; k < n; k += kKeptThreads) dst[k] = kst[k];
-    __syncthreads();
-    if (t == 0) s_nkeys = 0u;
-    __syncthreads();
-  };
-  uint32_t mnext[kKeptRows];
-#pragma unroll
-  for (int r = 0; r < kKeptRows; ++r) mnext[r] = krow[r] >= 0 ? __ldg(adjp + static_cast<size_t>(krow[r]) * d.stride + b_begin) : 0u;
-  issue(b_begin);
-  for (int b = b_begin; b < nb; ++b) {
-    uint32_t m[kKeptRows];
+  for (int a0 = static_cast<int>(blockIdx.z) * kKeptRowsPerCta; a0 < static_cast<int>(pl.n_keep);
+       a0 += static_cast<int>(gridDim.z) * kKeptRowsPerCta, q0 += b_end - b_begin) {
+    if (t == 0)
+      for (int bn = b_begin; bn < b_end && bn < b_begin + kKeptStages - 1; ++bn) issue(bn);
+    int krow[kKeptRows];
+    uint32_t rk[kKeptRows][WPL];
 #pragma unroll
     for (int r = 0; r < kKeptRows; ++r) {
-      m[r] = mnext[r];
-      mnext[r] = (krow[r] >= 0 && b + 1 < nb) ? __ldg(adjp + static_cast<size_t>(krow[r]) * d.stride + b + 1) : 0u;
-    }
-    if (b + 1 < nb) {
-      issue(b + 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const uint32_t* rows = buf + static_cast<size_t>((b - b_begin) & 1) * 32 * max_stride + lane;
-    uint32_t any = 0u;
+      const int a = a0 + warp * kKeptRows + r;
+      const bool valid = a < static_cast<int>(pl.n_keep);
+      krow[r] = valid ? static_cast<int>(kept[static_cast<size_t>(pair) * kNodeKeepMax + a]) : -1;
 #pragma unroll
-    for (int r = 0; r < kKeptRows; ++r) any |= m[r];
-    while (any) {
-      const int bb = __ffs(any) - 1;
-      any &= any - 1u;
-      const uint32_t* y = rows + bb * d.stride;
-      const int j = 32 * b + bb;
-#pragma unroll
-      for (int r = 0; r < kKeptRows; ++r) {
-        if ((m[r] >> bb) & 1u) {  // warp-uniform
-          const uint32_t T = static_cast<uint32_t>(__reduce_add_sync(0xffffffffu, and_popc<WPL>(rk[r], y)));
-          acc[r] += T;
-          if (lane == 0 && j > krow[r] && T >= thr) {
-            const uint32_t pos = atomicAdd(&s_nkeys, 1u);
-            kst[pos] = (static_cast<unsigned long long>(T) << 32) |
-                       (static_cast<unsigned long long>(0xFFFFu - static_cast<uint32_t>(krow[r])) << 16) |
-                       static_cast<unsigned long long>(0xFFFFu - static_cast<uint32_t>(j));
-            atomicAdd(&hist_s[T >> 4], 1u);
-          }
-        }
+      for (int s = 0; s < WPL; ++s) {
+        const int w = lane + 32 * s;
+        rk[r][s] = (valid && w < d.stride) ? __ldg(adjp + static_cast<size_t>(krow[r]) * d.stride + w) : 0u;
       }
     }
-    __syncthreads();  // the batch buffer may be overwritten; every key of this batch is staged
-    if (s_nkeys > static_cast<uint32_t>(kKeptKeyCap / 2)) flush();
-  }
-  flush();
+    unsigned long long acc[kKeptRows];  // warp-uniform part of the node sums (the reduced counts)
+    uint32_t accl[kKeptRows];           // per-lane part (counts that were never reduced); < 2^32: see the header
 #pragma unroll
-  for (int r = 0; r < kKeptRows; ++r)
-    if (lane == 0 && krow[r] >= 0 && acc[r]) atomicAdd(&t2[d.node_off + krow[r]], acc[r]);  // t2 starts at zero
+    for (int r = 0; r < kKeptRows; ++r) {
+      acc[r] = 0ull;
+      accl[r] = 0u;
+    }
+    const uint32_t thr = pl.min_deg - 1u;  // theta0
+    const uint32_t* kbp = keptbits + d.mask_off;
+    unsigned long long* kw = kbuf + warp * kKeptWarpKeys;
+    unsigned long long* const keyp = keys + state[pair].key_base;
+    int nk = 0;  // staged keys (warp-uniform)
+    auto flush = [&]() {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&state[pair].key_count, static_cast<unsigned long long>(nk));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      __syncwarp();
+      for (int k = lane; k < nk; k += 32) keyp[base + k] = kw[k];
+      __syncwarp();
+      nk = 0;
+    };
+    // one (kept row, neighbour row) item: count, node sum, key
+    auto item = [&](int r, uint32_t c, int j, bool jkept) {
+      if (jkept && j > krow[r]) {  // a key can arise: the count itself is needed
+        const uint32_t T = __reduce_add_sync(0xffffffffu, c);
+        acc[r] += T;
+        if (T >= thr) {
+          if (lane == 0) {
+            kw[nk] = (static_cast<unsigned long long>(T) << 32) |
+                     (static_cast<unsigned long long>(0xFFFFu - static_cast<uint32_t>(krow[r])) << 16) |
+                     static_cast<unsigned long long>(0xFFFFu - static_cast<uint32_t>(j));
+            atomicAdd(&hist_s[T >> 4], 1u);
+          }
+          if (++nk == kKeptWarpKeys) flush();
+        }
+      } else {
+        accl[r] += c;
+      }
+    };
+    // adjacency words of the kept rows for 32 batches at a time: lane l holds word blk + l (one coalesced load per
+    // row and 32 batches; the batch's word then comes from a shuffle)
+    uint32_t mw[kKeptRows], kbw32 = 0u;
+    int blk = -1;
+    for (int b = b_begin; b < b_end; ++b) {
+      const int q = q0 + b - b_begin, s = q % kKeptStages;
+      if (warp == 0) {
+        if (lane == 0 && b + kKeptStages - 1 < b_end) issue(b + kKeptStages - 1);
+        __syncwarp();
+      }
+      if ((b & ~31) != blk) {
+        blk = b & ~31;
+        const int w = blk + lane;
+#pragma unroll
+        for (int r = 0; r < kKeptRows; ++r)
+          mw[r] = (krow[r] >= 0 && w < d.stride) ? __ldg(adjp + static_cast<size_t>(krow[r]) * d.stride + w) : 0u;
+        kbw32 = w < d.stride ? __ldg(kbp + w) : 0u;
+      }
+      uint32_t m[kKeptRows];
+#pragma unroll
+      for (int r = 0; r < kKeptRows; ++r) m[r] = __shfl_sync(0xffffffffu, mw[r], b & 31);
+      const uint32_t kbw = __shfl_sync(0xffffffffu, kbw32, b & 31);
+      uint32_t common = m[0];
+#pragma unroll
+      for (int r = 1; r < kKeptRows; ++r) common &= m[r];
+      mbar_wait(&full[s], static_cast<uint32_t>((q / kKeptStages) & 1));
+      const uint32_t* rows = ring + s * slot_words + lane;
+      // neighbours of all four rows (the clique's rows against each other): the streamed row is read once and the
+      // four counts are independent instruction streams
+      for (uint32_t bits = common; bits;) {
+        const int bb = __ffs(bits) - 1;
+        bits &= bits - 1u;
+        const uint32_t* y = rows + bb * d.stride;
+        uint32_t yv[WPL];
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) yv[w] = y[32 * w];
+        uint32_t c[kKeptRows];
+#pragma unroll
+        for (int r = 0; r < kKeptRows; ++r) c[r] = and_popc<WPL>(rk[r], yv);
+        const int j = 32 * b + bb;
+        const bool jkept = (kbw >> bb) & 1u;
+#pragma unroll
+        for (int r = 0; r < kKeptRows; ++r) item(r, c[r], j, jkept);
+      }
+      // the others, row by row (one neighbour of every row per step, to have four chains in flight, was measured
+      // slower: 5.5 ms against 4.0 ms per 128-pair KITTI-scale step — the rows' neighbour counts differ too much)
+#pragma unroll
+      for (int r = 0; r < kKeptRows; ++r) {
+        for (uint32_t bits = m[r] & ~common; bits;) {
+          const int bb = __ffs(bits) - 1;
+          bits &= bits - 1u;
+          const uint32_t* y = rows + bb * d.stride;
+          uint32_t yv[WPL];
+#pragma unroll
+          for (int w = 0; w < WPL; ++w) yv[w] = y[32 * w];
+          item(r, and_popc<WPL>(rk[r], yv), 32 * b + bb, (kbw >> bb) & 1u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    if (nk) flush();
+#pragma unroll
+    for (int r = 0; r < kKeptRows; ++r) {
+      const unsigned long long tot = acc[r] + __reduce_add_sync(0xffffffffu, accl[r]);
+      if (lane == 0 && krow[r] >= 0 && tot) atomicAdd(&t2[d.node_off + krow[r]], tot);  // t2 starts at zero
+    }
+  }
+  __syncthreads();
   uint32_t* histp = hist + static_cast<size_t>(pair) * kHistBins;
   for (int k = t; k < my_bins; k += kKeptThreads) {
     const uint32_t v = hist_s[k];
@@ -325,7 +422,8 @@ __global__ void __launch_bounds__(kKeptThreads) triangles_kept_kernel(
 }
 
 size_t kept_smem_bytes(int max_stride, int bins) {
-  return static_cast<size_t>(2) * 32 * max_stride * 4 + static_cast<size_t>(kKeptKeyCap) * 8 + static_cast<size_t>(bins) * 4;
+  return static_cast<size_t>(kKeptStages) * 32 * max_stride * 4 + static_cast<size_t>(kKeptConsumers) * kKeptWarpKeys * 8 +
+         static_cast<size_t>((bins + 1) & ~1) * 4 + 2 * kKeptStages * 8;
 }
 
 }  // namespace
@@ -345,7 +443,7 @@ int launch_node_plan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
                      unsigned short* d_kept, uint32_t* d_keptbits, const uint2* d_tiles, int total_tiles, uint2* d_tiles_out,
                      int* d_total, int cost, int force) {
   int gx = (8 * lc.sm_count + pairs - 1) / pairs;
-  gx = std::max(1, std::min(gx, (max_npad + 7) / 8));
+  gx = std::max(1, std::min(gx, (max_npad + 31) / 32));
   node_degree_kernel<<<dim3(gx, pairs), 256, 0, lc.stream>>>(d_desc, d_adj, d_chunk, d_state, d_theta, d_deg, force);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -static_cast<int>(e);
@@ -359,21 +457,21 @@ int launch_node_plan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
 
 int launch_triangles_kept(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_n, int max_stride,
                           const uint32_t* d_adj, const NodePlan* d_plan, const unsigned short* d_kept,
-                          const ChunkDev* d_chunk, PairDev* d_state, unsigned long long* d_keys, uint32_t* d_hist,
+                          const uint32_t* d_keptbits, const ChunkDev* d_chunk, PairDev* d_state, unsigned long long* d_keys, uint32_t* d_hist,
                           unsigned long long* d_t2) {
   if (max_stride > 320) return 0;  // no pair of the chunk can be pruned (node_plan_kernel left them alone)
   const int bins = (max_n >> 4) + 1;
   const size_t smem = kept_smem_bytes(max_stride, bins);
-  // a pruned pair keeps a few hundred nodes (~6 row blocks): aim at two CTAs per SM
-  int slices = (2 * lc.sm_count + 6 * pairs - 1) / (6 * pairs);
-  slices = std::max(1, std::min(slices, std::min(32, max_stride / 4)));
-  const dim3 grid((kNodeKeepMax + kKeptRowsPerCta - 1) / kKeptRowsPerCta, pairs, slices);
+  const int want = (4 * lc.sm_count + pairs - 1) / pairs;            // CTAs per pair
+  const int slices = std::max(1, std::min(want, max_stride / 8));    // at least eight batches of 32 rows per slice
+  const int lanes = std::max(1, std::min((want + slices - 1) / slices, kNodeKeepMax / kKeptRowsPerCta));
+  const dim3 grid(slices, pairs, lanes);
   if (max_stride <= 160)
-    triangles_kept_kernel<5><<<grid, kKeptThreads, smem, lc.stream>>>(d_desc, d_adj, d_plan, d_kept, d_chunk, d_state, d_keys,
-                                                                      d_hist, d_t2, max_stride, bins);
+    triangles_kept_kernel<5><<<grid, kKeptThreads, smem, lc.stream>>>(d_desc, d_adj, d_plan, d_kept, d_keptbits, d_chunk,
+                                                                         d_state, d_keys, d_hist, d_t2, max_stride, bins);
   else
-    triangles_kept_kernel<10><<<grid, kKeptThreads, smem, lc.stream>>>(d_desc, d_adj, d_plan, d_kept, d_chunk, d_state, d_keys,
-                                                                       d_hist, d_t2, max_stride, bins);
+    triangles_kept_kernel<10><<<grid, kKeptThreads, smem, lc.stream>>>(d_desc, d_adj, d_plan, d_kept, d_keptbits, d_chunk,
+                                                                          d_state, d_keys, d_hist, d_t2, max_stride, bins);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }

@@ -294,52 +294,78 @@ __global__ void __launch_bounds__(128) select_apex_kernel(const PairDesc* __rest
   }
 }
 
-// Node-pruned pairs (kernels_prune.cu), one warp: walks the candidates of edge (ri, rj) that lie OUTSIDE the kept set
-// (kb = the pair's kept-node bit mask) and returns whether one of them has a count >= bound.  ts[k] of such a node is
-// 0 (nothing known), an upper bound with kApexBoundFlag set, or the exact count (evaluated for an earlier edge of this
-// CTA).  Bounds, cheapest first:
+// Node-pruned pairs (kernels_prune.cu), one warp: looks at the candidates of edge (ri, rj) that lie OUTSIDE the kept
+// set (kb = the pair's kept-node bit mask, degs = its exact degrees, both staged in shared memory) and returns
+// whether one of them has a count >= bound.  ts[k] of such a node is 0 (nothing known), an upper bound with
+// kApexBoundFlag set, or the exact count (evaluated for an earlier edge of this CTA).  Bounds, cheapest first:
 //   t_k <= deg_k (deg_k - 1) / 2                                   (every T_kn <= deg_k - 1)
 //   t_k <= 1/2 sum_{n in N(k)} (min(deg_k, deg_n) - 1)             (one degree lookup per neighbour)
 // and only a node whose second bound still reaches `bound` is evaluated exactly,
 //   t_k = 1/2 sum_{n in N(k)} popc(row_k & row_n).
-// Control flow is warp-uniform throughout: the words that hold such candidates are found with one ballot per 32
-// words and their bits are walked by the whole warp.  Only the PRUNED instance of the apex kernel carries this code.
+// Phase 1 is lane-parallel and free of warp-level primitives: every lane classifies the candidates in its own words
+// (all loads independent: one memory latency per edge).  Phase 2 serves the few that need the second bound or the
+// exact count, with warp-uniform control flow.  Only the PRUNED instance of the apex kernel carries this code.
 constexpr uint32_t kApexBoundFlag = 0x80000000u;  // counts are < 2^31
+constexpr int kApexPrunedWords = kNodePruneMaxNpad / 1024;  // adjacency words per lane: 10
 __device__ __forceinline__ bool apex_outside_candidates(const uint32_t* __restrict__ adjp, int stride,
                                                         const uint32_t* __restrict__ ri, const uint32_t* __restrict__ rj,
-                                                        const uint32_t* __restrict__ kb,
-                                                        const unsigned short* __restrict__ degp, uint32_t* ts,
+                                                        const uint32_t* kb, const unsigned short* degs, uint32_t* ts,
                                                         uint32_t bound) {
   const int lane = threadIdx.x & 31;
-  bool upset = false;  // warp-uniform
-  for (int w0 = 0; w0 < stride; w0 += 32) {
-    const int w = w0 + lane;
-    const uint32_t mine = w < stride ? (ri[w] & rj[w] & ~kb[w]) : 0u;
-    unsigned act = __ballot_sync(0xffffffffu, mine != 0u);
+  uint32_t need[kApexPrunedWords];
+  bool upset = false;
+#pragma unroll
+  for (int s = 0; s < kApexPrunedWords; ++s) {
+    const int w = 32 * s + lane;
+    need[s] = w < stride ? (ri[w] & rj[w] & ~kb[w]) : 0u;
+  }
+#pragma unroll
+  for (int s = 0; s < kApexPrunedWords; ++s) {
+    uint32_t bits = need[s], keep = 0u;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1u;
+      const int k = 32 * (32 * s + lane) + b;
+      const uint32_t v = ts[k];
+      if (v == 0u) {
+        const uint32_t dk = degs[k];
+        if (dk * (dk - 1u) / 2u >= bound) keep |= 1u << b;
+      } else if (v & kApexBoundFlag) {
+        if ((v & ~kApexBoundFlag) >= bound) keep |= 1u << b;
+      } else {
+        upset |= v >= bound;
+      }
+    }
+    need[s] = keep;
+  }
+  upset = __any_sync(0xffffffffu, upset);
+#pragma unroll
+  for (int s = 0; s < kApexPrunedWords; ++s) {
+    unsigned act = __ballot_sync(0xffffffffu, need[s] != 0u);
     while (act) {
       const int src = __ffs(act) - 1;
       act &= act - 1u;
-      uint32_t bits = __shfl_sync(0xffffffffu, mine, src);
+      uint32_t bits = __shfl_sync(0xffffffffu, need[s], src);
       while (bits) {
-        const int k = 32 * (w0 + src) + __ffs(bits) - 1;
+        const int k = 32 * (32 * s + src) + __ffs(bits) - 1;
         bits &= bits - 1u;
-        uint32_t v = ts[k];  // one shared-memory word: the same value in every lane
+        uint32_t v = ts[k];  // one shared-memory word: the same value in every lane (it may have moved on since phase 1)
         const uint32_t* rk = adjp + static_cast<size_t>(k) * stride;
         if (v == 0u) {
-          const uint32_t dk = degp[k];
-          if (dk * (dk - 1u) / 2u < bound) continue;
-          unsigned long long ub = 0;  // second bound
+          const uint32_t dk = degs[k];
+          uint32_t ub = 0;  // second bound, per lane: <= 10 words x 32 neighbours x 65534
           for (int x = lane; x < stride; x += 32) {
             uint32_t nb = rk[x];
             while (nb) {
               const int b2 = __ffs(nb) - 1;
               nb &= nb - 1u;
-              ub += min(dk, static_cast<uint32_t>(degp[32 * x + b2])) - 1u;  // an edge: both degrees >= 1
+              ub += min(dk, static_cast<uint32_t>(degs[32 * x + b2])) - 1u;  // an edge: both degrees >= 1
             }
           }
+          unsigned long long ub64 = ub;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) ub += __shfl_xor_sync(0xffffffffu, ub, o);
-          v = static_cast<uint32_t>(ub >> 1) | kApexBoundFlag;
+          for (int o = 16; o > 0; o >>= 1) ub64 += __shfl_xor_sync(0xffffffffu, ub64, o);
+          v = static_cast<uint32_t>(ub64 >> 1) | kApexBoundFlag;
           __syncwarp();
           if (lane == 0) ts[k] = v;  // another warp of the CTA may store this or the exact count: either is valid
           __syncwarp();
@@ -404,8 +430,13 @@ __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const 
   // The PRUNED instance handles those pairs, the plain one all the others (both are launched when the chunk may
   // hold pruned pairs; a CTA of the wrong kind leaves at once).
   if ((plan != nullptr && plan[pair].pruned != 0u) != PRUNED) return;
-  const unsigned short* degp = PRUNED ? deg + d.node_off : nullptr;
-  const uint32_t* kbp = PRUNED ? keptbits + d.mask_off : nullptr;
+  // PRUNED: the pair's degrees and kept-node bits follow the rank list in shared memory
+  unsigned short* deg_s = reinterpret_cast<unsigned short*>(apex_ts + d.Npad + 2 * kApexCap);
+  uint32_t* kb_s = reinterpret_cast<uint32_t*>(deg_s + d.Npad);
+  if constexpr (PRUNED) {
+    for (int k = threadIdx.x; k < d.Npad; k += kApexThreads) deg_s[k] = k < d.N ? deg[d.node_off + k] : static_cast<unsigned short>(0);
+    for (int k = threadIdx.x; k < d.stride; k += kApexThreads) kb_s[k] = keptbits[d.mask_off + k];
+  }
   const int lane = threadIdx.x & 31, tid = threadIdx.x;
   unsigned long long* rank_list = reinterpret_cast<unsigned long long*>(apex_ts + d.Npad);  // [kApexCap]
   {
@@ -512,7 +543,7 @@ __global__ void __launch_bounds__(kApexThreads) select_apex_staged_kernel(const 
       // reaches the m-th hit's count (a tie would go to the lower index: be strict).  Without m hits every unknown
       // candidate is evaluated (bound 0).
       const uint32_t bound = found >= m ? t_mth : 0u;
-      const bool upset = apex_outside_candidates(adj + d.adj_off, d.stride, ri, rj, kbp, degp, apex_ts, bound);
+      const bool upset = apex_outside_candidates(adj + d.adj_off, d.stride, ri, rj, kb_s, deg_s, apex_ts, bound);
       if (found >= m && !upset) continue;
       // otherwise the exhaustive path below decides among the known candidates: with m hits, the ones left unknown
       // (count 0) lie strictly below the m-th hit and cannot be selected
@@ -643,7 +674,8 @@ int launch_select_apex(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, i
     auto go = [&](auto kernel_plain, auto kernel_pruned) {
       kernel_plain<<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl, d_plan, d_deg, d_keptbits);
       if (d_plan) {
-        kernel_pruned<<<grid, kApexThreads, smem, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl, d_plan, d_deg, d_keptbits);
+        const size_t smem_pruned = smem + static_cast<size_t>(max_npad) * 2 + static_cast<size_t>(max_npad / 32) * 4;
+        kernel_pruned<<<grid, kApexThreads, smem_pruned, lc.stream>>>(d_desc, d_adj, d_t2, d_top, d_tri, Ke, m, rl, d_plan, d_deg, d_keptbits);
         launched = 2;
       }
     };
