@@ -651,8 +651,10 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
     panel_use = L.panel2;
     mark(ST_GRAPH);  // the first pass and the rebuild count as graph construction
   }
-  // exact node pruning: first-order graph, unsharded, rows short enough for the kept-row kernel
+  // exact node pruning: first-order graph, rows short enough for the kept-row kernel; not for the sharded phases
+  // (stop_after_edges: their later parts rank apexes from complete node sums, also with world = 1)
   const bool node_prune = tri_mode != 0 && ctx->tri_prune && ctx->node_prune != 0 && L.adj2 == nullptr && world <= 1 &&
+                          !stop_after_edges &&
                           L.max_npad <= kNodePruneMaxNpad && L.total_tiles > 0 && ctx->apex_path != 2 &&
                           (ctx->node_prune >= 2 || !ctx->keep_debug);
   if (tri_mode != 0) {

@@ -993,14 +993,14 @@ __device__ __forceinline__ int theta_sample(const PairDesc& d, const uint32_t* _
 template <typename Add>
 __device__ __forceinline__ void theta_count_chunk(const PairDesc& d, const uint32_t* __restrict__ adjp, const int* nodes,
                                                   const uint32_t* emask, uint32_t* rows_s, int nsel, int c0, int cw,
-                                                  int cw_max, Add add) {
+                                                  int cw_max, Add add, int j_begin = 0, int j_end = 4) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   for (int r = warp; r < nsel; r += 32) {
     const uint32_t* rp = adjp + static_cast<size_t>(nodes[r]) * d.stride + c0;
     for (int w = lane; w < cw_max; w += 32) rows_s[r * cw_max + w] = w < cw ? rp[w] : 0u;
   }
   __syncthreads();
-  for (int j = 0; j < 4; ++j) {
+  for (int j = j_begin; j < j_end; ++j) {  // (a caller may take only some of the four groups of sample rows)
     const int x = (j == 0) ? warp : (j == 1) ? 63 - warp : (j == 2) ? 64 + warp : 127 - warp;
     if (x >= nsel) continue;
     uint32_t rx[6];
@@ -1041,17 +1041,41 @@ __device__ __forceinline__ uint32_t theta_pick(const unsigned short* ts, int nts
   const int t = threadIdx.x;
   uint32_t th = 0;
   if (nts >= Ke) {  // block-uniform
-    // which of the 256 steps selects the bucket: thread 0 walks the histogram from the top
+    // which of the 256 bins holds the need-th largest entry: the highest bin b with at least `need` entries in bins
+    // >= b (bin 0 if there is none).  One warp, lane l owns bins 8 l .. 8 l + 7, suffix sums from the top.
     auto pick_bucket = [&](int need) {
       __syncthreads();
-      if (t == 0) {
-        int cum = 0, b = 255;
-        for (; b > 0; --b) {
-          if (cum + s_h[b] >= need) break;
-          cum += s_h[b];
+      if (t < 32) {
+        int mine[8], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          mine[k] = s_h[8 * t + k];
+          tot += mine[k];
         }
-        s_hi = b;
-        s_need = need - cum;  // still needed inside bucket b
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_down_sync(0xffffffffu, tot, o);
+          if (t + o < 32) tot += u;
+        }
+        int above = tot;  // entries in higher lanes' bins
+#pragma unroll
+        for (int k = 0; k < 8; ++k) above -= mine[k];
+        const bool here = above < need && tot >= need;  // true in exactly one lane if the total reaches need
+        if (here) {
+          int cum = above;
+          for (int k = 7; k >= 0; --k) {
+            if (cum + mine[k] >= need) {
+              s_hi = 8 * t + k;
+              s_need = need - cum;  // still needed inside that bin
+              break;
+            }
+            cum += mine[k];
+          }
+        }
+        if (!__any_sync(0xffffffffu, here) && t == 0) {  // fewer than `need` entries in all: the walk used to end at bin 0
+          s_hi = 0;
+          s_need = need - (tot - mine[0]);
+        }
       }
       __syncthreads();
     };
@@ -1169,8 +1193,11 @@ __global__ void __launch_bounds__(1024) tri_theta_count_kernel(const PairDesc* _
   if (t < kThetaNodes) nodes[t] = sc->nodes[t];
   if (t < kThetaNodes * 4) emask[t] = sc->emask[t];
   __syncthreads();
+  // gridDim.z = 4 (calls with very few pairs): one group of sample rows per CTA, so that a single pair of N = 5000
+  // runs on 12 CTAs instead of 3
+  const int j0 = gridDim.z == 4 ? static_cast<int>(blockIdx.z) : 0, j1 = gridDim.z == 4 ? j0 + 1 : 4;
   theta_count_chunk(d, adj + d.adj_off, nodes, emask, rows_s, sc->nsel, c0, min(kThetaSplitW, d.stride - c0), kThetaSplitW,
-                    [&](int x, int y, int c) { if (c) atomicAdd(&sc->ts[x * kThetaNodes + y], static_cast<uint32_t>(c)); });
+                    [&](int x, int y, int c) { if (c) atomicAdd(&sc->ts[x * kThetaNodes + y], static_cast<uint32_t>(c)); }, j0, j1);
 }
 
 __global__ void __launch_bounds__(1024) tri_theta_pick_kernel(const ChunkDev* __restrict__ chunk,
@@ -1301,7 +1328,8 @@ int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -static_cast<int>(e);
     const int nchunks = (max_npad / 32 + kThetaSplitW - 1) / kThetaSplitW;
-    tri_theta_count_kernel<<<dim3(nchunks, pairs), 1024, 0, lc.stream>>>(d_desc, d_adj, d_chunk, sc, prune);
+    const int groups = nchunks * pairs * 4 <= 2 * lc.sm_count ? 4 : 1;
+    tri_theta_count_kernel<<<dim3(nchunks, pairs, groups), 1024, 0, lc.stream>>>(d_desc, d_adj, d_chunk, sc, prune);
     e = cudaGetLastError();
     if (e != cudaSuccess) return -static_cast<int>(e);
     tri_theta_pick_kernel<<<pairs, 1024, 0, lc.stream>>>(d_chunk, sc, d_theta, Ke, prune);

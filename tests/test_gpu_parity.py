@@ -1028,3 +1028,25 @@ def test_node_pruning_off_for_second_order_and_debug_dumps(gpu, oracle):
     out_g, out_o = gpu.register(p.src, p.dst), oracle.register(p.src, p.dst)
     assert gpu.get("pruned_pairs") == 0
     compare_pose(*out_g, *out_o)
+
+
+def test_node_pruning_stays_out_of_the_sharded_phases(gpu_lib, oracle):
+    """A pair that WOULD prune, through the in-library sharded entry point with a one-rank communicator and without
+    keep_debug: the sharded phases rank apexes from complete node sums, so the pruning must stay off there."""
+    p = synth.make_pair(6000, 0.03, 9470, **KITTI)
+    ident = (C.c_ubyte * _abi.COMM_ID_BYTES)()
+    assert gpu_lib.sac_cot_comm_unique_id(ident) == _abi.OK
+    set_params(oracle, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
+    Ro, to, io = oracle.register(p.src, p.dst)
+    with Registrar(lib=gpu_lib) as one, Registrar(lib=gpu_lib) as sh:
+        for r in (one, sh):
+            set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier)
+        R1, t1, i1 = one.register(p.src, p.dst)
+        assert one.get("pruned_pairs") == 1
+        sh.comm_init(rank=0, world=1, unique_id=bytes(ident))
+        R, t, inl = sh.register_sharded(p.src, p.dst)
+        assert sh.get("pruned_pairs") == 0
+        np.testing.assert_array_equal(R, R1)
+        np.testing.assert_array_equal(t, t1)
+        assert inl == i1
+        compare_pose(R, t, inl, Ro, to, io)
