@@ -365,9 +365,10 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
     reg.set("lanes", lanes_default)
     # exact node pruning of S2 (kernels_prune.cu) in the last chunk of the pass above
     node_prune = {"mode": reg.get("node_prune"), "pruned_pairs_last_chunk": reg.get("pruned_pairs"),
-                  "kept_nodes_last_chunk": reg.get("kept_nodes"),
+                  "kept_nodes_last_chunk": reg.get("kept_nodes"), "trying": reg.get("node_prune_trying"),
                   "what": "pairs whose selectable edges provably join few high-degree nodes count triangles for those "
-                          "nodes' rows only (exact; --node-prune 0 switches it off)"}
+                          "nodes' rows only (exact; --node-prune 0 switches it off).  trying = 0: the ctx saw two calls "
+                          "in a row prune nothing and skips the attempt for its next node_prune_probe (30) calls"}
 
     # ---- timed region 2: end to end through the host-buffer C-ABI call (e2e) ----
     step_host()  # warm the host path (arena regrows once: it now also holds the input copy)

@@ -124,7 +124,9 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *        counts triangles for those nodes' rows only; results are unchanged; off while "keep_debug" is set,
  *        because SAC_COT_DBG_T_NODE then covers the kept nodes only; 2 = on whenever the kept list fits, also
  *        with keep_debug (tests); 0 = off; GPU only), "node_prune_cost" (default 200: a pair is pruned if
- *        (sum of the kept nodes' degrees) x cost <= Npad^2; GPU only),
+ *        (sum of the kept nodes' degrees) x cost <= Npad^2; GPU only), "node_prune_probe" (default 30: a ctx
+ *        whose last two calls tried and pruned nothing skips the attempt — five near-empty launches per chunk —
+ *        for this many calls, then tries again; results never depend on it; GPU only),
  *        "stage_timing" (0/1: bracket every pipeline stage with CUDA events on the ctx
  *        stream; setting it also clears the accumulated times; GPU only),
  *        test switches that never change a result (GPU only): "tile_runs" (tensor-core path, default 1:
@@ -133,7 +135,8 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *        2 = the global-lookup kernel that N > 51200 falls back to), "triangle_dbg" (experiments)
  *   get: "triangle_path_used" (0/1: which S2 kernels the latest chunk ran; synchronises; GPU only),
  *        "pruned_pairs" / "kept_nodes" (node pruning in the latest chunk: pairs that took the kept-row kernel and
- *        the nodes they kept in total; synchronises; GPU only),
+ *        the nodes they kept in total; synchronises; GPU only), "node_prune_trying" (1: the next call attempts the
+ *        node pruning, 0: the ctx is inside a back-off; GPU only),
  *        "launches" (kernels launched since ctx creation), "workspace_bytes",
  *        "device", "sm_count", "retries" (workspace-growth re-runs),
  *        "last_status" (deferred status of the SAC_COT_LOC_DEVICE calls since the previous query: SAC_COT_E_NOMEM

@@ -250,6 +250,15 @@ struct sac_cot_ctx {
   // the kept nodes only), 2 on whenever the kept list fits (tests)
   int node_prune = 1;
   int node_prune_cost = 200;  // a pair is pruned if (sum of kept degrees) x cost <= Npad^2
+  // Trying costs five near-empty launches per chunk when nothing can be pruned (indoor-scale graphs).  The ctx
+  // therefore watches the device-side count of pruned pairs: after two calls in a row that tried and pruned nothing
+  // it stops trying for node_prune_probe calls, then tries again.  Results never depend on it.
+  int node_prune_probe = 30;
+  int np_idle = 0;        // calls in a row that tried and pruned nothing
+  int np_skip_left = 0;   // calls that will not try
+  bool np_try = true;     // the current call tries
+  bool np_tried = false;  // some call since the last verdict enqueued the pruning kernels
+  uint32_t np_seen = 0;   // device counter at the last verdict
   int64_t launches = 0;
   int64_t retries = 0;
   int deferred_status = 0;  // device-location calls: status discovered after the fact
@@ -258,7 +267,7 @@ struct sac_cot_ctx {
   cudaEvent_t fork_event = nullptr;
   std::vector<ChunkDev*> h_chunks;  // pinned read-backs of the chunk headers (host-location calls)
   StickyDev* d_sticky = nullptr;    // device: overflow record that survives across calls
-  StickyDev* h_sticky = nullptr;    // pinned [2]: the record before / after the device-location calls whose verdict is open
+  StickyDev* h_sticky = nullptr;    // pinned [3]: the record before / after the device-location calls whose verdict is open; [2]: after a host-location call
   cudaEvent_t sticky_event = nullptr;
   bool sticky_pending = false;
 
@@ -561,6 +570,22 @@ int ensure_keys(sac_cot_ctx* ctx, Lane& ln, unsigned long long cap) {
 // completed; a changed overflow count means some chunk of those calls ran out of key-pool space: their outputs are
 // void, "last_status" reports SAC_COT_E_NOMEM once, and every lane's pool is grown to the recorded demand so the
 // caller's next call succeeds.  block = false never waits (a verdict that is not in yet is merely late).
+// node pruning: what the calls since the last verdict achieved (counter = pairs pruned so far on this ctx)
+void node_prune_verdict(sac_cot_ctx* ctx, uint32_t counter) {
+  if (ctx->np_tried) {
+    if (counter == ctx->np_seen) {
+      if (++ctx->np_idle >= 2) {
+        ctx->np_skip_left = ctx->node_prune_probe;
+        ctx->np_idle = 0;
+      }
+    } else {
+      ctx->np_idle = 0;
+    }
+    ctx->np_tried = false;
+  }
+  ctx->np_seen = counter;
+}
+
 int sticky_before(sac_cot_ctx* ctx) {
   if (ctx->sticky_pending) return 0;  // an open verdict keeps its "before" snapshot and will cover this call too
   CU_TRY(cudaMemcpyAsync(&ctx->h_sticky[0], ctx->d_sticky, sizeof(StickyDev), cudaMemcpyDeviceToHost, ctx->stream));
@@ -582,6 +607,7 @@ int resolve_pending(sac_cot_ctx* ctx, bool block) {
     if (q != cudaSuccess) return static_cast<int>(q);
   }
   ctx->sticky_pending = false;
+  node_prune_verdict(ctx, ctx->h_sticky[1].pruned_total);
   if (ctx->h_sticky[1].overflow_count != ctx->h_sticky[0].overflow_count) {
     ctx->deferred_status = SAC_COT_E_NOMEM;
     const unsigned long long demand = ctx->h_sticky[1].max_total_edges;
@@ -654,13 +680,14 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   // exact node pruning: first-order graph, rows short enough for the kept-row kernel; not for the sharded phases
   // (stop_after_edges: their later parts rank apexes from complete node sums, also with world = 1)
   const bool node_prune = tri_mode != 0 && ctx->tri_prune && ctx->node_prune != 0 && L.adj2 == nullptr && world <= 1 &&
-                          !stop_after_edges &&
+                          !stop_after_edges && ctx->np_try &&
                           L.max_npad <= kNodePruneMaxNpad && L.total_tiles > 0 && ctx->apex_path != 2 &&
                           (ctx->node_prune >= 2 || !ctx->keep_debug);
   if (tri_mode != 0) {
     KL_TRY(launch_tri_theta(lc, L.desc, L.pairs, L.max_npad, adj_use, L.chunk, L.theta, L.theta_ws, L.Ke, ctx->tri_prune));
+    if (node_prune) ctx->np_tried = true;
     if (node_prune)
-      KL_TRY(launch_node_plan(lc, L.desc, L.pairs, L.max_npad, adj_use, L.chunk, L.state, L.theta, L.deg, L.nplan, L.kept, L.keptbits, L.tile_tab,
+      KL_TRY(launch_node_plan(lc, L.desc, L.pairs, L.max_npad, adj_use, L.chunk, ctx->d_sticky, L.state, L.theta, L.deg, L.nplan, L.kept, L.keptbits, L.tile_tab,
                               L.total_tiles, L.tile_tab2, L.tile_total, ctx->node_prune_cost, ctx->node_prune));
     mark(ST_THETA);
     KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, node_prune ? L.tile_total : nullptr, L.tile_tab2,
@@ -885,6 +912,8 @@ int run_selected(sac_cot_ctx* ctx, const float* src, const float* dst, const int
   CU_TRY(cudaSetDevice(ctx->device));
   if (int rc = resolve_pending(ctx, false)) return rc;
   const bool host = location == SAC_COT_LOC_HOST;
+  ctx->np_try = ctx->node_prune >= 2 || ctx->np_skip_left == 0;
+  if (!ctx->np_try) --ctx->np_skip_left;
   // chunking: bounded workspace per wave of kernels (keep_debug keeps the whole batch resident on
   // lane 0); chunks are dealt round-robin to the lanes
   const int K = params->num_edges * params->apex_per_edge;
@@ -937,7 +966,11 @@ int run_selected(sac_cot_ctx* ctx, const float* src, const float* dst, const int
       ctx->ws_valid = nchunks == 1;
       return SAC_COT_OK;
     }
+    if (ctx->np_tried && !ctx->sticky_pending)
+      CU_TRY(cudaMemcpyAsync(&ctx->h_sticky[2], ctx->d_sticky, sizeof(StickyDev), cudaMemcpyDeviceToHost, ctx->stream));
+    const bool np_read = ctx->np_tried && !ctx->sticky_pending;
     CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (np_read) node_prune_verdict(ctx, ctx->h_sticky[2].pruned_total);
     // chunks whose edge count exceeded the lane's key pool: grow every lane to the measured demand
     // and re-run just those chunks
     std::vector<int> again;
@@ -1029,7 +1062,7 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
     if (e != cudaSuccess) { delete ctx; return static_cast<int>(e); }
     ctx->own_stream = true;
   }
-  cudaError_t e = cudaMallocHost(&ctx->h_sticky, 2 * sizeof(StickyDev));
+  cudaError_t e = cudaMallocHost(&ctx->h_sticky, 3 * sizeof(StickyDev));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->sticky_event, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_sticky, sizeof(StickyDev));
   if (e == cudaSuccess) e = cudaMemset(ctx->d_sticky, 0, sizeof(StickyDev));
@@ -1042,7 +1075,7 @@ int sac_cot_ctx_create(sac_cot_ctx** out, int32_t device, void* stream) {
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_xsum, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->match_uploaded, cudaEventDisableTiming);
   if (e != cudaSuccess) { sac_cot_ctx_destroy(ctx); return static_cast<int>(e); }
-  std::memset(ctx->h_sticky, 0, 2 * sizeof(StickyDev));
+  std::memset(ctx->h_sticky, 0, 3 * sizeof(StickyDev));
   int rc = triangles_configure();
   if (rc >= 0) rc = triangles_mma_configure();
   if (rc >= 0) rc = select_configure();
@@ -1120,6 +1153,13 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     ctx->node_prune_cost = static_cast<int>(value);
     return SAC_COT_OK;
   }
+  if (!std::strcmp(name, "node_prune_probe")) {
+    if (value < 0 || value > 1000000) return SAC_COT_E_SIZE;
+    ctx->node_prune_probe = static_cast<int>(value);
+    ctx->np_skip_left = 0;
+    ctx->np_idle = 0;
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "tile_runs")) {
     ctx->tile_runs = value != 0;
     return SAC_COT_OK;
@@ -1173,6 +1213,8 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
   }
   if (!std::strcmp(name, "node_prune")) { *value = ctx->node_prune; return SAC_COT_OK; }
   if (!std::strcmp(name, "node_prune_cost")) { *value = ctx->node_prune_cost; return SAC_COT_OK; }
+  if (!std::strcmp(name, "node_prune_probe")) { *value = ctx->node_prune_probe; return SAC_COT_OK; }
+  if (!std::strcmp(name, "node_prune_trying")) { *value = ctx->np_skip_left == 0 ? 1 : 0; return SAC_COT_OK; }
   if (!std::strcmp(name, "pruned_pairs") || !std::strcmp(name, "kept_nodes")) {
     // exact node pruning in the most recent chunk on lane 0: pairs that took the kept-row kernel / the nodes they
     // kept in total; synchronises

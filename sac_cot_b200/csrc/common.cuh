@@ -55,7 +55,7 @@ struct ChunkDev {
 struct StickyDev {
   unsigned long long max_total_edges;  // largest chunk demand seen in an overflowing chunk
   uint32_t overflow_count;             // number of chunks that overflowed so far
-  uint32_t pad_;
+  uint32_t pruned_total;               // pairs that took the kept-row kernel so far (kernels_prune.cu)
 };
 
 constexpr int kMaxEdges = 4096;     // == SAC_COT_MAX_EDGES
@@ -232,7 +232,7 @@ int node_prune_configure();
 // cost: a pair is pruned if (sum of kept degrees) x cost <= Npad^2; force >= 2: whenever the kept list fits (tests)
 // d_total: int[2] in the chunk's zero region: [0] tiles left (-1: nothing pruned, use the original list), [1] pruned pairs
 int launch_node_plan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
-                     const ChunkDev* d_chunk, const PairDev* d_state, const uint32_t* d_theta, unsigned short* d_deg, NodePlan* d_plan,
+                     const ChunkDev* d_chunk, StickyDev* d_sticky, const PairDev* d_state, const uint32_t* d_theta, unsigned short* d_deg, NodePlan* d_plan,
                      unsigned short* d_kept, uint32_t* d_keptbits, const uint2* d_tiles, int total_tiles, uint2* d_tiles_out,
                      int* d_total, int cost, int force);
 int launch_triangles_kept(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_n, int max_stride,

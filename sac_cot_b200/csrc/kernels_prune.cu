@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) node_degree_kernel(const PairDesc* __rest
 // kernel ~ Npad^3, so the pair is pruned if (sum of kept degrees) x cost <= Npad^2 (cost: api.cu).
 __global__ void __launch_bounds__(1024) node_plan_kernel(const PairDesc* __restrict__ descs,
                                                          const ChunkDev* __restrict__ chunk,
+                                                         StickyDev* __restrict__ sticky,
                                                          const PairDev* __restrict__ state,
                                                          const uint32_t* __restrict__ theta,
                                                          const unsigned short* __restrict__ deg,
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(1024) node_plan_kernel(const PairDesc* __restr
     pl->min_deg = min_deg;
     pl->pruned = 1u;
     atomicAdd(n_pruned, 1);
+    atomicAdd(&sticky->pruned_total, 1u);  // the host learns from it whether trying pays on this ctx's workload
   }
 }
 
@@ -439,7 +441,7 @@ int node_prune_configure() {
 }
 
 int launch_node_plan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
-                     const ChunkDev* d_chunk, const PairDev* d_state, const uint32_t* d_theta, unsigned short* d_deg, NodePlan* d_plan,
+                     const ChunkDev* d_chunk, StickyDev* d_sticky, const PairDev* d_state, const uint32_t* d_theta, unsigned short* d_deg, NodePlan* d_plan,
                      unsigned short* d_kept, uint32_t* d_keptbits, const uint2* d_tiles, int total_tiles, uint2* d_tiles_out,
                      int* d_total, int cost, int force) {
   int gx = (8 * lc.sm_count + pairs - 1) / pairs;
@@ -447,7 +449,7 @@ int launch_node_plan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
   node_degree_kernel<<<dim3(gx, pairs), 256, 0, lc.stream>>>(d_desc, d_adj, d_chunk, d_state, d_theta, d_deg, force);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -static_cast<int>(e);
-  node_plan_kernel<<<pairs, 1024, 0, lc.stream>>>(d_desc, d_chunk, d_state, d_theta, d_deg, d_plan, d_kept, d_keptbits, d_total + 1, cost, force);
+  node_plan_kernel<<<pairs, 1024, 0, lc.stream>>>(d_desc, d_chunk, d_sticky, d_state, d_theta, d_deg, d_plan, d_kept, d_keptbits, d_total + 1, cost, force);
   e = cudaGetLastError();
   if (e != cudaSuccess) return -static_cast<int>(e);
   tile_compact_kernel<<<1, 1024, 0, lc.stream>>>(d_tiles, total_tiles, d_plan, d_tiles_out, d_total);

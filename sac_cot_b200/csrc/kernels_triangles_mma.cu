@@ -1328,7 +1328,7 @@ int launch_tri_theta(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -static_cast<int>(e);
     const int nchunks = (max_npad / 32 + kThetaSplitW - 1) / kThetaSplitW;
-    const int groups = nchunks * pairs * 4 <= 2 * lc.sm_count ? 4 : 1;
+    const int groups = nchunks * pairs <= lc.sm_count ? 4 : 1;  // few CTAs: one group of sample rows each
     tri_theta_count_kernel<<<dim3(nchunks, pairs, groups), 1024, 0, lc.stream>>>(d_desc, d_adj, d_chunk, sc, prune);
     e = cudaGetLastError();
     if (e != cudaSuccess) return -static_cast<int>(e);

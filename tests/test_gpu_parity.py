@@ -1050,3 +1050,33 @@ def test_node_pruning_stays_out_of_the_sharded_phases(gpu_lib, oracle):
         np.testing.assert_array_equal(t, t1)
         assert inl == i1
         compare_pose(R, t, inl, Ro, to, io)
+
+
+def test_node_prune_probe_backs_off_and_comes_back(gpu_lib, oracle):
+    """A ctx whose calls prune nothing stops trying for node_prune_probe calls (five near-empty launches per chunk
+    saved), then tries again; the results never depend on it."""
+    dense = synth.make_config_pair("cfg2_3dmatch_256x5000", 12)     # indoor scale: nothing to prune
+    sparse = synth.make_pair(6000, 0.03, 9480, **KITTI)              # outdoor scale: prunes to the inlier clique
+    set_params(oracle, tau_compat=sparse.tau_compat, tau_inlier=sparse.tau_inlier)
+    Ro, to, io = oracle.register(sparse.src, sparse.dst)
+    with Registrar(lib=gpu_lib, device=0) as reg:
+        reg.set("node_prune_probe", 3)
+        assert reg.get("node_prune_probe") == 3 and reg.get("node_prune_trying") == 1
+        set_params(reg, tau_compat=dense.tau_compat, tau_inlier=dense.tau_inlier)
+        for _ in range(2):
+            reg.register(dense.src, dense.dst)
+            assert reg.get("pruned_pairs") == 0
+        assert reg.get("node_prune_trying") == 0
+        set_params(reg, tau_compat=sparse.tau_compat, tau_inlier=sparse.tau_inlier)
+        outs = []
+        for _ in range(3):   # inside the back-off: the dense kernel counts every triangle of the pair
+            outs.append(reg.register(sparse.src, sparse.dst))
+            assert reg.get("pruned_pairs") == 0
+        assert reg.get("node_prune_trying") == 1
+        outs.append(reg.register(sparse.src, sparse.dst))
+        assert reg.get("pruned_pairs") == 1
+        for R, t, inl in outs:
+            np.testing.assert_array_equal(R, outs[0][0])
+            np.testing.assert_array_equal(t, outs[0][1])
+            assert inl == outs[0][2]
+        compare_pose(*outs[-1], Ro, to, io)
