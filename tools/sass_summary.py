@@ -39,7 +39,7 @@ def main():
     names = list(kernels)
     dem = subprocess.run(["c++filt"] + names, capture_output=True, text=True).stdout.splitlines()
     for n, d in zip(names, dem):
-        demangle[n] = re.sub(r"\(.*", "", d).replace("saccot::", "")
+        demangle[n] = re.sub(r"\(.*", "", d.replace("(anonymous namespace)::", "")).replace("saccot::", "")
     print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)} — {len(kernels)} kernels, sm_100a")
     print(f"# {'kernel':58s} {'instr':>7s}  watched opcodes (count)")
     for n, c in kernels.items():
