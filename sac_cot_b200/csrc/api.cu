@@ -929,7 +929,11 @@ int run_selected(sac_cot_ctx* ctx, const float* src, const float* dst, const int
                                      params->compat_mode == SAC_COT_COMPAT_SECOND_ORDER);
       const size_t budget = static_cast<size_t>(3) << 30;  // ~3 GB of workspace per chunk (larger chunks measured faster)
       int nchunks = static_cast<int>((total + budget - 1) / budget);
-      if (nchunks < lanes && B >= 2 * lanes) nchunks = lanes;  // give every lane something to overlap
+      // give every lane something to overlap — but not chunks so small that their kernels under-fill the device:
+      // measured at N = 5000, 32 pairs run 11 % faster as one chunk (1.77 ms) than as three of 11 (1.98 ms), 64 pairs
+      // 1.5 % faster as two or three; a chunk of 32 such pairs is ~350 MB of workspace
+      const int worth = static_cast<int>(std::min<size_t>(static_cast<size_t>(lanes), std::max<size_t>(1, total / (static_cast<size_t>(350) << 20))));
+      if (nchunks < worth && B >= 2 * worth) nchunks = worth;
       chunk = (B + nchunks - 1) / std::max(1, nchunks);
     }
   }

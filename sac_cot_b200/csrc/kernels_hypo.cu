@@ -461,17 +461,21 @@ int launch_score(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max
   const int span = h_end - h_begin;
   if (span <= 0) return 0;
   const int hblocks = (span + kScoreThreads * kScoreHyp - 1) / (kScoreThreads * kScoreHyp);
-  // fewer CTAs than SMs (the single-pair calls): split the correspondences as well, at least 2 slabs per range.
-  // (Splitting merely to even out 3-4 CTAs per SM was measured slower: 334 -> 356 us for 32 pairs.)
+  // fewer than two CTAs per SM (single pairs, chunks of a dozen pairs): split the correspondences as well, into
+  // ranges of at least 2 slabs, aiming at four CTAs per SM.  Measured (score us per chunk, N = 5000): 8 pairs
+  // 125 -> 109, 11 pairs 232 -> 138, 16 pairs 233 -> 210; from 24 pairs (384 CTAs) on splitting is slower
+  // (280 -> 298; 32 pairs 334 -> 356).
   int nsplit = 1;
   const int slabs = (max_n + kScoreSlab - 1) / kScoreSlab;
-  if (hblocks * pairs < lc.sm_count && slabs >= 8) {
-    nsplit = std::min((2 * lc.sm_count + hblocks * pairs - 1) / (hblocks * pairs), slabs / 2);
+  if (hblocks * pairs < 2 * lc.sm_count && slabs >= 8) {
+    nsplit = std::min((4 * lc.sm_count + hblocks * pairs - 1) / (hblocks * pairs), slabs / 2);
     if (nsplit < 2) nsplit = 1;
   }
-  if (nsplit > 1) {
-    for (int b = 0; b < pairs; ++b) {
-      const cudaError_t me = cudaMemsetAsync(d_hyp_key + static_cast<size_t>(b) * K + h_begin, 0, sizeof(unsigned long long) * span, lc.stream);
+  if (nsplit > 1) {  // partial scores add up in hyp_key: start from zero (one memset when the range is all of K)
+    const int nset = span == K ? 1 : pairs;
+    const size_t bytes = sizeof(unsigned long long) * (span == K ? static_cast<size_t>(pairs) * K : static_cast<size_t>(span));
+    for (int b = 0; b < nset; ++b) {
+      const cudaError_t me = cudaMemsetAsync(d_hyp_key + static_cast<size_t>(b) * K + h_begin, 0, bytes, lc.stream);
       if (me != cudaSuccess) return -static_cast<int>(me);
     }
   }
