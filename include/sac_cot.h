@@ -124,7 +124,10 @@ SAC_COT_API int sac_cot_ctx_destroy(sac_cot_ctx* ctx);
  *        counts triangles for those nodes' rows only; results are unchanged; off while "keep_debug" is set,
  *        because SAC_COT_DBG_T_NODE then covers the kept nodes only; 2 = on whenever the kept list fits, also
  *        with keep_debug (tests); 0 = off; GPU only), "node_prune_cost" (default 200: a pair is pruned if
- *        (sum of the kept nodes' degrees) x cost <= Npad^2; GPU only), "node_prune_probe" (default 30: a ctx
+ *        (sum of the kept nodes' degrees) x cost <= Npad^2; GPU only), "node_prune_rect" (default 1: the kept rows of
+ *        pairs with N >= 1921 and at most 1024 kept nodes run on the tensor cores when the chunk holds >= 4 pairs,
+ *        2 = whatever the chunk size, 0 = always the POPC kept-row kernel; "rect_pairs" tells how many pairs of the
+ *        latest chunk did; GPU only), "node_prune_probe" (default 30: a ctx
  *        whose last two calls tried and pruned nothing skips the attempt — five near-empty launches per chunk —
  *        for this many calls, then tries again; results never depend on it; GPU only),
  *        "stage_timing" (0/1: bracket every pipeline stage with CUDA events on the ctx

@@ -94,7 +94,13 @@ struct Layout {
   unsigned short* kept = nullptr;
   uint32_t* keptbits = nullptr;  // [sum of Npad / 32], indexed like the inlier masks (PairDesc::mask_off)
   uint2* tile_tab2 = nullptr;
-  int* tile_total = nullptr;
+  int* tile_total = nullptr;     // int[4]: see launch_node_plan
+  // RECT instance of the tensor-core kernel (node-pruned pairs): its tile list and the compact panel copies
+  uint2* rect_tiles = nullptr;
+  int rect_max_tiles = 0;
+  uint32_t* kpanel = nullptr;
+  long long kpanel_pair_words = 0;
+  int max_npanel = 0;
   unsigned long long* sel = nullptr;
   unsigned long long* tie = nullptr;
   unsigned long long* top = nullptr;
@@ -250,6 +256,7 @@ struct sac_cot_ctx {
   // the kept nodes only), 2 on whenever the kept list fits (tests)
   int node_prune = 1;
   int node_prune_cost = 200;  // a pair is pruned if (sum of kept degrees) x cost <= Npad^2
+  int node_prune_rect = 1;    // kept rows of long pairs: 1 = the tensor-core kernel's RECT instance for chunks of >= 4 pairs, 2 = always, 0 = POPC kept-row kernel
   // Trying costs five near-empty launches per chunk when nothing can be pruned (indoor-scale graphs).  The ctx
   // therefore watches the device-side count of pruned pairs: after two calls in a row that tried and pruned nothing
   // it stops trying for node_prune_probe calls, then tries again.  Results never depend on it.
@@ -387,7 +394,7 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.unit_pitch = static_cast<int>(unit_count(static_cast<unsigned int>(L.max_nblk)));
   const size_t o_ucount = take(sizeof(uint32_t) * L.unit_pitch * pairs);
   const size_t o_nplan = take(sizeof(NodePlan) * pairs);
-  const size_t o_ttotal = take(2 * sizeof(int));
+  const size_t o_ttotal = take(4 * sizeof(int));
   L.zero_bytes = off;
   const size_t o_ubase = take(sizeof(uint32_t) * L.unit_pitch * pairs);
   const size_t o_desc = take(sizeof(PairDesc) * pairs);
@@ -410,6 +417,13 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   const size_t o_deg = tensor_path ? take(sizeof(unsigned short) * node) : 0;
   const size_t o_kept = tensor_path ? take(sizeof(unsigned short) * kNodeKeepMax * pairs) : 0;
   const size_t o_keptbits = tensor_path ? take(sizeof(uint32_t) * mask) : 0;
+  // RECT path: only for chunks whose rows are long enough and short enough for the node pruning at all
+  const bool rect = tensor_path && L.max_npad >= kRectMinNpad && L.max_npad <= kNodePruneMaxNpad;
+  L.max_npanel = (L.max_npad + 255) / 256;
+  L.rect_max_tiles = rect ? pairs * (kRectRows / kMmaTileM) * ((L.max_n + kMmaTileN - 1) / kMmaTileN) : 0;
+  L.kpanel_pair_words = rect ? static_cast<long long>((L.max_npanel + 1) & ~1) * kRectRows * 8 : 0;
+  const size_t o_rect = rect ? take(sizeof(uint2) * static_cast<size_t>(L.rect_max_tiles)) : 0;
+  const size_t o_kpanel = rect ? take(sizeof(uint32_t) * static_cast<size_t>(L.kpanel_pair_words) * pairs) : 0;
   const size_t o_sel = take(sizeof(unsigned long long) * L.Ke * pairs);
   const size_t o_tie = take(sizeof(unsigned long long) * kTieCap * pairs);
   const size_t o_top = take(sizeof(unsigned long long) * L.Ke * pairs);
@@ -451,6 +465,8 @@ void plan(const int32_t* Ns, int pairs, const sac_cot_params& prm, bool need_inp
   L.deg = tensor_path ? reinterpret_cast<unsigned short*>(o_deg) : nullptr;
   L.kept = tensor_path ? reinterpret_cast<unsigned short*>(o_kept) : nullptr;
   L.keptbits = tensor_path ? reinterpret_cast<uint32_t*>(o_keptbits) : nullptr;
+  L.rect_tiles = rect ? reinterpret_cast<uint2*>(o_rect + 1) : nullptr;      // +1: offset 0 must not read as "absent"
+  L.kpanel = rect ? reinterpret_cast<uint32_t*>(o_kpanel + 1) : nullptr;
   L.sel = reinterpret_cast<unsigned long long*>(o_sel);
   L.tie = reinterpret_cast<unsigned long long*>(o_tie);
   L.top = reinterpret_cast<unsigned long long*>(o_top);
@@ -499,6 +515,8 @@ void bind(Layout& L, unsigned char* base, bool has_input, bool tensor_path) {
   L.deg = rebase(L.deg, base, tensor_path);
   L.kept = rebase(L.kept, base, tensor_path);
   L.keptbits = rebase(L.keptbits, base, tensor_path);
+  L.rect_tiles = L.rect_tiles ? reinterpret_cast<uint2*>(base + (reinterpret_cast<size_t>(L.rect_tiles) - 1)) : nullptr;
+  L.kpanel = L.kpanel ? reinterpret_cast<uint32_t*>(base + (reinterpret_cast<size_t>(L.kpanel) - 1)) : nullptr;
   L.sel = rebase(L.sel, base);
   L.tie = rebase(L.tie, base);
   L.top = rebase(L.top, base);
@@ -686,13 +704,21 @@ int enqueue_pipeline(sac_cot_ctx* ctx, Lane& ln, const float* d_src, const float
   if (tri_mode != 0) {
     KL_TRY(launch_tri_theta(lc, L.desc, L.pairs, L.max_npad, adj_use, L.chunk, L.theta, L.theta_ws, L.Ke, ctx->tri_prune));
     if (node_prune) ctx->np_tried = true;
+    // RECT instance for the kept rows of long pairs — from four pairs per chunk on (a single pair's 40-80 tiles do not
+    // fill the 74 CTA pairs: 66 us against 56 us for the kept-row POPC kernel at N = 10 000); node_prune_rect = 2 forces it
+    const bool use_rect = node_prune && L.kpanel != nullptr && (ctx->node_prune_rect == 2 || (ctx->node_prune_rect == 1 && L.pairs >= 4));
     if (node_prune)
       KL_TRY(launch_node_plan(lc, L.desc, L.pairs, L.max_npad, adj_use, L.chunk, ctx->d_sticky, L.state, L.theta, L.deg, L.nplan, L.kept, L.keptbits, L.tile_tab,
-                              L.total_tiles, L.tile_tab2, L.tile_total, ctx->node_prune_cost, ctx->node_prune));
+                              L.total_tiles, L.tile_tab2, L.tile_total, ctx->node_prune_cost, ctx->node_prune, L.rect_tiles, panel_use,
+                              use_rect ? L.kpanel : nullptr, L.kpanel_pair_words, L.max_npanel));
     mark(ST_THETA);
     KL_TRY(launch_triangles_mma(lc, L.desc, L.tile_tab, L.total_tiles, node_prune ? L.tile_total : nullptr, L.tile_tab2,
                                 adj_use, panel_use, L.state, L.chunk, ln.keys, L.theta, L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg));
     if (node_prune) mark(ST_TRIANGLES);
+    if (use_rect)
+      KL_TRY(launch_triangles_mma_rect(lc, L.desc, L.rect_tiles, L.rect_max_tiles, L.tile_total + 2, adj_use, panel_use, L.state,
+                                       L.chunk, ln.keys, L.theta, L.hist, L.t2, L.Ke, ctx->tri_prune, ctx->tri_dbg, L.nplan, L.kept,
+                                       L.kpanel, L.kpanel_pair_words));
     if (node_prune)
       KL_TRY(launch_triangles_kept(lc, L.desc, L.pairs, L.max_n, L.max_stride, adj_use, L.nplan, L.kept, L.keptbits, L.chunk, L.state, ln.keys,
                                    L.hist, L.t2));
@@ -1157,6 +1183,11 @@ int sac_cot_ctx_set(sac_cot_ctx* ctx, const char* name, int64_t value) {
     ctx->node_prune_cost = static_cast<int>(value);
     return SAC_COT_OK;
   }
+  if (!std::strcmp(name, "node_prune_rect")) {
+    if (value < 0 || value > 2) return SAC_COT_E_UNSUPPORTED;
+    ctx->node_prune_rect = static_cast<int>(value);
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "node_prune_probe")) {
     if (value < 0 || value > 1000000) return SAC_COT_E_SIZE;
     ctx->node_prune_probe = static_cast<int>(value);
@@ -1218,6 +1249,20 @@ int sac_cot_ctx_get(sac_cot_ctx* ctx, const char* name, int64_t* value) {
   if (!std::strcmp(name, "node_prune")) { *value = ctx->node_prune; return SAC_COT_OK; }
   if (!std::strcmp(name, "node_prune_cost")) { *value = ctx->node_prune_cost; return SAC_COT_OK; }
   if (!std::strcmp(name, "node_prune_probe")) { *value = ctx->node_prune_probe; return SAC_COT_OK; }
+  if (!std::strcmp(name, "node_prune_rect")) { *value = ctx->node_prune_rect; return SAC_COT_OK; }
+  if (!std::strcmp(name, "rect_pairs")) {
+    // pairs of the most recent chunk on lane 0 whose kept rows went through the RECT instance; synchronises
+    Lane& ln = ctx->lanes[0];
+    if (!ln.arena || !ln.lay.nplan || ln.lay.pairs == 0) return SAC_COT_E_WHICH;
+    cudaSetDevice(ctx->device);
+    if (int rc = sync_all(ctx)) return rc;
+    std::vector<NodePlan> pl(ln.lay.pairs);
+    CU_TRY(cudaMemcpy(pl.data(), ln.lay.nplan, sizeof(NodePlan) * pl.size(), cudaMemcpyDeviceToHost));
+    int64_t n = 0;
+    for (const NodePlan& q : pl) n += q.pruned == 2u ? 1 : 0;
+    *value = n;
+    return SAC_COT_OK;
+  }
   if (!std::strcmp(name, "node_prune_trying")) { *value = ctx->np_skip_left == 0 ? 1 : 0; return SAC_COT_OK; }
   if (!std::strcmp(name, "pruned_pairs") || !std::strcmp(name, "kept_nodes")) {
     // exact node pruning in the most recent chunk on lane 0: pairs that took the kept-row kernel / the nodes they

@@ -183,6 +183,7 @@ int launch_triangles(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int
                      int world);
 int triangles_configure();  // opt-in dynamic shared memory; call once per device
 
+struct NodePlan;
 // kernels_triangles_mma.cu — S2 triangle counts on the tensor cores (tcgen05 kind::mxf4, TMEM)
 constexpr int kMmaTileM = 256;      // rows of i per tile: a CTA pair (cta_group::2), 128 rows = TMEM lanes per CTA
 constexpr int kMmaTileN = 240;      // columns of j per tile (UMMA N = 240; two accumulators = 480 TMEM columns)
@@ -212,6 +213,14 @@ int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint
                          const int* d_total, const uint2* d_tiles2, const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state,
                          const ChunkDev* d_chunk, unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist,
                          unsigned long long* d_t2, int Ke, int raise, int dbg);
+// the RECT instance: tiles of node-pruned pairs (256 kept nodes x 240 columns; list and length on the device)
+constexpr int kRectRows = 1024;     // kept nodes a pair may have to take this path (4 row blocks); rows of its compact panel copy
+constexpr int kRectMinNpad = 2048;  // shorter rows stay with the kept-row POPC kernel
+int launch_triangles_mma_rect(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_rect_tiles, int max_tiles,
+                              const int* d_rect_total, const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state,
+                              const ChunkDev* d_chunk, unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist,
+                              unsigned long long* d_t2, int Ke, int raise, int dbg, const struct NodePlan* d_plan,
+                              const unsigned short* d_kept, const uint32_t* d_kpanel, long long kpanel_pair_words);
 int triangles_mma_configure();
 // tensor-pipe peak probe (the triangle kernel's MMA shape, issued back to back): bench.py's roofline denominator
 int launch_mma_peak_probe(const LaunchCtx& lc, int clusters, int stage_pairs);
@@ -220,7 +229,7 @@ double mma_peak_probe_flops(int clusters, int stage_pairs);
 // kernels_prune.cu — exact node pruning of S2 on the tensor-core path: pairs whose selectable edges join few
 // high-degree nodes count triangles for those nodes' rows only
 struct NodePlan {
-  uint32_t pruned;   // 1: the pair takes the kept-row kernel, the tensor-core kernel skips its tiles
+  uint32_t pruned;   // the dense kernel skips the pair's tiles; its kept rows take 1: the POPC kept-row kernel, 2: the RECT instance
   uint32_t n_keep;   // nodes of degree >= min_deg, listed ascending in the pair's slice of the kept list
   uint32_t ub_rest;  // D (D - 1) / 2 >= t_k of every node outside the kept set, D = their largest degree (diagnostic)
   uint32_t min_deg;  // theta0 + 1
@@ -230,11 +239,13 @@ constexpr int kNodePruneMaxNpad = 10240;   // longest row the kept-row kernel ho
 int node_prune_configure();
 // exact degrees -> per-pair plan + kept list -> tile list without the pruned pairs' tiles (three launches).
 // cost: a pair is pruned if (sum of kept degrees) x cost <= Npad^2; force >= 2: whenever the kept list fits (tests)
-// d_total: int[2] in the chunk's zero region: [0] tiles left (-1: nothing pruned, use the original list), [1] pruned pairs
+// d_total: int[4] in the chunk's zero region: [0] tiles left (-1: nothing pruned, use the original list), [1] pruned
+// pairs, [2] tiles of the RECT list d_rect_tiles (pairs with plan.pruned == 2; d_kpanel = null: none gets that mode)
 int launch_node_plan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                      const ChunkDev* d_chunk, StickyDev* d_sticky, const PairDev* d_state, const uint32_t* d_theta, unsigned short* d_deg, NodePlan* d_plan,
                      unsigned short* d_kept, uint32_t* d_keptbits, const uint2* d_tiles, int total_tiles, uint2* d_tiles_out,
-                     int* d_total, int cost, int force);
+                     int* d_total, int cost, int force, uint2* d_rect_tiles, const uint32_t* d_panel, uint32_t* d_kpanel,
+                     long long kpanel_pair_words, int max_npanel);
 int launch_triangles_kept(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_n, int max_stride,
                           const uint32_t* d_adj, const NodePlan* d_plan, const unsigned short* d_kept,
                           const uint32_t* d_keptbits, const ChunkDev* d_chunk, PairDev* d_state, unsigned long long* d_keys, uint32_t* d_hist,

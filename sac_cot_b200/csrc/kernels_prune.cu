@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(1024) node_plan_kernel(const PairDesc* __restr
                                                          const unsigned short* __restrict__ deg,
                                                          NodePlan* __restrict__ plan, unsigned short* __restrict__ kept,
                                                          uint32_t* __restrict__ keptbits, int* __restrict__ n_pruned,
-                                                         int cost, int force) {
+                                                         int cost, int force, int rect) {
   const int pair = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   NodePlan* pl = plan + pair;
@@ -145,18 +145,24 @@ __global__ void __launch_bounds__(1024) node_plan_kernel(const PairDesc* __restr
     pl->n_keep = static_cast<uint32_t>(n_keep);
     pl->ub_rest = static_cast<uint32_t>(D ? D * (D - 1ull) / 2ull : 0ull);  // D <= 65534: < 2^31
     pl->min_deg = min_deg;
-    pl->pruned = 1u;
+    // 2: the kept rows go through the tensor-core kernel's RECT instance (long rows, few enough kept nodes for its
+    // compact panel copy); 1: through the kept-row POPC kernel
+    pl->pruned = (rect && n_keep <= kRectRows && d.Npad >= kRectMinNpad) ? 2u : 1u;
     atomicAdd(n_pruned, 1);
     atomicAdd(&sticky->pruned_total, 1u);  // the host learns from it whether trying pays on this ctx's workload
   }
 }
 
-// Order-preserving compaction of the tile list (the runs the host dealt stay runs).  One CTA.  out_total[0] = tiles
-// left, or -1 if no pair was pruned (the tensor-core kernel then walks the original list); out_total[1] = pruned
-// pairs (zeroed with the chunk state, counted by node_plan_kernel).
-__global__ void __launch_bounds__(1024) tile_compact_kernel(const uint2* __restrict__ tiles, int total,
+// Order-preserving compaction of the tile list (the runs the host dealt stay runs) and the tile list of the RECT
+// instance.  One CTA.  out_total[0] = tiles left, or -1 if no pair was pruned (the tensor-core kernel then walks the
+// original list); out_total[1] = pruned pairs (zeroed with the chunk state, counted by node_plan_kernel);
+// out_total[2] = RECT tiles: for every pair with plan.pruned == 2, column block by column block, its row blocks of
+// 256 kept nodes — entries (pair, row block << 16 | column block) like the square tiles.
+__global__ void __launch_bounds__(1024) tile_compact_kernel(const PairDesc* __restrict__ descs, int pairs,
+                                                            const uint2* __restrict__ tiles, int total,
                                                             const NodePlan* __restrict__ plan,
-                                                            uint2* __restrict__ out, int* __restrict__ out_total) {
+                                                            uint2* __restrict__ out, int* __restrict__ out_total,
+                                                            uint2* __restrict__ rect) {
   __shared__ int s_w[32];
   __shared__ int s_base;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -188,7 +194,64 @@ __global__ void __launch_bounds__(1024) tile_compact_kernel(const uint2* __restr
     }
     __syncthreads();
   }
-  if (t == 0) *out_total = s_base;
+  if (t == 0) {
+    out_total[0] = s_base;
+    s_base = 0;
+  }
+  __syncthreads();
+  for (int b0 = 0; b0 < pairs; b0 += 1024) {  // RECT tiles: one thread per pair, offsets by a block scan
+    const int b = b0 + t;
+    int nI = 0, nJ = 0;
+    if (b < pairs && plan[b].pruned == 2u) {
+      nI = (static_cast<int>(plan[b].n_keep) + kMmaTileM - 1) / kMmaTileM;
+      nJ = (descs[b].N + kMmaTileN - 1) / kMmaTileN;
+    }
+    const int cnt = nI * nJ;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_w[w];
+    uint2* dst = rect + before + incl - cnt;
+    for (int jq = 0; jq < nJ; ++jq)
+      for (int ib = 0; ib < nI; ++ib) *dst++ = make_uint2(static_cast<unsigned>(b), (static_cast<unsigned>(ib) << 16) | static_cast<unsigned>(jq));
+    __syncthreads();
+    if (t == 0) {
+      int add = 0;
+      for (int w = 0; w < 32; ++w) add += s_w[w];
+      s_base += add;
+    }
+    __syncthreads();
+  }
+  if (t == 0) out_total[2] = s_base;
+}
+
+// Compact copy of the kept nodes' K-panel records for the RECT instance: [panel][kRectRows rows][8 words] per pair,
+// row a = kept node a; the rows up to the next multiple of 256 are zero.  grid (panels, pairs).
+__global__ void __launch_bounds__(256) kept_panel_kernel(const PairDesc* __restrict__ descs, const uint32_t* __restrict__ panel,
+                                                         const NodePlan* __restrict__ plan, const unsigned short* __restrict__ kept,
+                                                         uint32_t* __restrict__ kpanel, long long kpanel_pair_words) {
+  const int pair = blockIdx.y;
+  const NodePlan pl = plan[pair];
+  if (pl.pruned != 2u) return;
+  const PairDesc d = descs[pair];
+  const int p = blockIdx.x;
+  if (p >= ((d.npanel + 1) & ~1)) return;
+  const int rows = (static_cast<int>(pl.n_keep) + kMmaTileM - 1) / kMmaTileM * kMmaTileM;
+  const uint4* src = reinterpret_cast<const uint4*>(panel + d.panel_off) + static_cast<size_t>(p) * d.Npad * 2;
+  uint4* dst = reinterpret_cast<uint4*>(kpanel + static_cast<long long>(pair) * kpanel_pair_words) + static_cast<size_t>(p) * kRectRows * 2;
+  const unsigned short* kp = kept + static_cast<size_t>(pair) * kNodeKeepMax;
+  for (int k = threadIdx.x; k < 2 * rows; k += 256) {
+    const int a = k >> 1, h = k & 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (a < static_cast<int>(pl.n_keep) && p < d.npanel) v = __ldg(src + static_cast<size_t>(kp[a]) * 2 + h);
+    dst[static_cast<size_t>(a) * 2 + h] = v;
+  }
 }
 
 // popc(x & y) summed over WPL words per lane.  POPC runs on the XU pipe at a quarter of the ALU rate (16 lanes per
@@ -253,7 +316,7 @@ __global__ void __launch_bounds__(kKeptThreads, 1) triangles_kept_kernel(
   if (chunk->overflow || !chunk->use_tensor) return;
   const int pair = blockIdx.y;
   const NodePlan pl = plan[pair];
-  if (!pl.pruned) return;
+  if (pl.pruned != 1u) return;  // 2: the tensor-core kernel's RECT instance takes the pair
   const PairDesc d = descs[pair];
   if (d.stride > 32 * WPL) return;  // launched with the instance that fits the chunk's longest row
   // batches of 32 rows: row block b <-> adjacency word b of a kept row; this CTA's slice of them
@@ -443,18 +506,23 @@ int node_prune_configure() {
 int launch_node_plan(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_npad, const uint32_t* d_adj,
                      const ChunkDev* d_chunk, StickyDev* d_sticky, const PairDev* d_state, const uint32_t* d_theta, unsigned short* d_deg, NodePlan* d_plan,
                      unsigned short* d_kept, uint32_t* d_keptbits, const uint2* d_tiles, int total_tiles, uint2* d_tiles_out,
-                     int* d_total, int cost, int force) {
+                     int* d_total, int cost, int force, uint2* d_rect_tiles, const uint32_t* d_panel, uint32_t* d_kpanel,
+                     long long kpanel_pair_words, int max_npanel) {
   int gx = (8 * lc.sm_count + pairs - 1) / pairs;
   gx = std::max(1, std::min(gx, (max_npad + 31) / 32));
   node_degree_kernel<<<dim3(gx, pairs), 256, 0, lc.stream>>>(d_desc, d_adj, d_chunk, d_state, d_theta, d_deg, force);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -static_cast<int>(e);
-  node_plan_kernel<<<pairs, 1024, 0, lc.stream>>>(d_desc, d_chunk, d_sticky, d_state, d_theta, d_deg, d_plan, d_kept, d_keptbits, d_total + 1, cost, force);
+  node_plan_kernel<<<pairs, 1024, 0, lc.stream>>>(d_desc, d_chunk, d_sticky, d_state, d_theta, d_deg, d_plan, d_kept, d_keptbits, d_total + 1, cost, force, d_kpanel != nullptr ? 1 : 0);
   e = cudaGetLastError();
   if (e != cudaSuccess) return -static_cast<int>(e);
-  tile_compact_kernel<<<1, 1024, 0, lc.stream>>>(d_tiles, total_tiles, d_plan, d_tiles_out, d_total);
+  tile_compact_kernel<<<1, 1024, 0, lc.stream>>>(d_desc, pairs, d_tiles, total_tiles, d_plan, d_tiles_out, d_total, d_rect_tiles);
   e = cudaGetLastError();
-  return e == cudaSuccess ? 3 : -static_cast<int>(e);
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  if (d_kpanel == nullptr) return 3;
+  kept_panel_kernel<<<dim3((max_npanel + 1) & ~1, pairs), 256, 0, lc.stream>>>(d_desc, d_panel, d_plan, d_kept, d_kpanel, kpanel_pair_words);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 4 : -static_cast<int>(e);
 }
 
 int launch_triangles_kept(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int max_n, int max_stride,

@@ -163,14 +163,16 @@ __device__ __forceinline__ void expand_quad(const uint4 w, unsigned char* dst) {
 struct PairLite {
   int32_t N, Npad, stride, npanel;
   int64_t adj_off, node_off, panel_off;
+  int32_t nkeep;  // RECT instance: kept nodes of the pair (rows of its tiles index the kept list)
 };
 // tile entry e = (pair, row block << 16 | column block); d follows the pair.  The roles load the entry of
 // their NEXT tile one tile ahead (a dependent L2 round trip per tile otherwise sits in front of every role).
 __device__ __forceinline__ void decode_tile(const uint2 e, const PairDesc* __restrict__ descs, int& pair, PairLite& d,
-                                            int& I0, int& J0) {
+                                            int& I0, int& J0, const NodePlan* __restrict__ plan = nullptr) {
   if (static_cast<int>(e.x) != pair) {
     pair = static_cast<int>(e.x);
     const PairDesc* pd = descs + pair;
+    d.nkeep = plan ? static_cast<int32_t>(plan[pair].n_keep) : 0;
     d.N = pd->N;
     d.Npad = pd->Npad;
     d.stride = pd->stride;
@@ -244,13 +246,23 @@ __device__ __noinline__ void flush_keys(unsigned long long* kb, EpiCtx* ctx) {
 // (shared-memory atomic); if the buffer is full the keys go straight to the pair's list.  lo0 = key bits of
 // the thread's first row and column, (0xFFFF - i) << 16 | (0xFFFF - j); fa / fb = edge bits of its two rows
 // (with theta = 0 a masked-off entry, kBias, passes the threshold test too).
-__device__ __forceinline__ void push16(const uint32_t (&m)[16], uint32_t fa, uint32_t fb, uint32_t lo0,
+// loA / loB: key bits (0xFFFF - i) << 16 | (0xFFFF - j0) of the thread's two rows and first column.  RECT (tiles of a
+// node-pruned pair: the rows are kept nodes, every column is visited): an edge shows up from both of its ends, only
+// the end with j > i emits it.
+template <bool RECT>
+__device__ __forceinline__ void push16(const uint32_t (&m)[16], uint32_t fa, uint32_t fb, uint32_t loA, uint32_t loB,
                                        unsigned long long* kb, EpiCtx* ctx, uint32_t* hist_s) {
   const uint32_t thb = ctx->thb;
   uint32_t cand = 0;
 #pragma unroll
   for (int k = 0; k < 16; ++k)
-    if (m[k] >= thb && ((((k & 2) ? fb : fa) >> (8 * (k >> 2) + (k & 1))) & 1u)) cand |= 1u << k;
+    if (m[k] >= thb && ((((k & 2) ? fb : fa) >> (8 * (k >> 2) + (k & 1))) & 1u)) {
+      if constexpr (RECT) {
+        const uint32_t lo = ((k & 2) ? loB : loA) - static_cast<uint32_t>(8 * (k >> 2) + (k & 1));
+        if ((lo & 0xFFFFu) >= (lo >> 16)) continue;  // j <= i
+      }
+      cand |= 1u << k;
+    }
   if (cand == 0) return;
   const uint32_t nc = __popc(cand);
   const uint32_t pos = atomicAdd(&ctx->fill, nc);
@@ -265,7 +277,7 @@ __device__ __forceinline__ void push16(const uint32_t (&m)[16], uint32_t fa, uin
   for (int k = 0; k < 16; ++k) {
     if (cand & (1u << k)) {
       const uint32_t T = m[k] - kBias;
-      const uint32_t lo = lo0 - ((static_cast<uint32_t>((k >> 1) & 1) * 8u) << 16) - static_cast<uint32_t>(8 * (k >> 2) + (k & 1));
+      const uint32_t lo = ((k & 2) ? loB : loA) - static_cast<uint32_t>(8 * (k >> 2) + (k & 1));
       *dst++ = (static_cast<unsigned long long>(T) << 32) | lo;
       atomicAdd(&hist_s[T >> 4], 1u);
     }
@@ -314,13 +326,20 @@ __device__ __noinline__ void raise_threshold(uint32_t* hist_s, uint32_t* histp, 
     }                                      \
   } while (0)
 
-template <bool PROF>
+// RECT instance: tiles of node-pruned pairs (kernels_prune.cu).  A tile is 256 KEPT nodes (positions I0 .. I0 + 255
+// of the pair's kept list) x 240 columns; every column block is visited.  The A operand rows come from the compact
+// copy `kpanel` of the kept nodes' K-panel records ([panel][kRectRows rows][8 words] per pair, rows past the kept
+// count zero), the B operand rows from the pair's panel copy as usual.  The epilogue maps its rows through the kept
+// list: edge windows, keys (j > i only), node sums (row sums over ALL columns; no column sums).
+template <bool PROF, bool RECT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangles_mma_kernel(
     const PairDesc* __restrict__ descs, const uint2* __restrict__ tiles, int total_tiles, const int* __restrict__ d_total,
     const uint2* __restrict__ tiles2,
     const uint32_t* __restrict__ adj, const uint32_t* __restrict__ panel, PairDev* __restrict__ state,
     const ChunkDev* __restrict__ chunk, unsigned long long* __restrict__ keys, uint32_t* __restrict__ theta,
-    uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2, int Ke, int raise, int dbg) {
+    uint32_t* __restrict__ hist, unsigned long long* __restrict__ t2, int Ke, int raise, int dbg,
+    const NodePlan* __restrict__ plan, const unsigned short* __restrict__ kept, const uint32_t* __restrict__ kpanel,
+    long long kpanel_pair_words) {
   if (chunk->overflow || !chunk->use_tensor) return;
   // the list was compacted on the device (kernels_prune.cu): fewer tiles than the grid was sized for, possibly none
   if (d_total && *d_total >= 0) {
@@ -422,9 +441,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     // ahead: as register loads the compiler spilled them right after issue, which exposed the full
     // global-load latency on every tile.
     uint32_t* wmine = wbuf + warp * (5 * 32) + lane;
-    auto load_window = [&](const PairLite& pd, int I0, int J0, int slot) {
-      const int i = I0 + kCtaM * static_cast<int>(rank) + 32 * q + lane;
-      const bool row_ok = i < pd.Npad;
+    int i_next = 0;  // RECT: original index of this thread's row in the tile whose window is being fetched
+    auto load_window = [&](const PairLite& pd, int I0, int J0, int slot, int pair_of) {
+      int i = I0 + kCtaM * static_cast<int>(rank) + 32 * q + lane;
+      bool row_ok = i < pd.Npad;
+      if constexpr (RECT) {
+        row_ok = i < pd.nkeep;
+        i = row_ok ? static_cast<int>(__ldg(kept + static_cast<size_t>(pair_of) * kNodeKeepMax + i)) : 0;
+        i_next = i;
+      }
       const uint32_t* rowp = adj + pd.adj_off + static_cast<size_t>(row_ok ? i : 0) * pd.stride;
       const int w0 = (J0 >> 5) + 4 * h;
       const uint32_t dst = smem_u32(wmine + slot * (kEpiWarps * 5 * 32));
@@ -445,14 +470,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     int t = cid, I0 = 0, J0 = 0;
     uint2 en = make_uint2(0u, 0u);  // entry of the tile after this one
     if (t < total_tiles) {
-      decode_tile(tiles[t], descs, pair, d, I0, J0);
-      load_window(d, I0, J0, 0);
+      decode_tile(tiles[t], descs, pair, d, I0, J0, RECT ? plan : nullptr);
+      load_window(d, I0, J0, 0, pair);
       if (t + ncl < total_tiles) en = tiles[t + ncl];
     }
     for (; t < total_tiles; ++n) {
       // ---- this tile ----
       const int tJ0 = J0;
       const long long node_off = d.node_off;
+      const int irow = i_next;  // RECT: this tile's row index (fetched with its window one tile ago)
       const long long tq0 = PROF ? clock64() : 0;
       if (pair != cur_pair) {
         if (cur_pair >= 0) flush_pair();
@@ -489,7 +515,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       const int rbase = I0 + kCtaM * static_cast<int>(rank) + 32 * q;  // first row of this warp
       const int i = rbase + lane;
       const int cbase = tJ0 + 128 * h;  // first column of this warp's half
-      {
+      if constexpr (!RECT) {
         const int dd = i - cbase;  // keep j > i: clear window bits 0..dd
         if (dd >= 0) {
 #pragma unroll
@@ -505,8 +531,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       //      behind this tile's work) and fetch the entry of the tile after it ----
       t += ncl;
       if (t < total_tiles) {
-        decode_tile(en, descs, pair, d, I0, J0);
-        load_window(d, I0, J0, (n + 1) & 1);
+        decode_tile(en, descs, pair, d, I0, J0, RECT ? plan : nullptr);
+        load_window(d, I0, J0, (n + 1) & 1, pair);
         if (t + ncl < total_tiles) en = tiles[t + ncl];
       }
 
@@ -534,7 +560,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       // row sums, the sums of this thread's two rows per column.  lo0 = key bits of (row t8 of the half, column
       // 2 t4 of the unit): (0xFFFF - i) << 16 | (0xFFFF - j).
       auto half16 = [&](const uint32_t(&vv)[16], uint32_t fa, uint32_t fb, uint32_t& ra, uint32_t& rb, uint32_t(&c)[8],
-                        uint32_t lo0, bool first) {
+                        uint32_t loA, uint32_t loB, bool first) {
         uint32_t m[16];
 #pragma unroll
         for (int b = 0; b < 4; ++b)
@@ -557,10 +583,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         // rare (with a tight theta): one of this thread's 16 edges reaches the pruning threshold
         if (max(a, bb) >= thb) {
           const long long te0 = PROF ? clock64() : 0;
-          push16(m, fa, fb, lo0, kb, ctx, hist_s);
+          push16<RECT>(m, fa, fb, loA, loB, kb, ctx, hist_s);
           if (PROF) t_emit += clock64() - te0;
         }
       };
+      // RECT: key bits of the original indices of the thread's four fragment rows (rows t8 + 8 s of the warp's 32)
+      uint32_t rowbits[4] = {0u, 0u, 0u, 0u};
+      if constexpr (RECT) {
+#pragma unroll
+        for (int sidx = 0; sidx < 4; ++sidx)
+          rowbits[sidx] = (0xFFFFu - static_cast<uint32_t>(__shfl_sync(0xffffffffu, irow, t8 + 8 * sidx))) << 16;
+      }
       if (!(dbg & 1)) {
         SACCOT_TMEM_LDF4(v[0], tbase);
 #pragma unroll 1
@@ -572,15 +605,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
           const uint32_t f2 = __shfl_sync(0xffffffffu, wown, t8 + 16) >> (2 * t4);
           const uint32_t f3 = __shfl_sync(0xffffffffu, wown, t8 + 24) >> (2 * t4);
           uint32_t c[8];
+          // key bits of (row t8 of the half, column 2 t4 of the unit); consecutive rows in the square tiles
           const uint32_t lo0 = ((0xFFFFu - static_cast<uint32_t>(rbase + t8)) << 16) |
                                (0xFFFFu - static_cast<uint32_t>(cbase + 32 * u + 2 * t4));
+          const uint32_t locol = lo0 & 0xFFFFu;
           SACCOT_TIMED_WAIT(t_ldw, asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"));
           SACCOT_TMEM_LDF4(v[1], tbase + (16u << 16) + 32u * u);
-          half16(v[0], f0, f1, rs0, rs1, c, lo0, true);
+          if constexpr (RECT) half16(v[0], f0, f1, rs0, rs1, c, rowbits[0] | locol, rowbits[1] | locol, true);
+          else half16(v[0], f0, f1, rs0, rs1, c, lo0, lo0 - (8u << 16), true);
           SACCOT_TIMED_WAIT(t_ldw, asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"));
           if (u + 1 < 4) SACCOT_TMEM_LDF4(v[0], tbase + 32u * (u + 1));
-          half16(v[1], f2, f3, rs2, rs3, c, lo0 - (16u << 16), false);
+          if constexpr (RECT) half16(v[1], f2, f3, rs2, rs3, c, rowbits[2] | locol, rowbits[3] | locol, false);
+          else half16(v[1], f2, f3, rs2, rs3, c, lo0 - (16u << 16), lo0 - (24u << 16), false);
           // column sums (t2_j): c[2 b + e] covers 4 of the 32 rows; reduce-scatter over the lanes that share t4
+          // (RECT: a kept node's sum is its row sum over all columns, nothing is collected per column)
+          if constexpr (!RECT) {
           {
             const bool hi = (lane & 16) != 0;
 #pragma unroll
@@ -604,6 +643,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
             const uint32_t cs = keep + __shfl_xor_sync(0xffffffffu, send, 4) - 32u * kBias;
             if (cs)
               atomicAdd(&t2[node_off + cbase + 32 * u + 8 * (t8 >> 1) + 2 * t4 + (t8 & 1)], static_cast<unsigned long long>(cs));
+          }
           }
           // staged keys: drain the buffer once it is half full (warp-uniform: every push happened before the barrier)
           __syncwarp();
@@ -634,7 +674,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         const uint32_t a1 = (hi2 ? rs3 : rs1) + __shfl_xor_sync(0xffffffffu, hi2 ? rs1 : rs3, 2);
         // 128 values x kBias = 0x80000000 (mod 2^32)
         const uint32_t rowsum = (hi1 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi1 ? a0 : a1, 1) - 128u * kBias;
-        if (rowsum) atomicAdd(&t2[node_off + rbase + t8 + 8 * t4], static_cast<unsigned long long>(rowsum));
+        int trow = rbase + t8 + 8 * t4;
+        if constexpr (RECT) trow = __shfl_sync(0xffffffffu, irow, t8 + 8 * t4);
+        if (rowsum) atomicAdd(&t2[node_off + trow], static_cast<unsigned long long>(rowsum));
       }
       if (PROF) t_tail += clock64() - tq4;
     }
@@ -736,6 +778,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       rowsB = max(0, min(kCtaNB, lNpad - b0));
       lsrcA = lbase + static_cast<size_t>(a0) * 2 + q;
       lsrcB = lbase + static_cast<size_t>(b0) * 2 + q;
+      if constexpr (RECT) {  // A rows: the compact copy of the kept nodes' records (whole row blocks, zero padded)
+        rowsA = kCtaM;
+        lsrcA = reinterpret_cast<const uint4*>(kpanel + static_cast<long long>(lpair) * kpanel_pair_words) + static_cast<size_t>(a0) * 2 + q;
+      }
     };
     if (lt < total_tiles) {
       enter_tile(tiles[lt]);
@@ -754,13 +800,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
       if (lt >= total_tiles) return false;
       const bool real = lit < lnpanel;  // the padding stage of an odd panel count carries no data
       const size_t poff = static_cast<size_t>(lit) * lNpad * 2;  // uint4 units: panel lit
+      const size_t poffA = RECT ? static_cast<size_t>(lit) * kRectRows * 2 : poff;
 #pragma unroll
       for (int k = 0; k < kTasksPerWarp; ++k) {
         const int gr = 2 * (wq + kWarpsPerGroup * k) + rg2;  // 8-row group of this lane
         const int r = 8 * gr + r8;
         const bool isA = r < kCtaM;
         const bool ok = real && gr < kGroups && (isA ? r < rowsA : r - kCtaM < rowsB);
-        const uint4* src = (isA ? lsrcA + static_cast<size_t>(r) * 2 : lsrcB + static_cast<size_t>(r - kCtaM) * 2) + poff;
+        const uint4* src = isA ? lsrcA + static_cast<size_t>(r) * 2 + poffA : lsrcB + static_cast<size_t>(r - kCtaM) * 2 + poff;
         w[k] = ok ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
       }
       lit += kGroupsP;
@@ -1303,9 +1350,11 @@ int launch_mma_peak_probe(const LaunchCtx& lc, int clusters, int stage_pairs) {
 }
 
 int triangles_mma_configure() {
-  cudaError_t e = cudaFuncSetAttribute(triangles_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(triangles_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(triangles_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    e = cudaFuncSetAttribute(triangles_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(triangles_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kStageBytes);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tri_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1348,12 +1397,29 @@ int launch_triangles_mma(const LaunchCtx& lc, const PairDesc* d_desc, const uint
   const int grid = 2 * mma_clusters(total_tiles, lc.sm_count);  // CTA pairs
   if (grid > 0) {
     if (dbg & 64)
-      triangles_mma_kernel<true><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_total, d_tiles2, d_adj, d_panel,
-                                                                           d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, Ke, raise, dbg);
+      triangles_mma_kernel<true, false><<<grid, kThreads, kSmemBytes, lc.stream>>>(
+          d_desc, d_tiles, total_tiles, d_total, d_tiles2, d_adj, d_panel, d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, Ke,
+          raise, dbg, nullptr, nullptr, nullptr, 0);
     else
-      triangles_mma_kernel<false><<<grid, kThreads, kSmemBytes, lc.stream>>>(d_desc, d_tiles, total_tiles, d_total, d_tiles2, d_adj, d_panel,
-                                                                            d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, Ke, raise, dbg);
+      triangles_mma_kernel<false, false><<<grid, kThreads, kSmemBytes, lc.stream>>>(
+          d_desc, d_tiles, total_tiles, d_total, d_tiles2, d_adj, d_panel, d_state, d_chunk, d_keys, d_theta, d_hist, d_t2, Ke,
+          raise, dbg, nullptr, nullptr, nullptr, 0);
   }
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -static_cast<int>(e);
+}
+
+// tiles of node-pruned pairs (kernels_prune.cu): the list and its length live on the device; max_tiles bounds it
+int launch_triangles_mma_rect(const LaunchCtx& lc, const PairDesc* d_desc, const uint2* d_rect_tiles, int max_tiles,
+                              const int* d_rect_total, const uint32_t* d_adj, const uint32_t* d_panel, PairDev* d_state,
+                              const ChunkDev* d_chunk, unsigned long long* d_keys, uint32_t* d_theta, uint32_t* d_hist,
+                              unsigned long long* d_t2, int Ke, int raise, int dbg, const NodePlan* d_plan,
+                              const unsigned short* d_kept, const uint32_t* d_kpanel, long long kpanel_pair_words) {
+  const int grid = 2 * mma_clusters(max_tiles, lc.sm_count);
+  if (grid <= 0) return 0;
+  triangles_mma_kernel<false, true><<<grid, kThreads, kSmemBytes, lc.stream>>>(
+      d_desc, d_rect_tiles, max_tiles, d_rect_total, d_rect_tiles, d_adj, d_panel, d_state, d_chunk, d_keys, d_theta, d_hist,
+      d_t2, Ke, raise, dbg, d_plan, d_kept, d_kpanel, kpanel_pair_words);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -static_cast<int>(e);
 }

@@ -203,6 +203,7 @@ def test_device_resident_entry_point(gpu_lib, oracle):
     with Registrar(lib=gpu_lib, device=0, stream=stream.cuda_stream) as g:
         g.set("triangle_path", 0)
         g.set("lanes", 2)
+        g.set("chunk_pairs", 3)   # (five pairs this small would otherwise run as one chunk)
         g.register_packed_ptr(d_src.data_ptr(), d_dst.data_ptr(), offsets, d_R.data_ptr(), d_t.data_ptr(),
                               d_i.data_ptr(), _abi.LOC_DEVICE)
         stream.synchronize()
@@ -927,17 +928,23 @@ def compare_node_pruned(gpu, oracle, pair_idx=0):
 KITTI = dict(box=(60.0, 60.0, 6.0), tau_compat=0.6)   # ~2.3 % edge density: outlier degrees stay below the clique's counts
 
 
+@pytest.mark.parametrize("rect", [1, 0])
 @pytest.mark.parametrize("apex_path", [0, 1])
 @pytest.mark.parametrize("N,ratio,Ke,m,kw", [
     (1200, 0.10, 256, 4, {}), (2048, 0.10, 256, 4, {}), (3000, 0.30, 512, 2, {}), (5000, 0.05, 1024, 4, KITTI),
     (5000, 0.05, 4096, 8, KITTI), (4999, 0.04, 64, 8, KITTI), (1500, 0.08, 1, 1, {}), (6000, 0.03, 1024, 4, KITTI),
     (10000, 0.03, 1024, 4, KITTI),
 ])
-def test_node_pruned_path_matches_oracle(gpu, oracle, N, ratio, Ke, m, kw, apex_path):
+def test_node_pruned_path_matches_oracle(gpu, oracle, N, ratio, Ke, m, kw, apex_path, rect):
+    """rect = 1: the kept rows of pairs with N >= 1921 (Npad >= 2048) and at most 1024 kept nodes go through the RECT
+    instance of the tensor-core kernel, the others (and everything with rect = 0) through the kept-row POPC kernel."""
+    if rect == 0 and apex_path == 1 and N > 3000:
+        pytest.skip("the apex paths do not depend on which kernel counted the kept rows")
     gpu.set("triangle_path", 1)
     gpu.set("node_prune", 2)
+    gpu.set("node_prune_rect", 2 * rect)   # 2: also for a single pair
     gpu.set("apex_path", apex_path)   # 1: no rank list, every edge evaluates its unknown candidates on demand
-    assert gpu.get("node_prune") == 2
+    assert gpu.get("node_prune") == 2 and gpu.get("node_prune_rect") == 2 * rect
     p = synth.make_pair(N, ratio, 9300 + N + Ke, **kw)
     for r in (gpu, oracle):
         set_params(r, tau_compat=p.tau_compat, tau_inlier=p.tau_inlier, num_edges=Ke, apex_per_edge=m)
@@ -945,6 +952,7 @@ def test_node_pruned_path_matches_oracle(gpu, oracle, N, ratio, Ke, m, kw, apex_
     out_o = oracle.register(p.src, p.dst)
     assert gpu.get("pruned_pairs") == 1, "the pair was expected to take the kept-row kernel"
     assert 2 <= gpu.get("kept_nodes") <= 2048
+    assert gpu.get("rect_pairs") == (1 if rect and N > 1920 and gpu.get("kept_nodes") <= 1024 else 0)
     compare_node_pruned(gpu, oracle)
     compare_pose(*out_g, *out_o)
 
@@ -975,6 +983,7 @@ def test_node_pruning_mixed_batch_and_cost_model(gpu, oracle):
     ro = oracle.register_batch([q.src for q in pairs], [q.dst for q in pairs])
     npr = gpu.get("pruned_pairs")
     assert 1 <= npr < len(pairs), npr
+    assert 1 <= gpu.get("rect_pairs") < npr   # the N = 2048 pair; the shorter ones take the kept-row POPC kernel
     for b in range(len(pairs)):
         compare_node_pruned(gpu, oracle, b)
         compare_pose(rg.R[b], rg.t[b], rg.inliers[b], ro.R[b], ro.t[b], ro.inliers[b])
@@ -990,7 +999,7 @@ def test_node_pruning_mixed_batch_and_cost_model(gpu, oracle):
 def test_node_pruning_is_the_default_and_invisible(gpu_lib, oracle):
     """Default ctx (no keep_debug): outdoor-scale pairs prune down to their inlier cliques; poses equal the oracle's and
     those of a ctx with the pruning switched off, bit for bit."""
-    ps = [synth.make_pair(6000, 0.03, 9450 + b, **KITTI) for b in range(3)]
+    ps = [synth.make_pair(6000, 0.03, 9450 + b, **KITTI) for b in range(5)]   # >= 4 pairs: RECT instance for the kept rows
     set_params(oracle, tau_compat=ps[0].tau_compat, tau_inlier=ps[0].tau_inlier)
     ro = oracle.register_batch([q.src for q in ps], [q.dst for q in ps])
     outs = []
@@ -1002,6 +1011,7 @@ def test_node_pruning_is_the_default_and_invisible(gpu_lib, oracle):
             rg = reg.register_batch([q.src for q in ps], [q.dst for q in ps])
             assert reg.get("triangle_path_used") == 1
             assert reg.get("pruned_pairs") == (len(ps) if mode else 0)
+            assert reg.get("rect_pairs") == (len(ps) if mode else 0)
             if mode:   # the inlier cliques and a few central (high-degree) outliers
                 n_in = sum(len(q.inlier_idx) for q in ps)
                 assert n_in <= reg.get("kept_nodes") <= 3 * n_in
