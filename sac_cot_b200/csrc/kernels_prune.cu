@@ -15,8 +15,11 @@
 //   node_degree_kernel   exact degrees (one warp per row)
 //   node_plan_kernel     per pair: kept list (ascending), D, and the decision (cost model below)
 //   tile_compact_kernel  tile list of the tensor-core kernel without the tiles of pruned pairs
-//   triangles_kept_kernel the loop above: a warp holds 4 kept rows in registers, a producer warp streams all rows of
-//                        the pair through a shared-memory ring in batches of 32 (bulk copies, mbarriers)
+//   triangles_kept_kernel the loop above on the CUDA cores: a warp holds 4 kept rows in registers, all rows of the pair
+//                        stream through a shared-memory ring in batches of 32 (bulk copies, mbarriers)
+//   kept_panel_kernel    compact copy of the kept nodes' K-panel records: long pairs in chunks of >= 4 run the same
+//                        loop as tiles "kept nodes x all columns" of the tensor-core kernel's RECT instance
+//                        (kernels_triangles_mma.cu), whose tile list tile_compact_kernel also writes
 #include "common.cuh"
 
 #include <algorithm>
