@@ -27,6 +27,7 @@ upstream repository ships no code (/root/reference/README.md:1-2), so the from-p
 """
 import argparse
 import ctypes
+import datetime
 import json
 import os
 import statistics
@@ -90,17 +91,17 @@ def time_oracle(lib, ps, cfg, threads=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  The sampling process is started when the object is
+    made (before the warm-up: nvidia-smi needs a few hundred ms before its first line, longer than a short timed
+    region); start() / stop() mark the timed region and only the samples whose timestamps fall inside it are used."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
-
-    def start(self):
+        self.t_begin = self.t_end = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
@@ -108,7 +109,18 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def start(self):
+        self.t_begin = time.time()
+
+    @staticmethod
+    def _when(stamp):
+        try:   # "2026/10/18 23:11:02.123", local time
+            return datetime.datetime.strptime(stamp, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
     def stop(self):
+        self.t_end = time.time()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -119,29 +131,37 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, smax, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        rows = []   # (time or None, sm, smax, power, reasons)
         for line in self.f:
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1]))
-                smax.append(float(c[2]))
-                power.append(float(c[3]))
+                row = (self._when(c[0]), float(c[2]), float(c[3]), float(c[4]),
+                       {name for name, v in zip(names, c[6:10]) if v.lower().startswith("active")})
             except ValueError:
                 continue
-            for name, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+            rows.append(row)
         self.f.close()
         os.unlink(self.f.name)
-        if sm:
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [r for r in rows if r[0] is None or t0 - 0.02 <= r[0] <= self.t_end + 0.02]
+        window = "timed region"
+        if not inside and rows:
+            # a region shorter than the sampling period: the samples of the second before it (the warm-up steps,
+            # the same kernels on the same device)
+            inside = [r for r in rows if r[0] is not None and t0 - 1.0 <= r[0] <= self.t_end + 0.02] or rows[-3:]
+            window = "no sample fell inside the timed region; taken from the warm-up steps just before it"
+        if inside:
+            sm = [r[1] for r in inside]
+            power = [r[3] for r in inside]
+            reasons = set().union(*[r[4] for r in inside])
             # "under load" = samples at or above the median power draw
             pm = statistics.median(power)
             load = [s for s, p in zip(sm, power) if p >= pm] or sm
-            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(smax), power_w_max=max(power),
-                       reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(r[2] for r in inside), power_w_max=max(power),
+                       reasons=sorted(reasons), samples=len(inside), window=window)
         return out
 
 
@@ -306,6 +326,7 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
         torch.cuda.synchronize(dev)
 
     # ---- warm-up (also grows the workspace / key pool to steady state) ----
+    sampler = ClockSampler(local_rank)   # sampling starts now; start() / stop() bracket the timed region
     for _ in range(args.warmup):
         step_device()
         torch.cuda.synchronize(dev)
@@ -323,7 +344,6 @@ def run_batched(args, rank, local_rank, world, emit, torch, dist, dev):
 
     # ---- timed region 1: device-resident (value) ----
     launches0 = reg.get("launches")
-    sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     sampler.start()
@@ -566,10 +586,10 @@ def run_group(args, emit, torch):
     def step():
         grp.register_packed_ptr(h_src.data_ptr(), h_dst.data_ptr(), offsets, h_R.data_ptr(), h_t.data_ptr(), h_i.data_ptr())
 
+    sampler = ClockSampler(0)
     for _ in range(args.warmup + 2):
         step()
     launches0 = sum(grp.get(g, "launches") for g in range(G))
-    sampler = ClockSampler(0)
     sampler.start()
     ts = []
     for _ in range(args.steps):
@@ -661,12 +681,12 @@ def run_match_bench(args, emit, torch, dev):
         torch.cuda.synchronize(dev)
         return [a.elapsed_time(b) for a, b in ev]
 
+    sampler = ClockSampler(dev.index)
     for _ in range(args.warmup):
         match()
         register()
         torch.cuda.synchronize(dev)
         reg.get("last_status")
-    sampler = ClockSampler(dev.index)
     sampler.start()
     launches0 = reg.get("launches")
     ms_match = timed(match, args.steps)
@@ -814,6 +834,7 @@ def run_single_sharded(args, rank, local_rank, world, emit, torch, dist, dev):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup + 1):
         step_device()
         torch.cuda.synchronize(dev)
@@ -825,7 +846,6 @@ def run_single_sharded(args, rank, local_rank, world, emit, torch, dist, dev):
     ang, dtr = synth.pose_error(R_sh, t_sh, p.R_gt, p.t_gt)
 
     launches0 = reg.get("launches")
-    sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     sampler.start()

@@ -60,14 +60,16 @@ int launch_pack_soa(const LaunchCtx& lc, const PairDesc* d_desc, int pairs, int 
 //     P(x, y) = | RN(RN(sqrt x) - RN(sqrt y)) | < tau          x = s2, y = d2 (fp32, as above)
 // Evaluating it literally costs two sqrt.rn expansions (~20 instructions).  Instead the kernel
 // computes, in fp32 (u = 2^-24, every op individually rounded),
-//     S = x + y;  U = S - tau2f;  Q = U*U - 4*(x*y);  Theta = (S*S) * 2^-19
+//     S = x + y;  U = S - tau2f;  Q = U*U - 4*(x*y);  Theta = (U*U) * (3 * 2^-20)
 // with tau2f = RN(tau*tau).  In real arithmetic  Q* = ((a-b)^2 - tau^2)((a+b)^2 - tau^2), a = sqrt x,
 // b = sqrt y, so for (a+b) > 2 tau its sign is the sign of |a-b| - tau.  Error analysis (DESIGN.md
 // "S1 exact filter"): if S > lo = max(4 tau2f, 2^-50) then |Q - Q*| <= 7.6u (x+y)^2 (+ 8u (x+y)^2 because the
 // filter forms x and y with fused multiply-adds, within 4u of the specified values), and whenever
 // the literal predicate could disagree with sign(|a-b| - tau) (rounding of the two square roots
 // and of their difference, at most 2.1u (a+b) in total) one has |Q*| <= 8.5u (x+y)^2.  Hence
-//     |Q| > Theta  (Theta >= 31.9u (x+y)^2 > 7.6u + 8u + 8.5u)   ==>   P(x, y) == (Q < 0)          exactly.
+//     |Q| > Theta  (S > 4 tau2f gives U >= 0.75 S, so Theta >= 26.9u (x+y)^2 > 7.6u + 8u + 8.5u)   ==>   P(x, y) == (Q < 0)
+// exactly.  (Theta re-uses the product U*U that Q needs anyway: one packed multiply less than (S*S) * 2^-19; the
+// factor 48u keeps the band of undecided pairs at 1.5x that version's where U ~ S, the usual case.)
 // Everything else — the ~1e-4 fraction of pairs inside the band, tiny/huge/NaN inputs, tau so
 // large that lo overflows — takes the literal sqrt.rn evaluation.  The result is bit-identical to
 // the oracle's for every input; tests/test_gpu_parity.py has adversarial near-threshold sets.
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
   for (int c = 0; c < 6; ++c) ri[c] = pack2(rv[c], rv[c]);  // SASS uses the scalar-broadcast operand form
   const f32x2 ntau2 = pack2(-tau2f, -tau2f);
   const f32x2 m4 = pack2(-4.0f, -4.0f);
-  const f32x2 kth = pack2(1.9073486328125e-06f, 1.9073486328125e-06f);  // 2^-19
+  const f32x2 kth = pack2(2.86102294921875e-06f, 2.86102294921875e-06f);  // 3 * 2^-20 = 48u
   mbar_wait(&bar, 0);
 
   // Pad rows (i >= N) and pad columns (j >= N) hold NaN and give zero bits through the literal path; that path
@@ -189,24 +191,30 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
   // were 6 % of the kernel's instructions.  They are skipped instead: same (zero) bits.
   const int ncv = min(128, d.N - J0);        // valid columns of this tile (> 0)
   const bool row_valid = I0 + r < d.N;
-  uint32_t words[4];
-#pragma unroll
+  // One word = 32 columns = eight groups of four (one 128-bit broadcast load per staged array and group).  The word
+  // is assembled by shifting one sign bit in per test (one funnel shift each): groups from the top of the word
+  // down, and the four columns of a group from the last to the first, so that every bit ends up at its column's
+  // position.  A group the filter is not sure about only leaves a flag; the flagged groups (rare: inside the
+  // rounding band, out-of-range magnitudes, or NaN pad columns) are re-evaluated literally after the word.  The
+  // loop over the words stays rolled and the eight groups of a full word are straight-line code without any
+  // per-group test: the kernel is bound by instruction issue, and the per-group loop overhead (validity tests,
+  // re-derived shared-memory addresses, the branch around the fallback) was 3 of 17 instructions per pair test
+  // (2.64 -> 2.43 ms per 256-pair step).  Measured slower (profiles/experiments/README.md): ONE predicate per word and
+  // the whole word redone group by group when it fails (+9 %; +18 % at KITTI scale) — per test the filter is
+  // undecided 2e-4 of the time, but a warp visits 1024 tests per word, so every fifth warp-word took the slow path.
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll 1
   for (int cw = 0; cw < 4; ++cw) {
-    // The word is assembled by shifting one sign bit in per test (one funnel shift each): column groups from the
-    // top of the word down, and the four columns of a group from the last to the first, so that every bit ends
-    // up at its column's position.
-    uint32_t wbits = 0;
-#pragma unroll 2
-    for (int b = 28; b >= 0; b -= 4) {
-      const int c = cw * 32 + b;
-      if (c >= ncv || !row_valid) {  // c >= ncv is uniform over the CTA
-        wbits <<= 4;
-        continue;
-      }
-      float4 cj[6];  // four staged columns per 128-bit broadcast load
+    const int c0 = cw * 32;
+    const int nv = ncv - c0;  // valid columns of this word (uniform over the CTA)
+    uint32_t wbits = 0, unsure = 0;
+    // columns c0 + 4 g .. c0 + 4 g + 3: shifts their four sign bits into wbits; `sure` stays true iff the filter is
+    // sure about all four
+    auto group4 = [&](const int g, bool& sure) {
+      const int c = c0 + 4 * g;
+      float4 cj[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) cj[k] = *reinterpret_cast<const float4*>(&cs[k][c]);
-      bool sure = true;
 #pragma unroll
       for (int h = 1; h >= 0; --h) {  // two packed column pairs: columns c+2, c+3 first
         f32x2 col[6];
@@ -218,8 +226,9 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
         // exact filter: trust sign(Q) iff |Q| > Theta and S > lo
         const f32x2 S = add2(x, y);
         const f32x2 U = add2(S, ntau2);
-        const f32x2 Q = fma2(mul2(x, y), m4, mul2(U, U));
-        const f32x2 T = mul2(mul2(S, S), kth);
+        const f32x2 UU = mul2(U, U);
+        const f32x2 Q = fma2(mul2(x, y), m4, UU);
+        const f32x2 T = mul2(UU, kth);
         float q0, q1, t0, t1, s0, s1;
         unpack2(Q, q0, q1);
         unpack2(T, t0, t1);
@@ -228,11 +237,36 @@ __global__ void __launch_bounds__(128) graph_kernel(const PairDesc* __restrict__
         wbits = __funnelshift_l(__float_as_uint(q1), wbits, 1);  // bit = (Q < 0) when sure
         wbits = __funnelshift_l(__float_as_uint(q0), wbits, 1);
       }
-      if (!sure)  // rare: inside the rounding band, out-of-range magnitudes, or NaN (pad columns)
-        wbits = (wbits & ~0xFu) | compat_literal4(cs, c, rv[0], rv[1], rv[2], rv[3], rv[4], rv[5], tau);
+    };
+    if (row_valid && nv > 0) {
+      if (nv >= 32) {
+#pragma unroll
+        for (int g = 7; g >= 0; --g) {
+          bool sure = true;
+          group4(g, sure);
+          if (!sure) unsure |= 1u << g;
+        }
+      } else {  // last column tile of the pair: only the groups that hold a valid column
+#pragma unroll 1
+        for (int g = (nv - 1) >> 2; g >= 0; --g) {
+          bool sure = true;
+          group4(g, sure);
+          if (!sure) unsure |= 1u << g;
+        }
+      }
+      while (unsure) {
+        const int g = __ffs(static_cast<int>(unsure)) - 1;
+        unsure &= unsure - 1u;
+        const uint32_t lit = compat_literal4(cs, c0 + 4 * g, rv[0], rv[1], rv[2], rv[3], rv[4], rv[5], tau);
+        wbits = (wbits & ~(0xFu << (4 * g))) | (lit << (4 * g));
+      }
     }
-    words[cw] = wbits;
+    if (cw == 0) w0 = wbits;
+    else if (cw == 1) w1 = wbits;
+    else if (cw == 2) w2 = wbits;
+    else w3 = wbits;
   }
+  uint32_t words[4] = {w0, w1, w2, w3};
 
   uint32_t* adjp = adj + d.adj_off;
   unsigned int cnt = 0;

@@ -261,13 +261,59 @@ __device__ __forceinline__ f32x2 residual2_x2(const f32x2 (&rt2)[12], f32x2 px, 
   return fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
 }
 
+// Shared-memory loads through explicit 32-bit shared addresses (phase 2 of the scoring kernel): with generic
+// pointers the compiler re-derives the shared window base (S2UR SR_CgaCtaId, UMOV, ULEA, ...) in every iteration
+// of that divergent loop.
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+
+// Phase 2 of the scoring kernel for one hypothesis and one chunk: the specified chain for every candidate in `bits`.
+// q4 / q2: shared addresses of correspondence 31 of the chunk in pts4 / pts2.  Point j of the chunk sits at mask bit
+// 31 - j: the highest set bit, at position pos, is point 31 - pos, at q - size * pos.
+template <int MODE>
+__device__ __forceinline__ void score_bits(const float (&rt)[12], uint32_t bits, const uint32_t q4, const uint32_t q2,
+                                           const float tau2, unsigned int& cnt, unsigned long long& fsum) {
+  while (bits) {
+    uint32_t pos;  // one FLO (31 - __clz costs three more instructions here)
+    asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(bits));
+    bits ^= 1u << pos;
+    const float4 pa = lds_f32x4(q4 - 16u * pos);  // sx, sy, sz, dx
+    const float2 pq = lds_f32x2(q2 - 8u * pos);   // dy, dz
+    const float r2 = residual2(rt, pa, make_float4(pq.x, pq.y, 0.0f, 0.0f));
+    if (MODE == 0) {
+      asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\n@p add.u32 %0, %0, 1;\n}" : "+r"(cnt) : "f"(r2), "f"(tau2));
+    } else {
+      const float mm = r2 < tau2 ? r2 : tau2;  // NaN -> tau2
+      fsum += static_cast<unsigned int>(FMUL(FDIV(mm, tau2), 1048576.0f));
+    }
+  }
+}
+
 // Two phases per 32 correspondences.  Phase 1 (packed, every correspondence): x' and the sign of ex^2 - tau^2 only —
 // 5 packed FP instructions per two points instead of 15.  r2 = fma(ez,ez,fma(ey,ey,ex*ex)) >= RN(ex*ex) in fp32 as
 // in real arithmetic (each fma adds a non-negative term and rounding is monotone), so a point with ex^2 >= tau^2
-// cannot be an inlier and contributes the constant 2^20 in mode 1; ~93 % of the points of a 3 m scene leave here.
+// cannot be an inlier and contributes the constant 2^20 in mode 1; ~89 % of the points of a 3 m scene leave here.
 // Phase 2 (scalar, the survivors, one bit per point in a register mask): the full specified chain, bit-identical to
-// the oracle's.  ncu before (`profiles/ncu_score_r01a.txt`): FP32 pipe saturated by 15 FFMA2-class instructions per
-// point pair and hypothesis, issue slots 56 % used.
+// the oracle's.  On the headline workload 10.6 % of the (hypothesis, correspondence) pairs get here (the 5 % inliers
+// and as many near misses); a warp runs for the largest count among its lanes (4.6 per 32 correspondences against
+// a mean of 3.4), which made this loop more than half of the kernel's instructions at 38 per iteration.  It reads
+// the correspondence from a second, point-by-point copy of the slab (one LDS.128 + one LDS.64 at explicit shared
+// addresses instead of six LDS.32 and a re-derived base) and finds it with one FLO: 29 instructions per iteration,
+// 56 registers (nine CTAs per SM instead of seven), 1.99 -> 1.77 ms per 256-pair step.  Tried and measured slower
+// (profiles/experiments/README.md, round 2): deferring phase 2 to the end of the slab with the masks in shared memory
+// (every lane walking its own list: fewer iterations, but 66 registers and a word-advance in the loop: +5 %); the
+// warp's COMMON candidates in a uniform loop first (+2 %); two candidates per iteration in packed lanes (the
+// packing moves cost more than the halved FP issue: +5 %).  ncu of the one-phase version
+// (`profiles/ncu_score_r01a.txt`): FP32 pipe saturated by 15 FFMA2-class instructions per point pair and hypothesis,
+// issue slots 56 % used.
 //
 // nsplit > 1 (few pairs, many points: the single-pair calls): the hypothesis blocks alone would leave most SMs idle,
 // so the correspondences are cut into nsplit ranges of whole slabs, one CTA per (hypothesis block, range); a CTA adds
@@ -287,8 +333,11 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
     n_begin = min(d.N, split * per * kScoreSlab);
     n_end = min(d.N, n_begin + per * kScoreSlab);
   }
-  // slab[p] holds correspondences 2p and 2p+1:  {sx0,sx1,sy0,sy1} {sz0,sz1,dx0,dx1} {dy0,dy1,dz0,dz1}
+  // slab[p] holds correspondences 2p and 2p+1:  {sx0,sx1,sy0,sy1} {sz0,sz1,dx0,dx1} {dy0,dy1,dz0,dz1}  (phase 1)
+  // pts4[n] / pts2[n]: the same correspondences one by one, {sx,sy,sz,dx} / {dy,dz}                    (phase 2)
   __shared__ float4 slab[kScoreSlab / 2][3];
+  __shared__ float4 pts4[kScoreSlab];
+  __shared__ __align__(16) float2 pts2[kScoreSlab];
   __shared__ unsigned long long wbest[kScoreThreads / 32];
 
   const int tid = threadIdx.x;
@@ -316,31 +365,38 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
   const float* base = soa + d.soa_off;
   const size_t np = static_cast<size_t>(d.Npad);
   const float nan = __int_as_float(0x7fc00000);
+  const uint32_t q4_0 = smem_u32(&pts4[31]), q2_0 = smem_u32(&pts2[31]);  // correspondence 31 of the slab's first chunk
   for (int n0 = n_begin; n0 < n_end; n0 += kScoreSlab) {
     const int nn = min(kScoreSlab, n_end - n0);
     const int npairs = (nn + 1) / 2;
     __syncthreads();  // previous slab fully consumed
     for (int k = tid; k < kScoreSlab / 2; k += kScoreThreads) {
       const int n = n0 + 2 * k;
+      float2 sx, sy, sz, dx, dy, dz;
       if (k < npairs) {
         // the SoA arrays are padded to Npad (even) with NaN, so n+1 is always readable; a NaN
-        // correspondence never passes phase 1
-        const float2 sx = *reinterpret_cast<const float2*>(base + n), sy = *reinterpret_cast<const float2*>(base + np + n),
-                     sz = *reinterpret_cast<const float2*>(base + 2 * np + n);
-        float2 dx = *reinterpret_cast<const float2*>(base + 3 * np + n), dy = *reinterpret_cast<const float2*>(base + 4 * np + n),
-               dz = *reinterpret_cast<const float2*>(base + 5 * np + n);
+        // correspondence never passes phase 2
+        sx = *reinterpret_cast<const float2*>(base + n);
+        sy = *reinterpret_cast<const float2*>(base + np + n);
+        sz = *reinterpret_cast<const float2*>(base + 2 * np + n);
+        dx = *reinterpret_cast<const float2*>(base + 3 * np + n);
+        dy = *reinterpret_cast<const float2*>(base + 4 * np + n);
+        dz = *reinterpret_cast<const float2*>(base + 5 * np + n);
         if (n + 1 >= n_end) { dx.y = nan; dy.y = nan; dz.y = nan; }
-        slab[k][0] = make_float4(sx.x, sx.y, sy.x, sy.y);
-        slab[k][1] = make_float4(sz.x, sz.y, dx.x, dx.y);
-        slab[k][2] = make_float4(dy.x, dy.y, dz.x, dz.y);
-      } else {  // tail of the last slab: NaN, never a candidate
-        slab[k][0] = make_float4(nan, nan, nan, nan);
-        slab[k][1] = make_float4(nan, nan, nan, nan);
-        slab[k][2] = make_float4(nan, nan, nan, nan);
+      } else {  // tail of the last slab: NaN, never an inlier
+        sx = sy = sz = dx = dy = dz = make_float2(nan, nan);
       }
+      slab[k][0] = make_float4(sx.x, sx.y, sy.x, sy.y);
+      slab[k][1] = make_float4(sz.x, sz.y, dx.x, dx.y);
+      slab[k][2] = make_float4(dy.x, dy.y, dz.x, dz.y);
+      pts4[2 * k] = make_float4(sx.x, sy.x, sz.x, dx.x);
+      pts4[2 * k + 1] = make_float4(sx.y, sy.y, sz.y, dx.y);
+      *reinterpret_cast<float4*>(&pts2[2 * k]) = make_float4(dy.x, dz.x, dy.y, dz.y);
     }
     __syncthreads();
-    for (int kc = 0; kc < npairs; kc += 16) {
+    const int nchunks = (npairs + 15) >> 4;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int kc = 16 * ch;
       // ---- phase 1: 32 correspondences.  The candidate bit of a point is the sign of ex*ex - tau^2, shifted into the
       //      mask with one funnel shift: point 2 j + p of the chunk ends up at bit 31 - (2 j + p).  (A NaN may land
       //      either way; phase 2 is exact for whatever it is given.) ----
@@ -367,22 +423,9 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
       // ---- phase 2: the full chain for the candidates ----
 #pragma unroll
       for (int u = 0; u < kScoreHyp; ++u) {
-        uint32_t bits = m[u];
-        if (MODE == 1) cnt[u] += __popc(bits);
-        while (bits) {
-          const int bpos = 31 - (__ffs(bits) - 1);  // index of the point within the chunk
-          bits &= bits - 1;
-          const float* sp = reinterpret_cast<const float*>(&slab[kc + (bpos >> 1)][0]) + (bpos & 1);
-          const float4 pa = make_float4(sp[0], sp[2], sp[4], sp[6]);  // sx, sy, sz, dx
-          const float4 pb = make_float4(sp[8], sp[10], 0.0f, 0.0f);   // dy, dz
-          const float r2 = residual2(rt[u], pa, pb);
-          if (MODE == 0) {
-            cnt[u] += r2 < tau2 ? 1u : 0u;
-          } else {
-            const float mm = r2 < tau2 ? r2 : tau2;  // NaN -> tau2
-            fsum[u] += static_cast<unsigned int>(FMUL(FDIV(mm, tau2), 1048576.0f));
-          }
-        }
+        if (MODE == 1) cnt[u] += __popc(m[u]);
+        score_bits<MODE>(rt[u], m[u], q4_0 + 512u * static_cast<uint32_t>(ch), q2_0 + 256u * static_cast<uint32_t>(ch), tau2,
+                         cnt[u], fsum[u]);
       }
     }
   }

@@ -2,7 +2,7 @@
 (sac_cot_b200/csrc/kernels_graph.cu, DESIGN.md "S1 exact filter").
 
 The kernel decides  P(x,y) = |RN(RN(sqrt x) - RN(sqrt y))| < tau  from
-    S = x+y;  U = S - tau2f;  Q = fma(x*y, -4, U*U);  Theta = (S*S) * 2^-19
+    S = x+y;  U = S - tau2f;  Q = fma(x*y, -4, U*U);  Theta = (U*U) * 3 * 2^-20
 and trusts sign(Q) only when |Q| > Theta and S > lo = max(4 tau2f, 2^-50).  Here the same fp32
 sequence is replayed with numpy (individually rounded fp32 ops; the single-rounding fma is
 emulated in float64, where UU - 4*XY is exact for operands this close in magnitude) on millions
@@ -26,7 +26,7 @@ def fast_filter(x, y, tau):
     UU = U * U
     XY = x * y
     Q = (UU.astype(np.float64) - 4.0 * XY.astype(np.float64)).astype(f32)  # fma: one rounding
-    T = (S * S) * f32(2.0 ** -19)
+    T = UU * f32(3.0 * 2.0 ** -20)   # re-uses the product Q needs; S > 4 tau2f gives U >= 0.75 S, so T >= 26.9u S^2
     with np.errstate(invalid="ignore"):
         sure = (np.abs(Q) > T) & (S > lo)
     return sure, Q < 0
@@ -100,3 +100,26 @@ def test_exact_ties_and_degenerate_inputs_fall_through():
         lit = literal(X.ravel(), Y.ravel(), tau)
     assert not (sure & (neg != lit)).any()
     assert not sure[np.isnan(X.ravel()) | np.isnan(Y.ravel())].any()
+
+
+@pytest.mark.parametrize("tau", [0.1, 0.6, 1e-3, 5.0])
+def test_short_lengths_just_above_the_lower_limit(tau):
+    """Theta = (U*U) * 3 * 2^-20 is smallest relative to (x+y)^2 where S is just above lo = 4 tau2f (U ~ 0.75 S): lengths of
+    a few tau, difference ~ tau.  Sure verdicts there, on values up to two ulps off, must still equal the literal
+    predicate on the exact ones."""
+    rng = np.random.default_rng(77)
+    n = 2_000_000
+    a = (rng.random(n) * 3.0 * tau).astype(np.float64)
+    eps = (rng.standard_normal(n) * 4e-7) + rng.choice([0.0, 0.0, 1e-4, -1e-4], n)
+    b = np.abs(a + rng.choice([-1.0, 1.0], n) * tau * (1.0 + eps))
+    x, y = (a * a).astype(f32), (b * b).astype(f32)
+    lit = literal(x, y, f32(tau))
+    up = lambda v: np.nextafter(v, np.where(rng.random(n) < 0.5, f32(np.inf), f32(-np.inf)).astype(f32))
+    xp, yp = up(up(x)), up(up(y))
+    for xs, ys in ((x, y), (xp, yp)):
+        sure, neg = fast_filter(xs, ys, f32(tau))
+        wrong = sure & (neg != lit)
+        assert not wrong.any(), (int(wrong.sum()), x[wrong][:4], y[wrong][:4])
+    # the regime is exercised: some of the sample lies above the limit and is decided
+    sure, _ = fast_filter(x, y, f32(tau))
+    assert sure.any() and (~sure).any()
