@@ -757,10 +757,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     const int r8 = lane & 7, rg2 = (lane >> 3) & 1, q = lane >> 4;
     long long w_empty = 0, t_sts = 0, t_fence = 0, t_arr = 0, t_begin = PROF ? clock64() : 0;
     // ---- load cursor: the group's next stage (tile lt, stage lit of it) ----
-    int lt = cid, lit = grp, lnp = 0, lnpanel = 0, lNpad = 0, rowsA = 0, rowsB = 0, lpair = -1;
-    const uint4* lbase = nullptr;  // the pair's K-panel copy
-    const uint4* lsrcA = nullptr;  // panel 0, row a0 (+ this lane's quad)
-    const uint4* lsrcB = nullptr;  // panel 0, row b0 (+ this lane's quad)
+    // Task k of this lane is row rbase + 32 k of the stage image: k < 4 are A rows, k >= 4 the B rows rbase + 32 (k - 4).
+    // Everything that depends on the tile only (this lane's two row pointers, which of its rows exist) is worked out
+    // when the tile is entered; a stage then costs two pointer offsets and eight predicated loads at constant
+    // distances.  (Before, every task re-derived its row, operand and pointer: ~170 instructions per stage, a third
+    // of an expansion warp's time by the in-kernel counters, on the warps the tensor pipe waits for.)
+    static_assert(kWarpsPerGroup == 2 && kTasksPerWarp == 8 && kCtaM == 128 && kCtaNB <= 128, "task -> row mapping");
+    const int rbase = 8 * (2 * wq + rg2) + r8;
+    int lt = cid, lit = grp, lnp = 0, lnpanel = 0, lNpad = 0, lpair = -1;
+    uint32_t strideA = 0, strideB = 0;  // uint4 units from one K panel to the next
+    bool okA = false;                   // this CTA's A rows exist (a whole row block does or does not)
+    uint32_t okB = 0;                   // bit k: B row rbase + 32 k exists
+    const uint4* lbase = nullptr;       // the pair's K-panel copy
+    const uint4* pA = nullptr;          // panel 0, this lane's first A row and quad
+    const uint4* pB = nullptr;          // panel 0, this lane's first B row and quad
     uint2 len = make_uint2(0u, 0u);
     auto enter_tile = [&](const uint2 e) {  // tile lt
       if (static_cast<int>(e.x) != lpair) {
@@ -770,17 +780,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
         lnpanel = pd->npanel;
         lnp = (lnpanel + 1) & ~1;
         lbase = reinterpret_cast<const uint4*>(panel + pd->panel_off);
+        strideB = 2u * static_cast<uint32_t>(lNpad);
+        strideA = RECT ? 2u * static_cast<uint32_t>(kRectRows) : strideB;
       }
       const int I0 = static_cast<int>(e.y >> 16) * kMmaTileM, J0 = static_cast<int>(e.y & 0xFFFFu) * kMmaTileN;
       const int a0 = I0 + kCtaM * static_cast<int>(rank), b0 = J0 + kCtaNB * static_cast<int>(rank);
       // rows past the end of the pair expand to zeros
-      rowsA = a0 < lNpad ? kCtaM : 0;
-      rowsB = max(0, min(kCtaNB, lNpad - b0));
-      lsrcA = lbase + static_cast<size_t>(a0) * 2 + q;
-      lsrcB = lbase + static_cast<size_t>(b0) * 2 + q;
+      const int rowsB = min(kCtaNB, lNpad - b0) - rbase;  // B row rbase + 32 k exists iff 32 k < rowsB
+      okB = (rowsB > 0 ? 1u : 0u) | (rowsB > 32 ? 2u : 0u) | (rowsB > 64 ? 4u : 0u) | (rowsB > 96 ? 8u : 0u);
+      pB = lbase + static_cast<size_t>(b0 + rbase) * 2 + q;
       if constexpr (RECT) {  // A rows: the compact copy of the kept nodes' records (whole row blocks, zero padded)
-        rowsA = kCtaM;
-        lsrcA = reinterpret_cast<const uint4*>(kpanel + static_cast<long long>(lpair) * kpanel_pair_words) + static_cast<size_t>(a0) * 2 + q;
+        okA = true;
+        pA = reinterpret_cast<const uint4*>(kpanel + static_cast<long long>(lpair) * kpanel_pair_words) +
+             static_cast<size_t>(a0 + rbase) * 2 + q;
+      } else {
+        okA = a0 < lNpad;
+        pA = lbase + static_cast<size_t>(a0 + rbase) * 2 + q;
       }
     };
     if (lt < total_tiles) {
@@ -799,16 +814,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) triangl
     auto load_stage = [&](uint4(&w)[kTasksPerWarp]) -> bool {
       if (lt >= total_tiles) return false;
       const bool real = lit < lnpanel;  // the padding stage of an odd panel count carries no data
-      const size_t poff = static_cast<size_t>(lit) * lNpad * 2;  // uint4 units: panel lit
-      const size_t poffA = RECT ? static_cast<size_t>(lit) * kRectRows * 2 : poff;
+      const uint4* a = pA + static_cast<size_t>(static_cast<uint32_t>(lit)) * strideA;  // panel lit
+      const uint4* b = pB + static_cast<size_t>(static_cast<uint32_t>(lit)) * strideB;
+      const bool ra = real && okA;
+      const uint32_t rb = real ? okB : 0u;
+      if (__all_sync(0xffffffffu, ra && rb == 0xFu)) {  // every row of every lane exists (all but the edge tiles)
 #pragma unroll
-      for (int k = 0; k < kTasksPerWarp; ++k) {
-        const int gr = 2 * (wq + kWarpsPerGroup * k) + rg2;  // 8-row group of this lane
-        const int r = 8 * gr + r8;
-        const bool isA = r < kCtaM;
-        const bool ok = real && gr < kGroups && (isA ? r < rowsA : r - kCtaM < rowsB);
-        const uint4* src = isA ? lsrcA + static_cast<size_t>(r) * 2 + poffA : lsrcB + static_cast<size_t>(r - kCtaM) * 2 + poff;
-        w[k] = ok ? __ldg(src) : make_uint4(0u, 0u, 0u, 0u);
+        for (int k = 0; k < 4; ++k) {  // 32 rows further = 64 uint4
+          w[k] = __ldg(a + 64 * k);
+          w[4 + k] = __ldg(b + 64 * k);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w[k] = ra ? __ldg(a + 64 * k) : make_uint4(0u, 0u, 0u, 0u);
+          w[4 + k] = ((rb >> k) & 1u) ? __ldg(b + 64 * k) : make_uint4(0u, 0u, 0u, 0u);
+        }
       }
       lit += kGroupsP;
       while (lt < total_tiles && lit >= lnp) {
