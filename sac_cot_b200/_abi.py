@@ -101,11 +101,44 @@ SYMBOLS = {
 }
 
 
+# entry points that make the library bind NCCL (dlopen("libnccl.so.2") on first use)
+_NCCL_BINDING = ("sac_cot_comm_unique_id", "sac_cot_ctx_comm_init", "sac_cot_ctx_set_comm")
+
+
+def _prefer_torch_nccl():
+    """torch ships its own libnccl.so.2 under the same soname as a system copy, and a process only ever holds ONE
+    library per soname: whichever is loaded first serves everybody.  If this library's dlopen brought in an older system
+    copy first, a later `import torch` dies on the symbols it misses (seen: system 2.27.3 against torch's 2.28.9,
+    `undefined symbol: ncclDevCommCreate`).  So a Python process that has torch installed loads torch's copy before the
+    library binds NCCL; a process without torch (or a C/C++ host) gets the system copy, or the file named by the
+    environment variable SAC_COT_NCCL_LIB."""
+    import sys
+
+    if "torch" in sys.modules:
+        return
+    try:
+        import torch  # noqa: F401
+    except Exception:  # noqa: BLE001 - no torch: the system copy is the right one
+        pass
+
+
 def bind(lib: C.CDLL) -> C.CDLL:
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
+    for name in _NCCL_BINDING:
+        raw = getattr(lib, name)
+        if getattr(raw, "_sac_cot_guarded", False):
+            continue
+
+        def guarded(*a, _raw=raw):
+            _prefer_torch_nccl()
+            return _raw(*a)
+
+        guarded._sac_cot_guarded = True
+        guarded.restype, guarded.argtypes = raw.restype, raw.argtypes  # what tests/test_library_abi.py reads
+        setattr(lib, name, guarded)
     return lib
 
 

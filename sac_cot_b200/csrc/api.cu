@@ -155,7 +155,11 @@ NcclApi* nccl_api() {
   static NcclApi api;
   static std::once_flag once;
   std::call_once(once, [] {
-    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    // SAC_COT_NCCL_LIB names the file to use (a process holds one library per soname: an application that will load
+    // another libnccl.so.2 later — torch bundles its own — should point this at that copy, or load it first)
+    const char* wanted = std::getenv("SAC_COT_NCCL_LIB");
+    for (const char* name : {wanted, "libnccl.so.2", "libnccl.so"}) {
+      if (!name || !*name) continue;
       api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
       if (api.handle) break;
     }

@@ -76,3 +76,14 @@ def test_product_sources_never_touch_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "libsaccot_oracle" not in text and "oracle/" not in text.replace("oracle/sac_cot_oracle.cpp", ""), \
                     os.path.join(dirpath, f)
+
+
+def test_nccl_binding_entry_points_load_torch_first(product_lib, monkeypatch):
+    """A process holds one libnccl.so.2: the Python binding makes sure torch's copy (when torch is installed) is the one
+    loaded before the library's own dlopen (see _abi._prefer_torch_nccl)."""
+    calls = []
+    monkeypatch.setattr(_abi, "_prefer_torch_nccl", lambda: calls.append(1))
+    for name in _abi._NCCL_BINDING:
+        assert getattr(getattr(product_lib, name), "_sac_cot_guarded", False), name
+    assert product_lib.sac_cot_ctx_set_comm(None, None, 0, 1) == _abi.E_NULL   # no ctx: refused before NCCL is touched
+    assert calls == [1]
