@@ -329,6 +329,28 @@ def test_graph_near_threshold_scaled_cloud(gpu, oracle):
         assert 0 < E < N * (N - 1) // 2
 
 
+def test_graph_short_lengths_around_the_filters_lower_limit(gpu, oracle):
+    # The filter's threshold Theta = U*U * 48u (U = x + y - tau^2) is smallest relative to (x + y)^2 where x + y is just
+    # above its lower limit 4 tau^2, i.e. for pairs a few tau apart in both clouds.  Tight clusters (radius ~ 1.5 tau,
+    # independent offsets in src and dst) put most intra-cluster pairs there, with |ls - ld| on both sides of tau; pairs
+    # of different clusters are ordinary.  The same cloud scaled so that tau sits at 2^-9 and 2^7 as well.
+    rng = np.random.default_rng(21)
+    N, C = 1536, 24
+    for tau in (0.1, 2.0 ** -9, 128.0):
+        centres = (rng.random((C, 3)) * 40 - 20) * tau
+        which = rng.integers(0, C, N)
+        src = (centres[which] + (rng.random((N, 3)) * 3 - 1.5) * tau).astype(np.float32)
+        dst = (centres[which] + (rng.random((N, 3)) * 3 - 1.5) * tau).astype(np.float32)
+        E = _adj_parity(gpu, oracle, src, dst, float(np.float32(tau)))
+        assert 0 < E < N * (N - 1) // 2
+        # a cloud only 4 tau wide and dst = rotated 1.7 x src: |ld - ls| = 0.7 ls, the decision boundary lies at
+        # ls = 1.43 tau, where x + y = 7.9 tau^2
+        src = ((rng.random((N, 3)) * 4 - 2) * tau).astype(np.float32)
+        dst = (1.7 * src.astype(np.float64) @ synth.make_pair(8, 0.5, 1).R_gt.T).astype(np.float32)
+        E = _adj_parity(gpu, oracle, src, dst, float(np.float32(tau)))
+        assert 0 < E < N * (N - 1) // 2
+
+
 def test_graph_exact_ties_on_a_lattice(gpu, oracle):
     # collinear integer lattice, dst stretched by 1 + 2^-6: ld - ls = |i-j| * 2^-6 exactly, so with
     # tau = k * 2^-6 every pair at lattice distance k is an exact tie (strict '<' => no edge)
