@@ -123,6 +123,8 @@ class ClockSampler:
         self.t_end = time.time()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
+            self.f.close()
+            os.unlink(self.f.name)
             return out
         self.p.terminate()
         try:
